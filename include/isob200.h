@@ -1,0 +1,91 @@
+/* isob200.h -- C ABI of libisob200.so, the B200 (sm_100a) implementation of the iso-points hot path.
+ *
+ * Every entry point
+ *   - takes raw DEVICE pointers + sizes + a cudaStream_t (passed as void*), no torch types;
+ *   - never allocates: outputs and workspaces are caller-owned (a *_ws_bytes() query precedes
+ *     each call that needs scratch);
+ *   - is stream-ordered on the given stream and returns an int status: 0 = ok, 1 = invalid
+ *     argument, 2 = CUDA error, 3 = workspace too small; isob200_last_error() returns the
+ *     message of the last failure on the calling thread (the Python layer raises RuntimeError
+ *     with it, as the reference's TORCH_CHECK / AT_CUDA_CHECK would).
+ * Each declaration cites the reference interface it replaces (paths relative to the
+ * yifita/iso-points tree).  The reference-side bindings are shown in INTEGRATION.md.
+ */
+#ifndef ISOB200_H_
+#define ISOB200_H_
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- library / error channel -------------------------------------------------------- */
+const char* isob200_last_error(void);
+int isob200_abi_version(void);
+int isob200_compiled_arch(void); /* 1000 = sm_100a */
+
+/* ---- exclusive scan: prefix_sum.prefix_sum_cuda(cnt, num_cells, off)
+ *      external/FRNN/external/prefix_sum/prefix_sum.cu:74-87 (prefix_sum.h:18-20);
+ *      batched over `rows`, on the caller's stream, no cudaMalloc --------------------- */
+size_t isob200_exclusive_scan_ws_bytes(int n, int rows);
+int isob200_exclusive_scan_i32(const int* in, int* out, int n, int rows, long long in_stride,
+                               long long out_stride, void* ws, size_t ws_bytes, void* stream);
+
+/* ---- FRNN grid: external/FRNN/frnn/frnn.py:55-71 (grid params host loop),
+ *      frnn._C.insert_points_cuda  (csrc/grid/grid.cu:135-184, ext.cpp:10),
+ *      frnn._C.counting_sort_cuda  (csrc/grid/counting_sort.cu:73-125),
+ *      and a fused deterministic build replacing insert + prefix_sum + counting_sort -- */
+int isob200_frnn_grid_params(const float* points, const int64_t* lengths, const float* rs, int N,
+                             int P, int D, double radius_cell_ratio, float* params, int* g_max,
+                             void* ws, size_t ws_bytes, void* stream);
+int isob200_frnn_insert_points(const float* points, const int64_t* lengths, const float* params,
+                               int* grid_cnt, int* grid_cell, int* grid_idx, int N, int P, int D,
+                               int G, void* stream);
+int isob200_frnn_counting_sort(const float* points, const int64_t* lengths, const int* grid_cell,
+                               const int* grid_idx, const int* grid_off, float* sorted_points,
+                               int* sorted_idxs, int N, int P, int D, int G, void* stream);
+size_t isob200_frnn_build_ws_bytes(int N, int P, int G);
+int isob200_frnn_build(const float* points, const int64_t* lengths, const float* params, int N, int P,
+                       int D, int G, int* cell_off, float* sorted_points, int* sorted_idxs, void* ws,
+                       size_t ws_bytes, void* stream);
+
+/* ---- FRNN query: frnn._C.find_nbrs_cuda (csrc/grid/grid.cu:384-440),
+ *      frnn.frnn_gather (frnn.py:304-352) and its autograd, frnn._C.frnn_backward_cuda
+ *      (csrc/backward/backward.cu:76-147) ------------------------------------------------ */
+int isob200_frnn_find_nbrs(const float* q_points, const int* q_order, const int64_t* lengths1,
+                           const int64_t* lengths2, const float* sorted_points2, const int* cell_off2,
+                           const int* sorted_idxs2, const float* params, const float* rs, int N,
+                           int P1, int P2, int D, int G, int K, float* dists, void* idxs,
+                           int idx_is_i64, int group_width, void* stream);
+int isob200_frnn_gather(const float* x, const void* idxs, int idx_is_i64, int N, int M, int L, int K,
+                        int U, float* out, void* stream);
+int isob200_frnn_gather_backward(const float* grad_out, const void* idxs, int idx_is_i64, int N, int M,
+                                 int L, int K, int U, float* grad_x, void* stream);
+int isob200_frnn_backward(const float* points1, const float* points2, const int64_t* lengths1,
+                          const int64_t* lengths2, const int64_t* idxs, const float* grad_dists, int N,
+                          int P1, int P2, int D, int K, float* grad_points1, float* grad_points2,
+                          void* stream);
+
+/* ---- level-set projection: UniformProjection._project_points
+ *      (DSS/models/levelset_sampling.py:290-351); one call per Newton iteration ---------- */
+size_t isob200_project_step_ws_bytes(int A);
+int isob200_project_step(float* points, float* normals, unsigned char* not_converged,
+                         const int* act_in, int A, const float* sdf, const float* grad, float tol,
+                         float max_step, int do_update, int* act_out, int* count_out, void* ws,
+                         size_t ws_bytes, void* stream);
+int isob200_gather_rows3(const float* src, const int* idx, int A, float* dst, void* stream);
+int isob200_project_sphere(float* points, float* normals, unsigned char* valid, long long M,
+                           float radius, float tol, float max_step, int max_iters, void* stream);
+
+/* ---- uniform resampling: UniformProjection.resample, one sample_iter
+ *      (DSS/models/levelset_sampling.py:259, 268-284) ------------------------------------ */
+int isob200_resample_step(const float* points, const float* normals, const void* idxs, int idx_is_i64,
+                          int idx_stride, int k_offset, const float* inv_sigma, int N, int P, int K,
+                          float* out, void* stream);
+int isob200_normalize_rows3(const float* x, long long M, float eps, float* out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ISOB200_H_ */

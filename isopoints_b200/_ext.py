@@ -1,0 +1,94 @@
+"""ctypes loader for libisob200.so -- the C ABI declared in include/isob200.h.
+
+There is deliberately NO fallback: if the shared library is missing or a kernel launch fails,
+the call raises.  PyTorch is used only for device memory, streams and autograd plumbing.
+"""
+import ctypes
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libisob200.so")
+
+_vp = ctypes.c_void_p
+_i = ctypes.c_int
+_ll = ctypes.c_longlong
+_sz = ctypes.c_size_t
+_f = ctypes.c_float
+_d = ctypes.c_double
+
+# name -> (restype, argtypes); must match include/isob200.h (tests/test_abi.py checks the export list)
+_PROTOS = {
+    "isob200_last_error": (ctypes.c_char_p, []),
+    "isob200_abi_version": (_i, []),
+    "isob200_compiled_arch": (_i, []),
+    "isob200_exclusive_scan_ws_bytes": (_sz, [_i, _i]),
+    "isob200_exclusive_scan_i32": (_i, [_vp, _vp, _i, _i, _ll, _ll, _vp, _sz, _vp]),
+    "isob200_frnn_grid_params": (_i, [_vp, _vp, _vp, _i, _i, _i, _d, _vp, _vp, _vp, _sz, _vp]),
+    "isob200_frnn_insert_points": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
+    "isob200_frnn_counting_sort": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
+    "isob200_frnn_build_ws_bytes": (_sz, [_i, _i, _i]),
+    "isob200_frnn_build": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "isob200_frnn_find_nbrs": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i,
+                                    _vp, _vp, _i, _i, _vp]),
+    "isob200_frnn_gather": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp]),
+    "isob200_frnn_gather_backward": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp]),
+    "isob200_frnn_backward": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp]),
+    "isob200_project_step_ws_bytes": (_sz, [_i]),
+    "isob200_project_step": (_i, [_vp, _vp, _vp, _vp, _i, _vp, _vp, _f, _f, _i, _vp, _vp, _vp, _sz, _vp]),
+    "isob200_gather_rows3": (_i, [_vp, _vp, _i, _vp, _vp]),
+    "isob200_project_sphere": (_i, [_vp, _vp, _vp, _ll, _f, _f, _f, _i, _vp]),
+    "isob200_resample_step": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp, _i, _i, _i, _vp, _vp]),
+    "isob200_normalize_rows3": (_i, [_vp, _ll, _f, _vp, _vp]),
+}
+
+_LIB = None
+
+
+def exported_symbols():
+    return sorted(_PROTOS)
+
+
+def lib():
+    """Load (once) and return the ctypes handle; raises ImportError if the library is absent."""
+    global _LIB
+    if _LIB is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(
+                "isopoints_b200: %s not found -- build it with `python -m isopoints_b200.build` "
+                "(there is no CPU/PyTorch fallback for the CUDA path)" % LIB_PATH)
+        h = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in _PROTOS.items():
+            fn = getattr(h, name)  # AttributeError if the .so is stale
+            fn.restype = res
+            fn.argtypes = args
+        _LIB = h
+    return _LIB
+
+
+def check(rc):
+    if rc != 0:
+        msg = lib().isob200_last_error()
+        raise RuntimeError("isob200: " + (msg.decode() if msg else "error %d" % rc))
+
+
+def ptr(t):
+    """Raw device pointer of a tensor (None -> NULL)."""
+    if t is None:
+        return None
+    return t.data_ptr()
+
+
+def stream(device=None):
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+def require_cuda(*tensors):
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise TypeError("for now only cuda version is supported")
+
+
+def workspace(nbytes, device):
+    return torch.empty((max(int(nbytes), 1),), dtype=torch.uint8, device=device)

@@ -1,0 +1,316 @@
+// FRNN fixed-radius K-nearest query, gather and backward for sm_100a.
+//
+// Replaces external/FRNN/frnn/csrc/grid/grid.cu:186-440 (FindNbrs{2,3}DKernel<K>: one thread
+// per query, K-entry MinK in local memory, fixed <<<256,256>>> grid), frnn.py:304-352
+// (frnn_gather as an expand+gather+mask chain) and backward/backward.cu:8-147.
+//
+// Query kernel design (B200): a GROUP of GW lanes (GW = 8/16/32 >= K) cooperates on one query.
+//  * the candidate cells of a query form (2c+1)^(D-1) runs that are CONTIGUOUS in the sorted
+//    point array (z is the fastest cell index), so the group streams each run with coalesced
+//    loads, GW candidates per step -- no per-thread divergent pointer chasing;
+//  * the running K-best list lives one entry per lane, kept sorted by (dist, index); an
+//    insertion is a ballot + shuffle-up, no local memory, no bubble sort at the end;
+//  * results are written straight to the caller's (N,P1,K) tensors (int64 or int32 indices),
+//    including the -1 padding, so no fill pass is needed.
+// Distances use the reference's exact fp32 expression as nvcc contracts it (SASS of grid.cu:
+// FMUL dx*dx; FFMA dy; FFMA dz), spelled with intrinsics so it can never be re-contracted.
+// Equal distances are ordered by smaller original index (the reference keeps whichever it saw
+// first, which depends on its atomic insertion order -- mink.cuh:64).
+#include "common.cuh"
+#include <float.h>
+#include <limits.h>
+
+namespace isob200 {
+
+template <int D>
+__device__ __forceinline__ float sqdist_ref(const float* __restrict__ p2, const float* q) {
+  const float dx = __fsub_rn(p2[0], q[0]);
+  const float dy = __fsub_rn(p2[1], q[1]);
+  float s = __fmaf_rn(dy, dy, __fmul_rn(dx, dx));
+  if (D == 3) {
+    const float dz = __fsub_rn(p2[2], q[2]);
+    s = __fmaf_rn(dz, dz, s);
+  }
+  return s;
+}
+
+template <int D, int GW, typename IdxT>
+__global__ void __launch_bounds__(256)
+frnn_query_kernel(const float* __restrict__ q_points,     // (N,P1,D) in processing order
+                  const int* __restrict__ q_order,        // (N,P1) processing slot -> original row, or null
+                  const int64_t* __restrict__ lengths1,   // (N,) or null
+                  const int64_t* __restrict__ lengths2,   // (N,) or null
+                  const float* __restrict__ sorted_points2,  // (N,P2,D)
+                  const int* __restrict__ cell_off2,         // (N,G)
+                  const int* __restrict__ sorted_idxs2,      // (N,P2)
+                  const float* __restrict__ params, const float* __restrict__ rs, int N, int P1,
+                  int P2, int G, int K, float* __restrict__ dists, IdxT* __restrict__ idxs) {
+  constexpr int PS = (D == 3) ? ISO_G3_SIZE : ISO_G2_SIZE;
+  constexpr int GROUPS = 256 / GW;
+  const int lane = threadIdx.x & 31;
+  const int gl = lane & (GW - 1);                       // lane within group
+  const unsigned gshift = lane & ~(GW - 1);             // first warp lane of this group
+  const unsigned gmask = (GW == 32) ? 0xffffffffu : (((1u << GW) - 1u) << gshift);
+  const long long total = (long long)N * P1;
+  const long long ngroups = (long long)gridDim.x * GROUPS;
+
+  for (long long item = (long long)blockIdx.x * GROUPS + threadIdx.x / GW; item < total;
+       item += ngroups) {
+    const int n = (int)(item / P1);
+    const int s = (int)(item - (long long)n * P1);
+    const int len1 = lengths1 ? (int)min((long long)lengths1[n], (long long)P1) : P1;
+    if (s >= len1) {  // padded row: reference leaves the -1 fill (grid.cu:422-423)
+      if (gl < K) {
+        const size_t o = ((size_t)n * P1 + s) * K + gl;
+        dists[o] = -1.f;
+        idxs[o] = (IdxT)-1;
+      }
+      continue;
+    }
+    const int row = q_order ? q_order[(size_t)n * P1 + s] : s;
+    const int len2 = lengths2 ? (int)min((long long)lengths2[n], (long long)P2) : P2;
+    const float* prm = params + (size_t)n * PS;
+    const float r = rs[n];
+    const float r2 = __fmul_rn(r, r);
+    float q[D];
+#pragma unroll
+    for (int d = 0; d < D; ++d) q[d] = q_points[((size_t)n * P1 + s) * D + d];
+
+    // candidate cell range, grid.cu:305-316 (fp32: (p - min -/+ r) * delta, floor)
+    int lo[D], hi[D], res[D];
+#pragma unroll
+    for (int d = 0; d < D; ++d) {
+      const float rel = __fsub_rn(q[d], prm[d]);
+      const float delta = prm[D];
+      res[d] = (int)prm[D + 1 + d];
+      lo[d] = max(__float2int_rd(__fmul_rn(__fsub_rn(rel, r), delta)), 0);
+      hi[d] = min(__float2int_rd(__fmul_rn(__fadd_rn(rel, r), delta)), res[d] - 1);
+    }
+    const int grid_total = (int)prm[2 * D + 1];
+
+    float best_d = FLT_MAX;   // lane gl holds the gl-th best (dist, idx), ascending
+    int best_i = INT_MAX;
+    float kth_d = FLT_MAX;    // current K-th best distance (pruning bound), group-uniform
+
+    const float* pts2 = sorted_points2 + (size_t)n * P2 * D;
+    const int* off2 = cell_off2 + (size_t)n * G;
+    const int* sid2 = sorted_idxs2 + (size_t)n * P2;
+
+    bool nonempty = true;
+#pragma unroll
+    for (int d = 0; d < D; ++d) nonempty = nonempty && (lo[d] <= hi[d]);
+    if (nonempty) {
+      const int ny = (D == 3) ? (hi[1] - lo[1] + 1) : 1;
+      const int nruns = (hi[0] - lo[0] + 1) * ny;  // <= 0 when empty
+      for (int run = 0; run < nruns; ++run) {
+        int c0, c1;
+        if (D == 3) {
+          const int x = lo[0] + run / ny, y = lo[1] + run % ny;
+          c0 = (x * res[1] + y) * res[2] + lo[2];
+          c1 = (x * res[1] + y) * res[2] + hi[2];
+        } else {
+          const int x = lo[0] + run;
+          c0 = x * res[1] + lo[1];
+          c1 = x * res[1] + hi[1];
+        }
+        const int start = off2[c0];
+        const int end = (c1 + 1 == grid_total) ? len2 : off2[c1 + 1];
+        for (int base = start; base < end; base += GW) {
+          const int j = base + gl;
+          const bool valid = j < end;
+          float d = FLT_MAX;
+          if (valid) d = sqdist_ref<D>(pts2 + (size_t)j * D, q);
+          const bool cand = valid && (d <= r2) && (d <= kth_d);
+          unsigned m = __ballot_sync(gmask, cand) & gmask;
+          if (m == 0) continue;
+          int ci_mine = cand ? sid2[j] : INT_MAX;
+          while (m) {
+            const int src = __ffs(m) - 1;
+            m &= m - 1;
+            const float cd = __shfl_sync(gmask, d, src);
+            const int ci = __shfl_sync(gmask, ci_mine, src);
+            const bool less = (best_d < cd) || (best_d == cd && best_i < ci);
+            const int pos = __popc(__ballot_sync(gmask, less) & gmask);
+            const float up_d = __shfl_up_sync(gmask, best_d, 1, GW);
+            const int up_i = __shfl_up_sync(gmask, best_i, 1, GW);
+            if (pos < K) {
+              if (gl > pos) { best_d = up_d; best_i = up_i; }
+              else if (gl == pos) { best_d = cd; best_i = ci; }
+            }
+          }
+          kth_d = __shfl_sync(gmask, best_d, (int)gshift + K - 1);
+        }
+      }
+    }
+    if (gl < K) {
+      const size_t o = ((size_t)n * P1 + row) * K + gl;
+      const bool found = best_i != INT_MAX;
+      dists[o] = found ? best_d : -1.f;
+      idxs[o] = found ? (IdxT)best_i : (IdxT)-1;
+    }
+  }
+}
+
+// x (N,M,U), idxs (N,L,K) -> out (N,L,K,U); 0 where idx < 0   (frnn.py:304-352)
+template <typename IdxT>
+__global__ void __launch_bounds__(256)
+frnn_gather_kernel(const float* __restrict__ x, const IdxT* __restrict__ idxs, int N, int M, int L,
+                   int K, int U, float* __restrict__ out) {
+  const long long total = (long long)N * L * K * U;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int u = (int)(i % U);
+    const long long e = i / U;  // (n,l,k) flat
+    const int n = (int)(e / ((long long)L * K));
+    const long long j = (long long)idxs[e];
+    out[i] = (j >= 0) ? x[((size_t)n * M + j) * U + u] : 0.f;
+  }
+}
+
+// grad_out (N,L,K,U) scattered back into grad_x (N,M,U) (+=), skipping idx < 0
+template <typename IdxT>
+__global__ void __launch_bounds__(256)
+frnn_gather_bwd_kernel(const float* __restrict__ grad_out, const IdxT* __restrict__ idxs, int N,
+                       int M, int L, int K, int U, float* __restrict__ grad_x) {
+  const long long total = (long long)N * L * K * U;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int u = (int)(i % U);
+    const long long e = i / U;
+    const int n = (int)(e / ((long long)L * K));
+    const long long j = (long long)idxs[e];
+    if (j >= 0) atomicAdd(&grad_x[((size_t)n * M + j) * U + u], grad_out[i]);
+  }
+}
+
+// d dists / d points (backward.cu:8-74): one warp-coalesced pass over (n,p1,k); the p1 side is
+// reduced over k in registers before a single atomic per coordinate.
+template <int D>
+__global__ void __launch_bounds__(256)
+frnn_backward_kernel(const float* __restrict__ points1, const float* __restrict__ points2,
+                     const int64_t* __restrict__ lengths1, const int64_t* __restrict__ lengths2,
+                     const int64_t* __restrict__ idxs, const float* __restrict__ grad_dists, int N,
+                     int P1, int P2, int K, float* __restrict__ grad_points1,
+                     float* __restrict__ grad_points2) {
+  const long long total = (long long)N * P1;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int n = (int)(i / P1), p1 = (int)(i % P1);
+    if (p1 >= lengths1[n]) continue;
+    const long long num2 = lengths2[n];
+    float a[D], g1[D];
+#pragma unroll
+    for (int d = 0; d < D; ++d) { a[d] = points1[i * D + d]; g1[d] = 0.f; }
+    for (int k = 0; k < K && k < num2; ++k) {
+      const long long j = idxs[i * K + k];
+      if (j < 0) continue;
+      const float g = grad_dists[i * K + k];
+#pragma unroll
+      for (int d = 0; d < D; ++d) {
+        const float diff = 2.0f * g * (a[d] - points2[((size_t)n * P2 + j) * D + d]);
+        g1[d] += diff;
+        atomicAdd(&grad_points2[((size_t)n * P2 + j) * D + d], -diff);
+      }
+    }
+#pragma unroll
+    for (int d = 0; d < D; ++d) atomicAdd(&grad_points1[i * D + d], g1[d]);
+  }
+}
+
+template <int D, typename IdxT>
+static int launch_query(int gw, int blocks, cudaStream_t st, const float* qp, const int* qo,
+                        const int64_t* l1, const int64_t* l2, const float* sp2, const int* off2,
+                        const int* sid2, const float* params, const float* rs, int N, int P1, int P2,
+                        int G, int K, float* dists, IdxT* idxs) {
+  if (gw == 8)
+    frnn_query_kernel<D, 8, IdxT><<<blocks, 256, 0, st>>>(qp, qo, l1, l2, sp2, off2, sid2, params, rs, N, P1, P2, G, K, dists, idxs);
+  else if (gw == 16)
+    frnn_query_kernel<D, 16, IdxT><<<blocks, 256, 0, st>>>(qp, qo, l1, l2, sp2, off2, sid2, params, rs, N, P1, P2, G, K, dists, idxs);
+  else
+    frnn_query_kernel<D, 32, IdxT><<<blocks, 256, 0, st>>>(qp, qo, l1, l2, sp2, off2, sid2, params, rs, N, P1, P2, G, K, dists, idxs);
+  ISO_CHECK_LAUNCH("frnn_query_kernel");
+  return ISOB200_OK;
+}
+
+}  // namespace isob200
+
+using namespace isob200;
+
+extern "C" {
+
+// == frnn._C.find_nbrs_cuda (grid.cu:384-440), minus the allocation: dists (N,P1,K) f32 and
+// idxs (N,P1,K) are caller tensors and are fully written (incl. -1 padding).
+//   q_points : query coordinates in processing order (pass the cell-sorted copy for locality)
+//   q_order  : processing slot -> original row (sorted_points1_idxs), or NULL for identity
+//   idx_is_i64: 1 -> idxs is int64 (reference API), 0 -> int32 (internal fused consumers)
+//   group_width: 0 = auto (smallest of 8/16/32 that is >= K)
+int isob200_frnn_find_nbrs(const float* q_points, const int* q_order, const int64_t* lengths1,
+                           const int64_t* lengths2, const float* sorted_points2, const int* cell_off2,
+                           const int* sorted_idxs2, const float* params, const float* rs, int N,
+                           int P1, int P2, int D, int G, int K, float* dists, void* idxs,
+                           int idx_is_i64, int group_width, void* stream_) {
+  cudaStream_t st = (cudaStream_t)stream_;
+  ISO_CHECK_ARG(D == 2 || D == 3, "for now only 2D and 3D are supported");
+  ISO_CHECK_ARG(K >= 1 && K <= 32, "Invalid range: K=%d must be in [1, 32]", K);
+  ISO_CHECK_ARG(N >= 0 && P1 >= 0 && P2 >= 0 && G > 0, "find_nbrs: bad sizes");
+  if ((long long)N * P1 == 0) return ISOB200_OK;
+  ISO_CHECK_ARG(q_points && sorted_points2 && cell_off2 && sorted_idxs2 && params && rs && dists && idxs,
+                "find_nbrs: null pointer");
+  int gw = group_width;
+  if (gw == 0) gw = (K <= 8) ? 8 : (K <= 16 ? 16 : 32);
+  ISO_CHECK_ARG((gw == 8 || gw == 16 || gw == 32) && gw >= K, "find_nbrs: group_width %d invalid for K=%d", gw, K);
+  const long long items = (long long)N * P1;
+  const int groups = 256 / gw;
+  long long need = (items + groups - 1) / groups;
+  const long long cap = (long long)kNumSMs * 8 * 16;  // 8 resident CTAs/SM, 16 waves max
+  const int blocks = (int)(need < cap ? need : cap);
+#define Q(DD, T) launch_query<DD, T>(gw, blocks, st, q_points, q_order, lengths1, lengths2, sorted_points2, cell_off2, sorted_idxs2, params, rs, N, P1, P2, G, K, dists, (T*)idxs)
+  if (D == 3) return idx_is_i64 ? Q(3, int64_t) : Q(3, int);
+  return idx_is_i64 ? Q(2, int64_t) : Q(2, int);
+#undef Q
+}
+
+int isob200_frnn_gather(const float* x, const void* idxs, int idx_is_i64, int N, int M, int L, int K,
+                        int U, float* out, void* stream_) {
+  cudaStream_t st = (cudaStream_t)stream_;
+  const long long total = (long long)N * L * K * U;
+  if (total == 0) return ISOB200_OK;
+  ISO_CHECK_ARG(x && idxs && out, "frnn_gather: null pointer");
+  const int g = grid_for(total, 256, 8);
+  if (idx_is_i64) frnn_gather_kernel<int64_t><<<g, 256, 0, st>>>(x, (const int64_t*)idxs, N, M, L, K, U, out);
+  else frnn_gather_kernel<int><<<g, 256, 0, st>>>(x, (const int*)idxs, N, M, L, K, U, out);
+  ISO_CHECK_LAUNCH("frnn_gather_kernel");
+  return ISOB200_OK;
+}
+
+int isob200_frnn_gather_backward(const float* grad_out, const void* idxs, int idx_is_i64, int N, int M,
+                                 int L, int K, int U, float* grad_x, void* stream_) {
+  cudaStream_t st = (cudaStream_t)stream_;
+  const long long total = (long long)N * L * K * U;
+  if (total == 0) return ISOB200_OK;
+  ISO_CHECK_ARG(grad_out && idxs && grad_x, "frnn_gather_backward: null pointer");
+  const int g = grid_for(total, 256, 8);
+  if (idx_is_i64) frnn_gather_bwd_kernel<int64_t><<<g, 256, 0, st>>>(grad_out, (const int64_t*)idxs, N, M, L, K, U, grad_x);
+  else frnn_gather_bwd_kernel<int><<<g, 256, 0, st>>>(grad_out, (const int*)idxs, N, M, L, K, U, grad_x);
+  ISO_CHECK_LAUNCH("frnn_gather_bwd_kernel");
+  return ISOB200_OK;
+}
+
+// == frnn._C.frnn_backward_cuda (backward.cu:76-147); grad_points{1,2} must be zero-initialised.
+int isob200_frnn_backward(const float* points1, const float* points2, const int64_t* lengths1,
+                          const int64_t* lengths2, const int64_t* idxs, const float* grad_dists, int N,
+                          int P1, int P2, int D, int K, float* grad_points1, float* grad_points2,
+                          void* stream_) {
+  cudaStream_t st = (cudaStream_t)stream_;
+  ISO_CHECK_ARG(D == 2 || D == 3, "for now only 2D and 3D are supported");
+  if ((long long)N * P1 * K == 0) return ISOB200_OK;
+  ISO_CHECK_ARG(points1 && points2 && lengths1 && lengths2 && idxs && grad_dists && grad_points1 && grad_points2,
+                "frnn_backward: null pointer");
+  const int g = grid_for((long long)N * P1, 256, 8);
+  if (D == 3) frnn_backward_kernel<3><<<g, 256, 0, st>>>(points1, points2, lengths1, lengths2, idxs, grad_dists, N, P1, P2, K, grad_points1, grad_points2);
+  else frnn_backward_kernel<2><<<g, 256, 0, st>>>(points1, points2, lengths1, lengths2, idxs, grad_dists, N, P1, P2, K, grad_points1, grad_points2);
+  ISO_CHECK_LAUNCH("frnn_backward_kernel");
+  return ISOB200_OK;
+}
+
+}  // extern "C"

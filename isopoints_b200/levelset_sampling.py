@@ -1,0 +1,364 @@
+"""Iso-point projection / resampling operators on libisob200.so.
+
+Mirrors the operator surface of DSS/models/levelset_sampling.py (``LevelSetProjection``,
+``UniformProjection``, ``EdgeAwareProjection``, ``sample_uniform_iso_points``,
+``ProjectionResult``): same constructor arguments, method names, argument meaning (including the
+``x or default`` idiom, :304-305, :377-378), return containers and early-exit behaviour, so the
+reference's callers (combined_modeling.py:449, implicit_modeling.py:156, trainer.py:227) can
+switch imports and run unchanged.
+
+Everything between two SDF evaluations runs in hand-written sm_100a kernels:
+  * one fused Newton-step + in-order compaction kernel per iteration (csrc/project.cu)
+    instead of ~15 boolean-mask / elementwise PyTorch kernels with 2 host syncs;
+  * one resample kernel per sample_iter (csrc/resample.cu) instead of two (N,P,K,3)
+    ``frnn_gather`` materialisations + ~20 elementwise kernels;
+  * the FRNN grid build / query kernels (csrc/frnn_*.cu).
+The SDF itself stays the caller's opaque ``nn.Module`` (evaluated through autograd exactly like
+levelset_sampling.py:142-170).  There is no CPU / PyTorch fallback for the kernels.
+"""
+from collections import namedtuple
+import math
+from typing import Callable, Optional, Tuple, Union
+
+import torch
+import torch.autograd as autograd
+import torch.nn.functional as F
+
+from . import _ext
+from . import frnn
+from .structures import (convert_pointclouds_to_tensor, is_pointclouds, packed_to_padded,
+                         padded_to_packed_idx, reduce_mask_padded,
+                         num_points_2_cloud_to_packed_first_idx)
+
+ProjectionResult = namedtuple('ProjectionResult', ('points', 'normals', 'mask'))
+_KNN = namedtuple("KNN", "dists idx knn")  # pytorch3d.ops.knn._KNN
+
+
+def _filter_projection_result(result: ProjectionResult) -> ProjectionResult:
+    """levelset_sampling.py:59-65."""
+    points, normals, mask = result
+    points = reduce_mask_padded(points, mask)
+    normals = reduce_mask_padded(normals, mask)
+    mask = reduce_mask_padded(mask, mask)
+    return ProjectionResult(points, normals, mask)
+
+
+class LevelSetProjection(object):
+    """levelset_sampling.py:67-76."""
+
+    def __init__(self, proj_max_iters=10, proj_tolerance=5.0e-5, max_points_per_pass=120000):
+        self.proj_max_iters = proj_max_iters
+        self.proj_tolerance = proj_tolerance
+        self.max_points_per_pass = max_points_per_pass
+
+    def project_points(self, points_init, network, latent, levelset):
+        raise NotImplementedError
+
+
+class UniformProjection(LevelSetProjection):
+    """Project points onto the zero level set and spread them uniformly (levelset_sampling.py:79-439)."""
+
+    def __init__(self, proj_max_iters=10, proj_tolerance=5e-5, max_points_per_pass=120000,
+                 sample_iters=1, knn_k=8, resampling_clip=0.02, **kwargs):
+        super().__init__(proj_max_iters=proj_max_iters, proj_tolerance=proj_tolerance,
+                         max_points_per_pass=max_points_per_pass)
+        self.knn_k = knn_k
+        self.sample_iters = sample_iters
+        self.resampling_clip = resampling_clip
+        self._knn_idx = None
+        self._knn_dists = None
+        self._knn_nn_cache = None
+        self._knn_src = None
+
+    # `_knn_nn` is only materialised if somebody reads it (the resample kernel gathers in registers)
+    @property
+    def _knn_nn(self):
+        if self._knn_nn_cache is None and self._knn_idx is not None and self._knn_src is not None:
+            self._knn_nn_cache = frnn.frnn_gather(self._knn_src, self._knn_idx)
+        return self._knn_nn_cache
+
+    def _create_tree(self, points_padded: torch.Tensor, refresh_tree=True, num_points_per_cloud=None):
+        """levelset_sampling.py:110-140: FRNN with K = knn_k + 1, r = sqrt(diag / n) * knn_k; the
+        first column is dropped as "self"."""
+        if not refresh_tree and getattr(self, '_knn_idx', None) is not None:
+            return self._knn_idx
+        assert (points_padded.ndim == 3)
+        if num_points_per_cloud is None:
+            num_points_per_cloud = torch.tensor([points_padded.shape[1]] * points_padded.shape[0],
+                                                device=points_padded.device, dtype=torch.long)
+        diag = (points_padded.max(dim=1).values - points_padded.min(dim=1).values).norm(dim=-1)
+        search_radius = torch.sqrt(diag / num_points_per_cloud.float()) * self.knn_k
+        dists, idxs, _, grid = frnn.frnn_grid_points(
+            points_padded, points_padded, num_points_per_cloud, num_points_per_cloud,
+            K=self.knn_k + 1, r=search_radius, grid=None, return_nn=False)
+        self._knn_gather = frnn.frnn_gather
+        self._knn_full_idx = idxs
+        self._knn_idx = idxs[..., 1:]
+        self._knn_dists = dists[..., 1:]
+        self._knn_src = points_padded
+        self._knn_nn_cache = None
+        self.knn_gather = frnn.frnn_gather
+        return self._knn_idx
+
+    def _compute_sdf_and_grad(self, points, model, latent=None, **forward_kwargs) -> Tuple[torch.Tensor]:
+        """Chunked SDF value + input gradient through autograd (levelset_sampling.py:142-170)."""
+        shp = points.shape
+        points_packed = points.reshape(-1, 3)
+        grad_packed = []
+        eval_packed = []
+        with autograd.no_grad():
+            model.eval()
+            for sub_points in torch.split(points_packed, self.max_points_per_pass, dim=0):
+                with autograd.enable_grad():
+                    net_input = sub_points.detach().requires_grad_(True)
+                    network_eval = model.forward(net_input, **forward_kwargs).sdf
+                    input_grad = autograd.grad([network_eval], [net_input], torch.ones_like(network_eval),
+                                               retain_graph=False)[0]
+                grad_packed.append(input_grad)
+                eval_packed.append(network_eval.detach())
+            if len(grad_packed) == 1:
+                grad_packed, eval_packed = grad_packed[0], eval_packed[0]
+            else:
+                grad_packed = torch.cat(grad_packed, dim=0)
+                eval_packed = torch.cat(eval_packed, dim=0)
+            grad_packed = grad_packed.view(shp)
+            eval_packed = eval_packed.view(shp[:-1])
+        return eval_packed, grad_packed
+
+    # ------------------------------------------------------------------------------------
+    def _project_points(self, model: Callable, points: torch.Tensor, num_points: torch.Tensor,
+                        proj_max_iters: int = None, proj_tolerance: float = None,
+                        **forward_kwargs) -> ProjectionResult:
+        """Newton projection of the live rows of ``points`` (B,P,3) (levelset_sampling.py:290-351).
+
+        Returns padded points (B,Pmax,3), the last SDF gradient as normals (B,Pmax,3) and the
+        converged mask (B,Pmax) bool.  Non-converged points keep their last position.
+        """
+        proj_max_iters = proj_max_iters or self.proj_max_iters
+        proj_tolerance = proj_tolerance or self.proj_tolerance
+        _ext.require_cuda(points)
+        lib = _ext.lib()
+        dev = points.device
+        B, P = points.shape[0], points.shape[1]
+        points = points.contiguous()
+        if points.dtype != torch.float32:
+            raise RuntimeError("expected scalar type Float")
+        num_list = [int(x) for x in num_points.tolist()]
+        full = all(n == P for n in num_list)
+        if full:
+            points_packed = points.reshape(-1, 3).clone()
+        else:
+            live, _ = padded_to_packed_idx(num_points, P)
+            points_packed = points.reshape(-1, 3)[live].contiguous()
+        M = points_packed.shape[0]
+        normals_packed = torch.zeros_like(points_packed)
+        not_converged = torch.ones((M,), dtype=torch.bool, device=dev)
+
+        analytic = getattr(model, "isob200_analytic_sdf", None)
+        if analytic is not None and not forward_kwargs and M > 0:
+            kind, radius = analytic
+            if kind != "sphere":
+                raise ValueError("unknown built-in SDF %r" % (kind,))
+            valid_u8 = torch.empty((M,), dtype=torch.uint8, device=dev)
+            _ext.check(lib.isob200_project_sphere(
+                _ext.ptr(points_packed), _ext.ptr(normals_packed), _ext.ptr(valid_u8), M, float(radius),
+                float(proj_tolerance), 0.1, int(proj_max_iters), _ext.stream(dev)))
+            valid_packed = valid_u8.bool()
+        else:
+            if M > 0:
+                act_a = torch.empty((M,), dtype=torch.int32, device=dev)
+                act_b = torch.empty((M,), dtype=torch.int32, device=dev)
+                count = torch.zeros((1,), dtype=torch.int32, device=dev)
+                ws = _ext.workspace(lib.isob200_project_step_ws_bytes(M), dev)
+                nc_u8 = not_converged.view(torch.uint8)
+                act_in, act_out = None, act_a
+                A = M
+                it = 0
+                while True:
+                    if act_in is None:
+                        curr_points = points_packed
+                    else:
+                        curr_points = torch.empty((A, 3), dtype=torch.float32, device=dev)
+                        _ext.check(lib.isob200_gather_rows3(_ext.ptr(points_packed), _ext.ptr(act_in), A,
+                                                            _ext.ptr(curr_points), _ext.stream(dev)))
+                    curr_sdf, curr_grad = self._compute_sdf_and_grad(curr_points, model, **forward_kwargs)
+                    curr_sdf = curr_sdf.reshape(-1).contiguous().float()
+                    curr_grad = curr_grad.reshape(-1, 3).contiguous().float()
+                    last = (it == proj_max_iters)
+                    _ext.check(lib.isob200_project_step(
+                        _ext.ptr(points_packed), _ext.ptr(normals_packed), _ext.ptr(nc_u8),
+                        _ext.ptr(act_in), A, _ext.ptr(curr_sdf), _ext.ptr(curr_grad),
+                        float(proj_tolerance), 0.1, 0 if last else 1, _ext.ptr(act_out), _ext.ptr(count),
+                        _ext.ptr(ws), ws.numel(), _ext.stream(dev)))
+                    if last:
+                        break
+                    A = int(count.item())  # the opaque SDF callback needs the batch shape
+                    if A == 0:
+                        break
+                    it += 1
+                    act_in = act_out
+                    act_out = act_b if act_in is act_a else act_a
+            valid_packed = ~not_converged
+
+        if full:
+            return ProjectionResult(points_packed.view(B, P, 3), normals_packed.view(B, P, 3),
+                                    valid_packed.view(B, P))
+        first = num_points_2_cloud_to_packed_first_idx(num_points)
+        pmax = max(num_list) if num_list else 0
+        points_out = packed_to_padded(points_packed, first, pmax)
+        normals_out = packed_to_padded(normals_packed, first, pmax)
+        valid_mask = packed_to_padded(valid_packed.view(-1, 1).float(), first, pmax).squeeze(-1).bool()
+        return ProjectionResult(points_out, normals_out, valid_mask)
+
+    # ------------------------------------------------------------------------------------
+    def resample(self, model, points_init, normals_init, num_points, sample_iters=None,
+                 **forward_kwargs) -> ProjectionResult:
+        """Repulse along neighbours' tangent planes then re-project, ``sample_iters`` times
+        (levelset_sampling.py:239-288)."""
+        sample_iters = sample_iters or self.sample_iters
+        batch_size = points_init.shape[0]
+        if num_points is None:
+            num_points = torch.full((batch_size,), points_init.shape[1], dtype=torch.long,
+                                    device=points_init.device)
+        if sample_iters == 0:
+            return ProjectionResult(points_init, normals_init,
+                                    points_init.new_full(points_init.shape[:-1], True, dtype=torch.bool))
+        if points_init.nelement() < 2 * (self.knn_k + 1):
+            return ProjectionResult(points_init, normals_init,
+                                    points_init.new_full(points_init.shape[:-1], True, dtype=torch.bool))
+        _ext.require_cuda(points_init)
+        lib = _ext.lib()
+        dev = points_init.device
+        flat = points_init.reshape(-1, 3)
+        diag = (flat.max(dim=0).values - flat.min(0).values).norm()  # stays on the device (:254)
+        inv_sigma_spatial = (num_points.float() / diag).contiguous()  # (B,)
+
+        points = points_init.contiguous()
+        B, P = points.shape[0], points.shape[1]
+        normals = torch.empty_like(points)
+        _ext.check(lib.isob200_normalize_rows3(_ext.ptr(normals_init.contiguous()), B * P, 1e-12,
+                                               _ext.ptr(normals), _ext.stream(dev)))
+        projection_result = None
+        for sample_iter in range(sample_iters):
+            if sample_iter % 2 == 0:
+                # assume repulsion doesn't change neighborhood
+                self._create_tree(points, refresh_tree=True, num_points_per_cloud=num_points)
+            idx_full = self._knn_full_idx  # (B,P,knn_k+1) int64, column 0 = self
+            moved = torch.empty_like(points)
+            _ext.check(lib.isob200_resample_step(
+                _ext.ptr(points), _ext.ptr(normals), _ext.ptr(idx_full), 1, idx_full.shape[2], 1,
+                _ext.ptr(inv_sigma_spatial), B, P, idx_full.shape[2] - 1, _ext.ptr(moved),
+                _ext.stream(dev)))
+            # NB (:284-286): the reference carries the MOVED, un-projected points into the next
+            # sample_iter (`points = points + move`); the projection result is only returned.
+            points = moved
+            projection_result = self._project_points(model, points, num_points, proj_max_iters=3,
+                                                     **forward_kwargs)
+        return projection_result
+
+    # ------------------------------------------------------------------------------------
+    def insert(self, ref_pcl, points, num_points, current_knn_result=None):
+        """Insert children around points close to high-saliency ``ref_pcl`` points
+        (levelset_sampling.py:172-233)."""
+        batch_size = points.shape[0]
+        diag = (points.view(-1, 3).max(dim=0).values - points.view(-1, 3).min(0).values).norm().item()
+        avg_spacing = math.sqrt(diag / ref_pcl.num_points_per_cloud().item())
+        patch_size = 8
+        knn_k = patch_size
+        search_radius = min(avg_spacing * knn_k, 0.2)
+        if current_knn_result is None:
+            dists, idxs, _, _ = frnn.frnn_grid_points(points, points, num_points, num_points, K=knn_k + 1,
+                                                      r=search_radius, grid=None, return_nn=False)
+            current_knn_result = _KNN(dists=dists[..., 1:], idx=idxs[..., 1:], knn=None)
+        try:
+            metrics = ref_pcl.features_packed()
+            num_ref = metrics.shape[0]
+            threshold = min(metrics.median() * 2, metrics.max() * 0.5)
+            assert (len(ref_pcl) == 1), "Support only 1 point cloud"
+            ref_pts = ref_pcl.points_packed()[(metrics > threshold).squeeze(-1)].view(1, -1, 3)
+            if ref_pts.shape[1] == 0 or ref_pts.shape[1] > min(50, int(num_ref / 20)):
+                ref_pts = ref_pcl.points_packed()[metrics.sort(dim=0).indices[
+                    -max(min(50, int(num_ref / 20)), 1):, 0]].view(1, -1, 3).expand(batch_size, -1, -1)
+            dists_to_ref, idxs_to_ref, _, _ = frnn.frnn_grid_points(
+                points, ref_pts.expand(batch_size, -1, -1).contiguous(), lengths1=num_points, lengths2=None,
+                K=1, return_nn=False, grid=None, r=search_radius * 4)
+            dists_to_ref = dists_to_ref.view(batch_size, -1)
+            dist_threshold = avg_spacing ** 2
+            father_pts_mask = (dists_to_ref < 4 * dist_threshold) & (dists_to_ref > 0)
+            father_pts = points[father_pts_mask]
+            mother_pts = frnn.frnn_gather(points, current_knn_result.idx[..., -patch_size:].contiguous())
+            mother_pts = mother_pts[father_pts_mask]
+            child_pts = 2 * father_pts.unsqueeze(-2) / 3 + mother_pts / 3
+            child_per_batch = father_pts_mask.sum(-1) * mother_pts.shape[-2]
+            child_pts = child_pts.view(-1, 3)
+            first_idx = F.pad(child_per_batch, (1, 0), 'constant', 0).cumsum(0)
+            child_pts = packed_to_padded(child_pts, first_idx[:-1], int(child_per_batch.max().item()))
+        except Exception as e:  # same recovery as the reference (:224-228)
+            import logging
+            logging.getLogger("isopoints_b200").error("Error occurred during insertion {}".format(e))
+            child_pts = points.new_zeros((batch_size, 0, 3))
+            child_per_batch = num_points.new_zeros((batch_size,))
+        points = torch.cat((points, child_pts), dim=1)
+        num_points = num_points + child_per_batch
+        return points, num_points, child_pts, child_per_batch
+
+    def upsample(self, points, n_points, model, num_points=None, **forward_kwargs):
+        """levelset_sampling.py:235-237."""
+        from .point_processing import upsample
+        points, num_points = upsample(points, n_points, num_points=num_points, neighborhood_size=31)
+        return points, num_points
+
+    # ------------------------------------------------------------------------------------
+    def project_points(self, point_clouds, model, normals_init: Optional[torch.Tensor] = None,
+                       skip_resampling: bool = False, skip_upsampling: bool = False,
+                       ref_pcl=None, proj_max_iters: Optional[int] = None,
+                       sample_iters: Optional[int] = None, **forward_kwargs):
+        """project -> (filter, resample) -> (insert | upsample, re-project); levelset_sampling.py:353-439.
+
+        Returns {'levelset_points', 'levelset_normals', 'mask'}; 'levelset_normals' is absent when
+        nothing converged (:396-399).
+        """
+        points_init, num_points = convert_pointclouds_to_tensor(point_clouds)
+        num_points_init = num_points
+        proj_max_iters = proj_max_iters or self.proj_max_iters
+        sample_iters = sample_iters or self.sample_iters
+        if normals_init is None and is_pointclouds(point_clouds):
+            normals_init = point_clouds.normals_padded()
+
+        with autograd.no_grad():
+            points_projected, normals_projected, valid_projection = self._project_points(
+                model, points_init, num_points, proj_max_iters=proj_max_iters, **forward_kwargs)
+            if not valid_projection.any():
+                return {'levelset_points': points_projected, 'mask': valid_projection}
+
+            if not skip_resampling:
+                points_projected, normals_projected, valid_projection = _filter_projection_result(
+                    ProjectionResult(points_projected, normals_projected, valid_projection))
+                num_points = valid_projection.sum(dim=-1)
+                points_projected, normals_projected, valid_projection = self.resample(
+                    model, points_projected, normals_projected, num_points, sample_iters=sample_iters,
+                    **forward_kwargs)
+                num_points = valid_projection.sum(dim=-1)
+
+            if not skip_upsampling and ref_pcl is not None:
+                points_projected, normals_projected, valid_projection = _filter_projection_result(
+                    ProjectionResult(points_projected, normals_projected, valid_projection))
+                num_points = valid_projection.sum(dim=-1)
+                _, _, new_points, num_new_points = self.insert(ref_pcl, points_projected, num_points)
+                new_points_projected, new_normals_projected, new_valid_projection = self._project_points(
+                    model, new_points, num_new_points, proj_max_iters=10, **forward_kwargs)
+                points_projected = torch.cat([points_projected, new_points_projected], dim=1)
+                normals_projected = torch.cat([normals_projected, new_normals_projected], dim=1)
+                valid_projection = torch.cat([valid_projection, new_valid_projection], dim=1)
+            elif not skip_upsampling:
+                points_projected, normals_projected, valid_projection = _filter_projection_result(
+                    ProjectionResult(points_projected, normals_projected, valid_projection))
+                num_points = valid_projection.sum(dim=-1)
+                points_projected, num_points = self.upsample(
+                    points_projected, num_points_init, model, num_points, **forward_kwargs)
+                points_projected, normals_projected, valid_projection = self._project_points(
+                    model, points_projected, num_points, proj_max_iters=10, **forward_kwargs)
+
+            return {'levelset_points': points_projected,
+                    'levelset_normals': normals_projected,
+                    'mask': valid_projection}
