@@ -1,0 +1,119 @@
+"""Generate tests/golden/*.npz by running the REFERENCE's own code (authoring container only).
+
+    python tests/golden/make_golden.py
+
+* projection / resample vectors: the reference's Python (DSS/models/levelset_sampling.py loaded
+  from /root/reference through oracle/ref_python.py's asserted 2-entry torch-2.x patch list) on
+  CPU tensors; its `frnn` dependency (CUDA-only) is replaced by a stand-in built on the
+  reference's own CPU brute force `frnn._C.frnn_bf_cpu` (oracle/_ref/ref_frnn_C.so).
+* FRNN vectors: `frnn._C.frnn_bf_cpu` (bruteforce_cpu.cpp:4-58).
+* splat vectors: the reference's `DSS._C._splat_points_naive` CPU twin
+  (rasterize_points_cpu.cpp:27-144) -- NB its bbox reject uses && where the CUDA kernel uses ||
+  (SURVEY 7.3), which is invisible when radii bound the cutoff ellipse, as they do here.
+The fixtures are small (< 1 MB total) and committed; the GPU box has no /root/reference.
+"""
+import os
+import sys
+import types
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+
+from oracle import ref_native, ref_python  # noqa: E402
+from tests.helpers import SphereSDF, TinySiren, make_splat_inputs  # noqa: E402
+
+
+class _CpuFrnn(types.SimpleNamespace):
+    """frnn.frnn_grid_points / frnn_gather on CPU tensors via the reference's frnn_bf_cpu."""
+
+    @staticmethod
+    def frnn_grid_points(points1, points2, lengths1=None, lengths2=None, K=-1, r=-1, grid=None,
+                         return_nn=False, return_sorted=True, radius_cell_ratio=2.0):
+        N = points1.shape[0]
+        if lengths1 is None:
+            lengths1 = torch.full((N,), points1.shape[1], dtype=torch.long)
+        if lengths2 is None:
+            lengths2 = torch.full((N,), points2.shape[1], dtype=torch.long)
+        rr = float(r.reshape(-1)[0]) if torch.is_tensor(r) else float(r)
+        idxs, dists = ref_native.frnn_bf_cpu(points1.contiguous(), points2.contiguous(), lengths1, lengths2, K, rr)
+        nn = _CpuFrnn.frnn_gather(points2, idxs, lengths2) if return_nn else None
+        return dists, idxs, nn, None
+
+    @staticmethod
+    def frnn_gather(x, idxs, lengths=None):
+        m = idxs < 0
+        j = idxs.clamp_min(0)
+        out = torch.stack([x[n][j[n]] for n in range(x.shape[0])], 0)
+        out[m] = 0
+        return out
+
+
+def main():
+    torch.set_num_threads(4)
+    ref = ref_python.load(frnn_module=_CpuFrnn)
+    LS = ref.levelset_sampling
+
+    # ---- C1: 4096 points, analytic unit sphere, 10 projection iterations -------------------
+    torch.manual_seed(0)
+    x = (torch.rand(1, 4096, 3) - 0.5) * 1.5
+    proj = LS.UniformProjection(proj_max_iters=10, proj_tolerance=5e-5)
+    out = proj.project_points(x.clone(), SphereSDF(), skip_resampling=True, skip_upsampling=True)
+    np.savez_compressed(os.path.join(HERE, "proj_sphere.npz"), x=x.numpy(),
+                        points=out["levelset_points"].numpy(), normals=out["levelset_normals"].numpy(),
+                        mask=out["mask"].numpy())
+    print("proj_sphere: converged", float(out["mask"].float().mean()))
+
+    # ---- opaque nn.Module SDF (tiny Siren), ragged batch of two clouds ---------------------
+    torch.manual_seed(1)
+    net = TinySiren(seed=3)
+    xb = (torch.rand(2, 1500, 3) - 0.5) * 1.6
+    num = torch.tensor([1500, 1100])
+    res = proj._project_points(net, xb.clone(), num, proj_max_iters=6)
+    np.savez_compressed(os.path.join(HERE, "proj_siren.npz"), x=xb.numpy(), num=num.numpy(),
+                        points=res.points.numpy(), normals=res.normals.numpy(), mask=res.mask.numpy())
+    print("proj_siren: converged", float(res.mask.float().mean()))
+
+    # ---- project -> filter -> resample (1 sample_iter, knn_k=8) on the sphere --------------
+    torch.manual_seed(2)
+    x2 = (torch.rand(1, 2048, 3) - 0.5) * 1.5
+    proj2 = LS.UniformProjection(proj_max_iters=10, proj_tolerance=5e-5, knn_k=8, sample_iters=1)
+    out2 = proj2.project_points(x2.clone(), SphereSDF(), skip_upsampling=True)
+    # and a 3-iteration resample directly (exercises the neighbourhood refresh on even iterations)
+    p0 = proj2._project_points(SphereSDF(), x2.clone(), torch.tensor([2048]))
+    r3 = proj2.resample(SphereSDF(), p0.points, p0.normals, torch.tensor([2048]), sample_iters=3)
+    np.savez_compressed(os.path.join(HERE, "resample_sphere.npz"), x=x2.numpy(),
+                        points=out2["levelset_points"].numpy(), normals=out2["levelset_normals"].numpy(),
+                        mask=out2["mask"].numpy(), points3=r3.points.numpy(), normals3=r3.normals.numpy(),
+                        mask3=r3.mask.numpy())
+    print("resample_sphere: valid", float(out2["mask"].float().mean()))
+
+    # ---- FRNN brute force -------------------------------------------------------------------
+    torch.manual_seed(3)
+    p = torch.rand(2, 1500, 3)
+    lens = torch.tensor([1500, 1200])
+    idxs, dists = ref_native.frnn_bf_cpu(p, p, lens, lens, 8, 0.1)
+    p2d = torch.rand(1, 1000, 2)
+    l2d = torch.tensor([1000])
+    idxs2, dists2 = ref_native.frnn_bf_cpu(p2d, p2d, l2d, l2d, 5, 0.05)
+    np.savez_compressed(os.path.join(HERE, "frnn_bf.npz"), p=p.numpy(), lens=lens.numpy(), K=8, r=0.1,
+                        idxs=idxs.numpy(), dists=dists.numpy(), p2d=p2d.numpy(), idxs2d=idxs2.numpy(),
+                        dists2d=dists2.numpy())
+
+    # ---- splat forward: reference naive CPU twin --------------------------------------------
+    C = ref_native.dss_C()
+    S, K = 48, 4
+    inp = make_splat_inputs(n_views=2, pts_per_view=[700, 500], S=S, seed=4, sigma_px=1.5)
+    t = {k: torch.as_tensor(v) for k, v in inp.items()}
+    idx, zbuf, qv, occ = C._splat_points_naive(t["points"], t["ellipse"], t["cutoff"], t["radii"],
+                                               t["first_idx"], t["num_points"], 0.05, S, K)
+    np.savez_compressed(os.path.join(HERE, "splat_naive_cpu.npz"), S=S, K=K, depth_merging_thres=0.05,
+                        idx=idx.numpy(), zbuf=zbuf.numpy(), qvalue=qv.numpy(), occ=occ.numpy(), **inp)
+    print("splat: occupied", float(occ.mean()))
+
+
+if __name__ == "__main__":
+    main()

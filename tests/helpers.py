@@ -1,0 +1,82 @@
+"""Shared synthetic inputs for tests, golden generation and bench (seeded, fp32)."""
+import types
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+
+class SphereSDF(nn.Module):
+    """sdf(x) = |x| - radius, returned as an object with a `.sdf` (n,1) field
+    (the interface levelset_sampling.py:160 expects)."""
+
+    def __init__(self, radius=1.0, analytic=False):
+        super().__init__()
+        self.radius = radius
+        if analytic:  # lets isopoints_b200 pick its fused built-in kernel
+            self.isob200_analytic_sdf = ("sphere", radius)
+
+    def forward(self, x, **kwargs):
+        return types.SimpleNamespace(sdf=x.norm(dim=-1, keepdim=True) - self.radius)
+
+
+class TinySiren(nn.Module):
+    """3 sine layers x 32 + linear head, deterministic init; offset so the zero set is a blob."""
+
+    def __init__(self, seed=0, hidden=32, omega=6.0):
+        super().__init__()
+        g = torch.Generator().manual_seed(seed)
+        self.omega = omega
+        dims = [3, hidden, hidden, hidden, 1]
+        self.lin = nn.ModuleList(nn.Linear(dims[i], dims[i + 1]) for i in range(4))
+        with torch.no_grad():
+            for i, l in enumerate(self.lin):
+                bound = (1.0 / dims[i]) if i == 0 else (np.sqrt(6.0 / dims[i]) / omega)
+                l.weight.copy_((torch.rand(l.weight.shape, generator=g) * 2 - 1) * bound)
+                l.bias.copy_((torch.rand(l.bias.shape, generator=g) * 2 - 1) * 0.1)
+
+    def forward(self, x, **kwargs):
+        h = x
+        for l in self.lin[:-1]:
+            h = torch.sin(self.omega * l(h))
+        out = self.lin[-1](h) + 0.5 * (x.norm(dim=-1, keepdim=True) - 0.6)
+        return types.SimpleNamespace(sdf=out)
+
+
+def make_splat_inputs(n_views, pts_per_view, S, seed, sigma_px=1.5, aniso=True, behind_frac=0.05):
+    """Packed screen-space splats at the kernel boundary: xy ~ U(-0.95,0.95),
+    z ~ U(1,3) (a few < 0 to exercise the behind-camera reject), ellipse (a,b,c) of a Gaussian
+    with std ~ sigma_px pixels (mildly anisotropic/rotated when `aniso`), cutoff = 1, radii =
+    the axis-aligned box of the cutoff ellipse."""
+    rng = np.random.RandomState(seed)
+    if isinstance(pts_per_view, int):
+        pts_per_view = [pts_per_view] * n_views
+    P = int(sum(pts_per_view))
+    xy = rng.uniform(-0.95, 0.95, size=(P, 2))
+    z = rng.uniform(1.0, 3.0, size=(P, 1))
+    z[rng.uniform(size=(P, 1)) < behind_frac] *= -1.0
+    sig = sigma_px * (2.0 / S)
+    if aniso:
+        s1 = sig * rng.uniform(0.7, 1.3, size=P)
+        s2 = sig * rng.uniform(0.7, 1.3, size=P)
+        th = rng.uniform(0, np.pi, size=P)
+    else:
+        s1 = np.full(P, sig); s2 = np.full(P, sig); th = np.zeros(P)
+    c_, s_ = np.cos(th), np.sin(th)
+    # covariance V = R diag(s1^2, s2^2) R^T ; Q = [dx dy] V^-1 [dx dy]^T = a dx^2 + b dx dy + c dy^2
+    v11 = c_ * c_ * s1 ** 2 + s_ * s_ * s2 ** 2
+    v22 = s_ * s_ * s1 ** 2 + c_ * c_ * s2 ** 2
+    v12 = c_ * s_ * (s1 ** 2 - s2 ** 2)
+    det = v11 * v22 - v12 ** 2
+    a = v22 / det
+    b = -2 * v12 / det
+    c = v11 / det
+    cutoff = np.ones(P)
+    # bbox of {Q <= cutoff}: half extents sqrt(cutoff * V11), sqrt(cutoff * V22)
+    radii = np.stack([np.sqrt(cutoff * v11), np.sqrt(cutoff * v22)], 1)
+    num = np.asarray(pts_per_view, np.int64)
+    first = np.concatenate([[0], np.cumsum(num)[:-1]]).astype(np.int64)
+    return dict(points=np.concatenate([xy, z], 1).astype(np.float32),
+                ellipse=np.stack([a, b, c], 1).astype(np.float32),
+                cutoff=cutoff.astype(np.float32), radii=radii.astype(np.float32),
+                first_idx=first, num_points=num)
