@@ -1,0 +1,320 @@
+#!/usr/bin/env python
+"""bench.py -- iso-points hot path on B200: one JSON line per run (see DESIGN.md "Measurement").
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+Workload (BASELINE.json configs[1], "C2"): 200 000 points per GPU, (rand-0.5)*2, random-init
+8-layer x 256 SIREN SDF, UniformProjection(proj_max_iters=10, tol=5e-5, knn_k=8, sample_iters=1)
+.project_points(x, sdf, skip_upsampling=True)  = project -> filter -> FRNN(K=9) -> resample ->
+3-iteration re-projection.  A "step" is one such pass over one synthetic cloud.
+  value : input iso-points / second, whole job, inputs resident in HBM, CUDA-event timed;
+  e2e   : same through the public API with HOST buffers (pinned H2D of the cloud, D2H of
+          points+normals+mask inside the timed region);
+  splat : second headline metric (pixel-splats/s, BASELINE configs[3] "C4") when the splat
+          kernels are built, reported in the same line under "splat".
+N > 1 (torchrun, one rank per GPU): the cloud is sharded by contiguous point ranges (weak scaling,
+200 000 points per rank); projection is embarrassingly parallel, the resample exchanges projected
+positions + normals with one all-gather so that every rank searches the full cloud.
+`--impl reference` times the CPU restatement of the reference path (oracle/port.py; the path is
+Python + third-party CUDA-only FRNN, so the reference itself cannot run on host cores) on rank 0.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+C2_POINTS = 200_000
+L2_FLUSH_BYTES = 256 << 20
+
+
+def _peaks():
+    try:
+        return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))), "measured"
+    except Exception:
+        return {"hbm_gbs": 6650.0}, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index=0):
+        self.rows = []
+        self.gpu = gpu_index
+        self._stop = threading.Event()
+        self._t = None
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                      "-i", str(self.gpu)], capture_output=True, text=True, timeout=5).stdout
+                for line in out.strip().splitlines():
+                    self.rows.append([c.strip() for c in line.split(",")])
+            except Exception:
+                pass
+            self._stop.wait(0.2)
+
+    def __enter__(self):
+        self._t = threading.Thread(target=self._run, daemon=True)
+        self._t.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        self._t.join(timeout=6)
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2]))
+            except Exception:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def _dist_init(n_gpus):
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        import torch.distributed as dist
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    return rank, world, local
+
+
+def _barrier(world):
+    if world > 1:
+        import torch.distributed as dist
+        dist.barrier()
+    torch.cuda.synchronize()
+
+
+def _max_over_ranks(x, world, dev):
+    if world == 1:
+        return x
+    import torch.distributed as dist
+    t = torch.tensor([x], dtype=torch.float64, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def _make_c2(rank, dev):
+    from tests.helpers import SirenSDF
+    g = torch.Generator().manual_seed(1000 + rank)
+    x = (torch.rand(1, C2_POINTS, 3, generator=g) - 0.5) * 2
+    net = SirenSDF(hidden=256, n_layers=7, omega=30.0, seed=0)
+    return x, net
+
+
+# ---------------------------------------------------------------------------------------------
+def run_ours(args):
+    from isopoints_b200 import _ext
+    from isopoints_b200.levelset_sampling import UniformProjection
+    rank, world, local = _dist_init(args.gpus)
+    dev = torch.device("cuda", local)
+    torch.cuda.set_device(dev)
+    torch.backends.cuda.matmul.allow_tf32 = False      # parity bar is fp32 1e-4 (SIREN x30 gain)
+    torch.backends.cudnn.allow_tf32 = False
+    lib = _ext.lib()
+    x_host, net = _make_c2(rank, dev)
+    net = net.to(dev)
+    x_dev = x_host.to(dev)
+    x_pin = x_host.pin_memory()
+    if world > 1:
+        from isopoints_b200.dist import ShardedUniformProjection
+        proj = ShardedUniformProjection(proj_max_iters=10, proj_tolerance=5e-5, knn_k=8, sample_iters=1)
+    else:
+        proj = UniformProjection(proj_max_iters=10, proj_tolerance=5e-5, knn_k=8, sample_iters=1)
+    flush = torch.empty(L2_FLUSH_BYTES, dtype=torch.uint8, device=dev)
+
+    def step(x):
+        return proj.project_points(x, net, skip_upsampling=True)
+
+    def step_e2e():
+        x = x_pin.to(dev, non_blocking=True)
+        out = step(x)
+        res = (out["levelset_points"].cpu(), out["levelset_normals"].cpu(), out["mask"].cpu())
+        return out, res
+
+    for _ in range(args.warmup):
+        out = step(x_dev)
+    _barrier(world)
+
+    # ---- timed region: K steps, device resident inputs, L2 flushed between steps ----------
+    _ext.PROFILE = {}
+    l0 = lib.isob200_launch_count()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    with ClockSampler(local) as clocks:
+        _barrier(world)
+        t0 = time.perf_counter()
+        for k in range(args.steps):
+            flush.fill_(k & 0xff)
+            ev[k][0].record()
+            out = step(x_dev)
+            ev[k][1].record()
+        _barrier(world)
+        wall = time.perf_counter() - t0
+    launches = lib.isob200_launch_count() - l0
+    prof = _ext.PROFILE
+    _ext.PROFILE = None
+    ms = sum(a.elapsed_time(b) for a, b in ev) / args.steps
+    ms = _max_over_ranks(ms, world, dev)
+    converged = float(out["mask"].float().mean())
+    n_out = int(out["mask"].shape[1])
+
+    kern = {}
+    for name, pairs in prof.items():
+        ts = [a.elapsed_time(b) for a, b in pairs]
+        kern[name.replace("isob200_", "")] = {"calls_per_step": len(ts) / args.steps,
+                                              "ms_per_step": sum(ts) / args.steps,
+                                              "avg_ms": sum(ts) / len(ts)}
+    own_ms = sum(v["ms_per_step"] for v in kern.values())
+
+    # ---- e2e: host buffers, H2D + D2H inside the timed region ------------------------------
+    for _ in range(2):
+        step_e2e()
+    _barrier(world)
+    ev2 = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    t_e2e = 0.0
+    for k in range(args.steps):
+        flush.fill_(k & 0xff)
+        torch.cuda.synchronize()
+        t1 = time.perf_counter()
+        o, res = step_e2e()
+        torch.cuda.synchronize()
+        t_e2e += time.perf_counter() - t1
+    e2e_ms = _max_over_ranks(t_e2e / args.steps * 1e3, world, dev)
+    h2d = x_pin.numel() * 4
+    d2h = sum(t.numel() * t.element_size() for t in res)
+
+    peaks, peak_src = _peaks()
+    # dominant own kernel of this path: the FRNN query (K = knn_k + 1 = 9, int64 idx + f32 dist out)
+    q = kern.get("frnn_find_nbrs")
+    roof = None
+    if q:
+        K = 9
+        n_q = n_out * (world if world > 1 else 1) if False else n_out
+        alg = n_q * (16 + 12 * K)                       # 16 + 12K bytes per query
+        achieved = alg / (q["avg_ms"] * 1e-3) / 1e9
+        roof = {"kernel": "frnn_query_kernel", "bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"],
+                "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"], "traffic": None, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": alg, "avg_launch_ms": q["avg_ms"]}
+
+    line = {
+        "metric": "iso-points/sec (project+resample)", "value": C2_POINTS * world / (ms * 1e-3), "unit": "points/s",
+        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "C2: 200000 pts/GPU, random-init SIREN 8x256 SDF (fp32, TF32 off), project(10 it)+"
+                               "resample(knn_k=8, 1 it)+reproject(3 it)", "points_per_gpu": C2_POINTS,
+                   "l2": "flushed between steps (256 MiB write)", "converged_frac": converged,
+                   "points_after_filter": n_out, "parallelism": "point-sharded x%d" % world},
+        "e2e": {"value": C2_POINTS * world / (e2e_ms * 1e-3), "unit": "points/s", "h2d_bytes_per_step": h2d,
+                "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms},
+        "gpu_launches": int(launches),
+        "clocks": clocks.summary(),
+        "roofline": roof,
+        "own_kernels_ms_per_step": own_ms,
+        "sdf_callback_and_glue_ms_per_step": ms - own_ms,
+        "kernels": kern,
+        "wall_s_timed_region": wall,
+    }
+    if rank == 0:
+        if world == 1:
+            line["cpu_baseline"] = cpu_baseline(sample_points=args.cpu_sample)
+            try:
+                import bench_splat
+                line["splat"] = bench_splat.run(args, dev, peaks, peak_src)
+            except ImportError:
+                pass
+        print(json.dumps(line))
+    if world > 1:
+        import torch.distributed as dist
+        dist.destroy_process_group()
+
+
+# ---------------------------------------------------------------------------------------------
+def cpu_baseline(sample_points=10_000, threads=None):
+    """The oracle port of the same workload on the host cores, on a bounded sample."""
+    from oracle import port
+    from tests.helpers import SirenSDF
+    threads = threads or os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    g = torch.Generator().manual_seed(1000)
+    x = ((torch.rand(1, C2_POINTS, 3, generator=g) - 0.5) * 2)[0, :sample_points].contiguous()
+    net = SirenSDF(hidden=256, n_layers=7, omega=30.0, seed=0)
+    t0 = time.perf_counter()
+    p, n, v = port.project_points_packed(net, x, proj_max_iters=10, proj_tolerance=5e-5)
+    t1 = time.perf_counter()
+    if int(v.sum()) >= 18:
+        port.resample(net, p[v], n[v], sample_iters=1, knn_k=8, proj_tolerance=5e-5)
+    t2 = time.perf_counter()
+    return {"value": sample_points / (t2 - t0), "unit": "points/s", "cores": threads, "kind": "port",
+            "sample": "first %d of the 200000 C2 points, same SIREN; project %.1fs + resample %.1fs; "
+                      "torch-CPU fp32 with %d threads (FRNN stage: numpy brute force, 1 thread)"
+                      % (sample_points, t1 - t0, t2 - t1, threads)}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if rank != 0:
+        return
+    vals = []
+    base = None
+    for _ in range(args.warmup if args.warmup < 2 else 1):
+        cpu_baseline(sample_points=max(1000, args.cpu_sample // 4))
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        base = cpu_baseline(sample_points=args.cpu_sample)
+        vals.append(base["value"])
+    v = float(np.mean(vals))
+    base["value"] = v
+    line = {"impl": "reference", "metric": "iso-points/sec (project+resample)", "value": v, "unit": "points/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": args.cpu_sample / v * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "C2 (bounded sample of %d points per step)" % args.cpu_sample},
+            "cpu_baseline": base,
+            "e2e": {"value": v, "unit": "points/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--cpu-sample", type=int, default=10_000)
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py: no CUDA device (there is no CPU fallback for the product path)")
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -24,6 +24,7 @@ extern "C" {
 const char* isob200_last_error(void);
 int isob200_abi_version(void);
 int isob200_compiled_arch(void); /* 1000 = sm_100a */
+long long isob200_launch_count(void); /* kernels launched by this library so far (bench.py gpu_launches) */
 
 /* ---- exclusive scan: prefix_sum.prefix_sum_cuda(cnt, num_cells, off)
  *      external/FRNN/external/prefix_sum/prefix_sum.cu:74-87 (prefix_sum.h:18-20);

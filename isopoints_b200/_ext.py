@@ -23,6 +23,7 @@ _PROTOS = {
     "isob200_last_error": (ctypes.c_char_p, []),
     "isob200_abi_version": (_i, []),
     "isob200_compiled_arch": (_i, []),
+    "isob200_launch_count": (_ll, []),
     "isob200_exclusive_scan_ws_bytes": (_sz, [_i, _i]),
     "isob200_exclusive_scan_i32": (_i, [_vp, _vp, _i, _i, _ll, _ll, _vp, _sz, _vp]),
     "isob200_frnn_grid_params": (_i, [_vp, _vp, _vp, _i, _i, _i, _d, _vp, _vp, _vp, _sz, _vp]),
@@ -44,6 +45,35 @@ _PROTOS = {
 }
 
 _LIB = None
+_RAW = None
+
+# Optional per-entry-point device timing (bench.py): when PROFILE is a dict, every C-ABI call is
+# bracketed by CUDA events on the stream it is launched on; PROFILE[name] collects (start, end).
+PROFILE = None
+_NO_TIMING = ("_ws_bytes", "isob200_last_error", "isob200_abi_version", "isob200_compiled_arch",
+              "isob200_launch_count")
+
+
+class _Lib:
+    pass
+
+
+def _wrap(name, fn):
+    if name.endswith(_NO_TIMING) or name in _NO_TIMING:
+        return fn
+
+    def call(*args):
+        if PROFILE is None:
+            return fn(*args)
+        st = torch.cuda.ExternalStream(args[-1]) if args[-1] else torch.cuda.current_stream()
+        a = torch.cuda.Event(enable_timing=True)
+        b = torch.cuda.Event(enable_timing=True)
+        a.record(st)
+        rc = fn(*args)
+        b.record(st)
+        PROFILE.setdefault(name, []).append((a, b))
+        return rc
+    return call
 
 
 def exported_symbols():
@@ -58,12 +88,16 @@ def lib():
             raise ImportError(
                 "isopoints_b200: %s not found -- build it with `python -m isopoints_b200.build` "
                 "(there is no CPU/PyTorch fallback for the CUDA path)" % LIB_PATH)
+        global _RAW
         h = ctypes.CDLL(LIB_PATH)
+        w = _Lib()
         for name, (res, args) in _PROTOS.items():
             fn = getattr(h, name)  # AttributeError if the .so is stale
             fn.restype = res
             fn.argtypes = args
-        _LIB = h
+            setattr(w, name, _wrap(name, fn))
+        _RAW = h
+        _LIB = w
     return _LIB
 
 

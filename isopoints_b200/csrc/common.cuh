@@ -14,6 +14,7 @@
 namespace isob200 {
 
 void set_error(const char* fmt, ...);
+void count_launch();  // bumps the library-wide kernel launch counter (isob200_launch_count)
 
 constexpr int kNumSMs = 148;  // B200
 
@@ -46,6 +47,7 @@ static inline size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a
       isob200::set_error("%s: CUDA error: %s", name, cudaGetErrorString(e__));        \
       return ISOB200_ERR_CUDA;                                                        \
     }                                                                                 \
+    isob200::count_launch();                                                          \
   } while (0)
 
 #define ISO_CUDA(call)                                                                \

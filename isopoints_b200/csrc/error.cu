@@ -3,6 +3,7 @@
 // RuntimeError the reference's TORCH_CHECK / AT_CUDA_CHECK would have raised).
 #include "common.cuh"
 #include <stdarg.h>
+#include <atomic>
 
 namespace isob200 {
 static thread_local char g_err[512] = "";
@@ -12,9 +13,12 @@ void set_error(const char* fmt, ...) {
   vsnprintf(g_err, sizeof(g_err), fmt, ap);
   va_end(ap);
 }
+static std::atomic<long long> g_launches{0};
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 }  // namespace isob200
 
 extern "C" {
+long long isob200_launch_count(void) { return isob200::g_launches.load(); }
 const char* isob200_last_error(void) { return isob200::g_err; }
 int isob200_abi_version(void) { return 1; }
 int isob200_compiled_arch(void) {

@@ -80,3 +80,29 @@ def make_splat_inputs(n_views, pts_per_view, S, seed, sigma_px=1.5, aniso=True, 
                 ellipse=np.stack([a, b, c], 1).astype(np.float32),
                 cutoff=cutoff.astype(np.float32), radii=radii.astype(np.float32),
                 first_idx=first, num_points=num)
+
+
+class SirenSDF(nn.Module):
+    """Random-init SIREN SDF of BASELINE config 2 ("8-layer x 256"): architecture and init of
+    DSS/models/common.py:56-165 with dim=3, c_dim=0, hidden_size=256, n_layers=7,
+    first_omega_0 = hidden_omega_0 = 30, outermost_linear=True -- 8 sine layers + a linear head.
+    (User-side model: the SDF is an opaque nn.Module callback on the hot path.)"""
+
+    def __init__(self, hidden=256, n_layers=7, omega=30.0, seed=0):
+        super().__init__()
+        self.omega = omega
+        g = torch.Generator().manual_seed(seed)
+        dims = [3] + [hidden] * (n_layers + 1) + [1]
+        self.lin = nn.ModuleList(nn.Linear(dims[i], dims[i + 1]) for i in range(len(dims) - 1))
+        with torch.no_grad():
+            for i, l in enumerate(self.lin):
+                fan = dims[i]
+                bound = (1.0 / fan) if i == 0 else (np.sqrt(6.0 / fan) / omega)
+                l.weight.copy_((torch.rand(l.weight.shape, generator=g) * 2 - 1) * bound)
+                l.bias.copy_((torch.rand(l.bias.shape, generator=g) * 2 - 1) / np.sqrt(fan))
+
+    def forward(self, x, **kwargs):
+        h = x
+        for l in self.lin[:-1]:
+            h = torch.sin(self.omega * l(h))
+        return types.SimpleNamespace(sdf=self.lin[-1](h))

@@ -1,0 +1,103 @@
+"""GPU parity: level-set projection and uniform resampling through the operator surface
+(isopoints_b200.levelset_sampling) vs the oracle and the reference-generated golden vectors."""
+import numpy as np
+import pytest
+import torch
+
+from isopoints_b200.levelset_sampling import UniformProjection
+from oracle import port
+from tests.helpers import SphereSDF, TinySiren
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+RTOL = 1e-4   # north_star: fp32 point positions within 1e-4 rel
+
+
+def _close(a, b, rtol=RTOL, atol=1e-6):
+    np.testing.assert_allclose(a.detach().cpu().numpy(), np.asarray(b), rtol=rtol, atol=atol)
+
+
+@pytest.mark.parametrize("analytic", [False, True])
+def test_c1_sphere_projection_matches_reference_golden(golden, analytic):
+    """BASELINE config 1: 4096 points, analytic unit sphere, 10 iterations."""
+    g = golden("proj_sphere")
+    x = torch.as_tensor(g["x"], device=DEV)
+    proj = UniformProjection(proj_max_iters=10, proj_tolerance=5e-5)
+    out = proj.project_points(x.clone(), SphereSDF(analytic=analytic).to(DEV), skip_resampling=True,
+                              skip_upsampling=True)
+    assert set(out) == {"levelset_points", "levelset_normals", "mask"}
+    assert out["mask"].dtype == torch.bool
+    assert np.array_equal(out["mask"].cpu().numpy(), g["mask"])
+    _close(out["levelset_points"], g["points"])
+    _close(out["levelset_normals"], g["normals"])
+
+
+def test_opaque_module_ragged_batch_matches_reference_golden(golden):
+    g = golden("proj_siren")
+    x = torch.as_tensor(g["x"], device=DEV)
+    num = torch.as_tensor(g["num"], device=DEV)
+    proj = UniformProjection(proj_max_iters=10, proj_tolerance=5e-5)
+    res = proj._project_points(TinySiren(seed=3).to(DEV), x.clone(), num, proj_max_iters=6)
+    m = res.mask.cpu().numpy()
+    # a point whose |sdf| sits within float noise of the tolerance may flip: allow <= 0.2 %
+    agree = m == g["mask"]
+    assert agree.mean() > 0.998
+    a = agree[..., None] & np.ones(3, bool)
+    np.testing.assert_allclose(res.points.cpu().numpy()[a], g["points"][a], rtol=RTOL, atol=2e-6)
+    np.testing.assert_allclose(res.normals.cpu().numpy()[a], g["normals"][a], rtol=1e-3, atol=1e-5)
+    assert (res.points[1, 1100:] == 0).all() and not res.mask[1, 1100:].any()
+
+
+def test_nothing_converged_early_exit_and_defaults():
+    x = (torch.rand(1, 256, 3, device=DEV) - 0.5) * 0.2          # deep inside the sphere
+    proj = UniformProjection(proj_max_iters=1, proj_tolerance=1e-9)
+    out = proj.project_points(x, SphereSDF().to(DEV), proj_max_iters=0)   # 0 -> instance default (x or default)
+    assert set(out) == {"levelset_points", "mask"} and not out["mask"].any()
+
+
+def test_project_then_resample_matches_reference_golden(golden):
+    g = golden("resample_sphere")
+    x = torch.as_tensor(g["x"], device=DEV)
+    proj = UniformProjection(proj_max_iters=10, proj_tolerance=5e-5, knn_k=8, sample_iters=1)
+    out = proj.project_points(x.clone(), SphereSDF().to(DEV), skip_upsampling=True)
+    assert np.array_equal(out["mask"].cpu().numpy(), g["mask"])
+    _close(out["levelset_points"], g["points"], atol=5e-6)
+    _close(out["levelset_normals"], g["normals"], atol=5e-6)
+    sdf = SphereSDF().to(DEV)
+    p0 = proj._project_points(sdf, x.clone(), torch.tensor([2048], device=DEV))
+    r3 = proj.resample(sdf, p0.points, p0.normals, torch.tensor([2048], device=DEV), sample_iters=3)
+    assert np.array_equal(r3.mask.cpu().numpy(), g["mask3"])
+    _close(r3.points, g["points3"], atol=1e-5)
+
+
+def test_resample_on_mlp_matches_oracle():
+    torch.manual_seed(7)
+    net = TinySiren(seed=5)
+    x = (torch.rand(1, 3000, 3) - 0.5) * 1.6
+    proj = UniformProjection(proj_max_iters=10, proj_tolerance=5e-5, knn_k=8, sample_iters=2)
+    out = proj.project_points(x.to(DEV), net.to(DEV), skip_upsampling=True)
+    net = net.cpu()
+    p, n, v = port.project_points_packed(net, x[0], proj_max_iters=10, proj_tolerance=5e-5)
+    rp, rn, rv = port.resample(net, p[v], n[v], sample_iters=2, knn_k=8, proj_tolerance=5e-5)
+    got_m = out["mask"][0].cpu().numpy()
+    assert got_m.shape == rv.numpy().shape
+    agree = got_m == rv.numpy()
+    assert agree.mean() > 0.99
+    np.testing.assert_allclose(out["levelset_points"][0].cpu().numpy()[agree], rp.numpy()[agree], rtol=RTOL, atol=1e-5)
+
+
+def test_projection_properties_at_c2_scale():
+    """200 000 points: idempotence (projecting a converged set moves nothing), mask <=> |sdf| <= tol."""
+    torch.manual_seed(0)
+    x = (torch.rand(1, 200_000, 3, device=DEV) - 0.5) * 2
+    sdf = SphereSDF().to(DEV)
+    proj = UniformProjection(proj_max_iters=10, proj_tolerance=5e-5)
+    out = proj.project_points(x, sdf, skip_resampling=True, skip_upsampling=True)
+    pts, m = out["levelset_points"], out["mask"]
+    val = sdf(pts).sdf.squeeze(-1).abs()
+    assert torch.equal(val <= 5e-5, m)
+    again = proj.project_points(pts, sdf, skip_resampling=True, skip_upsampling=True)
+    assert torch.equal(again["levelset_points"][m], pts[m])
+    fused = proj.project_points(x, SphereSDF(analytic=True).to(DEV), skip_resampling=True, skip_upsampling=True)
+    assert torch.equal(fused["mask"], m)
+    assert torch.allclose(fused["levelset_points"], pts, rtol=RTOL, atol=1e-6)
