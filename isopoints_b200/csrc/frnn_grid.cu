@@ -244,28 +244,22 @@ constexpr int RS_ROUNDS = 8;
 constexpr int RS_TILE = RS_THREADS * RS_ROUNDS;  // 2048 elements per CTA
 constexpr int RS_MAX_PASSES = 4;
 
-// digit histograms of all passes in one sweep (the multiset of digits is order independent).
-// hist layout: [pass][digit][tile]
+// per-tile digit histogram of ONE pass, taken over the key order that pass will scatter (the
+// per-tile counts depend on the order the previous pass left).  hist layout: [digit][tile]
 __global__ void __launch_bounds__(RS_THREADS)
-radix_hist_kernel(const unsigned* __restrict__ keys, int n, int passes, int tiles,
+radix_hist_kernel(const unsigned* __restrict__ keys, int n, int shift, int tiles,
                   int* __restrict__ hist) {
-  __shared__ int sh[RS_MAX_PASSES][256];
-  for (int i = threadIdx.x; i < RS_MAX_PASSES * 256; i += RS_THREADS) (&sh[0][0])[i] = 0;
+  __shared__ int sh[256];
+  sh[threadIdx.x] = 0;
   __syncthreads();
   const int base = blockIdx.x * RS_TILE;
 #pragma unroll
   for (int j = 0; j < RS_ROUNDS; ++j) {
     int e = base + j * RS_THREADS + threadIdx.x;
-    if (e < n) {
-      unsigned k = keys[e];
-      for (int d = 0; d < passes; ++d) atomicAdd(&sh[d][(k >> (8 * d)) & 255u], 1);
-    }
+    if (e < n) atomicAdd(&sh[(keys[e] >> shift) & 255u], 1);
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < passes * 256; i += RS_THREADS) {
-    int d = i >> 8, dig = i & 255;
-    hist[((size_t)d * 256 + dig) * tiles + blockIdx.x] = sh[d][dig];
-  }
+  hist[(size_t)threadIdx.x * tiles + blockIdx.x] = sh[threadIdx.x];
 }
 
 // one pass: stable scatter by digit `shift/8`.  Element order inside the CTA's tile is
@@ -372,9 +366,9 @@ static BuildWs carve_build_ws(void* ws, int N, int P, int G) {
   b.keys_b = (unsigned*)take(n * 4);
   b.vals_a = (int*)take(n * 4);
   b.vals_b = (int*)take(n * 4);
-  b.hist = (int*)take((size_t)RS_MAX_PASSES * 256 * tiles * 4);
+  b.hist = (int*)take((size_t)256 * tiles * 4);
   b.cloud_start = (int*)take((size_t)(N + 1) * 4);
-  size_t s1 = scan_ws_bytes(256 * tiles, RS_MAX_PASSES);
+  size_t s1 = scan_ws_bytes(256 * tiles, 1);
   size_t s2 = scan_ws_bytes(G, N);
   b.scan_ws_bytes = s1 > s2 ? s1 : s2;
   b.scan_ws = take(b.scan_ws_bytes);
@@ -408,19 +402,19 @@ static int frnn_build_impl(const float* points, const int64_t* lengths, const fl
 
   const int passes = key_passes((long long)N * G);
   const int tiles = div_up(n, RS_TILE);
-  radix_hist_kernel<<<tiles, RS_THREADS, 0, stream>>>(b.keys_a, (int)n, passes, tiles, b.hist);
-  ISO_CHECK_LAUNCH("radix_hist_kernel");
-  rc = exclusive_scan_i32(b.hist, b.hist, 256 * tiles, passes, 256ll * tiles, 256ll * tiles,
-                          b.scan_ws, b.scan_ws_bytes, stream);
-  if (rc) return rc;
   const unsigned* kin = b.keys_a;
   unsigned* kout = b.keys_b;
   const int* vin = nullptr;
   int* vout = b.vals_a;
   for (int d = 0; d < passes; ++d) {
     const bool last = (d == passes - 1);
+    radix_hist_kernel<<<tiles, RS_THREADS, 0, stream>>>(kin, (int)n, 8 * d, tiles, b.hist);
+    ISO_CHECK_LAUNCH("radix_hist_kernel");
+    rc = exclusive_scan_i32(b.hist, b.hist, 256 * tiles, 1, 256ll * tiles, 256ll * tiles, b.scan_ws,
+                            b.scan_ws_bytes, stream);
+    if (rc) return rc;
     radix_scatter_kernel<<<tiles, RS_THREADS, 0, stream>>>(
-        kin, vin, last ? nullptr : kout, vout, (int)n, 8 * d, tiles, b.hist + (size_t)d * 256 * tiles);
+        kin, vin, last ? nullptr : kout, vout, (int)n, 8 * d, tiles, b.hist);
     ISO_CHECK_LAUNCH("radix_scatter_kernel");
     unsigned* kt = (unsigned*)kin;
     kin = kout;

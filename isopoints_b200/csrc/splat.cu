@@ -1,0 +1,559 @@
+// DSS elliptical-splat rasteriser, forward, for sm_100a.
+//
+// Replaces DSS/csrc/rasterize_points.cu: RasterizePoints{Naive,Coarse,Fine}CudaKernel
+// (:131-212, :293-432, :506-597) behind DSS._C.splat_points (rasterize_points.h:461-525).
+//
+// Reference design: a (N,B,B,M) bin_points matrix with M = max(10000, Pmax) int32 slots per
+// 32x32-pixel bin (2.46 GB for 8 views x 300 k points), filled by a 64-block bitmask kernel, then
+// ONE THREAD PER PIXEL walking all M slots with a 150-entry Pix list in local memory.
+//
+// B200 design (HBM / L2-bound integer + fp32 work, no dense contraction):
+//   1. splat_tile_count : one thread per point -> exact range of 16x16-pixel tiles its radii box
+//      can touch -> per-tile counters (integer atomics: order independent).
+//   2. exclusive scan of the counters (scan.cu) -> tile offsets (+ total, read back once to size
+//      the record buffer).
+//   3. splat_tile_fill  : each (tile, point) pair becomes a packed 48-byte record
+//      {px,py,pz,a | b,c,cutoff,rx | ry,id,-,-} in the tile's contiguous slice (cursor atomics;
+//      slot order inside a tile is irrelevant: the per-pixel selection below is a total order).
+//   4. splat_raster<K>  : one CTA per tile, 8 warps, each warp owns an 8x4 pixel block.  The
+//      tile's record slice is streamed through shared memory in 128-record chunks by the TMA
+//      engine (cp.async.bulk + mbarrier, double buffered).  Per 32 records a warp does a
+//      one-lane-per-record box test against its pixel block, ballots the survivors, and only
+//      those are evaluated per pixel (exact reference predicate) and inserted into a K-entry
+//      (z, id, Q) list held in REGISTERS, sorted by (z, id).  Outputs idx/zbuf/qvalue/occ are
+//      written once, vectorised, -1 padding included (no fill pass).
+// Result = reference on tie-free depth: the K covering points with the smallest z, ascending,
+// cut at z - z0 > depth_merging_thres (:203-206); equal z is ordered by smaller point id (the
+// reference keeps whichever its atomics inserted first).
+// fp32 expressions that decide coverage are spelled with intrinsics in the exact order nvcc
+// contracts the reference's (SASS of RasterizePointsFineCudaKernel):
+//   xf = (float(2i)+1)/S - 1 ; dx = xf - px ; Q = fma(c*dy, dy, fma(a*dx, dx, (b*dx)*dy)).
+#include "common.cuh"
+#include "scan.cuh"
+#include <float.h>
+#include <limits.h>
+
+namespace isob200 {
+
+constexpr int TILE = 16;             // pixels per tile side
+constexpr int REC_F4 = 3;            // float4s per record (48 B)
+constexpr int CHUNK = 128;           // records per TMA chunk (6 KB)
+constexpr int STAGES = 2;
+
+__device__ __forceinline__ float pix_to_ndc(int i, float fS) {
+  // rasterization_utils.cuh:8-11: -1 + (2*i + 1.0f) / S
+  return __fadd_rn(__fdiv_rn(__fadd_rn((float)(2 * i), 1.0f), fS), -1.0f);
+}
+
+// Conservative-then-trimmed range of pixel indices i in [0,S) with |ndc(i) - p| <= r.
+// Returns lo > hi when empty.  Never a subset of the exact set (estimate error << 1 pixel and
+// the bounds start one pixel outside).
+__device__ __forceinline__ void pixel_range(float p, float r, int S, float fS, int& lo, int& hi) {
+  const float e_lo = (p - r + 1.0f) * fS * 0.5f - 0.5f;
+  const float e_hi = (p + r + 1.0f) * fS * 0.5f - 0.5f;
+  // clamp in float first: huge radii / far-away points must not overflow the int conversion
+  lo = (int)fmaxf(ceilf(e_lo) - 1.0f, 0.0f);
+  hi = (int)fminf(floorf(e_hi) + 1.0f, (float)(S - 1));
+  if (!(e_lo <= (float)S) || !(e_hi >= -1.0f)) { lo = 1; hi = 0; return; }  // also rejects NaN
+  if (lo <= hi && fabsf(__fsub_rn(pix_to_ndc(lo, fS), p)) > r) ++lo;
+  if (lo <= hi && fabsf(__fsub_rn(pix_to_ndc(hi, fS), p)) > r) --hi;
+}
+
+struct TileRect { int tx0, tx1, ty0, ty1; };
+
+// Tiles are indexed in OUTPUT image coordinates (col = S-1-xi, row = S-1-yi, the flip of
+// rasterize_points.cu:160-161 / :577-578) so that the raster kernel's stores are coalesced.
+__device__ __forceinline__ bool point_tile_rect(const float* __restrict__ points,
+                                                const float* __restrict__ radii, long long p, int S,
+                                                float fS, TileRect& t) {
+  const float px = points[3 * p], py = points[3 * p + 1], pz = points[3 * p + 2];
+  if (!(pz >= 0.0f)) return false;                       // behind the camera (:87-88)
+  const float rx = radii[2 * p], ry = radii[2 * p + 1];
+  int xl, xh, yl, yh;
+  pixel_range(px, rx, S, fS, xl, xh);
+  pixel_range(py, ry, S, fS, yl, yh);
+  if (xl > xh || yl > yh) return false;
+  t.tx0 = (S - 1 - xh) / TILE; t.tx1 = (S - 1 - xl) / TILE;
+  t.ty0 = (S - 1 - yh) / TILE; t.ty1 = (S - 1 - yl) / TILE;
+  return true;
+}
+
+__global__ void __launch_bounds__(256)
+splat_tile_count_kernel(const float* __restrict__ points, const float* __restrict__ radii,
+                        const int64_t* __restrict__ first_idx, const int64_t* __restrict__ num_points,
+                        int S, int T, int* __restrict__ tile_cnt) {
+  const int n = blockIdx.y;
+  const long long first = first_idx[n];
+  const long long num = num_points[n];
+  const float fS = (float)S;
+  int* cnt = tile_cnt + (size_t)n * T * T;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < num;
+       i += (long long)gridDim.x * blockDim.x) {
+    TileRect t;
+    if (!point_tile_rect(points, radii, first + i, S, fS, t)) continue;
+    for (int ty = t.ty0; ty <= t.ty1; ++ty)
+      for (int tx = t.tx0; tx <= t.tx1; ++tx) atomicAdd(&cnt[ty * T + tx], 1);
+  }
+}
+
+// total[0] = number of (tile, point) records = off[last] + cnt[last]
+__global__ void splat_total_kernel(const int* __restrict__ cnt, const int* __restrict__ off, int ntiles,
+                                   int* __restrict__ total) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) total[0] = ntiles > 0 ? off[ntiles - 1] + cnt[ntiles - 1] : 0;
+}
+
+__global__ void __launch_bounds__(256)
+splat_tile_fill_kernel(const float* __restrict__ points, const float* __restrict__ ellipse,
+                       const float* __restrict__ cutoff, const float* __restrict__ radii,
+                       const int64_t* __restrict__ first_idx, const int64_t* __restrict__ num_points,
+                       int S, int T, const int* __restrict__ tile_off, int* __restrict__ tile_cur,
+                       long long capacity, float4* __restrict__ recs) {
+  const int n = blockIdx.y;
+  const long long first = first_idx[n];
+  const long long num = num_points[n];
+  const float fS = (float)S;
+  const int* off = tile_off + (size_t)n * T * T;
+  int* cur = tile_cur + (size_t)n * T * T;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < num;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long p = first + i;
+    TileRect t;
+    if (!point_tile_rect(points, radii, p, S, fS, t)) continue;
+    const float4 r0 = make_float4(points[3 * p], points[3 * p + 1], points[3 * p + 2], ellipse[3 * p]);
+    const float4 r1 = make_float4(ellipse[3 * p + 1], ellipse[3 * p + 2], cutoff[p], radii[2 * p]);
+    const float4 r2 = make_float4(radii[2 * p + 1], __int_as_float((int)p), 0.f, 0.f);
+    for (int ty = t.ty0; ty <= t.ty1; ++ty)
+      for (int tx = t.tx0; tx <= t.tx1; ++tx) {
+        const int tile = ty * T + tx;
+        const long long slot = (long long)off[tile] + atomicAdd(&cur[tile], 1);
+        if (slot < capacity) {
+          recs[slot * REC_F4 + 0] = r0;
+          recs[slot * REC_F4 + 1] = r1;
+          recs[slot * REC_F4 + 2] = r2;
+        }
+      }
+  }
+}
+
+// ---- TMA / mbarrier helpers (cp.async.bulk: SASS UBLKCP) ----
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned phase) {
+  unsigned done;
+  do {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(done)
+        : "r"(smem_u32(bar)), "r"(phase)
+        : "memory");
+  } while (!done);
+}
+__device__ __forceinline__ void tma_bulk_g2s(void* smem_dst, const void* gmem_src, unsigned bytes,
+                                             unsigned long long* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(smem_dst)),
+               "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
+// (z, id) total order of the per-pixel selection
+__device__ __forceinline__ bool zid_less(float z, int id, float z2, int id2) {
+  return (z < z2) || (z == z2 && id < id2);
+}
+
+template <int K>
+struct PixList {
+  float z[K];
+  int id[K];
+  float q[K];
+  __device__ __forceinline__ void clear() {
+#pragma unroll
+    for (int k = 0; k < K; ++k) { z[k] = FLT_MAX; id[k] = INT_MAX; q[k] = 0.f; }
+  }
+  // keep the K smallest (z, id), ascending
+  __device__ __forceinline__ void insert(float cz, int cid, float cq) {
+    if (!zid_less(cz, cid, z[K - 1], id[K - 1])) return;
+#pragma unroll
+    for (int k = K - 1; k > 0; --k) {
+      const bool shift = zid_less(cz, cid, z[k - 1], id[k - 1]);   // candidate sits before slot k-1
+      const bool here = !shift && zid_less(cz, cid, z[k], id[k]);
+      const float nz = shift ? z[k - 1] : (here ? cz : z[k]);
+      const int ni = shift ? id[k - 1] : (here ? cid : id[k]);
+      const float nq = shift ? q[k - 1] : (here ? cq : q[k]);
+      z[k] = nz; id[k] = ni; q[k] = nq;
+    }
+    if (zid_less(cz, cid, z[0], id[0])) { z[0] = cz; id[0] = cid; q[0] = cq; }
+  }
+};
+
+template <int K>
+__global__ void __launch_bounds__(256)
+splat_raster_kernel(const float4* __restrict__ recs, const int* __restrict__ tile_off,
+                    const int* __restrict__ tile_cnt, int S, int T, float depth_merging_thres,
+                    int occ_inclusive, int* __restrict__ out_idx, float* __restrict__ out_z,
+                    float* __restrict__ out_q, float* __restrict__ out_occ) {
+  __shared__ __align__(128) float4 buf[STAGES][CHUNK * REC_F4];
+  __shared__ __align__(8) unsigned long long bar[STAGES];
+
+  const int tile = blockIdx.x;                 // n*T*T + ty*T + tx
+  const int n = tile / (T * T);
+  const int tr = tile - n * T * T;
+  const int ty = tr / T, tx = tr - ty * T;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int c0 = tx * TILE + (warp & 1) * 8;   // first output column of this warp's 8x4 block
+  const int r0 = ty * TILE + (warp >> 1) * 4;
+  const int col = c0 + (lane & 7), row = r0 + (lane >> 3);
+  const bool in_img = col < S && row < S;
+  const float fS = (float)S;
+  const int xi = S - 1 - col, yi = S - 1 - row;   // NDC pixel indices (may be < 0 outside the image)
+  const float xf = pix_to_ndc(xi, fS), yf = pix_to_ndc(yi, fS);
+  // NDC box of the warp's block, grown by half a pixel: a record whose radii box misses it
+  // cannot pass the exact per-pixel test for any of the 32 pixels
+  const float half = 1.0f / fS;
+  const float bx_lo = pix_to_ndc(S - 1 - (c0 + 7), fS) - half, bx_hi = pix_to_ndc(S - 1 - c0, fS) + half;
+  const float by_lo = pix_to_ndc(S - 1 - (r0 + 3), fS) - half, by_hi = pix_to_ndc(S - 1 - r0, fS) + half;
+
+  const int nrec = tile_cnt[tile];
+  const long long base = tile_off[tile];
+  const int nchunks = (nrec + CHUNK - 1) / CHUNK;
+
+  if (threadIdx.x == 0) {
+    mbar_init(&bar[0], 1);
+    mbar_init(&bar[1], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int c = 0; c < STAGES && c < nchunks; ++c) {
+      const int cnt = min(CHUNK, nrec - c * CHUNK);
+      const unsigned bytes = (unsigned)cnt * REC_F4 * 16u;
+      mbar_expect_tx(&bar[c], bytes);
+      tma_bulk_g2s(&buf[c][0], recs + (base + (long long)c * CHUNK) * REC_F4, bytes, &bar[c]);
+    }
+  }
+
+  PixList<K> L;
+  L.clear();
+
+  for (int c = 0; c < nchunks; ++c) {
+    const int st = c & 1;
+    mbar_wait(&bar[st], (unsigned)((c >> 1) & 1));
+    const int cnt = min(CHUNK, nrec - c * CHUNK);
+    const float4* rb = buf[st];
+    for (int j0 = 0; j0 < cnt; j0 += 32) {
+      const int j = j0 + lane;
+      bool hit = false;
+      if (j < cnt) {
+        const float4 a0 = rb[j * REC_F4 + 0];
+        const float rx = rb[j * REC_F4 + 1].w;
+        const float ry = rb[j * REC_F4 + 2].x;
+        hit = !(a0.x - rx > bx_hi) && !(a0.x + rx < bx_lo) && !(a0.y - ry > by_hi) && !(a0.y + ry < by_lo);
+      }
+      unsigned m = __ballot_sync(0xffffffffu, hit);
+      while (m) {
+        const int s = j0 + __ffs(m) - 1;
+        m &= m - 1;
+        const float4 a0 = rb[s * REC_F4 + 0];   // px py pz a   (smem broadcast)
+        const float4 a1 = rb[s * REC_F4 + 1];   // b  c  cutoff rx
+        const float4 a2 = rb[s * REC_F4 + 2];   // ry id
+        // CheckPixelInsidePoint, rasterize_points.cu:64-98
+        const float dx = __fsub_rn(xf, a0.x);
+        const float dy = __fsub_rn(yf, a0.y);
+        if (fabsf(dx) > a1.w || fabsf(dy) > a2.x) continue;
+        const float q = __fmaf_rn(__fmul_rn(a1.y, dy), dy,
+                                  __fmaf_rn(__fmul_rn(a0.w, dx), dx, __fmul_rn(__fmul_rn(a1.x, dx), dy)));
+        if (q > a1.z) continue;
+        L.insert(a0.z, __float_as_int(a2.y), q);
+      }
+    }
+    __syncthreads();   // every warp is done with this stage
+    if (threadIdx.x == 0 && c + STAGES < nchunks) {
+      const int c2 = c + STAGES;
+      const int cnt2 = min(CHUNK, nrec - c2 * CHUNK);
+      const unsigned bytes = (unsigned)cnt2 * REC_F4 * 16u;
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      mbar_expect_tx(&bar[st], bytes);
+      tma_bulk_g2s(&buf[st][0], recs + (base + (long long)c2 * CHUNK) * REC_F4, bytes, &bar[st]);
+    }
+  }
+
+  if (!in_img) return;
+  // epilogue: depth-merge cut (:203-206), occupancy (:196 naive >=, :581 fine >), -1 padding
+  int size = 0;
+  float zmax = -1000.0f;
+#pragma unroll
+  for (int k = 0; k < K; ++k)
+    if (L.id[k] != INT_MAX) { size = k + 1; zmax = L.z[k]; }
+  const float z0 = L.z[0];
+  bool alive = true;
+  int oi[K];
+  float oz[K], oq[K];
+#pragma unroll
+  for (int k = 0; k < K; ++k) {
+    alive = alive && (k < size) && !(__fsub_rn(L.z[k], z0) > depth_merging_thres);
+    oi[k] = alive ? L.id[k] : -1;
+    oz[k] = alive ? L.z[k] : -1.0f;
+    oq[k] = alive ? L.q[k] : -1.0f;
+  }
+  const size_t pix = ((size_t)n * S + row) * S + col;
+  out_occ[pix] = (size > 0 && (occ_inclusive ? (zmax >= 0.0f) : (zmax > 0.0f))) ? 1.0f : 0.0f;
+  int* pi = out_idx + pix * K;
+  float* pz = out_z + pix * K;
+  float* pq = out_q + pix * K;
+  if constexpr (K % 4 == 0) {
+#pragma unroll
+    for (int k = 0; k < K; k += 4) {
+      *reinterpret_cast<int4*>(pi + k) = make_int4(oi[k], oi[k + 1], oi[k + 2], oi[k + 3]);
+      *reinterpret_cast<float4*>(pz + k) = make_float4(oz[k], oz[k + 1], oz[k + 2], oz[k + 3]);
+      *reinterpret_cast<float4*>(pq + k) = make_float4(oq[k], oq[k + 1], oq[k + 2], oq[k + 3]);
+    }
+  } else if constexpr (K % 2 == 0) {
+#pragma unroll
+    for (int k = 0; k < K; k += 2) {
+      *reinterpret_cast<int2*>(pi + k) = make_int2(oi[k], oi[k + 1]);
+      *reinterpret_cast<float2*>(pz + k) = make_float2(oz[k], oz[k + 1]);
+      *reinterpret_cast<float2*>(pq + k) = make_float2(oq[k], oq[k + 1]);
+    }
+  } else {
+#pragma unroll
+    for (int k = 0; k < K; ++k) { pi[k] = oi[k]; pz[k] = oz[k]; pq[k] = oq[k]; }
+  }
+}
+
+// Generic K (17..150, rasterization_utils.cuh:18): same algorithm, list in local memory.
+__global__ void __launch_bounds__(256)
+splat_raster_bigk_kernel(const float4* __restrict__ recs, const int* __restrict__ tile_off,
+                         const int* __restrict__ tile_cnt, int S, int T, int K,
+                         float depth_merging_thres, int occ_inclusive, int* __restrict__ out_idx,
+                         float* __restrict__ out_z, float* __restrict__ out_q,
+                         float* __restrict__ out_occ) {
+  constexpr int KMAX = 150;
+  const int tile = blockIdx.x;
+  const int n = tile / (T * T);
+  const int tr = tile - n * T * T;
+  const int ty = tr / T, tx = tr - ty * T;
+  const int col = tx * TILE + (threadIdx.x & 15), row = ty * TILE + (threadIdx.x >> 4);
+  if (col >= S || row >= S) return;
+  const float fS = (float)S;
+  const float xf = pix_to_ndc(S - 1 - col, fS), yf = pix_to_ndc(S - 1 - row, fS);
+  float lz[KMAX], lq[KMAX];
+  int li[KMAX];
+  int size = 0;
+  const int nrec = tile_cnt[tile];
+  const float4* rb = recs + (long long)tile_off[tile] * REC_F4;
+  for (int s = 0; s < nrec; ++s) {
+    const float4 a0 = rb[s * REC_F4 + 0], a1 = rb[s * REC_F4 + 1], a2 = rb[s * REC_F4 + 2];
+    const float dx = __fsub_rn(xf, a0.x), dy = __fsub_rn(yf, a0.y);
+    if (fabsf(dx) > a1.w || fabsf(dy) > a2.x) continue;
+    const float q = __fmaf_rn(__fmul_rn(a1.y, dy), dy,
+                              __fmaf_rn(__fmul_rn(a0.w, dx), dx, __fmul_rn(__fmul_rn(a1.x, dx), dy)));
+    if (q > a1.z) continue;
+    const int cid = __float_as_int(a2.y);
+    if (size == K && !zid_less(a0.z, cid, lz[K - 1], li[K - 1])) continue;
+    int k = size < K ? size : K - 1;
+    while (k > 0 && zid_less(a0.z, cid, lz[k - 1], li[k - 1])) {
+      lz[k] = lz[k - 1]; li[k] = li[k - 1]; lq[k] = lq[k - 1];
+      --k;
+    }
+    lz[k] = a0.z; li[k] = cid; lq[k] = q;
+    if (size < K) ++size;
+  }
+  const size_t pix = ((size_t)n * S + row) * S + col;
+  const float zmax = size > 0 ? lz[size - 1] : -1000.0f;
+  out_occ[pix] = (size > 0 && (occ_inclusive ? (zmax >= 0.0f) : (zmax > 0.0f))) ? 1.0f : 0.0f;
+  bool alive = true;
+  for (int k = 0; k < K; ++k) {
+    alive = alive && (k < size) && !(__fsub_rn(lz[k], lz[0]) > depth_merging_thres);
+    out_idx[pix * K + k] = alive ? li[k] : -1;
+    out_z[pix * K + k] = alive ? lz[k] : -1.0f;
+    out_q[pix * K + k] = alive ? lq[k] : -1.0f;
+  }
+}
+
+// points_per_bin of RasterizePointsCoarseCudaKernel (rasterize_points.cu:353-412), which the
+// reference computes and drops: bins of bin_size pixels in NDC index space (NOT flipped), extents
+// PixToNdc(b*bin) - 1/S .. PixToNdc((b+1)*bin - 1) + 1/S in fp32, inclusive overlap, z >= 0.
+__global__ void __launch_bounds__(256)
+splat_bin_count_kernel(const float* __restrict__ points, const float* __restrict__ radii,
+                       const int64_t* __restrict__ first_idx, const int64_t* __restrict__ num_points,
+                       int S, int bin_size, int B, int* __restrict__ bin_cnt) {
+  const int n = blockIdx.y;
+  const long long first = first_idx[n], num = num_points[n];
+  const float fS = (float)S;
+  const float half = __fdiv_rn(1.0f, fS);
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < num;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long p = first + i;
+    const float px = points[3 * p], py = points[3 * p + 1], pz = points[3 * p + 2];
+    if (pz < 0) continue;
+    const float px0 = __fsub_rn(px, radii[2 * p]), px1 = __fadd_rn(px, radii[2 * p]);
+    const float py0 = __fsub_rn(py, radii[2 * p + 1]), py1 = __fadd_rn(py, radii[2 * p + 1]);
+    for (int by = 0; by < B; ++by) {
+      const float by0 = __fsub_rn(pix_to_ndc(by * bin_size, fS), half);
+      const float by1 = __fadd_rn(pix_to_ndc((by + 1) * bin_size - 1, fS), half);
+      if (!((py0 <= by1) && (by0 <= py1))) continue;
+      for (int bx = 0; bx < B; ++bx) {
+        const float bx0 = __fsub_rn(pix_to_ndc(bx * bin_size, fS), half);
+        const float bx1 = __fadd_rn(pix_to_ndc((bx + 1) * bin_size - 1, fS), half);
+        if ((px0 <= bx1) && (bx0 <= px1)) atomicAdd(&bin_cnt[((size_t)n * B + by) * B + bx], 1);
+      }
+    }
+  }
+}
+
+template <int K>
+static void launch_raster(int tiles, cudaStream_t st, const float4* recs, const int* off, const int* cnt,
+                          int S, int T, float thres, int occ_incl, int* oi, float* oz, float* oq,
+                          float* oo) {
+  splat_raster_kernel<K><<<tiles, 256, 0, st>>>(recs, off, cnt, S, T, thres, occ_incl, oi, oz, oq, oo);
+}
+
+struct SplatWs {
+  int* tile_cnt;
+  int* tile_off;
+  int* tile_cur;
+  int* total;
+  void* scan_ws;
+  size_t scan_bytes;
+  size_t bytes;
+};
+
+static SplatWs carve_splat_ws(void* ws, int N, int S) {
+  const int T = div_up(S, TILE);
+  const size_t nt = (size_t)N * T * T;
+  SplatWs w;
+  size_t off = 0;
+  auto take = [&](size_t b) { void* p = ws ? (char*)ws + off : nullptr; off += align_up(b); return p; };
+  w.tile_cnt = (int*)take(nt * 4);
+  w.tile_cur = (int*)take(nt * 4);     // adjacent to tile_cnt: one memset clears both
+  w.tile_off = (int*)take(nt * 4);
+  w.total = (int*)take(4);
+  w.scan_bytes = scan_ws_bytes((int)nt, 1);
+  w.scan_ws = take(w.scan_bytes);
+  w.bytes = off;
+  return w;
+}
+
+}  // namespace isob200
+
+using namespace isob200;
+
+extern "C" {
+
+size_t isob200_splat_ws_bytes(int N, int S) { return carve_splat_ws(nullptr, N, S).bytes; }
+int isob200_splat_record_bytes(void) { return REC_F4 * 16; }
+
+// Phase 1 of DSS._C.splat_points: per-tile record counts + offsets.  total_out (device int)
+// receives the number of (tile, point) records; the caller reads it back once to size `recs`.
+int isob200_splat_bin(const float* points, const float* radii, const int64_t* first_idx,
+                      const int64_t* num_points, int N, long long P, long long max_points_per_cloud,
+                      int S, void* ws, size_t ws_bytes, int* total_out, void* stream_) {
+  cudaStream_t st = (cudaStream_t)stream_;
+  ISO_CHECK_ARG(N >= 0 && S > 0 && P >= 0, "splat_bin: bad sizes");
+  SplatWs w = carve_splat_ws(ws, N, S);
+  if (ws == nullptr || ws_bytes < w.bytes) {
+    set_error("splat_bin: workspace too small (%zu < %zu)", ws_bytes, w.bytes);
+    return ISOB200_ERR_WORKSPACE;
+  }
+  ISO_CHECK_ARG(total_out, "splat_bin: null total_out");
+  const int T = div_up(S, TILE);
+  const size_t nt = (size_t)N * T * T;
+  ISO_CHECK_ARG(nt < (1u << 31), "splat_bin: too many tiles");
+  ISO_CUDA(cudaMemsetAsync(w.tile_cnt, 0, (char*)w.tile_off - (char*)w.tile_cnt, st));
+  if (N > 0 && P > 0 && max_points_per_cloud > 0) {
+    ISO_CHECK_ARG(points && radii && first_idx && num_points, "splat_bin: null pointer");
+    int bx = grid_for(max_points_per_cloud, 256, 8);
+    if (N > 1) bx = max(1, min(bx, (kNumSMs * 8 + N - 1) / N));
+    splat_tile_count_kernel<<<dim3(bx, N), 256, 0, st>>>(points, radii, first_idx, num_points, S, T,
+                                                        w.tile_cnt);
+    ISO_CHECK_LAUNCH("splat_tile_count_kernel");
+  }
+  if (nt > 0) {
+    int rc = exclusive_scan_i32(w.tile_cnt, w.tile_off, (int)nt, 1, (long long)nt, (long long)nt, w.scan_ws,
+                                w.scan_bytes, st);
+    if (rc) return rc;
+  }
+  splat_total_kernel<<<1, 32, 0, st>>>(w.tile_cnt, w.tile_off, (int)nt, w.total);
+  ISO_CHECK_LAUNCH("splat_total_kernel");
+  ISO_CUDA(cudaMemcpyAsync(total_out, w.total, sizeof(int), cudaMemcpyDeviceToDevice, st));
+  return ISOB200_OK;
+}
+
+// Phase 2 of DSS._C.splat_points (rasterize_points.h:461-525): fill the per-tile record lists
+// and rasterise.  `ws` must be the workspace isob200_splat_bin just filled; `recs` holds
+// `capacity` records of isob200_splat_record_bytes() each (capacity >= the total read back).
+// Outputs are fully written: idx int32 (N,S,S,K), zbuf/qvalue f32 (N,S,S,K), occ f32 (N,S,S).
+// occ_inclusive: 1 = naive-kernel rule q_max_z >= 0 (bin_size == 0), 0 = fine-kernel rule > 0.
+int isob200_splat_forward(const float* points, const float* ellipse, const float* cutoff,
+                          const float* radii, const int64_t* first_idx, const int64_t* num_points,
+                          int N, long long P, long long max_points_per_cloud, int S, int K,
+                          float depth_merging_thres, int occ_inclusive, void* ws, size_t ws_bytes,
+                          void* recs, long long capacity, int* out_idx, float* out_zbuf,
+                          float* out_qvalue, float* out_occ, void* stream_) {
+  cudaStream_t st = (cudaStream_t)stream_;
+  ISO_CHECK_ARG(N >= 0 && S > 0 && P >= 0, "splat_forward: bad sizes");
+  ISO_CHECK_ARG(K >= 1 && K <= 150, "Must have points_per_pixel <= 150");
+  if (N == 0) return ISOB200_OK;
+  SplatWs w = carve_splat_ws(ws, N, S);
+  if (ws == nullptr || ws_bytes < w.bytes) {
+    set_error("splat_forward: workspace too small (%zu < %zu)", ws_bytes, w.bytes);
+    return ISOB200_ERR_WORKSPACE;
+  }
+  ISO_CHECK_ARG(out_idx && out_zbuf && out_qvalue && out_occ, "splat_forward: null output");
+  ISO_CHECK_ARG(capacity == 0 || recs, "splat_forward: null record buffer");
+  ISO_CHECK_ARG(((uintptr_t)recs & 15) == 0, "splat_forward: record buffer must be 16-byte aligned");
+  const int T = div_up(S, TILE);
+  const int tiles = N * T * T;
+  if (P > 0 && max_points_per_cloud > 0 && capacity > 0) {
+    ISO_CHECK_ARG(points && ellipse && cutoff && radii && first_idx && num_points, "splat_forward: null pointer");
+    int bx = grid_for(max_points_per_cloud, 256, 8);
+    if (N > 1) bx = max(1, min(bx, (kNumSMs * 8 + N - 1) / N));
+    splat_tile_fill_kernel<<<dim3(bx, N), 256, 0, st>>>(points, ellipse, cutoff, radii, first_idx, num_points,
+                                                       S, T, w.tile_off, w.tile_cur, capacity, (float4*)recs);
+    ISO_CHECK_LAUNCH("splat_tile_fill_kernel");
+  }
+  const float4* r = (const float4*)recs;
+  int* oi = out_idx; float* oz = out_zbuf; float* oq = out_qvalue; float* oo = out_occ;
+  const float th = depth_merging_thres;
+#define RK(KK) case KK: launch_raster<KK>(tiles, st, r, w.tile_off, w.tile_cnt, S, T, th, occ_inclusive, oi, oz, oq, oo); break;
+  switch (K) {
+    RK(1) RK(2) RK(3) RK(4) RK(5) RK(6) RK(7) RK(8) RK(9) RK(10) RK(11) RK(12) RK(13) RK(14) RK(15) RK(16)
+    default:
+      splat_raster_bigk_kernel<<<tiles, 256, 0, st>>>(r, w.tile_off, w.tile_cnt, S, T, K, th, occ_inclusive, oi,
+                                                     oz, oq, oo);
+  }
+#undef RK
+  ISO_CHECK_LAUNCH("splat_raster_kernel");
+  return ISOB200_OK;
+}
+
+// (N,B,B) int32 points_per_bin of the reference's coarse pass, B = 1 + (S-1)/bin_size,
+// indexed [n][by][bx] in NDC bin order like the reference's bin_points (rasterize_points.cu:402-412).
+int isob200_splat_bin_counts(const float* points, const float* radii, const int64_t* first_idx,
+                             const int64_t* num_points, int N, long long max_points_per_cloud, int S,
+                             int bin_size, int* bin_cnt, void* stream_) {
+  cudaStream_t st = (cudaStream_t)stream_;
+  ISO_CHECK_ARG(N >= 0 && S > 0 && bin_size > 0, "splat_bin_counts: bad sizes");
+  const int B = 1 + (S - 1) / bin_size;
+  if (N == 0) return ISOB200_OK;
+  ISO_CHECK_ARG(bin_cnt, "splat_bin_counts: null output");
+  ISO_CUDA(cudaMemsetAsync(bin_cnt, 0, (size_t)N * B * B * sizeof(int), st));
+  if (max_points_per_cloud <= 0) return ISOB200_OK;
+  int bx = grid_for(max_points_per_cloud, 256, 8);
+  if (N > 1) bx = max(1, min(bx, (kNumSMs * 8 + N - 1) / N));
+  splat_bin_count_kernel<<<dim3(bx, N), 256, 0, st>>>(points, radii, first_idx, num_points, S, bin_size, B,
+                                                     bin_cnt);
+  ISO_CHECK_LAUNCH("splat_bin_count_kernel");
+  return ISOB200_OK;
+}
+
+}  // extern "C"

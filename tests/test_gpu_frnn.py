@@ -62,6 +62,25 @@ def test_frnn_small_bit_exact_vs_oracle(D, K):
     assert np.array_equal(grid.sorted_points2.cpu().numpy(), sp)
 
 
+def test_frnn_multi_tile_multi_pass_build():
+    """Several radix tiles x 3 digit passes in the deterministic grid build (N*G > 2^16)."""
+    rng = np.random.RandomState(77)
+    pts = rng.rand(2, 5000, 3).astype(np.float32)
+    lens = np.array([5000, 4100])
+    rs = np.array([0.03, 0.045], np.float32)
+    t = torch.as_tensor(pts, device=DEV)
+    l = torch.as_tensor(lens, device=DEV)
+    d, i, _, grid = frnn.frnn_grid_points(t, t, l, l, K=8, r=torch.as_tensor(rs))
+    params, G = port.frnn_grid_params(pts, lens, rs)
+    assert 2 * G > (1 << 16)
+    sp, off, sidx = port.frnn_build_grid(pts, lens, params, G)
+    assert np.array_equal(grid.pc2_grid_off.cpu().numpy(), off)
+    assert np.array_equal(grid.sorted_points2_idxs.cpu().numpy(), sidx)
+    assert np.array_equal(grid.sorted_points2.cpu().numpy(), sp)
+    want_i, want_d = port.frnn_bruteforce(pts, pts, lens, lens, K=8, r=rs)
+    assert np.array_equal(i.cpu().numpy(), want_i) and np.array_equal(d.cpu().numpy(), want_d)
+
+
 def test_frnn_two_clouds_and_grid_reuse():
     rng = np.random.RandomState(5)
     p1 = rng.rand(1, 400, 3).astype(np.float32) * 1.2 - 0.1      # queries partly outside the grid
@@ -174,12 +193,19 @@ def test_frnn_500k_bit_exact_vs_reference_cuda(shape):
     ri, rd, rsp2, roff, rsidx, rparams = ref_native.frnn_grid_points_cuda(p, p, lens, lens, 16, r)
     assert torch.equal(grid.grid_params, rparams)
     assert torch.equal(grid.pc2_grid_off, roff)
-    # tie-free input => the reference is deterministic and must be matched bit for bit
+    # distances must match bit for bit everywhere; indices too, except inside a run of EXACTLY equal
+    # distances (a handful of genuine fp32 ties at this size), where the reference's order is its
+    # atomic insertion order (mink.cuh:64) and ours is ascending index -- there the sets must agree
     full = d[0, :, -1] >= 0
-    ties = (d[0, :, 1:] == d[0, :, :-1]) & (d[0, :, 1:] >= 0)
-    assert int(ties.sum()) == 0
-    assert torch.equal(i, ri)
     assert torch.equal(d, rd)
+    tie = torch.zeros_like(d[0], dtype=torch.bool)
+    eq = (d[0, :, 1:] == d[0, :, :-1]) & (d[0, :, 1:] >= 0)
+    tie[:, 1:] |= eq
+    tie[:, :-1] |= eq
+    assert int(eq.sum()) < 50
+    assert torch.equal(i[0][~tie], ri[0][~tie])
+    rows = tie.any(-1)
+    assert torch.equal(i[0][rows].sort(-1).values, ri[0][rows].sort(-1).values)
     # size-independent properties
     assert (i[0, :, 0] == torch.arange(500_000, device=DEV)).all()          # self is nearest
     dd = torch.where(d < 0, torch.full_like(d, float("inf")), d)
