@@ -1,0 +1,117 @@
+"""Second headline metric of BASELINE.json: pixel-splats / second, config C4
+(8 views x 300 000 iso-point splats, 512^2, K = 8, sigma = 1.5 px, fwd and fwd+bwd).
+Called by bench.py (rank 0, N = 1) and runnable alone:  python bench_splat.py"""
+import json
+import os
+import sys
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+V, PV, S, K = 8, 300_000, 512, 8
+
+
+def _inputs(dev):
+    from tests.helpers import make_splat_inputs
+    inp = make_splat_inputs(V, PV, S, seed=0, sigma_px=1.5, aniso=False, behind_frac=0.0)
+    return {k: torch.as_tensor(v) for k, v in inp.items()}
+
+
+def run(args, dev, peaks, peak_src, steps=None):
+    from isopoints_b200 import _ext, splat
+    lib = _ext.lib()
+    steps = steps or max(3, args.steps)
+    host = _inputs(dev)
+    pin = {k: v.pin_memory() for k, v in host.items()}
+    t = {k: v.to(dev) for k, v in host.items()}
+    g = torch.Generator().manual_seed(0)
+    occ_grad = (torch.randn(V, S, S, generator=g) * (torch.rand(V, S, S, generator=g) < 0.1)).to(dev)
+    zbuf_grad = torch.randn(V, S, S, K, generator=g).to(dev)
+    rgb = torch.rand(V * PV, 3, generator=g).to(dev)
+    scaler = (torch.rand(V * PV, generator=g) + 0.5).to(dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    n_pairs = splat.count_pixel_splats(t["points"], t["ellipse"], t["cutoff"], t["radii"], S)
+
+    def fwd(tt, pts):
+        return splat.EllipticalRasterizer.apply(pts, tt["ellipse"], tt["cutoff"], tt["radii"], tt["first_idx"],
+                                                tt["num_points"], 0.05, S, K, 32, 0, 10.0)
+
+    def fwd_bwd(tt):
+        pts = tt["points"].detach().requires_grad_(True)
+        idx, zbuf, qv, occ = fwd(tt, pts)
+        img = splat.blend_rgba(idx, qv, occ, scaler, rgb)
+        ((occ * occ_grad).sum() + (zbuf * zbuf_grad).sum()).backward()
+        return img, pts.grad
+
+    for _ in range(3):
+        fwd_bwd(t)
+    torch.cuda.synchronize()
+
+    def timed(fn, n):
+        ms = 0.0
+        for k in range(n):
+            flush.fill_(k & 0xff)
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(); fn(); b.record()
+            torch.cuda.synchronize()
+            ms += a.elapsed_time(b)
+        return ms / n
+
+    with torch.no_grad():
+        ms_fwd = timed(lambda: fwd(t, t["points"]), steps)
+    _ext.PROFILE = {}
+    l0 = lib.isob200_launch_count()
+    ms_fb = timed(lambda: fwd_bwd(t), steps)
+    launches = (lib.isob200_launch_count() - l0) / steps
+    prof, _ext.PROFILE = _ext.PROFILE, None
+    kern = {n.replace("isob200_", ""): {"calls_per_step": len(p) / steps, "avg_ms": sum(a.elapsed_time(b) for a, b in p) / len(p)}
+            for n, p in prof.items()}
+
+    def e2e():
+        tt = {k: v.to(dev, non_blocking=True) for k, v in pin.items()}
+        img, grad = fwd_bwd(tt)
+        return img.cpu(), grad.cpu()
+    e2e()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        img, grad = e2e()
+    torch.cuda.synchronize()
+    ms_e2e = (time.perf_counter() - t0) / steps * 1e3
+    h2d = sum(v.numel() * v.element_size() for v in pin.values())
+    d2h = img.numel() * 4 + grad.numel() * 4
+
+    # dominant kernel: the raster kernel inside splat_forward; algorithmic bytes per launch
+    # (SURVEY 8d): 36 B per point in + (12K + 4) B per pixel out
+    alg = 36 * V * PV + (12 * K + 4) * V * S * S
+    f = kern.get("splat_forward")
+    roof = None
+    if f:
+        ach = alg / (f["avg_ms"] * 1e-3) / 1e9
+        roof = {"kernel": "splat_tile_fill + splat_raster_kernel<8>", "bound": "hbm", "achieved": ach,
+                "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": ach / peaks["hbm_gbs"], "traffic": None,
+                "peak_source": peak_src, "algorithmic_bytes_per_launch": alg, "avg_launch_ms": f["avg_ms"]}
+    return {"metric": "pixel-splats/sec", "unit": "pixel-splats/s",
+            "config": {"workload": "C4: %d views x %d splats, %dx%d, K=%d, sigma=1.5px, occ_grad on 10%% of pixels, "
+                                   "radii_backward_scaler=10" % (V, PV, S, S, K), "l2": "flushed between steps"},
+            "pixel_splats_per_call": n_pairs,
+            "value_fwd": n_pairs / (ms_fwd * 1e-3), "ms_fwd": ms_fwd,
+            "value": n_pairs / (ms_fb * 1e-3), "ms_fwd_blend_bwd": ms_fb,
+            "e2e": {"value": n_pairs / (ms_e2e * 1e-3), "unit": "pixel-splats/s", "ms_per_step": ms_e2e,
+                    "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+            "gpu_launches_per_step": launches, "roofline": roof, "kernels": kern}
+
+
+if __name__ == "__main__":
+    import argparse
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--steps", type=int, default=5)
+    a = ap.parse_args()
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))); src = "measured"
+    except Exception:
+        peaks, src = {"hbm_gbs": 6650.0}, "fallback"
+    print(json.dumps(run(a, torch.device("cuda", 0), peaks, src)))

@@ -86,6 +86,56 @@ int isob200_resample_step(const float* points, const float* normals, const void*
                           float* out, void* stream);
 int isob200_normalize_rows3(const float* x, long long M, float eps, float* out, void* stream);
 
+/* ---- DSS elliptical splat rasteriser, forward: DSS._C.splat_points
+ *      (DSS/csrc/rasterize_points.h:461-525 -> RasterizePoints{Naive,Coarse,Fine}Cuda,
+ *      rasterize_points.cu:214-285, 434-500, 599-667).  Two phases because the per-tile record
+ *      buffer is sized from a device-computed total (one 4-byte read-back by the caller). ---- */
+size_t isob200_splat_ws_bytes(int N, int S);
+int isob200_splat_record_bytes(void);
+int isob200_splat_bin(const float* points, const float* radii, const int64_t* first_idx,
+                      const int64_t* num_points, int N, long long P, long long max_points_per_cloud,
+                      int S, void* ws, size_t ws_bytes, int* total_out, void* stream);
+int isob200_splat_forward(const float* points, const float* ellipse, const float* cutoff,
+                          const float* radii, const int64_t* first_idx, const int64_t* num_points,
+                          int N, long long P, long long max_points_per_cloud, int S, int K,
+                          float depth_merging_thres, int occ_inclusive, void* ws, size_t ws_bytes,
+                          void* recs, long long capacity, int* out_idx, float* out_zbuf,
+                          float* out_qvalue, float* out_occ, void* stream);
+/* points_per_bin of the reference's coarse pass (rasterize_points.cu:353-412; computed there,
+ * never returned) -- for the "per-tile point counts bit-exact" parity check */
+int isob200_splat_bin_counts(const float* points, const float* radii, const int64_t* first_idx,
+                             const int64_t* num_points, int N, long long max_points_per_cloud, int S,
+                             int bin_size, int* bin_cnt, void* stream);
+
+/* number of (pixel, point) pairs passing CheckPixelInsidePoint (rasterize_points.cu:64-98): the
+ * "pixel-splat" unit of the throughput metric */
+int isob200_splat_count_pairs(const float* points, const float* ellipse, const float* cutoff,
+                              const float* radii, long long P, int S, unsigned long long* total_out,
+                              void* stream);
+
+/* ---- splat backward: DSS._C._splat_points_occ_fast_cuda_backward (rasterize_points.h:327-336,
+ *      rasterize_points_backward.cu:227-322; mode 0), DSS._C._splat_points_occ_backward
+ *      (rasterize_points.h:341-386; mode 1), DSS._C._backward_zbuf (rasterize_points.h:388-419),
+ *      per-point visibility (DSS/utils/__init__.py:378-399; DSS/core/rasterizer.py:851-857) ---- */
+int isob200_splat_occ_backward(const float* points, const float* radii, const unsigned char* visible,
+                               const int64_t* first_idx, const int64_t* num_points, const float* rs,
+                               float radii_s, const float* grad_occ, int N, int H, int W,
+                               long long max_points_per_cloud, int mode, float* grad_out, int out_stride,
+                               void* stream);
+int isob200_splat_zbuf_backward(const int* idx, const float* grad_zbuf, int N, int H, int W, int K,
+                                float* z_grad, int stride, void* stream);
+int isob200_splat_visibility(const int* idx, const float* mask, long long npix, int K, long long P,
+                             unsigned char* visible, void* stream);
+
+/* ---- RGBA blend: SurfaceSplattingRenderer.forward (DSS/core/renderer.py:53-78: exp(-Q/2)*scaler
+ *      weights + pytorch3d NormWeightedCompositor + occupancy as alpha) and its feature gradient */
+int isob200_splat_blend(const int* idx, const float* qvalue, const float* occ, const float* scaler,
+                        const float* feat, int feat_stride, long long npix, int K, int C, float eps,
+                        float* out, float* weights_out, void* stream);
+int isob200_splat_blend_backward(const int* idx, const float* weights, const float* grad_out,
+                                 long long npix, int K, int C, float eps, float* grad_feat,
+                                 int feat_stride, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

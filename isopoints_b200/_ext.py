@@ -42,6 +42,19 @@ _PROTOS = {
     "isob200_project_sphere": (_i, [_vp, _vp, _vp, _ll, _f, _f, _f, _i, _vp]),
     "isob200_resample_step": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp, _i, _i, _i, _vp, _vp]),
     "isob200_normalize_rows3": (_i, [_vp, _ll, _f, _vp, _vp]),
+    "isob200_splat_ws_bytes": (_sz, [_i, _i]),
+    "isob200_splat_record_bytes": (_i, []),
+    "isob200_splat_bin": (_i, [_vp, _vp, _vp, _vp, _i, _ll, _ll, _i, _vp, _sz, _vp, _vp]),
+    "isob200_splat_forward": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _ll, _ll, _i, _i, _f, _i, _vp, _sz,
+                                   _vp, _ll, _vp, _vp, _vp, _vp, _vp]),
+    "isob200_splat_bin_counts": (_i, [_vp, _vp, _vp, _vp, _i, _ll, _i, _i, _vp, _vp]),
+    "isob200_splat_count_pairs": (_i, [_vp, _vp, _vp, _vp, _ll, _i, _vp, _vp]),
+    "isob200_splat_occ_backward": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _f, _vp, _i, _i, _i, _ll, _i, _vp, _i,
+                                        _vp]),
+    "isob200_splat_zbuf_backward": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _i, _vp]),
+    "isob200_splat_visibility": (_i, [_vp, _vp, _ll, _i, _ll, _vp, _vp]),
+    "isob200_splat_blend": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _ll, _i, _i, _f, _vp, _vp, _vp]),
+    "isob200_splat_blend_backward": (_i, [_vp, _vp, _vp, _ll, _i, _i, _f, _vp, _i, _vp]),
 }
 
 _LIB = None
@@ -51,7 +64,7 @@ _RAW = None
 # bracketed by CUDA events on the stream it is launched on; PROFILE[name] collects (start, end).
 PROFILE = None
 _NO_TIMING = ("_ws_bytes", "isob200_last_error", "isob200_abi_version", "isob200_compiled_arch",
-              "isob200_launch_count")
+              "isob200_launch_count", "isob200_splat_record_bytes")
 
 
 class _Lib:

@@ -410,6 +410,39 @@ splat_bin_count_kernel(const float* __restrict__ points, const float* __restrict
   }
 }
 
+// number of (pixel, point) pairs that pass CheckPixelInsidePoint -- the "pixel-splat" unit of the
+// throughput metric.  One thread per point sweeps the point's own pixel window.
+__global__ void __launch_bounds__(256)
+splat_pair_count_kernel(const float* __restrict__ points, const float* __restrict__ ellipse,
+                        const float* __restrict__ cutoff, const float* __restrict__ radii, long long P,
+                        int S, unsigned long long* __restrict__ total) {
+  const float fS = (float)S;
+  unsigned long long mine = 0;
+  for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < P;
+       p += (long long)gridDim.x * blockDim.x) {
+    const float px = points[3 * p], py = points[3 * p + 1], pz = points[3 * p + 2];
+    if (!(pz >= 0.0f)) continue;
+    const float rx = radii[2 * p], ry = radii[2 * p + 1];
+    const float a = ellipse[3 * p], b = ellipse[3 * p + 1], c = ellipse[3 * p + 2], cut = cutoff[p];
+    int xl, xh, yl, yh;
+    pixel_range(px, rx, S, fS, xl, xh);
+    pixel_range(py, ry, S, fS, yl, yh);
+    for (int yi = yl; yi <= yh; ++yi) {
+      const float dy = __fsub_rn(pix_to_ndc(yi, fS), py);
+      if (fabsf(dy) > ry) continue;
+      for (int xi = xl; xi <= xh; ++xi) {
+        const float dx = __fsub_rn(pix_to_ndc(xi, fS), px);
+        if (fabsf(dx) > rx) continue;
+        const float q = __fmaf_rn(__fmul_rn(c, dy), dy, __fmaf_rn(__fmul_rn(a, dx), dx, __fmul_rn(__fmul_rn(b, dx), dy)));
+        if (!(q > cut)) ++mine;
+      }
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mine += __shfl_xor_sync(0xffffffffu, mine, o);
+  if ((threadIdx.x & 31) == 0 && mine) atomicAdd(total, mine);
+}
+
 template <int K>
 static void launch_raster(int tiles, cudaStream_t st, const float4* recs, const int* off, const int* cnt,
                           int S, int T, float thres, int occ_incl, int* oi, float* oz, float* oq,
@@ -533,6 +566,20 @@ int isob200_splat_forward(const float* points, const float* ellipse, const float
   }
 #undef RK
   ISO_CHECK_LAUNCH("splat_raster_kernel");
+  return ISOB200_OK;
+}
+
+// total_out (device uint64, zeroed here) = number of pixel-splats of the packed splat set.
+int isob200_splat_count_pairs(const float* points, const float* ellipse, const float* cutoff,
+                              const float* radii, long long P, int S, unsigned long long* total_out,
+                              void* stream_) {
+  cudaStream_t st = (cudaStream_t)stream_;
+  ISO_CHECK_ARG(total_out && S > 0 && P >= 0, "splat_count_pairs: bad argument");
+  ISO_CUDA(cudaMemsetAsync(total_out, 0, sizeof(unsigned long long), st));
+  if (P == 0) return ISOB200_OK;
+  ISO_CHECK_ARG(points && ellipse && cutoff && radii, "splat_count_pairs: null pointer");
+  splat_pair_count_kernel<<<grid_for(P, 256, 8), 256, 0, st>>>(points, ellipse, cutoff, radii, P, S, total_out);
+  ISO_CHECK_LAUNCH("splat_pair_count_kernel");
   return ISOB200_OK;
 }
 

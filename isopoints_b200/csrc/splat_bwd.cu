@@ -1,0 +1,301 @@
+// DSS elliptical-splat rasteriser: backward, per-point visibility and the fused RGBA blend, sm_100a.
+//
+// Replaces
+//   DSS/csrc/rasterize_points_backward.cu:30-212  RasterizePointsBackwardCudaFastKernel
+//   DSS/csrc/rasterize_points.cu:673-760          RasterizePointsOccBackwardCudaKernel (slow path)
+//   DSS/csrc/rasterize_points.cu:823-846          ZbufBackwardKernel
+//   DSS/utils/__init__.py:378-399                 get_per_point_visibility_mask (unique + scatter)
+//   DSS/core/renderer.py:53-78                    exp(-Q/2)*scaler weights + pytorch3d
+//                                                 NormWeightedCompositor + alpha concat
+//
+// Occupancy backward -- B200 design.  The reference is PIXEL-centric: one thread per pixel with
+// grad_occ != 0 walks a 2-D FRNN grid of the visible points (built per call with insert / scan /
+// counting-sort through frnn._C and a python loop) and issues two fp32 atomics per (pixel, point)
+// pair -- ~800 pairs per pixel at the default radii_backward_scaler = 10, nondeterministic sums.
+// The pair relation is symmetric, so here it is POINT-centric: one WARP per visible point sweeps
+// the (2r+1)^2 pixel window of grad_occ around the point with coalesced row reads (the 1 MB
+// grad_occ image of a view stays L2 resident), accumulates in registers, and finishes with a
+// warp-shuffle reduction and ONE plain store per coordinate: no grid build, no atomics,
+// run-to-run deterministic.  The predicate per (pixel, point) pair is the reference's, in its
+// fp32 form (dist2 = fma(dy, dy, dx*dx) <= r^2, ...), so the set of contributing pairs is equal.
+// NOT reproduced: the reference closes the last 2-D grid cell of views n >= 1 with a local count
+// while its offsets are packed-global (rasterize_points_backward.cu:124-126), silently dropping
+// that cell's points; here every in-radius pair contributes.
+#include "common.cuh"
+#include <float.h>
+
+namespace isob200 {
+
+__device__ __forceinline__ float pix_to_ndc_b(int i, float fS) {
+  return __fadd_rn(__fdiv_rn(__fadd_rn((float)(2 * i), 1.0f), fS), -1.0f);
+}
+
+// pixel indices i in [0,S) that can satisfy |ndc(i) - p| <= r  (superset, lo > hi when empty)
+__device__ __forceinline__ void pixel_window(float p, float r, int S, float fS, int& lo, int& hi) {
+  const float e_lo = (p - r + 1.0f) * fS * 0.5f - 0.5f;
+  const float e_hi = (p + r + 1.0f) * fS * 0.5f - 0.5f;
+  if (!(e_lo <= (float)S) || !(e_hi >= -1.0f)) { lo = 1; hi = 0; return; }
+  lo = (int)fmaxf(ceilf(e_lo) - 1.0f, 0.0f);
+  hi = (int)fminf(floorf(e_hi) + 1.0f, (float)(S - 1));
+}
+
+// rasterization_utils.cuh:38-44 (device eps_denom): sign(0) = 0, unlike the python helper
+__device__ __forceinline__ float eps_denom_dev(float d, float eps) {
+  const float s = (float)((0.0f < d) - (d < 0.0f));
+  return __fmul_rn(s, fmaxf(fabsf(d), eps));
+}
+
+// mode 0: fast-path semantics (rasterize_points_backward.cu): radius rs[n], circle test.
+// mode 1: slow-path semantics (rasterize_points.cu:673-760): per-point box radii * radii_s.
+template <int MODE>
+__global__ void __launch_bounds__(256)
+splat_occ_backward_kernel(const float* __restrict__ points, const float* __restrict__ radii,
+                          const unsigned char* __restrict__ visible,
+                          const int64_t* __restrict__ first_idx, const int64_t* __restrict__ num_points,
+                          const float* __restrict__ rs, float radii_s, const float* __restrict__ grad_occ,
+                          int H, int W, float* __restrict__ grad_out, int out_stride) {
+  const int n = blockIdx.y;
+  const long long first = first_idx[n], num = num_points[n];
+  const int lane = threadIdx.x & 31;
+  const long long warps = (long long)gridDim.x * (blockDim.x >> 5);
+  const float fW = (float)W, fH = (float)H;
+  const float* g_img = grad_occ + (size_t)n * H * W;
+  for (long long i = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); i < num; i += warps) {
+    const long long p = first + i;
+    float gx = 0.f, gy = 0.f;
+    const float px = points[3 * p], py = points[3 * p + 1], pz = points[3 * p + 2];
+    const bool live = (visible == nullptr || visible[p]) && !(pz < 0.f || fabsf(py) > 1.0f || fabsf(px) > 1.0f);
+    if (live) {
+      const float rx = radii[2 * p], ry = radii[2 * p + 1];
+      float wx, wy, r2 = 0.f, bx = rx, by = ry;
+      if (MODE == 0) {
+        const float r = rs[n];
+        r2 = __fmul_rn(r, r);
+        wx = wy = r;
+      } else {
+        wx = __fmul_rn(rx, radii_s);           // radiix (:724-725)
+        wy = __fmul_rn(ry, radii_s);
+        bx = __fdiv_rn(wx, radii_s);           // radiix / radii_s (:741)
+        by = __fdiv_rn(wy, radii_s);
+      }
+      int xl, xh, yl, yh;
+      pixel_window(px, wx, W, fW, xl, xh);
+      pixel_window(py, wy, H, fH, yl, yh);
+      if (xl <= xh && yl <= yh) {
+        const int c_lo = W - 1 - xh, c_hi = W - 1 - xl;   // output columns (x is flipped)
+        for (int yi = yl; yi <= yh; ++yi) {
+          const float dy = __fsub_rn(pix_to_ndc_b(yi, fH), py);
+          if (MODE == 1 && fabsf(dy) > wy) continue;
+          const float* g_row = g_img + (size_t)(H - 1 - yi) * W;
+          for (int col = c_lo + lane; col <= c_hi; col += 32) {
+            const float g = g_row[col];
+            if (g == 0.0f) continue;
+            const float dx = __fsub_rn(pix_to_ndc_b(W - 1 - col, fW), px);
+            const float d2 = __fmaf_rn(dy, dy, __fmul_rn(dx, dx));
+            if (MODE == 0) {
+              if (d2 > r2) continue;
+            } else {
+              if (fabsf(dx) > wx) continue;
+            }
+            const bool outside = (fabsf(dx) > bx) || (fabsf(dy) > by);
+            if (g > 0.0f && outside) continue;
+            const float den = eps_denom_dev(d2, 1e-10f);
+            gx += __fmul_rn(__fdiv_rn(dx, den), g);
+            gy += __fmul_rn(__fdiv_rn(dy, den), g);
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      gx += __shfl_xor_sync(0xffffffffu, gx, o);
+      gy += __shfl_xor_sync(0xffffffffu, gy, o);
+    }
+    if (lane == 0) {
+      grad_out[(size_t)p * out_stride + 0] = gx;
+      grad_out[(size_t)p * out_stride + 1] = gy;
+    }
+  }
+}
+
+// z_grad[idx] += grad_zbuf; zero gradients skipped, stop at the first -1 (rasterize_points.cu:835-843)
+__global__ void __launch_bounds__(256)
+splat_zbuf_backward_kernel(const int* __restrict__ idx, const float* __restrict__ grad_zbuf,
+                           long long npix, int K, float* __restrict__ z_grad, int stride) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < npix;
+       i += (long long)gridDim.x * blockDim.x) {
+    for (int k = 0; k < K; ++k) {
+      const float g = grad_zbuf[i * K + k];
+      if (g == 0.0f) continue;
+      const int p = idx[i * K + k];
+      if (p < 0) break;
+      atomicAdd(z_grad + (size_t)p * stride, g);
+    }
+  }
+}
+
+// visible[p] = 1 for every id in any of the K slots of an "active" pixel:
+//   mask == nullptr: active <=> idx[pixel, 0] >= 0   (EllipticalRasterizer.backward, rasterizer.py:851-857)
+//   mask != nullptr: active <=> mask[pixel] != 0     (occupancy: get_per_point_visibility_mask)
+__global__ void __launch_bounds__(256)
+splat_visibility_kernel(const int* __restrict__ idx, const float* __restrict__ mask, long long npix, int K,
+                        long long P, unsigned char* __restrict__ visible) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < npix * K;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long pix = i / K;
+    const bool active = mask ? (mask[pix] != 0.0f) : (idx[pix * K] >= 0);
+    const int p = idx[i];
+    if (active && p >= 0 && p < P) visible[p] = 1;
+  }
+}
+
+// RGBA = [ sum_k w_k f[idx_k] / max(sum_k w_k, eps) , occ ],  w_k = exp(-0.5 q_k) * scaler[idx_k]
+// over slots with idx >= 0 (renderer.py:53-78; the normalisation is pytorch3d's norm_weighted_sum).
+// Optionally stores the weights (N,S,S,K) for the backward.
+template <int C>
+__global__ void __launch_bounds__(256)
+splat_blend_kernel(const int* __restrict__ idx, const float* __restrict__ qvalue,
+                   const float* __restrict__ occ, const float* __restrict__ scaler,
+                   const float* __restrict__ feat, int feat_stride, long long npix, int K, float eps,
+                   float* __restrict__ out, float* __restrict__ weights_out) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < npix;
+       i += (long long)gridDim.x * blockDim.x) {
+    float acc[C];
+#pragma unroll
+    for (int c = 0; c < C; ++c) acc[c] = 0.f;
+    float sw = 0.f;
+    for (int k = 0; k < K; ++k) {
+      const int p = idx[i * K + k];
+      float w = 0.f;
+      if (p >= 0) {
+        w = expf(-0.5f * qvalue[i * K + k]) * (scaler ? scaler[p] : 1.0f);
+        sw += w;
+#pragma unroll
+        for (int c = 0; c < C; ++c) acc[c] += w * feat[(size_t)p * feat_stride + c];
+      }
+      if (weights_out) weights_out[i * K + k] = w;
+    }
+    const float den = fmaxf(sw, eps);
+#pragma unroll
+    for (int c = 0; c < C; ++c) out[i * (C + 1) + c] = acc[c] / den;
+    out[i * (C + 1) + C] = occ[i];
+  }
+}
+
+// d RGBA / d feat: grad_feat[idx_k, c] += w_k / max(sum w, eps) * grad_out[c]
+template <int C>
+__global__ void __launch_bounds__(256)
+splat_blend_backward_kernel(const int* __restrict__ idx, const float* __restrict__ weights,
+                            const float* __restrict__ grad_out, long long npix, int K, float eps,
+                            float* __restrict__ grad_feat, int feat_stride) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < npix;
+       i += (long long)gridDim.x * blockDim.x) {
+    float sw = 0.f;
+    for (int k = 0; k < K; ++k) sw += (idx[i * K + k] >= 0) ? weights[i * K + k] : 0.f;
+    const float inv = 1.0f / fmaxf(sw, eps);
+    float g[C];
+#pragma unroll
+    for (int c = 0; c < C; ++c) g[c] = grad_out[i * (C + 1) + c];
+    for (int k = 0; k < K; ++k) {
+      const int p = idx[i * K + k];
+      if (p < 0) continue;
+      const float a = weights[i * K + k] * inv;
+#pragma unroll
+      for (int c = 0; c < C; ++c) atomicAdd(&grad_feat[(size_t)p * feat_stride + c], a * g[c]);
+    }
+  }
+}
+
+}  // namespace isob200
+
+using namespace isob200;
+
+extern "C" {
+
+// == DSS._C._splat_points_occ_fast_cuda_backward + the python that feeds it
+//    (rasterizer.py:850-966; rasterize_points_backward.cu:227-322) when mode == 0, and
+// == DSS._C._splat_points_occ_backward (rasterize_points.h:341-386) when mode == 1.
+//   visible : (P,) uint8 from isob200_splat_visibility, or NULL = every point participates
+//   rs      : (N,) per-view search radius (mode 0);  radii_s: box scale (mode 1)
+//   grad_out: rows of `out_stride` floats; columns 0,1 of EVERY row are written (0 when the point
+//             does not participate), so the caller needs no zero fill.
+int isob200_splat_occ_backward(const float* points, const float* radii, const unsigned char* visible,
+                               const int64_t* first_idx, const int64_t* num_points, const float* rs,
+                               float radii_s, const float* grad_occ, int N, int H, int W,
+                               long long max_points_per_cloud, int mode, float* grad_out, int out_stride,
+                               void* stream_) {
+  cudaStream_t st = (cudaStream_t)stream_;
+  ISO_CHECK_ARG(N >= 0 && H > 0 && W > 0 && out_stride >= 2, "splat_occ_backward: bad sizes");
+  ISO_CHECK_ARG(mode == 0 || mode == 1, "splat_occ_backward: mode must be 0 (fast) or 1 (slow)");
+  if (N == 0 || max_points_per_cloud <= 0) return ISOB200_OK;
+  ISO_CHECK_ARG(points && radii && first_idx && num_points && grad_occ && grad_out, "splat_occ_backward: null pointer");
+  ISO_CHECK_ARG(mode == 1 || rs, "splat_occ_backward: null rs");
+  long long need = (max_points_per_cloud + 7) / 8;          // 8 warps (points) per CTA
+  int bx = (int)min(need, (long long)kNumSMs * 8 * 8);
+  if (N > 1) bx = max(1, min(bx, (kNumSMs * 8 * 8 + N - 1) / N));
+  if (mode == 0)
+    splat_occ_backward_kernel<0><<<dim3(bx, N), 256, 0, st>>>(points, radii, visible, first_idx, num_points, rs,
+                                                             radii_s, grad_occ, H, W, grad_out, out_stride);
+  else
+    splat_occ_backward_kernel<1><<<dim3(bx, N), 256, 0, st>>>(points, radii, visible, first_idx, num_points, rs,
+                                                             radii_s, grad_occ, H, W, grad_out, out_stride);
+  ISO_CHECK_LAUNCH("splat_occ_backward_kernel");
+  return ISOB200_OK;
+}
+
+// == DSS._C._backward_zbuf (rasterize_points.h:388-419): in place, z_grad[p*stride] += ...
+int isob200_splat_zbuf_backward(const int* idx, const float* grad_zbuf, int N, int H, int W, int K,
+                                float* z_grad, int stride, void* stream_) {
+  cudaStream_t st = (cudaStream_t)stream_;
+  const long long npix = (long long)N * H * W;
+  if (npix == 0 || K == 0) return ISOB200_OK;
+  ISO_CHECK_ARG(idx && grad_zbuf && z_grad && stride >= 1, "splat_zbuf_backward: bad argument");
+  splat_zbuf_backward_kernel<<<grid_for(npix, 256, 8), 256, 0, st>>>(idx, grad_zbuf, npix, K, z_grad, stride);
+  ISO_CHECK_LAUNCH("splat_zbuf_backward_kernel");
+  return ISOB200_OK;
+}
+
+// visible (P,) uint8 must be zero-initialised by the caller.
+int isob200_splat_visibility(const int* idx, const float* mask, long long npix, int K, long long P,
+                             unsigned char* visible, void* stream_) {
+  cudaStream_t st = (cudaStream_t)stream_;
+  if (npix == 0 || K == 0 || P == 0) return ISOB200_OK;
+  ISO_CHECK_ARG(idx && visible, "splat_visibility: null pointer");
+  splat_visibility_kernel<<<grid_for(npix * K, 256, 8), 256, 0, st>>>(idx, mask, npix, K, P, visible);
+  ISO_CHECK_LAUNCH("splat_visibility_kernel");
+  return ISOB200_OK;
+}
+
+// out (npix, C+1) = [normalised weighted colour, occ]; C in 1..4.  weights_out may be NULL.
+int isob200_splat_blend(const int* idx, const float* qvalue, const float* occ, const float* scaler,
+                        const float* feat, int feat_stride, long long npix, int K, int C, float eps,
+                        float* out, float* weights_out, void* stream_) {
+  cudaStream_t st = (cudaStream_t)stream_;
+  if (npix == 0) return ISOB200_OK;
+  ISO_CHECK_ARG(idx && qvalue && occ && feat && out, "splat_blend: null pointer");
+  ISO_CHECK_ARG(C >= 1 && C <= 4 && feat_stride >= C, "splat_blend: C must be in [1,4]");
+  const int g = grid_for(npix, 256, 8);
+#define BL(CC) case CC: splat_blend_kernel<CC><<<g, 256, 0, st>>>(idx, qvalue, occ, scaler, feat, feat_stride, npix, K, eps, out, weights_out); break;
+  switch (C) { BL(1) BL(2) BL(3) BL(4) }
+#undef BL
+  ISO_CHECK_LAUNCH("splat_blend_kernel");
+  return ISOB200_OK;
+}
+
+// grad_feat (P, feat_stride) += ; must be zero-initialised by the caller.
+int isob200_splat_blend_backward(const int* idx, const float* weights, const float* grad_out,
+                                 long long npix, int K, int C, float eps, float* grad_feat,
+                                 int feat_stride, void* stream_) {
+  cudaStream_t st = (cudaStream_t)stream_;
+  if (npix == 0) return ISOB200_OK;
+  ISO_CHECK_ARG(idx && weights && grad_out && grad_feat, "splat_blend_backward: null pointer");
+  ISO_CHECK_ARG(C >= 1 && C <= 4 && feat_stride >= C, "splat_blend_backward: C must be in [1,4]");
+  const int g = grid_for(npix, 256, 8);
+#define BB(CC) case CC: splat_blend_backward_kernel<CC><<<g, 256, 0, st>>>(idx, weights, grad_out, npix, K, eps, grad_feat, feat_stride); break;
+  switch (C) { BB(1) BB(2) BB(3) BB(4) }
+#undef BB
+  ISO_CHECK_LAUNCH("splat_blend_backward_kernel");
+  return ISOB200_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,375 @@
+"""Differentiable elliptical-splat rasteriser on libisob200.so.
+
+Mirrors the operator surface of DSS/core/rasterizer.py + DSS/csrc (``DSS._C``) + the blend of
+DSS/core/renderer.py:
+
+* ``_C.splat_points(points, ellipse_params, cutoff_thres, radii, cloud_to_packed_first_idx,
+  num_points_per_cloud, depth_merging_thres, image_size, points_per_pixel, bin_size,
+  max_points_per_bin) -> (idx i32 (N,S,S,K), zbuf, qvalue f32 (N,S,S,K), occ f32 (N,S,S))``
+  (rasterize_points.h:461-525), ``_C._splat_points_naive``, ``_C._backward_zbuf`` (in place),
+  ``_C._splat_points_occ_backward`` and ``_C._splat_points_occ_fast_cuda_backward``;
+* ``rasterize_elliptical_points(...)`` (rasterizer.py:678-740) and the autograd Function
+  ``EllipticalRasterizer`` (rasterizer.py:743-973): gradients only for ``pts_screen`` -- xy from
+  ``occ_grad``, z from ``zbuf_grad``; ``qvalue_grad`` is ignored exactly like the reference;
+* ``blend_rgba`` = ``SurfaceSplattingRenderer.forward``'s weights + NormWeightedCompositor +
+  alpha (renderer.py:53-78) in one kernel, differentiable w.r.t. the point features.
+
+``bin_size`` / ``max_points_per_bin`` are accepted for signature compatibility; they only select
+the occupancy rule (bin_size == 0 is the reference's naive kernel: occupied when z >= 0, otherwise
+the fine kernel's z > 0, rasterize_points.cu:196 vs :581) and the reference's ``num_bins < 22``
+argument check.  The (N,B,B,M) ``bin_points`` matrix is not materialised.
+There is no CPU / PyTorch fallback: CPU tensors raise.
+"""
+from typing import NamedTuple, Optional
+
+import torch
+from torch import autograd
+
+from . import _ext
+
+kMaxPointsPerBin = 22
+kMaxPointsPerPixel = 150
+NORM_WEIGHT_EPS = 1e-4   # pytorch3d norm_weighted_sum kEpsilon [third party, restated]
+
+
+class PointFragments(NamedTuple):
+    """DSS/core/rasterizer.py:31-36."""
+    idx: torch.Tensor
+    zbuf: torch.Tensor
+    qvalue: torch.Tensor
+    scaler: torch.Tensor
+    occupancy: torch.Tensor
+
+
+def _f32c(t, name):
+    if not t.is_cuda:
+        raise TypeError("%s: for now only cuda version is supported" % name)
+    if t.dtype != torch.float32:
+        raise RuntimeError("%s: expected scalar type Float" % name)
+    return t.contiguous()
+
+
+def _i64c(t, dev):
+    return t.to(device=dev, dtype=torch.int64).contiguous()
+
+
+def _check_inputs(points, ellipse, cutoff, radii, first_idx, num_points):
+    """Shape checks of rasterize_points.h:470-486 (torch::checkDim / checkSize -> RuntimeError)."""
+    if points.dim() != 2 or points.shape[1] != 3:
+        raise RuntimeError("Expected 2-dimensional tensor of size (P, 3) for points, got %s" % (tuple(points.shape),))
+    P = points.shape[0]
+    if ellipse.dim() != 2 or tuple(ellipse.shape) != (P, 3):
+        raise RuntimeError("Expected ellipse_params of size (%d, 3), got %s" % (P, tuple(ellipse.shape)))
+    if radii.dim() != 2 or tuple(radii.shape) != (P, 2):
+        raise RuntimeError("Expected radii of size (%d, 2), got %s" % (P, tuple(radii.shape)))
+    if cutoff.dim() != 1 or cutoff.shape[0] not in (1, P):
+        raise RuntimeError("Expected cutoff_thres of size (%d,) or (1,), got %s" % (P, tuple(cutoff.shape)))
+    if first_idx.dim() != 1 or num_points.dim() != 1 or first_idx.shape != num_points.shape:
+        raise RuntimeError("cloud_to_packed_first_idx and num_points_per_cloud must be (N,) tensors of equal size")
+
+
+def _splat(points, ellipse, cutoff, radii, first_idx, num_points, depth_merging_thres, S, K, occ_inclusive):
+    _check_inputs(points, ellipse, cutoff, radii, first_idx, num_points)
+    lib = _ext.lib()
+    S, K = int(S), int(K)
+    if K > kMaxPointsPerPixel:
+        raise RuntimeError("Must have points_per_pixel <= %d" % kMaxPointsPerPixel)
+    points = _f32c(points, "points")
+    dev = points.device
+    ellipse = _f32c(ellipse, "ellipse_params")
+    radii = _f32c(radii, "radii")
+    P = points.shape[0]
+    cutoff = _f32c(cutoff.expand(P) if cutoff.shape[0] == 1 and P != 1 else cutoff, "cutoff_thres")
+    first_idx = _i64c(first_idx, dev)
+    num_points = _i64c(num_points, dev)
+    N = num_points.shape[0]
+    idx = torch.empty((N, S, S, K), dtype=torch.int32, device=dev)
+    zbuf = torch.empty((N, S, S, K), dtype=torch.float32, device=dev)
+    qvalue = torch.empty((N, S, S, K), dtype=torch.float32, device=dev)
+    occ = torch.empty((N, S, S), dtype=torch.float32, device=dev)
+    if idx.numel() == 0:
+        return idx, zbuf, qvalue, occ
+    st = _ext.stream(dev)
+    ws = _ext.workspace(lib.isob200_splat_ws_bytes(N, S), dev)
+    total = torch.empty((1,), dtype=torch.int32, device=dev)
+    # no view can own more than P points: P is a launch-shape bound that needs no host sync
+    maxp = P
+    _ext.check(lib.isob200_splat_bin(_ext.ptr(points), _ext.ptr(radii), _ext.ptr(first_idx), _ext.ptr(num_points),
+                                     N, P, maxp, S, _ext.ptr(ws), ws.numel(), _ext.ptr(total), st))
+    cap = int(total.item())          # the one read-back: sizes the per-tile record buffer
+    recs = torch.empty((max(cap, 1) * lib.isob200_splat_record_bytes(),), dtype=torch.uint8, device=dev)
+    _ext.check(lib.isob200_splat_forward(
+        _ext.ptr(points), _ext.ptr(ellipse), _ext.ptr(cutoff), _ext.ptr(radii), _ext.ptr(first_idx),
+        _ext.ptr(num_points), N, P, maxp, S, K, float(depth_merging_thres), 1 if occ_inclusive else 0,
+        _ext.ptr(ws), ws.numel(), _ext.ptr(recs), cap, _ext.ptr(idx), _ext.ptr(zbuf), _ext.ptr(qvalue),
+        _ext.ptr(occ), st))
+    return idx, zbuf, qvalue, occ
+
+
+def bin_counts(points, radii, first_idx, num_points, image_size, bin_size):
+    """``points_per_bin`` (N,B,B) int32 of the reference's coarse pass (rasterize_points.cu:353-412),
+    which it computes and drops; exposed for the per-tile-count parity check."""
+    lib = _ext.lib()
+    points = _f32c(points, "points")
+    radii = _f32c(radii, "radii")
+    dev = points.device
+    first_idx = _i64c(first_idx, dev)
+    num_points = _i64c(num_points, dev)
+    N = num_points.shape[0]
+    B = 1 + (int(image_size) - 1) // int(bin_size)
+    out = torch.empty((N, B, B), dtype=torch.int32, device=dev)
+    _ext.check(lib.isob200_splat_bin_counts(_ext.ptr(points), _ext.ptr(radii), _ext.ptr(first_idx),
+                                            _ext.ptr(num_points), N, points.shape[0], int(image_size), int(bin_size),
+                                            _ext.ptr(out), _ext.stream(dev)))
+    return out
+
+
+def count_pixel_splats(points, ellipse, cutoff, radii, image_size):
+    """Number of (pixel, point) pairs passing CheckPixelInsidePoint (rasterize_points.cu:64-98): the
+    "pixel-splat" unit of the throughput metric.  Returns a python int (synchronises)."""
+    points = _f32c(points, "points")
+    P = points.shape[0]
+    cutoff = _f32c(cutoff.expand(P) if cutoff.shape[0] == 1 and P != 1 else cutoff, "cutoff_thres")
+    total = torch.zeros((1,), dtype=torch.int64, device=points.device)
+    _ext.check(_ext.lib().isob200_splat_count_pairs(
+        _ext.ptr(points), _ext.ptr(_f32c(ellipse, "ellipse")), _ext.ptr(cutoff), _ext.ptr(_f32c(radii, "radii")), P,
+        int(image_size), _ext.ptr(total), _ext.stream(points.device)))
+    return int(total.item())
+
+
+def visibility_mask(idx, num_points_total, occupancy=None):
+    """(P,) bool: ids in any slot of an active pixel -- active = ``occupancy != 0`` when given
+    (get_per_point_visibility_mask, DSS/utils/__init__.py:378-399) else ``idx[..., 0] >= 0``
+    (EllipticalRasterizer.backward, rasterizer.py:851-857).  Replaces unique() + scatter."""
+    if not idx.is_cuda:
+        raise TypeError("for now only cuda version is supported")
+    idx = idx.contiguous()
+    K = idx.shape[-1]
+    vis = torch.zeros((int(num_points_total),), dtype=torch.uint8, device=idx.device)
+    mask = None if occupancy is None else _f32c(occupancy, "occupancy")
+    _ext.check(_ext.lib().isob200_splat_visibility(_ext.ptr(idx), _ext.ptr(mask), idx.numel() // max(K, 1), K,
+                                                   int(num_points_total), _ext.ptr(vis), _ext.stream(idx.device)))
+    return vis.bool()
+
+
+def _occ_backward(points, radii, visible_u8, first_idx, num_points, rs, radii_s, grad_occ, mode, out, out_stride):
+    N, H, W = grad_occ.shape
+    _ext.check(_ext.lib().isob200_splat_occ_backward(
+        _ext.ptr(points), _ext.ptr(radii), _ext.ptr(visible_u8), _ext.ptr(first_idx), _ext.ptr(num_points),
+        _ext.ptr(rs), float(radii_s), _ext.ptr(grad_occ), N, H, W, points.shape[0], mode, _ext.ptr(out),
+        out_stride, _ext.stream(points.device)))
+
+
+class _CExt:
+    """Drop-in for the bound subset of ``DSS._C`` (DSS/csrc/ext.cpp:5-18)."""
+
+    @staticmethod
+    def splat_points(points, ellipse_params, cutoff_thres, radii, cloud_to_packed_first_idx,
+                     num_points_per_cloud, depth_merging_thres, image_size, points_per_pixel, bin_size,
+                     max_points_per_bin):
+        if bin_size != 0:
+            num_bins = 1 + (int(image_size) - 1) // int(bin_size)
+            if num_bins >= kMaxPointsPerBin:   # rasterize_points.cu:462-468
+                raise RuntimeError("Got %d; that's too many!" % num_bins)
+        return _splat(points, ellipse_params, cutoff_thres, radii, cloud_to_packed_first_idx,
+                      num_points_per_cloud, depth_merging_thres, image_size, points_per_pixel,
+                      occ_inclusive=(bin_size == 0))
+
+    @staticmethod
+    def _splat_points_naive(points, ellipse_params, cutoff_thres, radii, cloud_to_packed_first_idx,
+                            num_points_per_cloud, depth_merging_thres, image_size, points_per_pixel):
+        return _splat(points, ellipse_params, cutoff_thres, radii, cloud_to_packed_first_idx,
+                      num_points_per_cloud, depth_merging_thres, image_size, points_per_pixel, occ_inclusive=True)
+
+    @staticmethod
+    def _backward_zbuf(idx, zbuf_grad, point_z_grad):
+        """In place: point_z_grad (P,1) += scatter of zbuf_grad by idx (rasterize_points.h:388-419)."""
+        if not idx.is_cuda:
+            raise TypeError("for now only cuda version is supported")
+        N, H, W, K = idx.shape
+        if not point_z_grad.is_contiguous():
+            raise RuntimeError("_backward_zbuf: point_z_grad must be contiguous")
+        _ext.check(_ext.lib().isob200_splat_zbuf_backward(
+            _ext.ptr(idx.contiguous()), _ext.ptr(_f32c(zbuf_grad, "zbuf_grad")), N, H, W, K,
+            _ext.ptr(point_z_grad), point_z_grad.stride(0) if point_z_grad.dim() > 1 else 1,
+            _ext.stream(idx.device)))
+
+    @staticmethod
+    def _splat_points_occ_backward(points, radii, grad_occ, cloud_to_packed_first_idx, num_points_per_cloud,
+                                   radii_s, depth_merging_thres):
+        """Slow-path occupancy backward (rasterize_points.h:341-386) -> (P,2)."""
+        points = _f32c(points, "points")
+        radii = _f32c(radii, "radii")
+        out = torch.empty((points.shape[0], 2), dtype=torch.float32, device=points.device)
+        if out.numel():
+            _occ_backward(points, radii, None, _i64c(cloud_to_packed_first_idx, points.device),
+                          _i64c(num_points_per_cloud, points.device), None, radii_s, _f32c(grad_occ, "grad_occ"),
+                          1, out, 2)
+        return out
+
+    @staticmethod
+    def _splat_points_occ_fast_cuda_backward(points_sorted, radii_sorted, rs, grad_occ, num_points_per_cloud,
+                                             cloud_to_packed_first_idx, points_grid_off=None, grid_params=None):
+        """Fast-path occupancy backward (rasterize_points.h:327-336) -> (P,2) in the order of the given
+        points.  The 2-D grid arguments of the reference are accepted and ignored: the kernel is
+        point-centric and needs no neighbour structure."""
+        points = _f32c(points_sorted, "points")
+        radii = _f32c(radii_sorted, "radii")
+        out = torch.empty((points.shape[0], 2), dtype=torch.float32, device=points.device)
+        if out.numel():
+            _occ_backward(points, radii, None, _i64c(cloud_to_packed_first_idx, points.device),
+                          _i64c(num_points_per_cloud, points.device), _f32c(rs, "rs"), 0.0,
+                          _f32c(grad_occ, "grad_occ"), 0, out, 2)
+        return out
+
+
+_C = _CExt()
+
+
+def per_view_median_radius(radii, visible, first_idx, num_points):
+    """median over the flattened (n_visible, 2) radii of every view (rasterizer.py:884; torch.median =
+    lower middle), without host synchronisation.  Views with no visible point get 0."""
+    P = radii.shape[0]
+    N = num_points.shape[0]
+    dev = radii.device
+    view = torch.repeat_interleave(torch.arange(N, device=dev), num_points, output_size=P)
+    vals = torch.where(visible[:, None], radii, torch.full_like(radii, float("inf"))).reshape(-1)
+    view2 = view.repeat_interleave(2)
+    v_sorted, o1 = torch.sort(vals)
+    o2 = torch.sort(view2[o1], stable=True).indices
+    grouped = v_sorted[o2]                                   # ascending inside each view's 2*num slice
+    cnt = torch.zeros((N,), dtype=torch.int64, device=dev).index_add_(0, view, visible.to(torch.int64)) * 2
+    pos = 2 * first_idx + (cnt - 1).clamp_min(0) // 2
+    med = grouped[pos.clamp(0, max(2 * P - 1, 0))] if P > 0 else torch.zeros((N,), device=dev)
+    return torch.where(cnt > 0, med, torch.zeros_like(med))
+
+
+class EllipticalRasterizer(autograd.Function):
+    """DSS/core/rasterizer.py:743-973."""
+
+    @staticmethod
+    def forward(ctx, pts_screen, ellipse_param, cutoff_threshold, radii, cloud_to_packed_first_idx,
+                num_points_per_cloud, depth_merging_threshold, image_size, points_per_pixel, bin_size=0,
+                max_points_per_bin=0, radii_backward_scaler=10.0):
+        idx, zbuf, qvalue_map, occ_map = _C.splat_points(
+            pts_screen, ellipse_param, cutoff_threshold, radii, cloud_to_packed_first_idx, num_points_per_cloud,
+            depth_merging_threshold, image_size, points_per_pixel, bin_size, max_points_per_bin)
+        ctx.radii_backward_scaler = radii_backward_scaler
+        ctx.depth_merging_threshold = depth_merging_threshold
+        ctx.save_for_backward(pts_screen, radii, idx, cloud_to_packed_first_idx, num_points_per_cloud)
+        ctx.mark_non_differentiable(idx)
+        return idx, zbuf, qvalue_map, occ_map
+
+    @staticmethod
+    def backward(ctx, idx_grad, zbuf_grad, qvalue_grad, occ_grad):
+        pts_screen, radii, idx, first_idx, num_points = ctx.saved_tensors
+        radii_s = ctx.radii_backward_scaler
+        if radii_s == 0:
+            raise RuntimeError("radii_backward_scaler == 0 (WeightBackward) is not implemented in the reference "
+                               "either (rasterizer.py:776-777 saves 4 tensors, :809-811 unpacks 8)")
+        dev = pts_screen.device
+        P = pts_screen.shape[0]
+        pts = _f32c(pts_screen.detach(), "pts_screen")
+        radii = _f32c(radii, "radii")
+        first_idx = _i64c(first_idx, dev)
+        num_points = _i64c(num_points, dev)
+        grads = torch.zeros((P, 3), dtype=torch.float32, device=dev)
+        if occ_grad is not None and P > 0:
+            vis = visibility_mask(idx, P)                                    # rasterizer.py:851-857
+            rs = (per_view_median_radius(radii, vis, first_idx, num_points) * radii_s).contiguous()   # :884
+            _occ_backward(pts, radii, vis.view(torch.uint8), first_idx, num_points, rs, radii_s,
+                          _f32c(occ_grad, "occ_grad"), 0, grads, 3)
+        if zbuf_grad is not None and P > 0:
+            N, H, W, K = idx.shape
+            _ext.check(_ext.lib().isob200_splat_zbuf_backward(
+                _ext.ptr(idx), _ext.ptr(_f32c(zbuf_grad, "zbuf_grad")), N, H, W, K,
+                grads.data_ptr() + 8, 3, _ext.stream(dev)))                  # column 2 of (P,3)
+        return (grads,) + (None,) * 11
+
+
+def rasterize_elliptical_points(pcls_screen, ellipse_params, cutoff_threshold, radii,
+                                depth_merging_threshold: float = 0.05, image_size: int = 512,
+                                points_per_pixel: int = 5, bin_size: Optional[int] = None,
+                                max_points_per_bin: Optional[int] = None, radii_backward_scaler: float = 10.0,
+                                clip_pts_grad: float = -1.0):
+    """DSS/core/rasterizer.py:678-740.  ``pcls_screen`` duck-types ``points_packed()``,
+    ``cloud_to_packed_first_idx()``, ``num_points_per_cloud()``."""
+    points_packed = pcls_screen.points_packed()
+    cloud_to_packed_first_idx = pcls_screen.cloud_to_packed_first_idx()
+    num_points_per_cloud = pcls_screen.num_points_per_cloud()
+    cutoff_threshold = cutoff_threshold.expand(points_packed.shape[0])
+    if bin_size is None:
+        if image_size <= 64:
+            bin_size = 8
+        elif image_size <= 256:
+            bin_size = 16
+        elif image_size <= 512:
+            bin_size = 32
+        elif image_size <= 1024:
+            bin_size = 64
+    if bin_size != 0:
+        num_bins = 1 + (image_size - 1) // bin_size
+        if num_bins >= kMaxPointsPerBin:
+            raise ValueError("bin_size too small, number of bins must be less than %d; got %d"
+                             % (kMaxPointsPerBin, num_bins))
+    if max_points_per_bin is None:
+        max_points_per_bin = 0      # unused here: no (N,B,B,M) matrix, hence no .max() host sync
+    if points_packed.requires_grad and clip_pts_grad > 0:
+        def _clip(g, m=clip_pts_grad):
+            norm = g.norm(dim=-1, keepdim=True)
+            return torch.where(norm > m, g * (m / norm.clamp_min(1e-20)), g)
+        points_packed.register_hook(_clip)
+    return EllipticalRasterizer.apply(points_packed, ellipse_params, cutoff_threshold, radii,
+                                      cloud_to_packed_first_idx, num_points_per_cloud, depth_merging_threshold,
+                                      image_size, points_per_pixel, bin_size, max_points_per_bin,
+                                      radii_backward_scaler)
+
+
+class _Blend(autograd.Function):
+    @staticmethod
+    def forward(ctx, idx, qvalue, occ, scaler, feat, eps):
+        lib = _ext.lib()
+        N, H, W, K = idx.shape
+        C = feat.shape[1]
+        dev = idx.device
+        out = torch.empty((N, H, W, C + 1), dtype=torch.float32, device=dev)
+        need_grad = feat.requires_grad
+        weights = torch.empty((N, H, W, K), dtype=torch.float32, device=dev) if need_grad else None
+        _ext.check(lib.isob200_splat_blend(_ext.ptr(idx), _ext.ptr(qvalue), _ext.ptr(occ), _ext.ptr(scaler),
+                                           _ext.ptr(feat), feat.stride(0), N * H * W, K, C, float(eps),
+                                           _ext.ptr(out), _ext.ptr(weights), _ext.stream(dev)))
+        if need_grad:
+            ctx.save_for_backward(idx, weights)
+        ctx.meta = (feat.shape, eps)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        idx, weights = ctx.saved_tensors
+        shape, eps = ctx.meta
+        N, H, W, K = idx.shape
+        gfeat = torch.zeros(shape, dtype=torch.float32, device=idx.device)
+        _ext.check(_ext.lib().isob200_splat_blend_backward(
+            _ext.ptr(idx), _ext.ptr(weights), _ext.ptr(grad_out.contiguous()), N * H * W, K, shape[1], float(eps),
+            _ext.ptr(gfeat), gfeat.stride(0), _ext.stream(idx.device)))
+        return None, None, None, None, gfeat, None
+
+
+def blend_rgba(idx, qvalue, occupancy, scaler, features, eps: float = NORM_WEIGHT_EPS):
+    """(N,S,S,C+1) = [sum_k w_k f[idx_k] / max(sum_k w_k, eps), occupancy] with
+    w_k = exp(-0.5 qvalue_k) * scaler[idx_k] over idx >= 0 (renderer.py:53-78).
+    ``scaler``: per-POINT (P,) scaler (or None = 1); ``features``: (P, C<=4), e.g. rgb."""
+    if not idx.is_cuda:
+        raise TypeError("for now only cuda version is supported")
+    feat = features if features.dtype == torch.float32 else features.float()
+    if feat.stride(-1) != 1:
+        feat = feat.contiguous()
+    sc = None if scaler is None else _f32c(scaler.reshape(-1), "scaler")
+    return _Blend.apply(idx.contiguous(), _f32c(qvalue, "qvalue"), _f32c(occupancy, "occupancy"), sc, feat, eps)
+
+
+def gather_with_neg_idx(input: torch.Tensor, dim: int, index: torch.Tensor):
+    """DSS/utils/__init__.py:172-185 (without mutating ``index``)."""
+    mask = index >= 0
+    out = torch.gather(input, dim, index.clamp_min(0))
+    return out * mask.to(out.dtype)
