@@ -81,9 +81,9 @@ int isob200_project_sphere(float* points, float* normals, unsigned char* valid, 
 
 /* ---- uniform resampling: UniformProjection.resample, one sample_iter
  *      (DSS/models/levelset_sampling.py:259, 268-284) ------------------------------------ */
-int isob200_resample_step(const float* points, const float* normals, const void* idxs, int idx_is_i64,
-                          int idx_stride, int k_offset, const float* inv_sigma, int N, int P, int K,
-                          float* out, void* stream);
+int isob200_resample_step(const float* q_points, const float* points, const float* normals,
+                          const void* idxs, int idx_is_i64, int idx_stride, int k_offset,
+                          const float* inv_sigma, int N, int Pq, int P, int K, float* out, void* stream);
 int isob200_normalize_rows3(const float* x, long long M, float eps, float* out, void* stream);
 
 /* ---- DSS elliptical splat rasteriser, forward: DSS._C.splat_points

@@ -13,7 +13,7 @@
 //  * results are written straight to the caller's (N,P1,K) tensors (int64 or int32 indices),
 //    including the -1 padding, so no fill pass is needed.
 // Distances use the reference's exact fp32 expression as nvcc contracts it (SASS of grid.cu:
-// FMUL dx*dx; FFMA dy; FFMA dz), spelled with intrinsics so it can never be re-contracted.
+// FMUL dy*dy; FFMA dx; FFMA dz), spelled with intrinsics so it can never be re-contracted.
 // Equal distances are ordered by smaller original index (the reference keeps whichever it saw
 // first, which depends on its atomic insertion order -- mink.cuh:64).
 #include "common.cuh"
@@ -24,9 +24,10 @@ namespace isob200 {
 
 template <int D>
 __device__ __forceinline__ float sqdist_ref(const float* __restrict__ p2, const float* q) {
+  // SASS of FindNbrs{2,3}DKernel (every K): FMUL dy*dy ; FFMA dx*dx + . ; FFMA dz*dz + .
   const float dx = __fsub_rn(p2[0], q[0]);
   const float dy = __fsub_rn(p2[1], q[1]);
-  float s = __fmaf_rn(dy, dy, __fmul_rn(dx, dx));
+  float s = __fmaf_rn(dx, dx, __fmul_rn(dy, dy));
   if (D == 3) {
     const float dz = __fsub_rn(p2[2], q[2]);
     s = __fmaf_rn(dz, dz, s);

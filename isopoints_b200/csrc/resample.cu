@@ -25,22 +25,22 @@ __device__ __forceinline__ float eps_denom_r(float x, float eps) {
 
 template <typename IdxT>
 __global__ void __launch_bounds__(256)
-resample_step_kernel(const float* __restrict__ points, const float* __restrict__ normals,
-                     const IdxT* __restrict__ idxs, int idx_stride, int k_offset,
-                     const float* __restrict__ inv_sigma, int N, int P, int K,
+resample_step_kernel(const float* __restrict__ q_points, const float* __restrict__ points,
+                     const float* __restrict__ normals, const IdxT* __restrict__ idxs, int idx_stride,
+                     int k_offset, const float* __restrict__ inv_sigma, int N, int Pq, int P, int K,
                      float* __restrict__ out) {
   constexpr int GW = 8;
   const int lane = threadIdx.x & 31;
   const int gl = lane & (GW - 1);
-  const long long total = (long long)N * P;
+  const long long total = (long long)N * Pq;
   const long long ngroups = (long long)gridDim.x * (256 / GW);
   for (long long item = (long long)blockIdx.x * (256 / GW) + threadIdx.x / GW; item < total;
        item += ngroups) {
-    const int n = (int)(item / P);
+    const int n = (int)(item / Pq);
     const float isg = inv_sigma[n];
     const float* pts = points + (size_t)n * P * 3;
     const float* nrm = normals + (size_t)n * P * 3;
-    const float px = points[item * 3 + 0], py = points[item * 3 + 1], pz = points[item * 3 + 2];
+    const float px = q_points[item * 3 + 0], py = q_points[item * 3 + 1], pz = q_points[item * 3 + 2];
     float sw = 0.f, sx = 0.f, sy = 0.f, sz = 0.f;
     for (int k = gl; k < K; k += GW) {
       const long long j = (long long)idxs[item * idx_stride + k_offset + k];
@@ -91,31 +91,34 @@ using namespace isob200;
 extern "C" {
 
 // One resampling move (levelset_sampling.py:268-284).
-//   points, normals : (N,P,3); normals must already be unit length (isob200_normalize_rows3)
-//   idxs            : (N,P,idx_stride) neighbour ids (-1 = none), int64 (idx_is_i64) or int32;
+//   q_points        : (N,Pq,3) the points to move (== points for the reference's self-query; a
+//                     rank's shard of the cloud in the point-sharded multi-GPU path)
+//   points, normals : (N,P,3) the neighbour cloud; normals must already be unit length
+//   idxs            : (N,Pq,idx_stride) neighbour ids into `points` (-1 = none), int64 or int32;
 //                     the K columns starting at k_offset are used (k_offset = 1 drops the
 //                     "self" column the way `idxs[..., 1:]` does, :136)
 //   inv_sigma       : (N,) device floats  num_points / diag  (:256)
-//   out             : (N,P,3) moved points (may not alias points)
-int isob200_resample_step(const float* points, const float* normals, const void* idxs, int idx_is_i64,
-                          int idx_stride, int k_offset, const float* inv_sigma, int N, int P, int K,
-                          float* out, void* stream_) {
+//   out             : (N,Pq,3) moved points (may not alias points / q_points)
+int isob200_resample_step(const float* q_points, const float* points, const float* normals,
+                          const void* idxs, int idx_is_i64, int idx_stride, int k_offset,
+                          const float* inv_sigma, int N, int Pq, int P, int K, float* out,
+                          void* stream_) {
   cudaStream_t st = (cudaStream_t)stream_;
-  ISO_CHECK_ARG(N >= 0 && P >= 0 && K >= 0 && k_offset >= 0 && k_offset + K <= idx_stride,
+  ISO_CHECK_ARG(N >= 0 && P >= 0 && Pq >= 0 && K >= 0 && k_offset >= 0 && k_offset + K <= idx_stride,
                 "resample_step: bad sizes");
-  if ((long long)N * P == 0) return ISOB200_OK;
-  ISO_CHECK_ARG(points && normals && idxs && inv_sigma && out, "resample_step: null pointer");
-  ISO_CHECK_ARG(points != out, "resample_step: out must not alias points");
-  const long long groups = (long long)N * P;
+  if ((long long)N * Pq == 0) return ISOB200_OK;
+  ISO_CHECK_ARG(q_points && points && normals && idxs && inv_sigma && out, "resample_step: null pointer");
+  ISO_CHECK_ARG(points != out && q_points != out, "resample_step: out must not alias the inputs");
+  const long long groups = (long long)N * Pq;
   long long need = (groups + 31) / 32;
   const long long cap = (long long)kNumSMs * 8 * 4;
   const int blocks = (int)(need < cap ? need : cap);
   if (idx_is_i64)
-    resample_step_kernel<int64_t><<<blocks, 256, 0, st>>>(points, normals, (const int64_t*)idxs, idx_stride,
-                                                         k_offset, inv_sigma, N, P, K, out);
+    resample_step_kernel<int64_t><<<blocks, 256, 0, st>>>(q_points, points, normals, (const int64_t*)idxs,
+                                                         idx_stride, k_offset, inv_sigma, N, Pq, P, K, out);
   else
-    resample_step_kernel<int><<<blocks, 256, 0, st>>>(points, normals, (const int*)idxs, idx_stride,
-                                                     k_offset, inv_sigma, N, P, K, out);
+    resample_step_kernel<int><<<blocks, 256, 0, st>>>(q_points, points, normals, (const int*)idxs, idx_stride,
+                                                     k_offset, inv_sigma, N, Pq, P, K, out);
   ISO_CHECK_LAUNCH("resample_step_kernel");
   return ISOB200_OK;
 }

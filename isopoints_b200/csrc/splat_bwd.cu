@@ -17,7 +17,7 @@
 // grad_occ image of a view stays L2 resident), accumulates in registers, and finishes with a
 // warp-shuffle reduction and ONE plain store per coordinate: no grid build, no atomics,
 // run-to-run deterministic.  The predicate per (pixel, point) pair is the reference's, in its
-// fp32 form (dist2 = fma(dy, dy, dx*dx) <= r^2, ...), so the set of contributing pairs is equal.
+// fp32 form (dist2 = fma(dx, dx, dy*dy) <= r^2, ...), so the set of contributing pairs is equal.
 // NOT reproduced: the reference closes the last 2-D grid cell of views n >= 1 with a local count
 // while its offsets are packed-global (rasterize_points_backward.cu:124-126), silently dropping
 // that cell's points; here every in-radius pair contributes.
@@ -91,7 +91,7 @@ splat_occ_backward_kernel(const float* __restrict__ points, const float* __restr
             const float g = g_row[col];
             if (g == 0.0f) continue;
             const float dx = __fsub_rn(pix_to_ndc_b(W - 1 - col, fW), px);
-            const float d2 = __fmaf_rn(dy, dy, __fmul_rn(dx, dx));
+            const float d2 = __fmaf_rn(dx, dx, __fmul_rn(dy, dy));   // SASS: FMUL dy*dy ; FFMA dx
             if (MODE == 0) {
               if (d2 > r2) continue;
             } else {

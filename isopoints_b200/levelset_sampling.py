@@ -246,8 +246,8 @@ class UniformProjection(LevelSetProjection):
             idx_full = self._knn_full_idx  # (B,P,knn_k+1) int64, column 0 = self
             moved = torch.empty_like(points)
             _ext.check(lib.isob200_resample_step(
-                _ext.ptr(points), _ext.ptr(normals), _ext.ptr(idx_full), 1, idx_full.shape[2], 1,
-                _ext.ptr(inv_sigma_spatial), B, P, idx_full.shape[2] - 1, _ext.ptr(moved),
+                _ext.ptr(points), _ext.ptr(points), _ext.ptr(normals), _ext.ptr(idx_full), 1, idx_full.shape[2],
+                1, _ext.ptr(inv_sigma_spatial), B, P, P, idx_full.shape[2] - 1, _ext.ptr(moved),
                 _ext.stream(dev)))
             # NB (:284-286): the reference carries the MOVED, un-projected points into the next
             # sample_iter (`points = points + move`); the projection result is only returned.

@@ -33,11 +33,12 @@ def eps_denom(x: torch.Tensor, eps: float = 1e-17) -> torch.Tensor:
 # FRNN  (external/FRNN/frnn/frnn.py, csrc/grid/*.cu, csrc/bruteforce/*)
 # =========================================================================================
 def frnn_sqdist(p2: np.ndarray, q: np.ndarray) -> np.ndarray:
-    """grid.cu:331-334 as compiled: d = p2 - q ; FMUL dx*dx ; FFMA dy ; FFMA dz."""
+    """grid.cu:331-334 as compiled (SASS, every K): d = p2 - q ; FMUL dy*dy ; FFMA dx ; FFMA dz."""
     d = (p2 - q[None, :]).astype(np.float32)
-    s = (d[:, 0] * d[:, 0]).astype(np.float32)
-    for k in range(1, p2.shape[1]):
-        s = _fma(d[:, k], d[:, k], s)
+    s = (d[:, 1] * d[:, 1]).astype(np.float32)
+    s = _fma(d[:, 0], d[:, 0], s)
+    if p2.shape[1] == 3:
+        s = _fma(d[:, 2], d[:, 2], s)
     return s
 
 
@@ -561,7 +562,7 @@ def splat_backward(points, radii, idx, first_idx, num_points, grad_occ, grad_zbu
                 continue
             dx = (xf - px).astype(np.float32)
             dy = (yf - py).astype(np.float32)
-            d2 = _fma(dy, dy, (dx * dx).astype(np.float32))
+            d2 = _fma(dx, dx, (dy * dy).astype(np.float32))   # SASS: FMUL dy*dy ; FFMA dx
             sel = ~(d2 > r2)
             outside = (np.abs(dx) > radii[p, 0]) | (np.abs(dy) > radii[p, 1])
             sel &= ~((g > 0) & outside)

@@ -101,3 +101,27 @@ def test_projection_properties_at_c2_scale():
     fused = proj.project_points(x, SphereSDF(analytic=True).to(DEV), skip_resampling=True, skip_upsampling=True)
     assert torch.equal(fused["mask"], m)
     assert torch.allclose(fused["levelset_points"], pts, rtol=RTOL, atol=1e-6)
+
+
+def test_sharded_projection_world1_equals_single_gpu():
+    """The point-sharded operator on a 1-rank NCCL group reproduces the single-GPU operator bit for bit
+    (same kernels, same neighbour sets); multi-rank equality is checked by tests/run_dist_gpu.py."""
+    import os
+    import socket
+    import torch.distributed as dist
+    from isopoints_b200.dist import ShardedUniformProjection
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("nccl", rank=0, world_size=1, device_id=torch.device("cuda", 0))
+    try:
+        torch.manual_seed(3)
+        x = (torch.rand(1, 5000, 3, device=DEV) - 0.5) * 1.6
+        net = TinySiren(seed=2).to(DEV)
+        kw = dict(proj_max_iters=10, proj_tolerance=5e-5, knn_k=8, sample_iters=2)
+        a = UniformProjection(**kw).project_points(x, net, skip_upsampling=True)
+        b = ShardedUniformProjection(**kw).project_points(x, net, skip_upsampling=True)
+        assert torch.equal(a["mask"], b["mask"])
+        assert torch.equal(a["levelset_points"], b["levelset_points"])
+    finally:
+        dist.destroy_process_group()
