@@ -136,6 +136,20 @@ int isob200_splat_blend_backward(const int* idx, const float* weights, const flo
                                  long long npix, int K, int C, float eps, float* grad_feat,
                                  int feat_stride, void* stream);
 
+/* ---- point-set operators around the projection: DSS/utils/point_processing.py
+ *      wlop (:35-122: density_P :77-80, one iteration :90-118), upsample (:321-340, one round),
+ *      farthest_sampling (:473-499 -> torch_cluster.fps, third party) ------------------------ */
+int isob200_wlop_density(const float* pts, const int64_t* idx, int idx_stride, int k_offset,
+                         const float* sigma_inv, int N, int P, int K, float* density, void* stream);
+int isob200_wlop_step(const float* X, const float* Pc, const int64_t* idx_xp, const int64_t* idx_xx,
+                      int xx_stride, int xx_k_offset, const float* density_P, const float* sigma_inv, float mu,
+                      int N, int PX, int PP, int K, float* out, void* stream);
+int isob200_upsample_sparsity(const float* pts, const int64_t* idx, int idx_stride, int k_offset,
+                              const int64_t* lengths, int N, int P, int K, float* sparsity, float* child,
+                              void* stream);
+int isob200_fps(const float* pts, const int64_t* lengths, const int64_t* samples, const int64_t* start, int N,
+                int P, int Mmax, float* mind, int64_t* out_idx, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

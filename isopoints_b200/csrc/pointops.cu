@@ -1,0 +1,276 @@
+// Point-set operators used around the iso-point projection, for sm_100a.
+//
+// Replaces the PyTorch op chains / third-party kernels of DSS/utils/point_processing.py:
+//   wlop          (:35-122)   2 (N,P,K,3) frnn_gather materialisations + ~40 elementwise kernels
+//                             per iteration -> one fused kernel per iteration (+ one for density_P)
+//   upsample      (:281-362)  the (N,P,K,K,3) mid-point / neighbour difference tensor (P*K*K*12 B:
+//                             2.3 GB at 200 k points, K = 31) -> one warp per point in registers
+//   farthest_sampling (:473-499) torch_cluster.fps [third party, absent from the reference tree]
+// All are gather-heavy fp32 kernels bound by L2 bandwidth / latency; neighbour ids come from the
+// FRNN query kernel (frnn_query.cu).
+#include "common.cuh"
+#include <float.h>
+#include <limits.h>
+#include <math.h>
+
+namespace isob200 {
+
+__device__ __forceinline__ float eps_denom_p(float x, float eps) {   // mathHelper.py:14-18
+  const float s = (x < 0.f) ? -1.f : 1.f;
+  return s * fmaxf(fabsf(x), eps);
+}
+
+// density_P[i] = 1 + sum_k theta(|P_i - P_j|^2), theta(r2) = exp(-r2 * sigma_inv[n])
+// (point_processing.py:77-80); idx (N,P,stride) with the K columns from k_offset.
+__global__ void __launch_bounds__(256)
+wlop_density_kernel(const float* __restrict__ pts, const int64_t* __restrict__ idx, int stride, int k_offset,
+                    const float* __restrict__ sigma_inv, int N, int P, int K, float* __restrict__ density) {
+  const long long total = (long long)N * P;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int n = (int)(i / P);
+    const float s = sigma_inv[n];
+    const float* base = pts + (size_t)n * P * 3;
+    const float x = pts[3 * i], y = pts[3 * i + 1], z = pts[3 * i + 2];
+    float acc = 1.0f;
+    for (int k = 0; k < K; ++k) {
+      const long long j = idx[i * stride + k_offset + k];
+      if (j < 0) continue;
+      const float dx = x - base[3 * j], dy = y - base[3 * j + 1], dz = z - base[3 * j + 2];
+      // the reference squares a norm: (sqrt(d2))^2
+      const float nr = sqrtf(dx * dx + dy * dy + dz * dz);
+      acc += expf(-(nr * nr) * s);
+    }
+    density[i] = acc;
+  }
+}
+
+// One WLOP iteration (point_processing.py:90-118).  One group of 8 lanes per X point.
+//   X (N,PX,3), Pc (N,PP,3), idx_xp (N,PX,K) ids into Pc, idx_xx (N,PX,sxx) ids into X (K columns
+//   from k_offset_xx), density_P (N,PP); out (N,PX,3).
+// Missing neighbours (id < 0) are gathered as the ORIGIN by frnn_gather, and the reference lets
+// them contribute to density_X (theta(|x - 0|^2)); alpha / beta are zeroed for them (:108, :111).
+__global__ void __launch_bounds__(256)
+wlop_step_kernel(const float* __restrict__ X, const float* __restrict__ Pc,
+                 const int64_t* __restrict__ idx_xp, const int64_t* __restrict__ idx_xx, int sxx,
+                 int k_offset_xx, const float* __restrict__ density_P, const float* __restrict__ sigma_inv,
+                 float mu, int N, int PX, int PP, int K, float* __restrict__ out) {
+  constexpr int GW = 8;
+  const int lane = threadIdx.x & 31, gl = lane & (GW - 1);
+  const long long total = (long long)N * PX;
+  const long long ngroups = (long long)gridDim.x * (256 / GW);
+  for (long long item = (long long)blockIdx.x * (256 / GW) + threadIdx.x / GW; item < total; item += ngroups) {
+    const int n = (int)(item / PX);
+    const float s = sigma_inv[n];
+    const float* Pb = Pc + (size_t)n * PP * 3;
+    const float* Xb = X + (size_t)n * PX * 3;
+    const float* dP = density_P + (size_t)n * PP;
+    const float x = X[3 * item], y = X[3 * item + 1], z = X[3 * item + 2];
+    float sa = 0.f, ax = 0.f, ay = 0.f, az = 0.f;     // data term
+    float dens = 0.f;                                 // sum theta(delta^2) (density_X - 1)
+    float sb = 0.f, bx = 0.f, by = 0.f, bz = 0.f;     // repulsion term (without the density_X factor)
+    for (int k = gl; k < K; k += GW) {
+      const long long jp = idx_xp[item * K + k];
+      if (jp >= 0) {
+        const float qx = Pb[3 * jp], qy = Pb[3 * jp + 1], qz = Pb[3 * jp + 2];
+        const float ex = x - qx, ey = y - qy, ez = z - qz;
+        const float e2 = ex * ex + ey * ey + ez * ez;
+        const float a = expf(-e2 * s) / eps_denom_p(sqrtf(e2), 1e-17f) / dP[jp];
+        sa += a; ax += a * qx; ay += a * qy; az += a * qz;
+      }
+      const long long jx = idx_xx[item * sxx + k_offset_xx + k];
+      float nx = 0.f, ny = 0.f, nz = 0.f;
+      if (jx >= 0) { nx = Xb[3 * jx]; ny = Xb[3 * jx + 1]; nz = Xb[3 * jx + 2]; }
+      const float dx = x - nx, dy = y - ny, dz = z - nz;
+      const float d2 = dx * dx + dy * dy + dz * dz;
+      const float th = expf(-d2 * s);
+      dens += th;
+      if (jx >= 0) {
+        const float b = th / eps_denom_p(sqrtf(d2), 1e-17f);
+        sb += b; bx += b * dx; by += b * dy; bz += b * dz;
+      }
+    }
+#pragma unroll
+    for (int o = GW / 2; o > 0; o >>= 1) {
+      sa += __shfl_xor_sync(0xffffffffu, sa, o); ax += __shfl_xor_sync(0xffffffffu, ax, o);
+      ay += __shfl_xor_sync(0xffffffffu, ay, o); az += __shfl_xor_sync(0xffffffffu, az, o);
+      dens += __shfl_xor_sync(0xffffffffu, dens, o);
+      sb += __shfl_xor_sync(0xffffffffu, sb, o); bx += __shfl_xor_sync(0xffffffffu, bx, o);
+      by += __shfl_xor_sync(0xffffffffu, by, o); bz += __shfl_xor_sync(0xffffffffu, bz, o);
+    }
+    if (gl < 3) {
+      const float dX = dens + 1.0f;
+      const float a = gl == 0 ? ax : (gl == 1 ? ay : az);
+      const float b = gl == 0 ? bx : (gl == 1 ? by : bz);
+      // new_beta = density_X * beta  =>  both numerator and denominator carry the factor
+      out[3 * item + gl] = a / eps_denom_p(sa, 1e-17f) + mu * (dX * b) / eps_denom_p(dX * sb, 1e-17f);
+    }
+  }
+}
+
+// upsample, one round (point_processing.py:321-340): for point i with neighbours nn_k (k < K):
+//   mid_k = (nn_k + 2 p) / 3 ; s_k = min_j |mid_k - nn_j| ; sparsity = max_k s_k, father = argmax_k
+// (first maximum).  Writes sparsity (N,P) and child (N,P,3) = mid_father.  Missing neighbours
+// (id < 0) are the origin, like knn_gather on pytorch3d's 0-padded ids would give point 0 -- the
+// caller guarantees K valid neighbours (exact KNN), so this only matters for P <= K.
+// One warp per point; K <= 32: lane k owns mid_k.
+__global__ void __launch_bounds__(256)
+upsample_sparsity_kernel(const float* __restrict__ pts, const int64_t* __restrict__ idx, int stride, int k_offset,
+                         const int64_t* __restrict__ lengths, int N, int P, int K,
+                         float* __restrict__ sparsity, float* __restrict__ child) {
+  const int lane = threadIdx.x & 31;
+  const long long total = (long long)N * P;
+  const long long warps = (long long)gridDim.x * (blockDim.x >> 5);
+  for (long long i = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); i < total; i += warps) {
+    const int n = (int)(i / P);
+    const float* base = pts + (size_t)n * P * 3;
+    const float px = pts[3 * i], py = pts[3 * i + 1], pz = pts[3 * i + 2];
+    float nx = 0.f, ny = 0.f, nz = 0.f;
+    if (lane < K) {
+      const long long j = idx[i * stride + k_offset + lane];
+      if (j >= 0) { nx = base[3 * j]; ny = base[3 * j + 1]; nz = base[3 * j + 2]; }
+    }
+    const float mx = (nx + 2.f * px) / 3.f, my = (ny + 2.f * py) / 3.f, mz = (nz + 2.f * pz) / 3.f;
+    float best = FLT_MAX;
+    for (int j = 0; j < K; ++j) {
+      const float qx = __shfl_sync(0xffffffffu, nx, j), qy = __shfl_sync(0xffffffffu, ny, j),
+                  qz = __shfl_sync(0xffffffffu, nz, j);
+      const float dx = mx - qx, dy = my - qy, dz = mz - qz;
+      best = fminf(best, sqrtf(dx * dx + dy * dy + dz * dz));
+    }
+    float v = (lane < K) ? best : -FLT_MAX;
+    int arg = lane;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ov = __shfl_xor_sync(0xffffffffu, v, o);
+      const int oa = __shfl_xor_sync(0xffffffffu, arg, o);
+      if (ov > v || (ov == v && oa < arg)) { v = ov; arg = oa; }
+    }
+    const float cx = __shfl_sync(0xffffffffu, mx, arg), cy = __shfl_sync(0xffffffffu, my, arg),
+                cz = __shfl_sync(0xffffffffu, mz, arg);
+    if (lane == 0) {
+      const bool live = lengths == nullptr || (i - (long long)n * P) < lengths[n];
+      sparsity[i] = live ? v : -FLT_MAX;      // padded rows never win the top-k
+      child[3 * i] = cx; child[3 * i + 1] = cy; child[3 * i + 2] = cz;
+    }
+  }
+}
+
+// Farthest point sampling, one CTA of 1024 threads per cloud.  Start index `start[n]`, then
+// repeatedly the point with the largest distance to the selected set (ties -> smaller index).
+// mind (N,P) is scratch.  out_idx (N,M) int64 (indices into the cloud), M = samples[n] <= Mmax rows
+// are written, the rest -1.
+__global__ void __launch_bounds__(1024)
+fps_kernel(const float* __restrict__ pts, const int64_t* __restrict__ lengths,
+           const int64_t* __restrict__ samples, const int64_t* __restrict__ start, int P, int Mmax,
+           float* __restrict__ mind, int64_t* __restrict__ out_idx) {
+  __shared__ float s_val[32];
+  __shared__ int s_arg[32];
+  __shared__ int s_pick;
+  const int n = blockIdx.x;
+  const int len = lengths ? (int)min((long long)lengths[n], (long long)P) : P;
+  const int M = (int)min((long long)samples[n], (long long)Mmax);
+  const float* base = pts + (size_t)n * P * 3;
+  float* md = mind + (size_t)n * P;
+  int64_t* out = out_idx + (size_t)n * Mmax;
+  for (int i = threadIdx.x; i < Mmax; i += blockDim.x) out[i] = -1;
+  for (int i = threadIdx.x; i < len; i += blockDim.x) md[i] = FLT_MAX;
+  if (len == 0 || M == 0) return;
+  int cur = start ? (int)min((long long)start[n], (long long)len - 1) : 0;
+  __syncthreads();
+  for (int m = 0; m < M; ++m) {
+    if (threadIdx.x == 0) out[m] = cur;
+    const float cx = base[3 * cur], cy = base[3 * cur + 1], cz = base[3 * cur + 2];
+    float bv = -1.f;
+    int ba = INT_MAX;
+    for (int i = threadIdx.x; i < len; i += blockDim.x) {
+      const float dx = base[3 * i] - cx, dy = base[3 * i + 1] - cy, dz = base[3 * i + 2] - cz;
+      const float d = fminf(md[i], dx * dx + dy * dy + dz * dz);
+      md[i] = d;
+      if (d > bv) { bv = d; ba = i; }     // ascending i within a thread: first max kept
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+      const int oa = __shfl_xor_sync(0xffffffffu, ba, o);
+      if (ov > bv || (ov == bv && oa < ba)) { bv = ov; ba = oa; }
+    }
+    if ((threadIdx.x & 31) == 0) { s_val[threadIdx.x >> 5] = bv; s_arg[threadIdx.x >> 5] = ba; }
+    __syncthreads();
+    if (threadIdx.x < 32) {
+      bv = s_val[threadIdx.x];
+      ba = s_arg[threadIdx.x];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+        const int oa = __shfl_xor_sync(0xffffffffu, ba, o);
+        if (ov > bv || (ov == bv && oa < ba)) { bv = ov; ba = oa; }
+      }
+      if (threadIdx.x == 0) s_pick = ba;
+    }
+    __syncthreads();
+    cur = s_pick;
+  }
+}
+
+}  // namespace isob200
+
+using namespace isob200;
+
+extern "C" {
+
+int isob200_wlop_density(const float* pts, const int64_t* idx, int idx_stride, int k_offset,
+                         const float* sigma_inv, int N, int P, int K, float* density, void* stream_) {
+  cudaStream_t st = (cudaStream_t)stream_;
+  if ((long long)N * P == 0) return ISOB200_OK;
+  ISO_CHECK_ARG(pts && idx && sigma_inv && density, "wlop_density: null pointer");
+  ISO_CHECK_ARG(K >= 0 && k_offset >= 0 && k_offset + K <= idx_stride, "wlop_density: bad K");
+  wlop_density_kernel<<<grid_for((long long)N * P, 256, 8), 256, 0, st>>>(pts, idx, idx_stride, k_offset, sigma_inv,
+                                                                        N, P, K, density);
+  ISO_CHECK_LAUNCH("wlop_density_kernel");
+  return ISOB200_OK;
+}
+
+int isob200_wlop_step(const float* X, const float* Pc, const int64_t* idx_xp, const int64_t* idx_xx,
+                      int xx_stride, int xx_k_offset, const float* density_P, const float* sigma_inv, float mu,
+                      int N, int PX, int PP, int K, float* out, void* stream_) {
+  cudaStream_t st = (cudaStream_t)stream_;
+  if ((long long)N * PX == 0) return ISOB200_OK;
+  ISO_CHECK_ARG(X && Pc && idx_xp && idx_xx && density_P && sigma_inv && out, "wlop_step: null pointer");
+  ISO_CHECK_ARG(X != out, "wlop_step: out must not alias X");
+  ISO_CHECK_ARG(K >= 1 && xx_k_offset >= 0 && xx_k_offset + K <= xx_stride, "wlop_step: bad K");
+  const long long need = ((long long)N * PX + 31) / 32;
+  const long long cap = (long long)kNumSMs * 8 * 4;
+  wlop_step_kernel<<<(int)(need < cap ? need : cap), 256, 0, st>>>(X, Pc, idx_xp, idx_xx, xx_stride, xx_k_offset,
+                                                                  density_P, sigma_inv, mu, N, PX, PP, K, out);
+  ISO_CHECK_LAUNCH("wlop_step_kernel");
+  return ISOB200_OK;
+}
+
+int isob200_upsample_sparsity(const float* pts, const int64_t* idx, int idx_stride, int k_offset,
+                              const int64_t* lengths, int N, int P, int K, float* sparsity, float* child,
+                              void* stream_) {
+  cudaStream_t st = (cudaStream_t)stream_;
+  if ((long long)N * P == 0) return ISOB200_OK;
+  ISO_CHECK_ARG(pts && idx && sparsity && child, "upsample_sparsity: null pointer");
+  ISO_CHECK_ARG(K >= 1 && K <= 32 && k_offset >= 0 && k_offset + K <= idx_stride, "upsample_sparsity: K must be in [1, 32]");
+  const long long need = ((long long)N * P + 7) / 8;
+  const long long cap = (long long)kNumSMs * 8 * 8;
+  upsample_sparsity_kernel<<<(int)(need < cap ? need : cap), 256, 0, st>>>(pts, idx, idx_stride, k_offset, lengths, N,
+                                                                          P, K, sparsity, child);
+  ISO_CHECK_LAUNCH("upsample_sparsity_kernel");
+  return ISOB200_OK;
+}
+
+// mind: (N,P) float scratch.  out_idx: (N,Mmax) int64.
+int isob200_fps(const float* pts, const int64_t* lengths, const int64_t* samples, const int64_t* start, int N,
+                int P, int Mmax, float* mind, int64_t* out_idx, void* stream_) {
+  cudaStream_t st = (cudaStream_t)stream_;
+  if (N == 0 || Mmax == 0) return ISOB200_OK;
+  ISO_CHECK_ARG(pts && samples && mind && out_idx, "fps: null pointer");
+  fps_kernel<<<N, 1024, 0, st>>>(pts, lengths, samples, start, P, Mmax, mind, out_idx);
+  ISO_CHECK_LAUNCH("fps_kernel");
+  return ISOB200_OK;
+}
+
+}  // extern "C"

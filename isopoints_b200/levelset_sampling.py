@@ -362,3 +362,32 @@ class UniformProjection(LevelSetProjection):
             return {'levelset_points': points_projected,
                     'levelset_normals': normals_projected,
                     'mask': valid_projection}
+
+
+def _mask_padded_to_list(values, mask):
+    """DSS/utils/__init__.py:119-134: per-cloud tensors of the mask == True rows."""
+    return [values[b][mask[b]] for b in range(values.shape[0])]
+
+
+def sample_uniform_iso_points(model, n_points: int, init_points: Optional[torch.Tensor] = None,
+                              bounding_sphere_radius: float = 1.0, pointclouds_cls=None):
+    """Uniformly distributed iso-points of ``model`` (levelset_sampling.py:1405-1445): project 4n random
+    points, keep those inside the bounding sphere, WLOP-consolidate to ~n/2.., upsample + re-project
+    twice.  Returns a ``Pointclouds`` with one cloud of ~``n_points`` points."""
+    from .point_processing import upsample, wlop
+    from .structures import Pointclouds as _Local
+    Pointclouds = pointclouds_cls or _Local
+    projector = UniformProjection(max_points_per_pass=16000, proj_max_iters=10, proj_tolerance=5e-5, knn_k=8)
+    if init_points is None:
+        init_points = (torch.rand((1, n_points * 4, 3)) - 0.5) * 2 * bounding_sphere_radius
+        init_points = init_points.cuda()
+    proj_results = projector.project_points(init_points, model, skip_resampling=True, skip_upsampling=True)
+    boundary_mask = proj_results['levelset_points'].norm(dim=-1) < bounding_sphere_radius
+    proj_pcl = Pointclouds(_mask_padded_to_list(proj_results['levelset_points'],
+                                                proj_results['mask'] & boundary_mask.view_as(proj_results['mask'])))
+    wlop_result = wlop(proj_pcl, min(0.5, n_points / proj_pcl.num_points_per_cloud().item()))
+    proj_results = projector.project_points(wlop_result, model, skip_resampling=True, skip_upsampling=False)
+    proj_pcl = Pointclouds(_mask_padded_to_list(proj_results['levelset_points'], proj_results['mask']))
+    upsampled_pcl = upsample(proj_pcl, n_points)
+    proj_results = projector.project_points(upsampled_pcl, model, skip_resampling=True, skip_upsampling=False)
+    return Pointclouds(_mask_padded_to_list(proj_results['levelset_points'], proj_results['mask']))

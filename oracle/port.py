@@ -585,3 +585,81 @@ def splat_backward(points, radii, idx, first_idx, num_points, grad_occ, grad_zbu
         np.add.at(grad[:, 2], flat_idx[use, k], gk[use].astype(np.float64))
         alive &= ~(nz & neg)      # `break` only triggers when the gradient is non-zero
     return grad, rs
+
+
+# =========================================================================================
+# point-set operators  (DSS/utils/point_processing.py)
+# =========================================================================================
+def knn_bruteforce(p1: torch.Tensor, p2: torch.Tensor, K: int):
+    """Exact K nearest neighbours of (P1,3) in (P2,3): squared dists ascending, idx (float64 ranking)."""
+    d = torch.cdist(p1.double(), p2.double()) ** 2
+    v, i = torch.topk(d, min(K, p2.shape[0]), dim=1, largest=False)
+    return v.float(), i
+
+
+def _gather0(x, idx):
+    """frnn_gather for one cloud: rows of x at idx, zeros where idx < 0 (frnn.py:340-352)."""
+    return x[idx.clamp_min(0)] * (idx >= 0)[..., None]
+
+
+def wlop(P: torch.Tensor, noise: torch.Tensor, neighborhood_size=16, iters=3, repulsion_mu=0.5, frnn_fn=None):
+    """wlop(ratio=1.0) for one cloud (P,3) (point_processing.py:35-122): X0 = P + noise * 0.1 h,
+    h = 4 sqrt(diag/n), theta(r2) = exp(-16 r2 / h^2), search radius min(h K, 0.2);
+    X <- sum alpha p / sum alpha + mu sum beta delta / sum beta with
+    alpha = theta(|eps|^2) / |eps| / density_P[j],  beta = density_X theta(|delta|^2) / |delta|."""
+    n = P.shape[0]
+    K = neighborhood_size
+    diag = float((P.max(0).values - P.min(0).values).norm())
+    h = 4 * math.sqrt(diag / n)
+    r = min(h * K, 0.2)
+    s_inv = 16 / h / h
+    fn = frnn_fn or (lambda a, b, K, r: torch.as_tensor(frnn_bruteforce(a[None].numpy(), b[None].numpy(), K=K, r=r)[0][0]))
+    theta = lambda r2: torch.exp(-r2 * s_inv)
+    X = P + noise * h * 0.1
+    idx_pp = fn(P, P, K + 1, r)[:, 1:]
+    dpp = (P[:, None] - _gather0(P, idx_pp)).norm(dim=-1)
+    th = theta(dpp ** 2) * (idx_pp >= 0)
+    density_P = th.sum(-1) + 1
+    for _ in range(iters):
+        idx_xp = fn(X, P, K, r)
+        idx_xx = fn(X, X, K + 1, r)[:, 1:]
+        nn_xp = _gather0(P, idx_xp)
+        eps = X[:, None] - nn_xp
+        delta = X[:, None] - _gather0(X, idx_xx)
+        dxx2 = (delta ** 2).sum(-1)
+        dxp2 = (eps ** 2).sum(-1)
+        alpha = theta(dxp2) / eps_denom(eps.norm(dim=-1))
+        beta = theta(dxx2) / eps_denom(delta.norm(dim=-1))
+        density_X = theta(dxx2).sum(-1) + 1
+        na = alpha / _gather0(density_P[:, None], idx_xp).squeeze(-1)
+        na = torch.where(idx_xp < 0, torch.zeros_like(na), na)
+        nb = density_X[:, None] * beta
+        nb = torch.where(idx_xx < 0, torch.zeros_like(nb), nb)
+        X = (na[..., None] * nn_xp).sum(-2) / eps_denom(na.sum(-1, keepdim=True)) + \
+            repulsion_mu * (nb[..., None] * delta).sum(-2) / eps_denom(nb.sum(-1, keepdim=True))
+    return X
+
+
+def upsample(points: torch.Tensor, n_points: int, neighborhood_size=16):
+    """upsample for one cloud (P,3) -> (n_points,3) (point_processing.py:281-362): per round, every
+    point proposes the mid-point (nn_k + 2p)/3 that is farthest from all its K neighbours; the P//8
+    sparsest proposals (at most the remaining count) are PREPENDED; K-NN is rebuilt each round."""
+    K = neighborhood_size
+    pts = points
+    remaining = n_points - pts.shape[0]
+    while remaining > 0:
+        Pn = pts.shape[0]
+        max_P = Pn // 8
+        _, idx = knn_bruteforce(pts, pts, K + 1)
+        nn = pts[idx[:, 1:]]                                   # (P,K,3)
+        mid = (nn + 2 * pts[:, None]) / 3
+        dist = (mid[:, :, None] - nn[:, None]).norm(dim=-1)     # (P,K,K)
+        sparsity, father = dist.min(-1).values.max(-1)
+        order = sparsity.sort().indices[Pn - max_P:]
+        n_new = min(remaining, max_P)
+        new = mid[torch.arange(Pn), father][order]
+        pts = torch.cat([new[max_P - n_new:], pts], 0)
+        remaining -= n_new
+        if max_P == 0:
+            break
+    return pts

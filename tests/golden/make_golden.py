@@ -103,6 +103,42 @@ def main():
                         idxs=idxs.numpy(), dists=dists.numpy(), p2d=p2d.numpy(), idxs2d=idxs2.numpy(),
                         dists2d=dists2.numpy())
 
+    # ---- wlop (ratio = 1: no FPS) and upsample through the reference's own Python ------------
+    import pytorch3d.ops.knn as o3dk
+    from isopoints_b200.structures import Pointclouds
+    PP = ref.point_processing
+
+    def _knn_points_cpu(p1, p2, lengths1=None, lengths2=None, K=1, return_nn=False, return_sorted=True, **kw):
+        outs_d, outs_i = [], []
+        for n in range(p1.shape[0]):
+            l1 = p1.shape[1] if lengths1 is None else int(lengths1[n])
+            l2 = p2.shape[1] if lengths2 is None else int(lengths2[n])
+            d = torch.cdist(p1[n, :l1].double(), p2[n, :l2].double()) ** 2
+            v, i = torch.topk(d, min(K, l2), dim=1, largest=False)
+            dd = torch.zeros(p1.shape[1], K); ii = torch.zeros(p1.shape[1], K, dtype=torch.long)
+            dd[:l1, :v.shape[1]] = v.float(); ii[:l1, :i.shape[1]] = i
+            outs_d.append(dd); outs_i.append(ii)
+        dists, idx = torch.stack(outs_d), torch.stack(outs_i)
+        nn = torch.stack([p2[n][idx[n]] for n in range(p1.shape[0])]) if return_nn else None
+        return o3dk._KNN(dists=dists, idx=idx, knn=nn)
+
+    PP.knn_points = _knn_points_cpu
+    PP.Pointclouds = Pointclouds
+    torch.manual_seed(5)
+    sph = torch.nn.functional.normalize(torch.randn(1, 1500, 3), dim=-1) * (1 + 0.01 * torch.randn(1, 1500, 1))
+    noise = torch.randn(1500, 3)
+    real_randn_like = torch.randn_like
+    PP.torch.randn_like = lambda x: noise.clone()
+    try:
+        wl = PP.wlop(Pointclouds(sph.clone()), ratio=1.0, neighborhood_size=16, iters=3, repulsion_mu=0.5)
+    finally:
+        PP.torch.randn_like = real_randn_like
+    up_pts, up_num = PP.upsample(sph[:, :1000].clone(), 1300, num_points=torch.tensor([1000]), neighborhood_size=16)
+    np.savez_compressed(os.path.join(HERE, "wlop_upsample.npz"), P=sph.numpy(), noise=noise.numpy(),
+                        wlop=wl.points_padded().numpy(), up_in=sph[:, :1000].numpy(), up_pts=up_pts.numpy(),
+                        up_num=up_num.numpy())
+    print("wlop: mean radius", float(wl.points_padded().norm(dim=-1).mean()), "upsample:", tuple(up_pts.shape))
+
     # ---- splat forward: reference naive CPU twin --------------------------------------------
     C = ref_native.dss_C()
     S, K = 48, 4

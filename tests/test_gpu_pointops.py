@@ -1,0 +1,99 @@
+"""GPU parity: knn_points / farthest_sampling / wlop / upsample / sample_uniform_iso_points vs the oracle
+and the reference-generated golden vectors."""
+import numpy as np
+import pytest
+import torch
+
+from isopoints_b200 import point_processing as pp
+from isopoints_b200.levelset_sampling import UniformProjection, sample_uniform_iso_points
+from isopoints_b200.structures import Pointclouds
+from oracle import port
+from tests.helpers import SphereSDF
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def test_knn_points_exact_vs_bruteforce():
+    torch.manual_seed(0)
+    # surface-like cloud (sphere shell) + a ragged second cloud: exercises the radius escalation
+    a = torch.nn.functional.normalize(torch.randn(3000, 3), dim=-1)
+    b = torch.rand(3000, 3) * torch.tensor([2.0, 0.1, 0.1])
+    p = torch.stack([a, b]).to(DEV)
+    lens = torch.tensor([3000, 1700], device=DEV)
+    for K in (1, 9, 17, 32):
+        out = pp.knn_points(p, p, lens, lens, K=K, return_nn=True)
+        for n in range(2):
+            L = int(lens[n])
+            wd, wi = port.knn_bruteforce(p[n, :L].cpu(), p[n, :L].cpu(), K)
+            assert torch.equal(out.idx[n, :L].cpu(), wi)
+            np.testing.assert_allclose(out.dists[n, :L].cpu().numpy(), wd.numpy(), rtol=1e-5, atol=1e-9)
+            assert torch.equal(out.knn[n, :L].cpu(), p[n, :L].cpu()[wi])
+    few = torch.rand(1, 5, 3, device=DEV)                  # fewer points than K: 0-padding like pytorch3d
+    out = pp.knn_points(few, few, K=8)
+    assert (out.idx[0, :, 5:] == 0).all() and (out.dists[0, :, 5:] == 0).all() and (out.idx[0, :, 0] == torch.arange(5, device=DEV)).all()
+
+
+def test_farthest_sampling_matches_sequential_definition():
+    torch.manual_seed(1)
+    pts = torch.rand(2, 900, 3)
+    pcl = Pointclouds([pts[0], pts[1, :500]], normals=[pts[0] * 2, pts[1, :500] * 2]).to(DEV)
+    out = pp.farthest_sampling(pcl, 0.25)
+    for n, L in enumerate((900, 500)):
+        x = pts[n, :L].double()
+        m = int(np.ceil(L * 0.25))
+        sel = [0]
+        md = ((x - x[0]) ** 2).sum(-1).float()
+        for _ in range(m - 1):
+            j = int(torch.argmax(md))
+            sel.append(j)
+            md = torch.minimum(md, ((x - x[j]) ** 2).sum(-1).float())
+        got = out.points_list()[n].cpu()
+        assert got.shape == (m, 3)
+        assert (got == pts[n][sel]).all(-1).float().mean() > 0.98     # fp32 vs fp64 argmax near-ties
+        assert torch.equal(out.normals_list()[n].cpu(), got * 2)
+
+
+def test_wlop_matches_reference_golden(golden):
+    g = golden("wlop_upsample")
+    P = torch.as_tensor(g["P"], device=DEV)
+    out = pp.wlop(Pointclouds(P), ratio=1.0, neighborhood_size=16, iters=3, repulsion_mu=0.5,
+                  noise=torch.as_tensor(g["noise"], device=DEV))
+    np.testing.assert_allclose(out.points_padded().cpu().numpy(), g["wlop"], rtol=1e-4, atol=5e-6)
+    sub = pp.wlop(Pointclouds(P), ratio=0.5)                      # FPS path: shape + stays near the surface
+    assert sub.points_padded().shape == (1, 750, 3)
+    assert float((sub.points_padded().norm(dim=-1) - 1).abs().max()) < 0.1
+
+
+def test_upsample_matches_reference_golden(golden):
+    g = golden("wlop_upsample")
+    x = torch.as_tensor(g["up_in"], device=DEV)
+    pts, num = pp.upsample(x, 1300, num_points=torch.tensor([1000], device=DEV), neighborhood_size=16)
+    assert int(num[0]) == 1300 and pts.shape == (1, 1300, 3)
+    np.testing.assert_allclose(pts.cpu().numpy(), g["up_pts"], rtol=1e-4, atol=2e-6)
+    pcl = pp.upsample(Pointclouds(x), 1100)
+    assert isinstance(pcl, Pointclouds) and int(pcl.num_points_per_cloud()[0]) == 1100
+    same = pp.upsample(x, 900, num_points=torch.tensor([1000], device=DEV))
+    assert same[0].shape == (1, 1000, 3)
+
+
+def test_project_points_with_upsampling_and_sample_uniform_iso_points():
+    torch.manual_seed(0)
+    sdf = SphereSDF().to(DEV)
+    x = (torch.rand(1, 3000, 3, device=DEV) - 0.5) * 1.5
+    proj = UniformProjection(proj_max_iters=10, proj_tolerance=5e-5, knn_k=8, sample_iters=1)
+    out = proj.project_points(x, sdf)                              # project + resample + upsample + re-project
+    assert out["levelset_points"].shape[1] == 3000
+    m = out["mask"][0]
+    assert float(m.float().mean()) > 0.99
+    assert float((out["levelset_points"][0][m].norm(dim=-1) - 1).abs().max()) < 1e-4
+    pcl = sample_uniform_iso_points(sdf, 2000, bounding_sphere_radius=1.2)
+    n = int(pcl.num_points_per_cloud()[0])
+    assert abs(n - 2000) <= 20
+    p = pcl.points_packed()
+    assert float((p.norm(dim=-1) - 1).abs().max()) < 1e-4
+    # uniformity: nearest-neighbour spacing has a small spread compared with a random sample
+    d = pp.knn_points(p[None], p[None], K=2).dists[0, :, 1].sqrt()
+    rnd = torch.nn.functional.normalize(torch.randn(1, n, 3, device=DEV), dim=-1)
+    d0 = pp.knn_points(rnd, rnd, K=2).dists[0, :, 1].sqrt()
+    assert float(d.std() / d.mean()) < 0.6 * float(d0.std() / d0.mean())

@@ -98,3 +98,15 @@ def test_splat_bin_counts_against_pairs(golden):
     # every point with z >= 0 lands in at least one bin when inside the frame
     z_ok = (g["points"][:, 2] >= 0).sum()
     assert cnt.sum() >= z_ok
+
+
+def test_wlop_and_upsample_match_reference(golden):
+    g = golden("wlop_upsample")
+    P = torch.as_tensor(g["P"])[0]
+    bf = lambda a, b, K, r: torch.as_tensor(port.frnn_bruteforce(a[None].numpy(), b[None].numpy(), K=K, r=r,
+                                                                   inclusive=False)[0][0])
+    X = port.wlop(P, torch.as_tensor(g["noise"]), neighborhood_size=16, iters=3, repulsion_mu=0.5, frnn_fn=bf)
+    np.testing.assert_allclose(X.numpy(), g["wlop"][0], rtol=1e-4, atol=2e-6)
+    up = port.upsample(torch.as_tensor(g["up_in"])[0], 1300, neighborhood_size=16)
+    assert up.shape == (1300, 3) and int(g["up_num"][0]) == 1300
+    np.testing.assert_allclose(up.numpy(), g["up_pts"][0], rtol=1e-5, atol=1e-6)
