@@ -122,6 +122,11 @@ int isob200_splat_occ_backward(const float* points, const float* radii, const un
                                float radii_s, const float* grad_occ, int N, int H, int W,
                                long long max_points_per_cloud, int mode, float* grad_out, int out_stride,
                                void* stream);
+size_t isob200_splat_search_radius_ws_bytes(int N);
+/* per-view median(visible radii) * radii_s: DSS/core/rasterizer.py:881-884 */
+int isob200_splat_search_radius(const float* radii, const unsigned char* visible, const int64_t* first_idx,
+                                const int64_t* num_points, int N, long long max_points_per_cloud, float radii_s,
+                                float* rs, void* ws, size_t ws_bytes, void* stream);
 int isob200_splat_zbuf_backward(const int* idx, const float* grad_zbuf, int N, int H, int W, int K,
                                 float* z_grad, int stride, void* stream);
 int isob200_splat_visibility(const int* idx, const float* mask, long long npix, int K, long long P,

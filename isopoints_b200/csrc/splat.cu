@@ -170,28 +170,54 @@ __device__ __forceinline__ bool zid_less(float z, int id, float z2, int id2) {
   return (z < z2) || (z == z2 && id < id2);
 }
 
+// Per-pixel candidate list in registers: the reference's algorithm (unsorted K slots + running
+// maximum, rasterize_points.cu:99-123) with the order made total by (z, id); ONE sorting network at
+// the end instead of a sorted insertion per hit -- the warp executes the list update whenever any of
+// its 32 pixels is hit, so its instruction count is what bounds the kernel.
 template <int K>
 struct PixList {
   float z[K];
   int id[K];
   float q[K];
+  int cnt;
+  float maxz;
+  int maxid, maxpos;
   __device__ __forceinline__ void clear() {
 #pragma unroll
     for (int k = 0; k < K; ++k) { z[k] = FLT_MAX; id[k] = INT_MAX; q[k] = 0.f; }
+    cnt = 0; maxz = -FLT_MAX; maxid = -1; maxpos = 0;
   }
-  // keep the K smallest (z, id), ascending
   __device__ __forceinline__ void insert(float cz, int cid, float cq) {
-    if (!zid_less(cz, cid, z[K - 1], id[K - 1])) return;
+    if (cnt < K) {
 #pragma unroll
-    for (int k = K - 1; k > 0; --k) {
-      const bool shift = zid_less(cz, cid, z[k - 1], id[k - 1]);   // candidate sits before slot k-1
-      const bool here = !shift && zid_less(cz, cid, z[k], id[k]);
-      const float nz = shift ? z[k - 1] : (here ? cz : z[k]);
-      const int ni = shift ? id[k - 1] : (here ? cid : id[k]);
-      const float nq = shift ? q[k - 1] : (here ? cq : q[k]);
-      z[k] = nz; id[k] = ni; q[k] = nq;
+      for (int k = 0; k < K; ++k)
+        if (k == cnt) { z[k] = cz; id[k] = cid; q[k] = cq; }
+      if (zid_less(maxz, maxid, cz, cid)) { maxz = cz; maxid = cid; maxpos = cnt; }
+      ++cnt;
+    } else if (zid_less(cz, cid, maxz, maxid)) {
+#pragma unroll
+      for (int k = 0; k < K; ++k)
+        if (k == maxpos) { z[k] = cz; id[k] = cid; q[k] = cq; }
+      maxz = z[0]; maxid = id[0]; maxpos = 0;
+#pragma unroll
+      for (int k = 1; k < K; ++k)
+        if (zid_less(maxz, maxid, z[k], id[k])) { maxz = z[k]; maxid = id[k]; maxpos = k; }
     }
-    if (zid_less(cz, cid, z[0], id[0])) { z[0] = cz; id[0] = cid; q[0] = cq; }
+  }
+  __device__ __forceinline__ void cswap(int a, int b) {
+    const bool sw = zid_less(z[b], id[b], z[a], id[a]);
+    const float tz = sw ? z[b] : z[a], uz = sw ? z[a] : z[b];
+    const int ti = sw ? id[b] : id[a], ui = sw ? id[a] : id[b];
+    const float tq = sw ? q[b] : q[a], uq = sw ? q[a] : q[b];
+    z[a] = tz; z[b] = uz; id[a] = ti; id[b] = ui; q[a] = tq; q[b] = uq;
+  }
+  // ascending (z, id); empty slots (FLT_MAX, INT_MAX) sink to the end.  Odd-even transposition network.
+  __device__ __forceinline__ void sort() {
+#pragma unroll
+    for (int r = 0; r < K; ++r) {
+#pragma unroll
+      for (int k = (r & 1); k + 1 < K; k += 2) cswap(k, k + 1);
+    }
   }
 };
 
@@ -287,12 +313,10 @@ splat_raster_kernel(const float4* __restrict__ recs, const int* __restrict__ til
   }
 
   if (!in_img) return;
-  // epilogue: depth-merge cut (:203-206), occupancy (:196 naive >=, :581 fine >), -1 padding
-  int size = 0;
-  float zmax = -1000.0f;
-#pragma unroll
-  for (int k = 0; k < K; ++k)
-    if (L.id[k] != INT_MAX) { size = k + 1; zmax = L.z[k]; }
+  // epilogue: sort, depth-merge cut (:203-206), occupancy (:196 naive >=, :581 fine >), -1 padding
+  L.sort();
+  const int size = L.cnt;
+  const float zmax = size > 0 ? L.maxz : -1000.0f;
   const float z0 = L.z[0];
   bool alive = true;
   int oi[K];

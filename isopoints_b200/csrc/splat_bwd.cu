@@ -83,25 +83,41 @@ splat_occ_backward_kernel(const float* __restrict__ points, const float* __restr
       pixel_window(py, wy, H, fH, yl, yh);
       if (xl <= xh && yl <= yh) {
         const int c_lo = W - 1 - xh, c_hi = W - 1 - xl;   // output columns (x is flipped)
-        for (int yi = yl; yi <= yh; ++yi) {
-          const float dy = __fsub_rn(pix_to_ndc_b(yi, fH), py);
-          if (MODE == 1 && fabsf(dy) > wy) continue;
-          const float* g_row = g_img + (size_t)(H - 1 - yi) * W;
-          for (int col = c_lo + lane; col <= c_hi; col += 32) {
-            const float g = g_row[col];
-            if (g == 0.0f) continue;
-            const float dx = __fsub_rn(pix_to_ndc_b(W - 1 - col, fW), px);
-            const float d2 = __fmaf_rn(dx, dx, __fmul_rn(dy, dy));   // SASS: FMUL dy*dy ; FFMA dx
-            if (MODE == 0) {
-              if (d2 > r2) continue;
-            } else {
-              if (fabsf(dx) > wx) continue;
+        // lane = column: dx is row independent, so it is formed once per 32-column chunk; the
+        // per-row dy comes from a lane that computed ndc(y) for 32 rows at once (one shuffle per
+        // row instead of an int->float + IEEE division per pixel).
+        for (int cb = c_lo; cb <= c_hi; cb += 32) {
+          const int col = cb + lane;
+          const bool col_ok = col <= c_hi;
+          const float dx = __fsub_rn(pix_to_ndc_b(W - 1 - col, fW), px);
+          const bool x_out = fabsf(dx) > bx;              // outside the splat's radii box in x
+          const bool x_far = (MODE == 1) && (fabsf(dx) > wx);
+          const float* g_col = g_img + (col_ok ? col : c_lo);
+          for (int rb = yl; rb <= yh; rb += 32) {
+            const float dy_l = __fsub_rn(pix_to_ndc_b(min(rb + lane, H - 1), fH), py);
+            const int nr = min(32, yh - rb + 1);
+#pragma unroll 4
+            for (int r = 0; r < nr; ++r) {
+              const float g = g_col[(size_t)(H - 1 - (rb + r)) * W];
+              const float dy = __shfl_sync(0xffffffffu, dy_l, r);
+              if (g == 0.0f || !col_ok) continue;
+              const float d2 = __fmaf_rn(dx, dx, __fmul_rn(dy, dy));   // SASS: FMUL dy*dy ; FFMA dx
+              if (MODE == 0) {
+                if (d2 > r2) continue;
+              } else {
+                if (x_far || fabsf(dy) > wy) continue;
+              }
+              if (g > 0.0f && (x_out || fabsf(dy) > by)) continue;
+              // dx / eps_denom(d2, 1e-10) * g with the device eps_denom's sign(0) = 0 (0/0 -> NaN kept);
+              // the quotient goes through the SFU reciprocal (1 ulp): gradients are fp32 sums whose
+              // order the reference itself does not fix
+              const float den = (d2 > 0.0f) ? fmaxf(d2, 1e-10f) : 0.0f;
+              float inv;
+              asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(inv) : "f"(den));
+              const float w = inv * g;
+              gx = fmaf(dx, w, gx);
+              gy = fmaf(dy, w, gy);
             }
-            const bool outside = (fabsf(dx) > bx) || (fabsf(dy) > by);
-            if (g > 0.0f && outside) continue;
-            const float den = eps_denom_dev(d2, 1e-10f);
-            gx += __fmul_rn(__fdiv_rn(dx, den), g);
-            gy += __fmul_rn(__fdiv_rn(dy, den), g);
           }
         }
       }
@@ -116,6 +132,68 @@ splat_occ_backward_kernel(const float* __restrict__ points, const float* __restr
       grad_out[(size_t)p * out_stride + 1] = gy;
     }
   }
+}
+
+// ---- per-view search radius: median(radii of the view's visible points) * radii_s -------------
+// (rasterizer.py:884; torch.median = lower middle of the flattened (n_visible, 2) values).  Exact
+// radix select on the order-preserving uint image of the floats: 4 passes of 8 bits, one
+// histogram sweep + one tiny select kernel per pass; no sort, no host round trip.
+__device__ __forceinline__ unsigned f2ord_b(float f) {
+  const unsigned u = __float_as_uint(f);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float ord2f_b(unsigned u) {
+  return __uint_as_float((u & 0x80000000u) ? (u & 0x7fffffffu) : ~u);
+}
+
+// state per view: [0] prefix bits fixed so far, [1] rank still to descend, [2] done flag
+__global__ void __launch_bounds__(256)
+median_hist_kernel(const float* __restrict__ radii, const unsigned char* __restrict__ visible,
+                   const int64_t* __restrict__ first_idx, const int64_t* __restrict__ num_points, int shift,
+                   const unsigned* __restrict__ state, unsigned* __restrict__ hist) {
+  __shared__ unsigned sh[256];
+  const int n = blockIdx.y;
+  sh[threadIdx.x] = 0;
+  __syncthreads();
+  const long long first = first_idx[n], num = num_points[n];
+  const unsigned prefix = state[n * 4 + 0];
+  const unsigned himask = (shift >= 24) ? 0u : (0xffffffffu << (shift + 8));
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < 2 * num;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long p = first + (i >> 1);
+    if (visible && !visible[p]) continue;
+    const unsigned u = f2ord_b(radii[2 * first + i]);
+    if (((u ^ prefix) & himask) == 0) atomicAdd(&sh[(u >> shift) & 255u], 1u);
+  }
+  __syncthreads();
+  if (sh[threadIdx.x]) atomicAdd(&hist[n * 256 + threadIdx.x], sh[threadIdx.x]);
+}
+
+__global__ void median_select_kernel(unsigned* __restrict__ state, unsigned* __restrict__ hist, int shift,
+                                     int first_pass, int last_pass, float radii_s, float* __restrict__ rs) {
+  const int n = blockIdx.x;
+  if (threadIdx.x != 0) return;
+  unsigned* h = hist + n * 256;
+  unsigned* s = state + n * 4;
+  if (first_pass) {
+    unsigned long long cnt = 0;
+    for (int b = 0; b < 256; ++b) cnt += h[b];
+    s[2] = (cnt == 0);
+    s[1] = cnt ? (unsigned)((cnt - 1) / 2) : 0u;
+  }
+  if (!s[2]) {
+    unsigned k = s[1], acc = 0;
+    int b = 0;
+    for (; b < 256; ++b) {
+      if (acc + h[b] > k) break;
+      acc += h[b];
+    }
+    b = min(b, 255);
+    s[0] |= ((unsigned)b) << shift;
+    s[1] = k - acc;
+  }
+  for (int b = 0; b < 256; ++b) h[b] = 0;
+  if (last_pass) rs[n] = s[2] ? 0.0f : __fmul_rn(ord2f_b(s[0]), radii_s);
 }
 
 // z_grad[idx] += grad_zbuf; zero gradients skipped, stop at the first -1 (rasterize_points.cu:835-843)
@@ -240,6 +318,35 @@ int isob200_splat_occ_backward(const float* points, const float* radii, const un
     splat_occ_backward_kernel<1><<<dim3(bx, N), 256, 0, st>>>(points, radii, visible, first_idx, num_points, rs,
                                                              radii_s, grad_occ, H, W, grad_out, out_stride);
   ISO_CHECK_LAUNCH("splat_occ_backward_kernel");
+  return ISOB200_OK;
+}
+
+size_t isob200_splat_search_radius_ws_bytes(int N) { return align_up((size_t)N * (256 + 4) * sizeof(unsigned)); }
+
+// rs[n] = median(radii[visible rows of view n].flatten()) * radii_s  (rasterizer.py:881-884), 0 for a view
+// without visible points.  visible may be NULL (all rows).
+int isob200_splat_search_radius(const float* radii, const unsigned char* visible, const int64_t* first_idx,
+                                const int64_t* num_points, int N, long long max_points_per_cloud, float radii_s,
+                                float* rs, void* ws, size_t ws_bytes, void* stream_) {
+  cudaStream_t st = (cudaStream_t)stream_;
+  if (N <= 0) return ISOB200_OK;
+  ISO_CHECK_ARG(radii && first_idx && num_points && rs && ws, "splat_search_radius: null pointer");
+  if (ws_bytes < isob200_splat_search_radius_ws_bytes(N)) {
+    set_error("splat_search_radius: workspace too small");
+    return ISOB200_ERR_WORKSPACE;
+  }
+  unsigned* hist = (unsigned*)ws;
+  unsigned* state = hist + (size_t)N * 256;
+  ISO_CUDA(cudaMemsetAsync(ws, 0, (size_t)N * (256 + 4) * sizeof(unsigned), st));
+  int bx = grid_for(2 * max(max_points_per_cloud, 1ll), 256, 4);
+  if (N > 1) bx = max(1, min(bx, (kNumSMs * 4 + N - 1) / N));
+  for (int pass = 0; pass < 4; ++pass) {
+    const int shift = 24 - 8 * pass;
+    median_hist_kernel<<<dim3(bx, N), 256, 0, st>>>(radii, visible, first_idx, num_points, shift, state, hist);
+    ISO_CHECK_LAUNCH("median_hist_kernel");
+    median_select_kernel<<<N, 32, 0, st>>>(state, hist, shift, pass == 0, pass == 3, radii_s, rs);
+    ISO_CHECK_LAUNCH("median_select_kernel");
+  }
   return ISOB200_OK;
 }
 

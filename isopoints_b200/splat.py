@@ -226,22 +226,25 @@ class _CExt:
 _C = _CExt()
 
 
-def per_view_median_radius(radii, visible, first_idx, num_points):
-    """median over the flattened (n_visible, 2) radii of every view (rasterizer.py:884; torch.median =
-    lower middle), without host synchronisation.  Views with no visible point get 0."""
-    P = radii.shape[0]
-    N = num_points.shape[0]
+def per_view_search_radius(radii, visible, first_idx, num_points, radii_s=1.0):
+    """(N,) median over the flattened (n_visible, 2) radii of every view, times ``radii_s``
+    (rasterizer.py:881-884; torch.median = lower middle): exact radix select on the device, no sort and
+    no host synchronisation.  Views with no visible point get 0."""
+    lib = _ext.lib()
+    radii = _f32c(radii, "radii")
     dev = radii.device
-    view = torch.repeat_interleave(torch.arange(N, device=dev), num_points, output_size=P)
-    vals = torch.where(visible[:, None], radii, torch.full_like(radii, float("inf"))).reshape(-1)
-    view2 = view.repeat_interleave(2)
-    v_sorted, o1 = torch.sort(vals)
-    o2 = torch.sort(view2[o1], stable=True).indices
-    grouped = v_sorted[o2]                                   # ascending inside each view's 2*num slice
-    cnt = torch.zeros((N,), dtype=torch.int64, device=dev).index_add_(0, view, visible.to(torch.int64)) * 2
-    pos = 2 * first_idx + (cnt - 1).clamp_min(0) // 2
-    med = grouped[pos.clamp(0, max(2 * P - 1, 0))] if P > 0 else torch.zeros((N,), device=dev)
-    return torch.where(cnt > 0, med, torch.zeros_like(med))
+    N = num_points.shape[0]
+    rs = torch.empty((N,), dtype=torch.float32, device=dev)
+    ws = _ext.workspace(lib.isob200_splat_search_radius_ws_bytes(N), dev)
+    vis = None if visible is None else visible.view(torch.uint8)
+    _ext.check(lib.isob200_splat_search_radius(_ext.ptr(radii), _ext.ptr(vis), _ext.ptr(_i64c(first_idx, dev)),
+                                               _ext.ptr(_i64c(num_points, dev)), N, radii.shape[0], float(radii_s),
+                                               _ext.ptr(rs), _ext.ptr(ws), ws.numel(), _ext.stream(dev)))
+    return rs
+
+
+def per_view_median_radius(radii, visible, first_idx, num_points):
+    return per_view_search_radius(radii, visible, first_idx, num_points, 1.0)
 
 
 class EllipticalRasterizer(autograd.Function):
@@ -276,7 +279,7 @@ class EllipticalRasterizer(autograd.Function):
         grads = torch.zeros((P, 3), dtype=torch.float32, device=dev)
         if occ_grad is not None and P > 0:
             vis = visibility_mask(idx, P)                                    # rasterizer.py:851-857
-            rs = (per_view_median_radius(radii, vis, first_idx, num_points) * radii_s).contiguous()   # :884
+            rs = per_view_search_radius(radii, vis, first_idx, num_points, radii_s)             # :881-884
             _occ_backward(pts, radii, vis.view(torch.uint8), first_idx, num_points, rs, radii_s,
                           _f32c(occ_grad, "occ_grad"), 0, grads, 3)
         if zbuf_grad is not None and P > 0:
