@@ -35,6 +35,15 @@ __device__ __forceinline__ float sqdist_ref(const float* __restrict__ p2, const 
   return s;
 }
 
+// Squared distance (in world units, conservative: never larger than the true minimum) from the
+// query at cell-space coordinate qc to cell index i along one axis.  The slack of 1e-3 cell
+// absorbs the fp32 rounding of (p - min) * delta that assigned points to cells.
+__device__ __forceinline__ float axis_gap2(float qc, int i, float inv_delta) {
+  const float g = fmaxf(fmaxf((float)i - qc, qc - (float)(i + 1)), 0.0f);
+  const float gs = fmaxf(g - 1e-3f, 0.0f) * inv_delta;
+  return gs * gs;
+}
+
 template <int D, int GW, typename IdxT>
 __global__ void __launch_bounds__(256)
 frnn_query_kernel(const float* __restrict__ q_points,     // (N,P1,D) in processing order
@@ -73,73 +82,103 @@ frnn_query_kernel(const float* __restrict__ q_points,     // (N,P1,D) in process
     const float* prm = params + (size_t)n * PS;
     const float r = rs[n];
     const float r2 = __fmul_rn(r, r);
-    float q[D];
+    const float delta = prm[D];
+    const float inv_delta = 1.0f / delta;
+    float q[D], qc[D];
 #pragma unroll
     for (int d = 0; d < D; ++d) q[d] = q_points[((size_t)n * P1 + s) * D + d];
 
     // candidate cell range, grid.cu:305-316 (fp32: (p - min -/+ r) * delta, floor)
-    int lo[D], hi[D], res[D];
+    int lo[D], hi[D], res[D], cq[D];
+    bool nonempty = true;
 #pragma unroll
     for (int d = 0; d < D; ++d) {
       const float rel = __fsub_rn(q[d], prm[d]);
-      const float delta = prm[D];
       res[d] = (int)prm[D + 1 + d];
       lo[d] = max(__float2int_rd(__fmul_rn(__fsub_rn(rel, r), delta)), 0);
       hi[d] = min(__float2int_rd(__fmul_rn(__fadd_rn(rel, r), delta)), res[d] - 1);
+      nonempty = nonempty && (lo[d] <= hi[d]);
+      qc[d] = rel * delta;
+      cq[d] = min(max(__float2int_rd(qc[d]), lo[d]), hi[d]);
     }
     const int grid_total = (int)prm[2 * D + 1];
 
     float best_d = FLT_MAX;   // lane gl holds the gl-th best (dist, idx), ascending
     int best_i = INT_MAX;
-    float kth_d = FLT_MAX;    // current K-th best distance (pruning bound), group-uniform
+    float bound = r2;         // min(r2, current K-th best distance): group-uniform pruning bound
 
     const float* pts2 = sorted_points2 + (size_t)n * P2 * D;
     const int* off2 = cell_off2 + (size_t)n * G;
     const int* sid2 = sorted_idxs2 + (size_t)n * P2;
 
-    bool nonempty = true;
-#pragma unroll
-    for (int d = 0; d < D; ++d) nonempty = nonempty && (lo[d] <= hi[d]);
     if (nonempty) {
-      const int ny = (D == 3) ? (hi[1] - lo[1] + 1) : 1;
-      const int nruns = (hi[0] - lo[0] + 1) * ny;  // <= 0 when empty
-      for (int run = 0; run < nruns; ++run) {
-        int c0, c1;
-        if (D == 3) {
-          const int x = lo[0] + run / ny, y = lo[1] + run % ny;
-          c0 = (x * res[1] + y) * res[2] + lo[2];
-          c1 = (x * res[1] + y) * res[2] + hi[2];
-        } else {
-          const int x = lo[0] + run;
-          c0 = x * res[1] + lo[1];
-          c1 = x * res[1] + hi[1];
-        }
-        const int start = off2[c0];
-        const int end = (c1 + 1 == grid_total) ? len2 : off2[c1 + 1];
-        for (int base = start; base < end; base += GW) {
-          const int j = base + gl;
-          const bool valid = j < end;
-          float d = FLT_MAX;
-          if (valid) d = sqdist_ref<D>(pts2 + (size_t)j * D, q);
-          const bool cand = valid && (d <= r2) && (d <= kth_d);
-          unsigned m = __ballot_sync(gmask, cand) & gmask;
-          if (m == 0) continue;
-          int ci_mine = cand ? sid2[j] : INT_MAX;
-          while (m) {
-            const int src = __ffs(m) - 1;
-            m &= m - 1;
-            const float cd = __shfl_sync(gmask, d, src);
-            const int ci = __shfl_sync(gmask, ci_mine, src);
-            const bool less = (best_d < cd) || (best_d == cd && best_i < ci);
-            const int pos = __popc(__ballot_sync(gmask, less) & gmask);
-            const float up_d = __shfl_up_sync(gmask, best_d, 1, GW);
-            const int up_i = __shfl_up_sync(gmask, best_i, 1, GW);
-            if (pos < K) {
-              if (gl > pos) { best_d = up_d; best_i = up_i; }
-              else if (gl == pos) { best_d = cd; best_i = ci; }
+      // Best-first traversal: rings of runs around the query's own cell.  Once K candidates are
+      // held, a run (and the far cells of a run) whose closest possible point is beyond the K-th
+      // best distance cannot change the result (strict >, so equal-distance ties still compete)
+      // and is skipped.  The visited set shrinks from (2r/cell+1)^D cells to those overlapping the
+      // K-th-neighbour ball; the result is the same K smallest (dist, index) pairs.
+      const int R0 = max(cq[0] - lo[0], hi[0] - cq[0]);
+      const int R1 = (D == 3) ? max(cq[1] - lo[1], hi[1] - cq[1]) : 0;
+      const int R = max(R0, R1);
+      for (int ring = 0; ring <= R; ++ring) {
+        const int xstep = (D == 2) ? max(2 * ring, 1) : 1;   // 2-D: the ring is just the two end cells
+        for (int ox = -ring; ox <= ring; ox += xstep) {
+          const int x = cq[0] + ox;
+          if (x < lo[0] || x > hi[0]) continue;
+          const float gx2 = axis_gap2(qc[0], x, inv_delta);
+          if (gx2 > bound) continue;
+          const int ystep = (D == 3 && (ox == -ring || ox == ring)) ? 1 : max(2 * ring, 1);
+          for (int oy = (D == 3 ? -ring : 0); oy <= (D == 3 ? ring : 0); oy += ystep) {
+            int c0, c1;
+            float gxy2 = gx2;
+            int zlo, zhi;       // cell range along the fastest axis
+            float qcz;
+            if (D == 3) {
+              const int y = cq[1] + oy;
+              if (y < lo[1] || y > hi[1]) continue;
+              gxy2 += axis_gap2(qc[1], y, inv_delta);
+              if (gxy2 > bound) continue;
+              zlo = lo[2]; zhi = hi[2]; qcz = qc[2];
+              c0 = (x * res[1] + y) * res[2];
+            } else {
+              zlo = lo[1]; zhi = hi[1]; qcz = qc[1];
+              c0 = x * res[1];
+            }
+            // shrink the run to the cells that can still hold a candidate within `bound`
+            const float gz = sqrtf(fmaxf(bound - gxy2, 0.0f)) * delta + 2e-3f;
+            zlo = max(zlo, __float2int_ru(qcz - 1.0f - gz));
+            zhi = min(zhi, __float2int_rd(qcz + gz));
+            if (zlo > zhi) continue;
+            c1 = c0 + zhi;
+            c0 = c0 + zlo;
+            const int start = off2[c0];
+            const int end = (c1 + 1 == grid_total) ? len2 : off2[c1 + 1];
+            for (int base = start; base < end; base += GW) {
+              const int j = base + gl;
+              const bool valid = j < end;
+              float d = FLT_MAX;
+              if (valid) d = sqdist_ref<D>(pts2 + (size_t)j * D, q);
+              const bool cand = valid && (d <= bound);
+              unsigned m = __ballot_sync(gmask, cand) & gmask;
+              if (m == 0) continue;
+              int ci_mine = cand ? sid2[j] : INT_MAX;
+              while (m) {
+                const int src = __ffs(m) - 1;
+                m &= m - 1;
+                const float cd = __shfl_sync(gmask, d, src);
+                const int ci = __shfl_sync(gmask, ci_mine, src);
+                const bool less = (best_d < cd) || (best_d == cd && best_i < ci);
+                const int pos = __popc(__ballot_sync(gmask, less) & gmask);
+                const float up_d = __shfl_up_sync(gmask, best_d, 1, GW);
+                const int up_i = __shfl_up_sync(gmask, best_i, 1, GW);
+                if (pos < K) {
+                  if (gl > pos) { best_d = up_d; best_i = up_i; }
+                  else if (gl == pos) { best_d = cd; best_i = ci; }
+                }
+              }
+              bound = fminf(r2, __shfl_sync(gmask, best_d, (int)gshift + K - 1));
             }
           }
-          kth_d = __shfl_sync(gmask, best_d, (int)gshift + K - 1);
         }
       }
     }
