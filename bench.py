@@ -241,11 +241,10 @@ def run_ours(args):
     if rank == 0:
         if world == 1:
             line["cpu_baseline"] = cpu_baseline(sample_points=args.cpu_sample)
-            try:
-                import bench_splat
-                line["splat"] = bench_splat.run(args, dev, peaks, peak_src)
-            except ImportError:
-                pass
+            import bench_frnn
+            import bench_splat
+            line["frnn"] = bench_frnn.run(args, dev, peaks, peak_src)
+            line["splat"] = bench_splat.run(args, dev, peaks, peak_src)
         print(json.dumps(line))
     if world > 1:
         import torch.distributed as dist

@@ -1,0 +1,74 @@
+"""BASELINE.json configs[2] ("C3"): 500 000 points, FRNN radius = 0.05, K = 16 grid query, reported under
+"frnn" in bench.py's JSON line (N = 1) and runnable alone:  python bench_frnn.py"""
+import json
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+P, K, R = 500_000, 16, 0.05
+
+
+def run(args, dev, peaks, peak_src, steps=None):
+    from isopoints_b200 import _ext, frnn
+    steps = steps or max(5, args.steps)
+    g = torch.Generator().manual_seed(0)
+    host = torch.rand(1, P, 3, generator=g)
+    pin = host.pin_memory()
+    p = host.to(dev)
+    lens = torch.tensor([P], device=dev)
+    r = torch.tensor([R], device=dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    for _ in range(3):
+        frnn.frnn_grid_points(p, p, lens, lens, K=K, r=r)
+    torch.cuda.synchronize()
+    _ext.PROFILE = {}
+    ms = 0.0
+    for k in range(steps):
+        flush.fill_(k & 0xff)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        d, i, _, _ = frnn.frnn_grid_points(p, p, lens, lens, K=K, r=r)
+        b.record()
+        torch.cuda.synchronize()
+        ms += a.elapsed_time(b)
+    ms /= steps
+    prof, _ext.PROFILE = _ext.PROFILE, None
+    kern = {n.replace("isob200_", ""): sum(x.elapsed_time(y) for x, y in v) / len(v) for n, v in prof.items()}
+    import time
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        x = pin.to(dev, non_blocking=True)
+        d, i, _, _ = frnn.frnn_grid_points(x, x, lens, lens, K=K, r=r)
+        dh, ih = d.cpu(), i.cpu()
+    torch.cuda.synchronize()
+    e2e_ms = (time.perf_counter() - t0) / steps * 1e3
+    alg = P * (16 + 12 * K)                      # 16 + 12K bytes per query
+    q = kern.get("frnn_find_nbrs")
+    roof = None
+    if q:
+        ach = alg / (q * 1e-3) / 1e9
+        roof = {"kernel": "frnn_query_kernel<3,16,int64>", "bound": "hbm", "achieved": ach, "peak": peaks["hbm_gbs"],
+                "unit": "GB/s", "frac": ach / peaks["hbm_gbs"], "traffic": None, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": alg, "avg_launch_ms": q}
+    return {"metric": "FRNN queries/sec", "unit": "queries/s",
+            "config": {"workload": "C3: %d uniform points in the unit box, self query, K=%d, r=%g, radius_cell_ratio=2"
+                                   % (P, K, R), "l2": "flushed between steps"},
+            "value": P / (ms * 1e-3), "ms_per_step": ms, "avg_neighbours_found": float((i >= 0).float().sum(-1).mean()),
+            "e2e": {"value": P / (e2e_ms * 1e-3), "unit": "queries/s", "ms_per_step": e2e_ms,
+                    "h2d_bytes_per_step": host.numel() * 4, "d2h_bytes_per_step": dh.numel() * 4 + ih.numel() * 8},
+            "roofline": roof, "kernels_avg_ms": kern}
+
+
+if __name__ == "__main__":
+    import argparse
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--steps", type=int, default=5)
+    a = ap.parse_args()
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))); src = "measured"
+    except Exception:
+        peaks, src = {"hbm_gbs": 6650.0}, "fallback"
+    print(json.dumps(run(a, torch.device("cuda", 0), peaks, src)))
