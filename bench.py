@@ -32,6 +32,14 @@ import torch
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+
+def _ncu_traffic(kernel):
+    """dram bytes per launch of `kernel` from the committed ncu --set full capture (profiles/ncu_traffic.json)."""
+    try:
+        return json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))[kernel]["dram_bytes_per_launch"]
+    except Exception:
+        return None
+
 C2_POINTS = 200_000
 L2_FLUSH_BYTES = 256 << 20
 
@@ -217,7 +225,7 @@ def run_ours(args):
         alg = n_q * (16 + 12 * K)                       # 16 + 12K bytes per query
         achieved = alg / (q["avg_ms"] * 1e-3) / 1e9
         roof = {"kernel": "frnn_query_kernel", "bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"],
-                "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"], "traffic": None, "peak_source": peak_src,
+                "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"], "traffic": _ncu_traffic("frnn_query_kernel"), "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": alg, "avg_launch_ms": q["avg_ms"]}
 
     line = {

@@ -11,6 +11,14 @@ import torch
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+
+def _ncu_traffic(kernel):
+    """dram bytes per launch of `kernel` from the committed ncu --set full capture (profiles/ncu_traffic.json)."""
+    try:
+        return json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))[kernel]["dram_bytes_per_launch"]
+    except Exception:
+        return None
+
 V, PV, S, K = 8, 300_000, 512, 8
 
 
@@ -92,7 +100,7 @@ def run(args, dev, peaks, peak_src, steps=None):
     if f:
         ach = alg / (f["avg_ms"] * 1e-3) / 1e9
         roof = {"kernel": "splat_tile_fill + splat_raster_kernel<8>", "bound": "hbm", "achieved": ach,
-                "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": ach / peaks["hbm_gbs"], "traffic": None,
+                "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": ach / peaks["hbm_gbs"], "traffic": _ncu_traffic("splat_raster_kernel"),
                 "peak_source": peak_src, "algorithmic_bytes_per_launch": alg, "avg_launch_ms": f["avg_ms"]}
     return {"metric": "pixel-splats/sec", "unit": "pixel-splats/s",
             "config": {"workload": "C4: %d views x %d splats, %dx%d, K=%d, sigma=1.5px, occ_grad on 10%% of pixels, "

@@ -51,7 +51,8 @@ project_step_kernel(float* __restrict__ points, float* __restrict__ normals,
                     unsigned char* __restrict__ not_converged, const int* __restrict__ act_in,
                     int A, const float* __restrict__ sdf, const float* __restrict__ grad,
                     float tol, float max_step, int do_update, int* __restrict__ act_out,
-                    int* __restrict__ count_out, unsigned* __restrict__ ws) {
+                    float* __restrict__ next_points, int* __restrict__ count_out,
+                    unsigned* __restrict__ ws) {
   __shared__ int s_tile;
   __shared__ int s_warp[PJ_THREADS / 32];
   __shared__ int s_prefix;
@@ -64,6 +65,7 @@ project_step_kernel(float* __restrict__ points, float* __restrict__ normals,
 
   int keep[PJ_ITEMS];
   int id[PJ_ITEMS];
+  float nx[PJ_ITEMS][3];   // position after the update (the next SDF evaluation's input row)
   int cnt = 0;
 #pragma unroll
   for (int j = 0; j < PJ_ITEMS; ++j) {
@@ -82,6 +84,10 @@ project_step_kernel(float* __restrict__ points, float* __restrict__ normals,
       if (not_converged) not_converged[p] = still ? 1 : 0;
       if (still) {
         keep[j] = 1;
+        {
+          const float* q0 = points + 3 * (size_t)p;
+          nx[j][0] = q0[0]; nx[j][1] = q0[1]; nx[j][2] = q0[2];
+        }
         if (do_update) {
           const float ss = __fadd_rn(__fadd_rn(__fmul_rn(gx, gx), __fmul_rn(gy, gy)), __fmul_rn(gz, gz));
           const float den = eps_denom_f(ss, 1.0e-17f);
@@ -92,9 +98,10 @@ project_step_kernel(float* __restrict__ points, float* __restrict__ normals,
           const float dn = fmaxf(nrm, 1e-15f);        // F.normalize(eps=1e-15)
           const float len = fminf(nrm, max_step);     // clamp_max(0.1)
           float* q = points + 3 * (size_t)p;
-          q[0] = __fsub_rn(q[0], __fmul_rn(__fdiv_rn(mx, dn), len));
-          q[1] = __fsub_rn(q[1], __fmul_rn(__fdiv_rn(my, dn), len));
-          q[2] = __fsub_rn(q[2], __fmul_rn(__fdiv_rn(mz, dn), len));
+          nx[j][0] = __fsub_rn(nx[j][0], __fmul_rn(__fdiv_rn(mx, dn), len));
+          nx[j][1] = __fsub_rn(nx[j][1], __fmul_rn(__fdiv_rn(my, dn), len));
+          nx[j][2] = __fsub_rn(nx[j][2], __fmul_rn(__fdiv_rn(mz, dn), len));
+          q[0] = nx[j][0]; q[1] = nx[j][1]; q[2] = nx[j][2];
         }
       }
     }
@@ -142,7 +149,15 @@ project_step_kernel(float* __restrict__ points, float* __restrict__ normals,
   int pos = s_prefix + woff + incl - cnt;
 #pragma unroll
   for (int j = 0; j < PJ_ITEMS; ++j)
-    if (keep[j]) act_out[pos++] = id[j];
+    if (keep[j]) {
+      act_out[pos] = id[j];
+      if (next_points) {   // compacted input of the next SDF evaluation: no separate gather pass
+        next_points[3 * (size_t)pos + 0] = nx[j][0];
+        next_points[3 * (size_t)pos + 1] = nx[j][1];
+        next_points[3 * (size_t)pos + 2] = nx[j][2];
+      }
+      ++pos;
+    }
 }
 
 // dst[i, :] = src[idx[i], :]   (curr_points = points_packed[not_converged], :315)
@@ -215,10 +230,12 @@ size_t isob200_project_step_ws_bytes(int A) {
 //   do_update       : 0 for the final evaluation (it == proj_max_iters, :329): flags and normals
 //                     are refreshed but points do not move
 //   act_out (>=A ints), count_out (device int): compacted still-active rows and their number
+//   next_points (>=A x 3 floats, may be NULL): updated positions of the still-active rows, compacted in
+//                     the same order -- points[act_out] without a gather pass (:315 of the next iteration)
 int isob200_project_step(float* points, float* normals, unsigned char* not_converged,
                          const int* act_in, int A, const float* sdf, const float* grad, float tol,
-                         float max_step, int do_update, int* act_out, int* count_out, void* ws,
-                         size_t ws_bytes, void* stream_) {
+                         float max_step, int do_update, int* act_out, float* next_points,
+                         int* count_out, void* ws, size_t ws_bytes, void* stream_) {
   cudaStream_t st = (cudaStream_t)stream_;
   ISO_CHECK_ARG(A >= 0, "project_step: negative A");
   ISO_CHECK_ARG(count_out, "project_step: null count_out");
@@ -236,8 +253,8 @@ int isob200_project_step(float* points, float* normals, unsigned char* not_conve
   ISO_CUDA(cudaMemsetAsync(ws, 0, need, st));
   const int tiles = div_up(A, PJ_TILE);
   project_step_kernel<<<tiles, PJ_THREADS, 0, st>>>(points, normals, not_converged, act_in, A, sdf, grad,
-                                                   tol, max_step, do_update, act_out, count_out,
-                                                   (unsigned*)ws);
+                                                   tol, max_step, do_update, act_out, next_points,
+                                                   count_out, (unsigned*)ws);
   ISO_CHECK_LAUNCH("project_step_kernel");
   return ISOB200_OK;
 }

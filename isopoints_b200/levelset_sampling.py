@@ -172,15 +172,13 @@ class UniformProjection(LevelSetProjection):
                 ws = _ext.workspace(lib.isob200_project_step_ws_bytes(M), dev)
                 nc_u8 = not_converged.view(torch.uint8)
                 act_in, act_out = None, act_a
+                nxt_a = torch.empty((M, 3), dtype=torch.float32, device=dev)   # compacted next SDF inputs
+                nxt_b = torch.empty((M, 3), dtype=torch.float32, device=dev)
+                nxt_in, nxt_out = None, nxt_a
                 A = M
                 it = 0
                 while True:
-                    if act_in is None:
-                        curr_points = points_packed
-                    else:
-                        curr_points = torch.empty((A, 3), dtype=torch.float32, device=dev)
-                        _ext.check(lib.isob200_gather_rows3(_ext.ptr(points_packed), _ext.ptr(act_in), A,
-                                                            _ext.ptr(curr_points), _ext.stream(dev)))
+                    curr_points = points_packed if act_in is None else nxt_in[:A]
                     curr_sdf, curr_grad = self._compute_sdf_and_grad(curr_points, model, **forward_kwargs)
                     curr_sdf = curr_sdf.reshape(-1).contiguous().float()
                     curr_grad = curr_grad.reshape(-1, 3).contiguous().float()
@@ -188,8 +186,9 @@ class UniformProjection(LevelSetProjection):
                     _ext.check(lib.isob200_project_step(
                         _ext.ptr(points_packed), _ext.ptr(normals_packed), _ext.ptr(nc_u8),
                         _ext.ptr(act_in), A, _ext.ptr(curr_sdf), _ext.ptr(curr_grad),
-                        float(proj_tolerance), 0.1, 0 if last else 1, _ext.ptr(act_out), _ext.ptr(count),
-                        _ext.ptr(ws), ws.numel(), _ext.stream(dev)))
+                        float(proj_tolerance), 0.1, 0 if last else 1, _ext.ptr(act_out),
+                        None if last else _ext.ptr(nxt_out), _ext.ptr(count), _ext.ptr(ws), ws.numel(),
+                        _ext.stream(dev)))
                     if last:
                         break
                     A = int(count.item())  # the opaque SDF callback needs the batch shape
@@ -198,6 +197,8 @@ class UniformProjection(LevelSetProjection):
                     it += 1
                     act_in = act_out
                     act_out = act_b if act_in is act_a else act_a
+                    nxt_in = nxt_out
+                    nxt_out = nxt_b if nxt_in is nxt_a else nxt_a
             valid_packed = ~not_converged
 
         if full:

@@ -1,19 +1,21 @@
 #!/bin/bash
-# One GPU-box visit: parity tests, smoke, both bench arms, ncu launch lists and full captures of the
-# dominant kernels.  Outputs land in gpurun_out/ (copied into profiles/ by hand after reading).
+# One GPU-box visit: parity tests, smoke, both bench arms; with "prof": ncu launch lists, full captures of the
+# dominant kernels, reference-CUDA timings and a compute-sanitizer pass over the small parity tests.
 set -u
 mkdir -p gpurun_out
 timeout 900 python -m pytest tests -m gpu -q 2>&1 | tail -40 > gpurun_out/pytest_gpu.log; tail -5 gpurun_out/pytest_gpu.log
 timeout 200 python __graft_entry__.py smoke 2>&1 | tail -2
-timeout 600 python bench.py --steps 5 --warmup 3 > gpurun_out/bench.json 2> gpurun_out/bench.err; tail -c 1500 gpurun_out/bench.json; grep -v Warning gpurun_out/bench.err | tail -5
-timeout 300 python bench.py --impl reference --steps 1 --warmup 0 > gpurun_out/bench_reference.json 2>/dev/null; tail -c 400 gpurun_out/bench_reference.json
+timeout 600 python bench.py --steps 5 --warmup 3 > gpurun_out/bench.json 2> gpurun_out/bench.err; tail -c 3000 gpurun_out/bench.json; grep -v Warning gpurun_out/bench.err | tail -5
+timeout 300 python bench.py --impl reference --steps 1 --warmup 0 > gpurun_out/bench_reference.json 2>/dev/null; tail -c 300 gpurun_out/bench_reference.json
 if [ "${1:-}" = "prof" ]; then
-  # launch lists (cold-cache, serialised: compare shares)
+  timeout 500 python scripts/ref_cuda_timing.py 2>&1 | grep -v Warning | tail -1
   timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 6000 --csv --log-file gpurun_out/launches_c2.csv python bench.py --steps 1 --warmup 3 > gpurun_out/ncu_c2.log 2>&1
   timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_c4.csv python bench_splat.py --steps 1 > gpurun_out/ncu_c4.log 2>&1
-  # full captures of the dominant kernels
-  timeout 600 ncu --set full --clock-control none --import-source on -k regex:frnn_query_kernel -s 3 -c 1 -f -o gpurun_out/prof_frnn_query python bench.py --steps 1 --warmup 3 > gpurun_out/ncu_frnn.log 2>&1
+  timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv --log-file gpurun_out/launches_c3.csv python bench_frnn.py --steps 1 > gpurun_out/ncu_c3.log 2>&1
+  timeout 600 ncu --set full --clock-control none --import-source on -k regex:frnn_query_kernel -s 3 -c 1 -f -o gpurun_out/prof_frnn_query python bench_frnn.py --steps 1 > gpurun_out/ncu_frnn.log 2>&1
   timeout 600 ncu --set full --clock-control none --import-source on -k regex:splat_raster_kernel -s 3 -c 1 -f -o gpurun_out/prof_splat_raster python bench_splat.py --steps 1 > gpurun_out/ncu_raster.log 2>&1
   timeout 600 ncu --set full --clock-control none --import-source on -k regex:splat_occ_backward_kernel -s 3 -c 1 -f -o gpurun_out/prof_splat_occ_bwd python bench_splat.py --steps 1 > gpurun_out/ncu_occ.log 2>&1
-  ls -la gpurun_out/
+  timeout 900 compute-sanitizer --tool memcheck --error-exitcode 7 python -m pytest tests/test_gpu_splat.py tests/test_gpu_frnn.py tests/test_gpu_projection.py -m gpu -q -k "not 500k and not c4_scale and not c2_scale and not world1" > gpurun_out/sanitizer_memcheck.log 2>&1; echo "memcheck rc=$?"; tail -3 gpurun_out/sanitizer_memcheck.log
+  timeout 900 compute-sanitizer --tool racecheck --error-exitcode 7 python -m pytest tests/test_gpu_splat.py -m gpu -q -k "bit_exact_vs_oracle or backward_matches_oracle or blend" > gpurun_out/sanitizer_racecheck.log 2>&1; echo "racecheck rc=$?"; tail -3 gpurun_out/sanitizer_racecheck.log
+  ls gpurun_out/
 fi

@@ -57,6 +57,20 @@ def raw(rep):
     return "\n".join(res)
 
 
+def traffic(rep):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch, in bytes (first captured launch)."""
+    out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(out.splitlines()))
+    hdr, units = rows[0], rows[1]
+    d, u = dict(zip(hdr, rows[2])), dict(zip(hdr, units))
+    mult = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    tot = 0.0
+    for k in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+        tot += float(d[k].replace(",", "")) * mult.get(u[k], 1)
+    name = re.sub(r"<.*", "", d["Kernel Name"].replace("void ", "").replace("isob200::", "")).strip()
+    return name, tot
+
+
 def hot_lines(rep, top=14):
     """SASS-level hot spots: share of warp-stall samples and of executed instructions."""
     out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
@@ -88,12 +102,21 @@ def main():
         p = os.path.join(OUT, name + ".csv")
         if os.path.exists(p):
             open(os.path.join(PROF, "%s_%s.txt" % (tag, name)), "w").write(launches(p) + "\n")
+    import json
+    tpath = os.path.join(PROF, "ncu_traffic.json")
+    tr = json.load(open(tpath)) if os.path.exists(tpath) else {}
     for f in sorted(os.listdir(OUT)):
         if f.endswith(".ncu-rep"):
             rep = os.path.join(OUT, f)
+            try:
+                name, b = traffic(rep)
+                tr[name] = {"dram_bytes_per_launch": b, "capture": "%s_%s" % (tag, f[:-8])}
+            except Exception as e:
+                print("traffic:", f, e)
             txt = raw(rep) + "\n\nhottest source lines (share of executed instructions):\n" + hot_lines(rep) + "\n"
             open(os.path.join(PROF, "%s_%s.txt" % (tag, f[:-8])), "w").write(txt)
-    for f in ("bench.json", "bench_reference.json", "bench_splat.json"):
+    json.dump(tr, open(tpath, "w"), indent=1, sort_keys=True)
+    for f in ("bench.json", "bench_reference.json", "bench_splat.json", "bench_n2.json", "ref_cuda_timing.json"):
         p = os.path.join(OUT, f)
         if os.path.exists(p):
             lines = [l for l in open(p).read().splitlines() if l.startswith("{")]

@@ -1,0 +1,47 @@
+"""Host-side containers and packed/padded helpers (CPU only)."""
+import torch
+
+from isopoints_b200 import structures as S
+
+
+def test_pointclouds_container_surface():
+    a, b = torch.rand(5, 3), torch.rand(3, 3)
+    pcl = S.Pointclouds([a, b], normals=[a + 1, b + 1], features=[a[:, :1], b[:, :1]])
+    assert len(pcl) == 2 and not pcl.isempty()
+    assert pcl.num_points_per_cloud().tolist() == [5, 3]
+    assert pcl.cloud_to_packed_first_idx().tolist() == [0, 5]
+    assert pcl.packed_to_cloud_idx().tolist() == [0] * 5 + [1] * 3
+    pad = pcl.points_padded()
+    assert pad.shape == (2, 5, 3) and torch.equal(pad[1, :3], b) and (pad[1, 3:] == 0).all()
+    assert torch.equal(pcl.points_packed(), torch.cat([a, b]))
+    assert torch.equal(pcl.normals_padded()[0], a + 1) and pcl.features_packed().shape == (8, 1)
+    ext = pcl[0].extend(3)
+    assert len(ext) == 3 and torch.equal(ext.points_padded()[2], a)
+    bb = pcl.get_bounding_boxes()
+    assert bb.shape == (2, 3, 2) and torch.equal(bb[0, :, 0], a.min(0)[0])
+    moved = pcl.clone().offset_(torch.ones(8, 3))
+    assert torch.allclose(moved.points_packed(), torch.cat([a, b]) + 1) and torch.equal(pcl.points_packed(), torch.cat([a, b]))
+    upd = pcl.update_padded(pad * 2)
+    assert torch.equal(upd.points_list()[1], b * 2) and upd.__class__ is S.Pointclouds
+    t = S.Pointclouds(torch.rand(2, 4, 3))
+    assert t.num_points_per_cloud().tolist() == [4, 4]
+    assert S.is_pointclouds(pcl) and not S.is_pointclouds(pad)
+    x, n = S.convert_pointclouds_to_tensor(pad)
+    assert n.tolist() == [5, 5] and x is pad
+
+
+def test_packed_padded_round_trip_and_mask_reduce():
+    num = torch.tensor([4, 0, 2])
+    first = S.num_points_2_cloud_to_packed_first_idx(num)
+    assert first.tolist() == [0, 4, 4]
+    packed = torch.arange(18, dtype=torch.float32).view(6, 3)
+    padded = S.packed_to_padded(packed, first, 4)
+    assert padded.shape == (3, 4, 3) and (padded[1] == 0).all() and torch.equal(padded[2, :2], packed[4:])
+    assert torch.equal(S.padded_to_packed(padded, first, 6), packed)
+    live, mask = S.padded_to_packed_idx(num, 4)
+    assert live.tolist() == [0, 1, 2, 3, 8, 9] and mask.sum() == 6
+    vals = torch.arange(12, dtype=torch.float32).view(2, 6)
+    m = torch.tensor([[1, 0, 1, 0, 0, 1], [0, 0, 0, 1, 0, 0]], dtype=torch.bool)
+    red = S.reduce_mask_padded(vals, m)
+    assert red.tolist() == [[0.0, 2.0, 5.0], [9.0, 0.0, 0.0]]
+    assert S.reduce_mask_padded(m, m).dtype == torch.bool
