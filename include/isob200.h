@@ -149,9 +149,11 @@ int isob200_wlop_density(const float* pts, const int64_t* idx, int idx_stride, i
 int isob200_wlop_step(const float* X, const float* Pc, const int64_t* idx_xp, const int64_t* idx_xx,
                       int xx_stride, int xx_k_offset, const float* density_P, const float* sigma_inv, float mu,
                       int N, int PX, int PP, int K, float* out, void* stream);
-int isob200_upsample_sparsity(const float* pts, const int64_t* idx, int idx_stride, int k_offset,
-                              const int64_t* lengths, int N, int P, int K, float* sparsity, float* child,
-                              void* stream);
+/* normals != NULL selects the edge-aware score of EdgeAwareProjection.upsample
+ * (DSS/models/levelset_sampling.py:614-628) */
+int isob200_upsample_sparsity(const float* pts, const float* normals, float edge_sensitivity,
+                              const int64_t* idx, int idx_stride, int k_offset, const int64_t* lengths, int N,
+                              int P, int K, float* sparsity, float* child, void* stream);
 int isob200_fps(const float* pts, const int64_t* lengths, const int64_t* samples, const int64_t* start, int N,
                 int P, int Mmax, float* mind, int64_t* out_idx, void* stream);
 

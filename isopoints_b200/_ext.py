@@ -44,7 +44,7 @@ _PROTOS = {
     "isob200_normalize_rows3": (_i, [_vp, _ll, _f, _vp, _vp]),
     "isob200_wlop_density": (_i, [_vp, _vp, _i, _i, _vp, _i, _i, _i, _vp, _vp]),
     "isob200_wlop_step": (_i, [_vp, _vp, _vp, _vp, _i, _i, _vp, _vp, _f, _i, _i, _i, _i, _vp, _vp]),
-    "isob200_upsample_sparsity": (_i, [_vp, _vp, _i, _i, _vp, _i, _i, _i, _vp, _vp, _vp]),
+    "isob200_upsample_sparsity": (_i, [_vp, _vp, _f, _vp, _i, _i, _vp, _i, _i, _i, _vp, _vp, _vp]),
     "isob200_fps": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp]),
     "isob200_splat_ws_bytes": (_sz, [_i, _i]),
     "isob200_splat_record_bytes": (_i, []),

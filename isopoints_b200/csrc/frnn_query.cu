@@ -19,6 +19,7 @@
 #include "common.cuh"
 #include <float.h>
 #include <limits.h>
+#include <stdlib.h>
 
 namespace isob200 {
 
@@ -129,7 +130,7 @@ frnn_query_kernel(const float* __restrict__ q_points,     // (N,P1,D) in process
           if (gx2 > bound) continue;
           const int ystep = (D == 3 && (ox == -ring || ox == ring)) ? 1 : max(2 * ring, 1);
           for (int oy = (D == 3 ? -ring : 0); oy <= (D == 3 ? ring : 0); oy += ystep) {
-            int c0, c1;
+            int c0;
             float gxy2 = gx2;
             int zlo, zhi;       // cell range along the fastest axis
             float qcz;
@@ -144,41 +145,176 @@ frnn_query_kernel(const float* __restrict__ q_points,     // (N,P1,D) in process
               zlo = lo[1]; zhi = hi[1]; qcz = qc[1];
               c0 = x * res[1];
             }
-            // shrink the run to the cells that can still hold a candidate within `bound`
-            const float gz = sqrtf(fmaxf(bound - gxy2, 0.0f)) * delta + 2e-3f;
-            zlo = max(zlo, __float2int_ru(qcz - 1.0f - gz));
-            zhi = min(zhi, __float2int_rd(qcz + gz));
-            if (zlo > zhi) continue;
-            c1 = c0 + zhi;
-            c0 = c0 + zlo;
-            const int start = off2[c0];
-            const int end = (c1 + 1 == grid_total) ? len2 : off2[c1 + 1];
-            for (int base = start; base < end; base += GW) {
-              const int j = base + gl;
-              const bool valid = j < end;
-              float d = FLT_MAX;
-              if (valid) d = sqdist_ref<D>(pts2 + (size_t)j * D, q);
-              const bool cand = valid && (d <= bound);
-              unsigned m = __ballot_sync(gmask, cand) & gmask;
-              if (m == 0) continue;
-              int ci_mine = cand ? sid2[j] : INT_MAX;
-              while (m) {
-                const int src = __ffs(m) - 1;
-                m &= m - 1;
-                const float cd = __shfl_sync(gmask, d, src);
-                const int ci = __shfl_sync(gmask, ci_mine, src);
-                const bool less = (best_d < cd) || (best_d == cd && best_i < ci);
-                const int pos = __popc(__ballot_sync(gmask, less) & gmask);
-                const float up_d = __shfl_up_sync(gmask, best_d, 1, GW);
-                const int up_i = __shfl_up_sync(gmask, best_i, 1, GW);
-                if (pos < K) {
-                  if (gl > pos) { best_d = up_d; best_i = up_i; }
-                  else if (gl == pos) { best_d = cd; best_i = ci; }
+            // scan the cells [za, zb] of this run (contiguous in the sorted array)
+            auto scan = [&](int za, int zb) {
+              if (za > zb) return;
+              const int start = off2[c0 + za];
+              const int end = (c0 + zb + 1 == grid_total) ? len2 : off2[c0 + zb + 1];
+              for (int base = start; base < end; base += GW) {
+                const int j = base + gl;
+                const bool valid = j < end;
+                float d = FLT_MAX;
+                if (valid) d = sqdist_ref<D>(pts2 + (size_t)j * D, q);
+                const bool cand = valid && (d <= bound);
+                unsigned m = __ballot_sync(gmask, cand) & gmask;
+                if (m == 0) continue;
+                int ci_mine = cand ? sid2[j] : INT_MAX;
+                while (m) {
+                  const int src = __ffs(m) - 1;
+                  m &= m - 1;
+                  const float cd = __shfl_sync(gmask, d, src);
+                  const int ci = __shfl_sync(gmask, ci_mine, src);
+                  const bool less = (best_d < cd) || (best_d == cd && best_i < ci);
+                  const int pos = __popc(__ballot_sync(gmask, less) & gmask);
+                  const float up_d = __shfl_up_sync(gmask, best_d, 1, GW);
+                  const int up_i = __shfl_up_sync(gmask, best_i, 1, GW);
+                  if (pos < K) {
+                    if (gl > pos) { best_d = up_d; best_i = up_i; }
+                    else if (gl == pos) { best_d = cd; best_i = ci; }
+                  }
                 }
+                bound = fminf(r2, __shfl_sync(gmask, best_d, (int)gshift + K - 1));
               }
-              bound = fminf(r2, __shfl_sync(gmask, best_d, (int)gshift + K - 1));
+            };
+            // cells of the run that can still hold a candidate within `bound`
+            auto zrange = [&](int& a, int& b) {
+              const float gz = sqrtf(fmaxf(bound - gxy2, 0.0f)) * delta + 2e-3f;
+              a = max(zlo, __float2int_ru(qcz - 1.0f - gz));
+              b = min(zhi, __float2int_rd(qcz + gz));
+            };
+            int za, zb;
+            zrange(za, zb);
+            if (ring == 0) {
+              // the query's own run: its three central cells first, so that the K-th distance bound
+              // exists before the far cells (and every other run) are looked at
+              const int zc = min(max(__float2int_rd(qcz), za), zb);
+              const int wa = max(za, zc - 1), wb = min(zb, zc + 1);
+              scan(wa, wb);
+              zrange(za, zb);
+              scan(za, min(zb, wa - 1));
+              scan(max(za, wb + 1), zb);
+            } else {
+              scan(za, zb);
             }
           }
+        }
+      }
+    }
+    if (gl < K) {
+      const size_t o = ((size_t)n * P1 + row) * K + gl;
+      const bool found = best_i != INT_MAX;
+      dists[o] = found ? best_d : -1.f;
+      idxs[o] = found ? (IdxT)best_i : (IdxT)-1;
+    }
+  }
+}
+
+// A/B baseline: exhaustive traversal of the full (2c+1)^D block (no best-first order, no pruning)
+template <int D, int GW, typename IdxT>
+__global__ void __launch_bounds__(256)
+frnn_query_exhaustive_kernel(const float* __restrict__ q_points,     // (N,P1,D) in processing order
+                  const int* __restrict__ q_order,        // (N,P1) processing slot -> original row, or null
+                  const int64_t* __restrict__ lengths1,   // (N,) or null
+                  const int64_t* __restrict__ lengths2,   // (N,) or null
+                  const float* __restrict__ sorted_points2,  // (N,P2,D)
+                  const int* __restrict__ cell_off2,         // (N,G)
+                  const int* __restrict__ sorted_idxs2,      // (N,P2)
+                  const float* __restrict__ params, const float* __restrict__ rs, int N, int P1,
+                  int P2, int G, int K, float* __restrict__ dists, IdxT* __restrict__ idxs) {
+  constexpr int PS = (D == 3) ? ISO_G3_SIZE : ISO_G2_SIZE;
+  constexpr int GROUPS = 256 / GW;
+  const int lane = threadIdx.x & 31;
+  const int gl = lane & (GW - 1);                       // lane within group
+  const unsigned gshift = lane & ~(GW - 1);             // first warp lane of this group
+  const unsigned gmask = (GW == 32) ? 0xffffffffu : (((1u << GW) - 1u) << gshift);
+  const long long total = (long long)N * P1;
+  const long long ngroups = (long long)gridDim.x * GROUPS;
+
+  for (long long item = (long long)blockIdx.x * GROUPS + threadIdx.x / GW; item < total;
+       item += ngroups) {
+    const int n = (int)(item / P1);
+    const int s = (int)(item - (long long)n * P1);
+    const int len1 = lengths1 ? (int)min((long long)lengths1[n], (long long)P1) : P1;
+    if (s >= len1) {  // padded row: reference leaves the -1 fill (grid.cu:422-423)
+      if (gl < K) {
+        const size_t o = ((size_t)n * P1 + s) * K + gl;
+        dists[o] = -1.f;
+        idxs[o] = (IdxT)-1;
+      }
+      continue;
+    }
+    const int row = q_order ? q_order[(size_t)n * P1 + s] : s;
+    const int len2 = lengths2 ? (int)min((long long)lengths2[n], (long long)P2) : P2;
+    const float* prm = params + (size_t)n * PS;
+    const float r = rs[n];
+    const float r2 = __fmul_rn(r, r);
+    float q[D];
+#pragma unroll
+    for (int d = 0; d < D; ++d) q[d] = q_points[((size_t)n * P1 + s) * D + d];
+
+    // candidate cell range, grid.cu:305-316 (fp32: (p - min -/+ r) * delta, floor)
+    int lo[D], hi[D], res[D];
+#pragma unroll
+    for (int d = 0; d < D; ++d) {
+      const float rel = __fsub_rn(q[d], prm[d]);
+      const float delta = prm[D];
+      res[d] = (int)prm[D + 1 + d];
+      lo[d] = max(__float2int_rd(__fmul_rn(__fsub_rn(rel, r), delta)), 0);
+      hi[d] = min(__float2int_rd(__fmul_rn(__fadd_rn(rel, r), delta)), res[d] - 1);
+    }
+    const int grid_total = (int)prm[2 * D + 1];
+
+    float best_d = FLT_MAX;   // lane gl holds the gl-th best (dist, idx), ascending
+    int best_i = INT_MAX;
+    float kth_d = FLT_MAX;    // current K-th best distance (pruning bound), group-uniform
+
+    const float* pts2 = sorted_points2 + (size_t)n * P2 * D;
+    const int* off2 = cell_off2 + (size_t)n * G;
+    const int* sid2 = sorted_idxs2 + (size_t)n * P2;
+
+    bool nonempty = true;
+#pragma unroll
+    for (int d = 0; d < D; ++d) nonempty = nonempty && (lo[d] <= hi[d]);
+    if (nonempty) {
+      const int ny = (D == 3) ? (hi[1] - lo[1] + 1) : 1;
+      const int nruns = (hi[0] - lo[0] + 1) * ny;  // <= 0 when empty
+      for (int run = 0; run < nruns; ++run) {
+        int c0, c1;
+        if (D == 3) {
+          const int x = lo[0] + run / ny, y = lo[1] + run % ny;
+          c0 = (x * res[1] + y) * res[2] + lo[2];
+          c1 = (x * res[1] + y) * res[2] + hi[2];
+        } else {
+          const int x = lo[0] + run;
+          c0 = x * res[1] + lo[1];
+          c1 = x * res[1] + hi[1];
+        }
+        const int start = off2[c0];
+        const int end = (c1 + 1 == grid_total) ? len2 : off2[c1 + 1];
+        for (int base = start; base < end; base += GW) {
+          const int j = base + gl;
+          const bool valid = j < end;
+          float d = FLT_MAX;
+          if (valid) d = sqdist_ref<D>(pts2 + (size_t)j * D, q);
+          const bool cand = valid && (d <= r2) && (d <= kth_d);
+          unsigned m = __ballot_sync(gmask, cand) & gmask;
+          if (m == 0) continue;
+          int ci_mine = cand ? sid2[j] : INT_MAX;
+          while (m) {
+            const int src = __ffs(m) - 1;
+            m &= m - 1;
+            const float cd = __shfl_sync(gmask, d, src);
+            const int ci = __shfl_sync(gmask, ci_mine, src);
+            const bool less = (best_d < cd) || (best_d == cd && best_i < ci);
+            const int pos = __popc(__ballot_sync(gmask, less) & gmask);
+            const float up_d = __shfl_up_sync(gmask, best_d, 1, GW);
+            const int up_i = __shfl_up_sync(gmask, best_i, 1, GW);
+            if (pos < K) {
+              if (gl > pos) { best_d = up_d; best_i = up_i; }
+              else if (gl == pos) { best_d = cd; best_i = ci; }
+            }
+          }
+          kth_d = __shfl_sync(gmask, best_d, (int)gshift + K - 1);
         }
       }
     }
@@ -262,6 +398,14 @@ static int launch_query(int gw, int blocks, cudaStream_t st, const float* qp, co
                         const int64_t* l1, const int64_t* l2, const float* sp2, const int* off2,
                         const int* sid2, const float* params, const float* rs, int N, int P1, int P2,
                         int G, int K, float* dists, IdxT* idxs) {
+  static const bool exhaustive = getenv("ISOB200_FRNN_EXHAUSTIVE") != nullptr;
+  if (exhaustive) {
+    if (gw == 8) frnn_query_exhaustive_kernel<D, 8, IdxT><<<blocks, 256, 0, st>>>(qp, qo, l1, l2, sp2, off2, sid2, params, rs, N, P1, P2, G, K, dists, idxs);
+    else if (gw == 16) frnn_query_exhaustive_kernel<D, 16, IdxT><<<blocks, 256, 0, st>>>(qp, qo, l1, l2, sp2, off2, sid2, params, rs, N, P1, P2, G, K, dists, idxs);
+    else frnn_query_exhaustive_kernel<D, 32, IdxT><<<blocks, 256, 0, st>>>(qp, qo, l1, l2, sp2, off2, sid2, params, rs, N, P1, P2, G, K, dists, idxs);
+    ISO_CHECK_LAUNCH("frnn_query_exhaustive_kernel");
+    return ISOB200_OK;
+  }
   if (gw == 8)
     frnn_query_kernel<D, 8, IdxT><<<blocks, 256, 0, st>>>(qp, qo, l1, l2, sp2, off2, sid2, params, rs, N, P1, P2, G, K, dists, idxs);
   else if (gw == 16)

@@ -114,8 +114,12 @@ wlop_step_kernel(const float* __restrict__ X, const float* __restrict__ Pc,
 // (id < 0) are the origin, like knn_gather on pytorch3d's 0-padded ids would give point 0 -- the
 // caller guarantees K valid neighbours (exact KNN), so this only matters for P <= K.
 // One warp per point; K <= 32: lane k owns mid_k.
+// With `normals` (N,P,3) the edge-aware variant of EdgeAwareProjection.upsample
+// (levelset_sampling.py:614-628) is computed instead:
+//   s_k = sqrt(max(|min_j (|mid_k - nn_j| - ((mid_k - nn_j) . n_j)^2)|, 1e-17)) * (2 - n . n_k)^edge_sensitivity
 __global__ void __launch_bounds__(256)
-upsample_sparsity_kernel(const float* __restrict__ pts, const int64_t* __restrict__ idx, int stride, int k_offset,
+upsample_sparsity_kernel(const float* __restrict__ pts, const float* __restrict__ normals,
+                         float edge_sensitivity, const int64_t* __restrict__ idx, int stride, int k_offset,
                          const int64_t* __restrict__ lengths, int N, int P, int K,
                          float* __restrict__ sparsity, float* __restrict__ child) {
   const int lane = threadIdx.x & 31;
@@ -125,10 +129,17 @@ upsample_sparsity_kernel(const float* __restrict__ pts, const int64_t* __restric
     const int n = (int)(i / P);
     const float* base = pts + (size_t)n * P * 3;
     const float px = pts[3 * i], py = pts[3 * i + 1], pz = pts[3 * i + 2];
-    float nx = 0.f, ny = 0.f, nz = 0.f;
+    float nx = 0.f, ny = 0.f, nz = 0.f;      // neighbour position
+    float ux = 0.f, uy = 0.f, uz = 0.f;      // neighbour normal (edge-aware variant)
     if (lane < K) {
       const long long j = idx[i * stride + k_offset + lane];
-      if (j >= 0) { nx = base[3 * j]; ny = base[3 * j + 1]; nz = base[3 * j + 2]; }
+      if (j >= 0) {
+        nx = base[3 * j]; ny = base[3 * j + 1]; nz = base[3 * j + 2];
+        if (normals) {
+          const float* nb = normals + (size_t)n * P * 3 + 3 * j;
+          ux = nb[0]; uy = nb[1]; uz = nb[2];
+        }
+      }
     }
     const float mx = (nx + 2.f * px) / 3.f, my = (ny + 2.f * py) / 3.f, mz = (nz + 2.f * pz) / 3.f;
     float best = FLT_MAX;
@@ -136,7 +147,19 @@ upsample_sparsity_kernel(const float* __restrict__ pts, const int64_t* __restric
       const float qx = __shfl_sync(0xffffffffu, nx, j), qy = __shfl_sync(0xffffffffu, ny, j),
                   qz = __shfl_sync(0xffffffffu, nz, j);
       const float dx = mx - qx, dy = my - qy, dz = mz - qz;
-      best = fminf(best, sqrtf(dx * dx + dy * dy + dz * dz));
+      float val = sqrtf(dx * dx + dy * dy + dz * dz);
+      if (normals) {
+        const float vx = __shfl_sync(0xffffffffu, ux, j), vy = __shfl_sync(0xffffffffu, uy, j),
+                    vz = __shfl_sync(0xffffffffu, uz, j);
+        const float pr = dx * vx + dy * vy + dz * vz;
+        val -= pr * pr;
+      }
+      best = fminf(best, val);
+    }
+    if (normals) {
+      const float* ni = normals + 3 * i;
+      const float dot = ni[0] * ux + ni[1] * uy + ni[2] * uz;
+      best = sqrtf(fmaxf(fabsf(best), 1e-17f)) * powf(2.0f - dot, edge_sensitivity);
     }
     float v = (lane < K) ? best : -FLT_MAX;
     int arg = lane;
@@ -247,17 +270,18 @@ int isob200_wlop_step(const float* X, const float* Pc, const int64_t* idx_xp, co
   return ISOB200_OK;
 }
 
-int isob200_upsample_sparsity(const float* pts, const int64_t* idx, int idx_stride, int k_offset,
-                              const int64_t* lengths, int N, int P, int K, float* sparsity, float* child,
-                              void* stream_) {
+int isob200_upsample_sparsity(const float* pts, const float* normals, float edge_sensitivity,
+                              const int64_t* idx, int idx_stride, int k_offset, const int64_t* lengths, int N,
+                              int P, int K, float* sparsity, float* child, void* stream_) {
   cudaStream_t st = (cudaStream_t)stream_;
   if ((long long)N * P == 0) return ISOB200_OK;
   ISO_CHECK_ARG(pts && idx && sparsity && child, "upsample_sparsity: null pointer");
   ISO_CHECK_ARG(K >= 1 && K <= 32 && k_offset >= 0 && k_offset + K <= idx_stride, "upsample_sparsity: K must be in [1, 32]");
   const long long need = ((long long)N * P + 7) / 8;
   const long long cap = (long long)kNumSMs * 8 * 8;
-  upsample_sparsity_kernel<<<(int)(need < cap ? need : cap), 256, 0, st>>>(pts, idx, idx_stride, k_offset, lengths, N,
-                                                                          P, K, sparsity, child);
+  upsample_sparsity_kernel<<<(int)(need < cap ? need : cap), 256, 0, st>>>(pts, normals, edge_sensitivity, idx,
+                                                                          idx_stride, k_offset, lengths, N, P, K,
+                                                                          sparsity, child);
   ISO_CHECK_LAUNCH("upsample_sparsity_kernel");
   return ISOB200_OK;
 }

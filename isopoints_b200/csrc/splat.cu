@@ -221,6 +221,48 @@ struct PixList {
   }
 };
 
+// The unsorted phase of the list lives in SHARED memory, one column per thread ([k][tid]: a thread's
+// slot k sits in bank tid % 32 whatever k is, so dynamically indexed appends are conflict-free and cost
+// three STS instead of a K-way chain of predicated register moves).  Registers keep only the count and
+// the running maximum; the K slots are pulled into registers once, for the final sorting network.
+template <int K>
+struct SmemList {
+  float* z;      // [K][256]
+  int* id;
+  float* q;
+  int cnt, maxid, maxpos;
+  float maxz;
+  __device__ __forceinline__ void init(float* base) {
+    z = base + threadIdx.x;
+    id = reinterpret_cast<int*>(base + K * 256) + threadIdx.x;
+    q = base + 2 * K * 256 + threadIdx.x;
+    cnt = 0; maxz = -FLT_MAX; maxid = -1; maxpos = 0;
+  }
+  __device__ __forceinline__ void insert(float cz, int cid, float cq) {
+    if (cnt < K) {
+      z[cnt * 256] = cz; id[cnt * 256] = cid; q[cnt * 256] = cq;
+      if (zid_less(maxz, maxid, cz, cid)) { maxz = cz; maxid = cid; maxpos = cnt; }
+      ++cnt;
+    } else if (zid_less(cz, cid, maxz, maxid)) {
+      z[maxpos * 256] = cz; id[maxpos * 256] = cid; q[maxpos * 256] = cq;
+      maxz = z[0]; maxid = id[0]; maxpos = 0;
+#pragma unroll
+      for (int k = 1; k < K; ++k) {
+        const float kz = z[k * 256];
+        const int ki = id[k * 256];
+        if (zid_less(maxz, maxid, kz, ki)) { maxz = kz; maxid = ki; maxpos = k; }
+      }
+    }
+  }
+  __device__ __forceinline__ void drain(PixList<K>& L) const {
+    L.clear();
+#pragma unroll
+    for (int k = 0; k < K; ++k)
+      if (k < cnt) { L.z[k] = z[k * 256]; L.id[k] = id[k * 256]; L.q[k] = q[k * 256]; }
+    L.cnt = cnt; L.maxz = maxz; L.maxid = maxid; L.maxpos = maxpos;
+  }
+};
+
 template <int K>
 __global__ void __launch_bounds__(256)
 splat_raster_kernel(const float4* __restrict__ recs, const int* __restrict__ tile_off,
@@ -267,8 +309,9 @@ splat_raster_kernel(const float4* __restrict__ recs, const int* __restrict__ til
     }
   }
 
-  PixList<K> L;
-  L.clear();
+  extern __shared__ __align__(16) float list_smem[];   // 3 * K * 256 words
+  SmemList<K> SL;
+  SL.init(list_smem);
 
   for (int c = 0; c < nchunks; ++c) {
     const int st = c & 1;
@@ -298,7 +341,7 @@ splat_raster_kernel(const float4* __restrict__ recs, const int* __restrict__ til
         const float q = __fmaf_rn(__fmul_rn(a1.y, dy), dy,
                                   __fmaf_rn(__fmul_rn(a0.w, dx), dx, __fmul_rn(__fmul_rn(a1.x, dx), dy)));
         if (q > a1.z) continue;
-        L.insert(a0.z, __float_as_int(a2.y), q);
+        SL.insert(a0.z, __float_as_int(a2.y), q);
       }
     }
     __syncthreads();   // every warp is done with this stage
@@ -314,6 +357,8 @@ splat_raster_kernel(const float4* __restrict__ recs, const int* __restrict__ til
 
   if (!in_img) return;
   // epilogue: sort, depth-merge cut (:203-206), occupancy (:196 naive >=, :581 fine >), -1 padding
+  PixList<K> L;
+  SL.drain(L);
   L.sort();
   const int size = L.cnt;
   const float zmax = size > 0 ? L.maxz : -1000.0f;
@@ -471,7 +516,10 @@ template <int K>
 static void launch_raster(int tiles, cudaStream_t st, const float4* recs, const int* off, const int* cnt,
                           int S, int T, float thres, int occ_incl, int* oi, float* oz, float* oq,
                           float* oo) {
-  splat_raster_kernel<K><<<tiles, 256, 0, st>>>(recs, off, cnt, S, T, thres, occ_incl, oi, oz, oq, oo);
+  const int smem = 3 * K * 256 * (int)sizeof(float);
+  // static + dynamic shared memory passes 48 KB from K = 12: opt in (per device, so on every launch)
+  cudaFuncSetAttribute(splat_raster_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  splat_raster_kernel<K><<<tiles, 256, smem, st>>>(recs, off, cnt, S, T, thres, occ_incl, oi, oz, oq, oo);
 }
 
 struct SplatWs {

@@ -189,8 +189,9 @@ def upsample(pcl, n_points: Union[int, torch.Tensor], num_points=None, neighborh
         knn = knn_points(points, points, num_points, num_points, K=K + 1)
         sparsity = torch.empty((B, P), dtype=torch.float32, device=dev)
         child = torch.empty((B, P, 3), dtype=torch.float32, device=dev)
-        _ext.check(lib.isob200_upsample_sparsity(_ext.ptr(points), _ext.ptr(knn.idx), K + 1, 1, _ext.ptr(num_points),
-                                                 B, P, K, _ext.ptr(sparsity), _ext.ptr(child), _ext.stream(dev)))
+        _ext.check(lib.isob200_upsample_sparsity(_ext.ptr(points), None, 0.0, _ext.ptr(knn.idx), K + 1, 1,
+                                                 _ext.ptr(num_points), B, P, K, _ext.ptr(sparsity), _ext.ptr(child),
+                                                 _ext.stream(dev)))
         order = sparsity.sort(dim=1).indices[:, P - max_P:] if max_P > 0 else sparsity.new_zeros((B, 0)).long()
         n_new = torch.clamp(n_remaining, max=max_P)
         new_pts = torch.gather(child, 1, order.unsqueeze(-1).expand(-1, -1, 3))

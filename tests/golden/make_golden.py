@@ -139,6 +139,17 @@ def main():
                         up_num=up_num.numpy())
     print("wlop: mean radius", float(wl.points_padded().norm(dim=-1).mean()), "upsample:", tuple(up_pts.shape))
 
+    # ---- EdgeAwareProjection (exact K-NN neighbourhoods; pytorch3d knn_points / knn_gather stand-ins) ---
+    LS.knn_points = _knn_points_cpu
+    LS.knn_gather = lambda x, idx, lengths=None: torch.stack([x[n][idx[n]] for n in range(x.shape[0])])
+    torch.manual_seed(6)
+    xe = (torch.rand(1, 1200, 3) - 0.5) * 1.5
+    ear = LS.EdgeAwareProjection(proj_max_iters=10, proj_tolerance=5e-5, knn_k=15, sample_iters=2, upsample_ratio=1.5)
+    oe = ear.project_points(xe.clone(), SphereSDF())
+    np.savez_compressed(os.path.join(HERE, "edge_aware.npz"), x=xe.numpy(), points=oe["levelset_points"].numpy(),
+                        mask=oe["mask"].numpy())
+    print("edge_aware:", tuple(oe["levelset_points"].shape), float(oe["mask"].float().mean()))
+
     # ---- splat forward: reference naive CPU twin --------------------------------------------
     C = ref_native.dss_C()
     S, K = 48, 4

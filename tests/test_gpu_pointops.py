@@ -97,3 +97,22 @@ def test_project_points_with_upsampling_and_sample_uniform_iso_points():
     rnd = torch.nn.functional.normalize(torch.randn(1, n, 3, device=DEV), dim=-1)
     d0 = pp.knn_points(rnd, rnd, K=2).dists[0, :, 1].sqrt()
     assert float(d.std() / d.mean()) < 0.6 * float(d0.std() / d0.mean())
+
+
+def test_edge_aware_projection_matches_reference_golden(golden):
+    """EdgeAwareProjection.project_points (resample with exact K-NN + LOP move + edge-aware insertion +
+    re-projection).  The insertion ranks float scores, so a near-tie may pick another mid-point: positions
+    are compared row by row where they agree and as point sets otherwise."""
+    from isopoints_b200.levelset_sampling import EdgeAwareProjection
+    g = golden("edge_aware")
+    x = torch.as_tensor(g["x"], device=DEV)
+    ear = EdgeAwareProjection(proj_max_iters=10, proj_tolerance=5e-5, knn_k=15, sample_iters=2, upsample_ratio=1.5)
+    out = ear.project_points(x.clone(), SphereSDF().to(DEV))
+    pts = out["levelset_points"][0]
+    want = torch.as_tensor(g["points"][0], device=DEV)
+    assert pts.shape == want.shape == (1800, 3)
+    assert float(out["mask"].float().mean()) > 0.995
+    row_ok = torch.isclose(pts, want, rtol=1e-4, atol=1e-5).all(-1)
+    assert float(row_ok.float().mean()) > 0.97
+    d = pp.knn_points(pts[None], want[None], K=1).dists[0, :, 0].sqrt()
+    assert float(d.max()) < 2e-2 and float(d.median()) < 1e-5
