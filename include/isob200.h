@@ -54,6 +54,8 @@ int isob200_frnn_build(const float* points, const int64_t* lengths, const float*
 /* ---- FRNN query: frnn._C.find_nbrs_cuda (csrc/grid/grid.cu:384-440),
  *      frnn.frnn_gather (frnn.py:304-352) and its autograd, frnn._C.frnn_backward_cuda
  *      (csrc/backward/backward.cu:76-147) ------------------------------------------------ */
+/* group_width: lanes cooperating on one query (0 = auto: smallest of 8/16/32 >= K), optionally OR-ed with a
+ * traversal mode << 8: 0 auto, 1 exhaustive block scan, 2 pruned best-first (identical results) */
 int isob200_frnn_find_nbrs(const float* q_points, const int* q_order, const int64_t* lengths1,
                            const int64_t* lengths2, const float* sorted_points2, const int* cell_off2,
                            const int* sorted_idxs2, const float* params, const float* rs, int N,

@@ -19,7 +19,6 @@
 #include "common.cuh"
 #include <float.h>
 #include <limits.h>
-#include <stdlib.h>
 
 namespace isob200 {
 
@@ -209,7 +208,10 @@ frnn_query_kernel(const float* __restrict__ q_points,     // (N,P1,D) in process
   }
 }
 
-// A/B baseline: exhaustive traversal of the full (2c+1)^D block (no best-first order, no pruning)
+// Exhaustive traversal of the full (2c+1)^D block in cell order (no best-first order, no pruning):
+// the better kernel when the grid is mostly EMPTY cells (surface-like clouds with a small cell: at
+// BASELINE config 2 there are ~0.1 points per cell), where skipping an empty run costs two offset loads
+// and the pruning bookkeeping of the kernel above costs more than it saves.
 template <int D, int GW, typename IdxT>
 __global__ void __launch_bounds__(256)
 frnn_query_exhaustive_kernel(const float* __restrict__ q_points,     // (N,P1,D) in processing order
@@ -394,11 +396,10 @@ frnn_backward_kernel(const float* __restrict__ points1, const float* __restrict_
 }
 
 template <int D, typename IdxT>
-static int launch_query(int gw, int blocks, cudaStream_t st, const float* qp, const int* qo,
+static int launch_query(bool exhaustive, int gw, int blocks, cudaStream_t st, const float* qp, const int* qo,
                         const int64_t* l1, const int64_t* l2, const float* sp2, const int* off2,
                         const int* sid2, const float* params, const float* rs, int N, int P1, int P2,
                         int G, int K, float* dists, IdxT* idxs) {
-  static const bool exhaustive = getenv("ISOB200_FRNN_EXHAUSTIVE") != nullptr;
   if (exhaustive) {
     if (gw == 8) frnn_query_exhaustive_kernel<D, 8, IdxT><<<blocks, 256, 0, st>>>(qp, qo, l1, l2, sp2, off2, sid2, params, rs, N, P1, P2, G, K, dists, idxs);
     else if (gw == 16) frnn_query_exhaustive_kernel<D, 16, IdxT><<<blocks, 256, 0, st>>>(qp, qo, l1, l2, sp2, off2, sid2, params, rs, N, P1, P2, G, K, dists, idxs);
@@ -427,7 +428,9 @@ extern "C" {
 //   q_points : query coordinates in processing order (pass the cell-sorted copy for locality)
 //   q_order  : processing slot -> original row (sorted_points1_idxs), or NULL for identity
 //   idx_is_i64: 1 -> idxs is int64 (reference API), 0 -> int32 (internal fused consumers)
-//   group_width: 0 = auto (smallest of 8/16/32 that is >= K)
+//   group_width: 0 = auto (smallest of 8/16/32 that is >= K), optionally OR-ed with a traversal mode in
+//                bits 8..9: 0 = auto (pruned best-first when the grid holds >= 1 point per cell on
+//                average, exhaustive otherwise), 1 = exhaustive, 2 = pruned.  Results are identical.
 int isob200_frnn_find_nbrs(const float* q_points, const int* q_order, const int64_t* lengths1,
                            const int64_t* lengths2, const float* sorted_points2, const int* cell_off2,
                            const int* sorted_idxs2, const float* params, const float* rs, int N,
@@ -440,15 +443,17 @@ int isob200_frnn_find_nbrs(const float* q_points, const int* q_order, const int6
   if ((long long)N * P1 == 0) return ISOB200_OK;
   ISO_CHECK_ARG(q_points && sorted_points2 && cell_off2 && sorted_idxs2 && params && rs && dists && idxs,
                 "find_nbrs: null pointer");
-  int gw = group_width;
+  const int mode = (group_width >> 8) & 3;
+  int gw = group_width & 0xff;
   if (gw == 0) gw = (K <= 8) ? 8 : (K <= 16 ? 16 : 32);
+  const bool exhaustive = mode == 1 || (mode == 0 && (long long)P2 < (long long)G);
   ISO_CHECK_ARG((gw == 8 || gw == 16 || gw == 32) && gw >= K, "find_nbrs: group_width %d invalid for K=%d", gw, K);
   const long long items = (long long)N * P1;
   const int groups = 256 / gw;
   long long need = (items + groups - 1) / groups;
   const long long cap = (long long)kNumSMs * 8 * 16;  // 8 resident CTAs/SM, 16 waves max
   const int blocks = (int)(need < cap ? need : cap);
-#define Q(DD, T) launch_query<DD, T>(gw, blocks, st, q_points, q_order, lengths1, lengths2, sorted_points2, cell_off2, sorted_idxs2, params, rs, N, P1, P2, G, K, dists, (T*)idxs)
+#define Q(DD, T) launch_query<DD, T>(exhaustive, gw, blocks, st, q_points, q_order, lengths1, lengths2, sorted_points2, cell_off2, sorted_idxs2, params, rs, N, P1, P2, G, K, dists, (T*)idxs)
   if (D == 3) return idx_is_i64 ? Q(3, int64_t) : Q(3, int);
   return idx_is_i64 ? Q(2, int64_t) : Q(2, int);
 #undef Q

@@ -29,6 +29,9 @@ from . import _ext
 
 _GRID = namedtuple("GRID", "sorted_points2 pc2_grid_off sorted_points2_idxs grid_params")
 
+# traversal of the query kernel: 0 = auto, 1 = exhaustive block scan, 2 = pruned best-first (same results)
+QUERY_MODE = 0
+
 _PARAMS_SIZE = {2: 6, 3: 8}
 _TOTAL_IDX = {2: 5, 3: 7}
 
@@ -85,8 +88,8 @@ def find_nbrs(points1, lengths1, lengths2, grid, K, r, q_points=None, q_order=No
     _ext.check(_ext.lib().isob200_frnn_find_nbrs(
         _ext.ptr(qp), _ext.ptr(q_order), _ext.ptr(lengths1), _ext.ptr(lengths2),
         _ext.ptr(sorted_points2), _ext.ptr(off), _ext.ptr(sorted_idxs2), _ext.ptr(params), _ext.ptr(r),
-        N, P1, P2, D, G, K, _ext.ptr(dists), _ext.ptr(idxs), 1 if idx_dtype == torch.int64 else 0, 0,
-        _ext.stream(dev)))
+        N, P1, P2, D, G, K, _ext.ptr(dists), _ext.ptr(idxs), 1 if idx_dtype == torch.int64 else 0,
+        (QUERY_MODE & 3) << 8, _ext.stream(dev)))
     return idxs, dists
 
 

@@ -37,9 +37,17 @@ def test_prefix_sum_cuda_api_in_place():
     assert torch.equal(off.cpu().long(), (torch.cumsum(x.long(), 0) - x.long()).cpu())
 
 
+@pytest.fixture(params=[1, 2], ids=["exhaustive", "pruned"])
+def query_mode(request):
+    old = frnn.QUERY_MODE
+    frnn.QUERY_MODE = request.param
+    yield request.param
+    frnn.QUERY_MODE = old
+
+
 @pytest.mark.parametrize("D", [3, 2])
 @pytest.mark.parametrize("K", [1, 5, 8, 9, 16, 17, 32])
-def test_frnn_small_bit_exact_vs_oracle(D, K):
+def test_frnn_small_bit_exact_vs_oracle(D, K, query_mode):
     rng = np.random.RandomState(10 * D + K)
     N, P = 2, 700
     pts = rng.rand(N, P, D).astype(np.float32)
@@ -62,7 +70,7 @@ def test_frnn_small_bit_exact_vs_oracle(D, K):
     assert np.array_equal(grid.sorted_points2.cpu().numpy(), sp)
 
 
-def test_frnn_multi_tile_multi_pass_build():
+def test_frnn_multi_tile_multi_pass_build(query_mode):
     """Several radix tiles x 3 digit passes in the deterministic grid build (N*G > 2^16)."""
     rng = np.random.RandomState(77)
     pts = rng.rand(2, 5000, 3).astype(np.float32)
@@ -81,7 +89,7 @@ def test_frnn_multi_tile_multi_pass_build():
     assert np.array_equal(i.cpu().numpy(), want_i) and np.array_equal(d.cpu().numpy(), want_d)
 
 
-def test_frnn_two_clouds_and_grid_reuse():
+def test_frnn_two_clouds_and_grid_reuse(query_mode):
     rng = np.random.RandomState(5)
     p1 = rng.rand(1, 400, 3).astype(np.float32) * 1.2 - 0.1      # queries partly outside the grid
     p2 = rng.rand(1, 900, 3).astype(np.float32)
@@ -179,7 +187,7 @@ def test_compat_primitives_match_reference_layout():
 
 @pytest.mark.skipif(not ref_native.available(), reason="oracle/_ref not built")
 @pytest.mark.parametrize("shape", ["box", "sphere"])
-def test_frnn_500k_bit_exact_vs_reference_cuda(shape):
+def test_frnn_500k_bit_exact_vs_reference_cuda(shape, query_mode):
     """BASELINE config 3: 500 000 points, r = 0.05, K = 16, index bit-exact vs the reference."""
     g = torch.Generator().manual_seed(0)
     if shape == "box":
