@@ -249,6 +249,7 @@ def run_ours(args):
     if rank == 0:
         if world == 1:
             line["cpu_baseline"] = cpu_baseline(sample_points=args.cpu_sample)
+            line["c1"] = bench_c1(dev)
             import bench_frnn
             import bench_splat
             line["frnn"] = bench_frnn.run(args, dev, peaks, peak_src)
@@ -257,6 +258,32 @@ def run_ours(args):
     if world > 1:
         import torch.distributed as dist
         dist.destroy_process_group()
+
+
+def bench_c1(dev, reps=20):
+    """BASELINE configs[0] ("C1"): 4 096 points, analytic unit-sphere SDF, 10 projection iterations --
+    through the opaque nn.Module callback (11 SDF evaluations) and through the fully fused built-in
+    sphere kernel (one launch, 37 B/point)."""
+    from isopoints_b200.levelset_sampling import UniformProjection
+    from tests.helpers import SphereSDF
+    torch.manual_seed(0)
+    x = ((torch.rand(1, 4096, 3) - 0.5) * 1.5).to(dev)
+    proj = UniformProjection(proj_max_iters=10, proj_tolerance=5e-5)
+    out = {}
+    for name, sdf in (("opaque_module", SphereSDF().to(dev)), ("fused_sphere_kernel", SphereSDF(analytic=True).to(dev))):
+        f = lambda: proj.project_points(x, sdf, skip_resampling=True, skip_upsampling=True)
+        for _ in range(3):
+            r = f()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(reps):
+            r = f()
+        b.record()
+        torch.cuda.synchronize()
+        ms = a.elapsed_time(b) / reps
+        out[name] = {"ms": ms, "points_per_s": 4096 / (ms * 1e-3), "converged": float(r["mask"].float().mean())}
+    return out
 
 
 # ---------------------------------------------------------------------------------------------

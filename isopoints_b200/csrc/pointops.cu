@@ -116,7 +116,7 @@ wlop_step_kernel(const float* __restrict__ X, const float* __restrict__ Pc,
 // One warp per point; K <= 32: lane k owns mid_k.
 // With `normals` (N,P,3) the edge-aware variant of EdgeAwareProjection.upsample
 // (levelset_sampling.py:614-628) is computed instead:
-//   s_k = sqrt(max(|min_j (|mid_k - nn_j| - ((mid_k - nn_j) . n_j)^2)|, 1e-17)) * (2 - n . n_k)^edge_sensitivity
+//   s_k = sqrt(max(|min_j (|mid_k - nn_j| - sum_c ((mid_k - nn_j)_c n_k,c)^2)|, 1e-17)) * (2 - n . n_k)^edge_sensitivity
 __global__ void __launch_bounds__(256)
 upsample_sparsity_kernel(const float* __restrict__ pts, const float* __restrict__ normals,
                          float edge_sensitivity, const int64_t* __restrict__ idx, int stride, int k_offset,
@@ -149,10 +149,10 @@ upsample_sparsity_kernel(const float* __restrict__ pts, const float* __restrict_
       const float dx = mx - qx, dy = my - qy, dz = mz - qz;
       float val = sqrtf(dx * dx + dy * dy + dz * dz);
       if (normals) {
-        const float vx = __shfl_sync(0xffffffffu, ux, j), vy = __shfl_sync(0xffffffffu, uy, j),
-                    vz = __shfl_sync(0xffffffffu, uz, j);
-        const float pr = dx * vx + dy * vy + dz * vz;
-        val -= pr * pr;
+        // (mid_k - nn_j) is projected on n_k, the normal of the neighbour that FORMS the mid-point: the
+        // reference broadcasts knn_normals.unsqueeze(-2) over the j axis (levelset_sampling.py:621-623)
+        // NB: sum_c (d_c * n_c)^2 -- the reference squares element-wise BEFORE the sum (:622-623)
+        val -= (dx * ux) * (dx * ux) + (dy * uy) * (dy * uy) + (dz * uz) * (dz * uz);
       }
       best = fminf(best, val);
     }
