@@ -41,6 +41,18 @@ def test_forward_bit_exact_vs_oracle(S, K):
     assert splat.count_pixel_splats(t["points"], t["ellipse"], t["cutoff"], t["radii"], S) == n_pairs
 
 
+def test_forward_max_points_per_pixel_150():
+    """kMaxPointsPerPixel = 150 (rasterization_utils.cuh:18): the large-K path, dense overlap."""
+    S, K = 24, 150
+    inp = make_splat_inputs(1, 4000, S, seed=2, sigma_px=2.5, behind_frac=0.0)
+    idx, zbuf, qv, occ = _fwd(_t(inp), S, K, thres=10.0)
+    wi, wz, wq, wo = port.splat_forward(inp["points"], inp["ellipse"], inp["cutoff"], inp["radii"],
+                                        inp["first_idx"], inp["num_points"], 10.0, S, K)
+    assert (wi >= 0).sum(-1).max() > 100                      # well past the register-list kernels
+    assert np.array_equal(idx.cpu().numpy(), wi) and np.array_equal(zbuf.cpu().numpy(), wz)
+    assert np.array_equal(qv.cpu().numpy(), wq) and np.array_equal(occ.cpu().numpy(), wo)
+
+
 def test_forward_naive_occupancy_rule_and_z0():
     """bin_size == 0 is the naive kernel (occupied when z >= 0), otherwise z > 0 (cu:196 vs :581)."""
     S, K = 32, 4
