@@ -280,19 +280,32 @@ frnn_query_exhaustive_kernel(const float* __restrict__ q_points,     // (N,P1,D)
     if (nonempty) {
       const int ny = (D == 3) ? (hi[1] - lo[1] + 1) : 1;
       const int nruns = (hi[0] - lo[0] + 1) * ny;  // <= 0 when empty
-      for (int run = 0; run < nruns; ++run) {
-        int c0, c1;
-        if (D == 3) {
-          const int x = lo[0] + run / ny, y = lo[1] + run % ny;
-          c0 = (x * res[1] + y) * res[2] + lo[2];
-          c1 = (x * res[1] + y) * res[2] + hi[2];
-        } else {
-          const int x = lo[0] + run;
-          c0 = x * res[1] + lo[1];
-          c1 = x * res[1] + hi[1];
+      // the [start, end) slices of up to GW runs are fetched by the lanes in parallel (one division
+      // and two offset loads per lane), then handed round with shuffles: an empty run -- most of
+      // them on a surface -- costs two shuffles and a compare instead of a dependent load chain
+      for (int rbase = 0; rbase < nruns; rbase += GW) {
+       int my_start = 0, my_end = 0;
+       {
+        const int run = rbase + gl;
+        if (run < nruns) {
+          int c0, c1;
+          if (D == 3) {
+            const int x = lo[0] + run / ny, y = lo[1] + run % ny;
+            c0 = (x * res[1] + y) * res[2] + lo[2];
+            c1 = (x * res[1] + y) * res[2] + hi[2];
+          } else {
+            const int x = lo[0] + run;
+            c0 = x * res[1] + lo[1];
+            c1 = x * res[1] + hi[1];
+          }
+          my_start = off2[c0];
+          my_end = (c1 + 1 == grid_total) ? len2 : off2[c1 + 1];
         }
-        const int start = off2[c0];
-        const int end = (c1 + 1 == grid_total) ? len2 : off2[c1 + 1];
+       }
+       const int nr = min(GW, nruns - rbase);
+       for (int rj = 0; rj < nr; ++rj) {
+        const int start = __shfl_sync(gmask, my_start, (int)gshift + rj);
+        const int end = __shfl_sync(gmask, my_end, (int)gshift + rj);
         for (int base = start; base < end; base += GW) {
           const int j = base + gl;
           const bool valid = j < end;
@@ -318,6 +331,7 @@ frnn_query_exhaustive_kernel(const float* __restrict__ q_points,     // (N,P1,D)
           }
           kth_d = __shfl_sync(gmask, best_d, (int)gshift + K - 1);
         }
+       }
       }
     }
     if (gl < K) {
