@@ -225,7 +225,7 @@ def run_ours(args):
         alg = n_q * (16 + 12 * K)                       # 16 + 12K bytes per query
         achieved = alg / (q["avg_ms"] * 1e-3) / 1e9
         roof = {"kernel": "frnn_query_kernel", "bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"],
-                "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"], "traffic": _ncu_traffic("frnn_query_kernel"), "peak_source": peak_src,
+                "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"], "traffic": _ncu_traffic("prof_frnn_query_c2"), "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": alg, "avg_launch_ms": q["avg_ms"]}
 
     line = {

@@ -59,7 +59,7 @@ def run(args, dev, peaks, peak_src, steps=None):
     if q:
         ach = alg / (q * 1e-3) / 1e9
         roof = {"kernel": "frnn_query_kernel<3,16,int64>", "bound": "hbm", "achieved": ach, "peak": peaks["hbm_gbs"],
-                "unit": "GB/s", "frac": ach / peaks["hbm_gbs"], "traffic": _ncu_traffic("frnn_query_kernel"), "peak_source": peak_src,
+                "unit": "GB/s", "frac": ach / peaks["hbm_gbs"], "traffic": _ncu_traffic("prof_frnn_query"), "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": alg, "avg_launch_ms": q}
     return {"metric": "FRNN queries/sec", "unit": "queries/s",
             "config": {"workload": "C3: %d uniform points in the unit box, self query, K=%d, r=%g, radius_cell_ratio=2"

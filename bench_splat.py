@@ -100,7 +100,7 @@ def run(args, dev, peaks, peak_src, steps=None):
     if f:
         ach = alg / (f["avg_ms"] * 1e-3) / 1e9
         roof = {"kernel": "splat_tile_fill + splat_raster_kernel<8>", "bound": "hbm", "achieved": ach,
-                "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": ach / peaks["hbm_gbs"], "traffic": _ncu_traffic("splat_raster_kernel"),
+                "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": ach / peaks["hbm_gbs"], "traffic": _ncu_traffic("prof_splat_raster"),
                 "peak_source": peak_src, "algorithmic_bytes_per_launch": alg, "avg_launch_ms": f["avg_ms"]}
     return {"metric": "pixel-splats/sec", "unit": "pixel-splats/s",
             "config": {"workload": "C4: %d views x %d splats, %dx%d, K=%d, sigma=1.5px, occ_grad on 10%% of pixels, "

@@ -110,7 +110,7 @@ def main():
             rep = os.path.join(OUT, f)
             try:
                 name, b = traffic(rep)
-                tr[name] = {"dram_bytes_per_launch": b, "capture": "%s_%s" % (tag, f[:-8])}
+                tr[f[:-8]] = {"dram_bytes_per_launch": b, "kernel": name, "capture": "%s_%s" % (tag, f[:-8])}
             except Exception as e:
                 print("traffic:", f, e)
             txt = raw(rep) + "\n\nhottest source lines (share of executed instructions):\n" + hot_lines(rep) + "\n"
