@@ -22,6 +22,7 @@
 // while its offsets are packed-global (rasterize_points_backward.cu:124-126), silently dropping
 // that cell's points; here every in-radius pair contributes.
 #include "common.cuh"
+#include "scan.cuh"
 #include <float.h>
 
 namespace isob200 {
@@ -117,6 +118,152 @@ splat_occ_backward_kernel(const float* __restrict__ points, const float* __restr
               const float w = inv * g;
               gx = fmaf(dx, w, gx);
               gy = fmaf(dy, w, gy);
+            }
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      gx += __shfl_xor_sync(0xffffffffu, gx, o);
+      gy += __shfl_xor_sync(0xffffffffu, gy, o);
+    }
+    if (lane == 0) {
+      grad_out[(size_t)p * out_stride + 0] = gx;
+      grad_out[(size_t)p * out_stride + 1] = gy;
+    }
+  }
+}
+
+// ---- sparse form of grad_occ: per 16x16 output tile, the list of pixels with a non-zero gradient ----
+// Occupancy gradients are zero wherever the rendered and target masks agree, i.e. almost everywhere
+// except a band around silhouettes; the point-centric sweep above still visits every pixel of its
+// window.  Two tiny kernels (+ the scan) turn the image into per-tile record lists {xf, yf, g, -} in
+// pixel order (deterministic), and the hybrid kernel below walks, for every tile its window touches,
+// either the tile's list (sparse tile) or the pixels themselves (dense tile).
+constexpr int GT = 16;   // tile side of the gradient-pixel lists
+
+__global__ void __launch_bounds__(256)
+gradpix_count_kernel(const float* __restrict__ grad_occ, int H, int W, int TX, int TY, int* __restrict__ tile_cnt) {
+  const int t = blockIdx.x;                       // n*TY*TX + ty*TX + tx
+  const int n = t / (TX * TY), tr = t - n * TX * TY;
+  const int ty = tr / TX, tx = tr - ty * TX;
+  const int col = tx * GT + (threadIdx.x & 15), row = ty * GT + (threadIdx.x >> 4);
+  const bool nz = col < W && row < H && grad_occ[((size_t)n * H + row) * W + col] != 0.0f;
+  const int c = __syncthreads_count(nz);
+  if (threadIdx.x == 0) tile_cnt[t] = c;
+}
+
+__global__ void __launch_bounds__(256)
+gradpix_fill_kernel(const float* __restrict__ grad_occ, int H, int W, int TX, int TY,
+                    const int* __restrict__ tile_off, float4* __restrict__ recs) {
+  __shared__ int warp_cnt[8];
+  const int t = blockIdx.x;
+  const int n = t / (TX * TY), tr = t - n * TX * TY;
+  const int ty = tr / TX, tx = tr - ty * TX;
+  const int col = tx * GT + (threadIdx.x & 15), row = ty * GT + (threadIdx.x >> 4);
+  float g = 0.0f;
+  if (col < W && row < H) g = grad_occ[((size_t)n * H + row) * W + col];
+  const bool nz = g != 0.0f;
+  const unsigned m = __ballot_sync(0xffffffffu, nz);
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  if (lane == 0) warp_cnt[w] = __popc(m);
+  __syncthreads();
+  int base = 0;
+  for (int i = 0; i < w; ++i) base += warp_cnt[i];
+  if (nz) {
+    const int slot = tile_off[t] + base + __popc(m & ((1u << lane) - 1u));
+    recs[slot] = make_float4(pix_to_ndc_b(W - 1 - col, (float)W), pix_to_ndc_b(H - 1 - row, (float)H), g, 0.0f);
+  }
+}
+
+// one (pixel, point) pair of the occupancy backward; returns false when the pair does not contribute
+template <int MODE>
+__device__ __forceinline__ void occ_pair(float dx, float dy, float g, float r2, float wx, float wy, float bx,
+                                         float by, float& gx, float& gy) {
+  const float d2 = __fmaf_rn(dx, dx, __fmul_rn(dy, dy));   // SASS of the reference: FMUL dy*dy ; FFMA dx
+  if (MODE == 0) {
+    if (d2 > r2) return;
+  } else {
+    if (fabsf(dx) > wx || fabsf(dy) > wy) return;
+  }
+  if (g > 0.0f && (fabsf(dx) > bx || fabsf(dy) > by)) return;
+  const float den = (d2 > 0.0f) ? fmaxf(d2, 1e-10f) : 0.0f;
+  float inv;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(inv) : "f"(den));
+  const float w = inv * g;
+  gx = fmaf(dx, w, gx);
+  gy = fmaf(dy, w, gy);
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(256)
+splat_occ_backward_hybrid_kernel(const float* __restrict__ points, const float* __restrict__ radii,
+                                 const unsigned char* __restrict__ visible,
+                                 const int64_t* __restrict__ first_idx, const int64_t* __restrict__ num_points,
+                                 const float* __restrict__ rs, float radii_s, const float* __restrict__ grad_occ,
+                                 const int* __restrict__ tile_cnt, const int* __restrict__ tile_off,
+                                 const float4* __restrict__ recs, int H, int W, int TX, int TY,
+                                 float* __restrict__ grad_out, int out_stride) {
+  const int n = blockIdx.y;
+  const long long first = first_idx[n], num = num_points[n];
+  const int lane = threadIdx.x & 31;
+  const long long warps = (long long)gridDim.x * (blockDim.x >> 5);
+  const float fW = (float)W, fH = (float)H;
+  const float* g_img = grad_occ + (size_t)n * H * W;
+  const int* cnt_n = tile_cnt + (size_t)n * TX * TY;
+  const int* off_n = tile_off + (size_t)n * TX * TY;
+  for (long long i = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); i < num; i += warps) {
+    const long long p = first + i;
+    float gx = 0.f, gy = 0.f;
+    const float px = points[3 * p], py = points[3 * p + 1], pz = points[3 * p + 2];
+    const bool live = (visible == nullptr || visible[p]) && !(pz < 0.f || fabsf(py) > 1.0f || fabsf(px) > 1.0f);
+    if (live) {
+      const float rx = radii[2 * p], ry = radii[2 * p + 1];
+      float wx, wy, r2 = 0.f, bx = rx, by = ry;
+      if (MODE == 0) {
+        const float r = rs[n];
+        r2 = __fmul_rn(r, r);
+        wx = wy = r;
+      } else {
+        wx = __fmul_rn(rx, radii_s);
+        wy = __fmul_rn(ry, radii_s);
+        bx = __fdiv_rn(wx, radii_s);
+        by = __fdiv_rn(wy, radii_s);
+      }
+      int xl, xh, yl, yh;
+      pixel_window(px, wx, W, fW, xl, xh);
+      pixel_window(py, wy, H, fH, yl, yh);
+      if (xl <= xh && yl <= yh) {
+        const int c_lo = W - 1 - xh, c_hi = W - 1 - xl;   // window in output coordinates
+        const int r_lo = H - 1 - yh, r_hi = H - 1 - yl;
+        for (int ty = r_lo / GT; ty <= r_hi / GT; ++ty) {
+          for (int tx = c_lo / GT; tx <= c_hi / GT; ++tx) {
+            const int t = ty * TX + tx;
+            const int cnt = cnt_n[t];
+            if (cnt == 0) continue;
+            if (cnt <= 96) {
+              // sparse tile: walk its non-zero pixels, 32 records per step
+              const float4* rl = recs + off_n[t];
+              for (int k = lane; k < cnt; k += 32) {
+                const float4 rc = rl[k];
+                occ_pair<MODE>(__fsub_rn(rc.x, px), __fsub_rn(rc.y, py), rc.z, r2, wx, wy, bx, by, gx, gy);
+              }
+            } else {
+              // dense tile: sweep the part of the window inside it (lane = column)
+              const int ca = max(c_lo, tx * GT), cb = min(c_hi, tx * GT + GT - 1);
+              const int ra = max(r_lo, ty * GT), rb = min(r_hi, ty * GT + GT - 1);
+              const int ncol = cb - ca + 1;                     // <= 16: two rows per warp step
+              const int col = ca + (lane & 15);
+              const bool col_ok = (lane & 15) < ncol;
+              const float dx = __fsub_rn(pix_to_ndc_b(W - 1 - col, fW), px);
+              for (int row = ra + (lane >> 4); row <= rb; row += 2) {
+                if (!col_ok) continue;
+                const float g = g_img[(size_t)row * W + col];
+                if (g == 0.0f) continue;
+                const float dy = __fsub_rn(pix_to_ndc_b(H - 1 - row, fH), py);
+                occ_pair<MODE>(dx, dy, g, r2, wx, wy, bx, by, gx, gy);
+              }
             }
           }
         }
@@ -297,11 +444,19 @@ extern "C" {
 //   rs      : (N,) per-view search radius (mode 0);  radii_s: box scale (mode 1)
 //   grad_out: rows of `out_stride` floats; columns 0,1 of EVERY row are written (0 when the point
 //             does not participate), so the caller needs no zero fill.
+size_t isob200_splat_occ_backward_ws_bytes(int N, int H, int W) {
+  const size_t nt = (size_t)N * div_up(W, GT) * div_up(H, GT);
+  return align_up(nt * 4) * 2 + align_up(scan_ws_bytes((int)nt, 1)) + align_up((size_t)N * H * W * sizeof(float4));
+}
+
+//   ws / ws_bytes: scratch of isob200_splat_occ_backward_ws_bytes(N,H,W) bytes enables the hybrid
+//             sparse/dense sweep (per-tile lists of the non-zero gradient pixels); NULL selects the plain
+//             window sweep.  Both give the same sums up to fp32 summation order.
 int isob200_splat_occ_backward(const float* points, const float* radii, const unsigned char* visible,
                                const int64_t* first_idx, const int64_t* num_points, const float* rs,
                                float radii_s, const float* grad_occ, int N, int H, int W,
                                long long max_points_per_cloud, int mode, float* grad_out, int out_stride,
-                               void* stream_) {
+                               void* ws, size_t ws_bytes, void* stream_) {
   cudaStream_t st = (cudaStream_t)stream_;
   ISO_CHECK_ARG(N >= 0 && H > 0 && W > 0 && out_stride >= 2, "splat_occ_backward: bad sizes");
   ISO_CHECK_ARG(mode == 0 || mode == 1, "splat_occ_backward: mode must be 0 (fast) or 1 (slow)");
@@ -311,6 +466,35 @@ int isob200_splat_occ_backward(const float* points, const float* radii, const un
   long long need = (max_points_per_cloud + 7) / 8;          // 8 warps (points) per CTA
   int bx = (int)min(need, (long long)kNumSMs * 8 * 8);
   if (N > 1) bx = max(1, min(bx, (kNumSMs * 8 * 8 + N - 1) / N));
+  if (ws != nullptr) {
+    if (ws_bytes < isob200_splat_occ_backward_ws_bytes(N, H, W)) {
+      set_error("splat_occ_backward: workspace too small");
+      return ISOB200_ERR_WORKSPACE;
+    }
+    const int TX = div_up(W, GT), TY = div_up(H, GT);
+    const int nt = N * TX * TY;
+    char* base = (char*)ws;
+    int* tcnt = (int*)base; base += align_up((size_t)nt * 4);
+    int* toff = (int*)base; base += align_up((size_t)nt * 4);
+    void* sws = base; const size_t sws_bytes = align_up(scan_ws_bytes(nt, 1)); base += sws_bytes;
+    float4* recs = (float4*)base;
+    gradpix_count_kernel<<<nt, 256, 0, st>>>(grad_occ, H, W, TX, TY, tcnt);
+    ISO_CHECK_LAUNCH("gradpix_count_kernel");
+    int rc = exclusive_scan_i32(tcnt, toff, nt, 1, nt, nt, sws, sws_bytes, st);
+    if (rc) return rc;
+    gradpix_fill_kernel<<<nt, 256, 0, st>>>(grad_occ, H, W, TX, TY, toff, recs);
+    ISO_CHECK_LAUNCH("gradpix_fill_kernel");
+    if (mode == 0)
+      splat_occ_backward_hybrid_kernel<0><<<dim3(bx, N), 256, 0, st>>>(points, radii, visible, first_idx, num_points,
+                                                                      rs, radii_s, grad_occ, tcnt, toff, recs, H, W,
+                                                                      TX, TY, grad_out, out_stride);
+    else
+      splat_occ_backward_hybrid_kernel<1><<<dim3(bx, N), 256, 0, st>>>(points, radii, visible, first_idx, num_points,
+                                                                      rs, radii_s, grad_occ, tcnt, toff, recs, H, W,
+                                                                      TX, TY, grad_out, out_stride);
+    ISO_CHECK_LAUNCH("splat_occ_backward_hybrid_kernel");
+    return ISOB200_OK;
+  }
   if (mode == 0)
     splat_occ_backward_kernel<0><<<dim3(bx, N), 256, 0, st>>>(points, radii, visible, first_idx, num_points, rs,
                                                              radii_s, grad_occ, H, W, grad_out, out_stride);

@@ -152,12 +152,19 @@ def visibility_mask(idx, num_points_total, occupancy=None):
     return vis.bool()
 
 
+# occupancy backward sweep: True = hybrid (per-tile lists of the non-zero gradient pixels, dense fallback
+# per tile), False = plain window sweep.  Same sums up to fp32 summation order.
+OCC_BACKWARD_HYBRID = True
+
+
 def _occ_backward(points, radii, visible_u8, first_idx, num_points, rs, radii_s, grad_occ, mode, out, out_stride):
     N, H, W = grad_occ.shape
-    _ext.check(_ext.lib().isob200_splat_occ_backward(
+    lib = _ext.lib()
+    ws = _ext.workspace(lib.isob200_splat_occ_backward_ws_bytes(N, H, W), points.device) if OCC_BACKWARD_HYBRID else None
+    _ext.check(lib.isob200_splat_occ_backward(
         _ext.ptr(points), _ext.ptr(radii), _ext.ptr(visible_u8), _ext.ptr(first_idx), _ext.ptr(num_points),
         _ext.ptr(rs), float(radii_s), _ext.ptr(grad_occ), N, H, W, points.shape[0], mode, _ext.ptr(out),
-        out_stride, _ext.stream(points.device)))
+        out_stride, _ext.ptr(ws), 0 if ws is None else ws.numel(), _ext.stream(points.device)))
 
 
 class _CExt:

@@ -161,7 +161,15 @@ def _backward_inputs(S, V, pts, seed, K=6):
     return inp, t, idx, occ_grad.to(DEV), zbuf_grad.to(DEV)
 
 
-def test_backward_matches_oracle():
+@pytest.fixture(params=[True, False], ids=["hybrid", "window"])
+def occ_sweep(request):
+    old = splat.OCC_BACKWARD_HYBRID
+    splat.OCC_BACKWARD_HYBRID = request.param
+    yield request.param
+    splat.OCC_BACKWARD_HYBRID = old
+
+
+def test_backward_matches_oracle(occ_sweep):
     S, V = 64, 2
     inp, t, idx, occ_grad, zbuf_grad = _backward_inputs(S, V, [700, 500], seed=5)
     pts = t["points"].clone().requires_grad_(True)
@@ -182,9 +190,29 @@ def test_backward_matches_oracle():
     assert (got[~vis, :2] == 0).all()
 
 
+def test_backward_dense_gradient_hybrid_equals_window():
+    """Every pixel carries a gradient: the hybrid sweep takes its dense-tile branch."""
+    S, V = 96, 2
+    inp = make_splat_inputs(V, [1500, 1100], S, seed=17, sigma_px=1.6)
+    t = _t(inp)
+    occ_grad = torch.randn(V, S, S, device=DEV)
+    res = []
+    for hybrid in (True, False):
+        splat.OCC_BACKWARD_HYBRID = hybrid
+        pts = t["points"].clone().requires_grad_(True)
+        out = splat.EllipticalRasterizer.apply(pts, t["ellipse"], t["cutoff"], t["radii"], t["first_idx"],
+                                               t["num_points"], 0.05, S, 6, 16, 0, 5.0)
+        (out[3] * occ_grad).sum().backward()
+        res.append(pts.grad.clone())
+    splat.OCC_BACKWARD_HYBRID = True
+    scale = res[1].abs().amax(0).clamp_min(1e-20)
+    np.testing.assert_allclose((res[0] / scale).cpu().numpy(), (res[1] / scale).cpu().numpy(), rtol=1e-4, atol=2e-5)
+    assert res[1][:, :2].abs().sum() > 0
+
+
 @REF
 @pytest.mark.parametrize("V", [1, 2])
-def test_backward_vs_reference_cuda(V):
+def test_backward_vs_reference_cuda(V, occ_sweep):
     """Fast-path occupancy + z-buffer backward vs the reference's own kernels and host sequence.
     For views n >= 1 the reference drops the points of its last 2-D grid cell (packed-vs-local
     offset bug, rasterize_points_backward.cu:124-126): those rows are excluded, and counted."""
@@ -218,7 +246,7 @@ def test_backward_vs_reference_cuda(V):
 
 
 @REF
-def test_slow_path_occ_backward_vs_reference():
+def test_slow_path_occ_backward_vs_reference(occ_sweep):
     S = 64
     inp, t, idx, occ_grad, _ = _backward_inputs(S, 2, [800, 600], seed=13)
     C = ref_native.dss_C()
