@@ -398,6 +398,208 @@ splat_raster_kernel(const float4* __restrict__ recs, const int* __restrict__ til
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Raster v2: record-centric hit generation.
+// v1 above evaluates every surviving record on all 32 pixels of a warp's 8x4 block although a
+// sigma = 1.5 px splat covers ~2 of them: ~7 % of the issued lanes do useful work, and the kernel is
+// issue-bound.  Here the roles are swapped for the collection phase:
+//   phase 1  one THREAD per record sweeps the record's own (exactly trimmed) pixel box inside the
+//            tile and appends each hit (z, id, Q) to that pixel's column in shared memory
+//            (slot = atomicAdd on a per-pixel shared counter; C slots per pixel);
+//   phase 2  one thread per pixel keeps the K smallest (z, id) of its <= C entries in place
+//            (replace-max), pulls them into registers and sorts them with the network of v1.
+// The arrival order inside a column depends on scheduling, the selected set and its order do not:
+// (z, id) is a total order.  A pixel that receives more than C hits (dense overdraw) is redone by
+// the v1 per-pixel algorithm in a second pass over the tile's records, so any input is handled.
+// ---------------------------------------------------------------------------------------------
+constexpr int CHUNK2 = 256;          // records per TMA chunk in v2: one per thread (12 KB)
+
+template <int K, int C>
+__global__ void __launch_bounds__(256)
+splat_raster_v2_kernel(const float4* __restrict__ recs, const int* __restrict__ tile_off,
+                       const int* __restrict__ tile_cnt, int S, int T, float depth_merging_thres,
+                       int occ_inclusive, int* __restrict__ out_idx, float* __restrict__ out_z,
+                       float* __restrict__ out_q, float* __restrict__ out_occ) {
+  __shared__ __align__(128) float4 buf[STAGES][CHUNK2 * REC_F4];
+  __shared__ __align__(8) unsigned long long bar[STAGES];
+  __shared__ int pcnt[256];
+  __shared__ float ndcx[TILE], ndcy[TILE];
+  extern __shared__ __align__(16) float list_smem[];   // [3][C][256]: z | id | q columns per pixel
+  float* lz = list_smem;
+  int* lid = reinterpret_cast<int*>(list_smem + C * 256);
+  float* lq = list_smem + 2 * C * 256;
+
+  const int tile = blockIdx.x;
+  const int n = tile / (T * T);
+  const int tr = tile - n * T * T;
+  const int ty = tr / T, tx = tr - ty * T;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const float fS = (float)S;
+  const int nrec = tile_cnt[tile];
+  const long long base = tile_off[tile];
+  const int nchunks = (nrec + CHUNK2 - 1) / CHUNK2;
+  // number of tile columns / rows that lie inside the image
+  const int ncol_img = min(TILE, S - tx * TILE), nrow_img = min(TILE, S - ty * TILE);
+
+  pcnt[tid] = 0;
+  if (tid < TILE) ndcx[tid] = pix_to_ndc(S - 1 - (tx * TILE + tid), fS);
+  else if (tid < 2 * TILE) ndcy[tid - TILE] = pix_to_ndc(S - 1 - (ty * TILE + tid - TILE), fS);
+  if (tid == 0) {
+    mbar_init(&bar[0], 1);
+    mbar_init(&bar[1], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  int gc = 0;   // chunks streamed so far over both passes: stage = gc & 1, parity = (gc >> 1) & 1
+  auto issue = [&](int c, int g) {
+    const int cnt = min(CHUNK2, nrec - c * CHUNK2);
+    const unsigned bytes = (unsigned)cnt * REC_F4 * 16u;
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    mbar_expect_tx(&bar[g & 1], bytes);
+    tma_bulk_g2s(&buf[g & 1][0], recs + (base + (long long)c * CHUNK2) * REC_F4, bytes, &bar[g & 1]);
+  };
+
+  // ---- phase 1: hit generation, one thread per record ----
+  if (tid == 0)
+    for (int c = 0; c < STAGES && c < nchunks; ++c) issue(c, gc + c);
+  for (int c = 0; c < nchunks; ++c, ++gc) {
+    mbar_wait(&bar[gc & 1], (unsigned)((gc >> 1) & 1));
+    const int cnt = min(CHUNK2, nrec - c * CHUNK2);
+    if (tid < cnt) {
+      const float4* rb = buf[gc & 1] + tid * REC_F4;
+      const float4 a0 = rb[0], a1 = rb[1], a2 = rb[2];
+      int xl, xh, yl, yh;
+      pixel_range(a0.x, a1.w, S, fS, xl, xh);
+      pixel_range(a0.y, a2.x, S, fS, yl, yh);
+      // to tile-local output coordinates (col = S-1-xi)
+      const int cx0 = max(S - 1 - xh - tx * TILE, 0), cx1 = min(S - 1 - xl - tx * TILE, ncol_img - 1);
+      const int cy0 = max(S - 1 - yh - ty * TILE, 0), cy1 = min(S - 1 - yl - ty * TILE, nrow_img - 1);
+      const int id = __float_as_int(a2.y);
+      for (int yy = cy0; yy <= cy1; ++yy) {
+        const float dy = __fsub_rn(ndcy[yy], a0.y);
+        if (fabsf(dy) > a2.x) continue;
+        const float cdy = __fmul_rn(a1.y, dy);
+        for (int xx = cx0; xx <= cx1; ++xx) {
+          const float dx = __fsub_rn(ndcx[xx], a0.x);
+          if (fabsf(dx) > a1.w) continue;
+          const float q = __fmaf_rn(cdy, dy, __fmaf_rn(__fmul_rn(a0.w, dx), dx, __fmul_rn(__fmul_rn(a1.x, dx), dy)));
+          if (q > a1.z) continue;
+          const int pix = yy * TILE + xx;
+          const int slot = atomicAdd(&pcnt[pix], 1);
+          if (slot < C) { lz[slot * 256 + pix] = a0.z; lid[slot * 256 + pix] = id; lq[slot * 256 + pix] = q; }
+        }
+      }
+    }
+    __syncthreads();
+    if (tid == 0 && c + STAGES < nchunks) issue(c + STAGES, gc + STAGES);
+  }
+
+  // ---- phase 2: per-pixel selection ----
+  const int col = tx * TILE + (tid & 15), row = ty * TILE + (tid >> 4);
+  const bool in_img = col < S && row < S;
+  const int nhit = pcnt[tid];
+  const bool overflow = nhit > C;
+  PixList<K> L;
+  L.clear();
+  if (__syncthreads_or(overflow)) {
+    // dense overdraw somewhere in this tile: the overflowing pixels are redone exactly by the v1
+    // per-pixel algorithm (warp-level box cull + replace-max list in the first K slots of the column)
+    SmemList<K> SL;
+    SL.z = lz + tid; SL.id = lid + tid; SL.q = lq + tid;
+    SL.cnt = 0; SL.maxz = -FLT_MAX; SL.maxid = -1; SL.maxpos = 0;
+    const float xf = ndcx[tid & 15], yf = ndcy[tid >> 4];
+    const unsigned need = __ballot_sync(0xffffffffu, overflow);
+    if (tid == 0)
+      for (int c = 0; c < STAGES && c < nchunks; ++c) issue(c, gc + c);
+    for (int c = 0; c < nchunks; ++c, ++gc) {
+      mbar_wait(&bar[gc & 1], (unsigned)((gc >> 1) & 1));
+      const int cnt = min(CHUNK2, nrec - c * CHUNK2);
+      if (need) {
+        const float4* rb = buf[gc & 1];
+        for (int s = 0; s < cnt; ++s) {
+          const float4 a0 = rb[s * REC_F4 + 0], a1 = rb[s * REC_F4 + 1], a2 = rb[s * REC_F4 + 2];
+          const float dx = __fsub_rn(xf, a0.x), dy = __fsub_rn(yf, a0.y);
+          if (!overflow || fabsf(dx) > a1.w || fabsf(dy) > a2.x) continue;
+          const float q = __fmaf_rn(__fmul_rn(a1.y, dy), dy,
+                                    __fmaf_rn(__fmul_rn(a0.w, dx), dx, __fmul_rn(__fmul_rn(a1.x, dx), dy)));
+          if (q > a1.z) continue;
+          SL.insert(a0.z, __float_as_int(a2.y), q);
+        }
+      }
+      __syncthreads();
+      if (tid == 0 && c + STAGES < nchunks) issue(c + STAGES, gc + STAGES);
+    }
+    if (overflow) SL.drain(L);
+  }
+  if (!in_img) return;
+  if (!overflow) {
+    float* cz = lz + tid; int* ci = lid + tid; float* cq = lq + tid;
+    if (nhit > K) {
+      // keep the K smallest (z, id) in slots [0, K): replace-max over the remaining entries
+      float maxz = cz[0]; int maxid = ci[0], maxpos = 0;
+#pragma unroll
+      for (int k = 1; k < K; ++k)
+        if (zid_less(maxz, maxid, cz[k * 256], ci[k * 256])) { maxz = cz[k * 256]; maxid = ci[k * 256]; maxpos = k; }
+      for (int e = K; e < nhit; ++e) {
+        const float ez = cz[e * 256];
+        const int ei = ci[e * 256];
+        if (!zid_less(ez, ei, maxz, maxid)) continue;
+        cz[maxpos * 256] = ez; ci[maxpos * 256] = ei; cq[maxpos * 256] = cq[e * 256];
+        maxz = cz[0]; maxid = ci[0]; maxpos = 0;
+#pragma unroll
+        for (int k = 1; k < K; ++k)
+          if (zid_less(maxz, maxid, cz[k * 256], ci[k * 256])) { maxz = cz[k * 256]; maxid = ci[k * 256]; maxpos = k; }
+      }
+    }
+    const int m = min(nhit, K);
+#pragma unroll
+    for (int k = 0; k < K; ++k)
+      if (k < m) { L.z[k] = cz[k * 256]; L.id[k] = ci[k * 256]; L.q[k] = cq[k * 256]; }
+    L.cnt = m;
+  }
+  L.sort();
+  const int size = L.cnt;
+  float zmax = -1000.0f;
+#pragma unroll
+  for (int k = 0; k < K; ++k)
+    if (k < size) zmax = L.z[k];
+  const float z0 = L.z[0];
+  bool alive = true;
+  int oi[K];
+  float oz[K], oq[K];
+#pragma unroll
+  for (int k = 0; k < K; ++k) {
+    alive = alive && (k < size) && !(__fsub_rn(L.z[k], z0) > depth_merging_thres);
+    oi[k] = alive ? L.id[k] : -1;
+    oz[k] = alive ? L.z[k] : -1.0f;
+    oq[k] = alive ? L.q[k] : -1.0f;
+  }
+  const size_t pix = ((size_t)n * S + row) * S + col;
+  out_occ[pix] = (size > 0 && (occ_inclusive ? (zmax >= 0.0f) : (zmax > 0.0f))) ? 1.0f : 0.0f;
+  int* pi = out_idx + pix * K;
+  float* pz = out_z + pix * K;
+  float* pq = out_q + pix * K;
+  if constexpr (K % 4 == 0) {
+#pragma unroll
+    for (int k = 0; k < K; k += 4) {
+      *reinterpret_cast<int4*>(pi + k) = make_int4(oi[k], oi[k + 1], oi[k + 2], oi[k + 3]);
+      *reinterpret_cast<float4*>(pz + k) = make_float4(oz[k], oz[k + 1], oz[k + 2], oz[k + 3]);
+      *reinterpret_cast<float4*>(pq + k) = make_float4(oq[k], oq[k + 1], oq[k + 2], oq[k + 3]);
+    }
+  } else if constexpr (K % 2 == 0) {
+#pragma unroll
+    for (int k = 0; k < K; k += 2) {
+      *reinterpret_cast<int2*>(pi + k) = make_int2(oi[k], oi[k + 1]);
+      *reinterpret_cast<float2*>(pz + k) = make_float2(oz[k], oz[k + 1]);
+      *reinterpret_cast<float2*>(pq + k) = make_float2(oq[k], oq[k + 1]);
+    }
+  } else {
+#pragma unroll
+    for (int k = 0; k < K; ++k) { pi[k] = oi[k]; pz[k] = oz[k]; pq[k] = oq[k]; }
+  }
+}
+
 // Generic K (17..150, rasterization_utils.cuh:18): same algorithm, list in local memory.
 __global__ void __launch_bounds__(256)
 splat_raster_bigk_kernel(const float4* __restrict__ recs, const int* __restrict__ tile_off,
@@ -513,9 +715,16 @@ splat_pair_count_kernel(const float* __restrict__ points, const float* __restric
 }
 
 template <int K>
-static void launch_raster(int tiles, cudaStream_t st, const float4* recs, const int* off, const int* cnt,
-                          int S, int T, float thres, int occ_incl, int* oi, float* oz, float* oq,
-                          float* oo) {
+static void launch_raster(int variant, int tiles, cudaStream_t st, const float4* recs, const int* off,
+                          const int* cnt, int S, int T, float thres, int occ_incl, int* oi, float* oz,
+                          float* oq, float* oo) {
+  if (variant != 1) {   // v2: C slots per pixel column; K <= 8 -> 24 (72 KB), else K + 16
+    constexpr int C = (K <= 8) ? 24 : K + 16;
+    const int smem2 = 3 * C * 256 * (int)sizeof(float);
+    cudaFuncSetAttribute(splat_raster_v2_kernel<K, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem2);
+    splat_raster_v2_kernel<K, C><<<tiles, 256, smem2, st>>>(recs, off, cnt, S, T, thres, occ_incl, oi, oz, oq, oo);
+    return;
+  }
   const int smem = 3 * K * 256 * (int)sizeof(float);
   // static + dynamic shared memory passes 48 KB from K = 12: opt in (per device, so on every launch)
   cudaFuncSetAttribute(splat_raster_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
@@ -597,7 +806,9 @@ int isob200_splat_bin(const float* points, const float* radii, const int64_t* fi
 // and rasterise.  `ws` must be the workspace isob200_splat_bin just filled; `recs` holds
 // `capacity` records of isob200_splat_record_bytes() each (capacity >= the total read back).
 // Outputs are fully written: idx int32 (N,S,S,K), zbuf/qvalue f32 (N,S,S,K), occ f32 (N,S,S).
-// occ_inclusive: 1 = naive-kernel rule q_max_z >= 0 (bin_size == 0), 0 = fine-kernel rule > 0.
+// occ_inclusive: bit 0: 1 = naive-kernel rule q_max_z >= 0 (bin_size == 0), 0 = fine-kernel rule > 0;
+//                bits 8..9: raster variant, 0/2 = v2 (record-centric hit generation, default),
+//                1 = v1 (pixel-centric with warp-level culling).  Results are identical.
 int isob200_splat_forward(const float* points, const float* ellipse, const float* cutoff,
                           const float* radii, const int64_t* first_idx, const int64_t* num_points,
                           int N, long long P, long long max_points_per_cloud, int S, int K,
@@ -626,10 +837,12 @@ int isob200_splat_forward(const float* points, const float* ellipse, const float
                                                        S, T, w.tile_off, w.tile_cur, capacity, (float4*)recs);
     ISO_CHECK_LAUNCH("splat_tile_fill_kernel");
   }
+  const int variant = (occ_inclusive >> 8) & 3;
+  occ_inclusive &= 1;
   const float4* r = (const float4*)recs;
   int* oi = out_idx; float* oz = out_zbuf; float* oq = out_qvalue; float* oo = out_occ;
   const float th = depth_merging_thres;
-#define RK(KK) case KK: launch_raster<KK>(tiles, st, r, w.tile_off, w.tile_cnt, S, T, th, occ_inclusive, oi, oz, oq, oo); break;
+#define RK(KK) case KK: launch_raster<KK>(variant, tiles, st, r, w.tile_off, w.tile_cnt, S, T, th, occ_inclusive, oi, oz, oq, oo); break;
   switch (K) {
     RK(1) RK(2) RK(3) RK(4) RK(5) RK(6) RK(7) RK(8) RK(9) RK(10) RK(11) RK(12) RK(13) RK(14) RK(15) RK(16)
     default:

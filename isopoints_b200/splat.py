@@ -27,6 +27,10 @@ from torch import autograd
 
 from . import _ext
 
+# raster kernel variant: 0/2 = v2 (record-centric hit generation, default), 1 = v1 (pixel-centric with
+# warp-level culling).  Identical results; v1 is kept as the fallback algorithm inside v2 and for A/B timing.
+RASTER_VARIANT = 0
+
 kMaxPointsPerBin = 22
 kMaxPointsPerPixel = 150
 NORM_WEIGHT_EPS = 1e-4   # pytorch3d norm_weighted_sum kEpsilon [third party, restated]
@@ -100,7 +104,8 @@ def _splat(points, ellipse, cutoff, radii, first_idx, num_points, depth_merging_
     recs = torch.empty((max(cap, 1) * lib.isob200_splat_record_bytes(),), dtype=torch.uint8, device=dev)
     _ext.check(lib.isob200_splat_forward(
         _ext.ptr(points), _ext.ptr(ellipse), _ext.ptr(cutoff), _ext.ptr(radii), _ext.ptr(first_idx),
-        _ext.ptr(num_points), N, P, maxp, S, K, float(depth_merging_thres), 1 if occ_inclusive else 0,
+        _ext.ptr(num_points), N, P, maxp, S, K, float(depth_merging_thres),
+        (1 if occ_inclusive else 0) | ((RASTER_VARIANT & 3) << 8),
         _ext.ptr(ws), ws.numel(), _ext.ptr(recs), cap, _ext.ptr(idx), _ext.ptr(zbuf), _ext.ptr(qvalue),
         _ext.ptr(occ), st))
     return idx, zbuf, qvalue, occ

@@ -23,8 +23,27 @@ def _fwd(t, S, K, thres=0.05, bin_size=16):
                                  t["num_points"], thres, S, K, bin_size, 10000)
 
 
+@pytest.fixture(params=[1, 2], ids=["raster_v1", "raster_v2"])
+def raster_variant(request):
+    old = splat.RASTER_VARIANT
+    splat.RASTER_VARIANT = request.param
+    yield request.param
+    splat.RASTER_VARIANT = old
+
+
+def test_forward_dense_overdraw_takes_the_overflow_path(raster_variant):
+    """~60 covering splats per pixel: far beyond the per-pixel column capacity of raster v2."""
+    S, K = 32, 8
+    inp = make_splat_inputs(1, 9000, S, seed=23, sigma_px=1.5, behind_frac=0.0)
+    idx, zbuf, qv, occ = _fwd(_t(inp), S, K)
+    wi, wz, wq, wo = port.splat_forward(inp["points"], inp["ellipse"], inp["cutoff"], inp["radii"],
+                                        inp["first_idx"], inp["num_points"], 0.05, S, K)
+    assert np.array_equal(idx.cpu().numpy(), wi) and np.array_equal(zbuf.cpu().numpy(), wz)
+    assert np.array_equal(qv.cpu().numpy(), wq) and np.array_equal(occ.cpu().numpy(), wo)
+
+
 @pytest.mark.parametrize("S,K", [(64, 1), (64, 3), (64, 4), (50, 5), (64, 8), (48, 16), (40, 20)])
-def test_forward_bit_exact_vs_oracle(S, K):
+def test_forward_bit_exact_vs_oracle(S, K, raster_variant):
     inp = make_splat_inputs(2, [1500, 900], S, seed=S + K, sigma_px=1.7)
     idx, zbuf, qv, occ = _fwd(_t(inp), S, K)
     wi, wz, wq, wo = port.splat_forward(inp["points"], inp["ellipse"], inp["cutoff"], inp["radii"],
@@ -68,7 +87,7 @@ def test_forward_naive_occupancy_rule_and_z0():
     assert ((i0[..., 1:] > i0[..., :-1]) | ~valid[..., 1:]).all()
 
 
-def test_forward_edge_cases():
+def test_forward_edge_cases(raster_variant):
     S, K = 32, 4
     t = _t(make_splat_inputs(2, [200, 0], S, seed=1))
     idx, zbuf, qv, occ = _fwd(t, S, K)
@@ -107,7 +126,7 @@ def test_bin_counts_bit_exact():
 
 @REF
 @pytest.mark.parametrize("bin_size", [0, 16])
-def test_forward_vs_reference_cuda_kernels(bin_size):
+def test_forward_vs_reference_cuda_kernels(bin_size, raster_variant):
     S, K = 128, 8
     inp = make_splat_inputs(3, [6000, 4000, 5000], S, seed=21, sigma_px=1.5)
     t = _t(inp)
@@ -126,7 +145,7 @@ def test_forward_vs_reference_cuda_kernels(bin_size):
 
 
 @REF
-def test_forward_c4_scale_vs_reference_and_properties():
+def test_forward_c4_scale_vs_reference_and_properties(raster_variant):
     """BASELINE config 4: 8 views x 300 000 splats at 512^2, K = 8, bin_size = 32."""
     S, K, V, Pv = 512, 8, 8, 300_000
     inp = make_splat_inputs(V, Pv, S, seed=0, sigma_px=1.5, aniso=False)
