@@ -208,8 +208,9 @@ frnn_query_kernel(const float* __restrict__ q_points,     // (N,P1,D) in process
   }
 }
 
-// Exhaustive traversal of the full (2c+1)^D block in cell order (no best-first order, no pruning):
-// the better kernel when the grid is mostly EMPTY cells (surface-like clouds with a small cell: at
+// Block traversal of the (2c+1)^D cell block: the lanes prefetch every run's slice and its distance
+// to the query, the runs next to the query are scanned first and the others are skipped when they
+// cannot beat the K-th best.  The better kernel when the grid is mostly EMPTY cells (surface-like clouds with a small cell: at
 // BASELINE config 2 there are ~0.1 points per cell), where skipping an empty run costs two offset loads
 // and the pruning bookkeeping of the kernel above costs more than it saves.
 template <int D, int GW, typename IdxT>
@@ -256,6 +257,8 @@ frnn_query_exhaustive_kernel(const float* __restrict__ q_points,     // (N,P1,D)
 
     // candidate cell range, grid.cu:305-316 (fp32: (p - min -/+ r) * delta, floor)
     int lo[D], hi[D], res[D];
+    float qc[D];
+    const float inv_delta = 1.0f / prm[D];
 #pragma unroll
     for (int d = 0; d < D; ++d) {
       const float rel = __fsub_rn(q[d], prm[d]);
@@ -263,6 +266,7 @@ frnn_query_exhaustive_kernel(const float* __restrict__ q_points,     // (N,P1,D)
       res[d] = (int)prm[D + 1 + d];
       lo[d] = max(__float2int_rd(__fmul_rn(__fsub_rn(rel, r), delta)), 0);
       hi[d] = min(__float2int_rd(__fmul_rn(__fadd_rn(rel, r), delta)), res[d] - 1);
+      qc[d] = rel * delta;
     }
     const int grid_total = (int)prm[2 * D + 1];
 
@@ -285,6 +289,7 @@ frnn_query_exhaustive_kernel(const float* __restrict__ q_points,     // (N,P1,D)
       // them on a surface -- costs two shuffles and a compare instead of a dependent load chain
       for (int rbase = 0; rbase < nruns; rbase += GW) {
        int my_start = 0, my_end = 0;
+       float my_gap2 = 0.f;   // conservative squared distance from the query to the run's cell column
        {
         const int run = rbase + gl;
         if (run < nruns) {
@@ -293,17 +298,27 @@ frnn_query_exhaustive_kernel(const float* __restrict__ q_points,     // (N,P1,D)
             const int x = lo[0] + run / ny, y = lo[1] + run % ny;
             c0 = (x * res[1] + y) * res[2] + lo[2];
             c1 = (x * res[1] + y) * res[2] + hi[2];
+            my_gap2 = axis_gap2(qc[0], x, inv_delta) + axis_gap2(qc[1], y, inv_delta);
           } else {
             const int x = lo[0] + run;
             c0 = x * res[1] + lo[1];
             c1 = x * res[1] + hi[1];
+            my_gap2 = axis_gap2(qc[0], x, inv_delta);
           }
           my_start = off2[c0];
           my_end = (c1 + 1 == grid_total) ? len2 : off2[c1 + 1];
         }
        }
        const int nr = min(GW, nruns - rbase);
-       for (int rj = 0; rj < nr; ++rj) {
+       // two sweeps over the prefetched runs: the ones next to the query first (they establish the
+       // K-th distance), then the rest -- skipped when even their nearest cell wall is farther than the
+       // K-th best (strict >, equal-distance ties still compete)
+       const float near2 = inv_delta * inv_delta;
+       for (int rj2 = 0; rj2 < 2 * nr; ++rj2) {
+        const int rj = rj2 < nr ? rj2 : rj2 - nr;
+        const float gap2 = __shfl_sync(gmask, my_gap2, (int)gshift + rj);
+        if ((gap2 <= near2) != (rj2 < nr)) continue;
+        if (gap2 > fminf(r2, kth_d)) continue;
         const int start = __shfl_sync(gmask, my_start, (int)gshift + rj);
         const int end = __shfl_sync(gmask, my_end, (int)gshift + rj);
         for (int base = start; base < end; base += GW) {

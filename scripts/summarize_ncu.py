@@ -68,7 +68,16 @@ def traffic(rep):
     for k in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
         tot += float(d[k].replace(",", "")) * mult.get(u[k], 1)
     name = re.sub(r"<.*", "", d["Kernel Name"].replace("void ", "").replace("isob200::", "")).strip()
-    return name, tot
+    extra = {}
+    for k, short in (("smsp__issue_active.avg.pct_of_peak_sustained_active", "issue_active_pct"),
+                     ("gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "dram_pct"),
+                     ("lts__throughput.avg.pct_of_peak_sustained_elapsed", "l2_pct"),
+                     ("sm__warps_active.avg.pct_of_peak_sustained_active", "occupancy_pct")):
+        try:
+            extra[short] = float(d[k].replace(",", ""))
+        except Exception:
+            pass
+    return name, tot, extra
 
 
 def hot_lines(rep, top=14):
@@ -109,8 +118,8 @@ def main():
         if f.endswith(".ncu-rep"):
             rep = os.path.join(OUT, f)
             try:
-                name, b = traffic(rep)
-                tr[f[:-8]] = {"dram_bytes_per_launch": b, "kernel": name, "capture": "%s_%s" % (tag, f[:-8])}
+                name, b, extra = traffic(rep)
+                tr[f[:-8]] = {"dram_bytes_per_launch": b, "kernel": name, "capture": "%s_%s" % (tag, f[:-8]), **extra}
             except Exception as e:
                 print("traffic:", f, e)
             txt = raw(rep) + "\n\nhottest source lines (share of executed instructions):\n" + hot_lines(rep) + "\n"
