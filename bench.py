@@ -131,11 +131,14 @@ def _max_over_ranks(x, world, dev):
     return float(t.item())
 
 
-def _make_c2(rank, dev):
-    from tests.helpers import SirenSDF
+def _make_c2(rank, dev, opaque=False):
+    """C2 cloud + SDF.  `Siren` is the structural twin of the reference decoder
+    (DSS/models/common.py:90-165), which the package evaluates with its fused tcgen05 kernel;
+    `SirenSDF` holds the same weights as an opaque nn.Module (autograd path)."""
+    from tests.helpers import Siren, SirenSDF
     g = torch.Generator().manual_seed(1000 + rank)
     x = (torch.rand(1, C2_POINTS, 3, generator=g) - 0.5) * 2
-    net = SirenSDF(hidden=256, n_layers=7, omega=30.0, seed=0)
+    net = (SirenSDF if opaque else Siren)(256, 7, 30.0, seed=0)
     return x, net
 
 
@@ -149,7 +152,7 @@ def run_ours(args):
     torch.backends.cuda.matmul.allow_tf32 = False      # parity bar is fp32 1e-4 (SIREN x30 gain)
     torch.backends.cudnn.allow_tf32 = False
     lib = _ext.lib()
-    x_host, net = _make_c2(rank, dev)
+    x_host, net = _make_c2(rank, dev, opaque=args.sdf == "opaque")
     net = net.to(dev)
     x_dev = x_host.to(dev)
     x_pin = x_host.pin_memory()
@@ -177,6 +180,9 @@ def run_ours(args):
 
     # ---- timed region: K steps, device resident inputs, L2 flushed between steps ----------
     _ext.PROFILE = {}
+    from isopoints_b200 import siren as _siren
+    for k_ in _siren.STATS:
+        _siren.STATS[k_] = 0
     l0 = lib.isob200_launch_count()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     with ClockSampler(local) as clocks:
@@ -192,6 +198,7 @@ def run_ours(args):
     launches = lib.isob200_launch_count() - l0
     prof = _ext.PROFILE
     _ext.PROFILE = None
+    siren_stats = dict(_siren.STATS)
     ms = sum(a.elapsed_time(b) for a, b in ev) / args.steps
     ms = _max_over_ranks(ms, world, dev)
     converged = float(out["mask"].float().mean())
@@ -223,25 +230,48 @@ def run_ours(args):
     d2h = sum(t.numel() * t.element_size() for t in res)
 
     peaks, peak_src = _peaks()
-    # dominant own kernel of this path: the FRNN query (K = knn_k + 1 = 9, int64 idx + f32 dist out)
+    sd = kern.get("siren_sdf_grad")
     q = kern.get("frnn_find_nbrs")
     roof = None
+    frnn_roof = None
     if q:
+        # the FRNN query (K = knn_k + 1 = 9, int64 idx + f32 dist out); SURVEY 8d: 16 + 12K bytes per query
         K = 9
-        n_q = n_out * (world if world > 1 else 1) if False else n_out
-        alg = n_q * (16 + 12 * K)                       # 16 + 12K bytes per query
+        alg = n_out * (16 + 12 * K)
         achieved = alg / (q["avg_ms"] * 1e-3) / 1e9
-        roof = {"kernel": "frnn_query_kernel", "bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"],
-                "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"], "traffic": _ncu_traffic("prof_frnn_query_c2"), "peak_source": peak_src,
-                "algorithmic_bytes_per_launch": alg, "avg_launch_ms": q["avg_ms"],
-                "limiter": "instruction issue, not HBM (candidates are served by L1/L2)", "ncu": _ncu("prof_frnn_query_c2")}
+        frnn_roof = {"kernel": "frnn_query_kernel", "bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"],
+                     "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"],
+                     "traffic": _ncu_traffic("prof_frnn_query_c2"), "peak_source": peak_src,
+                     "algorithmic_bytes_per_launch": alg, "avg_launch_ms": q["avg_ms"],
+                     "limiter": "instruction issue, not HBM (candidates are served by L1/L2)",
+                     "ncu": _ncu("prof_frnn_query_c2")}
+        roof = frnn_roof
+    if sd:
+        # dominant kernel of the step: the fused SIREN SDF + gradient kernel (tensor-core bound).
+        # achieved = fp32-equivalent algorithmic FLOPs of the timed launches / their CUDA-event time;
+        # every fp32-equivalent product costs three fp16 tcgen05 MMAs (hi*hi + lo*hi + hi*lo).
+        flops = siren_stats["flops"] / max(siren_stats["calls"], 1)
+        avg_ms = sd["avg_ms"]
+        achieved = flops / (avg_ms * 1e-3) / 1e12
+        peak_tf = peaks.get("bf16_tflops_sustained") or peaks.get("bf16_tflops") or 1500.0
+        roof = {"kernel": "siren_sdf_grad_kernel", "bound": "tensor", "achieved": achieved, "peak": peak_tf,
+                "unit": "TFLOP/s", "frac": achieved / peak_tf, "traffic": _ncu_traffic("prof_siren"),
+                "peak_source": peak_src + " (dense bf16 cuBLAS, sustained; fp16 MMA runs at the same rate)",
+                "algorithmic_flops_per_launch": flops, "avg_launch_ms": avg_ms,
+                "rows_per_launch": siren_stats["rows"] / max(siren_stats["calls"], 1),
+                "tensor_pipe_frac": 3 * achieved / peak_tf,
+                "note": "fp32 accuracy from 3 fp16 MMAs per product: frac <= 1/3 by construction; "
+                        "tensor_pipe_frac counts the issued MMA work", "ncu": _ncu("prof_siren")}
 
     line = {
         "metric": "iso-points/sec (project+resample)", "value": C2_POINTS * world / (ms * 1e-3), "unit": "points/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "C2: 200000 pts/GPU, random-init SIREN 8x256 SDF (fp32, TF32 off), project(10 it)+"
-                               "resample(knn_k=8, 1 it)+reproject(3 it)", "points_per_gpu": C2_POINTS,
+        "config": {"workload": "C2: 200000 pts/GPU, random-init SIREN 8x256 SDF (%s), project(10 it)+"
+                               "resample(knn_k=8, 1 it)+reproject(3 it)" % (
+                                   "fused tcgen05 kernel, fp32-equivalent via fp16 hi/lo split" if sd else
+                                   "opaque nn.Module through autograd, fp32, TF32 off"),
+                   "points_per_gpu": C2_POINTS, "sdf": args.sdf,
                    "l2": "flushed between steps (256 MiB write)", "converged_frac": converged,
                    "points_after_filter": n_out, "parallelism": "point-sharded x%d" % world},
         "e2e": {"value": C2_POINTS * world / (e2e_ms * 1e-3), "unit": "points/s", "h2d_bytes_per_step": h2d,
@@ -249,6 +279,7 @@ def run_ours(args):
         "gpu_launches": int(launches),
         "clocks": clocks.summary(),
         "roofline": roof,
+        "roofline_frnn": frnn_roof,
         "own_kernels_ms_per_step": own_ms,
         "sdf_callback_and_glue_ms_per_step": ms - own_ms,
         "kernels": kern,
@@ -348,6 +379,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--cpu-sample", type=int, default=10_000)
+    ap.add_argument("--sdf", default="siren", choices=["siren", "opaque"],
+                    help="siren: the reference's Siren decoder structure (fused SDF kernel); "
+                         "opaque: same weights behind an opaque nn.Module (autograd SDF)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

@@ -81,6 +81,26 @@ int isob200_gather_rows3(const float* src, const int* idx, int A, float* dst, vo
 int isob200_project_sphere(float* points, float* normals, unsigned char* valid, long long M,
                            float radius, float tol, float max_step, int max_iters, void* stream);
 
+/* ---- fused SIREN SDF value + input gradient: UniformProjection._compute_sdf_and_grad
+ *      (DSS/models/levelset_sampling.py:142-170) for SDF modules that are the reference's
+ *      Siren MLP (DSS/models/common.py:56-165; hidden width 256).  `pack` converts the fp32
+ *      parameters (w0 (256,3), b0 (256), w_hidden (L,256,256), b_hidden (L,256), w_last (256),
+ *      b_last (1); biases may be NULL) into the tensor-core operand images once per parameter
+ *      version; `sdf_grad` evaluates sdf (n) and d sdf / d x (n,3) for x (n,3).  n_dev, when
+ *      non-NULL, is a device int with the live row count (<= n_max) so a projection loop can
+ *      run without reading the active count back.  dbg (NULL in production) receives the raw
+ *      (128,256) accumulator of the first tile's GEMM number dbg_gemm (parity tests). ------- */
+size_t isob200_siren_blob_bytes(int n_hidden);
+size_t isob200_siren_pack_ws_bytes(void);
+size_t isob200_siren_scratch_bytes(int n_hidden);
+int isob200_siren_pack(const float* w0, const float* b0, const float* w_hidden, const float* b_hidden,
+                       const float* w_last, const float* b_last, float omega0, float omega, int hidden,
+                       int n_hidden, void* blob, size_t blob_bytes, void* ws, size_t ws_bytes,
+                       void* stream);
+int isob200_siren_sdf_grad(const float* x, int n_max, const int* n_dev, const void* blob, int n_hidden,
+                           float* sdf, float* grad, void* scratch, size_t scratch_bytes, float* dbg,
+                           int dbg_gemm, void* stream);
+
 /* ---- uniform resampling: UniformProjection.resample, one sample_iter
  *      (DSS/models/levelset_sampling.py:259, 268-284) ------------------------------------ */
 int isob200_resample_step(const float* q_points, const float* points, const float* normals,

@@ -1,0 +1,700 @@
+// Fused SIREN SDF value + input-gradient kernel.
+//
+// Replaces, for SDF modules that are a plain SIREN MLP (DSS/models/common.py:56-165: SineLayer
+// chain + linear head), the autograd round trip of UniformProjection._compute_sdf_and_grad
+// (DSS/models/levelset_sampling.py:142-170): model.forward(x).sdf followed by
+// autograd.grad(sdf, x, ones).  One persistent kernel evaluates the whole network and its
+// reverse-mode input gradient for 128-point tiles:
+//
+//   forward   z_0 = x W_0^T + b_0 (K = 3, SIMT)            h_0 = sin(w0 z_0)
+//             z_l = h_{l-1} W_l^T + b_l  (tcgen05 GEMM)    h_l = sin(w z_l),  c_l = w cos(w z_l)
+//             sdf = h_L . w_last + b_last
+//   backward  gp_L = w_last * c_L ;  g_{l-1} = gp_l W_l (tcgen05 GEMM) ;  gp_{l-1} = g_{l-1} * c_{l-1}
+//             grad = gp_0 W_0
+//
+// B200 mapping
+//   * the 2L hidden GEMMs [128 x 256] x [256 x 256] run on the 5th-gen tensor cores
+//     (tcgen05.mma.cta_group::1.kind::f16, M=128, N=256, K=16), accumulators in TMEM (two
+//     256-column buffers, ping-pong between consecutive GEMMs);
+//   * fp32 accuracy from fp16 tensor-core products: every operand is pre-scaled by a power of
+//     two to ~2^12 and split hi + lo (two fp16, 22 significand bits); each k-step issues
+//     hi*hi + lo*hi + hi*lo into the same fp32 accumulator (the dropped lo*lo term is 2^-24
+//     relative).  Activations are scaled by the static 2^12, weights per layer by a power of
+//     two derived on the device from max|W|, back-propagated rows by a per-row power of two;
+//     all scalings are exact and undone in the epilogue;
+//   * the A operand never leaves the SM: the epilogue warps read the accumulator with
+//     tcgen05.ld, apply bias / sin / cos (or the cos factor in the backward pass), split to
+//     fp16 hi/lo and store straight into the next GEMM's canonical K-major shared-memory
+//     layout (no-swizzle core matrices).  The hand-off is per 32-column k-block (8 mbarriers),
+//     so the next GEMM's tensor-core work overlaps the rest of the epilogue;
+//   * weights are packed once per parameter version (siren_pack_kernel) into the exact
+//     shared-memory image of each 32-wide k-block stage (hi | lo, 32 KB) for both orientations
+//     (W for the forward pass, W^T for the backward pass) and streamed L2 -> smem with 1-D TMA
+//     bulk copies (cp.async.bulk + mbarrier complete_tx) through a 3-stage ring by a producer
+//     warp;
+//   * w cos(w z_l) for the backward pass goes to a per-CTA scratch slab in global memory
+//     (float4 per thread, 512 B contiguous per warp); it is written and read back by the same
+//     thread within ~100 us, i.e. mostly L2 traffic.
+//   Warp roles: warps 0-7 epilogue (TMEM lane quarter = warp % 4, column half = warp / 4),
+//   warp 8 weight producer, warp 9 TMEM allocator + single-thread MMA issuer.
+//
+// Only H = 256 is built (BASELINE C2's "8-layer x 256 SIREN"); other widths keep the autograd path.
+#include "common.cuh"
+#include "isob200.h"
+#include <cuda_fp16.h>
+
+namespace isob200 {
+namespace siren {
+
+constexpr int H = 256;            // hidden width
+constexpr int TM = 128;           // points per tile (UMMA M)
+constexpr int KB = 32;            // k-block width (one weight stage)
+constexpr int NKB = H / KB;       // 8 k-blocks per GEMM
+constexpr int STAGES = 3;
+constexpr int STAGE_PART = H * KB * 2;        // 16 KB: one fp16 part (hi or lo) of a k-block of B
+constexpr int STAGE_BYTES = 2 * STAGE_PART;   // 32 KB: hi | lo
+constexpr int A_PART = TM * H * 2;            // 64 KB: one fp16 part of the A tile
+constexpr int A_LBO = TM * 16;                // 2048: byte stride between K-chunks (8 elems) of A
+constexpr int B_LBO = H * 16;                 // 4096: same for a B stage
+constexpr int SBO = 128;                      // byte stride between 8-row groups
+constexpr int N_EPI_WARPS = 8;
+constexpr int THREADS = (N_EPI_WARPS + 2) * 32;
+constexpr float A_SCALE = 4096.f;             // 2^12: static scale of sin() activations
+constexpr float A_SCALE_INV = 1.f / 4096.f;
+constexpr int MAX_LAYERS = 32;
+
+// ---- packed blob layout (all offsets in bytes) -------------------------------------------
+// [0,1024)        header floats: [l-1] = 2^-s_l (inverse weight scale of hidden layer l), l = 1..L
+//                 [64] gl_scale, [65] 1/gl_scale (static scale of gp_L), [66] b_last,
+//                 [67] omega_0 (first layer), [68] omega (hidden)
+// [1024,5120)     float4 w0b[256] = (W0[n,0], W0[n,1], W0[n,2], b0[n])
+// [5120,6144)     float  w_last[256]
+// [6144, ..)      float  bias[L][256]
+// images          (1024-aligned) for l = 1..L, orientation o = 0 (forward: B[n][k] = W_l[n][k])
+//                 and o = 1 (backward: B[n][k] = W_l[k][n]): 8 stages of 32 KB
+constexpr size_t HDR_GL_SCALE = 64, HDR_GL_SCALE_INV = 65, HDR_B_LAST = 66, HDR_OMEGA0 = 67, HDR_OMEGA = 68;
+constexpr size_t OFF_W0B = 1024;
+constexpr size_t OFF_WLAST = OFF_W0B + H * 16;
+constexpr size_t OFF_BIAS = OFF_WLAST + H * 4;
+__host__ __device__ inline size_t off_images(int L) { return (OFF_BIAS + (size_t)L * H * 4 + 1023) / 1024 * 1024; }
+__host__ __device__ inline size_t image_bytes() { return (size_t)NKB * STAGE_BYTES; }  // per (layer, orientation)
+__host__ __device__ inline size_t blob_bytes(int L) { return off_images(L) + (size_t)L * 2 * image_bytes(); }
+// scratch for the per-layer maxima (uint bit patterns of non-negative floats): L hidden + w_last
+constexpr size_t PACK_WS_BYTES = (MAX_LAYERS + 1) * sizeof(unsigned);
+
+// ---- shared memory map of the main kernel --------------------------------------------------
+constexpr int SM_A_HI = 0;
+constexpr int SM_A_LO = A_PART;
+constexpr int SM_STAGE = 2 * A_PART;                        // 131072
+constexpr int SM_XCH = SM_STAGE + STAGES * STAGE_BYTES;     // 229376: float xch[128][4]
+constexpr int SM_BAR = SM_XCH + TM * 4 * 4;                 // 231424
+// barriers: a_ready[8], acc_full[2], w_full[3], w_empty[3]  -> 16 * 8 B
+constexpr int SM_TMEM_PTR = SM_BAR + 16 * 8;
+constexpr int SMEM_BYTES = SM_TMEM_PTR + 16;                // 231568 <= 232448
+
+// ---- PTX helpers -----------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+// Bounded spin: a protocol bug traps (launch failure reported through the C ABI) instead of
+// hanging the GPU.  2^24 polls is >= 0.3 s, far beyond any legitimate wait in this kernel.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done = 0;
+  for (uint32_t spin = 0; !done; ++spin) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (spin > (1u << 24)) __trap();
+  }
+}
+__device__ __forceinline__ void tma_bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+               "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_mma_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                           uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// 32 lanes x 32 consecutive 32-bit columns: thread t of the warp receives lane (base lane + t)
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
+  uint32_t r[32];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void pair_barrier(int q) { asm volatile("bar.sync %0, 64;" ::"r"(q + 1) : "memory"); }
+
+// K-major, no-swizzle shared-memory matrix descriptor (cute::UMMA::SmemDescriptor, version 1):
+// core matrix = 8 rows x 16 B contiguous; SBO = stride between 8-row groups, LBO = stride
+// between the two 16-byte K-chunks of one K=16 step.
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo) {
+  return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)(lbo >> 4) << 16) | ((uint64_t)(SBO >> 4) << 32) |
+         (1ull << 46);
+}
+// instruction descriptor: D = f32, A = B = f16, K-major both, N = 256, M = 128
+constexpr uint32_t IDESC = (1u << 4) | ((uint32_t)(H >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
+
+// sin and cos of an fp32 argument to ~1 ulp for |a| < 1e5: three-constant Cody-Waite reduction by
+// pi/2, Taylor kernels on [-pi/4, pi/4] (remainders 1.7e-9 / 1.1e-10), quadrant fix-up.
+__device__ __forceinline__ void sincos_f32(float a, float& s, float& c) {
+  float j = rintf(a * 0.636619772f);
+  float r = fmaf(j, -1.57079601e+00f, a);
+  r = fmaf(j, -3.13916473e-07f, r);
+  r = fmaf(j, -5.39030253e-15f, r);
+  int q = __float2int_rn(j);
+  float r2 = r * r;
+  float sp = fmaf(r2, 2.75573192e-6f, -1.98412698e-4f);
+  sp = fmaf(sp, r2, 8.33333333e-3f);
+  sp = fmaf(sp, r2, -1.66666667e-1f);
+  sp = sp * r2;
+  sp = fmaf(sp, r, r);
+  float cp = fmaf(r2, -2.75573192e-7f, 2.48015873e-5f);
+  cp = fmaf(cp, r2, -1.38888889e-3f);
+  cp = fmaf(cp, r2, 4.16666667e-2f);
+  cp = fmaf(cp, r2, -0.5f);
+  cp = fmaf(cp, r2, 1.0f);
+  s = (q & 1) ? cp : sp;
+  c = (q & 1) ? sp : cp;
+  if (q & 2) s = -s;
+  if ((q + 1) & 2) c = -c;
+}
+
+// split 8 scaled fp32 values into fp16 hi / lo and store the two 16-byte K-chunks
+__device__ __forceinline__ void store_chunk(uint32_t a_hi_addr, uint32_t a_lo_addr, const float* o) {
+  uint32_t hi[4], lo[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    __half2 h = __floats2half2_rn(o[2 * i], o[2 * i + 1]);
+    float2 f = __half22float2(h);
+    __half2 l = __floats2half2_rn(o[2 * i] - f.x, o[2 * i + 1] - f.y);
+    hi[i] = *reinterpret_cast<uint32_t*>(&h);
+    lo[i] = *reinterpret_cast<uint32_t*>(&l);
+  }
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a_hi_addr), "r"(hi[0]), "r"(hi[1]), "r"(hi[2]),
+               "r"(hi[3])
+               : "memory");
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a_lo_addr), "r"(lo[0]), "r"(lo[1]), "r"(lo[2]),
+               "r"(lo[3])
+               : "memory");
+}
+
+// power of two p with bound * p in [2^11, 2^12) (1 for bound == 0 / non-finite)
+__device__ __forceinline__ float pow2_scale_for(float bound) {
+  int e = (int)((__float_as_uint(bound) >> 23) & 0xFF);  // biased exponent
+  if (e == 0 || e == 255) return 1.f;
+  int se = 127 + 11 - (e - 127);  // biased exponent of 2^(11 - (e-127))
+  se = se < 1 ? 1 : (se > 254 ? 254 : se);
+  return __uint_as_float((uint32_t)se << 23);
+}
+
+// ---------------------------------------------------------------------------------------------
+// pack: per-layer maxima, then fp16 hi/lo stage images + the small fp32 tables
+// ---------------------------------------------------------------------------------------------
+__global__ void siren_absmax_kernel(const float* __restrict__ w_hidden, const float* __restrict__ w_last, int L,
+                                    unsigned* __restrict__ maxbits) {
+  // blockIdx.y = layer (L = w_last)
+  int l = blockIdx.y;
+  const float* src = l < L ? w_hidden + (size_t)l * H * H : w_last;
+  int n = l < L ? H * H : H;
+  float m = 0.f;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) m = fmaxf(m, fabsf(src[i]));
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0 && m > 0.f) atomicMax(maxbits + l, __float_as_uint(m));
+}
+
+__global__ void siren_pack_kernel(const float* __restrict__ w0, const float* __restrict__ b0,
+                                  const float* __restrict__ w_hidden, const float* __restrict__ b_hidden,
+                                  const float* __restrict__ w_last, const float* __restrict__ b_last, float omega0,
+                                  float omega, int L, const unsigned* __restrict__ maxbits,
+                                  unsigned char* __restrict__ blob) {
+  float* hdr = reinterpret_cast<float*>(blob);
+  const int tid = blockIdx.x * blockDim.x + threadIdx.x;
+  const int nth = gridDim.x * blockDim.x;
+  if (tid < L) hdr[tid] = 1.f / pow2_scale_for(__uint_as_float(maxbits[tid]));
+  if (tid == 0) {
+    float gl = pow2_scale_for(fabsf(omega) * __uint_as_float(maxbits[L]));
+    hdr[HDR_GL_SCALE] = gl;
+    hdr[HDR_GL_SCALE_INV] = 1.f / gl;
+    hdr[HDR_B_LAST] = b_last ? b_last[0] : 0.f;
+    hdr[HDR_OMEGA0] = omega0;
+    hdr[HDR_OMEGA] = omega;
+  }
+  float4* w0b = reinterpret_cast<float4*>(blob + OFF_W0B);
+  float* wl = reinterpret_cast<float*>(blob + OFF_WLAST);
+  float* bias = reinterpret_cast<float*>(blob + OFF_BIAS);
+  for (int i = tid; i < H; i += nth) {
+    w0b[i] = make_float4(w0[3 * i], w0[3 * i + 1], w0[3 * i + 2], b0 ? b0[i] : 0.f);
+    wl[i] = w_last[i];
+  }
+  for (int i = tid; i < L * H; i += nth) bias[i] = b_hidden ? b_hidden[i] : 0.f;
+  // images: one thread per 16-byte chunk (8 consecutive k of one row n)
+  const size_t img0 = off_images(L);
+  const int chunks_per_img = NKB * (KB / 8) * H;  // 8 * 4 * 256
+  const long long total = (long long)L * 2 * chunks_per_img;
+  for (long long c = tid; c < total; c += nth) {
+    int n = (int)(c % H);
+    int k8 = (int)((c / H) % (KB / 8));
+    int kb = (int)((c / (H * (KB / 8))) % NKB);
+    int o = (int)((c / chunks_per_img) % 2);
+    int l = (int)(c / (2 * chunks_per_img));
+    const float* W = w_hidden + (size_t)l * H * H;
+    float sc = pow2_scale_for(__uint_as_float(maxbits[l]));
+    int k0 = kb * KB + k8 * 8;
+    uint32_t hi[4], lo[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      float v0 = (o == 0 ? W[(size_t)n * H + k0 + 2 * i] : W[(size_t)(k0 + 2 * i) * H + n]) * sc;
+      float v1 = (o == 0 ? W[(size_t)n * H + k0 + 2 * i + 1] : W[(size_t)(k0 + 2 * i + 1) * H + n]) * sc;
+      __half2 h = __floats2half2_rn(v0, v1);
+      float2 f = __half22float2(h);
+      __half2 lw = __floats2half2_rn(v0 - f.x, v1 - f.y);
+      hi[i] = *reinterpret_cast<uint32_t*>(&h);
+      lo[i] = *reinterpret_cast<uint32_t*>(&lw);
+    }
+    unsigned char* stage = blob + img0 + ((size_t)(l * 2 + o) * NKB + kb) * STAGE_BYTES;
+    size_t off = (size_t)k8 * B_LBO + (size_t)(n >> 3) * SBO + (size_t)(n & 7) * 16;
+    *reinterpret_cast<uint4*>(stage + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+    *reinterpret_cast<uint4*>(stage + STAGE_PART + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// main kernel
+// ---------------------------------------------------------------------------------------------
+// MMA k-block visiting order: alternate the two column halves so that both halves of the
+// epilogue warps (which produce k-blocks 0..3 and 4..7 concurrently) feed the tensor core early.
+__device__ __forceinline__ int kb_order(int i) { return (i >> 1) + ((i & 1) << 2); }
+
+__global__ void __launch_bounds__(THREADS, 1)
+siren_sdf_grad_kernel(const float* __restrict__ x, int n_max, const int* __restrict__ n_dev,
+                      const unsigned char* __restrict__ blob, int L, float* __restrict__ sdf_out,
+                      float* __restrict__ grad_out, float* __restrict__ scratch, float* __restrict__ dbg,
+                      int dbg_gemm) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t sbase = smem_u32(smem);
+  const uint32_t bar_a_ready = sbase + SM_BAR;             // [8]
+  const uint32_t bar_acc_full = sbase + SM_BAR + 8 * 8;    // [2]
+  const uint32_t bar_w_full = sbase + SM_BAR + 10 * 8;     // [3]
+  const uint32_t bar_w_empty = sbase + SM_BAR + 13 * 8;    // [3]
+  volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(smem + SM_TMEM_PTR);
+
+  int n = n_max;
+  if (n_dev) {
+    int nd = *n_dev;
+    n = nd < n_max ? nd : n_max;
+  }
+  const int num_tiles = (n + TM - 1) / TM;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < NKB; ++i) mbar_init(bar_a_ready + 8 * i, 128);
+    for (int i = 0; i < 2; ++i) mbar_init(bar_acc_full + 8 * i, 1);
+    for (int i = 0; i < STAGES; ++i) {
+      mbar_init(bar_w_full + 8 * i, 1);
+      mbar_init(bar_w_empty + 8 * i, 1);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == N_EPI_WARPS + 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(sbase + SM_TMEM_PTR),
+                 "r"(512)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  const float* hdr = reinterpret_cast<const float*>(blob);
+  const size_t img0 = off_images(L);
+  const int n_gemm = 2 * L;  // per tile
+
+  if (warp == N_EPI_WARPS) {
+    // ===================== weight producer =====================
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        for (int g = 0; g < n_gemm; ++g) {
+          // forward GEMM g -> layer g+1, orientation 0 ; backward -> layer 2L-g, orientation 1
+          int l = g < L ? g : (2 * L - 1 - g);  // 0-based hidden layer index
+          int o = g < L ? 0 : 1;
+          const unsigned char* img = blob + img0 + (size_t)(l * 2 + o) * image_bytes();
+          for (int i = 0; i < NKB; ++i, ++it) {
+            int kb = kb_order(i);
+            uint32_t s = it % STAGES;
+            uint32_t ph = (it / STAGES) & 1;
+            mbar_wait(bar_w_empty + 8 * s, ph ^ 1);
+            mbar_expect_tx(bar_w_full + 8 * s, STAGE_BYTES);
+            tma_bulk_g2s(sbase + SM_STAGE + s * STAGE_BYTES, img + (size_t)kb * STAGE_BYTES, STAGE_BYTES,
+                         bar_w_full + 8 * s);
+          }
+        }
+      }
+    }
+  } else if (warp == N_EPI_WARPS + 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      uint32_t it = 0;
+      uint32_t G = 0;  // global GEMM counter of this CTA
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        for (int g = 0; g < n_gemm; ++g, ++G) {
+          const uint32_t d_tmem = tmem_base + (G & 1) * H;
+          for (int i = 0; i < NKB; ++i, ++it) {
+            int kb = kb_order(i);
+            uint32_t s = it % STAGES;
+            uint32_t ph = (it / STAGES) & 1;
+            mbar_wait(bar_a_ready + 8 * kb, G & 1);
+            mbar_wait(bar_w_full + 8 * s, ph);
+            tc_fence_after();
+            const uint32_t a_hi = sbase + SM_A_HI + kb * (KB / 8) * A_LBO;
+            const uint32_t a_lo = sbase + SM_A_LO + kb * (KB / 8) * A_LBO;
+            const uint32_t b_hi = sbase + SM_STAGE + s * STAGE_BYTES;
+            const uint32_t b_lo = b_hi + STAGE_PART;
+#pragma unroll
+            for (int k16 = 0; k16 < KB / 16; ++k16) {
+              uint64_t dah = make_desc(a_hi + k16 * 2 * A_LBO, A_LBO);
+              uint64_t dal = make_desc(a_lo + k16 * 2 * A_LBO, A_LBO);
+              uint64_t dbh = make_desc(b_hi + k16 * 2 * B_LBO, B_LBO);
+              uint64_t dbl = make_desc(b_lo + k16 * 2 * B_LBO, B_LBO);
+              tc_mma_f16(d_tmem, dal, dbh, IDESC, (i | k16) ? 1u : 0u);
+              tc_mma_f16(d_tmem, dah, dbl, IDESC, 1u);
+              tc_mma_f16(d_tmem, dah, dbh, IDESC, 1u);
+            }
+            tc_commit(bar_w_empty + 8 * s);  // stage reusable once these MMAs have read it
+          }
+          tc_commit(bar_acc_full + 8 * (G & 1));  // accumulator of GEMM G complete
+        }
+      }
+    }
+  } else {
+    // ===================== epilogue warps =====================
+    const int q = warp & 3;      // TMEM lane quarter
+    const int hsel = warp >> 2;  // column half
+    const int row = 32 * q + lane;
+    const uint32_t tl = tmem_base + ((uint32_t)(32 * q) << 16);
+    const uint32_t a_row = (uint32_t)(row >> 3) * SBO + (uint32_t)(row & 7) * 16;
+    float* xch = reinterpret_cast<float*>(smem + SM_XCH);
+    const float4* w0b = reinterpret_cast<const float4*>(blob + OFF_W0B);
+    const float* w_last = reinterpret_cast<const float*>(blob + OFF_WLAST);
+    const float* bias = reinterpret_cast<const float*>(blob + OFF_BIAS);
+    const float omega0 = hdr[HDR_OMEGA0], omega = hdr[HDR_OMEGA];
+    const float gl_scale = hdr[HDR_GL_SCALE], gl_scale_inv = hdr[HDR_GL_SCALE_INV];
+    const float b_last = hdr[HDR_B_LAST];
+    // per-CTA stash: [(l-1)][col4 (64)][row (128)] float4, l = 1..L-1
+    float4* stash = reinterpret_cast<float4*>(scratch) + (size_t)blockIdx.x * (size_t)(L > 1 ? L - 1 : 1) * 64 * TM;
+    uint32_t G = 0;
+
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int grow = tile * TM + row;
+      float px = 0.f, py = 0.f, pz = 0.f;
+      if (grow < n) {
+        px = x[3 * (size_t)grow];
+        py = x[3 * (size_t)grow + 1];
+        pz = x[3 * (size_t)grow + 2];
+      }
+      // ---- E0: first layer in SIMT, A = 2^12 sin(w0 z_0) ----
+#pragma unroll 1
+      for (int j = 0; j < 4; ++j) {
+        const int kb = 4 * hsel + j;
+#pragma unroll
+        for (int c8 = 0; c8 < 4; ++c8) {
+          float o[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            float4 w = __ldg(w0b + kb * KB + c8 * 8 + i);
+            float z = fmaf(w.z, pz, fmaf(w.y, py, fmaf(w.x, px, w.w)));
+            float s, c;
+            sincos_f32(omega0 * z, s, c);
+            o[i] = s * A_SCALE;
+          }
+          const uint32_t off = (uint32_t)(kb * 4 + c8) * A_LBO + a_row;
+          store_chunk(sbase + SM_A_HI + off, sbase + SM_A_LO + off, o);
+        }
+        fence_proxy_async();
+        mbar_arrive(bar_a_ready + 8 * kb);
+      }
+
+      float row_scale_inv = 1.f;  // inverse of the scale applied to this row of the current backward A
+      for (int g = 0; g < n_gemm; ++g, ++G) {
+        const uint32_t buf = G & 1;
+        mbar_wait(bar_acc_full + 8 * buf, (G >> 1) & 1);
+        tc_fence_after();
+        const uint32_t tacc = tl + buf * H;
+        const bool fwd = g < L;
+        const int l = fwd ? g + 1 : 2 * L - g;  // 1-based hidden layer this GEMM belongs to
+        const float wsi = hdr[l - 1];
+
+        if (dbg && blockIdx.x == 0 && (int)G == dbg_gemm) {
+          // raw accumulator dump (unscaled), [128][256]
+#pragma unroll 1
+          for (int j = 0; j < 4; ++j) {
+            float v[32];
+            const int col0 = (4 * hsel + j) * KB;
+            tmem_ld32(tacc + col0, v);
+#pragma unroll
+            for (int i = 0; i < 32; ++i) dbg[(size_t)row * H + col0 + i] = v[i];
+          }
+        }
+
+        if (fwd && l < L) {
+          // ---- E_f(l): h_l = sin(w z_l) -> A ; stash c_l = w cos(w z_l) ----
+          const float sc = wsi * A_SCALE_INV;
+          float4* st = stash + (size_t)(l - 1) * 64 * TM + row;
+#pragma unroll 1
+          for (int j = 0; j < 4; ++j) {
+            const int kb = 4 * hsel + j;
+            float v[32];
+            tmem_ld32(tacc + kb * KB, v);
+#pragma unroll
+            for (int c8 = 0; c8 < 4; ++c8) {
+              float o[8], cc[8];
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                const int col = kb * KB + c8 * 8 + i;
+                float z = fmaf(v[c8 * 8 + i], sc, __ldg(bias + (l - 1) * H + col));
+                float s, c;
+                sincos_f32(omega * z, s, c);
+                o[i] = s * A_SCALE;
+                cc[i] = omega * c;
+              }
+              const int col4 = (kb * KB + c8 * 8) >> 2;
+              __stcg(st + (size_t)col4 * TM, make_float4(cc[0], cc[1], cc[2], cc[3]));
+              __stcg(st + (size_t)(col4 + 1) * TM, make_float4(cc[4], cc[5], cc[6], cc[7]));
+              const uint32_t off = (uint32_t)(kb * 4 + c8) * A_LBO + a_row;
+              store_chunk(sbase + SM_A_HI + off, sbase + SM_A_LO + off, o);
+            }
+            tc_fence_before();
+            fence_proxy_async();
+            mbar_arrive(bar_a_ready + 8 * kb);
+          }
+        } else if (fwd) {
+          // ---- E_f(L): sdf = h_L . w_last + b_last ; A = gl_scale * w_last * c_L ----
+          const float sc = wsi * A_SCALE_INV;
+          float acc_sdf = 0.f;
+#pragma unroll 1
+          for (int j = 0; j < 4; ++j) {
+            const int kb = 4 * hsel + j;
+            float v[32];
+            tmem_ld32(tacc + kb * KB, v);
+#pragma unroll
+            for (int c8 = 0; c8 < 4; ++c8) {
+              float o[8];
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                const int col = kb * KB + c8 * 8 + i;
+                float z = fmaf(v[c8 * 8 + i], sc, __ldg(bias + (l - 1) * H + col));
+                float s, c;
+                sincos_f32(omega * z, s, c);
+                float wl = __ldg(w_last + col);
+                acc_sdf = fmaf(s, wl, acc_sdf);
+                o[i] = (omega * c) * wl * gl_scale;
+              }
+              const uint32_t off = (uint32_t)(kb * 4 + c8) * A_LBO + a_row;
+              store_chunk(sbase + SM_A_HI + off, sbase + SM_A_LO + off, o);
+            }
+            tc_fence_before();
+            fence_proxy_async();
+            mbar_arrive(bar_a_ready + 8 * kb);
+          }
+          row_scale_inv = gl_scale_inv;
+          if (hsel == 1) xch[row * 4 + 2] = acc_sdf;
+          pair_barrier(q);
+          if (hsel == 0 && grow < n) sdf_out[grow] = acc_sdf + xch[row * 4 + 2] + b_last;
+          pair_barrier(q);
+        } else if (l > 1) {
+          // ---- E_b(l): g_{l-1} = acc / scales ; gp_{l-1} = g_{l-1} * c_{l-1} -> A (row-scaled) ----
+          const float sc = wsi * row_scale_inv;
+          // pass 1: row maximum of |g_{l-1}| over all 256 columns
+          float m = 0.f;
+#pragma unroll 1
+          for (int j = 0; j < 4; ++j) {
+            float v[32];
+            tmem_ld32(tacc + (4 * hsel + j) * KB, v);
+#pragma unroll
+            for (int i = 0; i < 32; ++i) m = fmaxf(m, fabsf(v[i]));
+          }
+          xch[row * 4 + hsel] = m;
+          pair_barrier(q);
+          m = fmaxf(m, xch[row * 4 + (hsel ^ 1)]);
+          pair_barrier(q);
+          const float new_scale = pow2_scale_for(m * sc * fabsf(omega));
+          const float scs = sc * new_scale;
+          const float4* st = stash + (size_t)(l - 2) * 64 * TM + row;
+#pragma unroll 1
+          for (int j = 0; j < 4; ++j) {
+            const int kb = 4 * hsel + j;
+            float v[32];
+            tmem_ld32(tacc + kb * KB, v);
+#pragma unroll
+            for (int c8 = 0; c8 < 4; ++c8) {
+              const int col4 = (kb * KB + c8 * 8) >> 2;
+              float4 c0 = __ldcg(st + (size_t)col4 * TM);
+              float4 c1 = __ldcg(st + (size_t)(col4 + 1) * TM);
+              float o[8];
+              o[0] = v[c8 * 8 + 0] * scs * c0.x;
+              o[1] = v[c8 * 8 + 1] * scs * c0.y;
+              o[2] = v[c8 * 8 + 2] * scs * c0.z;
+              o[3] = v[c8 * 8 + 3] * scs * c0.w;
+              o[4] = v[c8 * 8 + 4] * scs * c1.x;
+              o[5] = v[c8 * 8 + 5] * scs * c1.y;
+              o[6] = v[c8 * 8 + 6] * scs * c1.z;
+              o[7] = v[c8 * 8 + 7] * scs * c1.w;
+              const uint32_t off = (uint32_t)(kb * 4 + c8) * A_LBO + a_row;
+              store_chunk(sbase + SM_A_HI + off, sbase + SM_A_LO + off, o);
+            }
+            tc_fence_before();
+            fence_proxy_async();
+            mbar_arrive(bar_a_ready + 8 * kb);
+          }
+          row_scale_inv = 1.f / new_scale;
+        } else {
+          // ---- E_b(1): g_0 = acc / scales ; gp_0 = g_0 * w0 cos(w0 z_0) ; grad = gp_0 W_0 ----
+          const float sc = wsi * row_scale_inv;
+          float gx = 0.f, gy = 0.f, gz = 0.f;
+#pragma unroll 1
+          for (int j = 0; j < 4; ++j) {
+            const int kb = 4 * hsel + j;
+            float v[32];
+            tmem_ld32(tacc + kb * KB, v);
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              float4 w = __ldg(w0b + kb * KB + i);
+              float z = fmaf(w.z, pz, fmaf(w.y, py, fmaf(w.x, px, w.w)));
+              float s, c;
+              sincos_f32(omega0 * z, s, c);
+              float gp = v[i] * sc * (omega0 * c);
+              gx = fmaf(gp, w.x, gx);
+              gy = fmaf(gp, w.y, gy);
+              gz = fmaf(gp, w.z, gz);
+            }
+          }
+          tc_fence_before();
+          if (hsel == 1) {
+            xch[row * 4 + 0] = gx;
+            xch[row * 4 + 1] = gy;
+            xch[row * 4 + 2] = gz;
+          }
+          pair_barrier(q);
+          if (hsel == 0 && grow < n) {
+            grad_out[3 * (size_t)grow] = gx + xch[row * 4 + 0];
+            grad_out[3 * (size_t)grow + 1] = gy + xch[row * 4 + 1];
+            grad_out[3 * (size_t)grow + 2] = gz + xch[row * 4 + 2];
+          }
+          pair_barrier(q);
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == N_EPI_WARPS + 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+  }
+}
+
+}  // namespace siren
+}  // namespace isob200
+
+using namespace isob200;
+using namespace isob200::siren;
+
+extern "C" {
+
+size_t isob200_siren_blob_bytes(int n_hidden) {
+  if (n_hidden < 1 || n_hidden > MAX_LAYERS) return 0;
+  return blob_bytes(n_hidden);
+}
+size_t isob200_siren_pack_ws_bytes(void) { return PACK_WS_BYTES; }
+size_t isob200_siren_scratch_bytes(int n_hidden) {
+  int l = n_hidden > 1 ? n_hidden - 1 : 1;
+  return (size_t)kNumSMs * l * 64 * TM * sizeof(float4);
+}
+
+int isob200_siren_pack(const float* w0, const float* b0, const float* w_hidden, const float* b_hidden,
+                       const float* w_last, const float* b_last, float omega0, float omega, int hidden,
+                       int n_hidden, void* blob, size_t blob_bytes_, void* ws, size_t ws_bytes, void* stream) {
+  ISO_CHECK_ARG(hidden == H, "siren_pack: only hidden width %d is built (got %d)", H, hidden);
+  ISO_CHECK_ARG(n_hidden >= 1 && n_hidden <= MAX_LAYERS, "siren_pack: n_hidden must be in [1, %d]", MAX_LAYERS);
+  ISO_CHECK_ARG(w0 && w_hidden && w_last && blob && ws, "siren_pack: null pointer");
+  ISO_CHECK_ARG(blob_bytes_ >= blob_bytes(n_hidden), "siren_pack: blob too small");
+  if (ws_bytes < PACK_WS_BYTES) {
+    set_error("siren_pack: workspace too small");
+    return ISOB200_ERR_WORKSPACE;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  ISO_CUDA(cudaMemsetAsync(ws, 0, PACK_WS_BYTES, st));
+  siren_absmax_kernel<<<dim3(32, n_hidden + 1), 256, 0, st>>>(w_hidden, w_last, n_hidden, (unsigned*)ws);
+  ISO_CHECK_LAUNCH("siren_absmax_kernel");
+  siren_pack_kernel<<<kNumSMs * 2, 256, 0, st>>>(w0, b0, w_hidden, b_hidden, w_last, b_last, omega0, omega, n_hidden,
+                                                (const unsigned*)ws, (unsigned char*)blob);
+  ISO_CHECK_LAUNCH("siren_pack_kernel");
+  return ISOB200_OK;
+}
+
+int isob200_siren_sdf_grad(const float* x, int n_max, const int* n_dev, const void* blob, int n_hidden, float* sdf,
+                           float* grad, void* scratch, size_t scratch_bytes, float* dbg, int dbg_gemm,
+                           void* stream) {
+  ISO_CHECK_ARG(n_hidden >= 1 && n_hidden <= MAX_LAYERS, "siren_sdf_grad: n_hidden must be in [1, %d]", MAX_LAYERS);
+  ISO_CHECK_ARG(n_max >= 0, "siren_sdf_grad: negative point count");
+  if (n_max == 0) return ISOB200_OK;
+  ISO_CHECK_ARG(x && blob && sdf && grad && scratch, "siren_sdf_grad: null pointer");
+  if (scratch_bytes < isob200_siren_scratch_bytes(n_hidden)) {
+    set_error("siren_sdf_grad: scratch too small");
+    return ISOB200_ERR_WORKSPACE;
+  }
+  static bool attr_set = false;
+  if (!attr_set) {
+    ISO_CUDA(cudaFuncSetAttribute(siren_sdf_grad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    attr_set = true;
+  }
+  int tiles = (n_max + TM - 1) / TM;
+  int grid = tiles < kNumSMs ? tiles : kNumSMs;
+  siren_sdf_grad_kernel<<<grid, THREADS, SMEM_BYTES, (cudaStream_t)stream>>>(
+      x, n_max, n_dev, (const unsigned char*)blob, n_hidden, sdf, grad, (float*)scratch, dbg, dbg_gemm);
+  ISO_CHECK_LAUNCH("siren_sdf_grad_kernel");
+  return ISOB200_OK;
+}
+
+}  // extern "C"

@@ -26,6 +26,7 @@ import torch.nn.functional as F
 
 from . import _ext
 from . import frnn
+from . import siren
 from .structures import (convert_pointclouds_to_tensor, is_pointclouds, packed_to_padded,
                          padded_to_packed_idx, reduce_mask_padded,
                          num_points_2_cloud_to_packed_first_idx)
@@ -104,6 +105,11 @@ class UniformProjection(LevelSetProjection):
         """Chunked SDF value + input gradient through autograd (levelset_sampling.py:142-170)."""
         shp = points.shape
         points_packed = points.reshape(-1, 3)
+        if points_packed.is_cuda:
+            # the reference's own Siren decoder (common.py:90-165): one fused tcgen05 kernel
+            fused = None if latent is not None else siren.sdf_and_grad(model, points_packed, forward_kwargs)
+            if fused is not None:
+                return fused[0].view(shp[:-1]), fused[1].view(shp)
         grad_packed = []
         eval_packed = []
         with autograd.no_grad():

@@ -1,0 +1,161 @@
+"""Fused SDF value + input gradient for SIREN decoders (csrc/siren.cu).
+
+``UniformProjection._compute_sdf_and_grad`` (DSS/models/levelset_sampling.py:142-170) evaluates
+the caller's SDF module through autograd: ``model.forward(x).sdf`` then
+``autograd.grad(sdf, x, ones)``.  When that module is the reference's ``Siren`` MLP
+(DSS/models/common.py:90-165: ``net = Sequential(SineLayer, ..., SineLayer, Linear)``, every
+``SineLayer`` being ``sin(omega_0 * linear(x))``, :56-87) with hidden width 256 and no latent
+code, the same two quantities come from one tcgen05 kernel instead.  Any other module keeps the
+autograd path; nothing here changes what a caller has to pass.
+
+Recognition is structural (duck-typed, like the rest of the package): the class is called
+``Siren`` (or sets ``isob200_fused_siren = True``), has a ``net`` Sequential of modules with
+``.linear`` + ``.omega_0`` followed by one ``nn.Linear`` whose first output is the sdf.
+Set ``ISOB200_FUSED_SIREN=0`` to force the autograd path (parity tests compare the two).
+"""
+import os
+import weakref
+
+import torch
+import torch.nn as nn
+
+from . import _ext
+
+HIDDEN = 256
+_CACHE = weakref.WeakKeyDictionary()
+ENABLED = os.environ.get("ISOB200_FUSED_SIREN", "1") != "0"
+# rows / flops handed to the fused kernel since import (bench.py turns them into the roofline line)
+STATS = {"calls": 0, "rows": 0, "flops": 0}
+
+
+def algorithmic_flops(n_rows, n_hidden):
+    """fp32-equivalent FLOPs of one evaluation: forward + reverse pass, 2 flops per MAC, over
+    the first layer (3 x 256), the n_hidden 256 x 256 layers and the 256 x 1 head."""
+    return 2 * 2 * n_rows * (3 * HIDDEN + n_hidden * HIDDEN * HIDDEN + HIDDEN)
+
+
+class _Spec(object):
+    __slots__ = ("first", "hidden", "last", "omega0", "omega")
+
+
+def match(model, forward_kwargs=None):
+    """Return the layer spec if ``model`` is a fusable SIREN SDF, else None."""
+    if not ENABLED or not isinstance(model, nn.Module):
+        return None
+    if type(model).__name__ != "Siren" and not getattr(model, "isob200_fused_siren", False):
+        return None
+    if forward_kwargs:
+        c = forward_kwargs.get("c", None)
+        others = [k for k in forward_kwargs if k != "c"]
+        if others or (c is not None and c.numel() > 0):
+            return None
+    if getattr(model, "use_activation", False):
+        return None
+    fields = getattr(model, "_out_fields", None)
+    if fields is not None and (len(fields) == 0 or fields[0] != "sdf"):
+        return None
+    net = getattr(model, "net", None)
+    if not isinstance(net, nn.Sequential) or len(net) < 3:
+        return None
+    mods = list(net)
+    sines, last = mods[:-1], mods[-1]
+    if not isinstance(last, nn.Linear):
+        return None
+    for m in sines:
+        if not isinstance(getattr(m, "linear", None), nn.Linear) or not hasattr(m, "omega_0"):
+            return None
+        if m._forward_hooks or m._forward_pre_hooks:
+            return None
+    if model._forward_hooks or model._forward_pre_hooks:
+        return None
+    first, hidden = sines[0].linear, [m.linear for m in sines[1:]]
+    if first.in_features != 3 or first.out_features != HIDDEN or last.in_features != HIDDEN:
+        return None
+    if any(h.in_features != HIDDEN or h.out_features != HIDDEN for h in hidden):
+        return None
+    if not (1 <= len(hidden) <= 32):
+        return None
+    omegas = {float(m.omega_0) for m in sines[1:]}
+    if len(omegas) != 1:
+        return None
+    params = [first.weight, last.weight] + [h.weight for h in hidden]
+    if any((not p.is_cuda) or p.dtype != torch.float32 for p in params):
+        return None
+    s = _Spec()
+    s.first, s.hidden, s.last = first, hidden, last
+    s.omega0, s.omega = float(sines[0].omega_0), omegas.pop()
+    return s
+
+
+def _version_key(spec):
+    ps = [spec.first.weight, spec.first.bias, spec.last.weight, spec.last.bias]
+    for h in spec.hidden:
+        ps += [h.weight, h.bias]
+    return tuple((p.data_ptr(), p._version) if p is not None else None for p in ps) + (spec.omega0, spec.omega)
+
+
+def _pack(spec):
+    lib = _ext.lib()
+    dev = spec.first.weight.device
+    L = len(spec.hidden)
+    with torch.no_grad():
+        w0 = spec.first.weight.detach().contiguous()
+        b0 = spec.first.bias.detach().contiguous() if spec.first.bias is not None else None
+        wh = torch.stack([h.weight.detach() for h in spec.hidden]).contiguous()
+        if all(h.bias is not None for h in spec.hidden):
+            bh = torch.stack([h.bias.detach() for h in spec.hidden]).contiguous()
+        else:
+            bh = torch.stack([h.bias.detach() if h.bias is not None else torch.zeros(HIDDEN, device=dev)
+                              for h in spec.hidden]).contiguous()
+        wl = spec.last.weight.detach()[0].contiguous()
+        bl = spec.last.bias.detach()[:1].contiguous() if spec.last.bias is not None else None
+    nbytes = lib.isob200_siren_blob_bytes(L)
+    blob = torch.empty((nbytes,), dtype=torch.uint8, device=dev)
+    ws = _ext.workspace(lib.isob200_siren_pack_ws_bytes(), dev)
+    _ext.check(lib.isob200_siren_pack(_ext.ptr(w0), _ext.ptr(b0), _ext.ptr(wh), _ext.ptr(bh), _ext.ptr(wl),
+                                      _ext.ptr(bl), spec.omega0, spec.omega, HIDDEN, L, _ext.ptr(blob), nbytes,
+                                      _ext.ptr(ws), ws.numel(), _ext.stream(dev)))
+    scratch = _ext.workspace(lib.isob200_siren_scratch_bytes(L), dev)
+    return blob, scratch, L
+
+
+def packed(model, spec):
+    """(blob, scratch, L) for the current parameter values; re-packed when any parameter changed."""
+    key = _version_key(spec)
+    ent = _CACHE.get(model)
+    if ent is None or ent[0] != key:
+        ent = (key, _pack(spec))
+        _CACHE[model] = ent
+    return ent[1]
+
+
+def sdf_and_grad(model, points, forward_kwargs=None, n_dev=None, dbg_gemm=None):
+    """sdf (n,) and d sdf/d x (n,3) of a fusable SIREN at ``points`` (n,3) fp32 cuda, or None when
+    ``model`` is not fusable.  ``n_dev``: optional int32 device scalar with the live row count."""
+    spec = match(model, forward_kwargs)
+    if spec is None:
+        return None
+    _ext.require_cuda(points)
+    lib = _ext.lib()
+    x = points.reshape(-1, 3)
+    if x.dtype != torch.float32:
+        return None
+    x = x.contiguous()
+    n = x.shape[0]
+    dev = x.device
+    blob, scratch, L = packed(model, spec)
+    sdf = torch.empty((n,), dtype=torch.float32, device=dev)
+    grad = torch.empty((n, 3), dtype=torch.float32, device=dev)
+    dbg = None
+    if dbg_gemm is not None:
+        dbg = torch.zeros((128, HIDDEN), dtype=torch.float32, device=dev)
+    if n > 0:
+        STATS["calls"] += 1
+        STATS["rows"] += n
+        STATS["flops"] += algorithmic_flops(n, L)
+        _ext.check(lib.isob200_siren_sdf_grad(_ext.ptr(x), n, _ext.ptr(n_dev), _ext.ptr(blob), L, _ext.ptr(sdf),
+                                              _ext.ptr(grad), _ext.ptr(scratch), scratch.numel(), _ext.ptr(dbg),
+                                              -1 if dbg_gemm is None else int(dbg_gemm), _ext.stream(dev)))
+    if dbg_gemm is not None:
+        return sdf, grad, dbg
+    return sdf, grad

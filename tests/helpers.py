@@ -106,3 +106,46 @@ class SirenSDF(nn.Module):
         for l in self.lin[:-1]:
             h = torch.sin(self.omega * l(h))
         return types.SimpleNamespace(sdf=self.lin[-1](h))
+
+
+class SineLayer(nn.Module):
+    """sin(omega_0 * linear(x)) with the SIREN init (DSS/models/common.py:56-87)."""
+
+    def __init__(self, dim, out_dim, is_first=False, omega_0=30.0, gen=None):
+        super().__init__()
+        self.omega_0 = omega_0
+        self.linear = nn.Linear(dim, out_dim)
+        bound = (1.0 / dim) if is_first else (np.sqrt(6.0 / dim) / omega_0)
+        with torch.no_grad():
+            self.linear.weight.copy_((torch.rand(self.linear.weight.shape, generator=gen) * 2 - 1) * bound)
+            self.linear.bias.copy_((torch.rand(self.linear.bias.shape, generator=gen) * 2 - 1) / np.sqrt(dim))
+
+    def forward(self, x):
+        return torch.sin(self.omega_0 * self.linear(x))
+
+
+class Siren(nn.Module):
+    """Structural twin of the reference decoder DSS/models/common.py:90-165 for
+    ``Siren(dim=3, c_dim=0, hidden_size, n_layers, out_dims={'sdf': 1}, outermost_linear=True)``:
+    ``net = Sequential(SineLayer(first), n_layers x SineLayer, Linear)`` and a forward returning an
+    object with ``.sdf`` -- what isopoints_b200.siren recognises and fuses.  Same weights as
+    ``SirenSDF(hidden, n_layers, omega, seed)`` layer for layer (same generator order)."""
+
+    def __init__(self, hidden_size=256, n_layers=7, omega=30.0, seed=0):
+        super().__init__()
+        g = torch.Generator().manual_seed(seed)
+        self.dim, self.c_dim = 3, 0
+        self._out_fields, self._out_dims = ("sdf",), (1,)
+        self.use_activation = False
+        net = [SineLayer(3, hidden_size, True, omega, g)]
+        net += [SineLayer(hidden_size, hidden_size, False, omega, g) for _ in range(n_layers)]
+        head = nn.Linear(hidden_size, 1)
+        with torch.no_grad():
+            bound = np.sqrt(6.0 / hidden_size) / omega
+            head.weight.copy_((torch.rand(head.weight.shape, generator=g) * 2 - 1) * bound)
+            head.bias.copy_((torch.rand(head.bias.shape, generator=g) * 2 - 1) / np.sqrt(hidden_size))
+        net.append(head)
+        self.net = nn.Sequential(*net)
+
+    def forward(self, coords, c=None, **kwargs):
+        return types.SimpleNamespace(sdf=self.net(coords))
