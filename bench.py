@@ -183,6 +183,7 @@ def run_ours(args):
     from isopoints_b200 import siren as _siren
     for k_ in _siren.STATS:
         _siren.STATS[k_] = 0
+    _siren.RECORD = []
     l0 = lib.isob200_launch_count()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     with ClockSampler(local) as clocks:
@@ -198,7 +199,10 @@ def run_ours(args):
     launches = lib.isob200_launch_count() - l0
     prof = _ext.PROFILE
     _ext.PROFILE = None
+    _siren.resolve_record()
+    _siren.RECORD = None
     siren_stats = dict(_siren.STATS)
+    siren_stats["flops"] = _siren.algorithmic_flops(siren_stats["rows"], 7)
     ms = sum(a.elapsed_time(b) for a, b in ev) / args.steps
     ms = _max_over_ranks(ms, world, dev)
     converged = float(out["mask"].float().mean())

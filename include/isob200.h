@@ -74,8 +74,8 @@ int isob200_frnn_backward(const float* points1, const float* points2, const int6
  *      (DSS/models/levelset_sampling.py:290-351); one call per Newton iteration ---------- */
 size_t isob200_project_step_ws_bytes(int A);
 int isob200_project_step(float* points, float* normals, unsigned char* not_converged,
-                         const int* act_in, int A, const float* sdf, const float* grad, float tol,
-                         float max_step, int do_update, int* act_out, float* next_points,
+                         const int* act_in, int A, const int* a_dev, const float* sdf, const float* grad,
+                         float tol, float max_step, int do_update, int* act_out, float* next_points,
                          int* count_out, void* ws, size_t ws_bytes, void* stream);
 int isob200_gather_rows3(const float* src, const int* idx, int A, float* dst, void* stream);
 int isob200_project_sphere(float* points, float* normals, unsigned char* valid, long long M,

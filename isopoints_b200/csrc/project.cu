@@ -49,7 +49,8 @@ __device__ __forceinline__ float eps_denom_f(float x, float eps) {
 __global__ void __launch_bounds__(PJ_THREADS)
 project_step_kernel(float* __restrict__ points, float* __restrict__ normals,
                     unsigned char* __restrict__ not_converged, const int* __restrict__ act_in,
-                    int A, const float* __restrict__ sdf, const float* __restrict__ grad,
+                    int A, const int* __restrict__ a_dev, const float* __restrict__ sdf,
+                    const float* __restrict__ grad,
                     float tol, float max_step, int do_update, int* __restrict__ act_out,
                     float* __restrict__ next_points, int* __restrict__ count_out,
                     unsigned* __restrict__ ws) {
@@ -59,6 +60,14 @@ project_step_kernel(float* __restrict__ points, float* __restrict__ normals,
   if (threadIdx.x == 0) s_tile = (int)atomicAdd(&ws[0], 1u);  // ticket => forward progress
   __syncthreads();
   const int tile = s_tile;
+  if (a_dev) {  // live row count kept on the device (sync-free loop): A is only the upper bound
+    const int a = *a_dev;
+    A = a < A ? a : A;
+    if ((long long)tile * PJ_TILE >= A) {  // later tickets are all past the end too: nobody looks back here
+      if (tile == 0 && threadIdx.x == 0) *count_out = 0;
+      return;
+    }
+  }
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   // blocked assignment: thread t owns items [base + t*ITEMS, +ITEMS) => order-preserving ranks
   const int base = tile * PJ_TILE + threadIdx.x * PJ_ITEMS;
@@ -226,6 +235,8 @@ size_t isob200_project_step_ws_bytes(int A) {
 //   points, normals : (M,3) packed, updated in place at rows act_in[0..A)
 //   not_converged   : (M,) uint8/bool mask, updated at the same rows (may be NULL)
 //   act_in          : (A,) int32 row ids, ascending; NULL = identity (first iteration)
+//   a_dev           : NULL, or a device int holding the live row count (<= A, which then is only the
+//                     upper bound used to size the launch); must not alias count_out
 //   sdf (A,), grad (A,3) : SDF value and gradient at points[act_in]
 //   do_update       : 0 for the final evaluation (it == proj_max_iters, :329): flags and normals
 //                     are refreshed but points do not move
@@ -233,12 +244,13 @@ size_t isob200_project_step_ws_bytes(int A) {
 //   next_points (>=A x 3 floats, may be NULL): updated positions of the still-active rows, compacted in
 //                     the same order -- points[act_out] without a gather pass (:315 of the next iteration)
 int isob200_project_step(float* points, float* normals, unsigned char* not_converged,
-                         const int* act_in, int A, const float* sdf, const float* grad, float tol,
-                         float max_step, int do_update, int* act_out, float* next_points,
+                         const int* act_in, int A, const int* a_dev, const float* sdf, const float* grad,
+                         float tol, float max_step, int do_update, int* act_out, float* next_points,
                          int* count_out, void* ws, size_t ws_bytes, void* stream_) {
   cudaStream_t st = (cudaStream_t)stream_;
   ISO_CHECK_ARG(A >= 0, "project_step: negative A");
   ISO_CHECK_ARG(count_out, "project_step: null count_out");
+  ISO_CHECK_ARG(a_dev != count_out, "project_step: a_dev must not alias count_out");
   if (A == 0) {
     ISO_CUDA(cudaMemsetAsync(count_out, 0, sizeof(int), st));
     return ISOB200_OK;
@@ -252,7 +264,7 @@ int isob200_project_step(float* points, float* normals, unsigned char* not_conve
   }
   ISO_CUDA(cudaMemsetAsync(ws, 0, need, st));
   const int tiles = div_up(A, PJ_TILE);
-  project_step_kernel<<<tiles, PJ_THREADS, 0, st>>>(points, normals, not_converged, act_in, A, sdf, grad,
+  project_step_kernel<<<tiles, PJ_THREADS, 0, st>>>(points, normals, not_converged, act_in, A, a_dev, sdf, grad,
                                                    tol, max_step, do_update, act_out, next_points,
                                                    count_out, (unsigned*)ws);
   ISO_CHECK_LAUNCH("project_step_kernel");

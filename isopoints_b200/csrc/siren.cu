@@ -35,8 +35,11 @@
 //   * w cos(w z_l) for the backward pass goes to a per-CTA scratch slab in global memory
 //     (float4 per thread, 512 B contiguous per warp); it is written and read back by the same
 //     thread within ~100 us, i.e. mostly L2 traffic.
-//   Warp roles: warps 0-7 epilogue (TMEM lane quarter = warp % 4, column half = warp / 4),
-//   warp 8 weight producer, warp 9 TMEM allocator + single-thread MMA issuer.
+//   Warp roles: warps 0-15 epilogue (TMEM lane quarter = warp % 4; within every 32-column k-block
+//   the warp owns the 8-column slice warp / 4, i.e. exactly one 16-byte K-chunk of its row, so the
+//   k-blocks of the next GEMM's A operand complete one after the other and the tensor core trails
+//   the epilogue by a single k-block), warp 16 weight producer, warp 17 TMEM allocator +
+//   single-thread MMA issuer.
 //
 // Only H = 256 is built (BASELINE C2's "8-layer x 256 SIREN"); other widths keep the autograd path.
 #include "common.cuh"
@@ -57,7 +60,7 @@ constexpr int A_PART = TM * H * 2;            // 64 KB: one fp16 part of the A t
 constexpr int A_LBO = TM * 16;                // 2048: byte stride between K-chunks (8 elems) of A
 constexpr int B_LBO = H * 16;                 // 4096: same for a B stage
 constexpr int SBO = 128;                      // byte stride between 8-row groups
-constexpr int N_EPI_WARPS = 8;
+constexpr int N_EPI_WARPS = 16;
 constexpr int THREADS = (N_EPI_WARPS + 2) * 32;
 constexpr float A_SCALE = 4096.f;             // 2^12: static scale of sin() activations
 constexpr float A_SCALE_INV = 1.f / 4096.f;
@@ -67,9 +70,10 @@ constexpr int MAX_LAYERS = 32;
 // [0,1024)        header floats: [l-1] = 2^-s_l (inverse weight scale of hidden layer l), l = 1..L
 //                 [64] gl_scale, [65] 1/gl_scale (static scale of gp_L), [66] b_last,
 //                 [67] omega_0 (first layer), [68] omega (hidden)
-// [1024,5120)     float4 w0b[256] = (W0[n,0], W0[n,1], W0[n,2], b0[n])
+// [1024,5120)     float4 w0p[128][2]: column pair (a, b) = (2p, 2p+1) as (x_a, x_b, y_a, y_b), (z_a, z_b, w_a, w_b)
+//                 with (x, y, z, w)_n = omega_0 * (W0[n,0], W0[n,1], W0[n,2], b0[n])
 // [5120,6144)     float  w_last[256]
-// [6144, ..)      float  bias[L][256]
+// [6144, ..)      float  bias[L][256], pre-multiplied by omega
 // images          (1024-aligned) for l = 1..L, orientation o = 0 (forward: B[n][k] = W_l[n][k])
 //                 and o = 1 (backward: B[n][k] = W_l[k][n]): 8 stages of 32 KB
 constexpr size_t HDR_GL_SCALE = 64, HDR_GL_SCALE_INV = 65, HDR_B_LAST = 66, HDR_OMEGA0 = 67, HDR_OMEGA = 68;
@@ -159,7 +163,23 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
 #pragma unroll
   for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
-__device__ __forceinline__ void pair_barrier(int q) { asm volatile("bar.sync %0, 64;" ::"r"(q + 1) : "memory"); }
+// 32 lanes x 8 consecutive columns; issue and wait are separate so the next k-block's load can be
+// in flight during the current one's math.  The wait names the registers so that no use is
+// scheduled above it.
+__device__ __forceinline__ void tmem_ld8_issue(uint32_t taddr, uint32_t (&r)[8]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];\n"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait(uint32_t (&r)[8]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7])
+               :
+               : "memory");
+}
+// barrier among the 4 epilogue warps that own the same 32 rows (one per 8-column slice)
+__device__ __forceinline__ void row_barrier(int q) { asm volatile("bar.sync %0, 128;" ::"r"(q + 1) : "memory"); }
 
 // K-major, no-swizzle shared-memory matrix descriptor (cute::UMMA::SmemDescriptor, version 1):
 // core matrix = 8 rows x 16 B contiguous; SBO = stride between 8-row groups, LBO = stride
@@ -171,39 +191,52 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo) {
 // instruction descriptor: D = f32, A = B = f16, K-major both, N = 256, M = 128
 constexpr uint32_t IDESC = (1u << 4) | ((uint32_t)(H >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
 
-// sin and cos of an fp32 argument to ~1 ulp for |a| < 1e5: three-constant Cody-Waite reduction by
-// pi/2, Taylor kernels on [-pi/4, pi/4] (remainders 1.7e-9 / 1.1e-10), quadrant fix-up.
-__device__ __forceinline__ void sincos_f32(float a, float& s, float& c) {
-  float j = rintf(a * 0.636619772f);
-  float r = fmaf(j, -1.57079601e+00f, a);
-  r = fmaf(j, -3.13916473e-07f, r);
-  r = fmaf(j, -5.39030253e-15f, r);
-  int q = __float2int_rn(j);
-  float r2 = r * r;
-  float sp = fmaf(r2, 2.75573192e-6f, -1.98412698e-4f);
-  sp = fmaf(sp, r2, 8.33333333e-3f);
-  sp = fmaf(sp, r2, -1.66666667e-1f);
-  sp = sp * r2;
-  sp = fmaf(sp, r, r);
-  float cp = fmaf(r2, -2.75573192e-7f, 2.48015873e-5f);
-  cp = fmaf(cp, r2, -1.38888889e-3f);
-  cp = fmaf(cp, r2, 4.16666667e-2f);
-  cp = fmaf(cp, r2, -0.5f);
-  cp = fmaf(cp, r2, 1.0f);
-  s = (q & 1) ? cp : sp;
-  c = (q & 1) ? sp : cp;
-  if (q & 2) s = -s;
-  if ((q + 1) & 2) c = -c;
+// ---- packed fp32x2 math (sm_100 FFMA2 / FMUL2 / FADD2: two lanes per issued instruction) ------
+// The epilogue is instruction-issue bound (one row x 8 columns of sin/cos per thread and k-block),
+// so every elementwise step works on column PAIRS.
+__device__ __forceinline__ float2 bc2(float a) { return make_float2(a, a); }
+
+// sin and cos of two fp32 arguments, ~1 ulp absolute (1.2e-7 / 1.5e-7 measured) for |a| < 2^21 pi:
+// j = round(a / pi) with the 1.5 * 2^23 trick, three-constant Cody-Waite reduction by pi, minimax
+// polynomials on [-pi/2, pi/2] (degree 11 odd / 12 even, least-squares fit on Chebyshev nodes).
+// Returns sn = sin(a) (sign applied through the odd polynomial's argument), cp = |.|-branch cosine
+// WITHOUT its sign, and the sign bits (bit 31) so that the caller folds them into a scale factor:
+// cos(a) = cp ^ sg.
+__device__ __forceinline__ void sincos2(float2 a, float2& sn, float2& cp, uint32_t& sgx, uint32_t& sgy) {
+  const float2 jm = __ffma2_rn(a, bc2(0.318309886f), bc2(12582912.f));
+  sgx = __float_as_uint(jm.x) << 31;
+  sgy = __float_as_uint(jm.y) << 31;
+  const float2 j = __fadd2_rn(jm, bc2(-12582912.f));
+  float2 r = __ffma2_rn(j, bc2(-3.140625f), a);
+  r = __ffma2_rn(j, bc2(-9.676535846665502e-4f), r);
+  r = __ffma2_rn(j, bc2(-5.126565838509123e-12f), r);
+  const float2 r2 = __fmul2_rn(r, r);
+  float2 t = __ffma2_rn(r2, bc2(-2.39068338458992e-08f), bc2(2.7526464236871107e-06f));
+  t = __ffma2_rn(t, r2, bc2(-1.9840890308842063e-04f));
+  t = __ffma2_rn(t, r2, bc2(8.333330973982811e-03f));
+  t = __ffma2_rn(t, r2, bc2(-0.1666666716337204f));
+  t = __fmul2_rn(t, r2);
+  const float2 rs = make_float2(__uint_as_float(__float_as_uint(r.x) ^ sgx), __uint_as_float(__float_as_uint(r.y) ^ sgy));
+  sn = __ffma2_rn(t, rs, rs);
+  float2 u = __ffma2_rn(r2, bc2(1.9918149352093906e-09f), bc2(-2.7525521772986394e-07f));
+  u = __ffma2_rn(u, r2, bc2(2.4801065592328086e-05f));
+  u = __ffma2_rn(u, r2, bc2(-1.3888884568586946e-03f));
+  u = __ffma2_rn(u, r2, bc2(0.0416666679084301f));
+  u = __ffma2_rn(u, r2, bc2(-0.5f));
+  cp = __ffma2_rn(u, r2, bc2(1.0f));
+}
+__device__ __forceinline__ float2 signed_scale(float sc, uint32_t sgx, uint32_t sgy) {
+  return make_float2(__uint_as_float(__float_as_uint(sc) ^ sgx), __uint_as_float(__float_as_uint(sc) ^ sgy));
 }
 
-// split 8 scaled fp32 values into fp16 hi / lo and store the two 16-byte K-chunks
-__device__ __forceinline__ void store_chunk(uint32_t a_hi_addr, uint32_t a_lo_addr, const float* o) {
+// split 8 scaled fp32 values (4 pairs) into fp16 hi / lo and store the two 16-byte K-chunks
+__device__ __forceinline__ void store_chunk(uint32_t a_hi_addr, uint32_t a_lo_addr, const float2* o) {
   uint32_t hi[4], lo[4];
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
-    __half2 h = __floats2half2_rn(o[2 * i], o[2 * i + 1]);
-    float2 f = __half22float2(h);
-    __half2 l = __floats2half2_rn(o[2 * i] - f.x, o[2 * i + 1] - f.y);
+    __half2 h = __floats2half2_rn(o[i].x, o[i].y);
+    const float2 d = __ffma2_rn(__half22float2(h), bc2(-1.f), o[i]);
+    __half2 l = __floats2half2_rn(d.x, d.y);
     hi[i] = *reinterpret_cast<uint32_t*>(&h);
     lo[i] = *reinterpret_cast<uint32_t*>(&l);
   }
@@ -261,10 +294,16 @@ __global__ void siren_pack_kernel(const float* __restrict__ w0, const float* __r
   float* wl = reinterpret_cast<float*>(blob + OFF_WLAST);
   float* bias = reinterpret_cast<float*>(blob + OFF_BIAS);
   for (int i = tid; i < H; i += nth) {
-    w0b[i] = make_float4(w0[3 * i], w0[3 * i + 1], w0[3 * i + 2], b0 ? b0[i] : 0.f);
+    {
+      float* w0p = reinterpret_cast<float*>(w0b) + (i >> 1) * 8 + (i & 1);   // pair-transposed, see layout
+      w0p[0] = omega0 * w0[3 * i];
+      w0p[2] = omega0 * w0[3 * i + 1];
+      w0p[4] = omega0 * w0[3 * i + 2];
+      w0p[6] = b0 ? omega0 * b0[i] : 0.f;
+    }
     wl[i] = w_last[i];
   }
-  for (int i = tid; i < L * H; i += nth) bias[i] = b_hidden ? b_hidden[i] : 0.f;
+  for (int i = tid; i < L * H; i += nth) bias[i] = b_hidden ? omega * b_hidden[i] : 0.f;
   // images: one thread per 16-byte chunk (8 consecutive k of one row n)
   const size_t img0 = off_images(L);
   const int chunks_per_img = NKB * (KB / 8) * H;  // 8 * 4 * 256
@@ -299,9 +338,8 @@ __global__ void siren_pack_kernel(const float* __restrict__ w0, const float* __r
 // ---------------------------------------------------------------------------------------------
 // main kernel
 // ---------------------------------------------------------------------------------------------
-// MMA k-block visiting order: alternate the two column halves so that both halves of the
-// epilogue warps (which produce k-blocks 0..3 and 4..7 concurrently) feed the tensor core early.
-__device__ __forceinline__ int kb_order(int i) { return (i >> 1) + ((i & 1) << 2); }
+// MMA k-block visiting order = the order in which the epilogue completes them.
+__device__ __forceinline__ int kb_order(int i) { return i; }
 
 __global__ void __launch_bounds__(THREADS, 1)
 siren_sdf_grad_kernel(const float* __restrict__ x, int n_max, const int* __restrict__ n_dev,
@@ -326,7 +364,7 @@ siren_sdf_grad_kernel(const float* __restrict__ x, int n_max, const int* __restr
   const int num_tiles = (n + TM - 1) / TM;
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < NKB; ++i) mbar_init(bar_a_ready + 8 * i, 128);
+    for (int i = 0; i < NKB; ++i) mbar_init(bar_a_ready + 8 * i, N_EPI_WARPS);
     for (int i = 0; i < 2; ++i) mbar_init(bar_acc_full + 8 * i, 1);
     for (int i = 0; i < STAGES; ++i) {
       mbar_init(bar_w_full + 8 * i, 1);
@@ -376,15 +414,26 @@ siren_sdf_grad_kernel(const float* __restrict__ x, int n_max, const int* __restr
     if (lane == 0) {
       uint32_t it = 0;
       uint32_t G = 0;  // global GEMM counter of this CTA
+      // dbg_gemm == -2: cycle stamps of the first two tiles of CTA 0 (bring-up / tuning aid)
+      long long* tstamp = (dbg && dbg_gemm == -2 && blockIdx.x == 0) ? reinterpret_cast<long long*>(dbg) : nullptr;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         for (int g = 0; g < n_gemm; ++g, ++G) {
           const uint32_t d_tmem = tmem_base + (G & 1) * H;
+          long long wa = 0, ww = 0, t_first = 0;
           for (int i = 0; i < NKB; ++i, ++it) {
             int kb = kb_order(i);
             uint32_t s = it % STAGES;
             uint32_t ph = (it / STAGES) & 1;
+            long long t0 = tstamp ? clock64() : 0;
             mbar_wait(bar_a_ready + 8 * kb, G & 1);
+            long long t1 = tstamp ? clock64() : 0;
             mbar_wait(bar_w_full + 8 * s, ph);
+            if (tstamp) {
+              long long t2 = clock64();
+              wa += t1 - t0;
+              ww += t2 - t1;
+              if (i == 0) t_first = t1;
+            }
             tc_fence_after();
             const uint32_t a_hi = sbase + SM_A_HI + kb * (KB / 8) * A_LBO;
             const uint32_t a_lo = sbase + SM_A_LO + kb * (KB / 8) * A_LBO;
@@ -403,26 +452,46 @@ siren_sdf_grad_kernel(const float* __restrict__ x, int n_max, const int* __restr
             tc_commit(bar_w_empty + 8 * s);  // stage reusable once these MMAs have read it
           }
           tc_commit(bar_acc_full + 8 * (G & 1));  // accumulator of GEMM G complete
+          if (tstamp && G < 2u * n_gemm) {
+            tstamp[G * 8 + 3] = t_first;
+            tstamp[G * 8 + 4] = clock64();
+            tstamp[G * 8 + 5] = ww;
+            tstamp[G * 8 + 6] = wa;
+          }
         }
       }
     }
   } else {
     // ===================== epilogue warps =====================
-    const int q = warp & 3;      // TMEM lane quarter
-    const int hsel = warp >> 2;  // column half
+    const int q = warp & 3;        // TMEM lane quarter
+    const int cslice = warp >> 2;  // 8-column slice inside every 32-column k-block
     const int row = 32 * q + lane;
-    const uint32_t tl = tmem_base + ((uint32_t)(32 * q) << 16);
-    const uint32_t a_row = (uint32_t)(row >> 3) * SBO + (uint32_t)(row & 7) * 16;
+    const uint32_t tl = tmem_base + ((uint32_t)(32 * q) << 16) + 8 * cslice;
+    // this thread's 16-byte K-chunk of k-block kb lives at chunk index 4 kb + cslice
+    const uint32_t a_thr = (uint32_t)cslice * A_LBO + (uint32_t)(row >> 3) * SBO + (uint32_t)(row & 7) * 16;
     float* xch = reinterpret_cast<float*>(smem + SM_XCH);
-    const float4* w0b = reinterpret_cast<const float4*>(blob + OFF_W0B);
-    const float* w_last = reinterpret_cast<const float*>(blob + OFF_WLAST);
-    const float* bias = reinterpret_cast<const float*>(blob + OFF_BIAS);
-    const float omega0 = hdr[HDR_OMEGA0], omega = hdr[HDR_OMEGA];
+    // grad partials of column slices 1..3 go through the (idle) A tile in the last stage: the 16-byte
+    // slot of this row in k-chunk (cslice - 1), which only this row's own warps ever write
+    unsigned char* gsc = smem + SM_A_HI + row * 16;
+    const float4* w0p = reinterpret_cast<const float4*>(blob + OFF_W0B) + cslice * 8;   // 4 pairs x 2 float4 per k-block
+    const float4* w_last4 = reinterpret_cast<const float4*>(blob + OFF_WLAST) + cslice * 2;
+    const float* biasw = reinterpret_cast<const float*>(blob + OFF_BIAS);
+    const float omega = hdr[HDR_OMEGA];
     const float gl_scale = hdr[HDR_GL_SCALE], gl_scale_inv = hdr[HDR_GL_SCALE_INV];
     const float b_last = hdr[HDR_B_LAST];
     // per-CTA stash: [(l-1)][col4 (64)][row (128)] float4, l = 1..L-1
     float4* stash = reinterpret_cast<float4*>(scratch) + (size_t)blockIdx.x * (size_t)(L > 1 ? L - 1 : 1) * 64 * TM;
     uint32_t G = 0;
+
+    // publish this thread's K-chunk of k-block kb: generic-proxy stores -> async proxy, one arrive per warp
+    auto publish = [&](int kb, const float2* o) {
+      const uint32_t off = (uint32_t)(kb * 4) * A_LBO + a_thr;
+      store_chunk(sbase + SM_A_HI + off, sbase + SM_A_LO + off, o);
+      tc_fence_before();
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_a_ready + 8 * kb);
+    };
 
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int grow = tile * TM + row;
@@ -432,196 +501,229 @@ siren_sdf_grad_kernel(const float* __restrict__ x, int n_max, const int* __restr
         py = x[3 * (size_t)grow + 1];
         pz = x[3 * (size_t)grow + 2];
       }
+      const float2 px2 = bc2(px), py2 = bc2(py), pz2 = bc2(pz);
       // ---- E0: first layer in SIMT, A = 2^12 sin(w0 z_0) ----
 #pragma unroll 1
-      for (int j = 0; j < 4; ++j) {
-        const int kb = 4 * hsel + j;
+      for (int kb = 0; kb < NKB; ++kb) {
+        float2 o[4];
 #pragma unroll
-        for (int c8 = 0; c8 < 4; ++c8) {
-          float o[8];
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            float4 w = __ldg(w0b + kb * KB + c8 * 8 + i);
-            float z = fmaf(w.z, pz, fmaf(w.y, py, fmaf(w.x, px, w.w)));
-            float s, c;
-            sincos_f32(omega0 * z, s, c);
-            o[i] = s * A_SCALE;
-          }
-          const uint32_t off = (uint32_t)(kb * 4 + c8) * A_LBO + a_row;
-          store_chunk(sbase + SM_A_HI + off, sbase + SM_A_LO + off, o);
+        for (int pr = 0; pr < 4; ++pr) {
+          const float4 wa = __ldg(w0p + kb * 32 + pr * 2), wb = __ldg(w0p + kb * 32 + pr * 2 + 1);
+          const float2 th = __ffma2_rn(make_float2(wb.x, wb.y), pz2,
+                                       __ffma2_rn(make_float2(wa.z, wa.w), py2,
+                                                  __ffma2_rn(make_float2(wa.x, wa.y), px2, make_float2(wb.z, wb.w))));
+          float2 sn, cp;
+          uint32_t sx, sy;
+          sincos2(th, sn, cp, sx, sy);
+          o[pr] = __fmul2_rn(sn, bc2(A_SCALE));
         }
-        fence_proxy_async();
-        mbar_arrive(bar_a_ready + 8 * kb);
+        publish(kb, o);
       }
 
       float row_scale_inv = 1.f;  // inverse of the scale applied to this row of the current backward A
       for (int g = 0; g < n_gemm; ++g, ++G) {
         const uint32_t buf = G & 1;
+        long long* tstamp =
+            (dbg && dbg_gemm == -2 && blockIdx.x == 0 && threadIdx.x == 0 && G < 2u * n_gemm)
+                ? reinterpret_cast<long long*>(dbg) + G * 8 : nullptr;
+        if (tstamp) tstamp[7] = clock64();
         mbar_wait(bar_acc_full + 8 * buf, (G >> 1) & 1);
         tc_fence_after();
+        if (tstamp) tstamp[0] = clock64();
         const uint32_t tacc = tl + buf * H;
         const bool fwd = g < L;
         const int l = fwd ? g + 1 : 2 * L - g;  // 1-based hidden layer this GEMM belongs to
         const float wsi = hdr[l - 1];
+        uint32_t rn[8];                    // next k-block's accumulator slice, loaded ahead
+        tmem_ld8_issue(tacc, rn);
+        {
+          // the cos factors the NEXT backward stage will read were written up to 2(L-1) stages ago and
+          // may have left L2: start pulling this thread's 16 lines back in one stage ahead
+          const int lp = fwd ? (l == L ? L - 1 : 0) : l - 2;   // stash slot (1-based layer) read next
+          if (lp >= 1) {
+            const float4* pf = stash + (size_t)(lp - 1) * 64 * TM + row;
+#pragma unroll
+            for (int kb = 0; kb < NKB; ++kb) {
+              const int col4 = kb * 8 + cslice * 2;
+              asm volatile("prefetch.global.L2 [%0];" ::"l"(pf + (size_t)col4 * TM));
+              asm volatile("prefetch.global.L2 [%0];" ::"l"(pf + (size_t)(col4 + 1) * TM));
+            }
+          }
+        }
 
         if (dbg && blockIdx.x == 0 && (int)G == dbg_gemm) {
           // raw accumulator dump (unscaled), [128][256]
 #pragma unroll 1
-          for (int j = 0; j < 4; ++j) {
-            float v[32];
-            const int col0 = (4 * hsel + j) * KB;
-            tmem_ld32(tacc + col0, v);
+          for (int kb = 0; kb < NKB; ++kb) {
+            uint32_t r[8];
+            tmem_ld8_issue(tacc + kb * KB, r);
+            tmem_ld_wait(r);
 #pragma unroll
-            for (int i = 0; i < 32; ++i) dbg[(size_t)row * H + col0 + i] = v[i];
+            for (int i = 0; i < 8; ++i) dbg[(size_t)row * H + kb * KB + cslice * 8 + i] = __uint_as_float(r[i]);
           }
         }
 
         if (fwd && l < L) {
           // ---- E_f(l): h_l = sin(w z_l) -> A ; stash c_l = w cos(w z_l) ----
-          const float sc = wsi * A_SCALE_INV;
+          const float2 sc2 = bc2(wsi * A_SCALE_INV * omega);
           float4* st = stash + (size_t)(l - 1) * 64 * TM + row;
+          const float4* bw4 = reinterpret_cast<const float4*>(biasw + (l - 1) * H) + cslice * 2;
+          float4 bwn0 = __ldg(bw4), bwn1 = __ldg(bw4 + 1);   // biases one k-block ahead
 #pragma unroll 1
-          for (int j = 0; j < 4; ++j) {
-            const int kb = 4 * hsel + j;
-            float v[32];
-            tmem_ld32(tacc + kb * KB, v);
+          for (int kb = 0; kb < NKB; ++kb) {
+            tmem_ld_wait(rn);
+            const float2 v[4] = {make_float2(__uint_as_float(rn[0]), __uint_as_float(rn[1])),
+                                 make_float2(__uint_as_float(rn[2]), __uint_as_float(rn[3])),
+                                 make_float2(__uint_as_float(rn[4]), __uint_as_float(rn[5])),
+                                 make_float2(__uint_as_float(rn[6]), __uint_as_float(rn[7]))};
+            if (kb + 1 < NKB) tmem_ld8_issue(tacc + (kb + 1) * KB, rn);
+            const float2 bb[4] = {make_float2(bwn0.x, bwn0.y), make_float2(bwn0.z, bwn0.w),
+                                  make_float2(bwn1.x, bwn1.y), make_float2(bwn1.z, bwn1.w)};
+            float2 o[4], cc[4];
 #pragma unroll
-            for (int c8 = 0; c8 < 4; ++c8) {
-              float o[8], cc[8];
-#pragma unroll
-              for (int i = 0; i < 8; ++i) {
-                const int col = kb * KB + c8 * 8 + i;
-                float z = fmaf(v[c8 * 8 + i], sc, __ldg(bias + (l - 1) * H + col));
-                float s, c;
-                sincos_f32(omega * z, s, c);
-                o[i] = s * A_SCALE;
-                cc[i] = omega * c;
-              }
-              const int col4 = (kb * KB + c8 * 8) >> 2;
-              __stcg(st + (size_t)col4 * TM, make_float4(cc[0], cc[1], cc[2], cc[3]));
-              __stcg(st + (size_t)(col4 + 1) * TM, make_float4(cc[4], cc[5], cc[6], cc[7]));
-              const uint32_t off = (uint32_t)(kb * 4 + c8) * A_LBO + a_row;
-              store_chunk(sbase + SM_A_HI + off, sbase + SM_A_LO + off, o);
+            for (int pr = 0; pr < 4; ++pr) {
+              float2 sn, cp;
+              uint32_t sx, sy;
+              sincos2(__ffma2_rn(v[pr], sc2, bb[pr]), sn, cp, sx, sy);
+              o[pr] = __fmul2_rn(sn, bc2(A_SCALE));
+              cc[pr] = __fmul2_rn(cp, signed_scale(omega, sx, sy));
             }
-            tc_fence_before();
-            fence_proxy_async();
-            mbar_arrive(bar_a_ready + 8 * kb);
+            publish(kb, o);
+            // global traffic right after the hand-off fence (which waits for everything in flight)
+            const int col4 = kb * 8 + cslice * 2;
+            st[(size_t)col4 * TM] = make_float4(cc[0].x, cc[0].y, cc[1].x, cc[1].y);
+            st[(size_t)(col4 + 1) * TM] = make_float4(cc[2].x, cc[2].y, cc[3].x, cc[3].y);
+            if (kb + 1 < NKB) {
+              bwn0 = __ldg(bw4 + (kb + 1) * 8);
+              bwn1 = __ldg(bw4 + (kb + 1) * 8 + 1);
+            }
           }
         } else if (fwd) {
           // ---- E_f(L): sdf = h_L . w_last + b_last ; A = gl_scale * w_last * c_L ----
-          const float sc = wsi * A_SCALE_INV;
-          float acc_sdf = 0.f;
+          const float2 sc2 = bc2(wsi * A_SCALE_INV * omega);
+          const float gls = gl_scale * omega;
+          const float4* bw4 = reinterpret_cast<const float4*>(biasw + (l - 1) * H) + cslice * 2;
+          float2 acc2 = bc2(0.f);
 #pragma unroll 1
-          for (int j = 0; j < 4; ++j) {
-            const int kb = 4 * hsel + j;
-            float v[32];
-            tmem_ld32(tacc + kb * KB, v);
+          for (int kb = 0; kb < NKB; ++kb) {
+            tmem_ld_wait(rn);
+            const float2 v[4] = {make_float2(__uint_as_float(rn[0]), __uint_as_float(rn[1])),
+                                 make_float2(__uint_as_float(rn[2]), __uint_as_float(rn[3])),
+                                 make_float2(__uint_as_float(rn[4]), __uint_as_float(rn[5])),
+                                 make_float2(__uint_as_float(rn[6]), __uint_as_float(rn[7]))};
+            if (kb + 1 < NKB) tmem_ld8_issue(tacc + (kb + 1) * KB, rn);
+            const float4 b0 = __ldg(bw4 + kb * 8), b1 = __ldg(bw4 + kb * 8 + 1);
+            const float4 w0 = __ldg(w_last4 + kb * 8), w1 = __ldg(w_last4 + kb * 8 + 1);
+            const float2 bb[4] = {make_float2(b0.x, b0.y), make_float2(b0.z, b0.w), make_float2(b1.x, b1.y),
+                                  make_float2(b1.z, b1.w)};
+            const float2 ww[4] = {make_float2(w0.x, w0.y), make_float2(w0.z, w0.w), make_float2(w1.x, w1.y),
+                                  make_float2(w1.z, w1.w)};
+            float2 o[4];
 #pragma unroll
-            for (int c8 = 0; c8 < 4; ++c8) {
-              float o[8];
-#pragma unroll
-              for (int i = 0; i < 8; ++i) {
-                const int col = kb * KB + c8 * 8 + i;
-                float z = fmaf(v[c8 * 8 + i], sc, __ldg(bias + (l - 1) * H + col));
-                float s, c;
-                sincos_f32(omega * z, s, c);
-                float wl = __ldg(w_last + col);
-                acc_sdf = fmaf(s, wl, acc_sdf);
-                o[i] = (omega * c) * wl * gl_scale;
-              }
-              const uint32_t off = (uint32_t)(kb * 4 + c8) * A_LBO + a_row;
-              store_chunk(sbase + SM_A_HI + off, sbase + SM_A_LO + off, o);
+            for (int pr = 0; pr < 4; ++pr) {
+              float2 sn, cp;
+              uint32_t sx, sy;
+              sincos2(__ffma2_rn(v[pr], sc2, bb[pr]), sn, cp, sx, sy);
+              acc2 = __ffma2_rn(sn, ww[pr], acc2);
+              o[pr] = __fmul2_rn(__fmul2_rn(cp, signed_scale(gls, sx, sy)), ww[pr]);
             }
-            tc_fence_before();
-            fence_proxy_async();
-            mbar_arrive(bar_a_ready + 8 * kb);
+            publish(kb, o);
           }
+          const float acc_sdf = acc2.x + acc2.y;
           row_scale_inv = gl_scale_inv;
-          if (hsel == 1) xch[row * 4 + 2] = acc_sdf;
-          pair_barrier(q);
-          if (hsel == 0 && grow < n) sdf_out[grow] = acc_sdf + xch[row * 4 + 2] + b_last;
-          pair_barrier(q);
+          if (cslice) xch[row * 4 + cslice] = acc_sdf;
+          row_barrier(q);
+          if (cslice == 0 && grow < n)
+            sdf_out[grow] = ((acc_sdf + xch[row * 4 + 1]) + (xch[row * 4 + 2] + xch[row * 4 + 3])) + b_last;
+          row_barrier(q);
         } else if (l > 1) {
           // ---- E_b(l): g_{l-1} = acc / scales ; gp_{l-1} = g_{l-1} * c_{l-1} -> A (row-scaled) ----
           const float sc = wsi * row_scale_inv;
-          // pass 1: row maximum of |g_{l-1}| over all 256 columns
+          // pass 1: row maximum of |g_{l-1}| over all 256 columns.  Any thread of the row may scan any
+          // columns, so this one takes the contiguous 64 starting at 64 * cslice: two wide loads.
           float m = 0.f;
-#pragma unroll 1
-          for (int j = 0; j < 4; ++j) {
-            float v[32];
-            tmem_ld32(tacc + (4 * hsel + j) * KB, v);
+          {
+            tmem_ld_wait(rn);   // retire the k-block 0 prefetch; it is re-issued below for pass 2
+            const uint32_t tcont = tacc - 8 * cslice + 64 * cslice;
 #pragma unroll
-            for (int i = 0; i < 32; ++i) m = fmaxf(m, fabsf(v[i]));
-          }
-          xch[row * 4 + hsel] = m;
-          pair_barrier(q);
-          m = fmaxf(m, xch[row * 4 + (hsel ^ 1)]);
-          pair_barrier(q);
-          const float new_scale = pow2_scale_for(m * sc * fabsf(omega));
-          const float scs = sc * new_scale;
-          const float4* st = stash + (size_t)(l - 2) * 64 * TM + row;
-#pragma unroll 1
-          for (int j = 0; j < 4; ++j) {
-            const int kb = 4 * hsel + j;
-            float v[32];
-            tmem_ld32(tacc + kb * KB, v);
+            for (int hblk = 0; hblk < 2; ++hblk) {
+              float w32[32];
+              tmem_ld32(tcont + 32 * hblk, w32);
 #pragma unroll
-            for (int c8 = 0; c8 < 4; ++c8) {
-              const int col4 = (kb * KB + c8 * 8) >> 2;
-              float4 c0 = __ldcg(st + (size_t)col4 * TM);
-              float4 c1 = __ldcg(st + (size_t)(col4 + 1) * TM);
-              float o[8];
-              o[0] = v[c8 * 8 + 0] * scs * c0.x;
-              o[1] = v[c8 * 8 + 1] * scs * c0.y;
-              o[2] = v[c8 * 8 + 2] * scs * c0.z;
-              o[3] = v[c8 * 8 + 3] * scs * c0.w;
-              o[4] = v[c8 * 8 + 4] * scs * c1.x;
-              o[5] = v[c8 * 8 + 5] * scs * c1.y;
-              o[6] = v[c8 * 8 + 6] * scs * c1.z;
-              o[7] = v[c8 * 8 + 7] * scs * c1.w;
-              const uint32_t off = (uint32_t)(kb * 4 + c8) * A_LBO + a_row;
-              store_chunk(sbase + SM_A_HI + off, sbase + SM_A_LO + off, o);
+              for (int i = 0; i < 32; ++i) m = fmaxf(m, fabsf(w32[i]));
             }
-            tc_fence_before();
-            fence_proxy_async();
-            mbar_arrive(bar_a_ready + 8 * kb);
+            tmem_ld8_issue(tacc, rn);
+          }
+          xch[row * 4 + cslice] = m;
+          row_barrier(q);
+          m = fmaxf(fmaxf(xch[row * 4], xch[row * 4 + 1]), fmaxf(xch[row * 4 + 2], xch[row * 4 + 3]));
+          row_barrier(q);
+          const float new_scale = pow2_scale_for(m * sc * fabsf(omega));
+          const float2 scs2 = bc2(sc * new_scale);
+          const float4* st = stash + (size_t)(l - 2) * 64 * TM + row + (size_t)(cslice * 2) * TM;
+          float4 c0 = __ldcg(st), c1 = __ldcg(st + TM);
+#pragma unroll 1
+          for (int kb = 0; kb < NKB; ++kb) {
+            tmem_ld_wait(rn);
+            float2 o[4];
+            o[0] = __fmul2_rn(__fmul2_rn(make_float2(__uint_as_float(rn[0]), __uint_as_float(rn[1])), scs2),
+                              make_float2(c0.x, c0.y));
+            o[1] = __fmul2_rn(__fmul2_rn(make_float2(__uint_as_float(rn[2]), __uint_as_float(rn[3])), scs2),
+                              make_float2(c0.z, c0.w));
+            o[2] = __fmul2_rn(__fmul2_rn(make_float2(__uint_as_float(rn[4]), __uint_as_float(rn[5])), scs2),
+                              make_float2(c1.x, c1.y));
+            o[3] = __fmul2_rn(__fmul2_rn(make_float2(__uint_as_float(rn[6]), __uint_as_float(rn[7])), scs2),
+                              make_float2(c1.z, c1.w));
+            if (kb + 1 < NKB) tmem_ld8_issue(tacc + (kb + 1) * KB, rn);
+            publish(kb, o);
+            if (kb + 1 < NKB) {   // next k-block's cos factors, right after the hand-off fence
+              c0 = __ldcg(st + (size_t)((kb + 1) * 8) * TM);
+              c1 = __ldcg(st + (size_t)((kb + 1) * 8 + 1) * TM);
+            }
           }
           row_scale_inv = 1.f / new_scale;
         } else {
           // ---- E_b(1): g_0 = acc / scales ; gp_0 = g_0 * w0 cos(w0 z_0) ; grad = gp_0 W_0 ----
+          // (the w0 table holds omega_0-scaled rows, so gp_0 . W_0 = sum (g_0 cos) * (omega_0 W_0))
           const float sc = wsi * row_scale_inv;
-          float gx = 0.f, gy = 0.f, gz = 0.f;
+          float2 gx2 = bc2(0.f), gy2 = bc2(0.f), gz2 = bc2(0.f);
 #pragma unroll 1
-          for (int j = 0; j < 4; ++j) {
-            const int kb = 4 * hsel + j;
-            float v[32];
-            tmem_ld32(tacc + kb * KB, v);
+          for (int kb = 0; kb < NKB; ++kb) {
+            tmem_ld_wait(rn);
+            const float2 v[4] = {make_float2(__uint_as_float(rn[0]), __uint_as_float(rn[1])),
+                                 make_float2(__uint_as_float(rn[2]), __uint_as_float(rn[3])),
+                                 make_float2(__uint_as_float(rn[4]), __uint_as_float(rn[5])),
+                                 make_float2(__uint_as_float(rn[6]), __uint_as_float(rn[7]))};
+            if (kb + 1 < NKB) tmem_ld8_issue(tacc + (kb + 1) * KB, rn);
 #pragma unroll
-            for (int i = 0; i < 32; ++i) {
-              float4 w = __ldg(w0b + kb * KB + i);
-              float z = fmaf(w.z, pz, fmaf(w.y, py, fmaf(w.x, px, w.w)));
-              float s, c;
-              sincos_f32(omega0 * z, s, c);
-              float gp = v[i] * sc * (omega0 * c);
-              gx = fmaf(gp, w.x, gx);
-              gy = fmaf(gp, w.y, gy);
-              gz = fmaf(gp, w.z, gz);
+            for (int pr = 0; pr < 4; ++pr) {
+              const float4 wa = __ldg(w0p + kb * 32 + pr * 2), wb = __ldg(w0p + kb * 32 + pr * 2 + 1);
+              const float2 wx = make_float2(wa.x, wa.y), wy = make_float2(wa.z, wa.w), wz = make_float2(wb.x, wb.y);
+              const float2 th = __ffma2_rn(wz, pz2, __ffma2_rn(wy, py2, __ffma2_rn(wx, px2, make_float2(wb.z, wb.w))));
+              float2 sn, cp;
+              uint32_t sx, sy;
+              sincos2(th, sn, cp, sx, sy);
+              const float2 gp = __fmul2_rn(__fmul2_rn(v[pr], signed_scale(sc, sx, sy)), cp);
+              gx2 = __ffma2_rn(gp, wx, gx2);
+              gy2 = __ffma2_rn(gp, wy, gy2);
+              gz2 = __ffma2_rn(gp, wz, gz2);
             }
           }
+          const float gx = gx2.x + gx2.y, gy = gy2.x + gy2.y, gz = gz2.x + gz2.y;
           tc_fence_before();
-          if (hsel == 1) {
-            xch[row * 4 + 0] = gx;
-            xch[row * 4 + 1] = gy;
-            xch[row * 4 + 2] = gz;
+          if (cslice) *reinterpret_cast<float4*>(gsc + (cslice - 1) * A_LBO) = make_float4(gx, gy, gz, 0.f);
+          row_barrier(q);
+          if (cslice == 0 && grow < n) {
+            const float4 d0 = *reinterpret_cast<const float4*>(gsc);
+            const float4 d1 = *reinterpret_cast<const float4*>(gsc + A_LBO);
+            const float4 d2 = *reinterpret_cast<const float4*>(gsc + 2 * A_LBO);
+            grad_out[3 * (size_t)grow] = (gx + d0.x) + (d1.x + d2.x);
+            grad_out[3 * (size_t)grow + 1] = (gy + d0.y) + (d1.y + d2.y);
+            grad_out[3 * (size_t)grow + 2] = (gz + d0.z) + (d1.z + d2.z);
           }
-          pair_barrier(q);
-          if (hsel == 0 && grow < n) {
-            grad_out[3 * (size_t)grow] = gx + xch[row * 4 + 0];
-            grad_out[3 * (size_t)grow + 1] = gy + xch[row * 4 + 1];
-            grad_out[3 * (size_t)grow + 2] = gz + xch[row * 4 + 2];
-          }
-          pair_barrier(q);
+          row_barrier(q);
         }
+        if (tstamp) tstamp[2] = clock64();
       }
     }
   }

@@ -80,7 +80,7 @@ class ShardedUniformProjection(UniformProjection):
         self.group = group
 
     def resample(self, model, points_init, normals_init, num_points, sample_iters=None,
-                 **forward_kwargs) -> ProjectionResult:
+                 num_points_list=None, **forward_kwargs) -> ProjectionResult:
         sample_iters = sample_iters or self.sample_iters
         if points_init.shape[0] != 1:
             raise ValueError("ShardedUniformProjection: one cloud per call (B = 1)")
@@ -90,7 +90,10 @@ class ShardedUniformProjection(UniformProjection):
         _ext.require_cuda(points_init)
         lib = _ext.lib()
         dev = points_init.device
-        nloc = int(points_init.shape[1]) if num_points is None else int(num_points[0])
+        if num_points_list is not None:
+            nloc = int(num_points_list[0])
+        else:
+            nloc = int(points_init.shape[1]) if num_points is None else int(num_points[0])
         pts_loc = points_init[0, :nloc].contiguous()
         nrm_loc = torch.empty_like(pts_loc)
         if nloc:
@@ -125,5 +128,5 @@ class ShardedUniformProjection(UniformProjection):
                     _ext.ptr(inv_sigma), 1, nloc, ntot, idx.shape[2] - 1, _ext.ptr(moved), _ext.stream(dev)))
             pts_loc = moved
             result = self._project_points(model, pts_loc[None], torch.tensor([nloc], device=dev),
-                                          proj_max_iters=3, **forward_kwargs)
+                                          proj_max_iters=3, num_points_list=[nloc], **forward_kwargs)
         return result

@@ -44,6 +44,19 @@ def _filter_projection_result(result: ProjectionResult) -> ProjectionResult:
     return ProjectionResult(points, normals, mask)
 
 
+def _filter_projection_result_counted(result: ProjectionResult):
+    """``_filter_projection_result`` plus the survivor counts as a host list, with ONE read-back for
+    both (the reference pays one in ``.any()`` and more inside the boolean-mask indexing)."""
+    points, normals, mask = result
+    counts = [int(c) for c in mask.sum(dim=-1).tolist()]
+    if mask.shape[0] == 1:
+        # single cloud: order-preserving compaction with a known output size (no further sync)
+        idx = torch.nonzero_static(mask[0], size=counts[0]).squeeze(1)
+        return ProjectionResult(points[0].index_select(0, idx)[None], normals[0].index_select(0, idx)[None],
+                                mask.new_ones((1, counts[0]))), counts
+    return _filter_projection_result(result), counts
+
+
 class LevelSetProjection(object):
     """levelset_sampling.py:67-76."""
 
@@ -133,12 +146,14 @@ class UniformProjection(LevelSetProjection):
 
     # ------------------------------------------------------------------------------------
     def _project_points(self, model: Callable, points: torch.Tensor, num_points: torch.Tensor,
-                        proj_max_iters: int = None, proj_tolerance: float = None,
+                        proj_max_iters: int = None, proj_tolerance: float = None, num_points_list=None,
                         **forward_kwargs) -> ProjectionResult:
         """Newton projection of the live rows of ``points`` (B,P,3) (levelset_sampling.py:290-351).
 
         Returns padded points (B,Pmax,3), the last SDF gradient as normals (B,Pmax,3) and the
         converged mask (B,Pmax) bool.  Non-converged points keep their last position.
+        ``num_points_list``: the host copy of ``num_points`` when the caller already has it
+        (saves one read-back).
         """
         proj_max_iters = proj_max_iters or self.proj_max_iters
         proj_tolerance = proj_tolerance or self.proj_tolerance
@@ -149,7 +164,7 @@ class UniformProjection(LevelSetProjection):
         points = points.contiguous()
         if points.dtype != torch.float32:
             raise RuntimeError("expected scalar type Float")
-        num_list = [int(x) for x in num_points.tolist()]
+        num_list = [int(x) for x in (num_points_list if num_points_list is not None else num_points.tolist())]
         full = all(n == P for n in num_list)
         if full:
             points_packed = points.reshape(-1, 3).clone()
@@ -161,6 +176,7 @@ class UniformProjection(LevelSetProjection):
         not_converged = torch.ones((M,), dtype=torch.bool, device=dev)
 
         analytic = getattr(model, "isob200_analytic_sdf", None)
+        fused = siren.match(model, forward_kwargs) if M > 0 else None
         if analytic is not None and not forward_kwargs and M > 0:
             kind, radius = analytic
             if kind != "sphere":
@@ -170,6 +186,34 @@ class UniformProjection(LevelSetProjection):
                 _ext.ptr(points_packed), _ext.ptr(normals_packed), _ext.ptr(valid_u8), M, float(radius),
                 float(proj_tolerance), 0.1, int(proj_max_iters), _ext.stream(dev)))
             valid_packed = valid_u8.bool()
+        elif fused is not None:
+            # The reference's Siren decoder: SDF + gradient come from the fused tcgen05 kernel, which
+            # reads the live row count from device memory -- the whole loop is enqueued without a
+            # single read-back (the early exit of :329 becomes launches over an empty active set).
+            act = (torch.empty((M,), dtype=torch.int32, device=dev), torch.empty((M,), dtype=torch.int32, device=dev))
+            nxt = (torch.empty((M, 3), dtype=torch.float32, device=dev),
+                   torch.empty((M, 3), dtype=torch.float32, device=dev))
+            cnt = torch.zeros((proj_max_iters + 2,), dtype=torch.int32, device=dev)  # live rows entering iteration it
+            bufs = (torch.empty((M,), dtype=torch.float32, device=dev),
+                    torch.empty((M, 3), dtype=torch.float32, device=dev))
+            ws = _ext.workspace(lib.isob200_project_step_ws_bytes(M), dev)
+            nc_u8 = not_converged.view(torch.uint8)
+            st = _ext.stream(dev)
+            for it in range(proj_max_iters + 1):
+                last = (it == proj_max_iters)
+                a_dev = None if it == 0 else cnt[it:]
+                c_out = cnt[it + 1:]
+                cur = points_packed if it == 0 else nxt[it & 1]
+                siren.sdf_and_grad(model, cur, n_dev=a_dev, spec=fused, out=bufs)
+                _ext.check(lib.isob200_project_step(
+                    _ext.ptr(points_packed), _ext.ptr(normals_packed), _ext.ptr(nc_u8),
+                    None if it == 0 else _ext.ptr(act[it & 1]), M, _ext.ptr(a_dev), _ext.ptr(bufs[0]),
+                    _ext.ptr(bufs[1]), float(proj_tolerance), 0.1, 0 if last else 1,
+                    _ext.ptr(act[(it + 1) & 1]), None if last else _ext.ptr(nxt[(it + 1) & 1]), _ext.ptr(c_out),
+                    _ext.ptr(ws), ws.numel(), st))
+            if siren.RECORD is not None:   # bench.py: live row counts, resolved after the timed region
+                siren.RECORD.append((M, cnt))
+            valid_packed = ~not_converged
         else:
             if M > 0:
                 act_a = torch.empty((M,), dtype=torch.int32, device=dev)
@@ -191,7 +235,7 @@ class UniformProjection(LevelSetProjection):
                     last = (it == proj_max_iters)
                     _ext.check(lib.isob200_project_step(
                         _ext.ptr(points_packed), _ext.ptr(normals_packed), _ext.ptr(nc_u8),
-                        _ext.ptr(act_in), A, _ext.ptr(curr_sdf), _ext.ptr(curr_grad),
+                        _ext.ptr(act_in), A, None, _ext.ptr(curr_sdf), _ext.ptr(curr_grad),
                         float(proj_tolerance), 0.1, 0 if last else 1, _ext.ptr(act_out),
                         None if last else _ext.ptr(nxt_out), _ext.ptr(count), _ext.ptr(ws), ws.numel(),
                         _ext.stream(dev)))
@@ -219,7 +263,7 @@ class UniformProjection(LevelSetProjection):
 
     # ------------------------------------------------------------------------------------
     def resample(self, model, points_init, normals_init, num_points, sample_iters=None,
-                 **forward_kwargs) -> ProjectionResult:
+                 num_points_list=None, **forward_kwargs) -> ProjectionResult:
         """Repulse along neighbours' tangent planes then re-project, ``sample_iters`` times
         (levelset_sampling.py:239-288)."""
         sample_iters = sample_iters or self.sample_iters
@@ -260,7 +304,7 @@ class UniformProjection(LevelSetProjection):
             # sample_iter (`points = points + move`); the projection result is only returned.
             points = moved
             projection_result = self._project_points(model, points, num_points, proj_max_iters=3,
-                                                     **forward_kwargs)
+                                                     num_points_list=num_points_list, **forward_kwargs)
         return projection_result
 
     # ------------------------------------------------------------------------------------
@@ -332,19 +376,27 @@ class UniformProjection(LevelSetProjection):
         if normals_init is None and is_pointclouds(point_clouds):
             normals_init = point_clouds.normals_padded()
 
+        num_list = None
+        if torch.is_tensor(point_clouds):   # dense tensor input: every cloud has all P rows
+            num_list = [int(points_init.shape[1])] * int(points_init.shape[0])
         with autograd.no_grad():
             points_projected, normals_projected, valid_projection = self._project_points(
-                model, points_init, num_points, proj_max_iters=proj_max_iters, **forward_kwargs)
-            if not valid_projection.any():
-                return {'levelset_points': points_projected, 'mask': valid_projection}
-
-            if not skip_resampling:
-                points_projected, normals_projected, valid_projection = _filter_projection_result(
-                    ProjectionResult(points_projected, normals_projected, valid_projection))
-                num_points = valid_projection.sum(dim=-1)
+                model, points_init, num_points, proj_max_iters=proj_max_iters, num_points_list=num_list,
+                **forward_kwargs)
+            if skip_resampling:
+                if not valid_projection.any():
+                    return {'levelset_points': points_projected, 'mask': valid_projection}
+            else:
+                unfiltered = (points_projected, valid_projection)
+                (points_projected, normals_projected, valid_projection), counts = \
+                    _filter_projection_result_counted(
+                        ProjectionResult(points_projected, normals_projected, valid_projection))
+                if sum(counts) == 0:   # nothing converged (:396-399)
+                    return {'levelset_points': unfiltered[0], 'mask': unfiltered[1]}
+                num_points = torch.as_tensor(counts, dtype=torch.int64, device=points_projected.device)
                 points_projected, normals_projected, valid_projection = self.resample(
                     model, points_projected, normals_projected, num_points, sample_iters=sample_iters,
-                    **forward_kwargs)
+                    num_points_list=counts, **forward_kwargs)
                 num_points = valid_projection.sum(dim=-1)
 
             if not skip_upsampling and ref_pcl is not None:

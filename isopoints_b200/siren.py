@@ -26,6 +26,19 @@ _CACHE = weakref.WeakKeyDictionary()
 ENABLED = os.environ.get("ISOB200_FUSED_SIREN", "1") != "0"
 # rows / flops handed to the fused kernel since import (bench.py turns them into the roofline line)
 STATS = {"calls": 0, "rows": 0, "flops": 0}
+# when a list: the sync-free projection loop appends (first-iteration rows, device tensor of the live
+# row counts entering iterations 1..) so that bench.py can count the rows actually evaluated
+RECORD = None
+
+
+def resolve_record():
+    """Fold RECORD into STATS (reads the device counters: call outside any timed region)."""
+    global RECORD
+    if RECORD:
+        for m, cnt in RECORD:
+            # iteration 0 evaluated all m rows (already counted: it runs without a device count)
+            STATS["rows"] += sum(int(c) for c in cnt.tolist()[1:-1])
+        RECORD = []
 
 
 def algorithmic_flops(n_rows, n_hidden):
@@ -129,10 +142,13 @@ def packed(model, spec):
     return ent[1]
 
 
-def sdf_and_grad(model, points, forward_kwargs=None, n_dev=None, dbg_gemm=None):
+def sdf_and_grad(model, points, forward_kwargs=None, n_dev=None, dbg_gemm=None, spec=None, out=None):
     """sdf (n,) and d sdf/d x (n,3) of a fusable SIREN at ``points`` (n,3) fp32 cuda, or None when
-    ``model`` is not fusable.  ``n_dev``: optional int32 device scalar with the live row count."""
-    spec = match(model, forward_kwargs)
+    ``model`` is not fusable.  ``n_dev``: optional int32 device scalar with the live row count (rows
+    past it are left untouched); ``spec``: result of an earlier ``match``; ``out``: preallocated
+    (sdf, grad) buffers with at least n rows."""
+    if spec is None:
+        spec = match(model, forward_kwargs)
     if spec is None:
         return None
     _ext.require_cuda(points)
@@ -144,15 +160,18 @@ def sdf_and_grad(model, points, forward_kwargs=None, n_dev=None, dbg_gemm=None):
     n = x.shape[0]
     dev = x.device
     blob, scratch, L = packed(model, spec)
-    sdf = torch.empty((n,), dtype=torch.float32, device=dev)
-    grad = torch.empty((n, 3), dtype=torch.float32, device=dev)
+    if out is not None:
+        sdf, grad = out[0][:n], out[1][:n]
+    else:
+        sdf = torch.empty((n,), dtype=torch.float32, device=dev)
+        grad = torch.empty((n, 3), dtype=torch.float32, device=dev)
     dbg = None
     if dbg_gemm is not None:
         dbg = torch.zeros((128, HIDDEN), dtype=torch.float32, device=dev)
     if n > 0:
         STATS["calls"] += 1
-        STATS["rows"] += n
-        STATS["flops"] += algorithmic_flops(n, L)
+        if n_dev is None or RECORD is None:
+            STATS["rows"] += n
         _ext.check(lib.isob200_siren_sdf_grad(_ext.ptr(x), n, _ext.ptr(n_dev), _ext.ptr(blob), L, _ext.ptr(sdf),
                                               _ext.ptr(grad), _ext.ptr(scratch), scratch.numel(), _ext.ptr(dbg),
                                               -1 if dbg_gemm is None else int(dbg_gemm), _ext.stream(dev)))

@@ -133,3 +133,38 @@ def test_projection_with_fused_sdf_matches_autograd_path():
     # a random-init SIREN is chaotic (omega = 30 per layer): compare the bulk, bound the tail
     d = np.abs(pa - pb).max(axis=1)
     assert np.quantile(d, 0.99) < 1e-4 and np.median(d) < 2e-6
+
+
+def test_project_resample_and_ragged_batch_with_fused_sdf():
+    """The sync-free loop (device-side live counts) through filter + resample + re-projection, and
+    on a ragged two-cloud batch, against the opaque-module path on the same weights."""
+    torch.manual_seed(1)
+    fused, opaque = Siren(256, 2, 30.0, seed=7).to(DEV), SirenSDF(256, 2, 30.0, seed=7).to(DEV)
+    old = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        x = ((torch.rand(1, 5000, 3) - 0.5) * 2).to(DEV)
+        outs = []
+        for m in (fused, opaque):
+            proj = UniformProjection(proj_max_iters=10, proj_tolerance=5e-5, knn_k=8, sample_iters=1)
+            outs.append(proj.project_points(x.clone(), m, skip_upsampling=True))
+        a, b = outs
+        # survivors of the first projection may differ by a few borderline points, which shifts rows:
+        # compare as point sets through nearest-neighbour distance
+        pa, pb = a["levelset_points"][0][a["mask"][0]], b["levelset_points"][0][b["mask"][0]]
+        assert abs(pa.shape[0] - pb.shape[0]) <= 0.01 * pb.shape[0]
+        d = torch.cdist(pa, pb).min(dim=1).values
+        assert d.median().item() < 1e-5 and d.quantile(0.98).item() < 1e-3
+        # ragged batch straight into _project_points
+        xr = ((torch.rand(2, 1500, 3) - 0.5) * 2).to(DEV)
+        num = torch.tensor([1500, 900], device=DEV)
+        ra = UniformProjection(proj_max_iters=8)._project_points(fused, xr.clone(), num)
+        rb = UniformProjection(proj_max_iters=8)._project_points(opaque, xr.clone(), num)
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = old
+    agree = (ra.mask == rb.mask)
+    assert agree.float().mean().item() > 0.995
+    both = ra.mask & rb.mask
+    dd = (ra.points - rb.points).abs().max(dim=-1).values[both]
+    assert dd.median().item() < 2e-6 and dd.quantile(0.99).item() < 1e-4
+    assert not ra.mask[1, 900:].any() and (ra.points[1, 900:] == 0).all()
