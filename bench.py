@@ -166,13 +166,21 @@ def run_ours(args):
     def step(x):
         return proj.project_points(x, net, skip_upsampling=True)
 
+    # pinned host buffers for the results, allocated once (outputs have at most C2_POINTS rows)
+    pin = {"levelset_points": torch.empty((1, C2_POINTS, 3), dtype=torch.float32).pin_memory(),
+           "levelset_normals": torch.empty((1, C2_POINTS, 3), dtype=torch.float32).pin_memory(),
+           "mask": torch.empty((1, C2_POINTS), dtype=torch.bool).pin_memory()}
+
     def step_e2e():
         x = x_pin.to(dev, non_blocking=True)
         out = step(x)
-        res = tuple(torch.empty(out[k].shape, dtype=out[k].dtype).pin_memory().copy_(out[k], non_blocking=True)
-                    for k in ("levelset_points", "levelset_normals", "mask"))
+        res = []
+        for k in ("levelset_points", "levelset_normals", "mask"):
+            dst = pin[k][:, :out[k].shape[1]]
+            dst.copy_(out[k], non_blocking=True)
+            res.append(dst)
         torch.cuda.synchronize()
-        return out, res
+        return out, tuple(res)
 
     for _ in range(args.warmup):
         out = step(x_dev)

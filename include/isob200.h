@@ -78,6 +78,11 @@ int isob200_project_step(float* points, float* normals, unsigned char* not_conve
                          float tol, float max_step, int do_update, int* act_out, float* next_points,
                          int* count_out, void* ws, size_t ws_bytes, void* stream);
 int isob200_gather_rows3(const float* src, const int* idx, int A, float* dst, void* stream);
+/* _filter_projection_result (levelset_sampling.py:59-65) for one packed cloud: the converged rows of
+ * points / normals, in order, into out_* (>= M rows); *count_out = survivors.  ws as for project_step. */
+int isob200_compact_valid(const float* points, const float* normals, const unsigned char* valid,
+                          int M, float* out_points, float* out_normals, int* count_out, void* ws,
+                          size_t ws_bytes, void* stream);
 int isob200_project_sphere(float* points, float* normals, unsigned char* valid, long long M,
                            float radius, float tol, float max_step, int max_iters, void* stream);
 

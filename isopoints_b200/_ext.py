@@ -39,6 +39,7 @@ _PROTOS = {
     "isob200_project_step_ws_bytes": (_sz, [_i]),
     "isob200_project_step": (_i, [_vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _f, _f, _i, _vp, _vp, _vp, _vp, _sz, _vp]),
     "isob200_gather_rows3": (_i, [_vp, _vp, _i, _vp, _vp]),
+    "isob200_compact_valid": (_i, [_vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _sz, _vp]),
     "isob200_project_sphere": (_i, [_vp, _vp, _vp, _ll, _f, _f, _f, _i, _vp]),
     "isob200_siren_blob_bytes": (_sz, [_i]),
     "isob200_siren_pack_ws_bytes": (_sz, []),

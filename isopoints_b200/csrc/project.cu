@@ -169,6 +169,81 @@ project_step_kernel(float* __restrict__ points, float* __restrict__ normals,
     }
 }
 
+// Order-preserving compaction of the valid (converged) rows of (points, normals): _filter_projection_result
+// (levelset_sampling.py:59-65 -> DSS/utils/__init__.py:149-169) for one packed cloud, in one pass with
+// the same ticket + decoupled look-back scan as project_step_kernel.  count_out receives the number
+// of survivors (the only value the host reads back: it is the output shape).
+__global__ void __launch_bounds__(PJ_THREADS)
+compact_valid_kernel(const float* __restrict__ points, const float* __restrict__ normals,
+                     const unsigned char* __restrict__ valid, int M, float* __restrict__ out_points,
+                     float* __restrict__ out_normals, int* __restrict__ count_out, unsigned* __restrict__ ws) {
+  __shared__ int s_tile;
+  __shared__ int s_warp[PJ_THREADS / 32];
+  __shared__ int s_prefix;
+  if (threadIdx.x == 0) s_tile = (int)atomicAdd(&ws[0], 1u);
+  __syncthreads();
+  const int tile = s_tile;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int base = tile * PJ_TILE + threadIdx.x * PJ_ITEMS;
+  int keep[PJ_ITEMS];
+  int cnt = 0;
+#pragma unroll
+  for (int j = 0; j < PJ_ITEMS; ++j) {
+    const int i = base + j;
+    keep[j] = (i < M) && valid[i];
+    cnt += keep[j];
+  }
+  int incl = cnt;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int t = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += t;
+  }
+  if (lane == 31) s_warp[w] = incl;
+  __syncthreads();
+  int woff = 0, total = 0;
+#pragma unroll
+  for (int i = 0; i < PJ_THREADS / 32; ++i) {
+    const int t = s_warp[i];
+    if (i < w) woff += t;
+    total += t;
+  }
+  if (threadIdx.x == 0) {
+    unsigned* status = ws + 2;
+    int prefix = 0;
+    if (tile == 0) {
+      __threadfence();
+      atomicExch(&status[0], LB_FLAG_INC | (unsigned)total);
+    } else {
+      atomicExch(&status[tile], LB_FLAG_AGG | (unsigned)total);
+      int t = tile - 1;
+      while (true) {
+        const unsigned s = ld_volatile_u32(&status[t]);
+        if ((s >> 30) == 0) continue;
+        prefix += (int)(s & LB_VALUE_MASK);
+        if (s & LB_FLAG_INC) break;
+        --t;
+      }
+      atomicExch(&status[tile], LB_FLAG_INC | (unsigned)(prefix + total));
+    }
+    s_prefix = prefix;
+    if ((long long)(tile + 1) * PJ_TILE >= M) *count_out = prefix + total;
+  }
+  __syncthreads();
+  int pos = s_prefix + woff + incl - cnt;
+#pragma unroll
+  for (int j = 0; j < PJ_ITEMS; ++j)
+    if (keep[j]) {
+      const size_t i = (size_t)(base + j);
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        out_points[3 * (size_t)pos + c] = points[3 * i + c];
+        out_normals[3 * (size_t)pos + c] = normals[3 * i + c];
+      }
+      ++pos;
+    }
+}
+
 // dst[i, :] = src[idx[i], :]   (curr_points = points_packed[not_converged], :315)
 __global__ void __launch_bounds__(256)
 gather_rows3_kernel(const float* __restrict__ src, const int* __restrict__ idx, int A,
@@ -268,6 +343,29 @@ int isob200_project_step(float* points, float* normals, unsigned char* not_conve
                                                    tol, max_step, do_update, act_out, next_points,
                                                    count_out, (unsigned*)ws);
   ISO_CHECK_LAUNCH("project_step_kernel");
+  return ISOB200_OK;
+}
+
+// out_points / out_normals (>= M x 3) <- the rows with valid != 0, in order; *count_out = their number
+int isob200_compact_valid(const float* points, const float* normals, const unsigned char* valid,
+                          int M, float* out_points, float* out_normals, int* count_out, void* ws,
+                          size_t ws_bytes, void* stream_) {
+  cudaStream_t st = (cudaStream_t)stream_;
+  ISO_CHECK_ARG(M >= 0 && count_out, "compact_valid: bad arguments");
+  if (M == 0) {
+    ISO_CUDA(cudaMemsetAsync(count_out, 0, sizeof(int), st));
+    return ISOB200_OK;
+  }
+  ISO_CHECK_ARG(points && normals && valid && out_points && out_normals && ws, "compact_valid: null pointer");
+  const size_t need = isob200_project_step_ws_bytes(M);
+  if (ws_bytes < need) {
+    set_error("compact_valid: workspace too small (%zu < %zu)", ws_bytes, need);
+    return ISOB200_ERR_WORKSPACE;
+  }
+  ISO_CUDA(cudaMemsetAsync(ws, 0, need, st));
+  compact_valid_kernel<<<div_up(M, PJ_TILE), PJ_THREADS, 0, st>>>(points, normals, valid, M, out_points,
+                                                                 out_normals, count_out, (unsigned*)ws);
+  ISO_CHECK_LAUNCH("compact_valid_kernel");
   return ISOB200_OK;
 }
 

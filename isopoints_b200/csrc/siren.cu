@@ -661,8 +661,10 @@ siren_sdf_grad_kernel(const float* __restrict__ x, int n_max, const int* __restr
           const float new_scale = pow2_scale_for(m * sc * fabsf(omega));
           const float2 scs2 = bc2(sc * new_scale);
           const float4* st = stash + (size_t)(l - 2) * 64 * TM + row + (size_t)(cslice * 2) * TM;
+          // cos factors: two k-blocks in flight (an L2 hit is ~1 k-block of this loop away, a miss more)
           float4 c0 = __ldcg(st), c1 = __ldcg(st + TM);
-#pragma unroll 1
+          float4 d0 = __ldcg(st + (size_t)8 * TM), d1 = __ldcg(st + (size_t)9 * TM);
+#pragma unroll 2
           for (int kb = 0; kb < NKB; ++kb) {
             tmem_ld_wait(rn);
             float2 o[4];
@@ -676,9 +678,17 @@ siren_sdf_grad_kernel(const float* __restrict__ x, int n_max, const int* __restr
                               make_float2(c1.z, c1.w));
             if (kb + 1 < NKB) tmem_ld8_issue(tacc + (kb + 1) * KB, rn);
             publish(kb, o);
-            if (kb + 1 < NKB) {   // next k-block's cos factors, right after the hand-off fence
-              c0 = __ldcg(st + (size_t)((kb + 1) * 8) * TM);
-              c1 = __ldcg(st + (size_t)((kb + 1) * 8 + 1) * TM);
+            // this k-block's cos lines are dead now (the next tile rewrites them in full before reading):
+            // drop them from L2 instead of letting them be written back to HBM
+            if ((lane & 7) == 0) {
+              asm volatile("discard.global.L2 [%0], 128;" ::"l"(st + (size_t)(kb * 8) * TM) : "memory");
+              asm volatile("discard.global.L2 [%0], 128;" ::"l"(st + (size_t)(kb * 8 + 1) * TM) : "memory");
+            }
+            c0 = d0;
+            c1 = d1;
+            if (kb + 2 < NKB) {   // right after the hand-off fence, two k-blocks ahead of its use
+              d0 = __ldcg(st + (size_t)((kb + 2) * 8) * TM);
+              d1 = __ldcg(st + (size_t)((kb + 2) * 8 + 1) * TM);
             }
           }
           row_scale_inv = 1.f / new_scale;

@@ -48,12 +48,23 @@ def _filter_projection_result_counted(result: ProjectionResult):
     """``_filter_projection_result`` plus the survivor counts as a host list, with ONE read-back for
     both (the reference pays one in ``.any()`` and more inside the boolean-mask indexing)."""
     points, normals, mask = result
+    if mask.shape[0] == 1 and points.is_cuda and points.dtype == torch.float32:
+        # single cloud: one order-preserving compaction kernel; the count it leaves on the device is the
+        # output shape and the only thing read back
+        lib = _ext.lib()
+        dev = points.device
+        M = int(mask.shape[1])
+        pts, nrm = points.reshape(-1, 3).contiguous(), normals.reshape(-1, 3).contiguous()
+        valid = mask.reshape(-1).contiguous().view(torch.uint8)
+        out_p, out_n = torch.empty_like(pts), torch.empty_like(nrm)
+        count = torch.zeros((1,), dtype=torch.int32, device=dev)
+        ws = _ext.workspace(lib.isob200_project_step_ws_bytes(max(M, 1)), dev)
+        _ext.check(lib.isob200_compact_valid(_ext.ptr(pts), _ext.ptr(nrm), _ext.ptr(valid), M, _ext.ptr(out_p),
+                                             _ext.ptr(out_n), _ext.ptr(count), _ext.ptr(ws), ws.numel(),
+                                             _ext.stream(dev)))
+        n = int(count.item())
+        return ProjectionResult(out_p[:n][None], out_n[:n][None], mask.new_ones((1, n))), [n]
     counts = [int(c) for c in mask.sum(dim=-1).tolist()]
-    if mask.shape[0] == 1:
-        # single cloud: order-preserving compaction with a known output size (no further sync)
-        idx = torch.nonzero_static(mask[0], size=counts[0]).squeeze(1)
-        return ProjectionResult(points[0].index_select(0, idx)[None], normals[0].index_select(0, idx)[None],
-                                mask.new_ones((1, counts[0]))), counts
     return _filter_projection_result(result), counts
 
 
@@ -100,7 +111,10 @@ class UniformProjection(LevelSetProjection):
         if num_points_per_cloud is None:
             num_points_per_cloud = torch.tensor([points_padded.shape[1]] * points_padded.shape[0],
                                                 device=points_padded.device, dtype=torch.long)
-        diag = (points_padded.max(dim=1).values - points_padded.min(dim=1).values).norm(dim=-1)
+        diag = self.__dict__.pop("_diag_hint", None)   # resample() just computed it for this very tensor
+        if diag is None:
+            mn, mx = torch.aminmax(points_padded, dim=1)
+            diag = (mx - mn).norm(dim=-1)
         search_radius = torch.sqrt(diag / num_points_per_cloud.float()) * self.knn_k
         dists, idxs, _, grid = frnn.frnn_grid_points(
             points_padded, points_padded, num_points_per_cloud, num_points_per_cloud,
@@ -199,12 +213,13 @@ class UniformProjection(LevelSetProjection):
             ws = _ext.workspace(lib.isob200_project_step_ws_bytes(M), dev)
             nc_u8 = not_converged.view(torch.uint8)
             st = _ext.stream(dev)
+            pk = siren.packed(model, fused)   # operand images for the current parameter version
             for it in range(proj_max_iters + 1):
                 last = (it == proj_max_iters)
                 a_dev = None if it == 0 else cnt[it:]
                 c_out = cnt[it + 1:]
                 cur = points_packed if it == 0 else nxt[it & 1]
-                siren.sdf_and_grad(model, cur, n_dev=a_dev, spec=fused, out=bufs)
+                siren.sdf_and_grad(model, cur, n_dev=a_dev, spec=fused, out=bufs, pk=pk)
                 _ext.check(lib.isob200_project_step(
                     _ext.ptr(points_packed), _ext.ptr(normals_packed), _ext.ptr(nc_u8),
                     None if it == 0 else _ext.ptr(act[it & 1]), M, _ext.ptr(a_dev), _ext.ptr(bufs[0]),
@@ -281,7 +296,8 @@ class UniformProjection(LevelSetProjection):
         lib = _ext.lib()
         dev = points_init.device
         flat = points_init.reshape(-1, 3)
-        diag = (flat.max(dim=0).values - flat.min(0).values).norm()  # stays on the device (:254)
+        mn, mx = torch.aminmax(flat, dim=0)
+        diag = (mx - mn).norm()  # stays on the device (:254)
         inv_sigma_spatial = (num_points.float() / diag).contiguous()  # (B,)
 
         points = points_init.contiguous()
@@ -293,6 +309,8 @@ class UniformProjection(LevelSetProjection):
         for sample_iter in range(sample_iters):
             if sample_iter % 2 == 0:
                 # assume repulsion doesn't change neighborhood
+                if sample_iter == 0 and B == 1 and type(self)._create_tree is UniformProjection._create_tree:
+                    self._diag_hint = diag.reshape(1)   # same tensor, same bounding box (:129 == :254 for B = 1)
                 self._create_tree(points, refresh_tree=True, num_points_per_cloud=num_points)
             idx_full = self._knn_full_idx  # (B,P,knn_k+1) int64, column 0 = self
             moved = torch.empty_like(points)

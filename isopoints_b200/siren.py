@@ -51,7 +51,7 @@ class _Spec(object):
     __slots__ = ("first", "hidden", "last", "omega0", "omega")
 
 
-def match(model, forward_kwargs=None):
+def match(model, forward_kwargs=None, require_cuda=True):
     """Return the layer spec if ``model`` is a fusable SIREN SDF, else None."""
     if not ENABLED or not isinstance(model, nn.Module):
         return None
@@ -92,7 +92,7 @@ def match(model, forward_kwargs=None):
     if len(omegas) != 1:
         return None
     params = [first.weight, last.weight] + [h.weight for h in hidden]
-    if any((not p.is_cuda) or p.dtype != torch.float32 for p in params):
+    if any((require_cuda and not p.is_cuda) or p.dtype != torch.float32 for p in params):
         return None
     s = _Spec()
     s.first, s.hidden, s.last = first, hidden, last
@@ -142,11 +142,11 @@ def packed(model, spec):
     return ent[1]
 
 
-def sdf_and_grad(model, points, forward_kwargs=None, n_dev=None, dbg_gemm=None, spec=None, out=None):
+def sdf_and_grad(model, points, forward_kwargs=None, n_dev=None, dbg_gemm=None, spec=None, out=None, pk=None):
     """sdf (n,) and d sdf/d x (n,3) of a fusable SIREN at ``points`` (n,3) fp32 cuda, or None when
     ``model`` is not fusable.  ``n_dev``: optional int32 device scalar with the live row count (rows
     past it are left untouched); ``spec``: result of an earlier ``match``; ``out``: preallocated
-    (sdf, grad) buffers with at least n rows."""
+    (sdf, grad) buffers with at least n rows; ``pk``: result of an earlier ``packed`` (same parameters)."""
     if spec is None:
         spec = match(model, forward_kwargs)
     if spec is None:
@@ -159,7 +159,7 @@ def sdf_and_grad(model, points, forward_kwargs=None, n_dev=None, dbg_gemm=None, 
     x = x.contiguous()
     n = x.shape[0]
     dev = x.device
-    blob, scratch, L = packed(model, spec)
+    blob, scratch, L = pk if pk is not None else packed(model, spec)
     if out is not None:
         sdf, grad = out[0][:n], out[1][:n]
     else:

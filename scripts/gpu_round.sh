@@ -12,7 +12,10 @@ if [ "${1:-}" = "prof" ]; then
   timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 6000 --csv --log-file gpurun_out/launches_c2.csv python bench.py --steps 1 --warmup 3 > gpurun_out/ncu_c2.log 2>&1
   timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_c4.csv python bench_splat.py --steps 1 > gpurun_out/ncu_c4.log 2>&1
   timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv --log-file gpurun_out/launches_c3.csv python bench_frnn.py --steps 1 > gpurun_out/ncu_c3.log 2>&1
-  timeout 600 ncu --set full --clock-control none --import-source on -k regex:frnn_query_kernel -s 3 -c 1 -f -o gpurun_out/prof_frnn_query python bench_frnn.py --steps 1 > gpurun_out/ncu_frnn.log 2>&1
+  # the fused SIREN kernel: first launch of the timed step (all 200 000 rows live); 3 warm-up steps x 15 launches are skipped
+  timeout 600 ncu --set full --clock-control none --import-source on -k regex:siren_sdf_grad -s 45 -c 1 -f -o gpurun_out/prof_siren python bench.py --steps 1 --warmup 3 > gpurun_out/ncu_siren.log 2>&1
+  timeout 600 ncu --set full --clock-control none --import-source on -k regex:frnn_query -s 3 -c 1 -f -o gpurun_out/prof_frnn_query_c2 python bench.py --steps 1 --warmup 3 > gpurun_out/ncu_frnn_c2.log 2>&1
+  timeout 600 ncu --set full --clock-control none --import-source on -k regex:frnn_query -s 3 -c 1 -f -o gpurun_out/prof_frnn_query python bench_frnn.py --steps 1 > gpurun_out/ncu_frnn.log 2>&1
   timeout 600 ncu --set full --clock-control none --import-source on -k regex:splat_raster_v2_kernel -s 3 -c 1 -f -o gpurun_out/prof_splat_raster python bench_splat.py --steps 1 > gpurun_out/ncu_raster.log 2>&1
   timeout 600 ncu --set full --clock-control none --import-source on -k regex:splat_occ_backward_hybrid_kernel -s 3 -c 1 -f -o gpurun_out/prof_splat_occ_bwd python bench_splat.py --steps 1 > gpurun_out/ncu_occ.log 2>&1
   timeout 900 compute-sanitizer --tool memcheck --error-exitcode 7 python -m pytest tests/test_gpu_splat.py tests/test_gpu_frnn.py tests/test_gpu_projection.py -m gpu -q -k "not 500k and not c4_scale and not c2_scale and not world1" > gpurun_out/sanitizer_memcheck.log 2>&1; echo "memcheck rc=$?"; tail -3 gpurun_out/sanitizer_memcheck.log

@@ -54,6 +54,10 @@ def raw(rep):
         for k in KEYS:
             if k in d:
                 res.append("  %-72s %s %s" % (k, d[k], u.get(k, "")))
+        for k in hdr:   # tensor-pipe metrics (only non-zero for the tcgen05 kernel)
+            if (("pipe_tensor_cycles_active" in k or "utchmma_src_fp16_dst_fp32_sparsity_off.avg.pct_of_peak" in k
+                 or k == "sm__inst_executed.avg.per_cycle_active") and d.get(k, "0") not in ("0", "")):
+                res.append("  %-72s %s %s" % (k[-72:], d[k], u.get(k, "")))
     return "\n".join(res)
 
 
@@ -67,12 +71,15 @@ def traffic(rep):
     tot = 0.0
     for k in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
         tot += float(d[k].replace(",", "")) * mult.get(u[k], 1)
-    name = re.sub(r"<.*", "", d["Kernel Name"].replace("void ", "").replace("isob200::", "")).strip()
+    name = re.sub(r"[<(].*", "", d["Kernel Name"].replace("void ", "").replace("isob200::", "")).strip()
     extra = {}
     for k, short in (("smsp__issue_active.avg.pct_of_peak_sustained_active", "issue_active_pct"),
                      ("gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "dram_pct"),
                      ("lts__throughput.avg.pct_of_peak_sustained_elapsed", "l2_pct"),
-                     ("sm__warps_active.avg.pct_of_peak_sustained_active", "occupancy_pct")):
+                     ("sm__warps_active.avg.pct_of_peak_sustained_active", "occupancy_pct"),
+                     ("sm__ops_path_tensor_op_utchmma_src_fp16_dst_fp32_sparsity_off.avg.pct_of_peak_sustained_elapsed",
+                      "tensor_ops_pct_of_peak"),
+                     ("gpu__time_duration.sum", "duration")):
         try:
             extra[short] = float(d[k].replace(",", ""))
         except Exception:
@@ -107,7 +114,7 @@ def hot_lines(rep, top=14):
 def main():
     tag = sys.argv[1] if len(sys.argv) > 1 else "rXX"
     os.makedirs(PROF, exist_ok=True)
-    for name in ("launches_c2", "launches_c4"):
+    for name in ("launches_c2", "launches_c4", "launches_c3"):
         p = os.path.join(OUT, name + ".csv")
         if os.path.exists(p):
             open(os.path.join(PROF, "%s_%s.txt" % (tag, name)), "w").write(launches(p) + "\n")

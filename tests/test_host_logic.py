@@ -45,3 +45,27 @@ def test_packed_padded_round_trip_and_mask_reduce():
     red = S.reduce_mask_padded(vals, m)
     assert red.tolist() == [[0.0, 2.0, 5.0], [9.0, 0.0, 0.0]]
     assert S.reduce_mask_padded(m, m).dtype == torch.bool
+
+
+def test_siren_recognition_is_structural():
+    """isopoints_b200.siren.match: only the reference decoder's structure (common.py:90-165) with
+    width 256, one hidden omega, no latent code and an sdf head is fused; everything else keeps
+    the autograd callback (no compute here, parameters stay on the CPU)."""
+    import torch
+    from isopoints_b200 import siren
+    from tests.helpers import Siren, SirenSDF
+    m = Siren(256, 3, 30.0, seed=0)
+    assert siren.match(m) is None                                  # CPU parameters: CUDA path only
+    spec = siren.match(m, require_cuda=False)
+    assert spec is not None and len(spec.hidden) == 3 and spec.omega0 == 30.0 and spec.omega == 30.0
+    assert siren.match(SirenSDF(256, 3, 30.0), require_cuda=False) is None       # opaque module
+    assert siren.match(Siren(128, 3, 30.0), require_cuda=False) is None          # other width
+    assert siren.match(m, {"c": torch.ones(1, 2)}, require_cuda=False) is None   # latent code
+    assert siren.match(m, {"c": None}, require_cuda=False) is not None
+    assert siren.match(m, {"latent": torch.ones(1)}, require_cuda=False) is None
+    m.net[2].omega_0 = 10.0                                         # mixed hidden frequencies
+    assert siren.match(m, require_cuda=False) is None
+    m2 = Siren(256, 2, 30.0)
+    m2._out_fields = ("rgb", "sdf")                                 # sdf is not the first output
+    assert siren.match(m2, require_cuda=False) is None
+    assert siren.algorithmic_flops(1, 7) == 4 * (3 * 256 + 7 * 65536 + 256)
