@@ -29,7 +29,7 @@ sys.path.insert(0, ROOT)
 from isopoints_b200 import splat  # noqa: E402
 from isopoints_b200.dist import (ShardedUniformProjection, all_gather_varlen, all_reduce_point_grads,  # noqa: E402
                                  shard_range, shard_views)
-from tests.helpers import SirenSDF, SphereSDF  # noqa: E402
+from tests.helpers import Siren, SirenSDF, SphereSDF  # noqa: E402
 
 
 def view_rotation(v, n_views, dev):
@@ -72,7 +72,8 @@ def main():
     ap.add_argument("--points", type=int, default=2_000_000)
     ap.add_argument("--views", type=int, default=16)
     ap.add_argument("--size", type=int, default=1024)
-    ap.add_argument("--sdf", default="siren", choices=["siren", "sphere"])
+    ap.add_argument("--sdf", default="siren", choices=["siren", "opaque", "sphere"],
+                    help="siren: reference decoder structure (fused SDF kernel); opaque: same weights through autograd")
     ap.add_argument("--check", action="store_true")
     args = ap.parse_args()
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -87,7 +88,8 @@ def main():
     b, e = shard_range(args.points, rank, world)
     # every rank draws the same stream and keeps its slice: identical to a single-rank run
     x = ((torch.rand(args.points, 3, generator=g) - 0.5) * 2)[b:e].to(dev)[None]
-    net = (SirenSDF(seed=0) if args.sdf == "siren" else SphereSDF()).to(dev)
+    net = {"siren": lambda: Siren(256, 7, 30.0, seed=0), "opaque": lambda: SirenSDF(seed=0),
+           "sphere": SphereSDF}[args.sdf]().to(dev)
     proj = ShardedUniformProjection(proj_max_iters=10, proj_tolerance=5e-5, knn_k=8, sample_iters=1)
     gg = torch.Generator().manual_seed(9)
     occ_grads = [(torch.randn(S, S, generator=gg) * (torch.rand(S, S, generator=gg) < 0.1)).to(dev) for _ in range(V)]

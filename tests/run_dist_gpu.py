@@ -16,7 +16,7 @@ import torch.distributed as dist
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from isopoints_b200.dist import ShardedUniformProjection, all_gather_varlen, shard_range  # noqa: E402
 from isopoints_b200.levelset_sampling import UniformProjection  # noqa: E402
-from tests.helpers import SphereSDF, TinySiren  # noqa: E402
+from tests.helpers import Siren, SphereSDF, TinySiren  # noqa: E402
 
 
 def main():
@@ -26,7 +26,8 @@ def main():
     dist.init_process_group("nccl", device_id=dev)
     rank, world = dist.get_rank(), dist.get_world_size()
     ok = True
-    for name, net, n in (("sphere", SphereSDF(), 40_000), ("siren", TinySiren(seed=4), 30_001)):
+    for name, net, n in (("sphere", SphereSDF(), 40_000), ("siren", TinySiren(seed=4), 30_001),
+                         ("fused_siren", Siren(256, 2, 30.0, seed=6), 20_003)):
         g = torch.Generator().manual_seed(11)
         x = ((torch.rand(1, n, 3, generator=g) - 0.5) * 1.6).to(dev)
         net = net.to(dev)
