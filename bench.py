@@ -46,6 +46,8 @@ def _ncu_traffic(capture):
     return _ncu(capture).get("dram_bytes_per_launch")
 
 C2_POINTS = 200_000
+C2_WORKLOAD = ("C2: 200000 pts/GPU, random-init SIREN 8x256 SDF, project(10 it)+resample(knn_k=8, 1 it)+"
+               "reproject(3 it)")
 L2_FLUSH_BYTES = 256 << 20
 
 
@@ -242,7 +244,7 @@ def run_ours(args):
     d2h = sum(t.numel() * t.element_size() for t in res)
 
     peaks, peak_src = _peaks()
-    sd = kern.get("siren_sdf_grad")
+    sd = kern.get("siren_project_step") or kern.get("siren_sdf_grad")
     q = kern.get("frnn_find_nbrs")
     roof = None
     frnn_roof = None
@@ -279,11 +281,9 @@ def run_ours(args):
         "metric": "iso-points/sec (project+resample)", "value": C2_POINTS * world / (ms * 1e-3), "unit": "points/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "C2: 200000 pts/GPU, random-init SIREN 8x256 SDF (%s), project(10 it)+"
-                               "resample(knn_k=8, 1 it)+reproject(3 it)" % (
-                                   "fused tcgen05 kernel, fp32-equivalent via fp16 hi/lo split" if sd else
-                                   "opaque nn.Module through autograd, fp32, TF32 off"),
-                   "points_per_gpu": C2_POINTS, "sdf": args.sdf,
+        "config": {"workload": C2_WORKLOAD, "points_per_gpu": C2_POINTS, "sdf": args.sdf,
+                   "sdf_eval": ("fused tcgen05 kernel, fp32-equivalent via fp16 hi/lo split" if sd else
+                                "opaque nn.Module through autograd, fp32, TF32 off"),
                    "l2": "flushed between steps (256 MiB write)", "converged_frac": converged,
                    "points_after_filter": n_out, "parallelism": "point-sharded x%d" % world},
         "e2e": {"value": C2_POINTS * world / (e2e_ms * 1e-3), "unit": "points/s", "h2d_bytes_per_step": h2d,
@@ -378,7 +378,9 @@ def run_reference(args):
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": args.cpu_sample / v * 1e3, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "C2 (bounded sample of %d points per step)" % args.cpu_sample},
+            "config": {"workload": C2_WORKLOAD, "points_per_gpu": C2_POINTS,
+                       "sample": "each step = the first %d of the 200000 C2 points (bounded CPU sample), same SIREN, "
+                                 "torch-CPU fp32 autograd SDF" % args.cpu_sample},
             "cpu_baseline": base,
             "e2e": {"value": v, "unit": "points/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))

@@ -106,6 +106,16 @@ int isob200_siren_sdf_grad(const float* x, int n_max, const int* n_dev, const vo
                            float* sdf, float* grad, void* scratch, size_t scratch_bytes, float* dbg,
                            int dbg_gemm, void* stream);
 
+/* sdf_grad + project_step in one kernel (one Newton iteration, levelset_sampling.py:313-342, for the
+ * fused decoder): x = positions of the active rows (points[act_in], compacted), arguments as in
+ * isob200_project_step; *count_out must be zero before the call; act_out / next_points are appended
+ * per 128-row tile in completion order (rows are independent: results identical). */
+int isob200_siren_project_step(const float* x, int n_max, const int* n_dev, const void* blob, int n_hidden,
+                               void* scratch, size_t scratch_bytes, float* points, float* normals,
+                               unsigned char* not_converged, const int* act_in, float tol, float max_step,
+                               int do_update, int* act_out, float* next_points, int* count_out,
+                               void* stream);
+
 /* ---- uniform resampling: UniformProjection.resample, one sample_iter
  *      (DSS/models/levelset_sampling.py:259, 268-284) ------------------------------------ */
 int isob200_resample_step(const float* q_points, const float* points, const float* normals,

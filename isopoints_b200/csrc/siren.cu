@@ -94,7 +94,8 @@ constexpr int SM_XCH = SM_STAGE + STAGES * STAGE_BYTES;     // 229376: float xch
 constexpr int SM_BAR = SM_XCH + TM * 4 * 4;                 // 231424
 // barriers: a_ready[8], acc_full[2], w_full[3], w_empty[3]  -> 16 * 8 B
 constexpr int SM_TMEM_PTR = SM_BAR + 16 * 8;
-constexpr int SMEM_BYTES = SM_TMEM_PTR + 16;                // 231568 <= 232448
+constexpr int SM_CMP = SM_TMEM_PTR + 16;                    // int cmp[8]: warp counts + reserved base
+constexpr int SMEM_BYTES = SM_CMP + 32;                     // 231600 <= 232448
 
 // ---- PTX helpers -----------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -338,6 +339,28 @@ __global__ void siren_pack_kernel(const float* __restrict__ w0, const float* __r
 // ---------------------------------------------------------------------------------------------
 // main kernel
 // ---------------------------------------------------------------------------------------------
+// Optional fused Newton step (UniformProjection._project_points, levelset_sampling.py:313-342): when
+// `points` is non-null the thread that ends up holding a row's sdf and gradient also applies the update
+// of csrc/project.cu's project_step_kernel (same fp32 operation order) and appends still-active rows to
+// the next iteration's active list -- the SDF value and gradient never leave the SM.
+struct Newton {
+  float* points;             // (M,3) packed positions, updated in place at the active rows
+  float* normals;            // (M,3) last gradient
+  unsigned char* not_conv;   // (M) flags
+  const int* act_in;         // active row ids of this launch (NULL = identity)
+  int* act_out;              // still-active row ids (tiles append in completion order)
+  float* next_points;        // their updated positions, same order (NULL on the last evaluation)
+  int* count_out;            // number of still-active rows (zero before the launch)
+  float tol, max_step;
+  int do_update;
+};
+
+// eps_denom(x, eps) of DSS/utils/mathHelper.py:14-18: (sign(x) + [x == 0]) * max(|x|, eps)
+__device__ __forceinline__ float eps_denom_f(float x, float eps) {
+  const float sgn = (x > 0.f) ? 1.f : ((x < 0.f) ? -1.f : 1.f);
+  return __fmul_rn(sgn, fmaxf(fabsf(x), eps));
+}
+
 // MMA k-block visiting order = the order in which the epilogue completes them.
 __device__ __forceinline__ int kb_order(int i) { return i; }
 
@@ -345,7 +368,7 @@ __global__ void __launch_bounds__(THREADS, 1)
 siren_sdf_grad_kernel(const float* __restrict__ x, int n_max, const int* __restrict__ n_dev,
                       const unsigned char* __restrict__ blob, int L, float* __restrict__ sdf_out,
                       float* __restrict__ grad_out, float* __restrict__ scratch, float* __restrict__ dbg,
-                      int dbg_gemm) {
+                      int dbg_gemm, const Newton nw) {
   extern __shared__ __align__(1024) unsigned char smem[];
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -521,6 +544,7 @@ siren_sdf_grad_kernel(const float* __restrict__ x, int n_max, const int* __restr
       }
 
       float row_scale_inv = 1.f;  // inverse of the scale applied to this row of the current backward A
+      float sdf_row = 0.f;        // this row's sdf (slice-0 thread), kept for the fused Newton step
       for (int g = 0; g < n_gemm; ++g, ++G) {
         const uint32_t buf = G & 1;
         long long* tstamp =
@@ -633,8 +657,10 @@ siren_sdf_grad_kernel(const float* __restrict__ x, int n_max, const int* __restr
           row_scale_inv = gl_scale_inv;
           if (cslice) xch[row * 4 + cslice] = acc_sdf;
           row_barrier(q);
-          if (cslice == 0 && grow < n)
-            sdf_out[grow] = ((acc_sdf + xch[row * 4 + 1]) + (xch[row * 4 + 2] + xch[row * 4 + 3])) + b_last;
+          if (cslice == 0) {
+            sdf_row = ((acc_sdf + xch[row * 4 + 1]) + (xch[row * 4 + 2] + xch[row * 4 + 3])) + b_last;
+            if (grow < n && sdf_out) sdf_out[grow] = sdf_row;
+          }
           row_barrier(q);
         } else if (l > 1) {
           // ---- E_b(l): g_{l-1} = acc / scales ; gp_{l-1} = g_{l-1} * c_{l-1} -> A (row-scaled) ----
@@ -723,15 +749,72 @@ siren_sdf_grad_kernel(const float* __restrict__ x, int n_max, const int* __restr
           tc_fence_before();
           if (cslice) *reinterpret_cast<float4*>(gsc + (cslice - 1) * A_LBO) = make_float4(gx, gy, gz, 0.f);
           row_barrier(q);
-          if (cslice == 0 && grow < n) {
+          float fgx = 0.f, fgy = 0.f, fgz = 0.f;
+          if (cslice == 0) {
             const float4 d0 = *reinterpret_cast<const float4*>(gsc);
             const float4 d1 = *reinterpret_cast<const float4*>(gsc + A_LBO);
             const float4 d2 = *reinterpret_cast<const float4*>(gsc + 2 * A_LBO);
-            grad_out[3 * (size_t)grow] = (gx + d0.x) + (d1.x + d2.x);
-            grad_out[3 * (size_t)grow + 1] = (gy + d0.y) + (d1.y + d2.y);
-            grad_out[3 * (size_t)grow + 2] = (gz + d0.z) + (d1.z + d2.z);
+            fgx = (gx + d0.x) + (d1.x + d2.x);
+            fgy = (gy + d0.y) + (d1.y + d2.y);
+            fgz = (gz + d0.z) + (d1.z + d2.z);
+            if (grow < n && grad_out) {
+              grad_out[3 * (size_t)grow] = fgx;
+              grad_out[3 * (size_t)grow + 1] = fgy;
+              grad_out[3 * (size_t)grow + 2] = fgz;
+            }
           }
           row_barrier(q);
+          if (nw.points && cslice == 0) {
+            // ---- fused Newton step on this row (warps 0..3 hold the tile's 128 rows) ----
+            int* cmp = reinterpret_cast<int*>(smem + SM_CMP);
+            bool still = false;
+            int p = 0;
+            float nx = 0.f, ny = 0.f, nz = 0.f;
+            if (grow < n) {
+              p = nw.act_in ? nw.act_in[grow] : grow;
+              nw.normals[3 * (size_t)p] = fgx;
+              nw.normals[3 * (size_t)p + 1] = fgy;
+              nw.normals[3 * (size_t)p + 2] = fgz;
+              still = fabsf(sdf_row) > nw.tol;
+              nw.not_conv[p] = still ? 1 : 0;
+              if (still) {
+                nx = px; ny = py; nz = pz;   // the evaluated position IS points[p]
+                if (nw.do_update) {
+                  const float ss = __fadd_rn(__fadd_rn(__fmul_rn(fgx, fgx), __fmul_rn(fgy, fgy)), __fmul_rn(fgz, fgz));
+                  const float den = eps_denom_f(ss, 1.0e-17f);
+                  const float mx = __fmul_rn(sdf_row, __fdiv_rn(fgx, den));
+                  const float my = __fmul_rn(sdf_row, __fdiv_rn(fgy, den));
+                  const float mz = __fmul_rn(sdf_row, __fdiv_rn(fgz, den));
+                  const float nrm = sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(mx, mx), __fmul_rn(my, my)), __fmul_rn(mz, mz)));
+                  const float dn = fmaxf(nrm, 1e-15f);           // F.normalize(eps=1e-15)
+                  const float len = fminf(nrm, nw.max_step);     // clamp_max(0.1)
+                  nx = __fsub_rn(nx, __fmul_rn(__fdiv_rn(mx, dn), len));
+                  ny = __fsub_rn(ny, __fmul_rn(__fdiv_rn(my, dn), len));
+                  nz = __fsub_rn(nz, __fmul_rn(__fdiv_rn(mz, dn), len));
+                  nw.points[3 * (size_t)p] = nx;
+                  nw.points[3 * (size_t)p + 1] = ny;
+                  nw.points[3 * (size_t)p + 2] = nz;
+                }
+              }
+            }
+            // append the still-active rows: in-tile order, one reservation per tile
+            const unsigned bal = __ballot_sync(0xffffffffu, still);
+            if (lane == 0) cmp[q] = __popc(bal);
+            asm volatile("bar.sync 5, 128;" ::: "memory");
+            const int c0 = cmp[0], c1 = cmp[1], c2 = cmp[2], c3 = cmp[3];
+            if (threadIdx.x == 0) cmp[4] = (c0 + c1 + c2 + c3) ? atomicAdd(nw.count_out, c0 + c1 + c2 + c3) : 0;
+            asm volatile("bar.sync 5, 128;" ::: "memory");
+            if (still) {
+              const int pos = cmp[4] + (q > 0 ? c0 : 0) + (q > 1 ? c1 : 0) + (q > 2 ? c2 : 0) +
+                              __popc(bal & ((1u << lane) - 1u));
+              nw.act_out[pos] = p;
+              if (nw.next_points) {
+                nw.next_points[3 * (size_t)pos] = nx;
+                nw.next_points[3 * (size_t)pos + 1] = ny;
+                nw.next_points[3 * (size_t)pos + 2] = nz;
+              }
+            }
+          }
         }
         if (tstamp) tstamp[2] = clock64();
       }
@@ -785,28 +868,49 @@ int isob200_siren_pack(const float* w0, const float* b0, const float* w_hidden, 
   return ISOB200_OK;
 }
 
-int isob200_siren_sdf_grad(const float* x, int n_max, const int* n_dev, const void* blob, int n_hidden, float* sdf,
-                           float* grad, void* scratch, size_t scratch_bytes, float* dbg, int dbg_gemm,
-                           void* stream) {
-  ISO_CHECK_ARG(n_hidden >= 1 && n_hidden <= MAX_LAYERS, "siren_sdf_grad: n_hidden must be in [1, %d]", MAX_LAYERS);
-  ISO_CHECK_ARG(n_max >= 0, "siren_sdf_grad: negative point count");
+static int launch_siren(const float* x, int n_max, const int* n_dev, const void* blob, int n_hidden, float* sdf,
+                        float* grad, void* scratch, size_t scratch_bytes, float* dbg, int dbg_gemm,
+                        const Newton& nw, void* stream, const char* who) {
+  ISO_CHECK_ARG(n_hidden >= 1 && n_hidden <= MAX_LAYERS, "%s: n_hidden must be in [1, %d]", who, MAX_LAYERS);
+  ISO_CHECK_ARG(n_max >= 0, "%s: negative point count", who);
   if (n_max == 0) return ISOB200_OK;
-  ISO_CHECK_ARG(x && blob && sdf && grad && scratch, "siren_sdf_grad: null pointer");
+  ISO_CHECK_ARG(x && blob && scratch, "%s: null pointer", who);
   if (scratch_bytes < isob200_siren_scratch_bytes(n_hidden)) {
-    set_error("siren_sdf_grad: scratch too small");
+    set_error("%s: scratch too small", who);
     return ISOB200_ERR_WORKSPACE;
   }
-  static bool attr_set = false;
-  if (!attr_set) {
-    ISO_CUDA(cudaFuncSetAttribute(siren_sdf_grad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-    attr_set = true;
-  }
+  ISO_CUDA(cudaFuncSetAttribute(siren_sdf_grad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
   int tiles = (n_max + TM - 1) / TM;
   int grid = tiles < kNumSMs ? tiles : kNumSMs;
   siren_sdf_grad_kernel<<<grid, THREADS, SMEM_BYTES, (cudaStream_t)stream>>>(
-      x, n_max, n_dev, (const unsigned char*)blob, n_hidden, sdf, grad, (float*)scratch, dbg, dbg_gemm);
+      x, n_max, n_dev, (const unsigned char*)blob, n_hidden, sdf, grad, (float*)scratch, dbg, dbg_gemm, nw);
   ISO_CHECK_LAUNCH("siren_sdf_grad_kernel");
   return ISOB200_OK;
+}
+
+int isob200_siren_sdf_grad(const float* x, int n_max, const int* n_dev, const void* blob, int n_hidden, float* sdf,
+                           float* grad, void* scratch, size_t scratch_bytes, float* dbg, int dbg_gemm,
+                           void* stream) {
+  ISO_CHECK_ARG(n_max == 0 || (sdf && grad), "siren_sdf_grad: null output");
+  Newton nw = {};
+  return launch_siren(x, n_max, n_dev, blob, n_hidden, sdf, grad, scratch, scratch_bytes, dbg, dbg_gemm, nw, stream,
+                      "siren_sdf_grad");
+}
+
+// One Newton iteration of _project_points with the SDF evaluation fused in: isob200_siren_sdf_grad at
+// x (the positions of the active rows) followed by isob200_project_step, in one kernel.  Differences
+// from that pair: act_out / next_points are appended per tile in completion order (rows are independent,
+// so the results are identical), and *count_out must be zero before the call.
+int isob200_siren_project_step(const float* x, int n_max, const int* n_dev, const void* blob, int n_hidden,
+                               void* scratch, size_t scratch_bytes, float* points, float* normals,
+                               unsigned char* not_converged, const int* act_in, float tol, float max_step,
+                               int do_update, int* act_out, float* next_points, int* count_out, void* stream) {
+  ISO_CHECK_ARG(n_max == 0 || (points && normals && not_converged && act_out && count_out),
+                "siren_project_step: null pointer");
+  ISO_CHECK_ARG(n_dev != count_out, "siren_project_step: n_dev must not alias count_out");
+  Newton nw = {points, normals, not_converged, act_in, act_out, next_points, count_out, tol, max_step, do_update};
+  return launch_siren(x, n_max, n_dev, blob, n_hidden, nullptr, nullptr, scratch, scratch_bytes, nullptr, -1, nw,
+                      stream, "siren_project_step");
 }
 
 }  // extern "C"

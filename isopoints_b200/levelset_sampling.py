@@ -45,8 +45,9 @@ def _filter_projection_result(result: ProjectionResult) -> ProjectionResult:
 
 
 def _filter_projection_result_counted(result: ProjectionResult):
-    """``_filter_projection_result`` plus the survivor counts as a host list, with ONE read-back for
-    both (the reference pays one in ``.any()`` and more inside the boolean-mask indexing)."""
+    """``_filter_projection_result`` plus the survivor counts as a host list and as a device int64
+    tensor, with ONE read-back for all of it (the reference pays one in ``.any()`` and more inside
+    the boolean-mask indexing)."""
     points, normals, mask = result
     if mask.shape[0] == 1 and points.is_cuda and points.dtype == torch.float32:
         # single cloud: one order-preserving compaction kernel; the count it leaves on the device is the
@@ -63,9 +64,9 @@ def _filter_projection_result_counted(result: ProjectionResult):
                                              _ext.ptr(out_n), _ext.ptr(count), _ext.ptr(ws), ws.numel(),
                                              _ext.stream(dev)))
         n = int(count.item())
-        return ProjectionResult(out_p[:n][None], out_n[:n][None], mask.new_ones((1, n))), [n]
-    counts = [int(c) for c in mask.sum(dim=-1).tolist()]
-    return _filter_projection_result(result), counts
+        return ProjectionResult(out_p[:n][None], out_n[:n][None], mask.new_ones((1, n))), [n], count.long()
+    num = mask.sum(dim=-1)
+    return _filter_projection_result(result), [int(c) for c in num.tolist()], num
 
 
 class LevelSetProjection(object):
@@ -201,31 +202,28 @@ class UniformProjection(LevelSetProjection):
                 float(proj_tolerance), 0.1, int(proj_max_iters), _ext.stream(dev)))
             valid_packed = valid_u8.bool()
         elif fused is not None:
-            # The reference's Siren decoder: SDF + gradient come from the fused tcgen05 kernel, which
-            # reads the live row count from device memory -- the whole loop is enqueued without a
-            # single read-back (the early exit of :329 becomes launches over an empty active set).
+            # The reference's Siren decoder: one kernel per Newton iteration -- fused tcgen05 SDF +
+            # gradient, the update of :333-342 and the compaction of the still-active rows -- reading
+            # the live row count from device memory: the whole loop is enqueued without a single
+            # read-back (the early exit of :329 becomes launches over an empty active set).
             act = (torch.empty((M,), dtype=torch.int32, device=dev), torch.empty((M,), dtype=torch.int32, device=dev))
             nxt = (torch.empty((M, 3), dtype=torch.float32, device=dev),
                    torch.empty((M, 3), dtype=torch.float32, device=dev))
             cnt = torch.zeros((proj_max_iters + 2,), dtype=torch.int32, device=dev)  # live rows entering iteration it
-            bufs = (torch.empty((M,), dtype=torch.float32, device=dev),
-                    torch.empty((M, 3), dtype=torch.float32, device=dev))
-            ws = _ext.workspace(lib.isob200_project_step_ws_bytes(M), dev)
             nc_u8 = not_converged.view(torch.uint8)
             st = _ext.stream(dev)
-            pk = siren.packed(model, fused)   # operand images for the current parameter version
+            blob, scratch, n_hidden = siren.packed(model, fused)   # operand images, current parameter version
             for it in range(proj_max_iters + 1):
                 last = (it == proj_max_iters)
-                a_dev = None if it == 0 else cnt[it:]
-                c_out = cnt[it + 1:]
                 cur = points_packed if it == 0 else nxt[it & 1]
-                siren.sdf_and_grad(model, cur, n_dev=a_dev, spec=fused, out=bufs, pk=pk)
-                _ext.check(lib.isob200_project_step(
-                    _ext.ptr(points_packed), _ext.ptr(normals_packed), _ext.ptr(nc_u8),
-                    None if it == 0 else _ext.ptr(act[it & 1]), M, _ext.ptr(a_dev), _ext.ptr(bufs[0]),
-                    _ext.ptr(bufs[1]), float(proj_tolerance), 0.1, 0 if last else 1,
-                    _ext.ptr(act[(it + 1) & 1]), None if last else _ext.ptr(nxt[(it + 1) & 1]), _ext.ptr(c_out),
-                    _ext.ptr(ws), ws.numel(), st))
+                _ext.check(lib.isob200_siren_project_step(
+                    _ext.ptr(cur), M, None if it == 0 else _ext.ptr(cnt[it:]), _ext.ptr(blob), n_hidden,
+                    _ext.ptr(scratch), scratch.numel(), _ext.ptr(points_packed), _ext.ptr(normals_packed),
+                    _ext.ptr(nc_u8), None if it == 0 else _ext.ptr(act[it & 1]), float(proj_tolerance), 0.1,
+                    0 if last else 1, _ext.ptr(act[(it + 1) & 1]),
+                    None if last else _ext.ptr(nxt[(it + 1) & 1]), _ext.ptr(cnt[it + 1:]), st))
+            siren.STATS["calls"] += proj_max_iters + 1
+            siren.STATS["rows"] += M
             if siren.RECORD is not None:   # bench.py: live row counts, resolved after the timed region
                 siren.RECORD.append((M, cnt))
             valid_packed = ~not_converged
@@ -406,12 +404,11 @@ class UniformProjection(LevelSetProjection):
                     return {'levelset_points': points_projected, 'mask': valid_projection}
             else:
                 unfiltered = (points_projected, valid_projection)
-                (points_projected, normals_projected, valid_projection), counts = \
+                (points_projected, normals_projected, valid_projection), counts, num_points = \
                     _filter_projection_result_counted(
                         ProjectionResult(points_projected, normals_projected, valid_projection))
                 if sum(counts) == 0:   # nothing converged (:396-399)
                     return {'levelset_points': unfiltered[0], 'mask': unfiltered[1]}
-                num_points = torch.as_tensor(counts, dtype=torch.int64, device=points_projected.device)
                 points_projected, normals_projected, valid_projection = self.resample(
                     model, points_projected, normals_projected, num_points, sample_iters=sample_iters,
                     num_points_list=counts, **forward_kwargs)

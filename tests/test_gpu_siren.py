@@ -168,3 +168,53 @@ def test_project_resample_and_ragged_batch_with_fused_sdf():
     dd = (ra.points - rb.points).abs().max(dim=-1).values[both]
     assert dd.median().item() < 2e-6 and dd.quantile(0.99).item() < 1e-4
     assert not ra.mask[1, 900:].any() and (ra.points[1, 900:] == 0).all()
+
+
+def test_fused_newton_iteration_equals_sdf_grad_plus_project_step():
+    """isob200_siren_project_step == isob200_siren_sdf_grad followed by isob200_project_step: same
+    positions / normals / flags bit for bit, the same SET of still-active rows (tiles append in
+    completion order) with matching compacted positions."""
+    from isopoints_b200 import _ext
+    lib = _ext.lib()
+    model = Siren(256, 3, 30.0, seed=9).to(DEV)
+    spec = siren.match(model)
+    blob, scratch, L = siren.packed(model, spec)
+    torch.manual_seed(3)
+    M = 20000
+    pts0 = ((torch.rand(M, 3) - 0.5) * 2).to(DEV)
+    st = _ext.stream(torch.device(DEV))
+    tol = 5e-5
+
+    def fused(points):
+        normals = torch.zeros_like(points)
+        nc = torch.ones(M, dtype=torch.uint8, device=DEV)
+        act = torch.full((M,), -1, dtype=torch.int32, device=DEV)
+        nxt = torch.zeros((M, 3), device=DEV)
+        cnt = torch.zeros(1, dtype=torch.int32, device=DEV)
+        _ext.check(lib.isob200_siren_project_step(
+            _ext.ptr(points), M, None, _ext.ptr(blob), L, _ext.ptr(scratch), scratch.numel(), _ext.ptr(points),
+            _ext.ptr(normals), _ext.ptr(nc), None, tol, 0.1, 1, _ext.ptr(act), _ext.ptr(nxt), _ext.ptr(cnt), st))
+        return normals, nc, act, nxt, int(cnt.item())
+
+    def split(points):
+        sdf, grad = siren.sdf_and_grad(model, points.clone())
+        normals = torch.zeros_like(points)
+        nc = torch.ones(M, dtype=torch.uint8, device=DEV)
+        act = torch.full((M,), -1, dtype=torch.int32, device=DEV)
+        nxt = torch.zeros((M, 3), device=DEV)
+        cnt = torch.zeros(1, dtype=torch.int32, device=DEV)
+        ws = _ext.workspace(lib.isob200_project_step_ws_bytes(M), torch.device(DEV))
+        _ext.check(lib.isob200_project_step(
+            _ext.ptr(points), _ext.ptr(normals), _ext.ptr(nc), None, M, None, _ext.ptr(sdf), _ext.ptr(grad), tol, 0.1, 1,
+            _ext.ptr(act), _ext.ptr(nxt), _ext.ptr(cnt), _ext.ptr(ws), ws.numel(), st))
+        return normals, nc, act, nxt, int(cnt.item())
+
+    pa, pb = pts0.clone(), pts0.clone()
+    na, fa, aa, xa, ca = fused(pa)
+    nb, fb, ab, xb, cb = split(pb)
+    assert ca == cb and 0 < ca < M
+    assert torch.equal(pa, pb) and torch.equal(na, nb) and torch.equal(fa, fb)
+    oa, ob = torch.argsort(aa[:ca]), torch.argsort(ab[:cb])
+    assert torch.equal(aa[:ca][oa], ab[:cb][ob])                  # same active rows
+    assert torch.equal(xa[:ca][oa], xb[:cb][ob])                  # with the same updated positions
+    assert torch.equal(xa[:ca], pa[aa[:ca].long()])               # next_points == points[act_out]
