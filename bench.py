@@ -4,7 +4,9 @@
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
 
 Workload (BASELINE.json configs[1], "C2"): 200 000 points per GPU, (rand-0.5)*2, random-init
-8-layer x 256 SIREN SDF, UniformProjection(proj_max_iters=10, tol=5e-5, knn_k=8, sample_iters=1)
+8-layer x 256 SIREN SDF in the reference decoder's structure (--sdf siren, default: evaluated by the
+package's fused tcgen05 kernel; --sdf opaque: the same weights behind an opaque nn.Module, i.e. the
+autograd callback), UniformProjection(proj_max_iters=10, tol=5e-5, knn_k=8, sample_iters=1)
 .project_points(x, sdf, skip_upsampling=True)  = project -> filter -> FRNN(K=9) -> resample ->
 3-iteration re-projection.  A "step" is one such pass over one synthetic cloud.
   value : input iso-points / second, whole job, inputs resident in HBM, CUDA-event timed;
