@@ -132,8 +132,19 @@ def _pack(spec):
     return blob, scratch, L
 
 
+def invalidate(model=None):
+    """Drop the packed operand images of ``model`` (all models if None).  Only needed after a parameter
+    was modified behind autograd's back (``p.data.mul_(...)`` does not bump ``p._version``); optimizer
+    steps, ``load_state_dict`` and any in-place op on the parameter itself are detected."""
+    if model is None:
+        _CACHE.clear()
+    else:
+        _CACHE.pop(model, None)
+
+
 def packed(model, spec):
-    """(blob, scratch, L) for the current parameter values; re-packed when any parameter changed."""
+    """(blob, scratch, L) for the current parameter values; re-packed when any parameter changed
+    (storage pointer or autograd version counter, see ``invalidate``)."""
     key = _version_key(spec)
     ent = _CACHE.get(model)
     if ent is None or ent[0] != key:
