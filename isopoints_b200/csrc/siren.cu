@@ -747,6 +747,11 @@ siren_sdf_grad_kernel(const float* __restrict__ x, int n_max, const int* __restr
           }
           const float gx = gx2.x + gx2.y, gy = gy2.x + gy2.y, gz = gz2.x + gz2.y;
           tc_fence_before();
+          // The slot was last written as an A chunk by another warp of this row group two stages ago; that
+          // write is ordered before this one through the a_ready / acc_full mbarrier chain (the GEMM that
+          // consumed it has completed).  The extra bar.sync only restates that ordering in a form
+          // compute-sanitizer's racecheck tracks (~100 cycles per tile).
+          row_barrier(q);
           if (cslice) *reinterpret_cast<float4*>(gsc + (cslice - 1) * A_LBO) = make_float4(gx, gy, gz, 0.f);
           row_barrier(q);
           float fgx = 0.f, fgy = 0.f, fgz = 0.f;

@@ -18,7 +18,8 @@ if [ "${1:-}" = "prof" ]; then
   timeout 600 ncu --set full --clock-control none --import-source on -k regex:frnn_query -s 3 -c 1 -f -o gpurun_out/prof_frnn_query python bench_frnn.py --steps 1 > gpurun_out/ncu_frnn.log 2>&1
   timeout 600 ncu --set full --clock-control none --import-source on -k regex:splat_raster_v2_kernel -s 3 -c 1 -f -o gpurun_out/prof_splat_raster python bench_splat.py --steps 1 > gpurun_out/ncu_raster.log 2>&1
   timeout 600 ncu --set full --clock-control none --import-source on -k regex:splat_occ_backward_hybrid_kernel -s 3 -c 1 -f -o gpurun_out/prof_splat_occ_bwd python bench_splat.py --steps 1 > gpurun_out/ncu_occ.log 2>&1
-  timeout 900 compute-sanitizer --tool memcheck --error-exitcode 7 python -m pytest tests/test_gpu_splat.py tests/test_gpu_frnn.py tests/test_gpu_projection.py -m gpu -q -k "not 500k and not c4_scale and not c2_scale and not world1" > gpurun_out/sanitizer_memcheck.log 2>&1; echo "memcheck rc=$?"; tail -3 gpurun_out/sanitizer_memcheck.log
+  timeout 900 compute-sanitizer --tool memcheck --error-exitcode 7 python -m pytest tests/test_gpu_splat.py tests/test_gpu_frnn.py tests/test_gpu_projection.py tests/test_gpu_siren.py -m gpu -q -k "not 500k and not c4_scale and not c2_scale and not world1 and not match_fp64 and not projection_with_fused and not project_resample_and_ragged" > gpurun_out/sanitizer_memcheck.log 2>&1; echo "memcheck rc=$?"; tail -3 gpurun_out/sanitizer_memcheck.log
   timeout 900 compute-sanitizer --tool racecheck --error-exitcode 7 python -m pytest tests/test_gpu_splat.py -m gpu -q -k "bit_exact_vs_oracle or backward_matches_oracle or blend" > gpurun_out/sanitizer_racecheck.log 2>&1; echo "racecheck rc=$?"; tail -3 gpurun_out/sanitizer_racecheck.log
+  timeout 600 compute-sanitizer --tool racecheck --error-exitcode 7 python -m pytest tests/test_gpu_siren.py -m gpu -q -k "layer_counts or fused_newton" > gpurun_out/sanitizer_racecheck_siren.log 2>&1; echo "racecheck(siren) rc=$?"; tail -1 gpurun_out/sanitizer_racecheck_siren.log
   ls gpurun_out/
 fi
