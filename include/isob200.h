@@ -116,6 +116,10 @@ int isob200_siren_project_step(const float* x, int n_max, const int* n_dev, cons
                                int do_update, int* act_out, float* next_points, int* count_out,
                                void* stream);
 
+/* Bring-up probe of the 2-CTA tensor-core path (tcgen05 cta_group::2, M = 128 across a CTA pair): one
+ * (128 x K) x (256 x K)^T fp16 GEMM, dump (2,128,128) = raw TMEM of both CTAs.  Test-only. */
+int isob200_umma2_probe(const float* a, const float* b, int K, float* dump, void* stream);
+
 /* ---- uniform resampling: UniformProjection.resample, one sample_iter
  *      (DSS/models/levelset_sampling.py:259, 268-284) ------------------------------------ */
 int isob200_resample_step(const float* q_points, const float* points, const float* normals,

@@ -218,3 +218,23 @@ def test_fused_newton_iteration_equals_sdf_grad_plus_project_step():
     assert torch.equal(aa[:ca][oa], ab[:cb][ob])                  # same active rows
     assert torch.equal(xa[:ca][oa], xb[:cb][ob])                  # with the same updated positions
     assert torch.equal(xa[:ca], pa[aa[:ca].long()])               # next_points == points[act_out]
+
+
+def test_two_cta_mma_probe():
+    """tcgen05 cta_group::2 bring-up probe (csrc/umma2_probe.cu): a 128 x 256 x K fp16 GEMM on a CTA
+    pair; pins the accumulator layout the paired kernel design relies on (lane = row + 64 * (col >= 128),
+    TMEM column = col % 128, 64 rows per CTA)."""
+    from isopoints_b200 import _ext
+    lib = _ext.lib()
+    dev = torch.device(DEV)
+    for K in (16, 32, 64):
+        torch.manual_seed(K)
+        A, B = torch.randn(128, K, device=dev), torch.randn(256, K, device=dev)
+        dump = torch.full((2, 128, 128), float("nan"), device=dev)
+        _ext.check(lib.isob200_umma2_probe(_ext.ptr(A), _ext.ptr(B), K, _ext.ptr(dump), _ext.stream(dev)))
+        ref = A.half().float() @ B.half().float().t()
+        got = torch.empty_like(ref)
+        for r in range(2):
+            got[64 * r:64 * r + 64, :128] = dump[r, :64]
+            got[64 * r:64 * r + 64, 128:] = dump[r, 64:]
+        assert (got - ref).abs().max().item() < 1e-3 * ref.abs().max().item()
