@@ -95,6 +95,10 @@ int isob200_project_sphere(float* points, float* normals, unsigned char* valid, 
  *      non-NULL, is a device int with the live row count (<= n_max) so a projection loop can
  *      run without reading the active count back.  dbg (NULL in production) receives the raw
  *      (128,256) accumulator of the first tile's GEMM number dbg_gemm (parity tests). ------- */
+/* kernel variant behind the siren entry points: 0 = one CTA per 128-row tile, 1 = CTA pairs (tcgen05
+ * cta_group::2, two tiles in flight per pair); identical results.  Returns the previous setting. */
+int isob200_siren_set_pair_mode(int on);
+int isob200_siren_pair_stamps(long long* out_host, int n); /* tuning aid: cycle stamps of pair 0 (host buffer) */
 size_t isob200_siren_blob_bytes(int n_hidden);
 size_t isob200_siren_pack_ws_bytes(void);
 size_t isob200_siren_scratch_bytes(int n_hidden);
