@@ -220,15 +220,17 @@ siren_sdf_grad_kernel(const float* __restrict__ x, int n_max, const int* __restr
             int kb = kb_order(i);
             uint32_t s = it % STAGES;
             uint32_t ph = (it / STAGES) & 1;
+            // weights first: they are normally in place already, and a completed try_wait still costs ~180
+            // cycles -- this keeps it off the path between the epilogue's hand-off and the MMA issue
             long long t0 = tstamp ? clock64() : 0;
-            mbar_wait(bar_a_ready + 8 * kb, G & 1);
-            long long t1 = tstamp ? clock64() : 0;
             mbar_wait(bar_w_full + 8 * s, ph);
+            long long t1 = tstamp ? clock64() : 0;
+            mbar_wait(bar_a_ready + 8 * kb, G & 1);
             if (tstamp) {
               long long t2 = clock64();
-              wa += t1 - t0;
-              ww += t2 - t1;
-              if (i == 0) t_first = t1;
+              ww += t1 - t0;
+              wa += t2 - t1;
+              if (i == 0) t_first = t2;
             }
             tc_fence_after();
             const uint32_t a_hi = sbase + SM_A_HI + kb * (KB / 8) * A_LBO;
