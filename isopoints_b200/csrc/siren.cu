@@ -675,7 +675,16 @@ static int launch_siren(const float* x, int n_max, const int* n_dev, const void*
   }
   if (g_siren_pair_mode && !dbg)
     return launch_siren_pair(x, n_max, n_dev, blob, n_hidden, sdf, grad, scratch, nw, (cudaStream_t)stream);
-  ISO_CUDA(cudaFuncSetAttribute(siren_sdf_grad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+  {
+    // opt-in to > 48 KB of dynamic shared memory: once per device
+    static bool attr_done[64] = {};
+    int dev = 0;
+    ISO_CUDA(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64 || !attr_done[dev]) {
+      ISO_CUDA(cudaFuncSetAttribute(siren_sdf_grad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+      if (dev >= 0 && dev < 64) attr_done[dev] = true;
+    }
+  }
   int tiles = (n_max + TM - 1) / TM;
   int grid = tiles < kNumSMs ? tiles : kNumSMs;
   siren_sdf_grad_kernel<<<grid, THREADS, SMEM_BYTES, (cudaStream_t)stream>>>(
