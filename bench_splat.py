@@ -50,7 +50,7 @@ def run(args, dev, peaks, peak_src, steps=None):
 
     def fwd(tt, pts):
         return splat.EllipticalRasterizer.apply(pts, tt["ellipse"], tt["cutoff"], tt["radii"], tt["first_idx"],
-                                                tt["num_points"], 0.05, S, K, 32, 0, 10.0)
+                                                tt["num_points"], 0.05, S, K, 32 if S <= 512 else 64, 0, 10.0)
 
     def fwd_bwd(tt):
         pts = tt["points"].detach().requires_grad_(True)
