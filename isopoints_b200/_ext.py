@@ -51,6 +51,7 @@ _PROTOS = {
     "isob200_siren_project_step": (_i, [_vp, _i, _vp, _vp, _i, _vp, _sz, _vp, _vp, _vp, _vp, _f, _f, _i, _vp, _vp,
                                         _vp, _vp]),
     "isob200_umma2_probe": (_i, [_vp, _vp, _i, _vp, _vp]),
+    "isob200_umma_rate": (_i, [_i, _i, _vp, _vp]),
     "isob200_resample_step": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _vp, _i, _i, _i, _i, _vp, _vp]),
     "isob200_normalize_rows3": (_i, [_vp, _ll, _f, _vp, _vp]),
     "isob200_wlop_density": (_i, [_vp, _vp, _i, _i, _vp, _i, _i, _i, _vp, _vp]),

@@ -136,8 +136,85 @@ umma2_probe_kernel(const float* __restrict__ A, const float* __restrict__ B, int
     asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256) : "memory");
 }
 
+// Issue-rate microbenchmark: `reps` back-to-back K = 16 MMAs of one shape on (garbage) shared-memory
+// operands, cycles from the first issue to the completion of the commit.  mode 0: cta_group::1, M = 128;
+// mode 1: cta_group::2, M = 128 (64 rows per CTA); mode 2: cta_group::2, M = 256 (128 rows per CTA).  N = 256.
+// mode + 10: the same shapes with 128-byte-swizzled K-major operands (rows of 128 B, 8-row atoms of 1 KB)
+// instead of the no-swizzle core-matrix layout the SIREN kernels use.
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128)
+umma_rate_kernel(int mode_in, int reps, long long* __restrict__ cycles) {
+  __shared__ __align__(1024) unsigned char sB[256 * 128];   // 256 rows x up to 128 B (contents irrelevant:
+  unsigned char* sA = sB;                                    //  A reads the same buffer)
+  const bool sw128 = mode_in >= 10;
+  const int mode = mode_in % 10;
+  __shared__ __align__(8) unsigned long long bars[1];
+  __shared__ uint32_t tmem_ptr;
+  const uint32_t rank = cluster_rank();
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const uint32_t bar_done = smem_u32(&bars[0]);
+  for (int i = tid; i < 256 * 128 / 4; i += 128) reinterpret_cast<uint32_t*>(sB)[i] = 0x3c003c00u;
+  if (tid == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar_done), "r"(1));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  cluster_sync();
+  if (warp == 0) {
+    if (mode == 0) {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_ptr)), "r"(256) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_ptr)), "r"(256) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  cluster_sync();
+  const uint32_t tmem_base = tmem_ptr;
+  const bool issuer = tid == 32 && (mode == 0 || rank == 0);
+  long long t0 = 0;
+  if (issuer) {
+    const int a_rows = mode == 1 ? 64 : 128, b_rows = mode == 0 ? 256 : 128;
+    const uint32_t m = mode == 2 ? 256 : 128;
+    const uint32_t idesc = (1u << 4) | ((uint32_t)(256 >> 3) << 17) | ((m >> 4) << 24);
+    // SW128 K-major: SBO = 1024 (8 rows x 128 B), LBO unused, layout type 2 in bits 61..63
+    const uint64_t sw = (uint64_t)((1024 >> 4)) << 32 | (1ull << 16) | (1ull << 46) | (2ull << 61);
+    const uint64_t da = sw128 ? (sw | ((smem_u32(sA) >> 4) & 0x3FFF)) : make_desc(smem_u32(sA), a_rows * 16);
+    const uint64_t db = sw128 ? (sw | ((smem_u32(sB) >> 4) & 0x3FFF)) : make_desc(smem_u32(sB), b_rows * 16);
+    t0 = clock64();
+    for (int r = 0; r < reps; ++r) {
+      if (mode == 0)
+        asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}\n" ::"r"(tmem_base), "l"(da), "l"(db), "r"(idesc), "r"(r ? 1u : 0u) : "memory");
+      else
+        asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n}\n" ::"r"(tmem_base), "l"(da), "l"(db), "r"(idesc), "r"(r ? 1u : 0u) : "memory");
+    }
+    if (mode == 0)
+      asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar_done) : "memory");
+    else
+      asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar_done), "h"((unsigned short)3) : "memory");
+  }
+  mbar_wait(bar_done, 0);
+  if (issuer) cycles[rank] = clock64() - t0;
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  cluster_sync();
+  if (warp == 0) {
+    if (mode == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256) : "memory");
+    else asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256) : "memory");
+  }
+}
+
 }  // namespace probe
 }  // namespace isob200
+
+extern "C" int isob200_umma_rate(int mode, int reps, long long* cycles_dev, void* stream) {
+  using namespace isob200;
+  ISO_CHECK_ARG(mode >= 0 && mode % 10 <= 2 && mode < 20 && reps > 0 && cycles_dev, "umma_rate: bad arguments");
+  probe::umma_rate_kernel<<<2, 128, 0, (cudaStream_t)stream>>>(mode, reps, cycles_dev);
+  ISO_CHECK_LAUNCH("umma_rate_kernel");
+  return ISOB200_OK;
+}
 
 extern "C" int isob200_umma2_probe(const float* a, const float* b, int K, float* dump, void* stream) {
   using namespace isob200;

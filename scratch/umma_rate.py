@@ -1,0 +1,16 @@
+"""MMA issue-rate microbenchmark (csrc/umma2_probe.cu): cycles per N=256, K=16 fp16 MMA."""
+import sys
+import torch
+sys.path.insert(0, ".")
+from isopoints_b200 import _ext
+lib = _ext.lib()
+dev = torch.device("cuda")
+names = {0: "cta_group::1 M=128", 1: "cta_group::2 M=128 (64 rows/CTA)", 2: "cta_group::2 M=256 (128 rows/CTA)"}
+for mode in (0, 1, 2, 10, 11, 12):
+    for reps in (64, 512):
+        c = torch.zeros(2, dtype=torch.int64, device=dev)
+        for _ in range(2):
+            _ext.check(lib.isob200_umma_rate(mode, reps, _ext.ptr(c), _ext.stream(dev)))
+        torch.cuda.synchronize()
+        v = c.tolist()
+        print("%-36s %s reps %4d: %7d cycles -> %.1f cycles / MMA" % (names[mode % 10], "SW128     " if mode >= 10 else "no-swizzle", reps, max(v), max(v) / reps))
