@@ -61,27 +61,70 @@ def _peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    """SM clock / throttle reasons sampled DURING the timed region.
+
+    Uses NVML in-process (nvidia_ml_py): forking `nvidia-smi` from a process that holds a CUDA context
+    can stall the launching thread for tens of milliseconds -- visible as an outlier step now that the
+    Newton loop is enqueued without read-backs and the GPU depends on the host keeping its queue full.
+    `nvidia-smi` remains the fallback when NVML cannot be loaded."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
          "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    REASONS = (("hw_slowdown", 0x8), ("hw_thermal_slowdown", 0x40), ("sw_thermal_slowdown", 0x20),
+               ("sw_power_cap", 0x4))
 
-    def __init__(self, gpu_index=0):
-        self.rows = []
+    def __init__(self, gpu_index=0, period=0.004):
+        self.sm, self.mx, self.reasons = [], [], set()
         self.gpu = gpu_index
+        self.period = period
         self._stop = threading.Event()
         self._t = None
+        self._h = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            idx = gpu_index
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            if vis:
+                try:
+                    idx = int(vis.split(",")[gpu_index])
+                except Exception:
+                    idx = gpu_index
+            self._h = pynvml.nvmlDeviceGetHandleByIndex(idx)
+            self._nv = pynvml
+            self._max = float(pynvml.nvmlDeviceGetMaxClockInfo(self._h, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self._h = None
+
+    def _sample_nvml(self):
+        nv = self._nv
+        self.sm.append(float(nv.nvmlDeviceGetClockInfo(self._h, nv.NVML_CLOCK_SM)))
+        self.mx.append(self._max)
+        bits = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self._h))
+        for name, bit in self.REASONS:
+            if bits & bit:
+                self.reasons.add(name)
+
+    def _sample_smi(self):
+        out = subprocess.run(["nvidia-smi", "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                              "-i", str(self.gpu)], capture_output=True, text=True, timeout=5).stdout
+        for line in out.strip().splitlines():
+            r = [c.strip() for c in line.split(",")]
+            self.sm.append(float(r[1])); self.mx.append(float(r[2]))
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                if v.lower().startswith("active"):
+                    self.reasons.add(name)
 
     def _run(self):
         while not self._stop.is_set():
             try:
-                out = subprocess.run(["nvidia-smi", "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
-                                      "-i", str(self.gpu)], capture_output=True, text=True, timeout=5).stdout
-                for line in out.strip().splitlines():
-                    self.rows.append([c.strip() for c in line.split(",")])
+                if self._h is not None:
+                    self._sample_nvml()
+                else:
+                    self._sample_smi()
             except Exception:
                 pass
-            self._stop.wait(0.2)
+            self._stop.wait(self.period if self._h is not None else 0.2)
 
     def __enter__(self):
         self._t = threading.Thread(target=self._run, daemon=True)
@@ -93,19 +136,11 @@ class ClockSampler:
         self._t.join(timeout=6)
 
     def summary(self):
-        sm, mx, reasons = [], [], set()
-        for r in self.rows:
-            try:
-                sm.append(float(r[1])); mx.append(float(r[2]))
-            except Exception:
-                continue
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
-        if not sm:
+        if not self.sm:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
-        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
-                "samples": len(sm)}
+        return {"sm_mhz": float(np.median(self.sm)), "sm_max_mhz": float(max(self.mx)),
+                "reasons": sorted(self.reasons), "samples": len(self.sm),
+                "source": "nvml" if self._h is not None else "nvidia-smi"}
 
 
 def _dist_init(n_gpus):
@@ -215,7 +250,8 @@ def run_ours(args):
     _siren.RECORD = None
     siren_stats = dict(_siren.STATS)
     siren_stats["flops"] = _siren.algorithmic_flops(siren_stats["rows"], 7)
-    ms = sum(a.elapsed_time(b) for a, b in ev) / args.steps
+    step_ms = [a.elapsed_time(b) for a, b in ev]
+    ms = sum(step_ms) / args.steps
     ms = _max_over_ranks(ms, world, dev)
     converged = float(out["mask"].float().mean())
     n_out = int(out["mask"].shape[1])
@@ -298,6 +334,7 @@ def run_ours(args):
         "sdf_callback_and_glue_ms_per_step": ms - own_ms,
         "kernels": kern,
         "wall_s_timed_region": wall,
+        "ms_each_step": [round(t, 3) for t in step_ms],
     }
     if rank == 0:
         if world == 1:
