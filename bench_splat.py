@@ -33,6 +33,39 @@ def _inputs(dev):
     return {k: torch.as_tensor(v) for k, v in inp.items()}
 
 
+def run_ewa(dev, peaks, peak_src, steps, flush):
+    """The step right before the splat: per-point EWA parameters for the C4 point set
+    (V views x PV world-space points near a sphere, one camera per view) and the renderable mask.
+    Algorithmic bytes per point: 12 (xyz) + 12 (normal) + 4 (h_k) in, 8 + 12 + 4 + 4 out = 56 B;
+    the mask kernel: 24 B in, 1 B out."""
+    from isopoints_b200 import _ext, ewa
+    from tests.helpers import make_cameras, make_surface_points
+    pts, nrm, first, num = make_surface_points([PV] * V, seed=0)
+    w2v, proj, _ = make_cameras(V, seed=1)
+    pts, nrm, first, w2v, proj = (x.to(dev) for x in (pts, nrm, first, w2v, proj))
+    h = (torch.rand(V * PV, device=dev) * 1e-3 + 5e-5)
+    out = {}
+    for name, fn, nbytes in (
+            ("ewa_point_params", lambda: ewa.get_per_point_info(pts, nrm, first, proj, h, S, 1.0, 1.0), 56),
+            ("renderable_mask", lambda: ewa.renderable_mask(pts, nrm, first, w2v, 1.0, 100.0, True), 25)):
+        for _ in range(3):
+            fn()
+        _ext.PROFILE = {}
+        for k in range(steps):
+            flush.fill_(k & 0xff)
+            fn()
+        torch.cuda.synchronize()
+        prof, _ext.PROFILE = _ext.PROFILE, None
+        ev = prof["isob200_" + name]
+        ms = sum(a.elapsed_time(b) for a, b in ev) / len(ev)
+        ach = nbytes * V * PV / (ms * 1e-3) / 1e9
+        out[name] = {"points": V * PV, "avg_launch_ms": ms, "points_per_s": V * PV / (ms * 1e-3),
+                     "roofline": {"bound": "hbm", "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                                  "frac": ach / peaks["hbm_gbs"], "peak_source": peak_src,
+                                  "algorithmic_bytes_per_launch": nbytes * V * PV}}
+    return out
+
+
 def run(args, dev, peaks, peak_src, steps=None):
     from isopoints_b200 import _ext, splat
     lib = _ext.lib()
@@ -115,7 +148,8 @@ def run(args, dev, peaks, peak_src, steps=None):
                 "peak_source": peak_src, "algorithmic_bytes_per_launch": alg, "avg_launch_ms": f["avg_ms"],
                 "limiter": "instruction issue / shared-memory atomics, DRAM traffic = algorithmic bytes",
                 "ncu": _ncu("prof_splat_raster")}
-    return {"metric": "pixel-splats/sec", "unit": "pixel-splats/s",
+    ewa_rec = run_ewa(dev, peaks, peak_src, steps, flush)
+    return {"ewa_point_params": ewa_rec, "metric": "pixel-splats/sec", "unit": "pixel-splats/s",
             "config": {"workload": "C4: %d views x %d splats, %dx%d, K=%d, sigma=1.5px, occ_grad on 10%% of pixels, "
                                    "radii_backward_scaler=10" % (V, PV, S, S, K), "l2": "flushed between steps"},
             "pixel_splats_per_call": n_pairs,

@@ -79,7 +79,8 @@ int isob200_project_step(float* points, float* normals, unsigned char* not_conve
                          int* count_out, void* ws, size_t ws_bytes, void* stream);
 int isob200_gather_rows3(const float* src, const int* idx, int A, float* dst, void* stream);
 /* _filter_projection_result (levelset_sampling.py:59-65) for one packed cloud: the converged rows of
- * points / normals, in order, into out_* (>= M rows); *count_out = survivors.  ws as for project_step. */
+ * points / normals, in order, into out_* (>= M rows); *count_out = survivors.  ws as for project_step.
+ * normals / out_normals may both be NULL (rows of one array only). */
 int isob200_compact_valid(const float* points, const float* normals, const unsigned char* valid,
                           int M, float* out_points, float* out_normals, int* count_out, void* ws,
                           size_t ws_bytes, void* stream);
@@ -189,6 +190,32 @@ int isob200_splat_blend(const int* idx, const float* qvalue, const float* occ, c
 int isob200_splat_blend_backward(const int* idx, const float* weights, const float* grad_out,
                                  long long npix, int K, int C, float eps, float* grad_feat,
                                  int feat_stride, void* stream);
+
+/* ---- per-point EWA splat parameters + renderable filter: the op chains of SurfaceSplatting that
+ *      run right before the splat kernel (DSS/core/rasterizer.py).
+ *      Packed points (P,3) / normals (P,3), view-major; first_idx / num_points (n_views) int64;
+ *      camera matrices row-major in the row-vector convention of pytorch3d (p_hom @ M), either one
+ *      per view or a single broadcast one (gather_batch_to_packed, DSS/utils/__init__.py:218-250). */
+/* _compute_isotropic_Vrk (:358-386): sq_dists (n_views, P1, K) from the K = 7 self query
+ * (slot 0 = the point itself) -> h (P,) = clamp(0.5 max_k>=1, 5e-5, 0.01); clouds with < K points: 1e-3 */
+int isob200_ewa_vrk_h(const float* sq_dists, const int64_t* first_idx, const int64_t* num_points, int n_views,
+                      long long P1, int K, long long P, float* h, void* stream);
+/* _get_per_point_info (:514-563) = _compute_WJk (:438-487) + _compute_variance_and_detMk (:402-436)
+ * + _get_ellipse_axis_aligned_radius (:489-512), isotropic V_k^r (:388-400).
+ * proj (proj_views,4,4) = cameras.get_full_projection_transform().get_matrix();
+ * pixel_var = antialiasing_sigma * (2 / image_size)^2; outputs radii (P,2), ellipse (P,3) =
+ * (a, b, c) of a x^2 + b xy + c y^2, cutoff_out (P,), scaler (P,). */
+int isob200_ewa_point_params(const float* points, const float* normals, const int64_t* first_idx, int n_views,
+                             long long P, const float* proj, int proj_views, const float* vrk_h,
+                             float pixel_var, float cutoff, float* radii, float* ellipse, float* cutoff_out,
+                             float* scaler, void* stream);
+/* filter_renderable (:220-255): _filter_points_with_invalid_depth (:163-218) and, with nmat != NULL,
+ * _filter_backface_points (:124-161) as one mask: znear <= z_view <= zfar [and n_view.z < 0].
+ * w2v (cam_views,4,4) world-to-view; nmat (cam_views,3,3) the matrix normals are right-multiplied by.
+ * mask (P,) uint8; kept (n_views,) int32 = survivors per view (zeroed here). */
+int isob200_renderable_mask(const float* points, const float* normals, const int64_t* first_idx, int n_views,
+                            long long P, const float* w2v, const float* nmat, int cam_views, float znear,
+                            float zfar, unsigned char* mask, int* kept, void* stream);
 
 /* ---- point-set operators around the projection: DSS/utils/point_processing.py
  *      wlop (:35-122: density_P :77-80, one iteration :90-118), upsample (:321-340, one round),

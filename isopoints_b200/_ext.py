@@ -72,6 +72,9 @@ _PROTOS = {
     "isob200_splat_search_radius": (_i, [_vp, _vp, _vp, _vp, _i, _ll, _f, _vp, _vp, _sz, _vp]),
     "isob200_splat_zbuf_backward": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _i, _vp]),
     "isob200_splat_visibility": (_i, [_vp, _vp, _ll, _i, _ll, _vp, _vp]),
+    "isob200_ewa_vrk_h": (_i, [_vp, _vp, _vp, _i, _ll, _i, _ll, _vp, _vp]),
+    "isob200_ewa_point_params": (_i, [_vp, _vp, _vp, _i, _ll, _vp, _i, _vp, _f, _f, _vp, _vp, _vp, _vp, _vp]),
+    "isob200_renderable_mask": (_i, [_vp, _vp, _vp, _i, _ll, _vp, _vp, _i, _f, _f, _vp, _vp, _vp]),
     "isob200_splat_blend": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _ll, _i, _i, _f, _vp, _vp, _vp]),
     "isob200_splat_blend_backward": (_i, [_vp, _vp, _vp, _ll, _i, _i, _f, _vp, _i, _vp]),
 }

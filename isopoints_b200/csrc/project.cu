@@ -238,7 +238,7 @@ compact_valid_kernel(const float* __restrict__ points, const float* __restrict__
 #pragma unroll
       for (int c = 0; c < 3; ++c) {
         out_points[3 * (size_t)pos + c] = points[3 * i + c];
-        out_normals[3 * (size_t)pos + c] = normals[3 * i + c];
+        if (normals) out_normals[3 * (size_t)pos + c] = normals[3 * i + c];
       }
       ++pos;
     }
@@ -356,7 +356,8 @@ int isob200_compact_valid(const float* points, const float* normals, const unsig
     ISO_CUDA(cudaMemsetAsync(count_out, 0, sizeof(int), st));
     return ISOB200_OK;
   }
-  ISO_CHECK_ARG(points && normals && valid && out_points && out_normals && ws, "compact_valid: null pointer");
+  ISO_CHECK_ARG(points && valid && out_points && ws, "compact_valid: null pointer");
+  ISO_CHECK_ARG(!normals == !out_normals, "compact_valid: normals and out_normals go together");
   const size_t need = isob200_project_step_ws_bytes(M);
   if (ws_bytes < need) {
     set_error("compact_valid: workspace too small (%zu < %zu)", ws_bytes, need);

@@ -140,13 +140,16 @@ umma2_probe_kernel(const float* __restrict__ A, const float* __restrict__ B, int
 // operands, cycles from the first issue to the completion of the commit.  mode 0: cta_group::1, M = 128;
 // mode 1: cta_group::2, M = 128 (64 rows per CTA); mode 2: cta_group::2, M = 256 (128 rows per CTA).  N = 256.
 // mode + 10: the same shapes with 128-byte-swizzled K-major operands (rows of 128 B, 8-row atoms of 1 KB)
-// instead of the no-swizzle core-matrix layout the SIREN kernels use.
+// instead of the no-swizzle core-matrix layout the SIREN kernels use.  mode 3: cta_group::1, M = 64.
+// mode + 100 n: N = 256 >> n (n = 0..3) instead of 256.
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128)
 umma_rate_kernel(int mode_in, int reps, long long* __restrict__ cycles) {
   __shared__ __align__(1024) unsigned char sB[256 * 128];   // 256 rows x up to 128 B (contents irrelevant:
   unsigned char* sA = sB;                                    //  A reads the same buffer)
-  const bool sw128 = mode_in >= 10;
-  const int mode = mode_in % 10;
+  const bool sw128 = (mode_in / 10) % 10 != 0;
+  const int mode = mode_in % 10 == 3 ? 0 : mode_in % 10;
+  const bool m64 = mode_in % 10 == 3;
+  const uint32_t nn = 256u >> (mode_in / 100);
   __shared__ __align__(8) unsigned long long bars[1];
   __shared__ uint32_t tmem_ptr;
   const uint32_t rank = cluster_rank();
@@ -177,8 +180,8 @@ umma_rate_kernel(int mode_in, int reps, long long* __restrict__ cycles) {
   long long t0 = 0;
   if (issuer) {
     const int a_rows = mode == 1 ? 64 : 128, b_rows = mode == 0 ? 256 : 128;
-    const uint32_t m = mode == 2 ? 256 : 128;
-    const uint32_t idesc = (1u << 4) | ((uint32_t)(256 >> 3) << 17) | ((m >> 4) << 24);
+    const uint32_t m = mode == 2 ? 256 : (m64 ? 64 : 128);
+    const uint32_t idesc = (1u << 4) | ((nn >> 3) << 17) | ((m >> 4) << 24);
     // SW128 K-major: SBO = 1024 (8 rows x 128 B), LBO unused, layout type 2 in bits 61..63
     const uint64_t sw = (uint64_t)((1024 >> 4)) << 32 | (1ull << 16) | (1ull << 46) | (2ull << 61);
     const uint64_t da = sw128 ? (sw | ((smem_u32(sA) >> 4) & 0x3FFF)) : make_desc(smem_u32(sA), a_rows * 16);
@@ -210,7 +213,8 @@ umma_rate_kernel(int mode_in, int reps, long long* __restrict__ cycles) {
 
 extern "C" int isob200_umma_rate(int mode, int reps, long long* cycles_dev, void* stream) {
   using namespace isob200;
-  ISO_CHECK_ARG(mode >= 0 && mode % 10 <= 2 && mode < 20 && reps > 0 && cycles_dev, "umma_rate: bad arguments");
+  ISO_CHECK_ARG(mode >= 0 && mode % 10 <= 3 && (mode / 10) % 10 <= 1 && mode < 400 && reps > 0 && cycles_dev,
+                "umma_rate: bad arguments");
   probe::umma_rate_kernel<<<2, 128, 0, (cudaStream_t)stream>>>(mode, reps, cycles_dev);
   ISO_CHECK_LAUNCH("umma_rate_kernel");
   return ISOB200_OK;

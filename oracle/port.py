@@ -663,3 +663,99 @@ def upsample(points: torch.Tensor, n_points: int, neighborhood_size=16):
         if max_P == 0:
             break
     return pts
+
+
+# =========================================================================================
+# EWA per-point splat parameters + renderable filter  (DSS/core/rasterizer.py:124-255, 344-563)
+# =========================================================================================
+def _to_packed_views(data: torch.Tensor, first_idx, num_points):
+    """gather_batch_to_packed (DSS/utils/__init__.py:218-250): per-view data -> per packed point;
+    a single-view tensor is broadcast."""
+    if data.shape[0] == 1:
+        return data.expand(int(sum(int(n) for n in num_points)), *data.shape[1:])
+    b = torch.repeat_interleave(torch.arange(len(num_points)), torch.as_tensor(num_points, dtype=torch.int64))
+    return data[b]
+
+
+def ewa_vrk_h(sq_dists: torch.Tensor, num_points) -> torch.Tensor:
+    """_compute_isotropic_Vrk, first half (rasterizer.py:358-386).  sq_dists (N, P1, K) padded result of
+    the K = 7 self query (slot 0 = the point itself); returns packed h_k (P,)."""
+    d = sq_dists[:, :, 1:].clone()
+    n = torch.as_tensor(num_points, dtype=torch.int64)
+    d[n < sq_dists.shape[2]] = 1e-3                                     # :376
+    packed = torch.cat([d[b, :int(n[b])] for b in range(d.shape[0])], 0)  # padded_to_packed :378-380
+    h = 0.5 * packed.max(dim=-1)[0]                                     # :382
+    return h.clamp(5e-5, 0.01)                                          # :385
+
+
+def ewa_point_params(points: torch.Tensor, normals: torch.Tensor, first_idx, num_points, proj: torch.Tensor,
+                     vrk_h: torch.Tensor, image_size: int, antialiasing_sigma: float, cutoff: float,
+                     rand: torch.Tensor = None, dtype=torch.float64):
+    """_get_per_point_info (rasterizer.py:514-563) with the isotropic V_k^r (:388-400), operation by
+    operation, in `dtype` (float64 = the checker; float32 = the reference's own arithmetic).
+    points / normals packed (P,3); proj (N or 1, 4, 4) = get_full_projection_transform().get_matrix().
+    `rand` (P,3) stands in for torch.rand_like (:393); the results do not depend on it beyond rounding.
+    Returns radii (P,2), ellipse (P,3), cutoff (P,), scaler (P,), det_mk (P,)."""
+    import torch.nn.functional as F
+    pts = points.to(dtype)
+    nrm = normals.to(dtype)
+    M44 = proj.to(dtype)
+    P = pts.shape[0]
+    if rand is None:
+        rand = torch.rand(P, 3, generator=torch.Generator().manual_seed(0)).to(dtype)
+    # ---- _compute_WJk (:438-487) ----
+    W = _to_packed_views(M44[..., :3, :], first_idx, num_points)               # (P,3,4)
+    hom = torch.cat([pts, torch.ones(P, 1, dtype=dtype)], -1)                    # to_homogen
+    denom = (hom[:, None, :] @ _to_packed_views(M44[..., 3:], first_idx, num_points)).view(-1)
+    denom_sqr = eps_denom(denom ** 2)
+    Jk = torch.zeros(P, 4, 2, dtype=dtype)
+    denom = eps_denom(denom)
+    Jk[:, 0, 0] = 1 / denom
+    Jk[:, 1, 1] = 1 / denom
+    xy_view = hom[:, None, :] @ _to_packed_views(M44[..., :2], first_idx, num_points)   # (P,1,2)
+    Jk[:, 3, 0] = -1 / denom_sqr * xy_view[:, :, 0].view(-1)
+    Jk[:, 3, 1] = -1 / denom_sqr * xy_view[:, :, 1].view(-1)
+    WJk = W @ Jk                                                                 # (P,3,2)
+    # ---- _compute_isotropic_Vrk, second half (:388-400) ----
+    u0 = F.normalize(torch.cross(nrm, nrm + rand.to(dtype), dim=-1), dim=-1)
+    u1 = F.normalize(torch.cross(nrm, u0, dim=-1), dim=-1)
+    Sk = torch.stack([u0, u1], dim=1)                                            # (P,2,3)
+    Vrk = vrk_h.to(dtype).view(-1, 1, 1) * Sk.transpose(1, 2) @ Sk
+    # ---- _compute_variance_and_detMk (:423-436) ----
+    Mk = Sk @ WJk
+    Vk = WJk.transpose(1, 2) @ Vrk @ WJk
+    pixel_size = 2.0 / image_size
+    variance = Vk + antialiasing_sigma * torch.eye(2, dtype=dtype).expand(P, 2, 2) * (pixel_size ** 2)
+    det_mk = torch.det(Mk)
+    # ---- _get_per_point_info (:526-557) ----
+    gv_det = torch.det(variance)
+    gv_inv = torch.inverse(variance)
+    ellipse = torch.stack([gv_inv[:, 0, 0], gv_inv[:, 0, 1] + gv_inv[:, 1, 0], gv_inv[:, 1, 1]], -1)
+    a, b, c = ellipse[:, 0], ellipse[:, 1], ellipse[:, 2]                        # :502-511
+    den = eps_denom(4 * a * c - b ** 2)
+    y = torch.sqrt((4 * a * cutoff / den).abs().clamp_min(1e-17))
+    x = torch.sqrt((4 * c * cutoff / den).abs().clamp_min(1e-17))
+    radii = torch.stack([x, y], -1)
+    scaler = torch.sqrt((gv_det * 4 * np.pi * np.pi).abs().clamp_min(1e-17))
+    scaler = det_mk.abs() / eps_denom(scaler)
+    return radii, ellipse, torch.full_like(a, cutoff), scaler, det_mk
+
+
+def renderable_mask(points: torch.Tensor, normals, first_idx, num_points, w2v: torch.Tensor,
+                    nmat: torch.Tensor = None, znear: float = 1.0, zfar: float = 100.0):
+    """filter_renderable (rasterizer.py:220-255) as one packed mask: _filter_points_with_invalid_depth
+    (:163-218: znear <= z_view <= zfar, z_view from Transform3d.transform_points = p_hom @ w2v, xyz / w)
+    and, when `nmat` is given, _filter_backface_points (:124-161: (normals @ nmat).z < 0, nmat =
+    inverse(w2v)[:3,:3]^T as pytorch3d's Transform3d.transform_normals builds it).  float32."""
+    P = points.shape[0]
+    hom = torch.cat([points, torch.ones(P, 1, dtype=points.dtype)], -1)
+    V = _to_packed_views(w2v, first_idx, num_points)
+    out = (hom[:, None, :] @ V)[:, 0]
+    zv = out[:, 2] / out[:, 3]
+    mask = (zv >= znear) & (zv <= zfar)
+    if nmat is not None:
+        nv = (normals[:, None, :] @ _to_packed_views(nmat, first_idx, num_points))[:, 0]
+        mask = mask & (nv[:, 2] < 0)
+    n = [int(x) for x in num_points]
+    kept = [int(mask[int(f):int(f) + c].sum()) for f, c in zip(first_idx, n)]
+    return mask, kept

@@ -9,7 +9,7 @@ container): tests/golden/make_golden.py uses it to produce the committed golden 
 * The handful of pytorch3d symbols the hot path really executes get functional pure-torch
   stand-ins (semantics restated from pytorch3d's documentation: zero padding, packed =
   concatenation).
-* Two idioms PyTorch 1.6 accepted raise on torch >= 2: they are patched in the SOURCE STRING at
+* Two idioms PyTorch 1.6 accepted (three sites) raise on torch >= 2: they are patched in the SOURCE STRING at
   load time, each pattern asserted to match (PATCHES below).  Nothing else is changed.
 """
 import importlib
@@ -38,6 +38,9 @@ PATCHES = (
     ("DSS/models/levelset_sampling.py",
      "not_converged[not_converged] = curr_not_converged",
      "not_converged[not_converged.clone()] = curr_not_converged", 1),
+    ("DSS/core/rasterizer.py",
+     "valid_depth_mask[valid_depth_mask] = frontface_mask",
+     "valid_depth_mask[valid_depth_mask.clone()] = frontface_mask", 1),
 )
 
 
@@ -226,3 +229,34 @@ def load(frnn_module=None):
         mods.levelset_sampling.frnn = frnn_module
         mods.point_processing.frnn = frnn_module
     return mods
+
+
+def load_rasterizer():
+    """Import the reference's DSS.core.rasterizer (for SurfaceSplatting._get_per_point_info and the
+    renderable filters).  DSS._C (the compiled extension) is stubbed: the per-point parameter code never
+    calls it.  pytorch3d.ops.knn_points / eyes get pure-torch stand-ins (documented semantics:
+    K smallest squared distances ascending; a batch of identity matrices)."""
+    load()
+    if "rasterizer" not in _LOADED:
+        import DSS
+        stub = _StubModule("DSS._C")
+        sys.modules["DSS._C"] = stub
+        DSS._C = stub
+        import pytorch3d.ops as o3d
+
+        def knn_points(p1, p2, lengths1=None, lengths2=None, K=1, **kw):
+            from collections import namedtuple
+            d = ((p1[:, :, None, :] - p2[:, None, :, :]) ** 2).sum(-1)
+            if lengths2 is not None:
+                col = torch.arange(p2.shape[1])[None, None, :]
+                d = d.masked_fill(col >= lengths2[:, None, None], float("inf"))
+            dist, idx = torch.topk(d, K, dim=-1, largest=False, sorted=True)
+            return namedtuple("KNN", "dists idx knn")(dist, idx, None)
+
+        def eyes(dim, N, device=None, dtype=torch.float32):
+            return torch.eye(dim, device=device, dtype=dtype)[None].repeat(N, 1, 1)
+
+        o3d.knn_points = knn_points
+        o3d.eyes = eyes
+        _LOADED["rasterizer"] = importlib.import_module("DSS.core.rasterizer")
+    return _LOADED["rasterizer"]

@@ -10,6 +10,12 @@
 * splat vectors: the reference's `DSS._C._splat_points_naive` CPU twin
   (rasterize_points_cpu.cpp:27-144) -- NB its bbox reject uses && where the CUDA kernel uses ||
   (SURVEY 7.3), which is invisible when radii bound the cutoff ellipse, as they do here.
+* EWA per-point parameters (`--only ewa` regenerates just this one): the reference's
+  `SurfaceSplatting._get_per_point_info` / `_filter_points_with_invalid_depth` /
+  `_filter_backface_points` (DSS/core/rasterizer.py) on CPU tensors, with duck-typed point clouds and
+  cameras (pytorch3d is not installed: the camera object hands out the 4x4 matrices directly and its
+  world-to-view transform restates Transform3d.transform_points / transform_normals), the K = 7
+  neighbour query through the reference's own `frnn_bf_cpu`.
 The fixtures are small (< 1 MB total) and committed; the GPU box has no /root/reference.
 """
 import os
@@ -24,7 +30,7 @@ ROOT = os.path.dirname(os.path.dirname(HERE))
 sys.path.insert(0, ROOT)
 
 from oracle import ref_native, ref_python  # noqa: E402
-from tests.helpers import SphereSDF, TinySiren, make_splat_inputs  # noqa: E402
+from tests.helpers import SphereSDF, TinySiren, make_splat_inputs, make_cameras, make_surface_points  # noqa: E402
 
 
 class _CpuFrnn(types.SimpleNamespace):
@@ -52,8 +58,130 @@ class _CpuFrnn(types.SimpleNamespace):
         return out
 
 
+class _Transform:
+    """What the reference uses of pytorch3d.transforms.Transform3d (row-vector convention)."""
+
+    def __init__(self, m):
+        self.m = m
+
+    def get_matrix(self):
+        return self.m
+
+    def transform_points(self, points, eps=None):
+        hom = torch.cat([points, torch.ones_like(points[..., :1])], -1)
+        out = hom @ self.m
+        return out[..., :3] / out[..., 3:]
+
+    def transform_normals(self, normals):
+        return normals @ torch.inverse(self.m)[:, :3, :3].transpose(1, 2)
+
+
+class _Cameras:
+    def __init__(self, w2v, proj, znear, zfar):
+        self.w2v, self.proj, self.znear, self.zfar = w2v, proj, znear, zfar
+        self.R = w2v[:, :3, :3]
+
+    def __len__(self):
+        return self.proj.shape[0]
+
+    def get_full_projection_transform(self):
+        return _Transform(self.proj)
+
+    def get_world_to_view_transform(self):
+        return _Transform(self.w2v)
+
+
+class _Clouds:
+    """The PointClouds3D accessors the per-point code touches (packed = concatenation, padded = zeros)."""
+
+    def __init__(self, points=None, normals=None, features=None):
+        self.pl, self.nl = list(points), (list(normals) if normals is not None else None)
+        self.device = self.pl[0].device
+
+    def __len__(self):
+        return len(self.pl)
+
+    def isempty(self):
+        return sum(len(p) for p in self.pl) == 0
+
+    def num_points_per_cloud(self):
+        return torch.tensor([len(p) for p in self.pl], dtype=torch.int64)
+
+    def cloud_to_packed_first_idx(self):
+        n = self.num_points_per_cloud()
+        return torch.cat([n.new_zeros(1), n.cumsum(0)[:-1]])
+
+    def packed_to_cloud_idx(self):
+        return torch.repeat_interleave(torch.arange(len(self.pl)), self.num_points_per_cloud())
+
+    def points_packed(self):
+        return torch.cat(self.pl, 0)
+
+    def normals_packed(self):
+        return torch.cat(self.nl, 0)
+
+    def _padded(self, lst):
+        out = lst[0].new_zeros(len(lst), max(len(p) for p in lst), 3)
+        for b, p in enumerate(lst):
+            out[b, :len(p)] = p
+        return out
+
+    def points_padded(self):
+        return self._padded(self.pl)
+
+    def normals_padded(self):
+        return self._padded(self.nl)
+
+    def features_padded(self):
+        return None
+
+
+def ewa_golden():
+    R = ref_python.load_rasterizer()
+    R.frnn = _CpuFrnn
+    SS = R.SurfaceSplatting
+    S, sigma, cutoff, znear, zfar, radius = 256, 1.0, 1.0, 2.0, 100.0, 0.2
+    num = [900, 5, 700]                       # the 5-point cloud takes the `< K points` branch (:376)
+    pts, nrm, first, numt = make_surface_points(num, seed=11)
+    nrm[7] = 0.0                              # a degenerate normal: S_k = 0
+    w2v, proj, nmat = make_cameras(3, seed=12, znear=znear, zfar=zfar)
+    ras = SS.__new__(SS)
+    ras.frnn_radius = radius
+    ras._Vrk_h = None
+    ras.raster_settings = types.SimpleNamespace(cutoff_threshold=cutoff, Vrk_invariant=False, Vrk_isotropic=True,
+                                                image_size=S, antialiasing_sigma=sigma, backface_culling=True)
+    ras.cameras = _Cameras(w2v, proj, znear, zfar)
+    clouds = _Clouds([pts[f:f + n] for f, n in zip(first.tolist(), num)],
+                     [nrm[f:f + n] for f, n in zip(first.tolist(), num)])
+    torch.manual_seed(5)
+    info = SS._get_per_point_info(ras, clouds)
+    sq_dists = _CpuFrnn.frnn_grid_points(clouds.points_padded(), clouds.points_padded(), numt, numt, K=7, r=radius)[0]
+    # the renderable filters rebuild clouds from PADDED tensors (:186-195), so a ragged batch would turn
+    # surviving zero padding into points; the reference only ever feeds them equal-sized clouds
+    numf = [500, 500, 500]
+    fpts, fnrm, ffirst, fnumt = make_surface_points(numf, seed=13)
+    fclouds = _Clouds([fpts[f:f + n] for f, n in zip(ffirst.tolist(), numf)],
+                      [fnrm[f:f + n] for f, n in zip(ffirst.tolist(), numf)])
+    _, mask_depth = SS._filter_points_with_invalid_depth(ras, fclouds)
+    _, mask_renderable = SS.filter_renderable(ras, fclouds)
+    np.savez_compressed(
+        os.path.join(HERE, "ewa_point_info.npz"), image_size=S, antialiasing_sigma=sigma, cutoff=cutoff,
+        znear=znear, zfar=zfar, frnn_radius=radius, points=pts.numpy(), normals=nrm.numpy(),
+        first_idx=first.numpy(), num_points=numt.numpy(), w2v=w2v.numpy(), proj=proj.numpy(), nmat=nmat.numpy(),
+        sq_dists=sq_dists.numpy(), vrk_h=ras._Vrk_h.view(-1).numpy(), radii=info["radii"].numpy(),
+        ellipse=info["ellipse_params"].numpy(), cutoff_threshold=info["cutoff_threshold"].numpy(),
+        scaler=info["scaler"].numpy(), filter_points=fpts.numpy(), filter_normals=fnrm.numpy(),
+        filter_first_idx=ffirst.numpy(), filter_num_points=fnumt.numpy(), mask_depth=mask_depth.numpy(),
+        mask_renderable=mask_renderable.numpy())
+    print("ewa: radii px", float(info["radii"].mean()) * S / 2, "depth-valid", float(mask_depth.float().mean()),
+          "renderable", float(mask_renderable.float().mean()))
+
+
 def main():
     torch.set_num_threads(4)
+    if "--only" in sys.argv and sys.argv[sys.argv.index("--only") + 1] == "ewa":
+        ref_python.load(frnn_module=_CpuFrnn)
+        return ewa_golden()
     ref = ref_python.load(frnn_module=_CpuFrnn)
     LS = ref.levelset_sampling
 
@@ -160,6 +288,7 @@ def main():
     np.savez_compressed(os.path.join(HERE, "splat_naive_cpu.npz"), S=S, K=K, depth_merging_thres=0.05,
                         idx=idx.numpy(), zbuf=zbuf.numpy(), qvalue=qv.numpy(), occ=occ.numpy(), **inp)
     print("splat: occupied", float(occ.mean()))
+    ewa_golden()
 
 
 if __name__ == "__main__":

@@ -149,3 +149,49 @@ class Siren(nn.Module):
 
     def forward(self, coords, c=None, **kwargs):
         return types.SimpleNamespace(sdf=self.net(coords))
+
+
+def make_cameras(n_views, seed, dist=(2.2, 3.2), focal=2.0, znear=1.0, zfar=100.0):
+    """Look-at perspective cameras around the origin in pytorch3d's row-vector convention
+    (p_hom @ M).  Returns float32 tensors: w2v (B,4,4) world-to-view, proj (B,4,4) full projection
+    (world -> NDC, w = view-space z), nmat (B,3,3) = inverse(w2v)[:3,:3]^T, the matrix normals are
+    right-multiplied by (Transform3d.transform_normals)."""
+    rng = np.random.RandomState(seed)
+    w2v = np.zeros((n_views, 4, 4))
+    proj = np.zeros((n_views, 4, 4))
+    for b in range(n_views):
+        eye = rng.normal(size=3)
+        eye *= rng.uniform(*dist) / np.linalg.norm(eye)
+        zax = -eye / np.linalg.norm(eye)                     # camera looks at the origin along +z
+        up = np.array([0.0, 1.0, 0.0]) if abs(zax[1]) < 0.9 else np.array([1.0, 0.0, 0.0])
+        xax = np.cross(up, zax); xax /= np.linalg.norm(xax)
+        yax = np.cross(zax, xax)
+        R = np.stack([xax, yax, zax], 1)                     # p_view = p_world @ R + T
+        T = -eye @ R
+        w2v[b, :3, :3] = R
+        w2v[b, 3, :3] = T
+        w2v[b, 3, 3] = 1.0
+        K = np.zeros((4, 4))
+        K[0, 0] = K[1, 1] = focal * rng.uniform(0.9, 1.1)
+        K[2, 2] = zfar / (zfar - znear)
+        K[3, 2] = -zfar * znear / (zfar - znear)
+        K[2, 3] = 1.0
+        proj[b] = w2v[b] @ K
+    nmat = np.linalg.inv(w2v)[:, :3, :3].transpose(0, 2, 1)
+    f = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32))  # noqa: E731
+    return f(w2v), f(proj), f(nmat)
+
+
+def make_surface_points(pts_per_view, seed, noise=0.02):
+    """Packed points near the unit-radius-0.8 sphere with outward normals (a few flipped / zero)."""
+    rng = np.random.RandomState(seed)
+    P = int(sum(pts_per_view))
+    d = rng.normal(size=(P, 3))
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    pts = 0.8 * d + noise * rng.normal(size=(P, 3))
+    nrm = d + 0.1 * rng.normal(size=(P, 3))
+    nrm *= rng.uniform(0.5, 2.0, size=(P, 1))                # not unit length on purpose
+    num = np.asarray(pts_per_view, np.int64)
+    first = np.concatenate([[0], np.cumsum(num)[:-1]]).astype(np.int64)
+    return (torch.from_numpy(pts.astype(np.float32)), torch.from_numpy(nrm.astype(np.float32)),
+            torch.from_numpy(first), torch.from_numpy(num))

@@ -1,0 +1,208 @@
+"""GPU parity: per-point EWA splat parameters + renderable filter (csrc/ewa.cu through the C ABI and the
+host mirror isopoints_b200/ewa.py) vs the golden vectors of the reference's SurfaceSplatting and the
+oracle (oracle/port.py).
+
+Tolerances (north_star: fp32 within 1e-4 rel): against the float64 oracle every output is within 1e-4 of
+the exact value, measured per row for the (a, b, c) triple (b crosses zero) and with an absolute floor of
+1e-6 x the largest scaler for splats seen edge-on (their scaler tends to 0).  Against the reference's own
+float32 results the bound is 5e-4: that is the reference's rounding (tests/test_oracle_golden.py), not ours.
+"""
+import types
+
+import numpy as np
+import pytest
+import torch
+
+from isopoints_b200 import _ext, ewa
+from isopoints_b200.structures import Pointclouds
+from oracle import port
+from tests.helpers import make_cameras, make_surface_points
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+NAMES = ("radii", "ellipse_params", "cutoff_threshold", "scaler")
+
+
+def _rel_rows(a, b, floor=0.0):
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    sc = np.abs(b).max(axis=-1, keepdims=True) if b.ndim > 1 else np.abs(b)
+    return float((np.abs(a - b) / (sc + floor * np.abs(b).max() + 1e-30)).max())
+
+
+def _check_info(info, want, tol):
+    for name, w in zip(NAMES, want):
+        got = info[name].cpu().numpy()
+        w = w.numpy() if torch.is_tensor(w) else w
+        assert got.dtype == np.float32 and got.shape == w.shape, name
+        assert np.isfinite(got).all(), name
+        assert _rel_rows(got, w, floor=1e-6 if name == "scaler" else 0.0) < tol, name
+
+
+class _Cams:
+    def __init__(self, w2v, proj, znear=1.0, zfar=100.0):
+        self.w2v, self.proj, self.znear, self.zfar = w2v, proj, znear, zfar
+
+    def get_full_projection_transform(self):
+        return types.SimpleNamespace(get_matrix=lambda: self.proj)
+
+    def get_world_to_view_transform(self):
+        return types.SimpleNamespace(get_matrix=lambda: self.w2v)
+
+
+def test_point_info_matches_reference_golden(golden):
+    g = golden("ewa_point_info")
+    t = lambda k: torch.as_tensor(g[k], device=DEV)  # noqa: E731
+    info = ewa.get_per_point_info(t("points"), t("normals"), t("first_idx"), t("proj"), t("vrk_h"),
+                                  int(g["image_size"]), float(g["antialiasing_sigma"]), float(g["cutoff"]))
+    _check_info(info, [g["radii"], g["ellipse"], g["cutoff_threshold"], g["scaler"]], 5e-4)
+    r64 = port.ewa_point_params(torch.as_tensor(g["points"]), torch.as_tensor(g["normals"]), g["first_idx"].tolist(),
+                                g["num_points"].tolist(), torch.as_tensor(g["proj"]), torch.as_tensor(g["vrk_h"]),
+                                int(g["image_size"]), float(g["antialiasing_sigma"]), float(g["cutoff"]))
+    _check_info(info, r64[:4], 1e-4)
+    assert float(info["scaler"][7]) == 0.0                       # zero normal: S_k = 0 in the reference
+    assert np.array_equal(info["cutoff_threshold"].cpu().numpy(), g["cutoff_threshold"])
+
+
+def test_vrk_h_bit_exact(golden):
+    g = golden("ewa_point_info")
+    t = lambda k: torch.as_tensor(g[k], device=DEV)  # noqa: E731
+    # the kernel on the reference's own neighbour distances
+    sq = t("sq_dists").contiguous()
+    P = int(g["num_points"].sum())
+    h = torch.empty(P, dtype=torch.float32, device=DEV)
+    first_d, num_d = t("first_idx"), t("num_points")              # named: the raw pointers must stay alive
+    _ext.check(_ext.lib().isob200_ewa_vrk_h(_ext.ptr(sq), _ext.ptr(first_d), _ext.ptr(num_d),
+                                            sq.shape[0], sq.shape[1], sq.shape[2], P, _ext.ptr(h), _ext.stream(DEV)))
+    assert np.array_equal(h.cpu().numpy(), g["vrk_h"])
+    # end to end through this package's FRNN query (K = 7, r = frnn_radius)
+    pts, num, first = g["points"], g["num_points"], g["first_idx"]
+    padded = torch.zeros(len(num), int(num.max()), 3, device=DEV)
+    for b in range(len(num)):
+        padded[b, :num[b]] = torch.as_tensor(pts[first[b]:first[b] + num[b]], device=DEV)
+    h2 = ewa.compute_isotropic_vrk_h(padded, t("num_points"), float(g["frnn_radius"]))
+    # the golden distances come from the reference's CPU brute force (no FMA contraction); its CUDA grid
+    # kernel, which this package's query reproduces bit for bit, can differ from that in the last ulp
+    np.testing.assert_allclose(h2.cpu().numpy(), g["vrk_h"], rtol=1e-6, atol=0)
+    _, d = port.frnn_bruteforce(padded.cpu().numpy(), padded.cpu().numpy(), num, num, K=7, r=float(g["frnn_radius"]))
+    assert np.array_equal(h2.cpu().numpy(), port.ewa_vrk_h(torch.as_tensor(d), num.tolist()).numpy())
+    with pytest.raises(NotImplementedError):
+        ewa.compute_isotropic_vrk_h(padded, t("num_points"), -1.0)
+
+
+def test_renderable_mask_matches_reference_golden(golden):
+    g = golden("ewa_point_info")
+    t = lambda k: torch.as_tensor(g[k], device=DEV)  # noqa: E731
+    m, kept = ewa.renderable_mask(t("filter_points"), t("filter_normals"), t("filter_first_idx"), t("w2v"),
+                                  float(g["znear"]), float(g["zfar"]), backface_culling=False)
+    assert np.array_equal(m.cpu().numpy(), g["mask_depth"])
+    m, kept = ewa.renderable_mask(t("filter_points"), t("filter_normals"), t("filter_first_idx"), t("w2v"),
+                                  float(g["znear"]), float(g["zfar"]), backface_culling=True)
+    assert np.array_equal(m.cpu().numpy(), g["mask_renderable"])
+    first, num = g["filter_first_idx"], g["filter_num_points"]
+    assert kept.tolist() == [int(g["mask_renderable"][f:f + n].sum()) for f, n in zip(first, num)]
+
+
+@pytest.mark.parametrize("views,broadcast", [([40000] * 8, False), ([1, 0, 70001, 333], False), ([50000], True),
+                                             ([3000] * 64, False)])
+def test_point_info_vs_oracle_sizes(views, broadcast):
+    pts, nrm, first, num = make_surface_points(views, seed=len(views))
+    w2v, proj, _ = make_cameras(1 if broadcast else len(views), seed=7)
+    P = pts.shape[0]
+    h = torch.rand(P, generator=torch.Generator().manual_seed(1)) * 2e-3 + 5e-5
+    for S, sigma, cutoff in ((512, 1.0, 1.0), (128, 0.25, 2.5)):
+        info = ewa.get_per_point_info(pts.to(DEV), nrm.to(DEV), first.to(DEV), proj.to(DEV), h.to(DEV), S, sigma,
+                                      cutoff)
+        want = port.ewa_point_params(pts, nrm, first.tolist(), num.tolist(), proj, h, S, sigma, cutoff)
+        _check_info(info, want[:4], 1e-4)
+        # radii are the bounding box of the cutoff ellipse: Q(rx, y*) = cutoff has a double root
+        e = info["ellipse_params"].double().cpu()
+        r = info["radii"].double().cpu()
+        np.testing.assert_allclose((r[:, 0] ** 2 * (4 * e[:, 0] * e[:, 2] - e[:, 1] ** 2) / (4 * e[:, 2])).numpy(),
+                                   cutoff, rtol=2e-3)
+
+
+def test_filter_renderable_compacts_in_order():
+    views = [30000, 1, 45000]
+    pts, nrm, first, num = make_surface_points(views, seed=3)
+    w2v, proj, nmat = make_cameras(3, seed=5)
+    want, kept = port.renderable_mask(pts, nrm, first.tolist(), num.tolist(), w2v, nmat, 2.0, 100.0)
+    feats = torch.rand(pts.shape[0], 4)
+    split = lambda x: list(torch.split(x.to(DEV), views))  # noqa: E731
+    pc = Pointclouds(points=split(pts), normals=split(nrm), features=split(feats))
+    ras = ewa.SurfaceSplatting(cameras=_Cams(w2v.to(DEV), proj.to(DEV), znear=2.0),
+                               raster_settings=ewa.PointsRasterizationSettings(backface_culling=True))
+    new, mask = ras.filter_renderable(pc)
+    # decisions within float rounding of the znear plane / the silhouette may legitimately differ from the
+    # float32 oracle: compare away from the boundaries (margins in float64), then use the kernel's own mask
+    b = torch.repeat_interleave(torch.arange(3), num)
+    hom = torch.cat([pts.double(), torch.ones(len(pts), 1, dtype=torch.float64)], 1)
+    zv = torch.bmm(hom[:, None], w2v.double()[b])[:, 0, 2]
+    nz = torch.bmm(nrm.double()[:, None], nmat.double()[b])[:, 0, 2]
+    clear = ((zv - 2.0).abs() > 1e-5) & (nz.abs() > 1e-5)
+    got = mask.cpu()
+    assert clear.float().mean() > 0.999 and torch.equal(got[clear], want[clear])
+    kept = [int(got[f:f + n].sum()) for f, n in zip(first.tolist(), views)]
+    assert new.num_points_per_cloud().tolist() == kept and 0.2 < got.float().mean() < 0.8
+    assert torch.equal(new.points_packed().cpu(), pts[got])
+    assert torch.equal(new.normals_packed().cpu(), nrm[got])
+    assert torch.equal(new.features_packed().cpu(), feats[got])
+    # nothing filtered -> the same object comes back (rasterizer.py:183-184)
+    ras2 = ewa.SurfaceSplatting(cameras=_Cams(w2v.to(DEV), proj.to(DEV), znear=0.01),
+                                raster_settings=ewa.PointsRasterizationSettings(backface_culling=False))
+    same, mask2 = ras2.filter_renderable(pc)
+    assert same is pc and bool(mask2.all())
+
+
+def test_surface_splatting_forward_and_gradient():
+    """filter -> per-point parameters -> screen transform -> splat, and a gradient back to the world points."""
+    views = [6000] * 3
+    pts, nrm, first, num = make_surface_points(views, seed=8, noise=0.002)
+    w2v, proj, nmat = make_cameras(3, seed=9)
+    S, K = 128, 5
+    rs = ewa.PointsRasterizationSettings(image_size=S, points_per_pixel=K, bin_size=16, backface_culling=True)
+    ras = ewa.SurfaceSplatting(cameras=_Cams(w2v.to(DEV), proj.to(DEV), znear=0.5), raster_settings=rs, frnn_radius=0.2)
+    world = pts.to(DEV).requires_grad_(True)
+    pc = Pointclouds(points=list(torch.split(world, views)), normals=list(torch.split(nrm.to(DEV), views)))
+    frag, filtered = ras(pc)
+    assert tuple(frag.idx.shape) == (3, S, S, K) and tuple(frag.occupancy.shape) == (3, S, S)
+    Pf = int(filtered.num_points_per_cloud().sum())
+    assert 0.3 * sum(views) < Pf < 0.7 * sum(views)               # back-face culling keeps about half a sphere
+    assert int(frag.idx.max()) < Pf and 0.2 < float(frag.occupancy.mean()) < 0.9
+    # the same fragments from the oracle's splat on this path's own per-point parameters
+    info = ras._get_per_point_info(filtered, refresh=False)
+    screen = ras.transform(filtered).points_packed().detach()
+    wi, wz, wq, wo = port.splat_forward(screen.cpu().numpy(), info["ellipse_params"].cpu().numpy(),
+                                        info["cutoff_threshold"].cpu().numpy(), info["radii"].cpu().numpy(),
+                                        filtered.cloud_to_packed_first_idx().cpu().numpy(),
+                                        filtered.num_points_per_cloud().cpu().numpy(), 0.05, S, K)
+    assert np.array_equal(frag.idx.cpu().numpy(), wi) and np.array_equal(frag.occupancy.cpu().numpy(), wo)
+    sc = info["scaler"].cpu().numpy()
+    assert np.array_equal(frag.scaler.cpu().numpy(), np.where(wi >= 0, sc[np.maximum(wi, 0)], 0.0).astype(np.float32))
+    # screen xy / depth against the float64 matrices
+    hom = torch.cat([filtered.points_packed().detach().cpu().double(), torch.ones(Pf, 1, dtype=torch.float64)], 1)
+    b = filtered.packed_to_cloud_idx().cpu()
+    ndc = torch.bmm(hom[:, None], proj.double()[b])[:, 0]
+    np.testing.assert_allclose(screen[:, :2].cpu().numpy(), (ndc[:, :2] / ndc[:, 3:]).numpy(), rtol=1e-4, atol=1e-5)
+    (frag.zbuf[frag.idx >= 0].sum() + frag.occupancy.sum()).backward()
+    assert world.grad is not None and bool(torch.isfinite(world.grad).all()) and float(world.grad.abs().sum()) > 0
+
+
+def test_edge_cases():
+    w2v, proj, nmat = make_cameras(2, seed=1)
+    z = lambda *s: torch.zeros(*s, device=DEV)  # noqa: E731
+    first = torch.zeros(2, dtype=torch.int64, device=DEV)
+    info = ewa.get_per_point_info(z(0, 3), z(0, 3), first, proj.to(DEV), z(0), 64)       # empty
+    assert all(info[k].shape[0] == 0 for k in NAMES)
+    m, kept = ewa.renderable_mask(z(0, 3), None, first, w2v.to(DEV))
+    assert m.numel() == 0 and kept.tolist() == [0, 0]
+    with pytest.raises(TypeError):
+        ewa.get_per_point_info(torch.zeros(4, 3), torch.zeros(4, 3), first.cpu(), proj, torch.zeros(4), 64)
+    with pytest.raises(ValueError):
+        ewa.get_per_point_info(z(4, 3), z(4, 3), torch.zeros(65, dtype=torch.int64, device=DEV), proj.to(DEV), z(4), 64)
+    with pytest.raises(ValueError):                                                          # 3 cameras, 2 clouds
+        ewa.get_per_point_info(z(4, 3), z(4, 3), first, make_cameras(3, 2)[1].to(DEV), z(4), 64)
+    with pytest.raises(RuntimeError):
+        ewa.get_per_point_info(z(4, 3), z(4, 3), first, proj.to(DEV), z(5), 64)
+    rc = _ext.lib().isob200_ewa_point_params(None, None, None, 1, 4, None, 1, None, 0.0, 1.0, None, None, None, None,
+                                             None)
+    assert rc != 0 and b"null" in _ext.lib().isob200_last_error()

@@ -69,3 +69,24 @@ def test_siren_recognition_is_structural():
     m2._out_fields = ("rgb", "sdf")                                 # sdf is not the first output
     assert siren.match(m2, require_cuda=False) is None
     assert siren.algorithmic_flops(1, 7) == 4 * (3 * 256 + 7 * 65536 + 256)
+
+
+def test_ewa_host_mirror_refuses_cpu_and_keeps_reference_defaults():
+    """isopoints_b200/ewa.py: the raster settings carry the reference's defaults
+    (DSS/core/rasterizer.py:74-88) and nothing runs on CPU tensors."""
+    import pytest
+    from isopoints_b200 import ewa
+    rs = ewa.PointsRasterizationSettings()
+    assert (rs.backface_culling, rs.cutoff_threshold, rs.depth_merging_threshold) == (True, 1.0, 0.05)
+    assert (rs.Vrk_invariant, rs.Vrk_isotropic, rs.radii_backward_scaler) == (False, True, 10.0)
+    assert (rs.image_size, rs.points_per_pixel, rs.bin_size, rs.max_points_per_bin) == (256, 8, 0, None)
+    assert (rs.clip_pts_grad, rs.antialiasing_sigma) == (-1.0, 1.0)
+    with pytest.raises(TypeError):
+        ewa.PointsRasterizationSettings(image_sise=3)
+    first = torch.zeros(1, dtype=torch.int64)
+    with pytest.raises(TypeError):
+        ewa.get_per_point_info(torch.zeros(4, 3), torch.zeros(4, 3), first, torch.eye(4)[None], torch.zeros(4), 64)
+    with pytest.raises(TypeError):
+        ewa.renderable_mask(torch.zeros(4, 3), None, first, torch.eye(4)[None])
+    with pytest.raises(NotImplementedError):
+        ewa.SurfaceSplatting(raster_settings=ewa.PointsRasterizationSettings(Vrk_isotropic=False))._get_per_point_info(None)

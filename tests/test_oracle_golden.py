@@ -110,3 +110,50 @@ def test_wlop_and_upsample_match_reference(golden):
     up = port.upsample(torch.as_tensor(g["up_in"])[0], 1300, neighborhood_size=16)
     assert up.shape == (1300, 3) and int(g["up_num"][0]) == 1300
     np.testing.assert_allclose(up.numpy(), g["up_pts"][0], rtol=1e-5, atol=1e-6)
+
+
+def _rel_rows(a, b):
+    """max |a - b| relative to the largest magnitude of each row of b (b can cross zero inside a row)."""
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    sc = np.abs(b).max(axis=-1, keepdims=True) if b.ndim > 1 else np.abs(b)
+    return float((np.abs(a - b) / (sc + 1e-30)).max())
+
+
+def test_ewa_point_info_matches_reference(golden):
+    """oracle/port.py ewa_* against SurfaceSplatting._get_per_point_info run from the reference tree
+    (ragged views, a 5-point cloud on the `< K` branch, a zero normal)."""
+    g = golden("ewa_point_info")
+    first, num = g["first_idx"].tolist(), g["num_points"].tolist()
+    h = port.ewa_vrk_h(torch.as_tensor(g["sq_dists"]), num)
+    assert np.array_equal(h.numpy(), g["vrk_h"])
+    assert float(h[num[0]]) == np.float32(5e-4)          # 0.5 * 1e-3: the small-cloud branch
+    args = (torch.as_tensor(g["points"]), torch.as_tensor(g["normals"]), first, num, torch.as_tensor(g["proj"]),
+            torch.as_tensor(g["vrk_h"]), int(g["image_size"]), float(g["antialiasing_sigma"]), float(g["cutoff"]))
+    # float64 restatement vs the reference's float32 run.  The reference's own rounding is the tolerance:
+    # a d - b^2 of the 2x2 variance cancels for splats seen at a grazing angle (condition number up to ~1e3
+    # here), so its float32 results sit up to ~1.5e-4 from the exact value on the worst points and ~1e-7
+    # on the typical one.
+    r64 = port.ewa_point_params(*args)
+    for name, got in zip(("radii", "ellipse", "cutoff_threshold", "scaler"), r64):
+        assert _rel_rows(got.numpy(), g[name]) < 5e-4, name
+        err = np.abs(got.numpy() - g[name]) / (np.abs(g[name]).max(axis=-1, keepdims=True) if g[name].ndim > 1
+                                               else np.abs(g[name]) + 1e-30)
+        assert float(np.median(err)) < 1e-6, name
+    # the float32 restatement with a different random tangent frame: same results up to rounding
+    r32 = port.ewa_point_params(*args, rand=torch.rand(len(g["points"]), 3, generator=torch.Generator().manual_seed(9)),
+                                dtype=torch.float32)
+    for name, got in zip(("radii", "ellipse", "cutoff_threshold", "scaler"), r32):
+        assert _rel_rows(got.numpy(), g[name]) < 5e-4, name
+    assert float(r64[3][7]) == 0.0 and float(g["scaler"][7]) == 0.0      # zero normal: S_k = 0, det M_k = 0
+
+
+def test_renderable_mask_matches_reference(golden):
+    g = golden("ewa_point_info")
+    first, num = g["filter_first_idx"].tolist(), g["filter_num_points"].tolist()
+    pts, nrm = torch.as_tensor(g["filter_points"]), torch.as_tensor(g["filter_normals"])
+    w2v, nmat = torch.as_tensor(g["w2v"]), torch.as_tensor(g["nmat"])
+    m, kept = port.renderable_mask(pts, nrm, first, num, w2v, None, float(g["znear"]), float(g["zfar"]))
+    assert np.array_equal(m.numpy(), g["mask_depth"])
+    m, kept = port.renderable_mask(pts, nrm, first, num, w2v, nmat, float(g["znear"]), float(g["zfar"]))
+    assert np.array_equal(m.numpy(), g["mask_renderable"])
+    assert sum(kept) == int(g["mask_renderable"].sum()) and 0.2 < m.float().mean() < 0.8
