@@ -24,7 +24,7 @@ import torch
 
 from . import _ext
 from .frnn import frnn_grid_points
-from .splat import PointFragments, rasterize_elliptical_points, visibility_mask
+from .splat import PointFragments, gather_with_neg_idx, rasterize_elliptical_points, visibility_mask
 from .structures import Pointclouds, packed_to_padded
 
 MAX_VIEWS = 64   # csrc/ewa.cu: camera matrices are staged in shared memory
@@ -231,12 +231,23 @@ class SurfaceSplatting:
         screen = torch.cat([ndc[:, :2] / ndc[:, 3:], view[:, 2:3] / view[:, 3:]], -1)
         return Pointclouds(points=list(torch.split(screen, point_clouds.num_points_per_cloud().tolist())))
 
+    def _empty_fragments(self, batch_size, **kwargs):
+        """rasterizer.py:565-582."""
+        rs = kwargs.get("raster_settings", self.raster_settings)
+        dev = kwargs.get("device", "cuda:%d" % torch.cuda.current_device())
+        S, K = rs.image_size, rs.points_per_pixel
+        idx = torch.full((batch_size, S, S, K), -1, dtype=torch.long, device=dev)
+        zbuf = torch.full((batch_size, S, S, K), -1.0, dtype=torch.float, device=dev)
+        qvalue = torch.full((batch_size, S, S, K), -1.0, dtype=torch.float, device=dev)
+        occ = torch.full((batch_size, S, S), 0, dtype=torch.float, device=dev)
+        return PointFragments(idx=idx, zbuf=zbuf, qvalue=qvalue, scaler=qvalue, occupancy=occ)
+
     def forward(self, point_clouds, point_clouds_filter=None, **kwargs):
         """rasterizer.py:584-661 -> (PointFragments, filtered point clouds)."""
         rs = kwargs.get("raster_settings", self.raster_settings)
         filtered, mask_filtered = self.filter_renderable(point_clouds, point_clouds_filter, **kwargs)
         if filtered.isempty():
-            raise ValueError("no renderable points")
+            return self._empty_fragments(len(filtered), device=filtered.device, **kwargs), filtered
         with torch.no_grad():
             info = self._get_per_point_info(filtered, **kwargs)
         screen = self.transform(filtered, **kwargs)
@@ -245,9 +256,7 @@ class SurfaceSplatting:
             depth_merging_threshold=rs.depth_merging_threshold, image_size=rs.image_size,
             points_per_pixel=rs.points_per_pixel, bin_size=rs.bin_size, max_points_per_bin=rs.max_points_per_bin,
             radii_backward_scaler=rs.radii_backward_scaler, clip_pts_grad=rs.clip_pts_grad)
-        flat = idx.view(-1).long()
-        frag_scaler = torch.where(flat >= 0, info["scaler"][flat.clamp_min(0)],
-                                  info["scaler"].new_zeros(())).view_as(qvalue)   # gather_with_neg_idx
+        frag_scaler = gather_with_neg_idx(info["scaler"], 0, idx.view(-1).long()).view_as(qvalue)   # :634-636
         return PointFragments(idx=idx, zbuf=zbuf, qvalue=qvalue, scaler=frag_scaler, occupancy=occ), filtered
 
     __call__ = forward

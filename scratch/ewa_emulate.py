@@ -5,10 +5,18 @@ import torch
 sys.path.insert(0, ".")
 from oracle import port
 
-g = np.load("tests/golden/ewa_point_info.npz")
 f = np.float32
-pts, nrm, proj, h = g["points"], g["normals"], g["proj"], g["vrk_h"]
-first, num = g["first_idx"], g["num_points"]
+if len(sys.argv) > 1:
+    from tests.helpers import make_cameras, make_surface_points
+    views = [40000] * 8
+    pts, nrm, first, num = (x.numpy() for x in make_surface_points(views, seed=len(views)))
+    proj = make_cameras(8, seed=7)[1].numpy()
+    h = (torch.rand(len(pts), generator=torch.Generator().manual_seed(1)) * 2e-3 + 5e-5).numpy()
+    g = dict(antialiasing_sigma=float(sys.argv[2]), image_size=int(sys.argv[1]), cutoff=float(sys.argv[3]))
+else:
+    g = np.load("tests/golden/ewa_point_info.npz")
+    pts, nrm, proj, h = g["points"], g["normals"], g["proj"], g["vrk_h"]
+    first, num = g["first_idx"], g["num_points"]
 b = np.repeat(np.arange(len(num)), num)
 M = proj[b]
 x, y, z = pts[:, 0], pts[:, 1], pts[:, 2]
@@ -54,6 +62,17 @@ def rel(a, b):
     sc = np.abs(b).max(-1, keepdims=True) if b.ndim > 1 else np.abs(b)
     return float((np.abs(a - b) / (sc + 1e-30)).max())
 print("radii", rel(np.stack([rx, ry], 1), r64[0]), "ellipse", rel(np.stack([ea, eb, ec], 1), r64[1]), "scaler", rel(sk, r64[3]))
+if len(sys.argv) > 1:
+    sfl = np.abs(sk - r64[3].numpy()) / (np.abs(r64[3].numpy()) + 1e-6 * np.abs(r64[3].numpy()).max())
+    print("scaler with floor", sfl.max())
+    ae = np.abs(sk - r64[3].numpy()); s64 = np.abs(r64[3].numpy())
+    print("scaler abs err max", ae.max(), "median s", np.median(s64), "max s", s64.max(), "max (ae - 1e-4 s)/median", ((ae - 1e-4 * s64) / np.median(s64)).max())
+    front = np.linalg.norm(np.cross(w0, w1), axis=1) / (2 * np.pi * np.sqrt(det))
+    print("err relative to the frontal scaler", (ae / front).max())
+    e = np.stack([ea, eb, ec], 1).astype(np.float64); r = np.stack([rx, ry], 1).astype(np.float64)
+    ident = r[:, 0] ** 2 * (4 * e[:, 0] * e[:, 2] - e[:, 1] ** 2) / (4 * e[:, 2])
+    print("identity", np.abs(ident / float(g["cutoff"]) - 1).max())
+    sys.exit()
 print("vs golden: radii", rel(np.stack([rx, ry], 1), torch.as_tensor(g["radii"])), "ellipse",
       rel(np.stack([ea, eb, ec], 1), torch.as_tensor(g["ellipse"])), "scaler", rel(sk, torch.as_tensor(g["scaler"])))
 s64 = r64[3].numpy()

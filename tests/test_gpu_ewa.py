@@ -3,8 +3,8 @@ host mirror isopoints_b200/ewa.py) vs the golden vectors of the reference's Surf
 oracle (oracle/port.py).
 
 Tolerances (north_star: fp32 within 1e-4 rel): against the float64 oracle every output is within 1e-4 of
-the exact value, measured per row for the (a, b, c) triple (b crosses zero) and with an absolute floor of
-1e-6 x the largest scaler for splats seen edge-on (their scaler tends to 0).  Against the reference's own
+the exact value, measured per row for the (a, b, c) triple (b crosses zero) and with an absolute term of
+1e-5 x the median scaler for splats seen edge-on (their scaler cancels to 0).  Against the reference's own
 float32 results the bound is 5e-4: that is the reference's rounding (tests/test_oracle_golden.py), not ours.
 """
 import types
@@ -35,7 +35,13 @@ def _check_info(info, want, tol):
         w = w.numpy() if torch.is_tensor(w) else w
         assert got.dtype == np.float32 and got.shape == w.shape, name
         assert np.isfinite(got).all(), name
-        assert _rel_rows(got, w, floor=1e-6 if name == "scaler" else 0.0) < tol, name
+        if name == "scaler":
+            # |n_hat . (w0 x w1)| / (2 pi sqrt det): for a splat seen edge-on the triple product cancels to ~0, and
+            # its absolute error is float32 eps x the frontal value -- hence the small absolute term
+            w64 = np.abs(np.asarray(w, np.float64))
+            assert (np.abs(got - w) <= tol * w64 + 1e-5 * np.median(w64)).all(), name
+        else:
+            assert _rel_rows(got, w) < tol, name
 
 
 class _Cams:
@@ -167,7 +173,7 @@ def test_surface_splatting_forward_and_gradient():
     assert tuple(frag.idx.shape) == (3, S, S, K) and tuple(frag.occupancy.shape) == (3, S, S)
     Pf = int(filtered.num_points_per_cloud().sum())
     assert 0.3 * sum(views) < Pf < 0.7 * sum(views)               # back-face culling keeps about half a sphere
-    assert int(frag.idx.max()) < Pf and 0.2 < float(frag.occupancy.mean()) < 0.9
+    assert int(frag.idx.max()) < Pf and 0.2 < float(frag.occupancy.detach().mean()) < 0.9
     # the same fragments from the oracle's splat on this path's own per-point parameters
     info = ras._get_per_point_info(filtered, refresh=False)
     screen = ras.transform(filtered).points_packed().detach()
@@ -175,9 +181,9 @@ def test_surface_splatting_forward_and_gradient():
                                         info["cutoff_threshold"].cpu().numpy(), info["radii"].cpu().numpy(),
                                         filtered.cloud_to_packed_first_idx().cpu().numpy(),
                                         filtered.num_points_per_cloud().cpu().numpy(), 0.05, S, K)
-    assert np.array_equal(frag.idx.cpu().numpy(), wi) and np.array_equal(frag.occupancy.cpu().numpy(), wo)
+    assert np.array_equal(frag.idx.cpu().numpy(), wi) and np.array_equal(frag.occupancy.detach().cpu().numpy(), wo)
     sc = info["scaler"].cpu().numpy()
-    assert np.array_equal(frag.scaler.cpu().numpy(), np.where(wi >= 0, sc[np.maximum(wi, 0)], 0.0).astype(np.float32))
+    assert np.array_equal(frag.scaler.detach().cpu().numpy(), np.where(wi >= 0, sc[np.maximum(wi, 0)], 0.0).astype(np.float32))
     # screen xy / depth against the float64 matrices
     hom = torch.cat([filtered.points_packed().detach().cpu().double(), torch.ones(Pf, 1, dtype=torch.float64)], 1)
     b = filtered.packed_to_cloud_idx().cpu()
@@ -185,6 +191,17 @@ def test_surface_splatting_forward_and_gradient():
     np.testing.assert_allclose(screen[:, :2].cpu().numpy(), (ndc[:, :2] / ndc[:, 3:]).numpy(), rtol=1e-4, atol=1e-5)
     (frag.zbuf[frag.idx >= 0].sum() + frag.occupancy.sum()).backward()
     assert world.grad is not None and bool(torch.isfinite(world.grad).all()) and float(world.grad.abs().sum()) > 0
+
+
+def test_forward_with_nothing_renderable_returns_empty_fragments():
+    pts, nrm, first, num = make_surface_points([500, 500], seed=2)
+    w2v, proj, nmat = make_cameras(2, seed=3)
+    rs = ewa.PointsRasterizationSettings(image_size=32, points_per_pixel=3, backface_culling=False)
+    ras = ewa.SurfaceSplatting(cameras=_Cams(w2v.to(DEV), proj.to(DEV), znear=50.0), raster_settings=rs)
+    pc = Pointclouds(points=list(torch.split(pts.to(DEV), [500, 500])), normals=list(torch.split(nrm.to(DEV), [500, 500])))
+    frag, filtered = ras(pc)
+    assert filtered.isempty() and tuple(frag.idx.shape) == (2, 32, 32, 3)
+    assert int(frag.idx.max()) == -1 and float(frag.occupancy.sum()) == 0.0 and float(frag.zbuf.max()) == -1.0
 
 
 def test_edge_cases():
