@@ -127,6 +127,24 @@ def test_point_info_vs_oracle_sizes(views, broadcast):
                                    cutoff, rtol=2e-3)
 
 
+def test_unaligned_and_tail_paths_agree_with_the_vector_path():
+    """Slices that start 12 bytes into an allocation take the one-point-per-thread kernels, P % 4 != 0 the tail."""
+    views = [1001, 2002]
+    pts, nrm, first, num = make_surface_points(views, seed=4)
+    w2v, proj, _ = make_cameras(2, seed=6)
+    h = torch.rand(pts.shape[0]) * 1e-3 + 5e-5
+    d = lambda x: x.to(DEV)  # noqa: E731
+    ref = ewa.get_per_point_info(d(pts), d(nrm), d(first), d(proj), d(h), 256)
+    pad = lambda x: torch.cat([x[:1], x], 0).to(DEV)[1:]  # noqa: E731  (same values, data_ptr offset by one row)
+    assert pad(pts).data_ptr() % 16 != 0
+    got = ewa.get_per_point_info(pad(pts), pad(nrm), d(first), d(proj), d(h), 256)
+    for k in NAMES:
+        assert torch.equal(ref[k], got[k]), k
+    m0, k0 = ewa.renderable_mask(d(pts), d(nrm), d(first), d(w2v), 2.5, 100.0, True)
+    m1, k1 = ewa.renderable_mask(pad(pts), pad(nrm), d(first), d(w2v), 2.5, 100.0, True)
+    assert torch.equal(m0, m1) and k0.tolist() == k1.tolist() == [int(m0[:1001].sum()), int(m0[1001:].sum())]
+
+
 def test_filter_renderable_compacts_in_order():
     views = [30000, 1, 45000]
     pts, nrm, first, num = make_surface_points(views, seed=3)
