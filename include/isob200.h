@@ -124,8 +124,9 @@ int isob200_siren_project_step(const float* x, int n_max, const int* n_dev, cons
 /* Bring-up probe of the 2-CTA tensor-core path (tcgen05 cta_group::2, M = 128 across a CTA pair): one
  * (128 x K) x (256 x K)^T fp16 GEMM, dump (2,128,128) = raw TMEM of both CTAs.  Test-only. */
 int isob200_umma2_probe(const float* a, const float* b, int K, float* dump, void* stream);
-/* issue-rate microbenchmark: reps back-to-back N = 256, K = 16 fp16 MMAs; mode 0 = cta_group::1 M = 128,
- * 1 = cta_group::2 M = 128, 2 = cta_group::2 M = 256; cycles_dev[rank] = cycles until the commit lands. */
+/* issue-rate microbenchmark: reps back-to-back K = 16 fp16 MMAs; mode % 10: 0 = cta_group::1 M = 128,
+ * 1 = cta_group::2 M = 128, 2 = cta_group::2 M = 256, 3 = cta_group::1 M = 64; + 10: 128-byte swizzled
+ * operands; + 100 n: N = 256 >> n (n = 0..3); cycles_dev[rank] = cycles until the commit lands. */
 int isob200_umma_rate(int mode, int reps, long long* cycles_dev, void* stream);
 
 /* ---- uniform resampling: UniformProjection.resample, one sample_iter

@@ -3,7 +3,7 @@
     python tests/golden/make_golden.py
 
 * projection / resample vectors: the reference's Python (DSS/models/levelset_sampling.py loaded
-  from /root/reference through oracle/ref_python.py's asserted 2-entry torch-2.x patch list) on
+  from /root/reference through oracle/ref_python.py's asserted 3-entry torch-2.x patch list) on
   CPU tensors; its `frnn` dependency (CUDA-only) is replaced by a stand-in built on the
   reference's own CPU brute force `frnn._C.frnn_bf_cpu` (oracle/_ref/ref_frnn_C.so).
 * FRNN vectors: `frnn._C.frnn_bf_cpu` (bruteforce_cpu.cpp:4-58).
