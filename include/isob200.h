@@ -77,6 +77,13 @@ int isob200_project_step(float* points, float* normals, unsigned char* not_conve
                          const int* act_in, int A, const int* a_dev, const float* sdf, const float* grad,
                          float tol, float max_step, int do_update, int* act_out, float* next_points,
                          int* count_out, void* ws, size_t ws_bytes, void* stream);
+/* ---- ray marching: SphereTracing.project_points (DSS/models/levelset_sampling.py:679-808); one call per
+ *      iteration, conventions as isob200_project_step: rays advance by alpha * sdf along dirs (step clamped
+ *      to max_step), retire when |sdf| <= active_tol or when the step would leave the sphere of radius `bound` */
+int isob200_trace_step(float* points, const float* dirs, float* eval, float* grad_out, const int* act_in, int A,
+                       const int* a_dev, const float* sdf, const float* grad, float active_tol, float alpha,
+                       float max_step, float bound, int do_update, int* act_out, float* next_points,
+                       int* count_out, void* ws, size_t ws_bytes, void* stream);
 int isob200_gather_rows3(const float* src, const int* idx, int A, float* dst, void* stream);
 /* _filter_projection_result (levelset_sampling.py:59-65) for one packed cloud: the converged rows of
  * points / normals, in order, into out_* (>= M rows); *count_out = survivors.  ws as for project_step.

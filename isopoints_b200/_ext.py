@@ -38,6 +38,8 @@ _PROTOS = {
     "isob200_frnn_backward": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp]),
     "isob200_project_step_ws_bytes": (_sz, [_i]),
     "isob200_project_step": (_i, [_vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _f, _f, _i, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "isob200_trace_step": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _f, _f, _f, _f, _i, _vp, _vp, _vp, _vp, _sz,
+                                _vp]),
     "isob200_gather_rows3": (_i, [_vp, _vp, _i, _vp, _vp]),
     "isob200_compact_valid": (_i, [_vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _sz, _vp]),
     "isob200_project_sphere": (_i, [_vp, _vp, _vp, _ll, _f, _f, _f, _i, _vp]),

@@ -169,6 +169,131 @@ project_step_kernel(float* __restrict__ points, float* __restrict__ normals,
     }
 }
 
+// One iteration of SphereTracing.project_points (levelset_sampling.py:733-786) on the active rays:
+//   eval[act[i]] = sdf[i] ; grad_out[act[i]] = grad[i]                           (:742-758)
+//   still = |sdf[i]| > 0.1 tol                   (active rays are inside the sphere by construction, :760-761)
+//   if still and this is not the last evaluation:                                (:764-776)
+//       move = alpha * sdf * dir ; move = normalize(move, eps=1e-15) * min(|move|, 0.1)
+//       p' = p + move ; inside = |p'| < padding + radius
+//       inside: points[act[i]] = p', the ray stays active; else the ray keeps its old position and retires
+// Same ticket + decoupled look-back compaction as project_step_kernel (order-preserving).
+__global__ void __launch_bounds__(PJ_THREADS)
+trace_step_kernel(float* __restrict__ points, const float* __restrict__ dirs, float* __restrict__ eval,
+                  float* __restrict__ grad_out, const int* __restrict__ act_in, int A,
+                  const int* __restrict__ a_dev, const float* __restrict__ sdf, const float* __restrict__ grad,
+                  float active_tol, float alpha, float max_step, float bound, int do_update,
+                  int* __restrict__ act_out, float* __restrict__ next_points, int* __restrict__ count_out,
+                  unsigned* __restrict__ ws) {
+  __shared__ int s_tile;
+  __shared__ int s_warp[PJ_THREADS / 32];
+  __shared__ int s_prefix;
+  if (threadIdx.x == 0) s_tile = (int)atomicAdd(&ws[0], 1u);
+  __syncthreads();
+  const int tile = s_tile;
+  if (a_dev) {
+    const int a = *a_dev;
+    A = a < A ? a : A;
+    if ((long long)tile * PJ_TILE >= A) {
+      if (tile == 0 && threadIdx.x == 0) *count_out = 0;
+      return;
+    }
+  }
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int base = tile * PJ_TILE + threadIdx.x * PJ_ITEMS;
+  int keep[PJ_ITEMS];
+  int id[PJ_ITEMS];
+  float nx[PJ_ITEMS][3];
+  int cnt = 0;
+#pragma unroll
+  for (int j = 0; j < PJ_ITEMS; ++j) {
+    const int i = base + j;
+    keep[j] = 0;
+    id[j] = -1;
+    if (i < A) {
+      const int p = act_in ? act_in[i] : i;
+      id[j] = p;
+      const float f = sdf[i];
+      eval[p] = f;
+      if (grad_out) {
+        grad_out[3 * (size_t)p + 0] = grad[3 * i + 0];
+        grad_out[3 * (size_t)p + 1] = grad[3 * i + 1];
+        grad_out[3 * (size_t)p + 2] = grad[3 * i + 2];
+      }
+      if (fabsf(f) > active_tol) {
+        float* q = points + 3 * (size_t)p;
+        nx[j][0] = q[0]; nx[j][1] = q[1]; nx[j][2] = q[2];
+        keep[j] = 1;
+        if (do_update) {
+          const float af = __fmul_rn(alpha, f);
+          const float mx = __fmul_rn(af, dirs[3 * (size_t)p + 0]);
+          const float my = __fmul_rn(af, dirs[3 * (size_t)p + 1]);
+          const float mz = __fmul_rn(af, dirs[3 * (size_t)p + 2]);
+          const float nrm = sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(mx, mx), __fmul_rn(my, my)), __fmul_rn(mz, mz)));
+          const float dn = fmaxf(nrm, 1e-15f);        // F.normalize(eps=1e-15)
+          const float len = fminf(nrm, max_step);     // clamp_max(0.1)
+          nx[j][0] = __fadd_rn(nx[j][0], __fmul_rn(__fdiv_rn(mx, dn), len));
+          nx[j][1] = __fadd_rn(nx[j][1], __fmul_rn(__fdiv_rn(my, dn), len));
+          nx[j][2] = __fadd_rn(nx[j][2], __fmul_rn(__fdiv_rn(mz, dn), len));
+          const float r = sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(nx[j][0], nx[j][0]), __fmul_rn(nx[j][1], nx[j][1])),
+                                          __fmul_rn(nx[j][2], nx[j][2])));
+          if (r < bound) { q[0] = nx[j][0]; q[1] = nx[j][1]; q[2] = nx[j][2]; }
+          else keep[j] = 0;                            // left the sphere: old position stays, ray retires
+        }
+      }
+    }
+    cnt += keep[j];
+  }
+  int incl = cnt;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int t = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += t;
+  }
+  if (lane == 31) s_warp[w] = incl;
+  __syncthreads();
+  int woff = 0, total = 0;
+#pragma unroll
+  for (int i = 0; i < PJ_THREADS / 32; ++i) {
+    const int t = s_warp[i];
+    if (i < w) woff += t;
+    total += t;
+  }
+  if (threadIdx.x == 0) {
+    unsigned* status = ws + 2;
+    int prefix = 0;
+    if (tile == 0) {
+      __threadfence();
+      atomicExch(&status[0], LB_FLAG_INC | (unsigned)total);
+    } else {
+      atomicExch(&status[tile], LB_FLAG_AGG | (unsigned)total);
+      int t = tile - 1;
+      while (true) {
+        const unsigned s = ld_volatile_u32(&status[t]);
+        if ((s >> 30) == 0) continue;
+        prefix += (int)(s & LB_VALUE_MASK);
+        if (s & LB_FLAG_INC) break;
+        --t;
+      }
+      atomicExch(&status[tile], LB_FLAG_INC | (unsigned)(prefix + total));
+    }
+    s_prefix = prefix;
+    if ((long long)(tile + 1) * PJ_TILE >= A) *count_out = prefix + total;
+  }
+  __syncthreads();
+  int pos = s_prefix + woff + incl - cnt;
+#pragma unroll
+  for (int j = 0; j < PJ_ITEMS; ++j)
+    if (keep[j]) {
+      act_out[pos] = id[j];
+      if (next_points) {
+        next_points[3 * (size_t)pos + 0] = nx[j][0];
+        next_points[3 * (size_t)pos + 1] = nx[j][1];
+        next_points[3 * (size_t)pos + 2] = nx[j][2];
+      }
+      ++pos;
+    }
+}
+
 // Order-preserving compaction of the valid (converged) rows of (points, normals): _filter_projection_result
 // (levelset_sampling.py:59-65 -> DSS/utils/__init__.py:149-169) for one packed cloud, in one pass with
 // the same ticket + decoupled look-back scan as project_step_kernel.  count_out receives the number
@@ -343,6 +468,38 @@ int isob200_project_step(float* points, float* normals, unsigned char* not_conve
                                                    tol, max_step, do_update, act_out, next_points,
                                                    count_out, (unsigned*)ws);
   ISO_CHECK_LAUNCH("project_step_kernel");
+  return ISOB200_OK;
+}
+
+// One iteration of SphereTracing.project_points (levelset_sampling.py:733-786) on the active rays; argument
+// conventions as isob200_project_step.  points (M,3) ray positions updated in place, dirs (M,3) ray directions,
+// eval (M,) last SDF value per ray, grad_out (M,3) last gradient per ray (may be NULL together with grad),
+// active_tol = 0.1 * proj_tolerance (:760), bound = padding + radius (:774).
+int isob200_trace_step(float* points, const float* dirs, float* eval, float* grad_out, const int* act_in, int A,
+                       const int* a_dev, const float* sdf, const float* grad, float active_tol, float alpha,
+                       float max_step, float bound, int do_update, int* act_out, float* next_points,
+                       int* count_out, void* ws, size_t ws_bytes, void* stream_) {
+  cudaStream_t st = (cudaStream_t)stream_;
+  ISO_CHECK_ARG(A >= 0, "trace_step: negative A");
+  ISO_CHECK_ARG(count_out, "trace_step: null count_out");
+  ISO_CHECK_ARG(a_dev != count_out, "trace_step: a_dev must not alias count_out");
+  if (A == 0) {
+    ISO_CUDA(cudaMemsetAsync(count_out, 0, sizeof(int), st));
+    return ISOB200_OK;
+  }
+  ISO_CHECK_ARG(points && dirs && eval && sdf && act_out && ws, "trace_step: null pointer");
+  ISO_CHECK_ARG(!grad_out == !grad, "trace_step: grad and grad_out go together");
+  ISO_CHECK_ARG(A < (1 << 30), "trace_step: A too large");
+  const size_t need = isob200_project_step_ws_bytes(A);
+  if (ws_bytes < need) {
+    set_error("trace_step: workspace too small (%zu < %zu)", ws_bytes, need);
+    return ISOB200_ERR_WORKSPACE;
+  }
+  ISO_CUDA(cudaMemsetAsync(ws, 0, need, st));
+  trace_step_kernel<<<div_up(A, PJ_TILE), PJ_THREADS, 0, st>>>(points, dirs, eval, grad_out, act_in, A, a_dev, sdf,
+                                                              grad, active_tol, alpha, max_step, bound, do_update,
+                                                              act_out, next_points, count_out, (unsigned*)ws);
+  ISO_CHECK_LAUNCH("trace_step_kernel");
   return ISOB200_OK;
 }
 

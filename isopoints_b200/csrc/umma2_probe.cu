@@ -141,7 +141,9 @@ umma2_probe_kernel(const float* __restrict__ A, const float* __restrict__ B, int
 // mode 1: cta_group::2, M = 128 (64 rows per CTA); mode 2: cta_group::2, M = 256 (128 rows per CTA).  N = 256.
 // mode + 10: the same shapes with 128-byte-swizzled K-major operands (rows of 128 B, 8-row atoms of 1 KB)
 // instead of the no-swizzle core-matrix layout the SIREN kernels use.  mode 3: cta_group::1, M = 64.
-// mode + 100 n: N = 256 >> n (n = 0..3) instead of 256.
+// mode + 100 n: N = 256 >> n (n = 0..3) instead of 256.  mode + 1000 (cta_group::1 only): consecutive MMAs
+// alternate between two accumulators (is the rate a dependent-accumulate latency?); mode + 2000
+// (cta_group::1 only): A operand read from tensor memory instead of shared memory.
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128)
 umma_rate_kernel(int mode_in, int reps, long long* __restrict__ cycles) {
   __shared__ __align__(1024) unsigned char sB[256 * 128];   // 256 rows x up to 128 B (contents irrelevant:
@@ -149,7 +151,8 @@ umma_rate_kernel(int mode_in, int reps, long long* __restrict__ cycles) {
   const bool sw128 = (mode_in / 10) % 10 != 0;
   const int mode = mode_in % 10 == 3 ? 0 : mode_in % 10;
   const bool m64 = mode_in % 10 == 3;
-  const uint32_t nn = 256u >> (mode_in / 100);
+  const uint32_t nn = 256u >> ((mode_in / 100) % 10);
+  const int variant = mode_in / 1000;   // 0 plain, 1 two accumulators, 2 A from TMEM
   __shared__ __align__(8) unsigned long long bars[1];
   __shared__ uint32_t tmem_ptr;
   const uint32_t rank = cluster_rank();
@@ -164,7 +167,7 @@ umma_rate_kernel(int mode_in, int reps, long long* __restrict__ cycles) {
   cluster_sync();
   if (warp == 0) {
     if (mode == 0) {
-      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_ptr)), "r"(256) : "memory");
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_ptr)), "r"(512) : "memory");
       asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     } else {
       asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_ptr)), "r"(256) : "memory");
@@ -188,8 +191,10 @@ umma_rate_kernel(int mode_in, int reps, long long* __restrict__ cycles) {
     const uint64_t db = sw128 ? (sw | ((smem_u32(sB) >> 4) & 0x3FFF)) : make_desc(smem_u32(sB), b_rows * 16);
     t0 = clock64();
     for (int r = 0; r < reps; ++r) {
-      if (mode == 0)
-        asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}\n" ::"r"(tmem_base), "l"(da), "l"(db), "r"(idesc), "r"(r ? 1u : 0u) : "memory");
+      if (mode == 0 && variant == 2)
+        asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n}\n" ::"r"(tmem_base), "r"(tmem_base + 256), "l"(db), "r"(idesc), "r"(r ? 1u : 0u) : "memory");
+      else if (mode == 0)
+        asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}\n" ::"r"(tmem_base + ((variant == 1 && (r & 1)) ? 256u : 0u)), "l"(da), "l"(db), "r"(idesc), "r"(r > 1 ? 1u : 0u) : "memory");
       else
         asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n}\n" ::"r"(tmem_base), "l"(da), "l"(db), "r"(idesc), "r"(r ? 1u : 0u) : "memory");
     }
@@ -203,7 +208,7 @@ umma_rate_kernel(int mode_in, int reps, long long* __restrict__ cycles) {
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   cluster_sync();
   if (warp == 0) {
-    if (mode == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256) : "memory");
+    if (mode == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
     else asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256) : "memory");
   }
 }
@@ -213,7 +218,8 @@ umma_rate_kernel(int mode_in, int reps, long long* __restrict__ cycles) {
 
 extern "C" int isob200_umma_rate(int mode, int reps, long long* cycles_dev, void* stream) {
   using namespace isob200;
-  ISO_CHECK_ARG(mode >= 0 && mode % 10 <= 3 && (mode / 10) % 10 <= 1 && mode < 400 && reps > 0 && cycles_dev,
+  ISO_CHECK_ARG(mode >= 0 && mode % 10 <= 3 && (mode / 10) % 10 <= 1 && (mode / 100) % 10 <= 3 && mode < 3000 &&
+                    (mode < 1000 || mode % 10 == 0 || mode % 10 == 3) && reps > 0 && cycles_dev,
                 "umma_rate: bad arguments");
   probe::umma_rate_kernel<<<2, 128, 0, (cudaStream_t)stream>>>(mode, reps, cycles_dev);
   ISO_CHECK_LAUNCH("umma_rate_kernel");

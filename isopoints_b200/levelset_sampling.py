@@ -438,6 +438,116 @@ class UniformProjection(LevelSetProjection):
                     'mask': valid_projection}
 
 
+class SphereTracing(LevelSetProjection):
+    """Ray marching onto the level set (levelset_sampling.py:663-808): every ray advances by
+    ``alpha * sdf`` along its direction (step clamped to 0.1) until ``|sdf| <= 0.1 * proj_tolerance``, it
+    would leave the sphere of radius ``radius + padding``, or ``proj_max_iters`` steps are used.
+
+    Same machinery as ``UniformProjection._project_points``: one SDF evaluation on the compacted active
+    rays + one fused update / compaction kernel (``isob200_trace_step``) per iteration; with the reference's
+    Siren decoder the loop runs off device-side ray counts without a read-back."""
+
+    def __init__(self, proj_max_iters=10, proj_tolerance=5e-5, max_points_per_pass=120000,
+                 alpha=1.0, radius=1.0, padding=0.1, **kwargs):
+        super().__init__(proj_max_iters=proj_max_iters, proj_tolerance=proj_tolerance,
+                         max_points_per_pass=max_points_per_pass)
+        self.alpha = alpha
+        self.radius = radius
+        self.padding = padding
+
+    def _eval(self, points, model, latent, forward_kwargs):
+        """SDF + input gradient of the active rays through autograd (:742-756), chunked."""
+        sdfs, grads = [], []
+        lat = [None] * (1 + points.shape[0] // self.max_points_per_pass) if latent is None else \
+            torch.split(latent, self.max_points_per_pass, dim=0)
+        for sub, c in zip(torch.split(points, self.max_points_per_pass, dim=0), lat):
+            with autograd.enable_grad():
+                net_input = sub.detach().requires_grad_(True)
+                network_eval = model.forward(net_input, c=c, **forward_kwargs).sdf
+                g = autograd.grad([network_eval], [net_input], torch.ones_like(network_eval))[0]
+            sdfs.append(network_eval.detach().reshape(-1))
+            grads.append(g.detach())
+        return torch.cat(sdfs).float().contiguous(), torch.cat(grads).float().contiguous()
+
+    def project_points(self, ray0: torch.Tensor, ray_direction: torch.Tensor, model,
+                       latent: Optional[torch.Tensor] = None, **forward_kwargs):
+        """Returns {'levelset_points' (shape of ray0), 'network_eval_on_levelset_points' (shape[:-1]),
+        'levelset_points_Dx' (the reference returns the points again under this key, :806), 'mask'}."""
+        shp = ray0.shape
+        _ext.require_cuda(ray0, ray_direction)
+        ray0, ray_direction = torch.broadcast_tensors(ray0, ray_direction)
+        if ray0.dtype != torch.float32:
+            raise RuntimeError("expected scalar type Float")
+        dev = ray0.device
+        points = ray0.reshape(-1, 3).clone()
+        dirs = ray_direction.reshape(-1, 3).float().contiguous()
+        M = points.shape[0]
+        if latent is not None and latent.nelement() > 0:
+            latent = latent.squeeze()
+            assert latent.ndim == 2
+            if len(shp) > 2:   # (N, C) per cloud -> one row per ray (:44-52)
+                latent = torch.repeat_interleave(latent, M // shp[0], dim=0) if latent.shape[0] > 1 \
+                    else latent.expand(M, -1)
+        else:
+            latent = None
+        lib = _ext.lib()
+        network_eval = torch.zeros((M,), dtype=torch.float32, device=dev)
+        grad = torch.zeros((M, 3), dtype=torch.float32, device=dev)
+        iters = int(self.proj_max_iters)
+        args = (float(0.1 * self.proj_tolerance), float(self.alpha), 0.1, float(self.padding + self.radius))
+        with autograd.no_grad():
+            model.eval()
+            fused = siren.match(model, forward_kwargs) if (M > 0 and latent is None) else None
+            if M > 0:
+                act = (torch.empty((M,), dtype=torch.int32, device=dev), torch.empty((M,), dtype=torch.int32, device=dev))
+                nxt = (torch.empty((M, 3), dtype=torch.float32, device=dev),
+                       torch.empty((M, 3), dtype=torch.float32, device=dev))
+                ws = _ext.workspace(lib.isob200_project_step_ws_bytes(M), dev)
+                st = _ext.stream(dev)
+            if fused is not None:
+                cnt = torch.zeros((iters + 2,), dtype=torch.int32, device=dev)   # active rays entering iteration it
+                pk = siren.packed(model, fused)
+                out = (torch.empty((M,), dtype=torch.float32, device=dev),
+                       torch.empty((M, 3), dtype=torch.float32, device=dev))
+                for it in range(iters + 1):
+                    last = (it == iters)
+                    cur = points if it == 0 else nxt[it & 1]
+                    n_dev = None if it == 0 else cnt[it:]
+                    siren.sdf_and_grad(model, cur, forward_kwargs, n_dev=n_dev, spec=fused, out=out, pk=pk)
+                    _ext.check(lib.isob200_trace_step(
+                        _ext.ptr(points), _ext.ptr(dirs), _ext.ptr(network_eval), _ext.ptr(grad),
+                        None if it == 0 else _ext.ptr(act[it & 1]), M, _ext.ptr(n_dev), _ext.ptr(out[0]),
+                        _ext.ptr(out[1]), *args, 0 if last else 1, _ext.ptr(act[(it + 1) & 1]),
+                        None if last else _ext.ptr(nxt[(it + 1) & 1]), _ext.ptr(cnt[it + 1:]), _ext.ptr(ws),
+                        ws.numel(), st))
+            elif M > 0:
+                count = torch.zeros((1,), dtype=torch.int32, device=dev)
+                A, it = M, 0
+                while True:
+                    cur = points if it == 0 else nxt[it & 1][:A]
+                    lat = latent if (latent is None or it == 0) else latent[act[it & 1][:A].long()]
+                    curr_sdf, curr_grad = self._eval(cur, model, lat, forward_kwargs)
+                    last = (it == iters)
+                    _ext.check(lib.isob200_trace_step(
+                        _ext.ptr(points), _ext.ptr(dirs), _ext.ptr(network_eval), _ext.ptr(grad),
+                        None if it == 0 else _ext.ptr(act[it & 1]), A, None, _ext.ptr(curr_sdf), _ext.ptr(curr_grad),
+                        *args, 0 if last else 1, _ext.ptr(act[(it + 1) & 1]),
+                        None if last else _ext.ptr(nxt[(it + 1) & 1]), _ext.ptr(count), _ext.ptr(ws), ws.numel(), st))
+                    if last:
+                        break
+                    A = int(count.item())   # the opaque SDF callback needs the batch shape
+                    if A == 0:
+                        break
+                    it += 1
+        valid_projection = network_eval.abs() <= self.proj_tolerance
+        levelset_points = points.view(shp)
+        self.last_gradient = grad.view(shp)   # d sdf / d x at the last evaluation of each ray (:745-757)
+        return {'levelset_points': levelset_points,
+                'network_eval_on_levelset_points': network_eval.view(shp[:-1]),
+                'levelset_points_Dx': levelset_points,
+                'mask': valid_projection.view(shp[:-1])}
+
+
 def _mask_padded_to_list(values, mask):
     """DSS/utils/__init__.py:119-134: per-cloud tensors of the mask == True rows."""
     return [values[b][mask[b]] for b in range(values.shape[0])]

@@ -759,3 +759,39 @@ def renderable_mask(points: torch.Tensor, normals, first_idx, num_points, w2v: t
     n = [int(x) for x in num_points]
     kept = [int(mask[int(f):int(f) + c].sum()) for f, c in zip(first_idx, n)]
     return mask, kept
+
+
+# =========================================================================================
+# SphereTracing.project_points  (DSS/models/levelset_sampling.py:679-808)
+# =========================================================================================
+def sphere_trace(model, ray0: torch.Tensor, ray_direction: torch.Tensor, proj_max_iters=10, proj_tolerance=5e-5,
+                 alpha=1.0, radius=1.0, padding=0.1, **kw):
+    """Packed rays (M,3).  Per iteration (:733-786): evaluate the SDF (+ gradient) at the active rays;
+    active = |sdf| > 0.1 tol and still inside the sphere; active rays advance by alpha * sdf * dir with
+    the step length clamped to 0.1; a ray whose new position leaves |x| < radius + padding keeps its old
+    position and retires.  Returns points (M,3), last sdf (M,), last gradient (M,3), mask = |sdf| <= tol."""
+    pts = ray0.clone()
+    M = pts.shape[0]
+    active = torch.ones(M, dtype=torch.bool)
+    inside = torch.ones(M, dtype=torch.bool)
+    sdf = torch.zeros(M)
+    grad = torch.zeros(M, 3)
+    trials = 0
+    while True:
+        if bool(active.any()):
+            s, g = sdf_and_grad(pts[active], model, **kw)
+            sdf[active] = s.reshape(-1)
+            grad[active] = g
+        active = (sdf.abs() > 1e-1 * proj_tolerance) & inside                      # :760-761
+        if not (bool(active.any()) and trials < proj_max_iters):                     # :764
+            break
+        move = alpha * sdf[active, None] * ray_direction[active]                    # :769-770
+        nrm = move.norm(dim=-1, keepdim=True)
+        move = move / nrm.clamp_min(1e-15) * nrm.clamp_max(0.1)                     # :771-772
+        new = pts[active] + move
+        ok = new.norm(dim=-1) < (padding + radius)                                  # :774-775
+        idx = torch.nonzero(active).reshape(-1)
+        inside[idx] = ok
+        pts[idx[ok]] = new[ok]                                                      # :776-777
+        trials += 1
+    return pts, sdf, grad, sdf.abs() <= proj_tolerance

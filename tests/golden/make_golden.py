@@ -16,6 +16,8 @@
   cameras (pytorch3d is not installed: the camera object hands out the 4x4 matrices directly and its
   world-to-view transform restates Transform3d.transform_points / transform_normals), the K = 7
   neighbour query through the reference's own `frnn_bf_cpu`.
+* sphere tracing (`--only trace`): the reference's `SphereTracing.project_points`
+  (levelset_sampling.py:679-808) on CPU tensors.
 The fixtures are small (< 1 MB total) and committed; the GPU box has no /root/reference.
 """
 import os
@@ -30,7 +32,8 @@ ROOT = os.path.dirname(os.path.dirname(HERE))
 sys.path.insert(0, ROOT)
 
 from oracle import ref_native, ref_python  # noqa: E402
-from tests.helpers import SphereSDF, TinySiren, make_splat_inputs, make_cameras, make_surface_points  # noqa: E402
+from tests.helpers import (SphereSDF, TinySiren, make_splat_inputs, make_cameras, make_surface_points,  # noqa: E402
+                           make_rays)
 
 
 class _CpuFrnn(types.SimpleNamespace):
@@ -177,11 +180,36 @@ def ewa_golden():
           "renderable", float(mask_renderable.float().mean()))
 
 
+def trace_golden(LS):
+    """SphereTracing.project_points (levelset_sampling.py:679-808) on CPU tensors: a blob SDF and the unit
+    sphere; rays that hit, graze and leave the bounding sphere."""
+    def same_shape(*args, device=None):   # pytorch3d.renderer.utils.convert_to_tensors_and_broadcast for
+        assert all(torch.is_tensor(a) and a.shape == args[0].shape for a in args)   # tensors of one shape
+        return list(args)
+    LS.convert_to_tensors_and_broadcast = same_shape
+    out = {}
+    for name, net, n, tol in (("siren", TinySiren(seed=3), 3000, 5e-5), ("sphere", SphereSDF(radius=0.5), 2000, 5e-5)):
+        ray0, dirs = make_rays(n, seed=21, target_radius=0.7)
+        tracer = LS.SphereTracing(proj_max_iters=25, proj_tolerance=tol, alpha=1.0, radius=1.0, padding=0.1)
+        res = tracer.project_points(ray0.view(2, -1, 3).clone(), dirs.view(2, -1, 3).clone(), net)
+        out[name + "_ray0"], out[name + "_dirs"] = ray0.numpy(), dirs.numpy()
+        out[name + "_points"] = res["levelset_points"].reshape(-1, 3).numpy()
+        out[name + "_eval"] = res["network_eval_on_levelset_points"].reshape(-1).numpy()
+        out[name + "_mask"] = res["mask"].reshape(-1).numpy()
+        moved = (res["levelset_points"].reshape(-1, 3) - ray0).norm(dim=-1)
+        print("trace %s: hit %.3f, moved mean %.3f, shapes %s %s" % (
+            name, float(res["mask"].float().mean()), float(moved.mean()), tuple(res["levelset_points"].shape),
+            tuple(res["mask"].shape)))
+    np.savez_compressed(os.path.join(HERE, "sphere_trace.npz"), proj_max_iters=25, **out)
+
+
 def main():
     torch.set_num_threads(4)
     if "--only" in sys.argv and sys.argv[sys.argv.index("--only") + 1] == "ewa":
         ref_python.load(frnn_module=_CpuFrnn)
         return ewa_golden()
+    if "--only" in sys.argv and sys.argv[sys.argv.index("--only") + 1] == "trace":
+        return trace_golden(ref_python.load(frnn_module=_CpuFrnn).levelset_sampling)
     ref = ref_python.load(frnn_module=_CpuFrnn)
     LS = ref.levelset_sampling
 
@@ -289,6 +317,7 @@ def main():
                         idx=idx.numpy(), zbuf=zbuf.numpy(), qvalue=qv.numpy(), occ=occ.numpy(), **inp)
     print("splat: occupied", float(occ.mean()))
     ewa_golden()
+    trace_golden(LS)
 
 
 if __name__ == "__main__":

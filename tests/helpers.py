@@ -195,3 +195,15 @@ def make_surface_points(pts_per_view, seed, noise=0.02):
     first = np.concatenate([[0], np.cumsum(num)[:-1]]).astype(np.int64)
     return (torch.from_numpy(pts.astype(np.float32)), torch.from_numpy(nrm.astype(np.float32)),
             torch.from_numpy(first), torch.from_numpy(num))
+
+
+def make_rays(n, seed, start_radius=1.0, target_radius=0.9):
+    """Rays from a sphere of radius ``start_radius`` towards random points within ``target_radius`` of the
+    origin (unit directions): most hit a blob around the origin, some graze it or leave the sphere."""
+    g = torch.Generator().manual_seed(seed)
+    o = torch.randn(n, 3, generator=g)
+    o = o / o.norm(dim=-1, keepdim=True) * start_radius
+    t = torch.randn(n, 3, generator=g)
+    t = t / t.norm(dim=-1, keepdim=True) * target_radius * torch.rand(n, 1, generator=g) ** (1.0 / 3)
+    d = t - o
+    return o.contiguous(), (d / d.norm(dim=-1, keepdim=True)).contiguous()

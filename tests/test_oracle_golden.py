@@ -157,3 +157,16 @@ def test_renderable_mask_matches_reference(golden):
     m, kept = port.renderable_mask(pts, nrm, first, num, w2v, nmat, float(g["znear"]), float(g["zfar"]))
     assert np.array_equal(m.numpy(), g["mask_renderable"])
     assert sum(kept) == int(g["mask_renderable"].sum()) and 0.2 < m.float().mean() < 0.8
+
+
+def test_sphere_tracing_matches_reference(golden):
+    """oracle/port.py sphere_trace against SphereTracing.project_points run from the reference tree."""
+    from tests.helpers import SphereSDF as _Sphere
+    g = golden("sphere_trace")
+    for name, net in (("siren", TinySiren(seed=3)), ("sphere", _Sphere(radius=0.5))):
+        pts, sdf, grad, mask = port.sphere_trace(net, torch.as_tensor(g[name + "_ray0"]), torch.as_tensor(g[name + "_dirs"]),
+                                                 proj_max_iters=int(g["proj_max_iters"]), proj_tolerance=5e-5)
+        assert np.array_equal(mask.numpy(), g[name + "_mask"]), name
+        np.testing.assert_allclose(pts.numpy(), g[name + "_points"], rtol=1e-6, atol=1e-6)
+        np.testing.assert_allclose(sdf.numpy(), g[name + "_eval"], rtol=1e-5, atol=1e-7)
+        assert 0.2 < mask.float().mean() < 0.9, name      # rays that hit and rays that leave the sphere
