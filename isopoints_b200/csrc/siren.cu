@@ -181,7 +181,8 @@ siren_sdf_grad_kernel(const float* __restrict__ x, int n_max, const int* __restr
 
   const float* hdr = reinterpret_cast<const float*>(blob);
   const size_t img0 = off_images(L);
-  const int n_gemm = 2 * L;  // per tile
+  const bool fwd_only = nw.mode == 1;            // ray marching needs the value only: L GEMMs, no tape
+  const int n_gemm = fwd_only ? L : 2 * L;      // per tile
 
   if (warp == N_EPI_WARPS) {
     // ===================== weight producer =====================
@@ -291,6 +292,28 @@ siren_sdf_grad_kernel(const float* __restrict__ x, int n_max, const int* __restr
       if (lane == 0) mbar_arrive(bar_a_ready + 8 * kb);
     };
 
+    // append the still-active rows of this tile to the next active list: in-tile order, one reservation per
+    // tile.  Called by the four cslice == 0 warps (they hold the tile's 128 rows), all lanes.
+    auto append_active = [&](bool still, int p, float nx, float ny, float nz) {
+      int* cmp = reinterpret_cast<int*>(smem + SM_CMP);
+      const unsigned bal = __ballot_sync(0xffffffffu, still);
+      if (lane == 0) cmp[q] = __popc(bal);
+      asm volatile("bar.sync 5, 128;" ::: "memory");
+      const int c0 = cmp[0], c1 = cmp[1], c2 = cmp[2], c3 = cmp[3];
+      if (threadIdx.x == 0) cmp[4] = (c0 + c1 + c2 + c3) ? atomicAdd(nw.count_out, c0 + c1 + c2 + c3) : 0;
+      asm volatile("bar.sync 5, 128;" ::: "memory");
+      if (still) {
+        const int pos = cmp[4] + (q > 0 ? c0 : 0) + (q > 1 ? c1 : 0) + (q > 2 ? c2 : 0) +
+                        __popc(bal & ((1u << lane) - 1u));
+        nw.act_out[pos] = p;
+        if (nw.next_points) {
+          nw.next_points[3 * (size_t)pos] = nx;
+          nw.next_points[3 * (size_t)pos + 1] = ny;
+          nw.next_points[3 * (size_t)pos + 2] = nz;
+        }
+      }
+    };
+
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int grow = tile * TM + row;
       float px = 0.f, py = 0.f, pz = 0.f;
@@ -339,7 +362,7 @@ siren_sdf_grad_kernel(const float* __restrict__ x, int n_max, const int* __restr
           // the cos factors the NEXT backward stage will read were written up to 2(L-1) stages ago and
           // may have left L2: start pulling this thread's 16 lines back in one stage ahead
           const int lp = fwd ? (l == L ? L - 1 : 0) : l - 2;   // stash slot (1-based layer) read next
-          if (lp >= 1) {
+          if (lp >= 1 && !fwd_only) {
             const float4* pf = stash + (size_t)(lp - 1) * 64 * TM + row;
 #pragma unroll
             for (int kb = 0; kb < NKB; ++kb) {
@@ -389,9 +412,11 @@ siren_sdf_grad_kernel(const float* __restrict__ x, int n_max, const int* __restr
             }
             publish(kb, o);
             // global traffic right after the hand-off fence (which waits for everything in flight)
-            const int col4 = kb * 8 + cslice * 2;
-            st[(size_t)col4 * TM] = make_float4(cc[0].x, cc[0].y, cc[1].x, cc[1].y);
-            st[(size_t)(col4 + 1) * TM] = make_float4(cc[2].x, cc[2].y, cc[3].x, cc[3].y);
+            if (!fwd_only) {
+              const int col4 = kb * 8 + cslice * 2;
+              st[(size_t)col4 * TM] = make_float4(cc[0].x, cc[0].y, cc[1].x, cc[1].y);
+              st[(size_t)(col4 + 1) * TM] = make_float4(cc[2].x, cc[2].y, cc[3].x, cc[3].y);
+            }
             if (kb + 1 < NKB) {
               bwn0 = __ldg(bw4 + (kb + 1) * 8);
               bwn1 = __ldg(bw4 + (kb + 1) * 8 + 1);
@@ -426,7 +451,7 @@ siren_sdf_grad_kernel(const float* __restrict__ x, int n_max, const int* __restr
               acc2 = __ffma2_rn(sn, ww[pr], acc2);
               o[pr] = __fmul2_rn(__fmul2_rn(cp, signed_scale(gls, sx, sy)), ww[pr]);
             }
-            publish(kb, o);
+            if (!fwd_only) publish(kb, o);   // forward-only: no reverse GEMM follows, the next A is the next tile's
           }
           const float acc_sdf = acc2.x + acc2.y;
           row_scale_inv = gl_scale_inv;
@@ -437,6 +462,41 @@ siren_sdf_grad_kernel(const float* __restrict__ x, int n_max, const int* __restr
             if (grow < n && sdf_out) sdf_out[grow] = sdf_row;
           }
           row_barrier(q);
+          if (fwd_only && cslice == 0) {
+            // ---- fused ray-marching step on this row (same arithmetic as trace_step_kernel, project.cu) ----
+            bool still = false;
+            int p = 0;
+            float nx = 0.f, ny = 0.f, nz = 0.f;
+            if (grow < n) {
+              p = nw.act_in ? nw.act_in[grow] : grow;
+              nw.eval[p] = sdf_row;
+              still = fabsf(sdf_row) > nw.tol;
+              if (still) {
+                nx = px; ny = py; nz = pz;   // the evaluated position IS points[p]
+                if (nw.do_update) {
+                  const float af = __fmul_rn(nw.alpha, sdf_row);
+                  const float mx = __fmul_rn(af, nw.dirs[3 * (size_t)p]);
+                  const float my = __fmul_rn(af, nw.dirs[3 * (size_t)p + 1]);
+                  const float mz = __fmul_rn(af, nw.dirs[3 * (size_t)p + 2]);
+                  const float nrm = sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(mx, mx), __fmul_rn(my, my)), __fmul_rn(mz, mz)));
+                  const float dn = fmaxf(nrm, 1e-15f);
+                  const float len = fminf(nrm, nw.max_step);
+                  nx = __fadd_rn(nx, __fmul_rn(__fdiv_rn(mx, dn), len));
+                  ny = __fadd_rn(ny, __fmul_rn(__fdiv_rn(my, dn), len));
+                  nz = __fadd_rn(nz, __fmul_rn(__fdiv_rn(mz, dn), len));
+                  const float r = sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(nx, nx), __fmul_rn(ny, ny)), __fmul_rn(nz, nz)));
+                  if (r < nw.bound) {
+                    nw.points[3 * (size_t)p] = nx;
+                    nw.points[3 * (size_t)p + 1] = ny;
+                    nw.points[3 * (size_t)p + 2] = nz;
+                  } else {
+                    still = false;               // left the sphere: old position stays, the ray retires
+                  }
+                }
+              }
+            }
+            append_active(still, p, nx, ny, nz);
+          }
         } else if (l > 1) {
           // ---- E_b(l): g_{l-1} = acc / scales ; gp_{l-1} = g_{l-1} * c_{l-1} -> A (row-scaled) ----
           const float sc = wsi * row_scale_inv;
@@ -546,7 +606,6 @@ siren_sdf_grad_kernel(const float* __restrict__ x, int n_max, const int* __restr
           row_barrier(q);
           if (nw.points && cslice == 0) {
             // ---- fused Newton step on this row (warps 0..3 hold the tile's 128 rows) ----
-            int* cmp = reinterpret_cast<int*>(smem + SM_CMP);
             bool still = false;
             int p = 0;
             float nx = 0.f, ny = 0.f, nz = 0.f;
@@ -577,23 +636,7 @@ siren_sdf_grad_kernel(const float* __restrict__ x, int n_max, const int* __restr
                 }
               }
             }
-            // append the still-active rows: in-tile order, one reservation per tile
-            const unsigned bal = __ballot_sync(0xffffffffu, still);
-            if (lane == 0) cmp[q] = __popc(bal);
-            asm volatile("bar.sync 5, 128;" ::: "memory");
-            const int c0 = cmp[0], c1 = cmp[1], c2 = cmp[2], c3 = cmp[3];
-            if (threadIdx.x == 0) cmp[4] = (c0 + c1 + c2 + c3) ? atomicAdd(nw.count_out, c0 + c1 + c2 + c3) : 0;
-            asm volatile("bar.sync 5, 128;" ::: "memory");
-            if (still) {
-              const int pos = cmp[4] + (q > 0 ? c0 : 0) + (q > 1 ? c1 : 0) + (q > 2 ? c2 : 0) +
-                              __popc(bal & ((1u << lane) - 1u));
-              nw.act_out[pos] = p;
-              if (nw.next_points) {
-                nw.next_points[3 * (size_t)pos] = nx;
-                nw.next_points[3 * (size_t)pos + 1] = ny;
-                nw.next_points[3 * (size_t)pos + 2] = nz;
-              }
-            }
+            append_active(still, p, nx, ny, nz);
           }
         }
         if (tstamp) tstamp[2] = clock64();
@@ -673,7 +716,7 @@ static int launch_siren(const float* x, int n_max, const int* n_dev, const void*
     set_error("%s: scratch too small", who);
     return ISOB200_ERR_WORKSPACE;
   }
-  if (g_siren_pair_mode && !dbg)
+  if (g_siren_pair_mode && !dbg && nw.mode == 0)
     return launch_siren_pair(x, n_max, n_dev, blob, n_hidden, sdf, grad, scratch, nw, (cudaStream_t)stream);
   {
     // opt-in to > 48 KB of dynamic shared memory: once per device
@@ -716,6 +759,21 @@ int isob200_siren_project_step(const float* x, int n_max, const int* n_dev, cons
   Newton nw = {points, normals, not_converged, act_in, act_out, next_points, count_out, tol, max_step, do_update};
   return launch_siren(x, n_max, n_dev, blob, n_hidden, nullptr, nullptr, scratch, scratch_bytes, nullptr, -1, nw,
                       stream, "siren_project_step");
+}
+
+// One iteration of SphereTracing.project_points (levelset_sampling.py:733-786) with the SDF evaluation
+// fused in: the FORWARD half of the SIREN kernel only (the march needs no gradient, so half the GEMMs and
+// no tape) followed by the update rule of isob200_trace_step.  Conventions as isob200_siren_project_step.
+int isob200_siren_trace_step(const float* x, int n_max, const int* n_dev, const void* blob, int n_hidden,
+                             void* scratch, size_t scratch_bytes, float* points, const float* dirs, float* eval,
+                             const int* act_in, float active_tol, float alpha, float max_step, float bound,
+                             int do_update, int* act_out, float* next_points, int* count_out, void* stream) {
+  ISO_CHECK_ARG(n_max == 0 || (points && dirs && eval && act_out && count_out), "siren_trace_step: null pointer");
+  ISO_CHECK_ARG(n_dev != count_out, "siren_trace_step: n_dev must not alias count_out");
+  Newton nw = {points, nullptr, nullptr, act_in, act_out, next_points, count_out, active_tol, max_step, do_update,
+               1, dirs, eval, alpha, bound};
+  return launch_siren(x, n_max, n_dev, blob, n_hidden, nullptr, nullptr, scratch, scratch_bytes, nullptr, -1, nw,
+                      stream, "siren_trace_step");
 }
 
 }  // extern "C"

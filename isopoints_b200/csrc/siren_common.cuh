@@ -288,6 +288,12 @@ struct Newton {
   int* count_out;            // number of still-active rows (zero before the launch)
   float tol, max_step;
   int do_update;
+  // mode 1: ray marching (SphereTracing.project_points, levelset_sampling.py:733-786) on the forward half of
+  // the network only -- no gradient, no tape: rays advance by alpha * sdf along dirs, tol = 0.1 * proj_tolerance
+  int mode;
+  const float* dirs;         // (M,3) ray directions
+  float* eval;               // (M) last sdf per ray
+  float alpha, bound;        // step factor; radius + padding of the bounding sphere
 };
 
 // eps_denom(x, eps) of DSS/utils/mathHelper.py:14-18: (sign(x) + [x == 0]) * max(|x|, eps)

@@ -505,21 +505,24 @@ class SphereTracing(LevelSetProjection):
                 ws = _ext.workspace(lib.isob200_project_step_ws_bytes(M), dev)
                 st = _ext.stream(dev)
             if fused is not None:
+                # The reference's Siren decoder: one kernel per iteration -- the FORWARD half of the fused
+                # tcgen05 SDF kernel (the march never uses the gradient the reference computes at :745-757),
+                # the update of :764-777 and the compaction of the still-active rays -- off device-side ray
+                # counts: the whole loop is enqueued without a read-back.
                 cnt = torch.zeros((iters + 2,), dtype=torch.int32, device=dev)   # active rays entering iteration it
-                pk = siren.packed(model, fused)
-                out = (torch.empty((M,), dtype=torch.float32, device=dev),
-                       torch.empty((M, 3), dtype=torch.float32, device=dev))
+                blob, scratch, n_hidden = siren.packed(model, fused)
                 for it in range(iters + 1):
                     last = (it == iters)
                     cur = points if it == 0 else nxt[it & 1]
-                    n_dev = None if it == 0 else cnt[it:]
-                    siren.sdf_and_grad(model, cur, forward_kwargs, n_dev=n_dev, spec=fused, out=out, pk=pk)
-                    _ext.check(lib.isob200_trace_step(
-                        _ext.ptr(points), _ext.ptr(dirs), _ext.ptr(network_eval), _ext.ptr(grad),
-                        None if it == 0 else _ext.ptr(act[it & 1]), M, _ext.ptr(n_dev), _ext.ptr(out[0]),
-                        _ext.ptr(out[1]), *args, 0 if last else 1, _ext.ptr(act[(it + 1) & 1]),
-                        None if last else _ext.ptr(nxt[(it + 1) & 1]), _ext.ptr(cnt[it + 1:]), _ext.ptr(ws),
-                        ws.numel(), st))
+                    _ext.check(lib.isob200_siren_trace_step(
+                        _ext.ptr(cur), M, None if it == 0 else _ext.ptr(cnt[it:]), _ext.ptr(blob), n_hidden,
+                        _ext.ptr(scratch), scratch.numel(), _ext.ptr(points), _ext.ptr(dirs), _ext.ptr(network_eval),
+                        None if it == 0 else _ext.ptr(act[it & 1]), *args, 0 if last else 1,
+                        _ext.ptr(act[(it + 1) & 1]), None if last else _ext.ptr(nxt[(it + 1) & 1]),
+                        _ext.ptr(cnt[it + 1:]), st))
+                siren.STATS["calls"] += iters + 1
+                siren.STATS["rows"] += M
+                grad = None
             elif M > 0:
                 count = torch.zeros((1,), dtype=torch.int32, device=dev)
                 A, it = M, 0
@@ -541,7 +544,9 @@ class SphereTracing(LevelSetProjection):
                     it += 1
         valid_projection = network_eval.abs() <= self.proj_tolerance
         levelset_points = points.view(shp)
-        self.last_gradient = grad.view(shp)   # d sdf / d x at the last evaluation of each ray (:745-757)
+        # d sdf / d x at the last evaluation of each ray (:745-757; not part of the reference's return value):
+        # available on the autograd path only, the fused path evaluates the forward half of the network
+        self.last_gradient = None if grad is None else grad.view(shp)
         return {'levelset_points': levelset_points,
                 'network_eval_on_levelset_points': network_eval.view(shp[:-1]),
                 'levelset_points_Dx': levelset_points,
