@@ -344,6 +344,8 @@ def run_ours(args):
             import bench_splat
             line["frnn"] = bench_frnn.run(args, dev, peaks, peak_src)
             line["splat"] = bench_splat.run(args, dev, peaks, peak_src)
+            import bench_trace
+            line["trace"] = bench_trace.run(dev, steps=3)
         print(json.dumps(line))
     if world > 1:
         import torch.distributed as dist

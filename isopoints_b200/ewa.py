@@ -10,7 +10,9 @@ Mirrors, with the reference's names and argument meaning:
 * ``SurfaceSplatting.filter_renderable`` (:220-255) -> ``filter_renderable`` (mask kernel + ordered
   compaction; the reference rebuilds Python lists of boolean-indexed padded tensors per view),
 * ``SurfaceSplatting.forward`` (:584-661) -> ``SurfaceSplatting.forward``: filter -> parameters -> screen
-  transform (PyTorch, differentiable, as in the reference) -> ``rasterize_elliptical_points``.
+  transform (PyTorch, differentiable, as in the reference) -> ``rasterize_elliptical_points``,
+* ``SurfaceSplattingRenderer.forward`` (DSS/core/renderer.py:36-82) -> ``SurfaceSplattingRenderer.forward``:
+  rasterise + ``splat.blend_rgba`` -> (N,S,S,4) RGBA.
 
 Cameras are duck-typed on what the reference calls (pytorch3d's camera API; pytorch3d itself is not a
 dependency): ``get_full_projection_transform().get_matrix()`` and
@@ -24,7 +26,8 @@ import torch
 
 from . import _ext
 from .frnn import frnn_grid_points
-from .splat import PointFragments, gather_with_neg_idx, rasterize_elliptical_points, visibility_mask
+from .splat import (PointFragments, blend_rgba, gather_with_neg_idx, rasterize_elliptical_points,
+                    visibility_mask)
 from .structures import Pointclouds, packed_to_padded
 
 MAX_VIEWS = 64   # csrc/ewa.cu: camera matrices are staged in shared memory
@@ -257,7 +260,51 @@ class SurfaceSplatting:
             points_per_pixel=rs.points_per_pixel, bin_size=rs.bin_size, max_points_per_bin=rs.max_points_per_bin,
             radii_backward_scaler=rs.radii_backward_scaler, clip_pts_grad=rs.clip_pts_grad)
         frag_scaler = gather_with_neg_idx(info["scaler"], 0, idx.view(-1).long()).view_as(qvalue)   # :634-636
-        return PointFragments(idx=idx, zbuf=zbuf, qvalue=qvalue, scaler=frag_scaler, occupancy=occ), filtered
+        fragments = PointFragments(idx=idx, zbuf=zbuf, qvalue=qvalue, scaler=frag_scaler, occupancy=occ)
+        self._last = (fragments, info["scaler"])   # per-point scaler of these fragments, for the renderer's blend
+        return fragments, filtered
+
+    __call__ = forward
+
+
+class SurfaceSplattingRenderer:
+    """DSS/core/renderer.py:14-82: rasterise, weight the fragments with scaler * exp(-Q/2), composite the point
+    features with pytorch3d's NormWeightedCompositor rule and append the occupancy as alpha -- the last three
+    steps in one kernel (``splat.blend_rgba``), differentiable w.r.t. the features; gradients to the points
+    come from the occupancy / depth terms of the rasteriser exactly as in the reference."""
+
+    def __init__(self, rasterizer, compositor="norm_weighted", antialiasing_sigma: float = 1.0,
+                 density: float = 1e-4, frnn_radius=-1):
+        if compositor is None:
+            raise NotImplementedError("compositor=None selects pytorch3d's un-normalised weighted_sum "
+                                      "(renderer.py:59-65); only the NormWeightedCompositor rule is built")
+        self.rasterizer = rasterizer
+        self.compositor = compositor
+        self.cameras = rasterizer.cameras
+        self.antialiasing_sigma = antialiasing_sigma
+        self.density = density
+        self.frnn_radius = frnn_radius
+
+    def forward(self, point_clouds, **kwargs):
+        if point_clouds.isempty():
+            return None
+        fragments = kwargs.get("fragments", None)
+        if fragments is None:
+            fragments, point_clouds = self.rasterizer(point_clouds, **kwargs)
+        last = getattr(self.rasterizer, "_last", None)
+        if last is not None and last[0] is fragments:
+            scaler = last[1]
+        else:
+            # fragments from elsewhere: every fragment of a point carries that point's scaler (rasterizer.py:634)
+            P = int(point_clouds.num_points_per_cloud().sum().item())
+            m = fragments.idx >= 0
+            scaler = fragments.scaler.new_zeros(P)
+            scaler[fragments.idx[m].long()] = fragments.scaler[m]
+        pts_rgb = point_clouds.features_packed()[:, :3]
+        images = blend_rgba(fragments.idx, fragments.qvalue, fragments.occupancy, scaler, pts_rgb)
+        if kwargs.get("verbose", False):
+            return images, fragments
+        return images
 
     __call__ = forward
 
@@ -274,5 +321,5 @@ def PointsRasterizationSettings(**kw):
     return SimpleNamespace(**d)
 
 
-__all__ = ["SurfaceSplatting", "PointsRasterizationSettings", "compute_isotropic_vrk_h", "get_per_point_info",
+__all__ = ["SurfaceSplatting", "SurfaceSplattingRenderer", "PointsRasterizationSettings", "compute_isotropic_vrk_h", "get_per_point_info",
            "renderable_mask", "visibility_mask", "packed_to_padded"]

@@ -360,14 +360,19 @@ class _Blend(autograd.Function):
 
     @staticmethod
     def backward(ctx, grad_out):
-        idx, weights = ctx.saved_tensors
         shape, eps = ctx.meta
-        N, H, W, K = idx.shape
-        gfeat = torch.zeros(shape, dtype=torch.float32, device=idx.device)
-        _ext.check(_ext.lib().isob200_splat_blend_backward(
-            _ext.ptr(idx), _ext.ptr(weights), _ext.ptr(grad_out.contiguous()), N * H * W, K, shape[1], float(eps),
-            _ext.ptr(gfeat), gfeat.stride(0), _ext.stream(idx.device)))
-        return None, None, None, None, gfeat, None
+        gfeat = None
+        if ctx.needs_input_grad[4]:
+            idx, weights = ctx.saved_tensors
+            N, H, W, K = idx.shape
+            gfeat = torch.zeros(shape, dtype=torch.float32, device=idx.device)
+            _ext.check(_ext.lib().isob200_splat_blend_backward(
+                _ext.ptr(idx), _ext.ptr(weights), _ext.ptr(grad_out.contiguous()), N * H * W, K, shape[1], float(eps),
+                _ext.ptr(gfeat), gfeat.stride(0), _ext.stream(idx.device)))
+        # alpha = occupancy is copied into the last channel (renderer.py:76-78: torch.cat with the mask), so its
+        # gradient goes straight back to the rasteriser's occupancy output
+        gocc = grad_out[..., shape[1]].contiguous() if ctx.needs_input_grad[2] else None
+        return None, None, gocc, None, gfeat, None
 
 
 def blend_rgba(idx, qvalue, occupancy, scaler, features, eps: float = NORM_WEIGHT_EPS):

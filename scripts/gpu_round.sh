@@ -7,6 +7,19 @@ timeout 900 python -m pytest tests -m gpu -q 2>&1 | tail -40 > gpurun_out/pytest
 timeout 200 python __graft_entry__.py smoke 2>&1 | tail -2
 timeout 600 python bench.py --steps 5 --warmup 3 > gpurun_out/bench.json 2> gpurun_out/bench.err; tail -c 3000 gpurun_out/bench.json; grep -v Warning gpurun_out/bench.err | tail -5
 timeout 300 python bench.py --impl reference --steps 1 --warmup 0 > gpurun_out/bench_reference.json 2>/dev/null; tail -c 300 gpurun_out/bench_reference.json
+if [ "${1:-}" = "prof2" ]; then
+  # kernels added after the r01g captures: EWA per-point parameters, the renderable mask, forward-only SIREN
+  timeout 300 python bench_splat.py --steps 5 > gpurun_out/bench_splat.json 2>/dev/null
+  timeout 300 python bench_trace.py --steps 5 > gpurun_out/bench_trace.json 2>/dev/null; tail -c 600 gpurun_out/bench_trace.json
+  timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_c4.csv python bench_splat.py --steps 1 > gpurun_out/ncu_c4.log 2>&1
+  timeout 600 ncu --set full --clock-control none --import-source on -k regex:point_params_x4 -s 3 -c 1 -f -o gpurun_out/prof_ewa_point_params python bench_splat.py --steps 1 > gpurun_out/ncu_ewa.log 2>&1
+  timeout 600 ncu --set full --clock-control none --import-source on -k regex:renderable_mask -s 3 -c 1 -f -o gpurun_out/prof_renderable_mask python bench_splat.py --steps 1 > gpurun_out/ncu_mask.log 2>&1
+  # first launch of the 4th marching pass (3 warm-up passes x 11 launches skipped): all 200 000 rays live
+  timeout 600 ncu --set full --clock-control none --import-source on -k regex:siren_sdf_grad -s 33 -c 1 -f -o gpurun_out/prof_siren_forward_only python bench_trace.py --steps 1 > gpurun_out/ncu_siren_fwd.log 2>&1
+  timeout 900 compute-sanitizer --tool memcheck --error-exitcode 7 python -m pytest tests/test_gpu_ewa.py tests/test_gpu_trace.py -m gpu -q -k "not 40000 and not views0 and not views3" > gpurun_out/sanitizer_memcheck_new.log 2>&1; echo "memcheck(new) rc=$?"; tail -2 gpurun_out/sanitizer_memcheck_new.log
+  timeout 600 compute-sanitizer --tool racecheck --error-exitcode 7 python -m pytest tests/test_gpu_trace.py tests/test_gpu_ewa.py -m gpu -q -k "forward_only_step or trace_step_kernel or unaligned or reference_golden" > gpurun_out/sanitizer_racecheck_new.log 2>&1; echo "racecheck(new) rc=$?"; tail -2 gpurun_out/sanitizer_racecheck_new.log
+  ls gpurun_out/
+fi
 if [ "${1:-}" = "prof" ]; then
   timeout 500 python scripts/ref_cuda_timing.py 2>&1 | grep -v Warning | tail -1
   timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 6000 --csv --log-file gpurun_out/launches_c2.csv python bench.py --steps 1 --warmup 3 > gpurun_out/ncu_c2.log 2>&1

@@ -132,7 +132,8 @@ def main():
             txt = raw(rep) + "\n\nhottest source lines (share of executed instructions):\n" + hot_lines(rep) + "\n"
             open(os.path.join(PROF, "%s_%s.txt" % (tag, f[:-8])), "w").write(txt)
     json.dump(tr, open(tpath, "w"), indent=1, sort_keys=True)
-    for f in ("bench.json", "bench_reference.json", "bench_splat.json", "bench_n2.json", "ref_cuda_timing.json"):
+    for f in ("bench.json", "bench_reference.json", "bench_splat.json", "bench_trace.json", "bench_n2.json",
+              "ref_cuda_timing.json"):
         p = os.path.join(OUT, f)
         if os.path.exists(p):
             lines = [l for l in open(p).read().splitlines() if l.startswith("{")]

@@ -211,6 +211,40 @@ def test_surface_splatting_forward_and_gradient():
     assert world.grad is not None and bool(torch.isfinite(world.grad).all()) and float(world.grad.abs().sum()) > 0
 
 
+def test_renderer_rgba_matches_oracle_blend_and_backpropagates():
+    """SurfaceSplattingRenderer.forward (renderer.py:36-82): RGBA from point clouds + cameras in one call."""
+    views = [5000] * 2
+    pts, nrm, first, num = make_surface_points(views, seed=12, noise=0.002)
+    w2v, proj, nmat = make_cameras(2, seed=13)
+    S, K = 96, 4
+    rs = ewa.PointsRasterizationSettings(image_size=S, points_per_pixel=K, bin_size=16, backface_culling=True)
+    ras = ewa.SurfaceSplatting(cameras=_Cams(w2v.to(DEV), proj.to(DEV), znear=0.5), raster_settings=rs)
+    renderer = ewa.SurfaceSplattingRenderer(ras)
+    rgb = torch.rand(pts.shape[0], 3).to(DEV).requires_grad_(True)
+    world = pts.to(DEV).requires_grad_(True)
+    pc = Pointclouds(points=list(torch.split(world, views)), normals=list(torch.split(nrm.to(DEV), views)),
+                     features=list(torch.split(rgb, views)))
+    img, frag = renderer(pc, verbose=True)
+    assert tuple(img.shape) == (2, S, S, 4)
+    filtered_rgb = rgb.detach()[ras.filter_renderable(pc)[1]].cpu().numpy()
+    sc = ras._last[1].cpu().numpy()
+    want = port.blend(frag.idx.cpu().numpy(), frag.qvalue.cpu().numpy(), frag.occupancy.detach().cpu().numpy(), sc,
+                      filtered_rgb)
+    np.testing.assert_allclose(img.detach().cpu().numpy(), want, rtol=1e-4, atol=1e-5)
+    # fragments handed in from outside: the per-point scaler is recovered from the per-fragment one
+    img2 = renderer(ras.filter_renderable(pc)[0], fragments=PointFragmentsCopy(frag))
+    assert torch.equal(img2.detach(), img.detach())
+    (img[..., :3].sum() + img[..., 3].sum()).backward()
+    assert float(rgb.grad.abs().sum()) > 0 and float(world.grad.abs().sum()) > 0
+    with pytest.raises(NotImplementedError):
+        ewa.SurfaceSplattingRenderer(ras, compositor=None)
+
+
+def PointFragmentsCopy(frag):
+    from isopoints_b200.splat import PointFragments
+    return PointFragments(*[t.detach().clone() for t in frag])
+
+
 def test_forward_with_nothing_renderable_returns_empty_fragments():
     pts, nrm, first, num = make_surface_points([500, 500], seed=2)
     w2v, proj, nmat = make_cameras(2, seed=3)
