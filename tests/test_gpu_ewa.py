@@ -228,7 +228,7 @@ def test_renderer_rgba_matches_oracle_blend_and_backpropagates():
     assert tuple(img.shape) == (2, S, S, 4)
     filtered_rgb = rgb.detach()[ras.filter_renderable(pc)[1]].cpu().numpy()
     sc = ras._last[1].cpu().numpy()
-    want = port.blend(frag.idx.cpu().numpy(), frag.qvalue.cpu().numpy(), frag.occupancy.detach().cpu().numpy(), sc,
+    want = port.blend(frag.idx.cpu().numpy(), frag.qvalue.detach().cpu().numpy(), frag.occupancy.detach().cpu().numpy(), sc,
                       filtered_rgb)
     np.testing.assert_allclose(img.detach().cpu().numpy(), want, rtol=1e-4, atol=1e-5)
     # fragments handed in from outside: the per-point scaler is recovered from the per-fragment one
