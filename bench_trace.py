@@ -56,7 +56,54 @@ def run(dev, steps=5):
         out[name] = {"ms_per_step": ms, "rays_per_s": RAYS / (ms * 1e-3), "hit_frac": float(res["mask"].float().mean()),
                      "gpu_launches_per_step": (lib.isob200_launch_count() - l0) / steps}
     out["speedup"] = out["opaque_module_autograd"]["ms_per_step"] / out["fused_forward_only"]["ms_per_step"]
+    out["ray_tracing"] = run_ray_tracing(dev, steps, flush)
     return out
+
+
+def run_ray_tracing(dev, steps, flush, cams=4, pixels=50_000):
+    """IDR RayTracing.forward (levelset_sampling.py:810-1167; isopoints_b200/ray_tracing.py), eval mode, on the
+    same network: 4 cameras x 50 000 pixel rays, 10 two-sided marching iterations, 100-sample search + 8 secant
+    steps on the rays left over.  SDF through the forward-only fused kernel (siren.sdf_fn) vs the same weights
+    evaluated by PyTorch under no_grad, as the reference's call site does (implicit_modeling.py:431)."""
+    from isopoints_b200 import _ext, siren
+    from isopoints_b200.ray_tracing import RayTracing
+    from tests.helpers import make_camera_rays
+    cam, dirs = make_camera_rays(cams, pixels, seed=1)
+    cam, dirs = cam.to(dev), dirs.to(dev)
+    object_mask = torch.ones(cams * pixels, dtype=torch.bool, device=dev)
+    tracer = RayTracing().eval()
+    lib = _ext.lib()
+    rec = {"workload": "%d x %d rays, eval mode, reference defaults (10 marching iterations, n_steps 100, 8 secant "
+                       "steps)" % (cams, pixels)}
+    for name, opaque in (("fused_forward_only", False), ("torch_no_grad", True)):
+        net = _model(opaque).to(dev).eval()
+        if opaque:
+            def sdf(x, net=net):
+                with torch.no_grad():
+                    return net(x).sdf.squeeze(-1)
+        else:
+            sdf = siren.sdf_fn(net)
+        rows0 = siren.STATS["rows"]
+        for _ in range(2):
+            pts, mask, dist = tracer(sdf, cam, object_mask, dirs)
+        torch.cuda.synchronize()
+        ms = 0.0
+        l0 = lib.isob200_launch_count()
+        rows0 = siren.STATS["rows"]
+        for k in range(steps):
+            flush.fill_(k & 0xff)
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            pts, mask, dist = tracer(sdf, cam, object_mask, dirs)
+            b.record()
+            torch.cuda.synchronize()
+            ms += a.elapsed_time(b)
+        ms /= steps
+        rec[name] = {"ms_per_step": ms, "rays_per_s": cams * pixels / (ms * 1e-3), "hit_frac": float(mask.float().mean()),
+                     "gpu_launches_per_step": (lib.isob200_launch_count() - l0) / steps,
+                     "sdf_evaluations_per_step": (siren.STATS["rows"] - rows0) / steps}
+    rec["speedup"] = rec["torch_no_grad"]["ms_per_step"] / rec["fused_forward_only"]["ms_per_step"]
+    return rec
 
 
 if __name__ == "__main__":

@@ -128,6 +128,9 @@ int isob200_siren_project_step(const float* x, int n_max, const int* n_dev, cons
                                int do_update, int* act_out, float* next_points, int* count_out,
                                void* stream);
 
+/* SDF value only (forward half of isob200_siren_sdf_grad: half the tensor work, no tape); same bits as its sdf */
+int isob200_siren_sdf(const float* x, int n_max, const int* n_dev, const void* blob, int n_hidden, float* sdf,
+                      void* scratch, size_t scratch_bytes, void* stream);
 /* isob200_trace_step with the SDF evaluation of the reference's Siren decoder fused in (forward half of
  * the network only: the march needs no gradient); conventions as isob200_siren_project_step */
 int isob200_siren_trace_step(const float* x, int n_max, const int* n_dev, const void* blob, int n_hidden,
@@ -135,6 +138,10 @@ int isob200_siren_trace_step(const float* x, int n_max, const int* n_dev, const 
                              const int* act_in, float active_tol, float alpha, float max_step, float bound,
                              int do_update, int* act_out, float* next_points, int* count_out, void* stream);
 
+/* tuning knob: persistent CTAs per SIREN launch (1..148, default 148 = one per SM); returns the old value */
+int isob200_siren_set_max_ctas(int n);
+/* tuning knob: tape (cos factor) layers 1..n are stored with the L2 evict-first policy; returns the old value */
+int isob200_siren_set_spill_layers(int n);
 /* Bring-up probe of the 2-CTA tensor-core path (tcgen05 cta_group::2, M = 128 across a CTA pair): one
  * (128 x K) x (256 x K)^T fp16 GEMM, dump (2,128,128) = raw TMEM of both CTAs.  Test-only. */
 int isob200_umma2_probe(const float* a, const float* b, int K, float* dump, void* stream);

@@ -44,6 +44,8 @@ _PROTOS = {
     "isob200_compact_valid": (_i, [_vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _sz, _vp]),
     "isob200_project_sphere": (_i, [_vp, _vp, _vp, _ll, _f, _f, _f, _i, _vp]),
     "isob200_siren_set_pair_mode": (_i, [_i]),
+    "isob200_siren_set_max_ctas": (_i, [_i]),
+    "isob200_siren_set_spill_layers": (_i, [_i]),
     "isob200_siren_pair_stamps": (_i, [_vp, _i]),
     "isob200_siren_blob_bytes": (_sz, [_i]),
     "isob200_siren_pack_ws_bytes": (_sz, []),
@@ -52,6 +54,7 @@ _PROTOS = {
     "isob200_siren_sdf_grad": (_i, [_vp, _i, _vp, _vp, _i, _vp, _vp, _vp, _sz, _vp, _i, _vp]),
     "isob200_siren_project_step": (_i, [_vp, _i, _vp, _vp, _i, _vp, _sz, _vp, _vp, _vp, _vp, _f, _f, _i, _vp, _vp,
                                         _vp, _vp]),
+    "isob200_siren_sdf": (_i, [_vp, _i, _vp, _vp, _i, _vp, _vp, _sz, _vp]),
     "isob200_siren_trace_step": (_i, [_vp, _i, _vp, _vp, _i, _vp, _sz, _vp, _vp, _vp, _vp, _f, _f, _f, _f, _i, _vp, _vp,
                                       _vp, _vp]),
     "isob200_umma2_probe": (_i, [_vp, _vp, _i, _vp, _vp]),
@@ -89,7 +92,7 @@ _RAW = None
 # Optional per-entry-point device timing (bench.py): when PROFILE is a dict, every C-ABI call is
 # bracketed by CUDA events on the stream it is launched on; PROFILE[name] collects (start, end).
 PROFILE = None
-_NO_TIMING = ("_ws_bytes", "_blob_bytes", "_scratch_bytes", "isob200_siren_set_pair_mode", "isob200_siren_pair_stamps", "isob200_last_error", "isob200_abi_version", "isob200_compiled_arch",
+_NO_TIMING = ("_ws_bytes", "_blob_bytes", "_scratch_bytes", "isob200_siren_set_pair_mode", "isob200_siren_set_max_ctas", "isob200_siren_set_spill_layers", "isob200_siren_pair_stamps", "isob200_last_error", "isob200_abi_version", "isob200_compiled_arch",
               "isob200_launch_count", "isob200_splat_record_bytes")
 
 

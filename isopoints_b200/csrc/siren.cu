@@ -132,6 +132,12 @@ __global__ void siren_pack_kernel(const float* __restrict__ w0, const float* __r
   }
 }
 
+__device__ __forceinline__ void st_f4_policy(float4* p, float4 v, uint64_t pol) {
+  asm volatile("st.global.L2::cache_hint.v4.f32 [%0], {%1, %2, %3, %4}, %5;" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z),
+               "f"(v.w), "l"(pol)
+               : "memory");
+}
+
 // ---------------------------------------------------------------------------------------------
 // main kernel
 // ---------------------------------------------------------------------------------------------
@@ -181,7 +187,7 @@ siren_sdf_grad_kernel(const float* __restrict__ x, int n_max, const int* __restr
 
   const float* hdr = reinterpret_cast<const float*>(blob);
   const size_t img0 = off_images(L);
-  const bool fwd_only = nw.mode == 1;            // ray marching needs the value only: L GEMMs, no tape
+  const bool fwd_only = nw.mode != 0;            // value only (mode 2) / ray marching (mode 1): L GEMMs, no tape
   const int n_gemm = fwd_only ? L : 2 * L;      // per tile
 
   if (warp == N_EPI_WARPS) {
@@ -281,6 +287,8 @@ siren_sdf_grad_kernel(const float* __restrict__ x, int n_max, const int* __restr
     // per-CTA stash: [(l-1)][col4 (64)][row (128)] float4, l = 1..L-1
     float4* stash = reinterpret_cast<float4*>(scratch) + (size_t)blockIdx.x * (size_t)(L > 1 ? L - 1 : 1) * 64 * TM;
     uint32_t G = 0;
+    uint64_t pol_first;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol_first));
 
     // publish this thread's K-chunk of k-block kb: generic-proxy stores -> async proxy, one arrive per warp
     auto publish = [&](int kb, const float2* o) {
@@ -414,8 +422,13 @@ siren_sdf_grad_kernel(const float* __restrict__ x, int n_max, const int* __restr
             // global traffic right after the hand-off fence (which waits for everything in flight)
             if (!fwd_only) {
               const int col4 = kb * 8 + cslice * 2;
-              st[(size_t)col4 * TM] = make_float4(cc[0].x, cc[0].y, cc[1].x, cc[1].y);
-              st[(size_t)(col4 + 1) * TM] = make_float4(cc[2].x, cc[2].y, cc[3].x, cc[3].y);
+              if (l <= nw.spill) {
+                st_f4_policy(st + (size_t)col4 * TM, make_float4(cc[0].x, cc[0].y, cc[1].x, cc[1].y), pol_first);
+                st_f4_policy(st + (size_t)(col4 + 1) * TM, make_float4(cc[2].x, cc[2].y, cc[3].x, cc[3].y), pol_first);
+              } else {
+                st[(size_t)col4 * TM] = make_float4(cc[0].x, cc[0].y, cc[1].x, cc[1].y);
+                st[(size_t)(col4 + 1) * TM] = make_float4(cc[2].x, cc[2].y, cc[3].x, cc[3].y);
+              }
             }
             if (kb + 1 < NKB) {
               bwn0 = __ldg(bw4 + (kb + 1) * 8);
@@ -462,7 +475,7 @@ siren_sdf_grad_kernel(const float* __restrict__ x, int n_max, const int* __restr
             if (grow < n && sdf_out) sdf_out[grow] = sdf_row;
           }
           row_barrier(q);
-          if (fwd_only && cslice == 0) {
+          if (nw.mode == 1 && cslice == 0) {
             // ---- fused ray-marching step on this row (same arithmetic as trace_step_kernel, project.cu) ----
             bool still = false;
             int p = 0;
@@ -699,9 +712,23 @@ int isob200_siren_pack(const float* w0, const float* b0, const float* w_hidden, 
 
 // 0: one CTA per 128-row tile (siren.cu); 1: CTA pairs, cta_group::2, two tiles in flight (siren_pair.cu)
 static int g_siren_pair_mode = 0;
+static int g_siren_max_ctas = kNumSMs;   // tuning knob: persistent CTAs per launch (<= one per SM)
+static int g_siren_spill = 0;            // tuning knob: tape layers stored with the L2 evict-first policy
 int isob200_siren_set_pair_mode(int on) {
   const int old = g_siren_pair_mode;
   g_siren_pair_mode = on ? 1 : 0;
+  return old;
+}
+
+int isob200_siren_set_spill_layers(int n) {
+  const int old = g_siren_spill;
+  g_siren_spill = n < 0 ? 0 : n;
+  return old;
+}
+
+int isob200_siren_set_max_ctas(int n) {
+  const int old = g_siren_max_ctas;
+  g_siren_max_ctas = n < 1 ? 1 : (n > kNumSMs ? kNumSMs : n);
   return old;
 }
 
@@ -729,9 +756,11 @@ static int launch_siren(const float* x, int n_max, const int* n_dev, const void*
     }
   }
   int tiles = (n_max + TM - 1) / TM;
-  int grid = tiles < kNumSMs ? tiles : kNumSMs;
+  int grid = tiles < g_siren_max_ctas ? tiles : g_siren_max_ctas;
+  Newton nwk = nw;
+  nwk.spill = g_siren_spill;
   siren_sdf_grad_kernel<<<grid, THREADS, SMEM_BYTES, (cudaStream_t)stream>>>(
-      x, n_max, n_dev, (const unsigned char*)blob, n_hidden, sdf, grad, (float*)scratch, dbg, dbg_gemm, nw);
+      x, n_max, n_dev, (const unsigned char*)blob, n_hidden, sdf, grad, (float*)scratch, dbg, dbg_gemm, nwk);
   ISO_CHECK_LAUNCH("siren_sdf_grad_kernel");
   return ISOB200_OK;
 }
@@ -759,6 +788,17 @@ int isob200_siren_project_step(const float* x, int n_max, const int* n_dev, cons
   Newton nw = {points, normals, not_converged, act_in, act_out, next_points, count_out, tol, max_step, do_update};
   return launch_siren(x, n_max, n_dev, blob, n_hidden, nullptr, nullptr, scratch, scratch_bytes, nullptr, -1, nw,
                       stream, "siren_project_step");
+}
+
+// SDF value only: the forward half of isob200_siren_sdf_grad (half the GEMMs, no tape).  Bit-identical to the
+// sdf output of isob200_siren_sdf_grad.
+int isob200_siren_sdf(const float* x, int n_max, const int* n_dev, const void* blob, int n_hidden, float* sdf,
+                      void* scratch, size_t scratch_bytes, void* stream) {
+  ISO_CHECK_ARG(n_max == 0 || sdf, "siren_sdf: null output");
+  Newton nw = {};
+  nw.mode = 2;
+  return launch_siren(x, n_max, n_dev, blob, n_hidden, sdf, nullptr, scratch, scratch_bytes, nullptr, -1, nw, stream,
+                      "siren_sdf");
 }
 
 // One iteration of SphereTracing.project_points (levelset_sampling.py:733-786) with the SDF evaluation

@@ -294,6 +294,9 @@ struct Newton {
   const float* dirs;         // (M,3) ray directions
   float* eval;               // (M) last sdf per ray
   float alpha, bound;        // step factor; radius + padding of the bounding sphere
+  // tape layers 1..spill are stored with an L2 evict-first policy: they are read last (the reverse pass
+  // walks the layers backwards), so when the live tape exceeds L2 they are the ones to send to HBM
+  int spill;
 };
 
 // eps_denom(x, eps) of DSS/utils/mathHelper.py:14-18: (sign(x) + [x == 0]) * max(|x|, eps)

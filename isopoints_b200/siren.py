@@ -189,3 +189,43 @@ def sdf_and_grad(model, points, forward_kwargs=None, n_dev=None, dbg_gemm=None, 
     if dbg_gemm is not None:
         return sdf, grad, dbg
     return sdf, grad
+
+
+def sdf(model, points, forward_kwargs=None, n_dev=None, spec=None, out=None, pk=None):
+    """sdf (n,) of a fusable SIREN at ``points`` (n,3) fp32 cuda through the forward half of the fused kernel
+    (no gradient: half the tensor work of ``sdf_and_grad``, same bits as its value), or None when ``model`` is
+    not fusable.  Arguments as ``sdf_and_grad``."""
+    if spec is None:
+        spec = match(model, forward_kwargs)
+    if spec is None:
+        return None
+    _ext.require_cuda(points)
+    x = points.reshape(-1, 3)
+    if x.dtype != torch.float32:
+        return None
+    x = x.contiguous()
+    n = x.shape[0]
+    blob, scratch, L = pk if pk is not None else packed(model, spec)
+    val = out[:n] if out is not None else torch.empty((n,), dtype=torch.float32, device=x.device)
+    if n > 0:
+        STATS["calls"] += 1
+        STATS["rows"] += n
+        _ext.check(_ext.lib().isob200_siren_sdf(_ext.ptr(x), n, _ext.ptr(n_dev), _ext.ptr(blob), L, _ext.ptr(val),
+                                                _ext.ptr(scratch), scratch.numel(), _ext.stream(x.device)))
+    return val
+
+
+class sdf_fn:
+    """``sdf`` callable for code that takes one (the reference's RayTracing, levelset_sampling.py:831:
+    ``sdf=lambda x: model.decode(x).sdf.squeeze(-1)``): evaluates a fusable decoder with the forward-only fused
+    kernel, anything else through ``model.forward(x).sdf`` without autograd."""
+
+    def __init__(self, model, **forward_kwargs):
+        self.model, self.forward_kwargs = model, forward_kwargs
+
+    def __call__(self, x):
+        v = sdf(self.model, x, self.forward_kwargs) if x.is_cuda else None
+        if v is None:
+            with torch.no_grad():
+                v = self.model.forward(x, **self.forward_kwargs).sdf.reshape(-1)
+        return v.reshape(x.shape[:-1])

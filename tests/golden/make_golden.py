@@ -18,6 +18,9 @@
   neighbour query through the reference's own `frnn_bf_cpu`.
 * sphere tracing (`--only trace`): the reference's `SphereTracing.project_points`
   (levelset_sampling.py:679-808) on CPU tensors.
+* IDR ray tracing (`--only rays`): the reference's `RayTracing.forward` (levelset_sampling.py:810-1167) on CPU
+  tensors (its hard-coded `.cuda()` calls made no-ops for the duration of the run; the `uniform_` draw of
+  `minimal_sdf_points` recorded so the parity test can inject the same positions), eval and training mode.
 The fixtures are small (< 1 MB total) and committed; the GPU box has no /root/reference.
 """
 import os
@@ -33,7 +36,7 @@ sys.path.insert(0, ROOT)
 
 from oracle import ref_native, ref_python  # noqa: E402
 from tests.helpers import (SphereSDF, TinySiren, make_splat_inputs, make_cameras, make_surface_points,  # noqa: E402
-                           make_rays)
+                           make_rays, make_camera_rays)
 
 
 class _CpuFrnn(types.SimpleNamespace):
@@ -203,6 +206,49 @@ def trace_golden(LS):
     np.savez_compressed(os.path.join(HERE, "sphere_trace.npz"), proj_max_iters=25, **out)
 
 
+def rays_golden(LS):
+    """RayTracing.forward (levelset_sampling.py:831-918) on CPU tensors.  Cases: the TinySiren blob (half-slope
+    SDF, so the march leaves rays for the sampler + secant) and a sphere (march converges), in eval and in
+    training mode (which adds the minimal-SDF search for the rays that disagree with the ground-truth mask)."""
+    real_cuda, real_uniform = torch.Tensor.cuda, torch.Tensor.uniform_
+    drawn = []
+
+    def uniform_rec(self, *a, **k):
+        real_uniform(self, *a, **k)
+        drawn.append(self.clone())
+        return self
+    torch.Tensor.cuda = lambda self, *a, **k: self
+    torch.Tensor.uniform_ = uniform_rec
+    out = {}
+    try:
+        for name, net, iters in (("siren", TinySiren(seed=3), 10), ("sphere", SphereSDF(radius=0.5), 10),
+                                 ("siren3", TinySiren(seed=5), 3)):
+            cam, dirs = make_camera_rays(2, 1500, seed=31)
+            with torch.no_grad():
+                inside = net(cam[:, None, :] + 2.5 * dirs).sdf  # crude ground-truth mask: correlated, not equal
+            g = torch.Generator().manual_seed(7)
+            object_mask = ((inside.reshape(-1) < 0.35) ^ (torch.rand(3000, generator=g) < 0.15))
+
+            def sdf(x):
+                with torch.no_grad():
+                    return net(x).sdf.squeeze(-1)
+            out[name + "_cam"], out[name + "_dirs"], out[name + "_object_mask"] = cam.numpy(), dirs.numpy(), object_mask.numpy()
+            for mode in ("eval", "train"):
+                tracer = LS.RayTracing(object_bounding_sphere=1.0, sphere_tracing_iters=iters, n_steps=64, n_secant_steps=8)
+                tracer.train(mode == "train")
+                del drawn[:]
+                pts, net_mask, dists = tracer(sdf, cam.clone(), object_mask.clone(), dirs.clone())
+                key = "%s_%s_" % (name, mode)
+                out[key + "points"], out[key + "mask"], out[key + "dists"] = pts.numpy(), net_mask.numpy(), dists.numpy()
+                if drawn:
+                    out[key + "steps"] = drawn[-1].numpy()
+                print("rays %s/%s: net mask %.3f, object mask %.3f, uniform draws %d" % (
+                    name, mode, float(net_mask.float().mean()), float(object_mask.float().mean()), len(drawn)))
+    finally:
+        torch.Tensor.cuda, torch.Tensor.uniform_ = real_cuda, real_uniform
+    np.savez_compressed(os.path.join(HERE, "ray_tracing.npz"), n_steps=64, **out)
+
+
 def main():
     torch.set_num_threads(4)
     if "--only" in sys.argv and sys.argv[sys.argv.index("--only") + 1] == "ewa":
@@ -210,6 +256,8 @@ def main():
         return ewa_golden()
     if "--only" in sys.argv and sys.argv[sys.argv.index("--only") + 1] == "trace":
         return trace_golden(ref_python.load(frnn_module=_CpuFrnn).levelset_sampling)
+    if "--only" in sys.argv and sys.argv[sys.argv.index("--only") + 1] == "rays":
+        return rays_golden(ref_python.load(frnn_module=_CpuFrnn).levelset_sampling)
     ref = ref_python.load(frnn_module=_CpuFrnn)
     LS = ref.levelset_sampling
 
@@ -318,6 +366,7 @@ def main():
     print("splat: occupied", float(occ.mean()))
     ewa_golden()
     trace_golden(LS)
+    rays_golden(LS)
 
 
 if __name__ == "__main__":

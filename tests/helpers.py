@@ -207,3 +207,16 @@ def make_rays(n, seed, start_radius=1.0, target_radius=0.9):
     t = t / t.norm(dim=-1, keepdim=True) * target_radius * torch.rand(n, 1, generator=g) ** (1.0 / 3)
     d = t - o
     return o.contiguous(), (d / d.norm(dim=-1, keepdim=True)).contiguous()
+
+
+def make_camera_rays(n_cams, n_pixels, seed, cam_dist=2.5, target_radius=1.15):
+    """``n_cams`` pinhole origins at distance ``cam_dist`` (outside the unit bounding sphere), ``n_pixels`` unit
+    rays each towards random points within ``target_radius`` of the origin: most cross the unit sphere, some
+    miss it.  Returns cam_loc (B,3), ray_directions (B,P,3)."""
+    g = torch.Generator().manual_seed(seed)
+    o = torch.randn(n_cams, 3, generator=g)
+    o = o / o.norm(dim=-1, keepdim=True) * cam_dist
+    t = torch.randn(n_cams, n_pixels, 3, generator=g)
+    t = t / t.norm(dim=-1, keepdim=True) * target_radius * torch.rand(n_cams, n_pixels, 1, generator=g) ** (1.0 / 3)
+    d = t - o[:, None, :]
+    return o.contiguous(), (d / d.norm(dim=-1, keepdim=True)).contiguous()

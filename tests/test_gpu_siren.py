@@ -265,3 +265,19 @@ def test_cta_pair_kernel_matches_single_cta_kernel():
     both = a.mask & b.mask
     d = (a.points - b.points).abs().max(dim=-1).values[both]
     assert d.median().item() < 2e-6 and d.quantile(0.99).item() < 1e-4
+
+
+@pytest.mark.parametrize("layers,n", [(1, 300), (2, 128 * 149 + 5), (7, 50000)])
+def test_value_only_kernel_is_the_forward_half(layers, n):
+    """isob200_siren_sdf (forward GEMMs only) returns the bits of isob200_siren_sdf_grad's value."""
+    model = Siren(256, layers, 30.0, seed=layers + 10).to(DEV)
+    x = ((torch.rand(n, 3, device=DEV) - 0.5) * 2).contiguous()
+    both = siren.sdf_and_grad(model, x)
+    only = siren.sdf(model, x)
+    assert torch.equal(both[0], only)
+    f = siren.sdf_fn(model)
+    assert torch.equal(f(x.view(1, n, 3)), only.view(1, n))
+    cnt = torch.tensor([n // 2], dtype=torch.int32, device=DEV)
+    out = torch.full((n,), 7.0, device=DEV)
+    siren.sdf(model, x, n_dev=cnt, out=out)
+    assert torch.equal(out[: n // 2], only[: n // 2]) and bool((out[n // 2:] == 7.0).all())
