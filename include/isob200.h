@@ -138,6 +138,14 @@ int isob200_siren_trace_step(const float* x, int n_max, const int* n_dev, const 
                              const int* act_in, float active_tol, float alpha, float max_step, float bound,
                              int do_update, int* act_out, float* next_points, int* count_out, void* stream);
 
+/* ---- in-surface sampler: closest point to every ray, Model.sample_offsurface_using_isopoints
+ *      (DSS/models/combined_modeling.py:325-352: the two (R,M) dist_to_ray matrices + topk(k = 1)).  For ray r
+ *      with origin o (n_origins = 1: shared by all rays, else R) and unit direction d, over points p (M,3):
+ *      t = (p - o).d, dist = |p - o|^2 - t^2; outputs at the point of smallest dist (ties: lowest index):
+ *      t_sq (R) = t^2, dist (R), idx (R) (-1 and t_sq 0 when M = 0); any output may be NULL ------------- */
+int isob200_ray_nearest_point(const float* origins, int n_origins, const float* dirs, int R, const float* points,
+                              int M, float* t_sq, float* dist, int* idx, void* stream);
+
 /* tuning knob: persistent CTAs per SIREN launch (1..148, default 148 = one per SM); returns the old value */
 int isob200_siren_set_max_ctas(int n);
 /* tuning knob: tape (cos factor) layers 1..n are stored with the L2 evict-first policy; returns the old value */

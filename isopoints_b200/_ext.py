@@ -57,6 +57,7 @@ _PROTOS = {
     "isob200_siren_sdf": (_i, [_vp, _i, _vp, _vp, _i, _vp, _vp, _sz, _vp]),
     "isob200_siren_trace_step": (_i, [_vp, _i, _vp, _vp, _i, _vp, _sz, _vp, _vp, _vp, _vp, _f, _f, _f, _f, _i, _vp, _vp,
                                       _vp, _vp]),
+    "isob200_ray_nearest_point": (_i, [_vp, _i, _vp, _i, _vp, _i, _vp, _vp, _vp, _vp]),
     "isob200_umma2_probe": (_i, [_vp, _vp, _i, _vp, _vp]),
     "isob200_umma_rate": (_i, [_i, _i, _vp, _vp]),
     "isob200_resample_step": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _vp, _i, _i, _i, _i, _vp, _vp]),

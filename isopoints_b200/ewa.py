@@ -183,15 +183,18 @@ class SurfaceSplatting:
                                   rs.antialiasing_sigma, rs.cutoff_threshold)
 
     def filter_renderable(self, point_clouds, point_clouds_filter=None, **kwargs):
-        """rasterizer.py:220-255: (new point clouds, packed mask over the input points)."""
-        if point_clouds_filter is not None:
-            raise NotImplementedError("activation filters (DSS/core/cloud.py PointCloudsFilters) are outside the "
-                                      "splat path built here")
+        """rasterizer.py:220-255: (new point clouds, packed mask over the points that entered the depth /
+        back-face test).  With a ``point_clouds_filter`` (DSS/core/cloud.py PointCloudsFilters) its visibility is
+        reset to all-False and its ``activation`` filter is applied first (:231-235)."""
         rs = kwargs.get("raster_settings", self.raster_settings)
         cameras = kwargs.get("cameras", self.cameras)
         n = point_clouds.num_points_per_cloud()
         if point_clouds.isempty():
             return point_clouds, torch.full((int(n.sum().item()),), True, dtype=torch.bool, device=point_clouds.device)
+        if point_clouds_filter is not None:
+            point_clouds_filter.set_filter(visibility=torch.full(
+                (len(point_clouds), int(n.max().item())), False, dtype=torch.bool, device=point_clouds.device))
+            point_clouds = point_clouds_filter.filter_with(point_clouds, ("activation",))
         w2v = cameras.get_world_to_view_transform().get_matrix()
         if w2v.shape[0] != len(point_clouds):
             point_clouds = point_clouds.extend(w2v.shape[0])     # :241-245
@@ -246,7 +249,8 @@ class SurfaceSplatting:
         return PointFragments(idx=idx, zbuf=zbuf, qvalue=qvalue, scaler=qvalue, occupancy=occ)
 
     def forward(self, point_clouds, point_clouds_filter=None, **kwargs):
-        """rasterizer.py:584-661 -> (PointFragments, filtered point clouds)."""
+        """rasterizer.py:584-661 -> (PointFragments, filtered point clouds).  A ``point_clouds_filter`` receives
+        the per-point visibility of the input clouds as its padded ``visibility`` filter (:642-650)."""
         rs = kwargs.get("raster_settings", self.raster_settings)
         filtered, mask_filtered = self.filter_renderable(point_clouds, point_clouds_filter, **kwargs)
         if filtered.isempty():
@@ -262,6 +266,16 @@ class SurfaceSplatting:
         frag_scaler = gather_with_neg_idx(info["scaler"], 0, idx.view(-1).long()).view_as(qvalue)   # :634-636
         fragments = PointFragments(idx=idx, zbuf=zbuf, qvalue=qvalue, scaler=frag_scaler, occupancy=occ)
         self._last = (fragments, info["scaler"])   # per-point scaler of these fragments, for the renderer's blend
+        if point_clouds_filter is not None:
+            # visibility of the points that survived the renderable filter, scattered back to the points that
+            # entered it, then padded with the INPUT clouds' first indices (:642-650; with more cameras than
+            # clouds this keeps the first view's rows, as the reference does)
+            vis = visibility_mask(idx.detach(), int(filtered.num_points_per_cloud().sum().item()), occ.detach())
+            full = torch.zeros_like(mask_filtered)
+            full[mask_filtered] = vis
+            max_p = int(point_clouds.num_points_per_cloud().max().item())
+            padded = packed_to_padded(full.float(), point_clouds.cloud_to_packed_first_idx(), max_p).bool()
+            point_clouds_filter.set_filter(visibility=padded)
         return fragments, filtered
 
     __call__ = forward
@@ -309,6 +323,22 @@ class SurfaceSplattingRenderer:
     __call__ = forward
 
 
+def get_visible_points(point_clouds, cameras, depth_merge_threshold=0.05, return_mask=False):
+    """DSS/utils/__init__.py:699-711: the points of ``point_clouds`` that own a fragment of an occupied pixel
+    when splatted at 256 x 256 with back-face culling -- as a new Pointclouds (and, with ``return_mask``, the
+    padded visibility mask)."""
+    from .cloud import PointCloudsFilters
+    splatter = SurfaceSplatting(raster_settings=PointsRasterizationSettings(
+        depth_merging_threshold=depth_merge_threshold, image_size=256, cutoff_threshold=1.0, backface_culling=True))
+    pcl_filter = PointCloudsFilters(device=point_clouds.device)
+    with torch.no_grad():
+        splatter(point_clouds, cameras=cameras, point_clouds_filter=pcl_filter)
+    visible = pcl_filter.filter_with(point_clouds, ("visibility",))
+    if return_mask:
+        return visible, pcl_filter.visibility
+    return visible
+
+
 def PointsRasterizationSettings(**kw):
     """DSS/core/rasterizer.py:38-100, same defaults."""
     d = dict(backface_culling=True, cutoff_threshold=1.0, depth_merging_threshold=0.05, Vrk_invariant=False,
@@ -321,5 +351,5 @@ def PointsRasterizationSettings(**kw):
     return SimpleNamespace(**d)
 
 
-__all__ = ["SurfaceSplatting", "SurfaceSplattingRenderer", "PointsRasterizationSettings", "compute_isotropic_vrk_h", "get_per_point_info",
+__all__ = ["SurfaceSplatting", "SurfaceSplattingRenderer", "get_visible_points", "PointsRasterizationSettings", "compute_isotropic_vrk_h", "get_per_point_info",
            "renderable_mask", "visibility_mask", "packed_to_padded"]

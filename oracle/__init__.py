@@ -11,7 +11,7 @@ product path fails loudly when libisob200.so is missing -- isopoints_b200/_ext.p
                 plus the host sequence of frnn.py:55-162 driving them -- the live oracle on a GPU.
   ref_python.py import hook that loads the reference's Python (DSS.models.levelset_sampling, ...)
                 from /root/reference with auto-stubbed third-party packages and a declared,
-                asserted 3-entry patch list for torch 2.x; used in the authoring container to
+                asserted 4-entry patch list for torch 2.x; used in the authoring container to
                 generate tests/golden/*.npz (tests/golden/make_golden.py).  /root/reference
                 does not exist on the GPU box, so nothing at test/bench time depends on it.
 

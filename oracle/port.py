@@ -795,3 +795,17 @@ def sphere_trace(model, ray0: torch.Tensor, ray_direction: torch.Tensor, proj_ma
         pts[idx[ok]] = new[ok]                                                      # :776-777
         trials += 1
     return pts, sdf, grad, sdf.abs() <= proj_tolerance
+
+
+# =========================================================================================
+# in-surface sampler: closest iso-point to a ray  (DSS/models/combined_modeling.py:326-352)
+# =========================================================================================
+def ray_nearest_point(cam_pos: torch.Tensor, ray0: torch.Tensor, points: torch.Tensor):
+    """The dense computation of combined_modeling.py:331-347 for one view, in the reference's own op sequence
+    (float32, torch-CPU): pC = p - C; ray_sq = ((pC * ray0).sum(-1))^2 (R,M); dist_to_ray = |pC|^2 - ray_sq;
+    the smallest dist per ray.  Returns (ray_sq at the arg-min (R,), idx (R,), dist_to_ray (R,M), ray_sq (R,M))."""
+    pC = points - cam_pos.view(1, 3)
+    ray_sq = (pC[None, :, :] * ray0[:, None, :]).sum(-1) ** 2
+    dist_to_ray = (pC ** 2).sum(-1).unsqueeze(0) - ray_sq
+    _, nn_idx = torch.topk(dist_to_ray, k=1, dim=1, largest=False)
+    return torch.gather(ray_sq, 1, nn_idx).view(-1), nn_idx.view(-1), dist_to_ray, ray_sq

@@ -9,7 +9,7 @@ container): tests/golden/make_golden.py uses it to produce the committed golden 
 * The handful of pytorch3d symbols the hot path really executes get functional pure-torch
   stand-ins (semantics restated from pytorch3d's documentation: zero padding, packed =
   concatenation).
-* Two idioms PyTorch 1.6 accepted (three sites) raise on torch >= 2: they are patched in the SOURCE STRING at
+* Two idioms PyTorch 1.6 accepted (four sites) raise on torch >= 2: they are patched in the SOURCE STRING at
   load time, each pattern asserted to match (PATCHES below).  Nothing else is changed.
 """
 import importlib
@@ -41,6 +41,9 @@ PATCHES = (
     ("DSS/core/rasterizer.py",
      "valid_depth_mask[valid_depth_mask] = frontface_mask",
      "valid_depth_mask[valid_depth_mask.clone()] = frontface_mask", 1),
+    ("DSS/models/combined_modeling.py",
+     "mask_insurface[b][mask_insurface[b]] = (ray_len0 < ray_len1).view(-1)",
+     "mask_insurface[b][mask_insurface[b].clone()] = (ray_len0 < ray_len1).view(-1)", 1),
 )
 
 

@@ -3,7 +3,7 @@
     python tests/golden/make_golden.py
 
 * projection / resample vectors: the reference's Python (DSS/models/levelset_sampling.py loaded
-  from /root/reference through oracle/ref_python.py's asserted 3-entry torch-2.x patch list) on
+  from /root/reference through oracle/ref_python.py's asserted 4-entry torch-2.x patch list) on
   CPU tensors; its `frnn` dependency (CUDA-only) is replaced by a stand-in built on the
   reference's own CPU brute force `frnn._C.frnn_bf_cpu` (oracle/_ref/ref_frnn_C.so).
 * FRNN vectors: `frnn._C.frnn_bf_cpu` (bruteforce_cpu.cpp:4-58).
@@ -21,6 +21,11 @@
 * IDR ray tracing (`--only rays`): the reference's `RayTracing.forward` (levelset_sampling.py:810-1167) on CPU
   tensors (its hard-coded `.cuda()` calls made no-ops for the duration of the run; the `uniform_` draw of
   `minimal_sdf_points` recorded so the parity test can inject the same positions), eval and training mode.
+* in-surface / off-surface sampler (`--only offsurface`): the reference's
+  `Model.sample_offsurface_using_isopoints` (DSS/models/combined_modeling.py:237-388) called unbound on a
+  duck-typed model (decoder = TinySiren) and cameras (tests/helpers.PinholeCameras), with its two
+  `get_visible_points` calls answered by preset front / back point sets (the visibility pass has its own tests)
+  and the `torch.rand_like` draw recorded; plus `intersection_with_unit_cube` and `get_tensor_values` alone.
 The fixtures are small (< 1 MB total) and committed; the GPU box has no /root/reference.
 """
 import os
@@ -36,7 +41,7 @@ sys.path.insert(0, ROOT)
 
 from oracle import ref_native, ref_python  # noqa: E402
 from tests.helpers import (SphereSDF, TinySiren, make_splat_inputs, make_cameras, make_surface_points,  # noqa: E402
-                           make_rays, make_camera_rays)
+                           make_rays, make_camera_rays, offsurface_inputs)
 
 
 class _CpuFrnn(types.SimpleNamespace):
@@ -249,6 +254,53 @@ def rays_golden(LS):
     np.savez_compressed(os.path.join(HERE, "ray_tracing.npz"), n_steps=64, **out)
 
 
+def offsurface_golden(ref):
+    import importlib
+    from isopoints_b200.structures import Pointclouds
+    CM = importlib.import_module("DSS.models.combined_modeling")
+    U = importlib.import_module("DSS.utils")
+    cams, pixels, mask_img, frontal, occluded, iso_pcl = offsurface_inputs()
+    answers = [Pointclouds(frontal), Pointclouds(occluded)]
+    calls = []
+
+    def visible(points, cameras, depth_merge_threshold=0.05, return_mask=False):
+        calls.append((cameras.R.clone(), cameras.T.clone(), depth_merge_threshold))
+        return answers[len(calls) - 1]
+    drawn = []
+    real_rand_like = torch.rand_like
+
+    def rand_like(x, *a, **k):
+        drawn.append(real_rand_like(x, *a, **k))
+        return drawn[-1]
+    net = TinySiren(seed=3)
+    model = types.SimpleNamespace(
+        _points=None, decoder=net, max_points_per_pass=10000, object_bounding_sphere=1.0,
+        renderer=types.SimpleNamespace(rasterizer=types.SimpleNamespace(
+            raster_settings=types.SimpleNamespace(depth_merging_threshold=0.05))))
+    CM.get_visible_points = visible
+    CM.torch.rand_like = rand_like
+    torch.manual_seed(11)
+    try:
+        p_off, p_ins, n_off, n_ins = CM.Model.sample_offsurface_using_isopoints(
+            model, pixels.clone(), mask_img.clone(), cams, n_points_per_ray=32,
+            max_insurface_per_batch=[150, 400], iso_pcl=Pointclouds(iso_pcl))
+    finally:
+        CM.torch.rand_like = real_rand_like
+    assert len(calls) == 2 and len(drawn) == 1
+    out = dict(p_off=p_off.numpy(), p_ins=p_ins.numpy(), n_off=n_off.numpy(), n_ins=n_ins.numpy(), rand=drawn[0].numpy(),
+               back_R=calls[1][0].numpy(), back_T=calls[1][1].numpy(), n_points_per_ray=32,
+               max_insurface=np.array([150, 400]))
+    # the two helpers alone
+    cam_pos = cams.get_camera_center()
+    world = cams.unproject_points(torch.cat([-pixels, torch.ones_like(pixels[..., :1])], -1), scaled_depth_input=False)
+    rays = torch.nn.functional.normalize(world - cam_pos[:, None, :], dim=-1)
+    c0, c1, cm = U.intersection_with_unit_cube(cam_pos.view(-1, 1, 3), rays, side_length=2.0)
+    vals = U.get_tensor_values(mask_img, pixels.clamp(-1, 1), squeeze_channel_dim=True)
+    out.update(cube_rays=rays.numpy(), cube0=c0.numpy(), cube1=c1.numpy(), cube_mask=cm.numpy(), mask_values=vals.numpy())
+    np.savez_compressed(os.path.join(HERE, "offsurface.npz"), **out)
+    print("offsurface: off %s, in %s of caps [150, 400], cube hits %.3f" % (n_off.tolist(), n_ins.tolist(), float(cm.float().mean())))
+
+
 def main():
     torch.set_num_threads(4)
     if "--only" in sys.argv and sys.argv[sys.argv.index("--only") + 1] == "ewa":
@@ -258,6 +310,8 @@ def main():
         return trace_golden(ref_python.load(frnn_module=_CpuFrnn).levelset_sampling)
     if "--only" in sys.argv and sys.argv[sys.argv.index("--only") + 1] == "rays":
         return rays_golden(ref_python.load(frnn_module=_CpuFrnn).levelset_sampling)
+    if "--only" in sys.argv and sys.argv[sys.argv.index("--only") + 1] == "offsurface":
+        return offsurface_golden(ref_python.load(frnn_module=_CpuFrnn))
     ref = ref_python.load(frnn_module=_CpuFrnn)
     LS = ref.levelset_sampling
 
@@ -367,6 +421,7 @@ def main():
     ewa_golden()
     trace_golden(LS)
     rays_golden(LS)
+    offsurface_golden(ref)
 
 
 if __name__ == "__main__":

@@ -220,3 +220,70 @@ def make_camera_rays(n_cams, n_pixels, seed, cam_dist=2.5, target_radius=1.15):
     t = t / t.norm(dim=-1, keepdim=True) * target_radius * torch.rand(n_cams, n_pixels, 1, generator=g) ** (1.0 / 3)
     d = t - o[:, None, :]
     return o.contiguous(), (d / d.norm(dim=-1, keepdim=True)).contiguous()
+
+
+class PinholeCameras:
+    """Minimal perspective cameras with the slice of pytorch3d's camera API the reference's sampling code calls
+    (row-vector convention: p_view = p_world @ R + T; NDC xy = focal * xy_view / z_view).  R (B,3,3), T (B,3)."""
+
+    def __init__(self, R, T, focal=2.0, znear=1.0, zfar=100.0):
+        self.R, self.T, self.focal, self.znear, self.zfar = R, T, focal, znear, zfar
+
+    @classmethod
+    def look_at_origin(cls, n_views, seed, dist=(2.2, 3.2), focal=2.0, device="cpu"):
+        w2v, _, _ = make_cameras(n_views, seed, dist=dist, focal=focal)
+        return cls(w2v[:, :3, :3].contiguous().to(device), w2v[:, 3, :3].contiguous().to(device), focal)
+
+    def clone(self):
+        return PinholeCameras(self.R.clone(), self.T.clone(), self.focal, self.znear, self.zfar)
+
+    def get_camera_center(self):
+        return -torch.bmm(self.T[:, None, :], self.R.transpose(1, 2))[:, 0]
+
+    def _w2v(self):
+        m = torch.zeros(self.R.shape[0], 4, 4, dtype=self.R.dtype, device=self.R.device)
+        m[:, :3, :3], m[:, 3, :3], m[:, 3, 3] = self.R, self.T, 1.0
+        return m
+
+    def _proj(self):
+        k = torch.zeros(4, 4, dtype=self.R.dtype, device=self.R.device)
+        k[0, 0] = k[1, 1] = self.focal
+        k[2, 2] = self.zfar / (self.zfar - self.znear)
+        k[3, 2] = -self.zfar * self.znear / (self.zfar - self.znear)
+        k[2, 3] = 1.0
+        return self._w2v() @ k
+
+    def get_world_to_view_transform(self):
+        return types.SimpleNamespace(get_matrix=self._w2v)
+
+    def get_full_projection_transform(self):
+        return types.SimpleNamespace(get_matrix=self._proj)
+
+    def transform_points(self, points, eps=None):
+        hom = torch.cat([points, torch.ones_like(points[..., :1])], dim=-1)
+        out = hom @ self._proj()
+        return out[..., :3] / out[..., 3:]
+
+    def unproject_points(self, xy_depth, scaled_depth_input=False, world_coordinates=True):
+        z = xy_depth[..., 2:3]
+        view = torch.cat([xy_depth[..., :2] * z / self.focal, z], dim=-1)
+        return (view - self.T[:, None, :]) @ self.R.transpose(1, 2)
+
+
+def offsurface_inputs(seed=41, n_views=2, n_pix=1200, n_iso=3000, S=64):
+    """Inputs shared by the generator and the parity test: cameras, NDC pixels, a disc mask image, and the
+    front / back halves (as seen from each camera) of a noisy sphere of iso-points of radius 0.6."""
+    g = torch.Generator().manual_seed(seed)
+    cams = PinholeCameras.look_at_origin(n_views, seed=seed, focal=2.0)
+    pixels = torch.rand(n_views, n_pix, 2, generator=g) * 1.6 - 0.8
+    yy, xx = torch.meshgrid(torch.linspace(-1, 1, S), torch.linspace(-1, 1, S), indexing="ij")
+    mask_img = ((xx ** 2 + yy ** 2) < 0.33 ** 2).float().expand(n_views, 1, S, S).contiguous()
+    d = torch.randn(n_iso, 3, generator=g)
+    iso = 0.6 * d / d.norm(dim=-1, keepdim=True) + 0.01 * torch.randn(n_iso, 3, generator=g)
+    centre = cams.get_camera_center()
+    facing = [((iso * centre[b]).sum(-1) > 0.05) for b in range(n_views)]
+    away = [((iso * centre[b]).sum(-1) < -0.05) for b in range(n_views)]
+    frontal = [iso[m] for m in facing]
+    occluded = [iso[m] for m in away]
+    iso_pcl = [iso[: n_iso // 2] * 1.5, iso[n_iso // 2: n_iso // 2 + 700] * 1.5]    # some project outside the disc
+    return cams, pixels, mask_img, frontal, occluded, iso_pcl
