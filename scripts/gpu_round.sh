@@ -7,6 +7,13 @@ timeout 900 python -m pytest tests -m gpu -q 2>&1 | tail -40 > gpurun_out/pytest
 timeout 200 python __graft_entry__.py smoke 2>&1 | tail -2
 timeout 600 python bench.py --steps 5 --warmup 3 > gpurun_out/bench.json 2> gpurun_out/bench.err; tail -c 3000 gpurun_out/bench.json; grep -v Warning gpurun_out/bench.err | tail -5
 timeout 300 python bench.py --impl reference --steps 1 --warmup 0 > gpurun_out/bench_reference.json 2>/dev/null; tail -c 300 gpurun_out/bench_reference.json
+if [ "${1:-}" = "prof3" ]; then
+  # added after the r01h captures: point-to-ray search of the in-surface sampler, RayTracing on the value-only SIREN mode
+  timeout 200 python bench_rays.py --steps 20 > gpurun_out/bench_rays.json 2>/dev/null; tail -c 700 gpurun_out/bench_rays.json; echo
+  timeout 300 ncu --set full --clock-control none --import-source on -k regex:ray_nearest_point -s 4 -c 1 -f -o gpurun_out/prof_ray_nearest_point python bench_rays.py --steps 1 > gpurun_out/ncu_rays.log 2>&1; tail -2 gpurun_out/ncu_rays.log
+  timeout 400 compute-sanitizer --tool memcheck --error-exitcode 7 python -m pytest tests/test_gpu_offsurface.py tests/test_gpu_rays.py -m gpu -q -k "ties_and_empty or 7-33 or 1-1 or no_ray_hits or golden-siren3" > gpurun_out/sanitizer_memcheck_r01i.log 2>&1; echo "memcheck(r01i) rc=$?"; tail -2 gpurun_out/sanitizer_memcheck_r01i.log
+  ls gpurun_out/
+fi
 if [ "${1:-}" = "prof2" ]; then
   # kernels added after the r01g captures: EWA per-point parameters, the renderable mask, forward-only SIREN
   timeout 300 python bench_splat.py --steps 5 > gpurun_out/bench_splat.json 2>/dev/null
