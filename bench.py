@@ -131,6 +131,12 @@ class ClockSampler:
         self._t.start()
         return self
 
+    def reset(self):
+        """Drop what was sampled so far: the sampler is started before the warm-up steps (the first NVML queries
+        of a process initialise driver state and were seen to stall the first step after them by tens of ms) and
+        reset when the timed region starts, so only samples taken during it are reported."""
+        self.sm, self.mx, self.reasons = [], [], set()
+
     def __exit__(self, *a):
         self._stop.set()
         self._t.join(timeout=6)
@@ -221,6 +227,8 @@ def run_ours(args):
         torch.cuda.synchronize()
         return out, tuple(res)
 
+    clocks = ClockSampler(local)
+    clocks.__enter__()            # sampling thread runs through the warm-up too; reset() below
     for _ in range(args.warmup):
         out = step(x_dev)
     _barrier(world)
@@ -233,8 +241,9 @@ def run_ours(args):
     _siren.RECORD = []
     l0 = lib.isob200_launch_count()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    with ClockSampler(local) as clocks:
+    try:
         _barrier(world)
+        clocks.reset()
         t0 = time.perf_counter()
         for k in range(args.steps):
             flush.fill_(k & 0xff)
@@ -243,6 +252,8 @@ def run_ours(args):
             ev[k][1].record()
         _barrier(world)
         wall = time.perf_counter() - t0
+    finally:
+        clocks.__exit__(None, None, None)
     launches = lib.isob200_launch_count() - l0
     prof = _ext.PROFILE
     _ext.PROFILE = None

@@ -1,7 +1,8 @@
-"""Free-space and in-surface training samples from the visible iso-points.
+"""Visible iso-points, and the free-space / in-surface training samples taken from them.
 
-Mirrors ``Model.sample_offsurface_using_isopoints`` (DSS/models/combined_modeling.py:237-388), the consumer of
-``get_visible_points`` in ``train_mvr.py``'s step:
+Mirrors ``Model.get_visible_iso_points`` (DSS/models/combined_modeling.py:390-455; see ``get_visible_iso_points``
+below) and ``Model.sample_offsurface_using_isopoints`` (:237-388), the consumers of ``get_visible_points`` in
+``train_mvr.py``'s step.  The sampler:
 
 * off-surface: for the pixels outside the ground-truth mask, a random point on the segment the camera ray cuts
   out of the bounding cube (``intersection_with_unit_cube``, DSS/utils/__init__.py:402-483) -- plus, optionally,
@@ -32,7 +33,7 @@ from . import _ext, siren
 from .structures import num_points_2_cloud_to_packed_first_idx  # noqa: F401  (re-exported for callers)
 
 __all__ = ["closest_point_to_rays", "intersection_with_unit_cube", "get_tensor_values", "insurface_segments",
-           "sample_offsurface_using_isopoints"]
+           "sample_offsurface_using_isopoints", "subsample_randomly", "get_visible_iso_points"]
 
 
 def closest_point_to_rays(origins, ray_directions, points, return_dist=False):
@@ -185,3 +186,90 @@ def sample_offsurface_using_isopoints(model, pixels, mask_img, cameras, n_points
         best = torch.argmin(vals.view(cand.shape[0], n_points_per_ray), dim=-1, keepdim=True)
         p_ins = torch.gather(cand, -2, best.unsqueeze(-1).expand(-1, -1, 3)).squeeze(-2)
     return p_off, p_ins, num_off, num_ins
+
+
+def subsample_randomly(point_clouds, ratio, generator=None):
+    """``PointClouds3D.subsample_randomly`` (DSS/core/cloud.py:260-283): keep ``int(ratio[b] * P_b)`` points of
+    every cloud, chosen by a random permutation (``generator``: optional torch.Generator for reproducible
+    tests; the reference uses the global CPU generator)."""
+    n = len(point_clouds)
+    if not torch.is_tensor(ratio):
+        ratio = torch.full((n,), float(ratio))
+    ratio = ratio.detach().float().cpu().clamp(max=1.0)
+    if ratio.numel() != n:
+        raise ValueError("subsample_randomly: %d ratios for %d clouds" % (ratio.numel(), n))
+    if bool((ratio == 1.0).all()):
+        return point_clouds.clone()
+    pts, nrm, feat = point_clouds.points_list(), point_clouds.normals_list(), point_clouds.features_list()
+    out_p, out_n, out_f = [], [], []
+    for b, p in enumerate(pts):
+        keep = torch.randperm(p.shape[0], generator=generator)[:int(ratio[b] * p.shape[0])].to(p.device)
+        out_p.append(p[keep])
+        if nrm is not None:
+            out_n.append(nrm[b][keep])
+        if feat is not None:
+            out_f.append(feat[b][keep])
+    return point_clouds.__class__(out_p, normals=out_n if nrm is not None else None,
+                                  features=out_f if feat is not None else None)
+
+
+def get_visible_iso_points(model, cameras, jitter=None, generator=None, **proj_kwargs):
+    """``Model.get_visible_iso_points`` (DSS/models/combined_modeling.py:390-455): the iso-points of
+    ``model._points`` that the cameras see, topped up / thinned to about ``model.max_iso_per_batch`` per view,
+    jittered by +-0.025, re-projected onto the level set (``model.projection.project_points``, no resampling) and
+    filtered for visibility once more.  Returns a Pointclouds with normals (one cloud per camera).
+
+    ``model`` is duck-typed on ``_points``, ``max_iso_per_batch``, ``projection``, ``decoder``, ``device``,
+    ``get_normals_from_grad`` (only called when the clouds carry no normals) and
+    ``renderer.rasterizer.raster_settings.depth_merging_threshold``.  ``jitter`` (P,3) in [0,1) replaces the
+    ``torch.rand_like`` draw of :441, ``generator`` seeds the random subsampling (reproducible tests).  Every
+    stage runs on this package's kernels: three visibility splats, FRNN-based upsampling, the fused projection."""
+    from .cloud import PointCloudsFilters
+    from .ewa import get_visible_points
+    from .levelset_sampling import _mask_padded_to_list
+    from .point_processing import upsample
+    from .structures import Pointclouds
+    cap = model.max_iso_per_batch
+    if cap == 0:
+        return torch.zeros((1, 0, 3), device=model.device, dtype=torch.float)
+    B = cameras.R.shape[0]
+    thr = model.renderer.rasterizer.raster_settings.depth_merging_threshold
+    if model._points.normals_packed() is None:          # the visibility test culls back faces
+        model._points.update_normals_(model.get_normals_from_grad(model._points.points_packed(), requires_grad=False))
+    ref_pcl = proj_kwargs.get("ref_pcl", None)
+    if ref_pcl is not None:
+        if len(ref_pcl) != 1:
+            raise AssertionError("Currently support optimizing a single shape, with only one reference point cloud.")
+        if ref_pcl.normals_packed() is None:
+            ref_pcl.update_normals_(model.get_normals_from_grad(ref_pcl.points_packed(), requires_grad=False))
+        _, seen = get_visible_points(ref_pcl, cameras, depth_merge_threshold=thr, return_mask=True)
+        ref_pcl = PointCloudsFilters(device=ref_pcl.device, visibility=seen.any(dim=0, keepdim=True)).filter(ref_pcl)
+        proj_kwargs["ref_pcl"] = ref_pcl
+
+    start = model._points.clone()
+    visible, seen = get_visible_points(start.extend(B), cameras, depth_merge_threshold=thr, return_mask=True)
+    if cap > 0:       # between 0.75 cap and cap points per view (:426-440)
+        hi, lo = cap, 0.75 * cap
+        if ref_pcl is not None:
+            lo, hi = int(0.8 * lo), int(0.8 * hi)
+        counts = visible.num_points_per_cloud().tolist()
+        per_view = []
+        for b in range(B):
+            if counts[b] > hi:
+                per_view.append(subsample_randomly(visible[b], hi / float(counts[b]), generator).points_packed())
+            elif counts[b] < lo:
+                per_view.append(upsample(visible[b], hi).points_packed())
+            else:
+                per_view.append(visible[b].points_packed())
+        visible = Pointclouds(per_view)
+    else:
+        visible = PointCloudsFilters(device=start.device, visibility=seen.any(dim=0, keepdim=True)).filter(start)
+
+    packed = visible.points_packed()
+    u = torch.rand_like(packed) if jitter is None else jitter.to(packed)
+    visible.offset_(0.05 * (u - 0.5))
+    res = model.projection.project_points(visible, model.decoder, skip_resampling=True,
+                                          skip_upsampling=(ref_pcl is None), **proj_kwargs)
+    iso = Pointclouds(list(_mask_padded_to_list(res["levelset_points"], res["mask"])),
+                      normals=list(_mask_padded_to_list(res["levelset_normals"], res["mask"])))
+    return get_visible_points(iso, cameras, depth_merge_threshold=thr)

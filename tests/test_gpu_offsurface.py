@@ -152,3 +152,44 @@ def test_sampler_end_to_end_on_the_fused_siren_decoder():
     assert float(p_off.abs().max()) <= 1.05 + 1e-5                 # off-surface samples stay in the padded cube
     none = offsurface.sample_offsurface_using_isopoints(_model(decoder, pc.extend(2)), pixels, mask_img, cams)
     assert none[1].shape == (0, 3) and none[3].tolist() == [0, 0]
+
+
+@pytest.mark.parametrize("cap,n_iso", [(2000, 20000), (6000, 9000)])
+def test_get_visible_iso_points(cap, n_iso):
+    """Model.get_visible_iso_points (combined_modeling.py:390-455): thinning (visible > cap) and topping up
+    (visible < 0.75 cap) branches; the result lies on the level set, faces the camera and carries normals."""
+    from isopoints_b200.levelset_sampling import UniformProjection
+    from tests.helpers import SphereSDF
+    pc = _sphere_cloud(n_iso, seed=4)
+    cams = PinholeCameras.look_at_origin(2, seed=6, device=DEV)
+    model = _model(SphereSDF(radius=0.6).to(DEV), pc)
+    model.max_iso_per_batch = cap
+    model.device = torch.device(DEV)
+    model.projection = UniformProjection(proj_max_iters=10, proj_tolerance=5e-5)
+    g = torch.Generator().manual_seed(0)
+    iso = offsurface.get_visible_iso_points(model, cams, generator=g)
+    assert len(iso) == 2 and iso.normals_packed() is not None
+    centre = cams.get_camera_center()
+    n_vis0 = ewa.get_visible_points(pc.extend(2), cams).num_points_per_cloud().tolist()
+    for b in range(2):
+        p, n = iso.points_list()[b], iso.normals_list()[b]
+        assert 0.5 * min(cap, n_vis0[b]) < p.shape[0] <= max(cap, n_vis0[b])
+        assert float((p.norm(dim=-1) - 0.6).abs().max()) < 1e-4                       # on the level set
+        assert bool(((p * centre[b]).sum(-1) > -0.05).all())                          # on the camera's side (back-face cull)
+        np.testing.assert_allclose(n.cpu().numpy(), (p / 0.6).cpu().numpy(), atol=1e-3)   # normals = SDF gradient
+    if cap == 2000:
+        assert max(n_vis0) > cap                 # the thinning branch ran
+    else:
+        assert max(n_vis0) < 0.75 * cap          # the topping-up branch ran
+    model.max_iso_per_batch = 0
+    assert tuple(offsurface.get_visible_iso_points(model, cams).shape) == (1, 0, 3)
+
+
+def test_subsample_randomly():
+    pc = Pointclouds([torch.rand(100, 3, device=DEV), torch.rand(40, 3, device=DEV)],
+                     normals=[torch.rand(100, 3, device=DEV), torch.rand(40, 3, device=DEV)])
+    out = offsurface.subsample_randomly(pc, torch.tensor([0.25, 2.0]), torch.Generator().manual_seed(1))
+    assert out.num_points_per_cloud().tolist() == [25, 40] and out.normals_packed().shape == (65, 3)
+    src = {tuple(r) for r in pc.points_list()[0].cpu().numpy().round(6).tolist()}
+    assert all(tuple(r) in src for r in out.points_list()[0].cpu().numpy().round(6).tolist())
+    assert offsurface.subsample_randomly(pc, 1.0).num_points_per_cloud().tolist() == [100, 40]

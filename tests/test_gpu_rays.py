@@ -48,7 +48,9 @@ def test_matches_reference_golden(golden, name, make, iters, mode):
     steps = torch.as_tensor(g[key + "steps"], device=DEV) if mode == "train" else None
     got = tracer(sdf, cam, om, dirs, minimal_sdf_steps=steps)
     assert got[0].shape == (3000, 3) and got[1].dtype == torch.bool and got[2].shape == (3000,)
-    _agree(got, (g[key + "points"], g[key + "mask"], g[key + "dists"]))
+    # training mode moves the network hits outside the ground-truth mask to the arg-min of 64 samples along the
+    # ray (:904-913): near-ties between two samples on either side of the minimum pick differently at 1e-7
+    _agree(got, (g[key + "points"], g[key + "mask"], g[key + "dists"]), frac_close=0.995 if mode == "eval" else 0.97)
     if mode == "train":
         # rays outside the network's object keep the minimal-SDF sample: compare those too (sample choice can
         # differ on near-ties, so a fraction)
