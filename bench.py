@@ -60,6 +60,9 @@ def _peaks():
         return {"hbm_gbs": 6650.0}, "fallback"
 
 
+PREROLL_STEPS = 50   # minimum number of untimed steps before the timed region (clock ramp of an idle GPU)
+
+
 class ClockSampler:
     """SM clock / throttle reasons sampled DURING the timed region.
 
@@ -234,12 +237,18 @@ def run_ours(args):
     from isopoints_b200 import siren as _siren
     _ext.PROFILE = {}
     _siren.RECORD = []
-    for k in range(args.warmup):
+    # ... and there are at least PREROLL_STEPS of them (~0.4 s; the same count on every rank -- the sharded step
+    # has collectives), so that a GPU that idled at low clocks on a fresh box has ramped up before the first
+    # timed step (seen: 13 ms first step of the first process on a box against 8.0-8.5 ms afterwards)
+    for k in range(max(args.warmup, PREROLL_STEPS)):
         flush.fill_(k & 0xff)
         wa, wb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         wa.record()
         out = step(x_dev)
         wb.record()
+        torch.cuda.synchronize()
+        _ext.PROFILE = {}
+        _siren.RECORD = []
     _barrier(world)
 
     # ---- timed region: K steps, device resident inputs, L2 flushed between steps ----------
@@ -341,7 +350,8 @@ def run_ours(args):
         "config": {"workload": C2_WORKLOAD, "points_per_gpu": C2_POINTS, "sdf": args.sdf,
                    "sdf_eval": ("fused tcgen05 kernel, fp32-equivalent via fp16 hi/lo split" if sd else
                                 "opaque nn.Module through autograd, fp32, TF32 off"),
-                   "l2": "flushed between steps (256 MiB write)", "converged_frac": converged,
+                   "l2": "flushed between steps (256 MiB write)", "untimed_steps_before": max(args.warmup, PREROLL_STEPS),
+                   "converged_frac": converged,
                    "points_after_filter": n_out, "parallelism": "point-sharded x%d" % world},
         "e2e": {"value": C2_POINTS * world / (e2e_ms * 1e-3), "unit": "points/s", "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms},

@@ -7,6 +7,12 @@ timeout 900 python -m pytest tests -m gpu -q 2>&1 | tail -40 > gpurun_out/pytest
 timeout 200 python __graft_entry__.py smoke 2>&1 | tail -2
 timeout 600 python bench.py --steps 5 --warmup 3 > gpurun_out/bench.json 2> gpurun_out/bench.err; tail -c 3000 gpurun_out/bench.json; grep -v Warning gpurun_out/bench.err | tail -5
 timeout 300 python bench.py --impl reference --steps 1 --warmup 0 > gpurun_out/bench_reference.json 2>/dev/null; tail -c 300 gpurun_out/bench_reference.json
+if [ "${1:-}" = "prof5" ]; then
+  timeout 200 python bench_splat.py --steps 5 > gpurun_out/bench_splat.json 2>/dev/null; tail -c 300 gpurun_out/bench_splat.json; echo
+  timeout 200 python bench_trace.py --steps 5 > gpurun_out/bench_trace.json 2>/dev/null; tail -c 300 gpurun_out/bench_trace.json; echo
+  timeout 100 python bench_rays.py --steps 20 > gpurun_out/bench_rays.json 2>/dev/null
+  timeout 100 python bench.py --steps 5 --warmup 3 2>/dev/null | python -c "import json,sys; d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print('second run:', d['value'], d['ms_each_step'])"
+fi
 if [ "${1:-}" = "prof4" ]; then
   # launch list of the C2 bench command (kernel shares of the step)
   timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 6000 --csv --log-file gpurun_out/launches_c2.csv python bench.py --steps 1 --warmup 3 > gpurun_out/ncu_c2.log 2>&1; tail -1 gpurun_out/ncu_c2.log | cut -c1-200
