@@ -220,8 +220,14 @@ class sdf_fn:
     ``sdf=lambda x: model.decode(x).sdf.squeeze(-1)``): evaluates a fusable decoder with the forward-only fused
     kernel, anything else through ``model.forward(x).sdf`` without autograd."""
 
+    any_size = True     # ray_tracing._eval_chunked: no need to chunk the input when the fused kernel evaluates it
+
     def __init__(self, model, **forward_kwargs):
         self.model, self.forward_kwargs = model, forward_kwargs
+
+    def fused(self):
+        """True when ``model`` is evaluated by the fused kernel (memory per row: 4 bytes out, no activations)."""
+        return match(self.model, self.forward_kwargs) is not None
 
     def __call__(self, x):
         v = sdf(self.model, x, self.forward_kwargs) if x.is_cuda else None
