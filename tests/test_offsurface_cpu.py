@@ -66,3 +66,44 @@ def test_point_cloud_filters():
 def test_kernel_entry_points_refuse_cpu_tensors():
     with pytest.raises(TypeError):
         offsurface.closest_point_to_rays(torch.zeros(3), torch.zeros(4, 3), torch.zeros(5, 3))
+
+
+def test_sampler_host_sequence_matches_reference_golden(golden, monkeypatch):
+    """The host sequence of ``sample_offsurface_using_isopoints`` on CPU tensors, with the point-to-ray kernel
+    stood in for by the oracle's dense formulation (test-only: the product entry point has no CPU path, see
+    test_kernel_entry_points_refuse_cpu_tensors) -- must reproduce the reference's own method exactly."""
+    import types
+    from oracle import port
+    from tests.helpers import TinySiren
+    g = golden("offsurface")
+    cams, pixels, mask_img, frontal, occluded, iso_pcl = offsurface_inputs()
+
+    def dense(origins, rays, points, return_dist=False):
+        t_sq, idx, _, _ = port.ray_nearest_point(origins.view(3), rays, points)
+        return t_sq, idx
+    monkeypatch.setattr(offsurface, "closest_point_to_rays", dense)
+    answers = [Pointclouds(frontal), Pointclouds(occluded)]
+    calls = []
+
+    def visible(points, cameras, depth_merge_threshold=0.05):
+        calls.append((cameras.R.clone(), cameras.T.clone()))
+        return answers[len(calls) - 1]
+    model = types.SimpleNamespace(
+        _points=None, decoder=TinySiren(seed=3), max_points_per_pass=10000, object_bounding_sphere=1.0,
+        renderer=types.SimpleNamespace(rasterizer=types.SimpleNamespace(
+            raster_settings=types.SimpleNamespace(depth_merging_threshold=0.05))))
+    R0, T0 = cams.R.clone(), cams.T.clone()
+    p_off, p_ins, n_off, n_ins = offsurface.sample_offsurface_using_isopoints(
+        model, pixels, mask_img, cams, n_points_per_ray=int(g["n_points_per_ray"]),
+        max_insurface_per_batch=g["max_insurface"].tolist(), iso_pcl=Pointclouds(iso_pcl),
+        rand=torch.as_tensor(g["rand"]), visible_points_fn=visible)
+    assert np.array_equal(n_off.numpy(), g["n_off"]) and np.array_equal(n_ins.numpy(), g["n_ins"])
+    np.testing.assert_allclose(p_off.numpy(), g["p_off"], rtol=0, atol=1e-6)
+    np.testing.assert_allclose(p_ins.numpy(), g["p_ins"], rtol=0, atol=1e-6)
+    # the mirrored camera handed to the second visibility pass; the caller's cameras are left alone
+    np.testing.assert_allclose(calls[1][0].numpy(), g["back_R"], atol=1e-7)
+    np.testing.assert_allclose(calls[1][1].numpy(), g["back_T"], atol=1e-6)
+    assert torch.equal(cams.R, R0) and torch.equal(cams.T, T0)
+    # the mirrored camera sits at the antipode of the original one
+    back = PinholeCameras(torch.as_tensor(g["back_R"]), torch.as_tensor(g["back_T"]))
+    np.testing.assert_allclose(back.get_camera_center().numpy(), -cams.get_camera_center().numpy(), atol=1e-5)
