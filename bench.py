@@ -17,6 +17,9 @@ autograd callback), UniformProjection(proj_max_iters=10, tol=5e-5, knn_k=8, samp
 N > 1 (torchrun, one rank per GPU): the cloud is sharded by contiguous point ranges (weak scaling,
 200 000 points per rank); projection is embarrassingly parallel, the resample exchanges projected
 positions + normals with one all-gather so that every rank searches the full cloud.
+Before the K timed steps: max(W, 50) untimed steps with exactly the timed steps' instrumentation (L2 flush,
+per-call CUDA events), so that event pools, NVML and the GPU clocks are in steady state -- `ms_each_step` in
+the line shows every timed step, `config.untimed_steps_before` the count.
 `--impl reference` times the CPU restatement of the reference path (oracle/port.py; the path is
 Python + third-party CUDA-only FRNN, so the reference itself cannot run on host cores) on rank 0.
 """
