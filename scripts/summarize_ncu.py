@@ -136,9 +136,15 @@ def main():
               "ref_cuda_timing.json"):
         p = os.path.join(OUT, f)
         if os.path.exists(p):
-            lines = [l for l in open(p).read().splitlines() if l.startswith("{")]
-            if lines:
-                open(os.path.join(PROF, "%s_%s" % (tag, f)), "w").write(lines[-1] + "\n")
+            text = open(p).read()
+            try:                                   # a pretty-printed file is one JSON document: keep it whole
+                json.loads(text)
+                keep = text.strip()
+            except ValueError:                     # a log with one JSON line at the end
+                lines = [l for l in text.splitlines() if l.startswith("{")]
+                keep = lines[-1] if lines else None
+            if keep:
+                open(os.path.join(PROF, "%s_%s" % (tag, f)), "w").write(keep + "\n")
 
 
 if __name__ == "__main__":
