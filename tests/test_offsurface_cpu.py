@@ -107,3 +107,86 @@ def test_sampler_host_sequence_matches_reference_golden(golden, monkeypatch):
     # the mirrored camera sits at the antipode of the original one
     back = PinholeCameras(torch.as_tensor(g["back_R"]), torch.as_tensor(g["back_T"]))
     np.testing.assert_allclose(back.get_camera_center().numpy(), -cams.get_camera_center().numpy(), atol=1e-5)
+
+
+def test_visible_iso_points_host_sequence(monkeypatch):
+    """Branch logic of ``get_visible_iso_points`` (combined_modeling.py:390-455) on CPU tensors with the three
+    kernel-backed stages stood in for: which clouds are thinned / topped up / kept (incl. the 0.8 factors with a
+    reference cloud), where the jitter goes, and what reaches the projection and the final visibility pass."""
+    import types
+    from isopoints_b200 import ewa, point_processing
+    g = torch.Generator().manual_seed(0)
+    base = torch.rand(1000, 3, generator=g)
+    seen_counts = [900, 500, 200]                       # per view: > cap, within [0.75 cap, cap], < 0.75 cap
+    log = {"visible": [], "upsample": [], "project": None}
+
+    def fake_visible(pcl, cameras, depth_merge_threshold=0.05, return_mask=False):
+        log["visible"].append((len(pcl), pcl.num_points_per_cloud().tolist(), depth_merge_threshold))
+        if len(log["visible"]) == 1:                    # the first pass: per-view subsets of the model's points
+            keep = [torch.arange(1000) < n for n in seen_counts]
+            out = Pointclouds([pcl.points_list()[b][keep[b]] for b in range(3)])
+            return (out, torch.stack(keep)) if return_mask else out
+        return pcl                                      # the last pass: everything stays visible
+
+    def fake_upsample(pcl, n_points):
+        log["upsample"].append((pcl.num_points_per_cloud().tolist(), n_points))
+        p = pcl.points_packed()
+        reps = -(-n_points // p.shape[0])
+        return Pointclouds([p.repeat(reps, 1)[:n_points]])
+
+    class FakeProjection:
+        def project_points(self, pcl, decoder, skip_resampling=False, skip_upsampling=False, **kw):
+            log["project"] = (pcl.num_points_per_cloud().tolist(), skip_resampling, skip_upsampling, sorted(kw))
+            pts = pcl.points_padded()
+            n = pcl.num_points_per_cloud()
+            mask = torch.arange(pts.shape[1])[None, :] < n[:, None]
+            mask[:, 0] = False                          # one point per view fails to converge
+            return {"levelset_points": pts + 1.0, "levelset_normals": torch.ones_like(pts), "mask": mask}
+
+    monkeypatch.setattr(ewa, "get_visible_points", fake_visible)
+    monkeypatch.setattr(point_processing, "upsample", fake_upsample)
+    cams = PinholeCameras.look_at_origin(3, seed=2)
+    model = types.SimpleNamespace(
+        _points=Pointclouds([base], normals=[torch.ones(1000, 3)]), decoder=None, max_iso_per_batch=600,
+        projection=FakeProjection(), device=torch.device("cpu"),
+        renderer=types.SimpleNamespace(rasterizer=types.SimpleNamespace(
+            raster_settings=types.SimpleNamespace(depth_merging_threshold=0.07))))
+    jitter = torch.full((600 + 500 + 600, 3), 0.5)      # zero offset after the (u - 0.5) shift
+    out = offsurface.get_visible_iso_points(model, cams, jitter=jitter, generator=torch.Generator().manual_seed(3))
+    assert log["visible"][0] == (3, [1000, 1000, 1000], 0.07)                # the model's cloud, one copy per view
+    assert log["upsample"] == [([200], 600)]                                 # only the sparse view is topped up
+    assert log["project"] == ([600, 500, 600], True, True, [])               # thinned / kept / topped up; no resampling
+    assert log["visible"][1][1] == [599, 499, 599]                           # converged points only
+    assert out.num_points_per_cloud().tolist() == [599, 499, 599] and out.normals_packed() is not None
+    kept_mid = out.points_list()[1] - 1.0                                    # the untouched view: points 1..499 of base
+    assert torch.allclose(kept_mid, base[1:500], atol=1e-6)
+    thinned = out.points_list()[0] - 1.0                                     # a random subset of the 900 seen points
+    gap = (thinned[:, None, :] - base[None, :900, :]).abs().amax(-1)              # (599, 900)
+    assert float(gap.min(dim=1).values.max()) < 1e-6
+    assert gap.argmin(dim=1).unique().numel() == thinned.shape[0]                   # no point taken twice
+    # with a reference cloud the bounds shrink by 0.8 (int(0.8 * 600) = 480, int(0.8 * 450) = 360) and the
+    # projection is allowed to upsample
+    log["visible"].clear(); log["upsample"].clear()
+    ref = Pointclouds([torch.rand(50, 3, generator=g)], normals=[torch.ones(50, 3)])
+    ref_seen = torch.arange(50)[None, :] < torch.tensor([[10], [20], [0]])     # per view; the union keeps 20 points
+
+    def fake_visible_ref(pcl, cameras, depth_merge_threshold=0.05, return_mask=False):
+        if pcl.num_points_per_cloud().tolist() == [50]:                          # the reference cloud's own pass
+            return pcl, ref_seen
+        return fake_visible(pcl, cameras, depth_merge_threshold, return_mask)
+    monkeypatch.setattr(ewa, "get_visible_points", fake_visible_ref)
+    seen_ref = {}
+
+    class RefProjection(FakeProjection):
+        def project_points(self, pcl, decoder, **kw):
+            seen_ref["n"] = kw["ref_pcl"].num_points_per_cloud().tolist()
+            return super().project_points(pcl, decoder, **kw)
+    model.projection = RefProjection()
+    jitter = torch.full((480 + 480 + 480, 3), 0.5)
+    offsurface.get_visible_iso_points(model, cams, jitter=jitter, ref_pcl=ref)
+    assert log["upsample"] == [([200], 480)]
+    counts, skip_rs, skip_up, extra = log["project"]
+    assert counts == [480, 480, 480] and skip_rs and not skip_up and extra == ["ref_pcl"]
+    assert seen_ref["n"] == [20]                      # the reference cloud reduced to what any camera sees
+    model.max_iso_per_batch = 0
+    assert tuple(offsurface.get_visible_iso_points(model, cams).shape) == (1, 0, 3)
