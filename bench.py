@@ -420,16 +420,35 @@ def cpu_baseline(sample_points=10_000, threads=None):
     g = torch.Generator().manual_seed(1000)
     x = ((torch.rand(1, C2_POINTS, 3, generator=g) - 0.5) * 2)[0, :sample_points].contiguous()
     net = SirenSDF(hidden=256, n_layers=7, omega=30.0, seed=0)
+    frnn_fn, frnn_how = _cpu_frnn()
     t0 = time.perf_counter()
     p, n, v = port.project_points_packed(net, x, proj_max_iters=10, proj_tolerance=5e-5)
     t1 = time.perf_counter()
     if int(v.sum()) >= 18:
-        port.resample(net, p[v], n[v], sample_iters=1, knn_k=8, proj_tolerance=5e-5)
+        port.resample(net, p[v], n[v], sample_iters=1, knn_k=8, proj_tolerance=5e-5, frnn_fn=frnn_fn)
     t2 = time.perf_counter()
     return {"value": sample_points / (t2 - t0), "unit": "points/s", "cores": threads, "kind": "port",
             "sample": "first %d of the 200000 C2 points, same SIREN; project %.1fs + resample %.1fs; "
-                      "torch-CPU fp32 with %d threads (FRNN stage: numpy brute force, 1 thread)"
-                      % (sample_points, t1 - t0, t2 - t1, threads)}
+                      "torch-CPU fp32 with %d threads (FRNN stage: %s)"
+                      % (sample_points, t1 - t0, t2 - t1, threads, frnn_how)}
+
+
+def _cpu_frnn():
+    """FRNN stage of the CPU baseline: the reference's OWN CPU implementation (frnn._C.frnn_bf_cpu,
+    external/FRNN/frnn/csrc/bruteforce/bruteforce_cpu.cpp, compiled unmodified into oracle/_ref) when that
+    library is present, else the numpy restatement in oracle/port.py.  Same indices either way."""
+    try:
+        from oracle import ref_native
+        probe = torch.rand(1, 32, 3)
+        ref_native.frnn_bf_cpu(probe, probe, torch.tensor([32]), torch.tensor([32]), 4, 0.5)
+
+        def fn(points, K, r):
+            t = torch.as_tensor(points)[None].contiguous()
+            n = torch.tensor([t.shape[1]])
+            return ref_native.frnn_bf_cpu(t, t, n, n, K, r)[0][0].numpy()
+        return fn, "the reference's own frnn_bf_cpu, 1 thread"
+    except Exception:
+        return None, "numpy brute force, 1 thread"
 
 
 def run_reference(args):
