@@ -30,7 +30,6 @@ import torch
 import torch.nn.functional as F
 
 from . import _ext, siren
-from .structures import num_points_2_cloud_to_packed_first_idx  # noqa: F401  (re-exported for callers)
 
 __all__ = ["closest_point_to_rays", "intersection_with_unit_cube", "get_tensor_values", "insurface_segments",
            "sample_offsurface_using_isopoints", "subsample_randomly", "get_visible_iso_points"]
