@@ -77,6 +77,29 @@ def compute_isotropic_vrk_h(points_padded, num_points_per_cloud, frnn_radius, fi
     return h
 
 
+def global_vrk_h_from_sq_dist(sq_dist, num_points_per_cloud):
+    """One h per cloud from the K = 7 self-query distances (N, P_max, 7) -- ``_compute_global_Vrk``
+    (rasterizer.py:303-322): drop the self column, clouds with fewer than 7 points get 1e-3 everywhere, half the
+    largest neighbour distance per row, MEAN OVER THE PADDED ROWS (their distances are the -1 padding, as in the
+    reference), clamped to [5e-5, 1e-3].  Returns (N,)."""
+    sq = sq_dist[:, :, 1:].clone()
+    sq[num_points_per_cloud.to(sq.device) < 7] = 1e-3
+    h = 0.5 * sq.max(dim=-1, keepdim=True)[0]
+    return h.mean(dim=1, keepdim=True).clamp(5e-5, 1e-3).view(-1)
+
+
+def compute_global_vrk_h(points_padded, num_points_per_cloud, frnn_radius):
+    """h_k of the view-invariant V_k^r (``Vrk_invariant=True``, rasterizer.py:292-343), packed (P,): the per-cloud
+    value of ``global_vrk_h_from_sq_dist`` repeated for the cloud's points."""
+    if frnn_radius <= 0:
+        raise NotImplementedError("frnn_radius <= 0 selects pytorch3d's brute-force knn_points in the reference "
+                                  "(rasterizer.py:306-311); only the FRNN branch (:312-315) is built")
+    pts = _f32(points_padded, "points_padded")
+    num = num_points_per_cloud.to(device=pts.device, dtype=torch.int64).contiguous()
+    sq_dist = frnn_grid_points(pts, pts, num, num, K=7, r=frnn_radius)[0]
+    return torch.repeat_interleave(global_vrk_h_from_sq_dist(sq_dist, num), num)
+
+
 def get_per_point_info(points_packed, normals_packed, cloud_to_packed_first_idx, proj_matrix, vrk_h,
                        image_size, antialiasing_sigma=1.0, cutoff_threshold=1.0):
     """_get_per_point_info (rasterizer.py:514-563) with the isotropic V_k^r: returns the reference's dict
@@ -150,8 +173,9 @@ def _compact_rows3(points, normals, mask_u8, n_keep):
 
 
 class SurfaceSplatting:
-    """DSS/core/rasterizer.py:79-661 on the kernels of this package (isotropic V_k^r, the default of
-    PointsRasterizationSettings: Vrk_isotropic=True, Vrk_invariant=False)."""
+    """DSS/core/rasterizer.py:79-661 on the kernels of this package: the isotropic V_k^r (the default of
+    PointsRasterizationSettings: Vrk_isotropic=True, Vrk_invariant=False) and the view-invariant one
+    (Vrk_invariant=True, one h per cloud); the anisotropic variant raises NotImplementedError."""
 
     def __init__(self, cameras=None, raster_settings=None, frnn_radius=0.2):
         if raster_settings is None:
@@ -174,9 +198,12 @@ class SurfaceSplatting:
     def _get_per_point_info(self, pointclouds, **kwargs):
         rs = kwargs.get("raster_settings", self.raster_settings)
         cameras = kwargs.get("cameras", self.cameras)
-        if getattr(rs, "Vrk_invariant", False) or not getattr(rs, "Vrk_isotropic", True):
-            raise NotImplementedError("only the isotropic V_k^r (rasterizer.py:344-400) is built")
-        h = self._compute_isotropic_Vrk_h(pointclouds, refresh=kwargs.get("refresh", True))
+        if getattr(rs, "Vrk_invariant", False):       # checked first, as in rasterizer.py:418-419
+            h = compute_global_vrk_h(pointclouds.points_padded(), pointclouds.num_points_per_cloud(), self.frnn_radius)
+        elif getattr(rs, "Vrk_isotropic", True):
+            h = self._compute_isotropic_Vrk_h(pointclouds, refresh=kwargs.get("refresh", True))
+        else:
+            raise NotImplementedError("the anisotropic V_k^r (rasterizer.py:256-290) is not built")
         return get_per_point_info(pointclouds.points_packed(), pointclouds.normals_packed(),
                                   pointclouds.cloud_to_packed_first_idx(),
                                   cameras.get_full_projection_transform().get_matrix(), h, rs.image_size,
@@ -351,5 +378,6 @@ def PointsRasterizationSettings(**kw):
     return SimpleNamespace(**d)
 
 
-__all__ = ["SurfaceSplatting", "SurfaceSplattingRenderer", "get_visible_points", "PointsRasterizationSettings", "compute_isotropic_vrk_h", "get_per_point_info",
+__all__ = ["SurfaceSplatting", "SurfaceSplattingRenderer", "get_visible_points", "compute_global_vrk_h",
+           "global_vrk_h_from_sq_dist", "PointsRasterizationSettings", "compute_isotropic_vrk_h", "get_per_point_info",
            "renderable_mask", "visibility_mask", "packed_to_padded"]

@@ -188,6 +188,42 @@ def ewa_golden():
           "renderable", float(mask_renderable.float().mean()))
 
 
+def ewa_global_golden():
+    """The view-invariant V_k^r setting (`Vrk_invariant=True`: `_compute_global_Vrk`, rasterizer.py:292-343 -- one
+    clamped mean h per cloud) through the reference's `_get_per_point_info`, on the inputs of `ewa_golden`
+    (ragged batch: the mean runs over the PADDED rows, whose distances are the -1 padding) and on an
+    equal-sized batch."""
+    R = ref_python.load_rasterizer()
+    R.frnn = _CpuFrnn
+    SS = R.SurfaceSplatting
+    S, sigma, cutoff, znear, zfar, radius = 256, 1.0, 1.0, 2.0, 100.0, 0.2
+    out = dict(image_size=S, antialiasing_sigma=sigma, cutoff=cutoff, frnn_radius=radius, znear=znear, zfar=zfar)
+    for tag, num, seed in (("ragged", [900, 5, 700], 11), ("equal", [12000, 12000], 21)):
+        pts, nrm, first, numt = make_surface_points(num, seed=seed)
+        w2v, proj, nmat = make_cameras(len(num), seed=seed + 1, znear=znear, zfar=zfar)
+        ras = SS.__new__(SS)
+        ras.frnn_radius = radius
+        ras._Vrk_h = None
+        ras.raster_settings = types.SimpleNamespace(cutoff_threshold=cutoff, Vrk_invariant=True, Vrk_isotropic=True,
+                                                    image_size=S, antialiasing_sigma=sigma, backface_culling=True)
+        ras.cameras = _Cameras(w2v, proj, znear, zfar)
+        clouds = _Clouds([pts[f:f + n] for f, n in zip(first.tolist(), num)],
+                         [nrm[f:f + n] for f, n in zip(first.tolist(), num)])
+        torch.manual_seed(5)
+        info = SS._get_per_point_info(ras, clouds)
+        sq = _CpuFrnn.frnn_grid_points(clouds.points_padded(), clouds.points_padded(), numt, numt, K=7, r=radius)[0]
+        sq = sq[:, :, 1:].clone()
+        sq[numt < 7] = 1e-3
+        h = (0.5 * sq.max(dim=-1, keepdim=True)[0]).mean(dim=1, keepdim=True).clamp(5e-5, 1e-3).view(-1)
+        # inputs are regenerated from (num, seed) by the test (tests/helpers.py); outputs every `step`-th row
+        step = 8 if sum(num) > 5000 else 1
+        out.update({tag + "_num": np.asarray(num), tag + "_seed": seed, tag + "_step": step, tag + "_h_cloud": h.numpy(),
+                    tag + "_radii": info["radii"].numpy()[::step], tag + "_ellipse": info["ellipse_params"].numpy()[::step],
+                    tag + "_scaler": info["scaler"].numpy()[::step]})
+        print("ewa global %s: h per cloud %s, radii px %.2f" % (tag, h.tolist(), float(info["radii"].mean()) * S / 2))
+    np.savez_compressed(os.path.join(HERE, "ewa_point_info_global.npz"), **out)
+
+
 def trace_golden(LS):
     """SphereTracing.project_points (levelset_sampling.py:679-808) on CPU tensors: a blob SDF and the unit
     sphere; rays that hit, graze and leave the bounding sphere."""
@@ -306,6 +342,9 @@ def main():
     if "--only" in sys.argv and sys.argv[sys.argv.index("--only") + 1] == "ewa":
         ref_python.load(frnn_module=_CpuFrnn)
         return ewa_golden()
+    if "--only" in sys.argv and sys.argv[sys.argv.index("--only") + 1] == "ewa_global":
+        ref_python.load(frnn_module=_CpuFrnn)
+        return ewa_global_golden()
     if "--only" in sys.argv and sys.argv[sys.argv.index("--only") + 1] == "trace":
         return trace_golden(ref_python.load(frnn_module=_CpuFrnn).levelset_sampling)
     if "--only" in sys.argv and sys.argv[sys.argv.index("--only") + 1] == "rays":

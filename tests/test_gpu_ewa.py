@@ -275,3 +275,36 @@ def test_edge_cases():
     rc = _ext.lib().isob200_ewa_point_params(None, None, None, 1, 4, None, 1, None, 0.0, 1.0, None, None, None, None,
                                              None)
     assert rc != 0 and b"null" in _ext.lib().isob200_last_error()
+
+
+@pytest.mark.parametrize("tag", ["ragged", "equal"])
+def test_view_invariant_vrk_matches_reference_golden(golden, tag):
+    """``Vrk_invariant=True`` (reference ``_compute_global_Vrk``, rasterizer.py:292-343): one clamped mean h per
+    cloud through the same parameter kernel, against the reference's own ``_get_per_point_info`` run with that
+    setting (tests/golden/make_golden.py --only ewa_global)."""
+    g = golden("ewa_point_info_global")
+    num, seed, step = g[tag + "_num"].tolist(), int(g[tag + "_seed"]), int(g[tag + "_step"])
+    pts, nrm, first, numt = make_surface_points(num, seed=seed)
+    w2v, proj, nmat = make_cameras(len(num), seed=seed + 1, znear=float(g["znear"]), zfar=float(g["zfar"]))
+    rs = ewa.PointsRasterizationSettings(image_size=int(g["image_size"]), antialiasing_sigma=float(g["antialiasing_sigma"]),
+                                         cutoff_threshold=float(g["cutoff"]), Vrk_invariant=True)
+    ras = ewa.SurfaceSplatting(cameras=_Cams(w2v.to(DEV), proj.to(DEV)), raster_settings=rs,
+                               frnn_radius=float(g["frnn_radius"]))
+    pc = Pointclouds(points=list(torch.split(pts.to(DEV), num)), normals=list(torch.split(nrm.to(DEV), num)))
+    h = ewa.compute_global_vrk_h(pc.points_padded(), pc.num_points_per_cloud(), float(g["frnn_radius"]))
+    assert tuple(h.shape) == (sum(num),)
+    per_cloud = torch.stack([h[f] for f in first.tolist()]).cpu().numpy()
+    np.testing.assert_allclose(per_cloud, g[tag + "_h_cloud"], rtol=1e-5, atol=0)
+    assert all(bool((h[f:f + n] == h[f]).all()) for f, n in zip(first.tolist(), num))      # one value per cloud
+    info = ras._get_per_point_info(pc)
+    for name, key in (("radii", "_radii"), ("ellipse_params", "_ellipse")):
+        got, want = info[name].cpu().numpy()[::step], g[tag + key]
+        assert got.shape == want.shape and np.isfinite(got).all(), name
+        assert _rel_rows(got, want) < 5e-4, name
+    got, want = info["scaler"].cpu().numpy()[::step], g[tag + "_scaler"]
+    w64 = np.abs(want.astype(np.float64))
+    assert (np.abs(got - want) <= 5e-4 * w64 + 1e-5 * np.median(w64)).all()
+    # and the setting changes the result: per-point h of the default setting differs from the per-cloud one
+    iso = ewa.compute_isotropic_vrk_h(pc.points_padded(), pc.num_points_per_cloud(), float(g["frnn_radius"]),
+                                      pc.cloud_to_packed_first_idx())
+    assert float((iso - h).abs().max()) > 1e-5
