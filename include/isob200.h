@@ -103,10 +103,6 @@ int isob200_project_sphere(float* points, float* normals, unsigned char* valid, 
  *      non-NULL, is a device int with the live row count (<= n_max) so a projection loop can
  *      run without reading the active count back.  dbg (NULL in production) receives the raw
  *      (128,256) accumulator of the first tile's GEMM number dbg_gemm (parity tests). ------- */
-/* kernel variant behind the siren entry points: 0 = one CTA per 128-row tile, 1 = CTA pairs (tcgen05
- * cta_group::2, two tiles in flight per pair); identical results.  Returns the previous setting. */
-int isob200_siren_set_pair_mode(int on);
-int isob200_siren_pair_stamps(long long* out_host, int n); /* tuning aid: cycle stamps of pair 0 (host buffer) */
 size_t isob200_siren_blob_bytes(int n_hidden);
 size_t isob200_siren_pack_ws_bytes(void);
 size_t isob200_siren_scratch_bytes(int n_hidden);
@@ -150,13 +146,6 @@ int isob200_ray_nearest_point(const float* origins, int n_origins, const float* 
 int isob200_siren_set_max_ctas(int n);
 /* tuning knob: tape (cos factor) layers 1..n are stored with the L2 evict-first policy; returns the old value */
 int isob200_siren_set_spill_layers(int n);
-/* Bring-up probe of the 2-CTA tensor-core path (tcgen05 cta_group::2, M = 128 across a CTA pair): one
- * (128 x K) x (256 x K)^T fp16 GEMM, dump (2,128,128) = raw TMEM of both CTAs.  Test-only. */
-int isob200_umma2_probe(const float* a, const float* b, int K, float* dump, void* stream);
-/* issue-rate microbenchmark: reps back-to-back K = 16 fp16 MMAs; mode % 10: 0 = cta_group::1 M = 128,
- * 1 = cta_group::2 M = 128, 2 = cta_group::2 M = 256, 3 = cta_group::1 M = 64; + 10: 128-byte swizzled
- * operands; + 100 n: N = 256 >> n (n = 0..3); cycles_dev[rank] = cycles until the commit lands. */
-int isob200_umma_rate(int mode, int reps, long long* cycles_dev, void* stream);
 
 /* ---- uniform resampling: UniformProjection.resample, one sample_iter
  *      (DSS/models/levelset_sampling.py:259, 268-284) ------------------------------------ */

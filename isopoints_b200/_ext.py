@@ -5,6 +5,7 @@ the call raises.  PyTorch is used only for device memory, streams and autograd p
 """
 import ctypes
 import os
+import threading
 
 import torch
 
@@ -43,10 +44,8 @@ _PROTOS = {
     "isob200_gather_rows3": (_i, [_vp, _vp, _i, _vp, _vp]),
     "isob200_compact_valid": (_i, [_vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _sz, _vp]),
     "isob200_project_sphere": (_i, [_vp, _vp, _vp, _ll, _f, _f, _f, _i, _vp]),
-    "isob200_siren_set_pair_mode": (_i, [_i]),
     "isob200_siren_set_max_ctas": (_i, [_i]),
     "isob200_siren_set_spill_layers": (_i, [_i]),
-    "isob200_siren_pair_stamps": (_i, [_vp, _i]),
     "isob200_siren_blob_bytes": (_sz, [_i]),
     "isob200_siren_pack_ws_bytes": (_sz, []),
     "isob200_siren_scratch_bytes": (_sz, [_i]),
@@ -58,8 +57,6 @@ _PROTOS = {
     "isob200_siren_trace_step": (_i, [_vp, _i, _vp, _vp, _i, _vp, _sz, _vp, _vp, _vp, _vp, _f, _f, _f, _f, _i, _vp, _vp,
                                       _vp, _vp]),
     "isob200_ray_nearest_point": (_i, [_vp, _i, _vp, _i, _vp, _i, _vp, _vp, _vp, _vp]),
-    "isob200_umma2_probe": (_i, [_vp, _vp, _i, _vp, _vp]),
-    "isob200_umma_rate": (_i, [_i, _i, _vp, _vp]),
     "isob200_resample_step": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _vp, _i, _i, _i, _i, _vp, _vp]),
     "isob200_normalize_rows3": (_i, [_vp, _ll, _f, _vp, _vp]),
     "isob200_wlop_density": (_i, [_vp, _vp, _i, _i, _vp, _i, _i, _i, _vp, _vp]),
@@ -89,11 +86,12 @@ _PROTOS = {
 
 _LIB = None
 _RAW = None
+_TLS = threading.local()
 
 # Optional per-entry-point device timing (bench.py): when PROFILE is a dict, every C-ABI call is
 # bracketed by CUDA events on the stream it is launched on; PROFILE[name] collects (start, end).
 PROFILE = None
-_NO_TIMING = ("_ws_bytes", "_blob_bytes", "_scratch_bytes", "isob200_siren_set_pair_mode", "isob200_siren_set_max_ctas", "isob200_siren_set_spill_layers", "isob200_siren_pair_stamps", "isob200_last_error", "isob200_abi_version", "isob200_compiled_arch",
+_NO_TIMING = ("_ws_bytes", "_blob_bytes", "_scratch_bytes", "isob200_siren_set_max_ctas", "isob200_siren_set_spill_layers", "isob200_last_error", "isob200_abi_version", "isob200_compiled_arch",
               "isob200_launch_count", "isob200_splat_record_bytes")
 
 
@@ -105,7 +103,7 @@ def _wrap(name, fn):
     if name.endswith(_NO_TIMING) or name in _NO_TIMING:
         return fn
 
-    def call(*args):
+    def timed(*args):
         if PROFILE is None:
             return fn(*args)
         st = torch.cuda.ExternalStream(args[-1]) if args[-1] else torch.cuda.current_stream()
@@ -116,6 +114,15 @@ def _wrap(name, fn):
         b.record(st)
         PROFILE.setdefault(name, []).append((a, b))
         return rc
+
+    def call(*args):
+        # device guard (the reference's torch extensions guard on the tensors' device): kernels launch on the
+        # CURRENT device, the stream handed in belongs to the device `stream()` was last asked for on this thread
+        dev = getattr(_TLS, "dev", None)
+        if dev is not None and dev != torch.cuda.current_device():
+            with torch.cuda.device(dev):
+                return timed(*args)
+        return timed(*args)
     return call
 
 
@@ -158,7 +165,10 @@ def ptr(t):
 
 
 def stream(device=None):
-    return torch.cuda.current_stream(device).cuda_stream
+    """Raw handle of torch's current stream on ``device``; remembers the device for the launch guard."""
+    s = torch.cuda.current_stream(device)
+    _TLS.dev = s.device.index
+    return s.cuda_stream
 
 
 def require_cuda(*tensors):

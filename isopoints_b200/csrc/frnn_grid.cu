@@ -118,7 +118,10 @@ __global__ void grid_params_kernel(const unsigned* __restrict__ bbox, const floa
   for (int d = 0; d < D; ++d) { p[d] = gmin[d]; p[D + 1 + d] = res[d]; }
   p[D] = delta;
   p[2 * D + 1] = total;
-  if (g_max) atomicMax(g_max, (int)total);
+  // `total` is a float product of up to three resolutions: with a collapsed axis (min extent 0) the reference's
+  // cell-size floor (:62-63) does not engage and a tiny radius asks for more cells than an int holds.  Report
+  // INT_MAX instead of an overflowed cast: the host wrapper raises (the reference would fail in its allocation).
+  if (g_max) atomicMax(g_max, (total < 1073741824.f) ? (int)total : 0x7fffffff);
 }
 
 // ----------------------------------------------------------------------------------------

@@ -122,13 +122,6 @@ __global__ void siren_pack_kernel(const float* __restrict__ w0, const float* __r
     size_t off = (size_t)k8 * B_LBO + (size_t)(n >> 3) * SBO + (size_t)(n & 7) * 16;
     *reinterpret_cast<uint4*>(stage + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
     *reinterpret_cast<uint4*>(stage + STAGE_PART + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
-    // the same chunk in the per-rank split image of the CTA-pair kernel
-    const int r = n >> 7, nl = n & 127;
-    unsigned char* st2 = blob + off_images_split(L) + (size_t)(l * 2 + o) * image_bytes() +
-                         (size_t)(kb * 2 + r) * (STAGE_BYTES / 2);
-    size_t off2 = (size_t)k8 * (B_LBO / 2) + (size_t)(nl >> 3) * SBO + (size_t)(nl & 7) * 16;
-    *reinterpret_cast<uint4*>(st2 + off2) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-    *reinterpret_cast<uint4*>(st2 + STAGE_PART / 2 + off2) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
   }
 }
 
@@ -670,12 +663,6 @@ siren_sdf_grad_kernel(const float* __restrict__ x, int n_max, const int* __restr
 
 using namespace isob200;
 using namespace isob200::siren;
-namespace isob200 {
-namespace siren {
-int launch_siren_pair(const float* x, int n_max, const int* n_dev, const void* blob, int n_hidden, float* sdf,
-                      float* grad, void* scratch, const Newton& nw, cudaStream_t stream);   // siren_pair.cu
-}  // namespace siren
-}  // namespace isob200
 
 extern "C" {
 
@@ -710,16 +697,8 @@ int isob200_siren_pack(const float* w0, const float* b0, const float* w_hidden, 
   return ISOB200_OK;
 }
 
-// 0: one CTA per 128-row tile (siren.cu); 1: CTA pairs, cta_group::2, two tiles in flight (siren_pair.cu)
-static int g_siren_pair_mode = 0;
 static int g_siren_max_ctas = kNumSMs;   // tuning knob: persistent CTAs per launch (<= one per SM)
 static int g_siren_spill = 0;            // tuning knob: tape layers stored with the L2 evict-first policy
-int isob200_siren_set_pair_mode(int on) {
-  const int old = g_siren_pair_mode;
-  g_siren_pair_mode = on ? 1 : 0;
-  return old;
-}
-
 int isob200_siren_set_spill_layers(int n) {
   const int old = g_siren_spill;
   g_siren_spill = n < 0 ? 0 : n;
@@ -743,8 +722,6 @@ static int launch_siren(const float* x, int n_max, const int* n_dev, const void*
     set_error("%s: scratch too small", who);
     return ISOB200_ERR_WORKSPACE;
   }
-  if (g_siren_pair_mode && !dbg && nw.mode == 0)
-    return launch_siren_pair(x, n_max, n_dev, blob, n_hidden, sdf, grad, scratch, nw, (cudaStream_t)stream);
   {
     // opt-in to > 48 KB of dynamic shared memory: once per device
     static bool attr_done[64] = {};

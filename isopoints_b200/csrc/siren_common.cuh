@@ -1,5 +1,4 @@
-// Shared pieces of the fused SIREN kernels (siren.cu: one CTA per 128-row tile; siren_pair.cu: CTA pairs,
-// tcgen05 cta_group::2, two half-tiles in flight): packed-blob layout, PTX wrappers, packed fp32x2 math,
+// Shared pieces of the fused SIREN kernel (siren.cu): packed-blob layout, PTX wrappers, packed fp32x2 math,
 // fp16 hi/lo split, the fused-Newton argument block.
 #pragma once
 #include "common.cuh"
@@ -35,18 +34,14 @@ constexpr int MAX_LAYERS = 32;
 // [5120,6144)     float  w_last[256]
 // [6144, ..)      float  bias[L][256], pre-multiplied by omega
 // images          (1024-aligned) for l = 1..L, orientation o = 0 (forward: B[n][k] = W_l[n][k])
-//                 and o = 1 (backward: B[n][k] = W_l[k][n]): 8 stages of 32 KB; then the same images split
-//                 by CTA rank for the pair kernel (see off_images_split)
+//                 and o = 1 (backward: B[n][k] = W_l[k][n]): 8 stages of 32 KB
 constexpr size_t HDR_GL_SCALE = 64, HDR_GL_SCALE_INV = 65, HDR_B_LAST = 66, HDR_OMEGA0 = 67, HDR_OMEGA = 68;
 constexpr size_t OFF_W0B = 1024;
 constexpr size_t OFF_WLAST = OFF_W0B + H * 16;
 constexpr size_t OFF_BIAS = OFF_WLAST + H * 4;
 __host__ __device__ inline size_t off_images(int L) { return (OFF_BIAS + (size_t)L * H * 4 + 1023) / 1024 * 1024; }
 __host__ __device__ inline size_t image_bytes() { return (size_t)NKB * STAGE_BYTES; }  // per (layer, orientation)
-// split images for the CTA-pair kernel follow the full ones: per (layer, orientation) and k-block, the
-// 128 weight rows of CTA rank r as one 16 KB stage (hi 8 KB | lo 8 KB, K-chunk stride 2048)
-__host__ __device__ inline size_t off_images_split(int L) { return off_images(L) + (size_t)L * 2 * image_bytes(); }
-__host__ __device__ inline size_t blob_bytes(int L) { return off_images(L) + (size_t)L * 4 * image_bytes(); }
+__host__ __device__ inline size_t blob_bytes(int L) { return off_images(L) + (size_t)L * 2 * image_bytes(); }
 // scratch for the per-layer maxima (uint bit patterns of non-negative floats): L hidden + w_last
 constexpr size_t PACK_WS_BYTES = (MAX_LAYERS + 1) * sizeof(unsigned);
 
@@ -93,57 +88,6 @@ __device__ __forceinline__ void tma_bulk_g2s(uint32_t dst, const void* src, uint
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
                "l"(src), "r"(bytes), "r"(bar)
                : "memory");
-}
-__device__ __forceinline__ uint32_t cluster_ctarank() {
-  uint32_t r;
-  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-  return r;
-}
-__device__ __forceinline__ void cluster_sync_all() {
-  asm volatile("barrier.cluster.arrive.aligned;" ::: "memory");
-  asm volatile("barrier.cluster.wait.aligned;" ::: "memory");
-}
-// arrive on the barrier at the same shared-memory offset in CTA `cta` of the cluster (release at cluster scope)
-__device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar, uint32_t cta) {
-  asm volatile(
-      "{\n"
-      ".reg .b32 ra;\n"
-      "mapa.shared::cluster.u32 ra, %0, %1;\n"
-      "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n"
-      "}\n" ::"r"(bar),
-      "r"(cta)
-      : "memory");
-}
-// same, without the cluster-scope release (which waits for every store in flight, global ones included):
-// for hand-offs whose data was already ordered by a full fence (fence.proxy.async = MEMBAR) just before
-__device__ __forceinline__ void mbar_arrive_cluster_relaxed(uint32_t bar, uint32_t cta) {
-  asm volatile(
-      "{\n"
-      ".reg .b32 ra;\n"
-      "mapa.shared::cluster.u32 ra, %0, %1;\n"
-      "mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [ra];\n"
-      "}\n" ::"r"(bar),
-      "r"(cta)
-      : "memory");
-}
-// 2-CTA variants: the MMA spans the CTA pair (M = 128: 64 rows of A, 128 rows of B per CTA); the commit
-// arrives on the barrier at this offset in both CTAs
-__device__ __forceinline__ void tc_commit2(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::
-                   "r"(bar),
-               "h"((unsigned short)3)
-               : "memory");
-}
-__device__ __forceinline__ void tc_mma2_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
-                                            uint32_t accumulate) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "setp.ne.b32 p, %4, 0;\n"
-      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n"
-      "}\n" ::"r"(d_tmem),
-      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
-      : "memory");
 }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }

@@ -72,12 +72,37 @@ class ShardedUniformProjection(UniformProjection):
     """``UniformProjection`` whose input is THIS RANK's contiguous shard of one cloud (B = 1).
 
     ``project_points`` / ``_project_points`` / ``resample`` keep the reference signatures
-    (levelset_sampling.py:239-439); results are the rank's shard of what the single-GPU operator
-    returns for the concatenated cloud."""
+    (levelset_sampling.py:239-439); with ``skip_upsampling=True`` the results are the rank's shard of what the
+    single-GPU operator returns for the concatenated cloud.  The insert / upsample branches (:411-433) need
+    neighbourhoods and a sparsity ranking over the WHOLE cloud and are not sharded: ``project_points`` raises
+    unless ``skip_upsampling=True`` (run them on the gathered cloud with ``UniformProjection``).
+
+    Every rank must make the same sequence of collective calls, so the reference's data-dependent early exit
+    ("nothing converged", :396-399) is decided on the GLOBAL survivor count, and a rank whose shard is empty
+    still takes part in every exchange of ``resample``."""
 
     def __init__(self, *args, group=None, **kwargs):
         super().__init__(*args, **kwargs)
         self.group = group
+
+    def project_points(self, point_clouds, model, normals_init=None, skip_resampling=False,
+                       skip_upsampling=False, ref_pcl=None, **kwargs):
+        if not skip_upsampling:
+            raise NotImplementedError(
+                "ShardedUniformProjection.project_points: the insert / upsample branches are not point-sharded; "
+                "pass skip_upsampling=True and upsample the gathered cloud with UniformProjection")
+        return super().project_points(point_clouds, model, normals_init=normals_init,
+                                      skip_resampling=skip_resampling, skip_upsampling=True, ref_pcl=ref_pcl, **kwargs)
+
+    def _nothing_converged(self, counts) -> bool:
+        """Collective version of the early exit: all ranks leave, or none does (a rank that returned alone would
+        leave the others waiting in resample's all-gather)."""
+        if not (dist.is_available() and dist.is_initialized()):
+            return sum(counts) == 0
+        dev = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend(self.group) == "nccl" else "cpu"
+        total = torch.tensor([sum(counts)], dtype=torch.int64, device=dev)
+        dist.all_reduce(total, op=dist.ReduceOp.SUM, group=self.group)
+        return int(total.item()) == 0
 
     def resample(self, model, points_init, normals_init, num_points, sample_iters=None,
                  num_points_list=None, **forward_kwargs) -> ProjectionResult:
@@ -119,8 +144,9 @@ class ShardedUniformProjection(UniformProjection):
                 radius = (torch.sqrt(diag / float(ntot)) * self.knn_k).reshape(1)
                 len2 = torch.tensor([ntot], dtype=torch.int64, device=dev)
                 len1 = torch.tensor([nloc], dtype=torch.int64, device=dev)
-                _, idx, _, _ = frnn.frnn_grid_points(pts_loc[None], g_pts[None], len1, len2, K=self.knn_k + 1,
-                                                     r=radius, return_nn=False)
+                if nloc:      # (an empty shard has nothing to search for, but stays in the exchange above)
+                    _, idx, _, _ = frnn.frnn_grid_points(pts_loc[None], g_pts[None], len1, len2, K=self.knn_k + 1,
+                                                         r=radius, return_nn=False)
             moved = torch.empty_like(pts_loc)
             if nloc:
                 _ext.check(lib.isob200_resample_step(

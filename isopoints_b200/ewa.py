@@ -279,6 +279,10 @@ class SurfaceSplatting:
         """rasterizer.py:584-661 -> (PointFragments, filtered point clouds).  A ``point_clouds_filter`` receives
         the per-point visibility of the input clouds as its padded ``visibility`` filter (:642-650)."""
         rs = kwargs.get("raster_settings", self.raster_settings)
+        cameras = kwargs.get("cameras", self.cameras)
+        n_cameras = int(cameras.get_world_to_view_transform().get_matrix().shape[0])
+        if len(point_clouds) == 1 and n_cameras > 1:          # :597-598: one copy of the cloud per camera, so the
+            point_clouds = point_clouds.extend(n_cameras)     # visibility below has one row per VIEW
         filtered, mask_filtered = self.filter_renderable(point_clouds, point_clouds_filter, **kwargs)
         if filtered.isempty():
             return self._empty_fragments(len(filtered), device=filtered.device, **kwargs), filtered
@@ -295,8 +299,7 @@ class SurfaceSplatting:
         self._last = (fragments, info["scaler"])   # per-point scaler of these fragments, for the renderer's blend
         if point_clouds_filter is not None:
             # visibility of the points that survived the renderable filter, scattered back to the points that
-            # entered it, then padded with the INPUT clouds' first indices (:642-650; with more cameras than
-            # clouds this keeps the first view's rows, as the reference does)
+            # entered it, then padded with the first indices of the (extended) input clouds (:642-650): (B, max_P)
             vis = visibility_mask(idx.detach(), int(filtered.num_points_per_cloud().sum().item()), occ.detach())
             full = torch.zeros_like(mask_filtered)
             full[mask_filtered] = vis

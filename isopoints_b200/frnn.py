@@ -32,6 +32,7 @@ _GRID = namedtuple("GRID", "sorted_points2 pc2_grid_off sorted_points2_idxs grid
 # traversal of the query kernel: 0 = auto, 1 = exhaustive block scan, 2 = pruned best-first (same results)
 QUERY_MODE = 0
 
+_MAX_CELLS = 1 << 28     # 1 GiB of int32 offsets per cloud; int cell ids stay far from overflow
 _PARAMS_SIZE = {2: 6, 3: 8}
 _TOTAL_IDX = {2: 5, 3: 7}
 
@@ -51,6 +52,9 @@ def _grid_params(points2, lengths2, r, radius_cell_ratio):
         _ext.ptr(points2), _ext.ptr(lengths2), _ext.ptr(r), N, P2, D, float(radius_cell_ratio),
         _ext.ptr(params), _ext.ptr(gmax), _ext.ptr(ws), ws.numel(), _ext.stream(points2.device)))
     G = int(gmax.item())
+    if G > _MAX_CELLS:
+        raise RuntimeError("frnn: the grid for this radius needs more than %d cells (a search radius far below "
+                           "the point spacing of a cloud with a collapsed axis?); use a larger r" % _MAX_CELLS)
     return params, G
 
 

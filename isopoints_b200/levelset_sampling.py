@@ -375,6 +375,11 @@ class UniformProjection(LevelSetProjection):
         points, num_points = upsample(points, n_points, num_points=num_points, neighborhood_size=31)
         return points, num_points
 
+    def _nothing_converged(self, counts) -> bool:
+        """The early exit of :396-399 (``not valid_projection.any()``) from the survivor counts already on the
+        host.  A hook: the point-sharded subclass has to take this decision collectively."""
+        return sum(counts) == 0
+
     # ------------------------------------------------------------------------------------
     def project_points(self, point_clouds, model, normals_init: Optional[torch.Tensor] = None,
                        skip_resampling: bool = False, skip_upsampling: bool = False,
@@ -407,7 +412,7 @@ class UniformProjection(LevelSetProjection):
                 (points_projected, normals_projected, valid_projection), counts, num_points = \
                     _filter_projection_result_counted(
                         ProjectionResult(points_projected, normals_projected, valid_projection))
-                if sum(counts) == 0:   # nothing converged (:396-399)
+                if self._nothing_converged(counts):   # (:396-399)
                     return {'levelset_points': unfiltered[0], 'mask': unfiltered[1]}
                 points_projected, normals_projected, valid_projection = self.resample(
                     model, points_projected, normals_projected, num_points, sample_iters=sample_iters,

@@ -47,15 +47,21 @@ def knn_points(p1, p2, lengths1=None, lengths2=None, K: int = 1, return_nn: bool
     p2 = p1 if p2 is p1 else p2.contiguous()
     need = torch.clamp(lengths2, max=K)                                   # hits every live query must reach
     live = torch.arange(P1, device=dev)[None, :] < lengths1[:, None]
-    # initial radius: sphere holding ~2K points at the cloud's mean density (surface-like clouds are
-    # denser locally, so this is usually an over-estimate)
-    ext = (p2.amax(dim=1) - p2.amin(dim=1)).clamp_min(1e-12)
-    vol = ext.prod(dim=-1)
-    r = (vol * (2.0 * K) / lengths2.clamp_min(1).float() * (3.0 / (4.0 * math.pi))) ** (1.0 / 3.0)
-    diag = ext.norm(dim=-1)
+    # initial radius: ball holding ~2K points at the cloud's mean density, measured in the dimensions the cloud
+    # really spans (volume, area or length: an axis whose extent is < 1e-6 of the largest does not count -- a
+    # planar cloud would otherwise start at r ~ 0 and ask FRNN for billions of cells).  Surface-like clouds are
+    # denser locally, so this is usually an over-estimate.
+    ext = (p2.amax(dim=1) - p2.amin(dim=1))
+    diag = ext.norm(dim=-1).clamp_min(1e-12)
+    live_ax = ext > 1e-6 * ext.amax(dim=-1, keepdim=True).clamp_min(1e-30)
+    ndim = live_ax.sum(dim=-1).clamp_min(1).float()
+    measure = torch.where(live_ax, ext, torch.ones_like(ext)).prod(dim=-1)
+    unit_ball = torch.tensor([2.0, math.pi, 4.0 * math.pi / 3.0], device=dev)[(ndim - 1).long()]
+    r = (measure * (2.0 * K) / lengths2.clamp_min(1).float() / unit_ball) ** (1.0 / ndim)
     r = torch.minimum(r.float(), diag)
     dists = idx = None
-    for _ in range(12):
+    ok = None
+    for _ in range(14):
         dists, idx, _, _ = frnn.frnn_grid_points(p1, p2, lengths1, lengths2, K=K, r=r, return_nn=False)
         found = (idx >= 0).sum(-1)
         ok = (found >= need[:, None]) | ~live
@@ -65,6 +71,14 @@ def knn_points(p1, p2, lengths1=None, lengths2=None, K: int = 1, return_nn: bool
         if bool(done.all()):
             break
         r = torch.minimum(r * 2.0, diag * 1.0001)
+    if not bool(ok.all()):
+        # last resort: one search at the bounding-box diagonal finds every point; a row still short of
+        # min(K, lengths2) hits after that would be returned padded as if it had real neighbours
+        dists, idx, _, _ = frnn.frnn_grid_points(p1, p2, lengths1, lengths2, K=K, r=diag * 1.0001, return_nn=False)
+        found = (idx >= 0).sum(-1)
+        if not bool(((found >= need[:, None]) | ~live).all()):
+            raise RuntimeError("knn_points: some queries found fewer than min(K, lengths2) neighbours "
+                               "(non-finite coordinates?)")
     pad = idx < 0
     idx = idx.masked_fill(pad, 0)
     dists = dists.masked_fill(pad, 0.0)
@@ -209,11 +223,14 @@ def upsample(pcl, n_points: Union[int, torch.Tensor], num_points=None, neighborh
 
 
 def resample_uniformly(pointclouds, neighborhood_size: int = 8, knn=None, normals=None, shrink_ratio: float = 0.5,
-                       repulsion_mu: float = 1.0):
+                       repulsion_mu: float = 1.0, noise=None):
     """WLOP consolidation to ``shrink_ratio`` of the points, then ``upsample`` back (:126-166).  The
-    reference also builds a K-NN and normals it never uses (:141-158); those dead steps are skipped."""
+    reference also builds a K-NN and normals it never uses (:141-158); those dead steps are skipped.
+    Returns a ``Pointclouds`` for a ``Pointclouds`` input (:164-165) and ``(padded points, num_points)`` for a
+    tensor input -- the convention the reference documents (:131-132, :166); its own tensor path never gets there
+    (``wlop`` calls ``pointclouds.get_bounding_boxes()``, :44).  ``noise``: see ``wlop``."""
     points_init, num_points = convert_pointclouds_to_tensor(pointclouds)
-    wl = wlop(pointclouds, ratio=shrink_ratio, repulsion_mu=repulsion_mu)
+    wl = wlop(pointclouds, ratio=shrink_ratio, repulsion_mu=repulsion_mu, noise=noise)
     if is_pointclouds(pointclouds):
         return upsample(wl, num_points)
     x, nx = (wl, torch.ceil(num_points.double() * shrink_ratio).long()) if torch.is_tensor(wl) else wl

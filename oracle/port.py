@@ -602,8 +602,10 @@ def _gather0(x, idx):
     return x[idx.clamp_min(0)] * (idx >= 0)[..., None]
 
 
-def wlop(P: torch.Tensor, noise: torch.Tensor, neighborhood_size=16, iters=3, repulsion_mu=0.5, frnn_fn=None):
-    """wlop(ratio=1.0) for one cloud (P,3) (point_processing.py:35-122): X0 = P + noise * 0.1 h,
+def wlop(P: torch.Tensor, noise: torch.Tensor, neighborhood_size=16, iters=3, repulsion_mu=0.5, frnn_fn=None,
+         X0: torch.Tensor = None):
+    """wlop for one cloud (P,3) (point_processing.py:35-122); ``X0`` = the farthest-point subsample for
+    ratio < 1 (:51-52), P itself for ratio = 1.0: X0 = X0 + noise * 0.1 h,
     h = 4 sqrt(diag/n), theta(r2) = exp(-16 r2 / h^2), search radius min(h K, 0.2);
     X <- sum alpha p / sum alpha + mu sum beta delta / sum beta with
     alpha = theta(|eps|^2) / |eps| / density_P[j],  beta = density_X theta(|delta|^2) / |delta|."""
@@ -615,7 +617,7 @@ def wlop(P: torch.Tensor, noise: torch.Tensor, neighborhood_size=16, iters=3, re
     s_inv = 16 / h / h
     fn = frnn_fn or (lambda a, b, K, r: torch.as_tensor(frnn_bruteforce(a[None].numpy(), b[None].numpy(), K=K, r=r)[0][0]))
     theta = lambda r2: torch.exp(-r2 * s_inv)
-    X = P + noise * h * 0.1
+    X = (P if X0 is None else X0) + noise * h * 0.1
     idx_pp = fn(P, P, K + 1, r)[:, 1:]
     dpp = (P[:, None] - _gather0(P, idx_pp)).norm(dim=-1)
     th = theta(dpp ** 2) * (idx_pp >= 0)
@@ -663,6 +665,59 @@ def upsample(points: torch.Tensor, n_points: int, neighborhood_size=16):
         if max_P == 0:
             break
     return pts
+
+
+def fps(points: torch.Tensor, m: int, start: int = 0):
+    """Farthest point sampling of one cloud (P,3) to m indices in selection order -- what
+    ``torch_cluster.fps`` computes for ``farthest_sampling`` (point_processing.py:473-499) [third party,
+    restated from its documentation; upstream draws the start point at random, here it is ``start``]:
+    repeatedly the point with the largest squared distance to the selected set (first arg-max)."""
+    sel = [start]
+    md = ((points - points[start]) ** 2).sum(-1)
+    for _ in range(m - 1):
+        j = int(torch.argmax(md))
+        sel.append(j)
+        md = torch.minimum(md, ((points - points[j]) ** 2).sum(-1))
+    return torch.tensor(sel, dtype=torch.int64)
+
+
+def resample_uniformly(P: torch.Tensor, noise: torch.Tensor, shrink_ratio=0.5, repulsion_mu=1.0, frnn_fn=None):
+    """resample_uniformly for one cloud (point_processing.py:126-166): wlop(ratio=shrink_ratio, repulsion_mu)
+    (:160; defaults neighborhood_size=16, iters=3) then upsample back to the input count (:161).  The K-NN and
+    normals of :141-158 are computed and never used."""
+    n = P.shape[0]
+    sub = fps(P, int(math.ceil(n * shrink_ratio)))
+    X = wlop(P, noise, repulsion_mu=repulsion_mu, frnn_fn=frnn_fn, X0=P[sub])
+    return upsample(X, n)
+
+
+def insert(ref_points: torch.Tensor, metrics: torch.Tensor, points: torch.Tensor, frnn_fn=None):
+    """UniformProjection.insert for one cloud (levelset_sampling.py:172-233): children 2f/3 + m/3 of every
+    "father" f = a point within 2 * avg_spacing of a high-saliency reference point (and not exactly on it),
+    m = its 8 FRNN neighbours (zeros where it has fewer, like frnn_gather).  ``metrics`` (R,1) is the
+    reference cloud's feature; salient = above min(2 median, max / 2) (:189), replaced by the top
+    max(min(50, R // 20), 1) when that set is empty or larger than min(50, R // 20) (:195-197).
+    Returns (child (C,3), n_children)."""
+    P = points.shape[0]
+    diag = float((points.max(0).values - points.min(0).values).norm())
+    avg_spacing = math.sqrt(diag / ref_points.shape[0])
+    patch = 8
+    r = min(avg_spacing * patch, 0.2)
+    fn = frnn_fn or (lambda a, b, K, r: frnn_bruteforce(a[None].numpy(), b[None].numpy(), K=K, r=r))
+    idx, _ = fn(points, points, patch + 1, r)
+    idx = torch.as_tensor(idx[0])[:, 1:]
+    R = metrics.shape[0]
+    threshold = min(metrics.median() * 2, metrics.max() * 0.5)
+    ref = ref_points[(metrics > threshold).squeeze(-1)]
+    cap = min(50, int(R / 20))
+    if ref.shape[0] == 0 or ref.shape[0] > cap:
+        ref = ref_points[metrics.sort(dim=0).indices[-max(cap, 1):, 0]]
+    _, d = fn(points, ref, 1, r * 4)
+    d = torch.as_tensor(d[0]).reshape(P)
+    father = (d < 4 * avg_spacing ** 2) & (d > 0)
+    mother = _gather0(points, idx[:, -patch:])[father]
+    child = 2 * points[father].unsqueeze(-2) / 3 + mother / 3
+    return child.reshape(-1, 3), int(father.sum()) * patch
 
 
 # =========================================================================================

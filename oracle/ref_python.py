@@ -22,7 +22,23 @@ import types
 
 import torch
 
-REF = os.environ.get("ISO_REFERENCE", "/root/reference")
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _find_ref():
+    """The reference tree: $ISO_REFERENCE, /root/reference (authoring container), or the git-ignored staged copy of
+    its Python files under baseline/_ref/ (oracle/stage_ref.py; it travels to the GPU box with the snapshot)."""
+    for c in (os.environ.get("ISO_REFERENCE"), "/root/reference", os.path.join(ROOT, "baseline", "_ref")):
+        if c and os.path.isdir(os.path.join(c, "DSS")):
+            return c
+    return "/root/reference"
+
+
+REF = _find_ref()
+
+
+def available():
+    return os.path.isdir(os.path.join(REF, "DSS"))
 
 STUB_PACKAGES = (
     "pytorch3d", "trimesh", "matplotlib", "skimage", "torch_batch_svd", "torch_cluster", "frnn",
@@ -231,21 +247,52 @@ def load(frnn_module=None):
     if frnn_module is not None:
         mods.levelset_sampling.frnn = frnn_module
         mods.point_processing.frnn = frnn_module
+    elif not isinstance(sys.modules.get("frnn"), _StubModule) and "frnn" in sys.modules:
+        mods.levelset_sampling.frnn = sys.modules["frnn"]      # use_natives() after an earlier load()
+        mods.point_processing.frnn = sys.modules["frnn"]
     return mods
 
 
+def use_natives(which):
+    """Choose the native code under the reference's Python BEFORE load():
+      "reference": the reference's own `frnn` Python package (external/FRNN/frnn/{__init__,frnn}.py) on the
+                   reference's own compiled extensions from oracle/_ref (frnn._C, prefix_sum, DSS._C) -- the
+                   reference-GPU arm;
+      "isob200":   isopoints_b200.install() -- the same three import names backed by libisob200.so (the drop-in)."""
+    if which == "isob200":
+        from isopoints_b200 import install
+        return install.install()
+    assert which == "reference", which
+    from oracle import ref_native
+    if not ref_native.available():
+        raise RuntimeError("oracle/_ref natives not built")
+    sys.modules["frnn._C"] = ref_native.frnn_C()
+    sys.modules["prefix_sum"] = ref_native.prefix_sum()
+    sys.modules["DSS._C"] = ref_native.dss_C()
+    pkg = os.path.join(REF, "external", "FRNN", "frnn", "__init__.py")
+    spec = importlib.util.spec_from_file_location("frnn", pkg, submodule_search_locations=[os.path.dirname(pkg)])
+    mod = importlib.util.module_from_spec(spec)
+    mod._C = sys.modules["frnn._C"]
+    sys.modules["frnn"] = mod
+    spec.loader.exec_module(mod)
+    return {"frnn": mod, "prefix_sum": sys.modules["prefix_sum"], "DSS._C": sys.modules["DSS._C"]}
+
+
 def load_rasterizer():
-    """Import the reference's DSS.core.rasterizer (for SurfaceSplatting._get_per_point_info and the
-    renderable filters).  DSS._C (the compiled extension) is stubbed: the per-point parameter code never
-    calls it.  pytorch3d.ops.knn_points / eyes get pure-torch stand-ins (documented semantics:
-    K smallest squared distances ascending; a batch of identity matrices)."""
+    """Import the reference's DSS.core.rasterizer (for SurfaceSplatting._get_per_point_info, the renderable
+    filters and -- when use_natives() registered a real DSS._C -- rasterize_elliptical_points /
+    EllipticalRasterizer).  Without natives DSS._C is stubbed: the per-point parameter code never calls it.
+    pytorch3d.ops.knn_points / eyes get pure-torch stand-ins (documented semantics: K smallest squared distances
+    ascending; a batch of identity matrices), kMaxPointsPerBin its upstream value 22."""
     load()
     if "rasterizer" not in _LOADED:
         import DSS
-        stub = _StubModule("DSS._C")
-        sys.modules["DSS._C"] = stub
-        DSS._C = stub
+        if isinstance(sys.modules.get("DSS._C"), _StubModule) or "DSS._C" not in sys.modules:
+            sys.modules["DSS._C"] = _StubModule("DSS._C")
+        DSS._C = sys.modules["DSS._C"]
         import pytorch3d.ops as o3d
+        import pytorch3d.renderer.points.rasterize_points as rp3d
+        rp3d.kMaxPointsPerBin = 22
 
         def knn_points(p1, p2, lengths1=None, lengths2=None, K=1, **kw):
             from collections import namedtuple

@@ -28,6 +28,7 @@
   and the `torch.rand_like` draw recorded; plus `intersection_with_unit_cube` and `get_tensor_values` alone.
 The fixtures are small (< 1 MB total) and committed; the GPU box has no /root/reference.
 """
+import math
 import os
 import sys
 import types
@@ -337,8 +338,153 @@ def offsurface_golden(ref):
     print("offsurface: off %s, in %s of caps [150, 400], cube hits %.3f" % (n_off.tolist(), n_ins.tolist(), float(cm.float().mean())))
 
 
+def pinned_golden():
+    """`--only pinned`: the C2 SDF as SURVEY 8d pins it -- the reference's own ``DSS.models.common.Siren(dim=3,
+    c_dim=0, hidden_size=256, n_layers=7, first_omega_0=30, hidden_omega_0=30, outermost_linear=True)`` built right
+    after ``torch.manual_seed(0)`` -- a fingerprint of its state_dict (so that tests/helpers.pinned_siren can be
+    checked where /root/reference is absent), its value / autograd gradient on 512 points in float64 from the
+    reference class itself, and the reference's ``UniformProjection.project_points(skip_upsampling=True)`` on the
+    first 4096 points of the C2 cloud (CPU fp32 autograd SDF, frnn = the reference's frnn_bf_cpu)."""
+    import importlib
+    ref = ref_python.load(frnn_module=_CpuFrnn)
+    common = importlib.import_module("DSS.models.common")
+    torch.manual_seed(0)
+    net = common.Siren(dim=3, c_dim=0, hidden_size=256, n_layers=7, first_omega_0=30, hidden_omega_0=30,
+                       outermost_linear=True)
+    sd = net.state_dict()
+    keys = sorted(sd.keys())
+    fp = np.stack([np.array([float(sd[k].double().sum()), float(sd[k].double().abs().sum()),
+                             float(sd[k].reshape(-1)[0]), float(sd[k].reshape(-1)[-1])]) for k in keys])
+    g = torch.Generator().manual_seed(1000)              # bench.py's C2 cloud of rank 0
+    x = ((torch.rand(1, 200000, 3, generator=g) - 0.5) * 2)[:, :4096].contiguous()
+    net64 = common.Siren(dim=3, c_dim=0, hidden_size=256, n_layers=7, first_omega_0=30, hidden_omega_0=30,
+                         outermost_linear=True).double()
+    net64.load_state_dict({k: v.double() for k, v in sd.items()})
+    xe = x[0, :512].double().requires_grad_(True)
+    s64 = net64(xe).sdf
+    g64, = torch.autograd.grad(s64, xe, torch.ones_like(s64))
+    proj = ref.levelset_sampling.UniformProjection(proj_max_iters=10, proj_tolerance=5e-5, knn_k=8, sample_iters=1)
+    p0 = proj._project_points(net, x.clone(), torch.tensor([4096]))
+    out = proj.project_points(x.clone(), net, skip_upsampling=True)
+    np.savez_compressed(os.path.join(HERE, "pinned_siren.npz"), keys=np.array(keys), fingerprint=fp, x=x.numpy(),
+                        sdf64=s64.detach().numpy().reshape(-1), grad64=g64.numpy(),
+                        proj_points=p0.points.numpy(), proj_normals=p0.normals.numpy(), proj_mask=p0.mask.numpy(),
+                        points=out["levelset_points"].numpy(), normals=out["levelset_normals"].numpy(),
+                        mask=out["mask"].numpy())
+    print("pinned: projection converged", float(p0.mask.float().mean()), "after resample", tuple(out["mask"].shape),
+          float(out["mask"].float().mean()))
+
+
+def insert_golden():
+    """`--only insert`: the reference's ``UniformProjection.insert`` (levelset_sampling.py:172-233) and the
+    ``ref_pcl`` branch of ``project_points`` (:411-424) on CPU tensors: a sphere SDF, a reference cloud whose
+    per-point feature (the saliency metric) peaks around two spots."""
+    from isopoints_b200.structures import Pointclouds
+    ref = ref_python.load(frnn_module=_CpuFrnn)
+    LS = ref.levelset_sampling
+    torch.manual_seed(11)
+    x = (torch.rand(1, 3000, 3) - 0.5) * 1.5
+    rp = torch.nn.functional.normalize(torch.randn(2500, 3), dim=-1)
+    spots = torch.nn.functional.normalize(torch.tensor([[1.0, 0.2, 0.1], [-0.3, 0.9, -0.2]]), dim=-1)
+    metric = torch.exp(-((rp[:, None, :] - spots[None]) ** 2).sum(-1) / 0.02).sum(-1, keepdim=True) \
+        + 0.01 * torch.rand(2500, 1)
+    ref_pcl = Pointclouds([rp], features=[metric])
+    proj = LS.UniformProjection(proj_max_iters=10, proj_tolerance=5e-5, knn_k=8, sample_iters=1)
+    out = proj.project_points(x.clone(), SphereSDF(), ref_pcl=ref_pcl)
+    # insert() alone on the projected + resampled cloud (what project_points hands it)
+    base = proj.project_points(x.clone(), SphereSDF(), skip_upsampling=True)
+    bp = base["levelset_points"][:, base["mask"][0]]
+    num = torch.tensor([bp.shape[1]])
+    pts_all, num_all, child, child_num = proj.insert(ref_pcl, bp.clone(), num)
+    # second case: threshold branch (few salient points -> the `metrics > threshold` selection is kept)
+    metric2 = 0.01 * torch.rand(2500, 1)
+    metric2[:30] = 1.0
+    ref_pcl2 = Pointclouds([rp], features=[metric2])
+    _, _, child2, child_num2 = proj.insert(ref_pcl2, bp.clone(), num)
+    np.savez_compressed(os.path.join(HERE, "insert.npz"), x=x.numpy(), ref_points=rp.numpy(), metric=metric.numpy(),
+                        metric2=metric2.numpy(), points=out["levelset_points"].numpy(),
+                        normals=out["levelset_normals"].numpy(), mask=out["mask"].numpy(), base=bp.numpy(),
+                        child=child.numpy(), child_num=child_num.numpy(), child2=child2.numpy(),
+                        child_num2=child_num2.numpy())
+    print("insert:", tuple(out["levelset_points"].shape), "children", int(child_num[0]), int(child_num2[0]),
+          "valid", float(out["mask"].float().mean()))
+
+
+def _fps_sequential(x, batch, ratio, random_start=False):
+    """torch_cluster.fps stand-in [third party, restated]: per cloud, start at its first point, repeatedly take
+    the point farthest (squared distance, first arg-max) from the selected set; ceil(ratio * n) indices per
+    cloud, in selection order, concatenated."""
+    out = []
+    for b in range(int(batch.max()) + 1):
+        ids = (batch == b).nonzero().reshape(-1)
+        pts = x[ids]
+        m = int(math.ceil(ratio * len(ids)))
+        sel = [0]
+        md = ((pts - pts[0]) ** 2).sum(-1)
+        for _ in range(m - 1):
+            j = int(torch.argmax(md))
+            sel.append(j)
+            md = torch.minimum(md, ((pts - pts[j]) ** 2).sum(-1))
+        out.append(ids[torch.tensor(sel)])
+    return torch.cat(out)
+
+
+def resample_uniformly_golden():
+    """`--only resample_uniformly`: the reference's ``resample_uniformly`` (point_processing.py:126-166) on a
+    ``Pointclouds`` (the only input type its ``wlop`` accepts, :44): WLOP to half the points (farthest sampling
+    through the stand-in above, the jitter draw recorded) then ``upsample`` back."""
+    from isopoints_b200.structures import Pointclouds
+    ref = ref_python.load(frnn_module=_CpuFrnn)
+    import pytorch3d.ops.knn as o3dk   # stubs installed by ref_python.load
+    import torch_cluster
+    PP = ref.point_processing
+    torch_cluster.fps = _fps_sequential
+    import frnn as frnn_stub            # resample_uniformly does a function-local `import frnn` (:134)
+    frnn_stub.frnn_grid_points = _CpuFrnn.frnn_grid_points
+    frnn_stub.frnn_gather = _CpuFrnn.frnn_gather
+
+    def _knn_points_cpu(p1, p2, lengths1=None, lengths2=None, K=1, return_nn=False, return_sorted=True, **kw):
+        outs_d, outs_i = [], []
+        for n in range(p1.shape[0]):
+            l1 = p1.shape[1] if lengths1 is None else int(lengths1[n])
+            l2 = p2.shape[1] if lengths2 is None else int(lengths2[n])
+            d = torch.cdist(p1[n, :l1].double(), p2[n, :l2].double()) ** 2
+            v, i = torch.topk(d, min(K, l2), dim=1, largest=False)
+            dd = torch.zeros(p1.shape[1], K); ii = torch.zeros(p1.shape[1], K, dtype=torch.long)
+            dd[:l1, :v.shape[1]] = v.float(); ii[:l1, :i.shape[1]] = i
+            outs_d.append(dd); outs_i.append(ii)
+        dists, idx = torch.stack(outs_d), torch.stack(outs_i)
+        nn = torch.stack([p2[n][idx[n]] for n in range(p1.shape[0])]) if return_nn else None
+        return o3dk._KNN(dists=dists, idx=idx, knn=nn)
+
+    PP.knn_points = _knn_points_cpu
+    PP.Pointclouds = Pointclouds
+    PP.estimate_pointcloud_normals = lambda p, **kw: torch.zeros_like(p)     # computed and never used (:153-158)
+    torch.manual_seed(12)
+    sph = torch.nn.functional.normalize(torch.randn(1, 1200, 3), dim=-1) * (1 + 0.01 * torch.randn(1, 1200, 1))
+    noise = torch.randn(600, 3)
+    real_randn_like = torch.randn_like
+    PP.torch.randn_like = lambda x: noise.clone()
+    try:
+        out = PP.resample_uniformly(Pointclouds(sph.clone()), shrink_ratio=0.5, repulsion_mu=1.0)
+    finally:
+        PP.torch.randn_like = real_randn_like
+    fps_idx = _fps_sequential(sph[0], torch.zeros(1200, dtype=torch.long), 0.5)
+    np.savez_compressed(os.path.join(HERE, "resample_uniformly.npz"), P=sph.numpy(), noise=noise.numpy(),
+                        fps_idx=fps_idx.numpy(), points=out.points_padded().numpy(),
+                        num=out.num_points_per_cloud().numpy())
+    print("resample_uniformly:", tuple(out.points_padded().shape), int(out.num_points_per_cloud()[0]))
+
+
 def main():
     torch.set_num_threads(4)
+    only = sys.argv[sys.argv.index("--only") + 1] if "--only" in sys.argv else None
+    if only == "pinned":
+        return pinned_golden()
+    if only == "insert":
+        return insert_golden()
+    if only == "resample_uniformly":
+        return resample_uniformly_golden()
     if "--only" in sys.argv and sys.argv[sys.argv.index("--only") + 1] == "ewa":
         ref_python.load(frnn_module=_CpuFrnn)
         return ewa_golden()
@@ -461,6 +607,9 @@ def main():
     trace_golden(LS)
     rays_golden(LS)
     offsurface_golden(ref)
+    pinned_golden()
+    insert_golden()
+    resample_uniformly_golden()
 
 
 if __name__ == "__main__":

@@ -150,6 +150,44 @@ class Siren(nn.Module):
     def forward(self, coords, c=None, **kwargs):
         return types.SimpleNamespace(sdf=self.net(coords))
 
+    def as_opaque(self):
+        """The same weights behind an opaque module (``SirenSDF`` structure: not recognised by the fused path)."""
+        n_layers = len(self.net) - 2
+        o = SirenSDF(self.net[0].linear.out_features, n_layers, float(self.net[0].omega_0), seed=0)
+        with torch.no_grad():
+            for dst, src in zip(o.lin, [m.linear for m in list(self.net)[:-1]] + [self.net[-1]]):
+                dst.weight.copy_(src.weight)
+                dst.bias.copy_(src.bias)
+        return o
+
+
+def pinned_siren(seed=0, hidden_size=256, n_layers=7, omega=30.0):
+    """The C2 SDF exactly as SURVEY 8d pins it: ``DSS.models.common.Siren(dim=3, c_dim=0, hidden_size=256,
+    n_layers=7, first_omega_0=30, hidden_omega_0=30, outermost_linear=True)`` constructed right after
+    ``torch.manual_seed(seed)`` -- i.e. every layer is an ``nn.Linear`` with PyTorch's default init (which draws
+    from the global generator: kaiming-uniform weight, then uniform bias) whose weight is then re-drawn with
+    ``uniform_`` (first layer +-1/dim, others +-sqrt(6/dim)/omega; DSS/models/common.py:72-127), in construction
+    order.  Returned in the ``Siren`` structural twin above; ``tests/test_oracle_golden.py`` asserts state_dict
+    equality with the reference's own class.  The global RNG state is left untouched (forked)."""
+    with torch.random.fork_rng(devices=[]):
+        m = Siren(hidden_size, n_layers, omega, seed=0)   # (nn.Linear's default init draws from the global generator)
+        torch.manual_seed(seed)
+        dims = [(3, hidden_size)] + [(hidden_size, hidden_size)] * n_layers
+        with torch.no_grad():
+            for i, (din, dout) in enumerate(dims):
+                lin = nn.Linear(din, dout)
+                if i == 0:
+                    lin.weight.uniform_(-1 / din, 1 / din)
+                else:
+                    lin.weight.uniform_(-np.sqrt(6 / din) / omega, np.sqrt(6 / din) / omega)
+                m.net[i].linear.weight.copy_(lin.weight)
+                m.net[i].linear.bias.copy_(lin.bias)
+            head = nn.Linear(hidden_size, 1)
+            head.weight.uniform_(-np.sqrt(6 / hidden_size) / omega, np.sqrt(6 / hidden_size) / omega)
+            m.net[-1].weight.copy_(head.weight)
+            m.net[-1].bias.copy_(head.bias)
+    return m
+
 
 def make_cameras(n_views, seed, dist=(2.2, 3.2), focal=2.0, znear=1.0, zfar=100.0):
     """Look-at perspective cameras around the origin in pytorch3d's row-vector convention

@@ -36,6 +36,17 @@ def _worker(rank, world, port, q):
         g = torch.full((7, 3), float(rank + 1))
         all_reduce_point_grads(g)
         ok = ok and bool((g == 3.0).all())
+        # the "nothing converged" early exit is a collective decision: a rank with an empty shard must not
+        # leave alone (the others would wait for it in resample's all-gather)
+        from isopoints_b200.dist import ShardedUniformProjection
+        sp = ShardedUniformProjection()
+        ok = ok and sp._nothing_converged([5] if rank == 0 else [0]) is False
+        ok = ok and sp._nothing_converged([0]) is True
+        try:
+            sp.project_points(torch.zeros(1, 4, 3), None)          # upsampling branch is not sharded
+            ok = False
+        except NotImplementedError:
+            pass
         q.put((rank, ok))
     finally:
         dist.destroy_process_group()

@@ -193,3 +193,31 @@ def test_subsample_randomly():
     src = {tuple(r) for r in pc.points_list()[0].cpu().numpy().round(6).tolist()}
     assert all(tuple(r) in src for r in out.points_list()[0].cpu().numpy().round(6).tolist())
     assert offsurface.subsample_randomly(pc, 1.0).num_points_per_cloud().tolist() == [100, 40]
+
+
+def test_single_cloud_is_extended_to_the_camera_count_like_the_reference():
+    """SurfaceSplatting.forward extends a single cloud to len(cameras) at the top (rasterizer.py:597-598): the
+    visibility filter has one row per VIEW, get_visible_points returns one cloud per view, and the sampler accepts
+    the model's single-cloud `_points` with B = 2 cameras."""
+    from isopoints_b200 import siren
+    pc = _sphere_cloud(20000, seed=8)
+    assert len(pc) == 1
+    cams = PinholeCameras.look_at_origin(2, seed=9, device=DEV)
+    vis1, m1 = ewa.get_visible_points(pc, cams, return_mask=True)
+    vis2, m2 = ewa.get_visible_points(pc.extend(2), cams, return_mask=True)
+    assert m1.shape == m2.shape == (2, 20000) and torch.equal(m1, m2)
+    assert len(vis1) == 2 and vis1.num_points_per_cloud().tolist() == vis2.num_points_per_cloud().tolist()
+    assert not torch.equal(m1[0], m1[1])                    # two different views, not view 0 twice
+    # union over views (what get_visible_iso_points computes for the reference cloud, combined_modeling.py:405-409)
+    assert int(m1.any(dim=0).sum()) > int(m1[0].sum())
+    g = torch.Generator().manual_seed(0)
+    pixels = (torch.rand(2, 1500, 2, generator=g) * 1.6 - 0.8).to(DEV)
+    S = 64
+    yy, xx = torch.meshgrid(torch.linspace(-1, 1, S), torch.linspace(-1, 1, S), indexing="ij")
+    mask_img = ((xx ** 2 + yy ** 2) < 0.3 ** 2).float().expand(2, 1, S, S).contiguous().to(DEV)
+    decoder = Siren(256, 2, 30.0, seed=2).to(DEV)
+    a = offsurface.sample_offsurface_using_isopoints(_model(decoder, pc), pixels, mask_img, cams,
+                                                     n_points_per_ray=16, max_insurface_per_batch=[200, 200])
+    b = offsurface.sample_offsurface_using_isopoints(_model(decoder, pc.extend(2)), pixels, mask_img, cams,
+                                                     n_points_per_ray=16, max_insurface_per_batch=[200, 200])
+    assert a[3].tolist() == b[3].tolist() and int(a[3].min()) > 50

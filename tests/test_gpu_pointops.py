@@ -121,3 +121,81 @@ def test_edge_aware_projection_matches_reference_golden(golden):
     spacing = pp.knn_points(want[None], want[None], K=2).dists[0, :, 1].sqrt().median()
     assert float(d.max()) < 2.0 * float(spacing)
     print("edge-aware inserted points identical to the reference's: %.3f" % float((d < 1e-5).float().mean()))
+
+
+def test_insert_matches_reference_golden(golden):
+    """UniformProjection.insert (levelset_sampling.py:172-233) against the reference's own method: both
+    salient-point selections (top-k replacement, :195-197, and the plain threshold, :189-193)."""
+    g = golden("insert")
+    proj = UniformProjection(proj_max_iters=10, proj_tolerance=5e-5, knn_k=8, sample_iters=1)
+    base = torch.as_tensor(g["base"], device=DEV)
+    num = torch.tensor([base.shape[1]], device=DEV)
+    rp = torch.as_tensor(g["ref_points"], device=DEV)
+    for m, c, n in (("metric", "child", "child_num"), ("metric2", "child2", "child_num2")):
+        ref_pcl = Pointclouds([rp], features=[torch.as_tensor(g[m], device=DEV)])
+        pts_all, num_all, child, child_num = proj.insert(ref_pcl, base.clone(), num)
+        assert child_num.tolist() == g[n].tolist() and child.shape == g[c].shape
+        np.testing.assert_allclose(child.cpu().numpy(), g[c], rtol=1e-6, atol=1e-7)
+        assert pts_all.shape[1] == base.shape[1] + int(g[n][0]) and num_all.tolist() == [pts_all.shape[1]]
+        assert torch.equal(pts_all[:, :base.shape[1]], base) and torch.equal(pts_all[:, base.shape[1]:], child)
+
+
+def test_project_points_with_ref_pcl_matches_reference_golden(golden):
+    """The `ref_pcl` branch of project_points (levelset_sampling.py:411-424): project -> filter -> resample ->
+    insert around the salient reference points -> 10-iteration projection of the children -> concatenation."""
+    g = golden("insert")
+    proj = UniformProjection(proj_max_iters=10, proj_tolerance=5e-5, knn_k=8, sample_iters=1)
+    ref_pcl = Pointclouds([torch.as_tensor(g["ref_points"], device=DEV)],
+                          features=[torch.as_tensor(g["metric"], device=DEV)])
+    out = proj.project_points(torch.as_tensor(g["x"], device=DEV), SphereSDF().to(DEV), ref_pcl=ref_pcl)
+    assert out["levelset_points"].shape == g["points"].shape
+    assert np.array_equal(out["mask"].cpu().numpy(), g["mask"])
+    np.testing.assert_allclose(out["levelset_points"].cpu().numpy(), g["points"], rtol=1e-4, atol=1e-5)
+    np.testing.assert_allclose(out["levelset_normals"].cpu().numpy(), g["normals"], rtol=1e-4, atol=1e-5)
+    n_child = int(g["child_num"][0])
+    assert n_child > 0 and out["levelset_points"].shape[1] == g["base"].shape[1] + n_child
+
+
+def test_resample_uniformly_matches_reference_golden(golden):
+    """resample_uniformly (point_processing.py:126-166) against the reference's own function: farthest sampling
+    to half the points (start point 0, like the stand-in the golden was made with), WLOP with the recorded jitter,
+    upsample back to the input count."""
+    g = golden("resample_uniformly")
+    P = torch.as_tensor(g["P"], device=DEV)
+    sub = pp.farthest_sampling(Pointclouds(P), 0.5)
+    assert torch.equal(sub.points_padded()[0].cpu(), torch.as_tensor(g["P"][0][g["fps_idx"]]))
+    noise = torch.as_tensor(g["noise"], device=DEV)
+    out = pp.resample_uniformly(Pointclouds(P), shrink_ratio=0.5, repulsion_mu=1.0, noise=noise)
+    assert isinstance(out, Pointclouds) and out.num_points_per_cloud().tolist() == g["num"].tolist()
+    got, want = out.points_padded()[0], torch.as_tensor(g["points"][0], device=DEV)
+    # rows 600.. = the 600 consolidated points, row by row; rows ..600 = inserted mid-points (sparsity ranking:
+    # a near-tie may pick another mid-point) -> compared row by row where they agree, as a set otherwise
+    np.testing.assert_allclose(got[600:].cpu().numpy(), want[600:].cpu().numpy(), rtol=1e-4, atol=5e-6)
+    row_ok = torch.isclose(got[:600], want[:600], rtol=1e-4, atol=5e-6).all(-1)
+    d = pp.knn_points(got[None, :600], want[None, :600], K=1).dists[0, :, 0].sqrt()
+    print("resample_uniformly: inserted rows identical %.3f, set distance max %.2e" % (float(row_ok.float().mean()), float(d.max())))
+    assert float(row_ok.float().mean()) > 0.9 and float(d.max()) < 0.05
+    # tensor input: the documented (padded, num_points) convention (:131-132, :164-166; the reference's own
+    # tensor path raises inside wlop, :44 `pointclouds.get_bounding_boxes()`)
+    pts, num = pp.resample_uniformly(P, shrink_ratio=0.5)
+    assert torch.is_tensor(pts) and pts.shape == (1, 1200, 3) and num.tolist() == [1200]
+
+
+def test_knn_points_on_degenerate_clouds():
+    """Exactly planar / collinear clouds (a collapsed bounding-box axis): the initial radius comes from the
+    dimensions the cloud spans, the result is still the exact K-NN; an absurdly small FRNN radius on such a
+    cloud raises instead of overflowing the cell count."""
+    from isopoints_b200 import frnn
+    torch.manual_seed(3)
+    plane = torch.rand(1, 4000, 3)
+    plane[..., 2] = 0.25
+    line = torch.zeros(1, 500, 3)
+    line[..., 0] = torch.rand(1, 500)
+    for cloud, K in ((plane, 9), (line, 4)):
+        p = cloud.to(DEV)
+        out = pp.knn_points(p, p, K=K)
+        wd, wi = port.knn_bruteforce(cloud[0], cloud[0], K)
+        np.testing.assert_allclose(out.dists[0].cpu().numpy(), wd.numpy(), rtol=1e-5, atol=1e-10)
+        assert (out.idx[0].cpu() == wi).float().mean() > 0.999          # equal-distance pairs may swap
+    with pytest.raises(RuntimeError, match="cells"):
+        frnn.frnn_grid_points(plane.to(DEV), plane.to(DEV), K=4, r=1e-7)

@@ -220,53 +220,6 @@ def test_fused_newton_iteration_equals_sdf_grad_plus_project_step():
     assert torch.equal(xa[:ca], pa[aa[:ca].long()])               # next_points == points[act_out]
 
 
-def test_two_cta_mma_probe():
-    """tcgen05 cta_group::2 bring-up probe (csrc/umma2_probe.cu): a 128 x 256 x K fp16 GEMM on a CTA
-    pair; pins the accumulator layout the paired kernel design relies on (lane = row + 64 * (col >= 128),
-    TMEM column = col % 128, 64 rows per CTA)."""
-    from isopoints_b200 import _ext
-    lib = _ext.lib()
-    dev = torch.device(DEV)
-    for K in (16, 32, 64):
-        torch.manual_seed(K)
-        A, B = torch.randn(128, K, device=dev), torch.randn(256, K, device=dev)
-        dump = torch.full((2, 128, 128), float("nan"), device=dev)
-        _ext.check(lib.isob200_umma2_probe(_ext.ptr(A), _ext.ptr(B), K, _ext.ptr(dump), _ext.stream(dev)))
-        ref = A.half().float() @ B.half().float().t()
-        got = torch.empty_like(ref)
-        for r in range(2):
-            got[64 * r:64 * r + 64, :128] = dump[r, :64]
-            got[64 * r:64 * r + 64, 128:] = dump[r, 64:]
-        assert (got - ref).abs().max().item() < 1e-3 * ref.abs().max().item()
-
-
-def test_cta_pair_kernel_matches_single_cta_kernel():
-    """The experimental CTA-pair variant (csrc/siren_pair.cu: tcgen05 cta_group::2, two tiles in flight;
-    off by default) evaluates the same network: same accuracy against float64, and the
-    fused Newton iteration gives the same flags / positions up to the different summation order of the
-    per-row partials."""
-    from isopoints_b200 import _ext
-    lib = _ext.lib()
-    model = Siren(256, 7, 30.0, seed=0).to(DEV)
-    old = lib.isob200_siren_set_pair_mode(1)
-    try:
-        for n in (1, 64, 65, 300, 128 * 74 * 2 + 77):
-            g = torch.Generator().manual_seed(n)
-            x = ((torch.rand(n, 3, generator=g) - 0.5) * 2).to(DEV)
-            _check(model, x)
-        x = ((torch.rand(1, 9000, 3) - 0.5) * 2).to(DEV)
-        num = torch.tensor([9000], device=DEV)
-        a = UniformProjection(proj_max_iters=6)._project_points(model, x.clone(), num)
-        lib.isob200_siren_set_pair_mode(0)
-        b = UniformProjection(proj_max_iters=6)._project_points(model, x.clone(), num)
-    finally:
-        lib.isob200_siren_set_pair_mode(old)
-    assert (a.mask == b.mask).float().mean().item() > 0.995
-    both = a.mask & b.mask
-    d = (a.points - b.points).abs().max(dim=-1).values[both]
-    assert d.median().item() < 2e-6 and d.quantile(0.99).item() < 1e-4
-
-
 @pytest.mark.parametrize("layers,n", [(1, 300), (2, 128 * 149 + 5), (7, 50000)])
 def test_value_only_kernel_is_the_forward_half(layers, n):
     """isob200_siren_sdf (forward GEMMs only) returns the bits of isob200_siren_sdf_grad's value."""

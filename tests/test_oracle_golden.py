@@ -170,3 +170,84 @@ def test_sphere_tracing_matches_reference(golden):
         np.testing.assert_allclose(pts.numpy(), g[name + "_points"], rtol=1e-6, atol=1e-6)
         np.testing.assert_allclose(sdf.numpy(), g[name + "_eval"], rtol=1e-5, atol=1e-7)
         assert 0.2 < mask.float().mean() < 0.9, name      # rays that hit and rays that leave the sphere
+
+
+def test_pinned_siren_is_the_reference_network(golden):
+    """tests/helpers.pinned_siren == DSS.models.common.Siren(dim=3, c_dim=0, hidden_size=256, n_layers=7, ...)
+    built after torch.manual_seed(0): fingerprint recorded from the reference's own class, and --
+    where the reference tree is present -- state_dict equality with the class itself."""
+    import os
+    from tests.helpers import pinned_siren
+    g = golden("pinned_siren")
+    m = pinned_siren(0)
+    sd = m.state_dict()
+    keys = sorted(sd.keys())
+    assert keys == [str(k) for k in g["keys"]]
+    fp = np.stack([np.array([float(sd[k].double().sum()), float(sd[k].double().abs().sum()),
+                             float(sd[k].reshape(-1)[0]), float(sd[k].reshape(-1)[-1])]) for k in keys])
+    np.testing.assert_array_equal(fp, g["fingerprint"])
+    state = torch.random.get_rng_state()
+    pinned_siren(0)
+    assert torch.equal(state, torch.random.get_rng_state())        # the global generator is left alone
+    from oracle import ref_python
+    if os.path.isdir(ref_python.REF):
+        import importlib
+        ref_python.load()
+        common = importlib.import_module("DSS.models.common")
+        with torch.random.fork_rng(devices=[]):
+            torch.manual_seed(0)
+            ref = common.Siren(dim=3, c_dim=0, hidden_size=256, n_layers=7, first_omega_0=30, hidden_omega_0=30,
+                               outermost_linear=True)
+        rsd = ref.state_dict()
+        assert sorted(rsd.keys()) == keys and all(torch.equal(rsd[k], sd[k]) for k in keys)
+        from isopoints_b200 import siren
+        assert siren.match(ref, require_cuda=False) is not None    # the real class is what the fused path recognises
+    # value / gradient in float64 against the reference class's own
+    x = torch.as_tensor(g["x"])[0, :512].double().requires_grad_(True)
+    s = m.double()(x).sdf
+    gr, = torch.autograd.grad(s, x, torch.ones_like(s))
+    np.testing.assert_allclose(s.detach().numpy().reshape(-1), g["sdf64"], rtol=0, atol=1e-12)
+    np.testing.assert_allclose(gr.numpy(), g["grad64"], rtol=0, atol=1e-10)
+
+
+def test_oracle_projection_on_the_pinned_siren_matches_reference(golden):
+    """C2's SDF at 7 hidden layers: the oracle's Newton loop + resample against the reference's own
+    UniformProjection on the first 4096 points of the bench cloud (60 % of the rows converge)."""
+    from tests.helpers import pinned_siren
+    g = golden("pinned_siren")
+    net = pinned_siren(0).as_opaque()
+    x = torch.as_tensor(g["x"])[0]
+    p, n, v = port.project_points_packed(net, x, proj_max_iters=10, proj_tolerance=5e-5)
+    assert 0.5 < float(v.float().mean()) < 0.7
+    agree = v.numpy() == g["proj_mask"][0]
+    assert agree.mean() > 0.999          # same torch ops: identical up to the rare |sdf| ~ tol row
+    both = agree & v.numpy()
+    np.testing.assert_allclose(p.numpy()[both], g["proj_points"][0][both], rtol=1e-4, atol=1e-5)
+    if agree.all():
+        bf = lambda pts, K, r: port.frnn_bruteforce(pts[None], pts[None], K=K, r=r, inclusive=False)[0][0]
+        rp, rn, rv = port.resample(net, p[v], n[v], sample_iters=1, knn_k=8, frnn_fn=bf, proj_tolerance=5e-5)
+        m = rv.numpy() == g["mask"][0]
+        assert m.mean() > 0.995
+        np.testing.assert_allclose(rp.numpy()[m & rv.numpy()], g["points"][0][m & rv.numpy()], rtol=1e-4, atol=1e-5)
+
+
+def test_insert_oracle_matches_reference(golden):
+    g = golden("insert")
+    bf = lambda a, b, K, r: port.frnn_bruteforce(a[None].numpy(), b[None].numpy(), K=K, r=r, inclusive=False)
+    for m, c, n in (("metric", "child", "child_num"), ("metric2", "child2", "child_num2")):
+        child, cn = port.insert(torch.as_tensor(g["ref_points"]), torch.as_tensor(g[m]),
+                                torch.as_tensor(g["base"][0]), frnn_fn=bf)
+        assert cn == int(g[n][0]) and cn > 0
+        np.testing.assert_allclose(child.numpy(), g[c][0], rtol=1e-6, atol=1e-7)
+    assert int(g["child_num"][0]) != int(g["child_num2"][0])       # the two selection branches (:189 vs :195-197)
+
+
+def test_resample_uniformly_oracle_matches_reference(golden):
+    g = golden("resample_uniformly")
+    P = torch.as_tensor(g["P"][0])
+    assert np.array_equal(port.fps(P, 600).numpy(), g["fps_idx"])
+    bf = lambda a, b, K, r: torch.as_tensor(
+        port.frnn_bruteforce(a[None].numpy(), b[None].numpy(), K=K, r=r, inclusive=False)[0][0])
+    out = port.resample_uniformly(P, torch.as_tensor(g["noise"]), frnn_fn=bf)
+    assert out.shape == (1200, 3) and int(g["num"][0]) == 1200
+    np.testing.assert_allclose(out.numpy(), g["points"][0], rtol=1e-5, atol=1e-6)
