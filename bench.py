@@ -3,10 +3,12 @@
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
 
-Workload (BASELINE.json configs[1], "C2"): 200 000 points per GPU, (rand-0.5)*2, random-init
-8-layer x 256 SIREN SDF in the reference decoder's structure (--sdf siren, default: evaluated by the
-package's fused tcgen05 kernel; --sdf opaque: the same weights behind an opaque nn.Module, i.e. the
-autograd callback), UniformProjection(proj_max_iters=10, tol=5e-5, knn_k=8, sample_iters=1)
+Workload (BASELINE.json configs[1], "C2"): 200 000 points per GPU, (rand-0.5)*2, and the SDF SURVEY 8d
+pins: the reference's own Siren(dim=3, c_dim=0, hidden_size=256, n_layers=7, omega 30, linear head) as
+constructed right after torch.manual_seed(0) (tests/helpers.pinned_siren; state_dict equality with the
+reference class is a CPU test) -- 60 % of the points converge on this random-init field, 7.5 SDF
+evaluations per input point (--sdf siren, default: evaluated by the package's fused tcgen05 kernel;
+--sdf opaque: the same weights behind an opaque nn.Module, i.e. the autograd callback), UniformProjection(proj_max_iters=10, tol=5e-5, knn_k=8, sample_iters=1)
 .project_points(x, sdf, skip_upsampling=True)  = project -> filter -> FRNN(K=9) -> resample ->
 3-iteration re-projection.  A "step" is one such pass over one synthetic cloud.
   value : input iso-points / second, whole job, inputs resident in HBM, CUDA-event timed;
@@ -22,6 +24,10 @@ per-call CUDA events), so that event pools, NVML and the GPU clocks are in stead
 the line shows every timed step, `config.untimed_steps_before` the count.
 `--impl reference` times the CPU restatement of the reference path (oracle/port.py; the path is
 Python + third-party CUDA-only FRNN, so the reference itself cannot run on host cores) on rank 0.
+Outside every timed region the line also gains: `ref_cuda` (N = 1: the reference's own Python on its own CUDA
+extensions recompiled for sm_100a, oracle/ref_gpu.py in a subprocess, C2 / C3 / C4 -- the GPU-vs-GPU baseline),
+`dist_parity` (N > 1: the sharded result equals the single-GPU operator on the concatenated cloud) and `c5`
+(BASELINE configs[4], bench_c5.py: the fixed 2 M-point project + resample + splat 16 x 1024^2 problem at this N).
 """
 import argparse
 import json
@@ -51,8 +57,8 @@ def _ncu_traffic(capture):
     return _ncu(capture).get("dram_bytes_per_launch")
 
 C2_POINTS = 200_000
-C2_WORKLOAD = ("C2: 200000 pts/GPU, random-init SIREN 8x256 SDF, project(10 it)+resample(knn_k=8, 1 it)+"
-               "reproject(3 it)")
+C2_WORKLOAD = ("C2: 200000 pts/GPU, SURVEY-pinned SIREN 8x256 SDF (reference Siren(n_layers=7) under "
+               "torch.manual_seed(0)), project(10 it)+resample(knn_k=8, 1 it)+reproject(3 it)")
 L2_FLUSH_BYTES = 256 << 20
 
 
@@ -183,14 +189,15 @@ def _max_over_ranks(x, world, dev):
 
 
 def _make_c2(rank, dev, opaque=False):
-    """C2 cloud + SDF.  `Siren` is the structural twin of the reference decoder
-    (DSS/models/common.py:90-165), which the package evaluates with its fused tcgen05 kernel;
-    `SirenSDF` holds the same weights as an opaque nn.Module (autograd path)."""
-    from tests.helpers import Siren, SirenSDF
+    """C2 cloud + SDF.  `pinned_siren(0)` = the reference decoder (DSS/models/common.py:90-165) exactly as
+    SURVEY 8d pins it (torch.manual_seed(0), default nn.Linear init then uniform_ on the weights), in the
+    structure the package evaluates with its fused tcgen05 kernel; `.as_opaque()` holds the same weights
+    behind an opaque nn.Module (autograd path)."""
+    from tests.helpers import pinned_siren
     g = torch.Generator().manual_seed(1000 + rank)
     x = (torch.rand(1, C2_POINTS, 3, generator=g) - 0.5) * 2
-    net = (SirenSDF if opaque else Siren)(256, 7, 30.0, seed=0)
-    return x, net
+    net = pinned_siren(0)
+    return x, (net.as_opaque() if opaque else net)
 
 
 # ---------------------------------------------------------------------------------------------
@@ -296,8 +303,13 @@ def run_ours(args):
     own_ms = sum(v["ms_per_step"] for v in kern.values())
 
     # ---- e2e: host buffers, H2D + D2H inside the timed region ------------------------------
+    # (same per-call event instrumentation as the device-timed loop above, so the two numbers are comparable)
+    _ext.PROFILE = {}
+    _siren.RECORD = []
     for _ in range(2):
         step_e2e()
+        _ext.PROFILE = {}
+        _siren.RECORD = []
     _barrier(world)
     ev2 = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     t_e2e = 0.0
@@ -309,6 +321,12 @@ def run_ours(args):
         torch.cuda.synchronize()
         t_e2e += time.perf_counter() - t1
     e2e_ms = _max_over_ranks(t_e2e / args.steps * 1e3, world, dev)
+    _ext.PROFILE = None
+    _siren.RECORD = None
+    # ---- outside every timed region: the projection's own converged fraction (SURVEY 8d asks for it) --------
+    p0 = proj._project_points(net, x_dev, torch.tensor([C2_POINTS], device=dev), num_points_list=[C2_POINTS])
+    converged_projection = float(p0.mask.float().mean())
+    torch.cuda.synchronize()
     h2d = x_pin.numel() * 4
     d2h = sum(t.numel() * t.element_size() for t in res)
 
@@ -354,8 +372,13 @@ def run_ours(args):
                    "sdf_eval": ("fused tcgen05 kernel, fp32-equivalent via fp16 hi/lo split" if sd else
                                 "opaque nn.Module through autograd, fp32, TF32 off"),
                    "l2": "flushed between steps (256 MiB write)", "untimed_steps_before": max(args.warmup, PREROLL_STEPS),
-                   "converged_frac": converged,
-                   "points_after_filter": n_out, "parallelism": "point-sharded x%d" % world},
+                   "converged_frac_projection": converged_projection,
+                   "valid_frac_after_resample": converged,
+                   "points_after_filter": n_out,
+                   "sdf_evaluations_per_point": siren_stats["rows"] / args.steps / C2_POINTS if sd else None,
+                   "sdf_evaluations_per_s": (siren_stats["rows"] / args.steps / (sd["ms_per_step"] * 1e-3)) if sd else None,
+                   "cpu_baseline_frnn": "O(n^2) single-thread brute force on the CPU sample (the reference's frnn_bf_cpu)",
+                   "parallelism": "point-sharded x%d" % world},
         "e2e": {"value": C2_POINTS * world / (e2e_ms * 1e-3), "unit": "points/s", "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms},
         "gpu_launches": int(launches),
@@ -368,8 +391,19 @@ def run_ours(args):
         "wall_s_timed_region": wall,
         "ms_each_step": [round(t, 3) for t in step_ms],
     }
+    if world > 1:
+        line["dist_parity"] = dist_parity(rank, world, dev, net, x_dev, out)
+    if not args.no_c5:
+        try:
+            import bench_c5
+            del flush
+            torch.cuda.empty_cache()
+            line["c5"] = bench_c5.run(rank, world, dev, steps=2, check=True)
+        except Exception as e:      # never lose the headline line to the side record
+            line["c5"] = {"error": "%s: %s" % (type(e).__name__, str(e)[:300])}
     if rank == 0:
         if world == 1:
+            cpu_baseline(sample_points=max(500, args.cpu_sample // 10))       # warm-up (thread pool, allocator)
             line["cpu_baseline"] = cpu_baseline(sample_points=args.cpu_sample)
             line["c1"] = bench_c1(dev)
             import bench_frnn
@@ -378,10 +412,56 @@ def run_ours(args):
             line["splat"] = bench_splat.run(args, dev, peaks, peak_src)
             import bench_trace
             line["trace"] = bench_trace.run(dev, steps=3)
+            if not args.no_ref_cuda:
+                line["ref_cuda"] = ref_cuda()
+                rc = line["ref_cuda"]
+                if rc.get("c2_ms"):
+                    rc["c2_speedup_vs_reference_gpu"] = rc["c2_ms"] / ms
         print(json.dumps(line))
     if world > 1:
         import torch.distributed as dist
         dist.destroy_process_group()
+
+
+def ref_cuda(timeout=420):
+    """The reference itself on THIS GPU (its Python + its CUDA extensions recompiled for sm_100a): oracle/ref_gpu.py
+    in a subprocess, after and outside every timed region of this process."""
+    try:
+        r = subprocess.run([sys.executable, "-m", "oracle.ref_gpu"], cwd=ROOT, capture_output=True, text=True,
+                           timeout=timeout)
+        lines = [ln for ln in r.stdout.strip().splitlines() if ln.startswith("{")]
+        if not lines:
+            return {"unavailable": "no output (rc %d): %s" % (r.returncode, r.stderr.strip()[-300:])}
+        return json.loads(lines[-1])
+    except Exception as e:
+        return {"unavailable": "%s: %s" % (type(e).__name__, str(e)[:200])}
+
+
+def dist_parity(rank, world, dev, net, x_dev, out):
+    """N > 1, outside the timed region: the concatenation of the ranks' sharded results equals the single-GPU
+    operator on the concatenated cloud (positions within 1e-4 rel, masks equal) -- tests/run_dist_gpu.py's check
+    on the bench workload itself."""
+    from isopoints_b200.dist import all_gather_varlen
+    from isopoints_b200.levelset_sampling import UniformProjection
+    pts, _ = all_gather_varlen(out["levelset_points"][0].contiguous())
+    msk, _ = all_gather_varlen(out["mask"][0].float()[:, None].contiguous())
+    xs, _ = all_gather_varlen(x_dev[0].contiguous())
+    ref = UniformProjection(proj_max_iters=10, proj_tolerance=5e-5, knn_k=8, sample_iters=1).project_points(
+        xs[None], net, skip_upsampling=True)
+    same_shape = ref["levelset_points"].shape[1] == pts.shape[0]
+    if same_shape:
+        agree = ref["mask"][0] == msk[:, 0].bool()
+        close = torch.isclose(ref["levelset_points"][0], pts, rtol=1e-4, atol=1e-5).all(-1)
+        frac = float((agree & close).float().mean())
+    else:
+        frac = 0.0
+    t = torch.tensor([frac], dtype=torch.float64, device=dev)
+    import torch.distributed as dist
+    dist.all_reduce(t, op=dist.ReduceOp.MIN)
+    return {"rows": int(pts.shape[0]), "rows_single_gpu": int(ref["levelset_points"].shape[1]),
+            "agree_frac": float(t.item()), "ok": bool(float(t.item()) > 0.999),
+            "what": "sharded project+resample (all ranks' rows concatenated) vs the single-GPU operator on the "
+                    "concatenated %d-point cloud: mask equal and position within 1e-4 rel, per row" % xs.shape[0]}
 
 
 def bench_c1(dev, reps=20):
@@ -414,12 +494,12 @@ def bench_c1(dev, reps=20):
 def cpu_baseline(sample_points=10_000, threads=None):
     """The oracle port of the same workload on the host cores, on a bounded sample."""
     from oracle import port
-    from tests.helpers import SirenSDF
+    from tests.helpers import pinned_siren
     threads = threads or os.cpu_count() or 1
     torch.set_num_threads(threads)
     g = torch.Generator().manual_seed(1000)
     x = ((torch.rand(1, C2_POINTS, 3, generator=g) - 0.5) * 2)[0, :sample_points].contiguous()
-    net = SirenSDF(hidden=256, n_layers=7, omega=30.0, seed=0)
+    net = pinned_siren(0).as_opaque()
     frnn_fn, frnn_how = _cpu_frnn()
     t0 = time.perf_counter()
     p, n, v = port.project_points_packed(net, x, proj_max_iters=10, proj_tolerance=5e-5)
@@ -446,9 +526,9 @@ def _cpu_frnn():
             t = torch.as_tensor(points)[None].contiguous()
             n = torch.tensor([t.shape[1]])
             return ref_native.frnn_bf_cpu(t, t, n, n, K, r)[0][0].numpy()
-        return fn, "the reference's own frnn_bf_cpu, 1 thread"
+        return fn, "the reference's own frnn_bf_cpu, O(n^2) brute force, 1 thread"
     except Exception:
-        return None, "numpy brute force, 1 thread"
+        return None, "numpy brute force O(n^2), 1 thread"
 
 
 def run_reference(args):
@@ -485,6 +565,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--cpu-sample", type=int, default=10_000)
+    ap.add_argument("--no-c5", action="store_true", help="skip the C5 side record (2 M points, 16 x 1024^2)")
+    ap.add_argument("--no-ref-cuda", action="store_true", help="skip the reference-on-GPU side record")
     ap.add_argument("--sdf", default="siren", choices=["siren", "opaque"],
                     help="siren: the reference's Siren decoder structure (fused SDF kernel); "
                          "opaque: same weights behind an opaque nn.Module (autograd SDF)")

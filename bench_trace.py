@@ -16,14 +16,14 @@ RAYS, ITERS = 200_000, 10
 
 
 def _model(opaque):
-    from tests.helpers import Siren, SirenSDF
-    net = (SirenSDF if opaque else Siren)(256, 7, 30.0, seed=0)
-    ref = Siren(256, 7, 30.0, seed=0)
+    """The SURVEY-pinned SIREN (tests/helpers.pinned_siren) with its head bias shifted so that the zero set
+    crosses the unit ball (a marching target); fused structure or the same weights behind an opaque module."""
+    from tests.helpers import pinned_siren
+    net = pinned_siren(0)
     with torch.no_grad():
         x = (torch.rand(4000, 3, generator=torch.Generator().manual_seed(0)) - 0.5) * 2
-        shift = ref(x).sdf.mean()
-        (net.lin[-1] if opaque else net.net[-1]).bias -= shift
-    return net
+        net.net[-1].bias -= net(x).sdf.mean()
+    return net.as_opaque() if opaque else net
 
 
 def run(dev, steps=5):

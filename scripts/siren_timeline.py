@@ -1,0 +1,54 @@
+#!/usr/bin/env python
+"""Developer tool: per-stage cycle stamps of CTA 0's first two tiles of the fused SIREN kernel (dbg_gemm = -2),
+plus the launch time at a few row counts.  Not part of the product or the tests.
+
+    python scripts/siren_timeline.py [rows]"""
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from isopoints_b200 import siren  # noqa: E402
+from tests.helpers import pinned_siren  # noqa: E402
+
+
+def main():
+    dev = "cuda"
+    L = 7
+    model = pinned_siren(0).to(dev)
+    n = int(sys.argv[1]) if len(sys.argv) > 1 else 200000
+    for rows in (n, 148 * 128, 148 * 128 * 4, 500, 128 * 148 * 10 + 7):
+        x = ((torch.rand(rows, 3, device=dev) - 0.5) * 2).contiguous()
+        for _ in range(3):
+            siren.sdf_and_grad(model, x)
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(10):
+            siren.sdf_and_grad(model, x)
+        b.record()
+        torch.cuda.synchronize()
+        ms = a.elapsed_time(b) / 10
+        print("rows %8d  value+grad %.4f ms  %.1f M evals/s" % (rows, ms, rows / ms / 1e3))
+        a.record()
+        for _ in range(10):
+            siren.sdf(model, x)
+        b.record()
+        torch.cuda.synchronize()
+        ms = a.elapsed_time(b) / 10
+        print("rows %8d  value only %.4f ms  %.1f M evals/s" % (rows, ms, rows / ms / 1e3))
+    x = ((torch.rand(n, 3, device=dev) - 0.5) * 2).contiguous()
+    out = siren.sdf_and_grad(model, x, dbg_gemm=-2)
+    torch.cuda.synchronize()
+    t = out[2].view(torch.int64).reshape(-1, 8)[:4 * L].cpu()
+    base = int(t[0, 7])
+    print("  G  epi_wait_begin  acc_full   stage_end | mma_first  mma_issued  wait_w  wait_a | epi_dur  mma_span")
+    for g in range(4 * L):
+        r = [int(v) for v in t[g]]
+        print("%3d %10d %10d %10d | %10d %10d %7d %7d | %7d %7d" % (
+            g, r[7] - base, r[0] - base, r[2] - base, r[3] - base, r[4] - base, r[5], r[6], r[2] - r[0], r[4] - r[3]))
+
+
+if __name__ == "__main__":
+    main()
