@@ -63,6 +63,24 @@ __global__ void siren_absmax_kernel(const float* __restrict__ w_hidden, const fl
   if ((threadIdx.x & 31) == 0 && m > 0.f) atomicMax(maxbits + l, __float_as_uint(m));
 }
 
+// hdr[HDR_GAIN + l] = |omega| * max_j sum_k |W_l[k][j]|  (one block per hidden layer, one thread per column j)
+__global__ void siren_gain_kernel(const float* __restrict__ w_hidden, float omega, unsigned char* __restrict__ blob) {
+  const int l = blockIdx.x, j = threadIdx.x;
+  const float* W = w_hidden + (size_t)l * H * H;
+  float s = 0.f;
+  for (int k = 0; k < H; ++k) s += fabsf(W[(size_t)k * H + j]);
+  __shared__ float red[H / 32];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s = fmaxf(s, __shfl_xor_sync(0xffffffffu, s, o));
+  if ((j & 31) == 0) red[j >> 5] = s;
+  __syncthreads();
+  if (j == 0) {
+    float m = red[0];
+    for (int i = 1; i < H / 32; ++i) m = fmaxf(m, red[i]);
+    reinterpret_cast<float*>(blob)[HDR_GAIN + l] = m * fabsf(omega);
+  }
+}
+
 __global__ void siren_pack_kernel(const float* __restrict__ w0, const float* __restrict__ b0,
                                   const float* __restrict__ w_hidden, const float* __restrict__ b_hidden,
                                   const float* __restrict__ w_last, const float* __restrict__ b_last, float omega0,
@@ -125,6 +143,18 @@ __global__ void siren_pack_kernel(const float* __restrict__ w0, const float* __r
   }
 }
 
+// ld.global.cg issued exactly here (volatile: ptxas does not sink it to the first use, which would put the L2
+// round trip back on the path it is meant to be taken off)
+__device__ __forceinline__ float4 ldcg_now(const float4* p) {
+  float4 v;
+  asm volatile("ld.global.cg.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ float4 ldnc_now(const float4* p) {
+  float4 v;
+  asm volatile("ld.global.nc.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+  return v;
+}
 __device__ __forceinline__ void st_f4_policy(float4* p, float4 v, uint64_t pol) {
   asm volatile("st.global.L2::cache_hint.v4.f32 [%0], {%1, %2, %3, %4}, %5;" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z),
                "f"(v.w), "l"(pol)
@@ -167,6 +197,8 @@ siren_sdf_grad_kernel(const float* __restrict__ x, int n_max, const int* __restr
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
+  if (threadIdx.x < 64)   // per-layer scale / gain table: read at the start of every stage, so keep it one LDS away
+    reinterpret_cast<float*>(smem + SM_HDR)[threadIdx.x] = reinterpret_cast<const float*>(blob)[threadIdx.x];
   if (warp == N_EPI_WARPS + 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(sbase + SM_TMEM_PTR),
                  "r"(512)
@@ -201,6 +233,19 @@ siren_sdf_grad_kernel(const float* __restrict__ x, int n_max, const int* __restr
             mbar_expect_tx(bar_w_full + 8 * s, STAGE_BYTES);
             tma_bulk_g2s(sbase + SM_STAGE + s * STAGE_BYTES, img + (size_t)kb * STAGE_BYTES, STAGE_BYTES,
                          bar_w_full + 8 * s);
+          }
+          // The cos factors the reverse stage after next will read were written up to 2(L-1) stages ago and may
+          // have left L2: ask the TMA unit to pull that layer's whole 128 KB slab ([col4][row] float4, contiguous)
+          // back in -- one instruction from this otherwise idle thread instead of 16 prefetches per epilogue thread.
+          // (GEMM g's weights are all requested: the epilogue is about to start stage g - 1 or g.)
+          if (!fwd_only) {
+            const int lt = g < L ? (g + 1 == L ? L - 1 : 0) : (2 * L - g) - 2;   // 1-based layer of that slab
+            if (lt >= 1)
+              asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(
+                               reinterpret_cast<const float4*>(scratch) +
+                               ((size_t)blockIdx.x * (size_t)(L > 1 ? L - 1 : 1) + (size_t)(lt - 1)) * 64 * TM),
+                           "r"(64 * TM * 16)
+                           : "memory");
           }
         }
       }
@@ -268,6 +313,7 @@ siren_sdf_grad_kernel(const float* __restrict__ x, int n_max, const int* __restr
     // this thread's 16-byte K-chunk of k-block kb lives at chunk index 4 kb + cslice
     const uint32_t a_thr = (uint32_t)cslice * A_LBO + (uint32_t)(row >> 3) * SBO + (uint32_t)(row & 7) * 16;
     float* xch = reinterpret_cast<float*>(smem + SM_XCH);
+    const float* shdr = reinterpret_cast<const float*>(smem + SM_HDR);
     // grad partials of column slices 1..3 go through the (idle) A tile in the last stage: the 16-byte
     // slot of this row in k-chunk (cslice - 1), which only this row's own warps ever write
     unsigned char* gsc = smem + SM_A_HI + row * 16;
@@ -284,13 +330,16 @@ siren_sdf_grad_kernel(const float* __restrict__ x, int n_max, const int* __restr
     asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol_first));
 
     // publish this thread's K-chunk of k-block kb: generic-proxy stores -> async proxy, one arrive per warp
-    auto publish = [&](int kb, const float2* o) {
+    auto publish = [&](int kb, const float2* o, long long* kst = nullptr) {
       const uint32_t off = (uint32_t)(kb * 4) * A_LBO + a_thr;
       store_chunk(sbase + SM_A_HI + off, sbase + SM_A_LO + off, o);
+      if (kst) kst[2] = clock64();
       tc_fence_before();
       fence_proxy_async();
+      if (kst) kst[3] = clock64();
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_a_ready + 8 * kb);
+      if (kst) kst[4] = clock64();
     };
 
     // append the still-active rows of this tile to the next active list: in-tile order, one reservation per
@@ -342,7 +391,17 @@ siren_sdf_grad_kernel(const float* __restrict__ x, int n_max, const int* __restr
         publish(kb, o);
       }
 
+      // operands of the NEXT stage's first k-blocks, requested one stage ahead so that their L2 latency is not
+      // between an accumulator becoming ready and the first k-block of the next A operand:
+      float4 pf0, pf1, pf2, pf3;   // forward: biases of k-block 0 (pf0, pf1); reverse: cos factors of k-blocks 0, 1
+      pf0 = pf1 = pf2 = pf3 = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (L > 0) {
+        const float4* bw4n = reinterpret_cast<const float4*>(biasw) + cslice * 2;   // layer 1
+        pf0 = __ldg(bw4n);
+        pf1 = __ldg(bw4n + 1);
+      }
       float row_scale_inv = 1.f;  // inverse of the scale applied to this row of the current backward A
+      float row_max = 0.f;        // max |.| over this row of the current backward A (scaled values, all 256 columns)
       float sdf_row = 0.f;        // this row's sdf (slice-0 thread), kept for the fused Newton step
       for (int g = 0; g < n_gemm; ++g, ++G) {
         const uint32_t buf = G & 1;
@@ -350,30 +409,19 @@ siren_sdf_grad_kernel(const float* __restrict__ x, int n_max, const int* __restr
             (dbg && dbg_gemm == -2 && blockIdx.x == 0 && threadIdx.x == 0 && G < 2u * n_gemm)
                 ? reinterpret_cast<long long*>(dbg) + G * 8 : nullptr;
         if (tstamp) tstamp[7] = clock64();
+        // dbg_gemm == -2: per-k-block stamps of thread 0 in stages G = 1 (forward) and G = 8 (reverse)
+        long long* kbase = (tstamp && (G == 1u || G == 8u)) ? reinterpret_cast<long long*>(dbg) + 512 + (G == 1u ? 0 : 64)
+                                                           : nullptr;
         mbar_wait(bar_acc_full + 8 * buf, (G >> 1) & 1);
         tc_fence_after();
         if (tstamp) tstamp[0] = clock64();
         const uint32_t tacc = tl + buf * H;
         const bool fwd = g < L;
         const int l = fwd ? g + 1 : 2 * L - g;  // 1-based hidden layer this GEMM belongs to
-        const float wsi = hdr[l - 1];
+        const float wsi = shdr[l - 1];
         uint32_t rn[8];                    // next k-block's accumulator slice, loaded ahead
         tmem_ld8_issue(tacc, rn);
-        {
-          // the cos factors the NEXT backward stage will read were written up to 2(L-1) stages ago and
-          // may have left L2: start pulling this thread's 16 lines back in one stage ahead
-          const int lp = fwd ? (l == L ? L - 1 : 0) : l - 2;   // stash slot (1-based layer) read next
-          if (lp >= 1 && !fwd_only) {
-            const float4* pf = stash + (size_t)(lp - 1) * 64 * TM + row;
-#pragma unroll
-            for (int kb = 0; kb < NKB; ++kb) {
-              const int col4 = kb * 8 + cslice * 2;
-              asm volatile("prefetch.global.L2 [%0];" ::"l"(pf + (size_t)col4 * TM));
-              asm volatile("prefetch.global.L2 [%0];" ::"l"(pf + (size_t)(col4 + 1) * TM));
-            }
-          }
-        }
-
+        if (kbase) kbase[15] = clock64();   // after the prefetch block
         if (dbg && blockIdx.x == 0 && (int)G == dbg_gemm) {
           // raw accumulator dump (unscaled), [128][256]
 #pragma unroll 1
@@ -391,10 +439,13 @@ siren_sdf_grad_kernel(const float* __restrict__ x, int n_max, const int* __restr
           const float2 sc2 = bc2(wsi * A_SCALE_INV * omega);
           float4* st = stash + (size_t)(l - 1) * 64 * TM + row;
           const float4* bw4 = reinterpret_cast<const float4*>(biasw + (l - 1) * H) + cslice * 2;
-          float4 bwn0 = __ldg(bw4), bwn1 = __ldg(bw4 + 1);   // biases one k-block ahead
+          float4 bwn0 = pf0, bwn1 = pf1;   // biases one k-block ahead (k-block 0: requested during the previous stage)
 #pragma unroll 1
           for (int kb = 0; kb < NKB; ++kb) {
+            long long* kst = kbase ? kbase + kb * 8 : nullptr;
+            if (kst) kst[0] = clock64();
             tmem_ld_wait(rn);
+            if (kst) kst[1] = clock64();
             const float2 v[4] = {make_float2(__uint_as_float(rn[0]), __uint_as_float(rn[1])),
                                  make_float2(__uint_as_float(rn[2]), __uint_as_float(rn[3])),
                                  make_float2(__uint_as_float(rn[4]), __uint_as_float(rn[5])),
@@ -411,7 +462,7 @@ siren_sdf_grad_kernel(const float* __restrict__ x, int n_max, const int* __restr
               o[pr] = __fmul2_rn(sn, bc2(A_SCALE));
               cc[pr] = __fmul2_rn(cp, signed_scale(omega, sx, sy));
             }
-            publish(kb, o);
+            publish(kb, o, kst);
             // global traffic right after the hand-off fence (which waits for everything in flight)
             if (!fwd_only) {
               const int col4 = kb * 8 + cslice * 2;
@@ -426,7 +477,11 @@ siren_sdf_grad_kernel(const float* __restrict__ x, int n_max, const int* __restr
             if (kb + 1 < NKB) {
               bwn0 = __ldg(bw4 + (kb + 1) * 8);
               bwn1 = __ldg(bw4 + (kb + 1) * 8 + 1);
+            } else {   // k-block 0 of the next layer (l + 1 <= L exists: this branch is l < L)
+              pf0 = ldnc_now(bw4 + H / 4);
+              pf1 = ldnc_now(bw4 + H / 4 + 1);
             }
+            if (kst) kst[5] = clock64();
           }
         } else if (fwd) {
           // ---- E_f(L): sdf = h_L . w_last + b_last ; A = gl_scale * w_last * c_L ----
@@ -434,6 +489,7 @@ siren_sdf_grad_kernel(const float* __restrict__ x, int n_max, const int* __restr
           const float gls = gl_scale * omega;
           const float4* bw4 = reinterpret_cast<const float4*>(biasw + (l - 1) * H) + cslice * 2;
           float2 acc2 = bc2(0.f);
+          float mloc = 0.f;
 #pragma unroll 1
           for (int kb = 0; kb < NKB; ++kb) {
             tmem_ld_wait(rn);
@@ -442,7 +498,7 @@ siren_sdf_grad_kernel(const float* __restrict__ x, int n_max, const int* __restr
                                  make_float2(__uint_as_float(rn[4]), __uint_as_float(rn[5])),
                                  make_float2(__uint_as_float(rn[6]), __uint_as_float(rn[7]))};
             if (kb + 1 < NKB) tmem_ld8_issue(tacc + (kb + 1) * KB, rn);
-            const float4 b0 = __ldg(bw4 + kb * 8), b1 = __ldg(bw4 + kb * 8 + 1);
+            const float4 b0 = kb ? __ldg(bw4 + kb * 8) : pf0, b1 = kb ? __ldg(bw4 + kb * 8 + 1) : pf1;
             const float4 w0 = __ldg(w_last4 + kb * 8), w1 = __ldg(w_last4 + kb * 8 + 1);
             const float2 bb[4] = {make_float2(b0.x, b0.y), make_float2(b0.z, b0.w), make_float2(b1.x, b1.y),
                                   make_float2(b1.z, b1.w)};
@@ -456,8 +512,14 @@ siren_sdf_grad_kernel(const float* __restrict__ x, int n_max, const int* __restr
               sincos2(__ffma2_rn(v[pr], sc2, bb[pr]), sn, cp, sx, sy);
               acc2 = __ffma2_rn(sn, ww[pr], acc2);
               o[pr] = __fmul2_rn(__fmul2_rn(cp, signed_scale(gls, sx, sy)), ww[pr]);
+              mloc = fmaxf(mloc, fmaxf(fabsf(o[pr].x), fabsf(o[pr].y)));
             }
             if (!fwd_only) publish(kb, o);   // forward-only: no reverse GEMM follows, the next A is the next tile's
+          }
+          if (!fwd_only && L > 1) {   // cos factors of k-blocks 0 / 1 of the first reverse stage (layer L - 1)
+            const float4* stn = stash + (size_t)(L - 2) * 64 * TM + row + (size_t)(cslice * 2) * TM;
+            pf0 = ldcg_now(stn); pf1 = ldcg_now(stn + TM);
+            pf2 = ldcg_now(stn + (size_t)8 * TM); pf3 = ldcg_now(stn + (size_t)9 * TM);
           }
           const float acc_sdf = acc2.x + acc2.y;
           row_scale_inv = gl_scale_inv;
@@ -468,6 +530,12 @@ siren_sdf_grad_kernel(const float* __restrict__ x, int n_max, const int* __restr
             if (grow < n && sdf_out) sdf_out[grow] = sdf_row;
           }
           row_barrier(q);
+          if (!fwd_only) {   // row maximum of what was just written: the next stage derives its scale from it
+            xch[row * 4 + cslice] = mloc;
+            row_barrier(q);
+            row_max = fmaxf(fmaxf(xch[row * 4], xch[row * 4 + 1]), fmaxf(xch[row * 4 + 2], xch[row * 4 + 3]));
+            row_barrier(q);
+          }
           if (nw.mode == 1 && cslice == 0) {
             // ---- fused ray-marching step on this row (same arithmetic as trace_step_kernel, project.cu) ----
             bool still = false;
@@ -506,34 +574,27 @@ siren_sdf_grad_kernel(const float* __restrict__ x, int n_max, const int* __restr
         } else if (l > 1) {
           // ---- E_b(l): g_{l-1} = acc / scales ; gp_{l-1} = g_{l-1} * c_{l-1} -> A (row-scaled) ----
           const float sc = wsi * row_scale_inv;
-          // pass 1: row maximum of |g_{l-1}| over all 256 columns.  Any thread of the row may scan any
-          // columns, so this one takes the contiguous 64 starting at 64 * cslice: two wide loads.
-          float m = 0.f;
-          {
-            tmem_ld_wait(rn);   // retire the k-block 0 prefetch; it is re-issued below for pass 2
-            const uint32_t tcont = tacc - 8 * cslice + 64 * cslice;
-#pragma unroll
-            for (int hblk = 0; hblk < 2; ++hblk) {
-              float w32[32];
-              tmem_ld32(tcont + 32 * hblk, w32);
-#pragma unroll
-              for (int i = 0; i < 32; ++i) m = fmaxf(m, fabsf(w32[i]));
-            }
-            tmem_ld8_issue(tacc, rn);
-          }
-          xch[row * 4 + cslice] = m;
-          row_barrier(q);
-          m = fmaxf(fmaxf(xch[row * 4], xch[row * 4 + 1]), fmaxf(xch[row * 4 + 2], xch[row * 4 + 3]));
-          row_barrier(q);
-          const float new_scale = pow2_scale_for(m * sc * fabsf(omega));
+          // Per-row scale of the next A operand (gp_{l-1}) WITHOUT a pass over the accumulator: the rows written
+          // one stage ago had the measured maximum `row_max` (scaled), so max_j |g_{l-1,j}| |omega| <=
+          // (row_max / row scale) * |omega| max_j sum_k |W_l[k][j]| (header gain).  The bound is a few binades
+          // above the true maximum (the sum does not see the cancellation); the fp16 hi/lo pair keeps 22 bits of
+          // the row maximum anywhere in [2^-3, 2^15], so landing at 2^7..2^10 instead of 2^11 costs nothing, and
+          // the next stage re-centres on the maximum it measures itself -- the slack does not accumulate.
+          const float new_scale = pow2_scale_for(row_max * row_scale_inv * shdr[HDR_GAIN + l - 1]);
+          float mloc = 0.f;
+          if (kbase) { kbase[23] = clock64(); kbase[6] = (long long)__float_as_int(new_scale); }
           const float2 scs2 = bc2(sc * new_scale);
           const float4* st = stash + (size_t)(l - 2) * 64 * TM + row + (size_t)(cslice * 2) * TM;
-          // cos factors: two k-blocks in flight (an L2 hit is ~1 k-block of this loop away, a miss more)
-          float4 c0 = __ldcg(st), c1 = __ldcg(st + TM);
-          float4 d0 = __ldcg(st + (size_t)8 * TM), d1 = __ldcg(st + (size_t)9 * TM);
+          // cos factors: two k-blocks in flight (an L2 hit is ~1 k-block of this loop away, a miss more); those of
+          // k-blocks 0 and 1 were requested at the end of the previous stage
+          float4 c0 = pf0, c1 = pf1, d0 = pf2, d1 = pf3;
+          if (kbase) { kbase[7] = clock64(); kbase[14] = (long long)__float_as_int(c0.x + d1.w); kbase[31] = clock64(); }
 #pragma unroll 2
           for (int kb = 0; kb < NKB; ++kb) {
+            long long* kst = kbase ? kbase + kb * 8 : nullptr;
+            if (kst) kst[0] = clock64();
             tmem_ld_wait(rn);
+            if (kst) kst[1] = clock64();
             float2 o[4];
             o[0] = __fmul2_rn(__fmul2_rn(make_float2(__uint_as_float(rn[0]), __uint_as_float(rn[1])), scs2),
                               make_float2(c0.x, c0.y));
@@ -543,8 +604,10 @@ siren_sdf_grad_kernel(const float* __restrict__ x, int n_max, const int* __restr
                               make_float2(c1.x, c1.y));
             o[3] = __fmul2_rn(__fmul2_rn(make_float2(__uint_as_float(rn[6]), __uint_as_float(rn[7])), scs2),
                               make_float2(c1.z, c1.w));
+            mloc = fmaxf(fmaxf(mloc, fmaxf(fabsf(o[0].x), fabsf(o[0].y))), fmaxf(fabsf(o[1].x), fabsf(o[1].y)));
+            mloc = fmaxf(fmaxf(mloc, fmaxf(fabsf(o[2].x), fabsf(o[2].y))), fmaxf(fabsf(o[3].x), fabsf(o[3].y)));
             if (kb + 1 < NKB) tmem_ld8_issue(tacc + (kb + 1) * KB, rn);
-            publish(kb, o);
+            publish(kb, o, kst);
             // this k-block's cos lines are dead now (the next tile rewrites them in full before reading):
             // drop them from L2 instead of letting them be written back to HBM
             if ((lane & 7) == 0) {
@@ -557,8 +620,18 @@ siren_sdf_grad_kernel(const float* __restrict__ x, int n_max, const int* __restr
               d0 = __ldcg(st + (size_t)((kb + 2) * 8) * TM);
               d1 = __ldcg(st + (size_t)((kb + 2) * 8 + 1) * TM);
             }
+            if (kst) kst[5] = clock64();
+          }
+          if (l > 2) {   // k-blocks 0 / 1 of the next reverse stage (layer l - 2's cos factors)
+            const float4* stn = stash + (size_t)(l - 3) * 64 * TM + row + (size_t)(cslice * 2) * TM;
+            pf0 = ldcg_now(stn); pf1 = ldcg_now(stn + TM);
+            pf2 = ldcg_now(stn + (size_t)8 * TM); pf3 = ldcg_now(stn + (size_t)9 * TM);
           }
           row_scale_inv = 1.f / new_scale;
+          xch[row * 4 + cslice] = mloc;      // off the critical path: the next accumulator is ~2 k cycles away
+          row_barrier(q);
+          row_max = fmaxf(fmaxf(xch[row * 4], xch[row * 4 + 1]), fmaxf(xch[row * 4 + 2], xch[row * 4 + 3]));
+          row_barrier(q);
         } else {
           // ---- E_b(1): g_0 = acc / scales ; gp_0 = g_0 * w0 cos(w0 z_0) ; grad = gp_0 W_0 ----
           // (the w0 table holds omega_0-scaled rows, so gp_0 . W_0 = sum (g_0 cos) * (omega_0 W_0))
@@ -694,6 +767,8 @@ int isob200_siren_pack(const float* w0, const float* b0, const float* w_hidden, 
   siren_pack_kernel<<<kNumSMs * 2, 256, 0, st>>>(w0, b0, w_hidden, b_hidden, w_last, b_last, omega0, omega, n_hidden,
                                                 (const unsigned*)ws, (unsigned char*)blob);
   ISO_CHECK_LAUNCH("siren_pack_kernel");
+  siren_gain_kernel<<<n_hidden, H, 0, st>>>(w_hidden, omega, (unsigned char*)blob);
+  ISO_CHECK_LAUNCH("siren_gain_kernel");
   return ISOB200_OK;
 }
 

@@ -27,6 +27,8 @@ constexpr int MAX_LAYERS = 32;
 
 // ---- packed blob layout (all offsets in bytes) -------------------------------------------
 // [0,1024)        header floats: [l-1] = 2^-s_l (inverse weight scale of hidden layer l), l = 1..L
+//                 [32 + l-1] = |omega| * max_j sum_k |W_l[k][j]| (bound on the gain of the reverse GEMM of layer l:
+//                 max_j |(gp W_l)_j| * |omega| <= max_k |gp_k| * this), l = 1..L
 //                 [64] gl_scale, [65] 1/gl_scale (static scale of gp_L), [66] b_last,
 //                 [67] omega_0 (first layer), [68] omega (hidden)
 // [1024,5120)     float4 w0p[128][2]: column pair (a, b) = (2p, 2p+1) as (x_a, x_b, y_a, y_b), (z_a, z_b, w_a, w_b)
@@ -35,6 +37,7 @@ constexpr int MAX_LAYERS = 32;
 // [6144, ..)      float  bias[L][256], pre-multiplied by omega
 // images          (1024-aligned) for l = 1..L, orientation o = 0 (forward: B[n][k] = W_l[n][k])
 //                 and o = 1 (backward: B[n][k] = W_l[k][n]): 8 stages of 32 KB
+constexpr size_t HDR_GAIN = 32;
 constexpr size_t HDR_GL_SCALE = 64, HDR_GL_SCALE_INV = 65, HDR_B_LAST = 66, HDR_OMEGA0 = 67, HDR_OMEGA = 68;
 constexpr size_t OFF_W0B = 1024;
 constexpr size_t OFF_WLAST = OFF_W0B + H * 16;
@@ -54,7 +57,8 @@ constexpr int SM_BAR = SM_XCH + TM * 4 * 4;                 // 231424
 // barriers: a_ready[8], acc_full[2], w_full[3], w_empty[3]  -> 16 * 8 B
 constexpr int SM_TMEM_PTR = SM_BAR + 16 * 8;
 constexpr int SM_CMP = SM_TMEM_PTR + 16;                    // int cmp[8]: warp counts + reserved base
-constexpr int SMEM_BYTES = SM_CMP + 32;                     // 231600 <= 232448
+constexpr int SM_HDR = SM_CMP + 32;                         // float hdr[64]: per-layer scales / gains (header copy)
+constexpr int SMEM_BYTES = SM_HDR + 64 * 4;                 // 231856 <= 232448
 
 // ---- PTX helpers -----------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -178,12 +182,21 @@ __device__ __forceinline__ void sincos2(float2 a, float2& sn, float2& cp, uint32
   t = __fmul2_rn(t, r2);
   const float2 rs = make_float2(__uint_as_float(__float_as_uint(r.x) ^ sgx), __uint_as_float(__float_as_uint(r.y) ^ sgy));
   sn = __ffma2_rn(t, rs, rs);
+#ifdef ISOB200_SIREN_POLY_COS
   float2 u = __ffma2_rn(r2, bc2(1.9918149352093906e-09f), bc2(-2.7525521772986394e-07f));
   u = __ffma2_rn(u, r2, bc2(2.4801065592328086e-05f));
   u = __ffma2_rn(u, r2, bc2(-1.3888884568586946e-03f));
   u = __ffma2_rn(u, r2, bc2(0.0416666679084301f));
   u = __ffma2_rn(u, r2, bc2(-0.5f));
   cp = __ffma2_rn(u, r2, bc2(1.0f));
+#else
+  // The cosine only ever multiplies back-propagated rows (the tape factor w cos(w z)); the forward value path
+  // uses the sine alone.  The epilogue is FP32-pipe bound (a packed FFMA2 holds the pipe for two cycles), so the
+  // six-term cosine polynomial moves to the special-function unit: MUFU.COS on the already reduced argument
+  // (|r| <= pi/2, where its absolute error is <= 2^-21.2), two scalar instructions per pair on an otherwise idle
+  // pipe.  Measured effect on the gradient against float64: see tests/test_gpu_siren.py.
+  cp = make_float2(__cosf(r.x), __cosf(r.y));
+#endif
 }
 __device__ __forceinline__ float2 signed_scale(float sc, uint32_t sgx, uint32_t sgy) {
   return make_float2(__uint_as_float(__float_as_uint(sc) ^ sgx), __uint_as_float(__float_as_uint(sc) ^ sgy));

@@ -41,14 +41,28 @@ def main():
     x = ((torch.rand(n, 3, device=dev) - 0.5) * 2).contiguous()
     out = siren.sdf_and_grad(model, x, dbg_gemm=-2)
     torch.cuda.synchronize()
-    t = out[2].view(torch.int64).reshape(-1, 8)[:4 * L].cpu()
+    raw = out[2].view(torch.int64).reshape(-1, 8).cpu()
+    t = raw[:4 * L]
     base = int(t[0, 7])
     print("  G  epi_wait_begin  acc_full   stage_end | mma_first  mma_issued  wait_w  wait_a | epi_dur  mma_span")
     for g in range(4 * L):
         r = [int(v) for v in t[g]]
         print("%3d %10d %10d %10d | %10d %10d %7d %7d | %7d %7d" % (
             g, r[7] - base, r[0] - base, r[2] - base, r[3] - base, r[4] - base, r[5], r[6], r[2] - r[0], r[4] - r[3]))
+    for name, off in (("forward stage G=1", 64), ("reverse stage G=8", 72)):
+        k = raw[off:off + 8]
+        print(name, "(thread 0): per k-block  ld_wait  math+st.shared  fences  syncwarp+arrive  -  global st/ld tail | total")
+        if name.startswith("reverse"):
+            a0 = int(t[8, 0])
+            print("   after acc_full: prefetch block done +%d, scale known +%d, tape loads issued +%d, first tape data +%d"
+                  % (int(k[1, 7]) - a0, int(k[2, 7]) - a0, int(k[0, 7]) - a0, int(k[3, 7]) - a0))
+        for kb in range(8):
+            r = [int(v) for v in k[kb]]
+            print("   kb %d: start +%6d | %5d %5d %5d %5d %5d %5d | %6d" % (
+                kb, r[0] - int(t[1 if off == 64 else 8, 0]), r[1] - r[0], r[2] - r[1], r[3] - r[2], r[4] - r[3], 0,
+                r[5] - r[4], r[5] - r[0]))
 
 
 if __name__ == "__main__":
     main()
+
