@@ -69,7 +69,7 @@ def _peaks():
         return {"hbm_gbs": 6650.0}, "fallback"
 
 
-PREROLL_STEPS = 50   # minimum number of untimed steps before the timed region (clock ramp of an idle GPU)
+PREROLL_STEPS = int(os.environ.get("ISO_BENCH_PREROLL", "50"))   # minimum number of untimed steps before the timed region (clock ramp of an idle GPU)
 
 
 class ClockSampler:
@@ -86,7 +86,7 @@ class ClockSampler:
                ("sw_power_cap", 0x4))
 
     def __init__(self, gpu_index=0, period=0.004):
-        self.sm, self.mx, self.reasons = [], [], set()
+        self.sm, self.mx, self.reasons, self.pw = [], [], set(), []
         self.gpu = gpu_index
         self.period = period
         self._stop = threading.Event()
@@ -112,6 +112,10 @@ class ClockSampler:
         nv = self._nv
         self.sm.append(float(nv.nvmlDeviceGetClockInfo(self._h, nv.NVML_CLOCK_SM)))
         self.mx.append(self._max)
+        try:
+            self.pw.append(nv.nvmlDeviceGetPowerUsage(self._h) / 1000.0)
+        except Exception:
+            pass
         bits = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self._h))
         for name, bit in self.REASONS:
             if bits & bit:
@@ -123,6 +127,10 @@ class ClockSampler:
         for line in out.strip().splitlines():
             r = [c.strip() for c in line.split(",")]
             self.sm.append(float(r[1])); self.mx.append(float(r[2]))
+            try:
+                self.pw.append(float(r[3]))
+            except Exception:
+                pass
             for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
                 if v.lower().startswith("active"):
                     self.reasons.add(name)
@@ -147,7 +155,7 @@ class ClockSampler:
         """Drop what was sampled so far: the sampler is started before the warm-up steps (the first NVML queries
         of a process initialise driver state and were seen to stall the first step after them by tens of ms) and
         reset when the timed region starts, so only samples taken during it are reported."""
-        self.sm, self.mx, self.reasons = [], [], set()
+        self.sm, self.mx, self.reasons, self.pw = [], [], set(), []
 
     def __exit__(self, *a):
         self._stop.set()
@@ -158,6 +166,7 @@ class ClockSampler:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
         return {"sm_mhz": float(np.median(self.sm)), "sm_max_mhz": float(max(self.mx)),
                 "reasons": sorted(self.reasons), "samples": len(self.sm),
+                "power_w": float(np.median(self.pw)) if self.pw else None,
                 "source": "nvml" if self._h is not None else "nvidia-smi"}
 
 
@@ -393,7 +402,7 @@ def run_ours(args):
     }
     if world > 1:
         line["dist_parity"] = dist_parity(rank, world, dev, net, x_dev, out)
-    if not args.no_c5:
+    if not args.no_c5 and not args.no_side:
         try:
             import bench_c5
             del flush
@@ -402,7 +411,7 @@ def run_ours(args):
         except Exception as e:      # never lose the headline line to the side record
             line["c5"] = {"error": "%s: %s" % (type(e).__name__, str(e)[:300])}
     if rank == 0:
-        if world == 1:
+        if world == 1 and not args.no_side:
             cpu_baseline(sample_points=max(500, args.cpu_sample // 10))       # warm-up (thread pool, allocator)
             line["cpu_baseline"] = cpu_baseline(sample_points=args.cpu_sample)
             line["c1"] = bench_c1(dev)
@@ -566,6 +575,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--cpu-sample", type=int, default=10_000)
     ap.add_argument("--no-c5", action="store_true", help="skip the C5 side record (2 M points, 16 x 1024^2)")
+    ap.add_argument("--no-side", action="store_true",
+                    help="profiling runs: skip every side record (c5, cpu_baseline, c1, frnn, splat, trace, ref_cuda)")
     ap.add_argument("--no-ref-cuda", action="store_true", help="skip the reference-on-GPU side record")
     ap.add_argument("--sdf", default="siren", choices=["siren", "opaque"],
                     help="siren: the reference's Siren decoder structure (fused SDF kernel); "

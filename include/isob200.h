@@ -144,8 +144,11 @@ int isob200_ray_nearest_point(const float* origins, int n_origins, const float* 
 
 /* tuning knob: persistent CTAs per SIREN launch (1..148, default 148 = one per SM); returns the old value */
 int isob200_siren_set_max_ctas(int n);
-/* tuning knob: tape (cos factor) layers 1..n are stored with the L2 evict-first policy; returns the old value */
-int isob200_siren_set_spill_layers(int n);
+/* tuning knob: the CTAs on odd SMs of a value + gradient launch with >= min_tiles 128-row tiles start `cycles` SM
+ * cycles late, so that half of the chip writes reverse-mode tape while the other half consumes it and the live
+ * tape stays L2 resident (cycles < 0: half a tile period, the default; 0: off; min_tiles <= 0: keep); returns the
+ * old cycle setting */
+int isob200_siren_set_stagger(int cycles, int min_tiles);
 
 /* ---- uniform resampling: UniformProjection.resample, one sample_iter
  *      (DSS/models/levelset_sampling.py:259, 268-284) ------------------------------------ */

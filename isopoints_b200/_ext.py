@@ -10,7 +10,9 @@ import threading
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libisob200.so")
+# ISOB200_LIB: another build of the same library (A/B timing of two kernel versions on one box); entry points it
+# does not export are skipped instead of failing the load
+LIB_PATH = os.environ.get("ISOB200_LIB") or os.path.join(_HERE, "libisob200.so")
 
 _vp = ctypes.c_void_p
 _i = ctypes.c_int
@@ -45,7 +47,7 @@ _PROTOS = {
     "isob200_compact_valid": (_i, [_vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _sz, _vp]),
     "isob200_project_sphere": (_i, [_vp, _vp, _vp, _ll, _f, _f, _f, _i, _vp]),
     "isob200_siren_set_max_ctas": (_i, [_i]),
-    "isob200_siren_set_spill_layers": (_i, [_i]),
+    "isob200_siren_set_stagger": (_i, [_i, _i]),
     "isob200_siren_blob_bytes": (_sz, [_i]),
     "isob200_siren_pack_ws_bytes": (_sz, []),
     "isob200_siren_scratch_bytes": (_sz, [_i]),
@@ -91,7 +93,7 @@ _TLS = threading.local()
 # Optional per-entry-point device timing (bench.py): when PROFILE is a dict, every C-ABI call is
 # bracketed by CUDA events on the stream it is launched on; PROFILE[name] collects (start, end).
 PROFILE = None
-_NO_TIMING = ("_ws_bytes", "_blob_bytes", "_scratch_bytes", "isob200_siren_set_max_ctas", "isob200_siren_set_spill_layers", "isob200_last_error", "isob200_abi_version", "isob200_compiled_arch",
+_NO_TIMING = ("_ws_bytes", "_blob_bytes", "_scratch_bytes", "isob200_siren_set_max_ctas", "isob200_siren_set_stagger", "isob200_last_error", "isob200_abi_version", "isob200_compiled_arch",
               "isob200_launch_count", "isob200_splat_record_bytes")
 
 
@@ -142,7 +144,12 @@ def lib():
         h = ctypes.CDLL(LIB_PATH)
         w = _Lib()
         for name, (res, args) in _PROTOS.items():
-            fn = getattr(h, name)  # AttributeError if the .so is stale
+            try:
+                fn = getattr(h, name)  # AttributeError if the .so is stale
+            except AttributeError:
+                if os.environ.get("ISOB200_LIB"):
+                    continue
+                raise
             fn.restype = res
             fn.argtypes = args
             setattr(w, name, _wrap(name, fn))

@@ -155,17 +155,24 @@ __device__ __forceinline__ float4 ldnc_now(const float4* p) {
   asm volatile("ld.global.nc.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
   return v;
 }
-__device__ __forceinline__ void st_f4_policy(float4* p, float4 v, uint64_t pol) {
-  asm volatile("st.global.L2::cache_hint.v4.f32 [%0], {%1, %2, %3, %4}, %5;" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z),
-               "f"(v.w), "l"(pol)
-               : "memory");
-}
-
 // ---------------------------------------------------------------------------------------------
 // main kernel
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ int kb_order(int i) { return i; }
+// Tile scheduler state: [slot][0] = next tile, [slot][1] = CTAs finished.  Zero at module load; the last CTA of a
+// launch puts its slot back to zero, and consecutive launches take consecutive slots, so kernels that overlap on
+// different streams do not share one.
+constexpr int SCHED_SLOTS = 64;
+__device__ int g_tile_sched[SCHED_SLOTS * 2];
 
+#define ISO_STAMP(p, i)              \
+  if constexpr (DBG) {               \
+    if (p) (p)[i] = clock64();       \
+  }
+
+// DBG = true: the bring-up build of the same kernel (cycle stamps of CTA 0's first two tiles for dbg_gemm == -2, raw
+// accumulator dump of GEMM dbg_gemm >= 0); launched only when the caller passes a dbg buffer.  The product
+// instantiation carries none of those instructions (they were ~6 % of the epilogue's issue slots when predicated off).
+template <bool DBG>
 __global__ void __launch_bounds__(THREADS, 1)
 siren_sdf_grad_kernel(const float* __restrict__ x, int n_max, const int* __restrict__ n_dev,
                       const unsigned char* __restrict__ blob, int L, float* __restrict__ sdf_out,
@@ -179,7 +186,9 @@ siren_sdf_grad_kernel(const float* __restrict__ x, int n_max, const int* __restr
   const uint32_t bar_acc_full = sbase + SM_BAR + 8 * 8;    // [2]
   const uint32_t bar_w_full = sbase + SM_BAR + 10 * 8;     // [3]
   const uint32_t bar_w_empty = sbase + SM_BAR + 13 * 8;    // [3]
+  const uint32_t bar_tile = sbase + SM_BAR + 16 * 8;       // [2]
   volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(smem + SM_TMEM_PTR);
+  volatile int* tile_slot = reinterpret_cast<volatile int*>(smem + SM_TILE);   // [2]
 
   int n = n_max;
   if (n_dev) {
@@ -195,6 +204,7 @@ siren_sdf_grad_kernel(const float* __restrict__ x, int n_max, const int* __restr
       mbar_init(bar_w_full + 8 * i, 1);
       mbar_init(bar_w_empty + 8 * i, 1);
     }
+    for (int i = 0; i < 2; ++i) mbar_init(bar_tile + 8 * i, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (threadIdx.x < 64)   // per-layer scale / gain table: read at the start of every stage, so keep it one LDS away
@@ -214,27 +224,47 @@ siren_sdf_grad_kernel(const float* __restrict__ x, int n_max, const int* __restr
   const size_t img0 = off_images(L);
   const bool fwd_only = nw.mode != 0;            // value only (mode 2) / ray marching (mode 1): L GEMMs, no tape
   const int n_gemm = fwd_only ? L : 2 * L;      // per tile
+  int* sched = g_tile_sched + 2 * nw.sched_slot;
 
   if (warp == N_EPI_WARPS) {
-    // ===================== weight producer =====================
+    // ===================== tile scheduler + weight producer =====================
     if (lane == 0) {
+      // Phase stagger.  A tile's reverse-mode tape grows to (L-1) x 128 KB over its forward half and is consumed over
+      // its reverse half; with every CTA in the same phase the live tape peaks at 148 x 768 KB = 116 MB (L = 7), of
+      // which only ~60 MB stay in L2 -- the rest makes a round trip through HBM (0.95 GB per 200 k rows, measured)
+      // and the reverse stages wait for it.  Half of the CTAs (odd SM id: the two SMs of a TPC differ) therefore
+      // start half a tile period late: one half of the chip is writing tape while the other half consumes it, the
+      // live total stays at its 55 MB mean and the kernel time per wave drops by ~12 % (89 vs 101 us, the time a
+      // 74-CTA launch needs per wave).  Tiles are handed out dynamically, so a late CTA simply takes fewer of them.
+      if (!fwd_only && nw.stagger_cycles > 0 && num_tiles >= nw.stagger_min_tiles) {
+        unsigned smid;
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        if (smid & 1u) {
+          const long long t0 = clock64();
+          while (clock64() - t0 < (long long)nw.stagger_cycles) __nanosleep(512);
+        }
+      }
       uint32_t it = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (uint32_t k = 0;; ++k) {
+        int tile = atomicAdd(sched, 1);
+        if (tile >= num_tiles) tile = -1;
+        tile_slot[k & 1] = tile;
+        mbar_arrive(bar_tile + 8 * (k & 1));   // release: the slot is visible to whoever sees the phase complete
+        if (tile < 0) break;
         for (int g = 0; g < n_gemm; ++g) {
           // forward GEMM g -> layer g+1, orientation 0 ; backward -> layer 2L-g, orientation 1
           int l = g < L ? g : (2 * L - 1 - g);  // 0-based hidden layer index
           int o = g < L ? 0 : 1;
           const unsigned char* img = blob + img0 + (size_t)(l * 2 + o) * image_bytes();
           for (int i = 0; i < NKB; ++i, ++it) {
-            int kb = kb_order(i);
             uint32_t s = it % STAGES;
             uint32_t ph = (it / STAGES) & 1;
             mbar_wait(bar_w_empty + 8 * s, ph ^ 1);
             mbar_expect_tx(bar_w_full + 8 * s, STAGE_BYTES);
-            tma_bulk_g2s(sbase + SM_STAGE + s * STAGE_BYTES, img + (size_t)kb * STAGE_BYTES, STAGE_BYTES,
+            tma_bulk_g2s(sbase + SM_STAGE + s * STAGE_BYTES, img + (size_t)i * STAGE_BYTES, STAGE_BYTES,
                          bar_w_full + 8 * s);
           }
-          // The cos factors the reverse stage after next will read were written up to 2(L-1) stages ago and may
+          // The tape words the reverse stage after next will read were written up to 2(L-1) stages ago and may
           // have left L2: ask the TMA unit to pull that layer's whole 128 KB slab ([col4][row] float4, contiguous)
           // back in -- one instruction from this otherwise idle thread instead of 16 prefetches per epilogue thread.
           // (GEMM g's weights are all requested: the epilogue is about to start stage g - 1 or g.)
@@ -256,30 +286,35 @@ siren_sdf_grad_kernel(const float* __restrict__ x, int n_max, const int* __restr
       uint32_t it = 0;
       uint32_t G = 0;  // global GEMM counter of this CTA
       // dbg_gemm == -2: cycle stamps of the first two tiles of CTA 0 (bring-up / tuning aid)
-      long long* tstamp = (dbg && dbg_gemm == -2 && blockIdx.x == 0) ? reinterpret_cast<long long*>(dbg) : nullptr;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      long long* tstamp = nullptr;
+      if constexpr (DBG) tstamp = (dbg && dbg_gemm == -2 && blockIdx.x == 0) ? reinterpret_cast<long long*>(dbg) : nullptr;
+      for (uint32_t k = 0;; ++k) {
+        mbar_wait(bar_tile + 8 * (k & 1), (k >> 1) & 1);
+        if (tile_slot[k & 1] < 0) break;
         for (int g = 0; g < n_gemm; ++g, ++G) {
           const uint32_t d_tmem = tmem_base + (G & 1) * H;
           long long wa = 0, ww = 0, t_first = 0;
           for (int i = 0; i < NKB; ++i, ++it) {
-            int kb = kb_order(i);
             uint32_t s = it % STAGES;
             uint32_t ph = (it / STAGES) & 1;
             // weights first: they are normally in place already, and a completed try_wait still costs ~180
             // cycles -- this keeps it off the path between the epilogue's hand-off and the MMA issue
-            long long t0 = tstamp ? clock64() : 0;
+            long long t0 = 0, t1 = 0;
+            if constexpr (DBG) t0 = tstamp ? clock64() : 0;
             mbar_wait(bar_w_full + 8 * s, ph);
-            long long t1 = tstamp ? clock64() : 0;
-            mbar_wait(bar_a_ready + 8 * kb, G & 1);
-            if (tstamp) {
-              long long t2 = clock64();
-              ww += t1 - t0;
-              wa += t2 - t1;
-              if (i == 0) t_first = t2;
+            if constexpr (DBG) t1 = tstamp ? clock64() : 0;
+            mbar_wait(bar_a_ready + 8 * i, G & 1);
+            if constexpr (DBG) {
+              if (tstamp) {
+                long long t2 = clock64();
+                ww += t1 - t0;
+                wa += t2 - t1;
+                if (i == 0) t_first = t2;
+              }
             }
             tc_fence_after();
-            const uint32_t a_hi = sbase + SM_A_HI + kb * (KB / 8) * A_LBO;
-            const uint32_t a_lo = sbase + SM_A_LO + kb * (KB / 8) * A_LBO;
+            const uint32_t a_hi = sbase + SM_A_HI + i * (KB / 8) * A_LBO;
+            const uint32_t a_lo = sbase + SM_A_LO + i * (KB / 8) * A_LBO;
             const uint32_t b_hi = sbase + SM_STAGE + s * STAGE_BYTES;
             const uint32_t b_lo = b_hi + STAGE_PART;
 #pragma unroll
@@ -295,11 +330,13 @@ siren_sdf_grad_kernel(const float* __restrict__ x, int n_max, const int* __restr
             tc_commit(bar_w_empty + 8 * s);  // stage reusable once these MMAs have read it
           }
           tc_commit(bar_acc_full + 8 * (G & 1));  // accumulator of GEMM G complete
-          if (tstamp && G < 2u * n_gemm) {
-            tstamp[G * 8 + 3] = t_first;
-            tstamp[G * 8 + 4] = clock64();
-            tstamp[G * 8 + 5] = ww;
-            tstamp[G * 8 + 6] = wa;
+          if constexpr (DBG) {
+            if (tstamp && G < 2u * n_gemm) {
+              tstamp[G * 8 + 3] = t_first;
+              tstamp[G * 8 + 4] = clock64();
+              tstamp[G * 8 + 5] = ww;
+              tstamp[G * 8 + 6] = wa;
+            }
           }
         }
       }
@@ -326,20 +363,18 @@ siren_sdf_grad_kernel(const float* __restrict__ x, int n_max, const int* __restr
     // per-CTA stash: [(l-1)][col4 (64)][row (128)] float4, l = 1..L-1
     float4* stash = reinterpret_cast<float4*>(scratch) + (size_t)blockIdx.x * (size_t)(L > 1 ? L - 1 : 1) * 64 * TM;
     uint32_t G = 0;
-    uint64_t pol_first;
-    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol_first));
 
     // publish this thread's K-chunk of k-block kb: generic-proxy stores -> async proxy, one arrive per warp
     auto publish = [&](int kb, const float2* o, long long* kst = nullptr) {
       const uint32_t off = (uint32_t)(kb * 4) * A_LBO + a_thr;
       store_chunk(sbase + SM_A_HI + off, sbase + SM_A_LO + off, o);
-      if (kst) kst[2] = clock64();
+      ISO_STAMP(kst, 2);
       tc_fence_before();
       fence_proxy_async();
-      if (kst) kst[3] = clock64();
+      ISO_STAMP(kst, 3);
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_a_ready + 8 * kb);
-      if (kst) kst[4] = clock64();
+      ISO_STAMP(kst, 4);
     };
 
     // append the still-active rows of this tile to the next active list: in-tile order, one reservation per
@@ -364,7 +399,10 @@ siren_sdf_grad_kernel(const float* __restrict__ x, int n_max, const int* __restr
       }
     };
 
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    for (uint32_t kt = 0;; ++kt) {
+      mbar_wait(bar_tile + 8 * (kt & 1), (kt >> 1) & 1);
+      const int tile = tile_slot[kt & 1];
+      if (tile < 0) break;
       const int grow = tile * TM + row;
       float px = 0.f, py = 0.f, pz = 0.f;
       if (grow < n) {
@@ -383,9 +421,9 @@ siren_sdf_grad_kernel(const float* __restrict__ x, int n_max, const int* __restr
           const float2 th = __ffma2_rn(make_float2(wb.x, wb.y), pz2,
                                        __ffma2_rn(make_float2(wa.z, wa.w), py2,
                                                   __ffma2_rn(make_float2(wa.x, wa.y), px2, make_float2(wb.z, wb.w))));
-          float2 sn, cp;
+          float2 sn, r;
           uint32_t sx, sy;
-          sincos2(th, sn, cp, sx, sy);
+          sin_red2(th, sn, r, sx, sy);
           o[pr] = __fmul2_rn(sn, bc2(A_SCALE));
         }
         publish(kb, o);
@@ -393,7 +431,7 @@ siren_sdf_grad_kernel(const float* __restrict__ x, int n_max, const int* __restr
 
       // operands of the NEXT stage's first k-blocks, requested one stage ahead so that their L2 latency is not
       // between an accumulator becoming ready and the first k-block of the next A operand:
-      float4 pf0, pf1, pf2, pf3;   // forward: biases of k-block 0 (pf0, pf1); reverse: cos factors of k-blocks 0, 1
+      float4 pf0, pf1, pf2, pf3;   // forward: biases of k-block 0 (pf0, pf1); reverse: tape words of k-blocks 0, 1
       pf0 = pf1 = pf2 = pf3 = make_float4(0.f, 0.f, 0.f, 0.f);
       if (L > 0) {
         const float4* bw4n = reinterpret_cast<const float4*>(biasw) + cslice * 2;   // layer 1
@@ -405,84 +443,100 @@ siren_sdf_grad_kernel(const float* __restrict__ x, int n_max, const int* __restr
       float sdf_row = 0.f;        // this row's sdf (slice-0 thread), kept for the fused Newton step
       for (int g = 0; g < n_gemm; ++g, ++G) {
         const uint32_t buf = G & 1;
-        long long* tstamp =
-            (dbg && dbg_gemm == -2 && blockIdx.x == 0 && threadIdx.x == 0 && G < 2u * n_gemm)
-                ? reinterpret_cast<long long*>(dbg) + G * 8 : nullptr;
-        if (tstamp) tstamp[7] = clock64();
-        // dbg_gemm == -2: per-k-block stamps of thread 0 in stages G = 1 (forward) and G = 8 (reverse)
-        long long* kbase = (tstamp && (G == 1u || G == 8u)) ? reinterpret_cast<long long*>(dbg) + 512 + (G == 1u ? 0 : 64)
-                                                           : nullptr;
+        long long* tstamp = nullptr;   // stage stamps (thread 0)
+        long long* kbase = nullptr;    // per-k-block stamps of thread 0 in stages G = 1 (forward) and G = 8 (reverse)
+        long long* wst = nullptr;      // per-warp stamps (lane 0) in the same two stages
+        if constexpr (DBG) {
+          const bool on = dbg && dbg_gemm == -2 && blockIdx.x == 0 && G < 2u * n_gemm;
+          long long* d64 = reinterpret_cast<long long*>(dbg);
+          if (on && threadIdx.x == 0) tstamp = d64 + G * 8;
+          if (tstamp && (G == 1u || G == 8u)) kbase = d64 + 512 + (G == 1u ? 0 : 64);
+          if (on && lane == 0 && (G == 1u || G == 8u)) wst = d64 + 1024 + (G == 1u ? 0 : 64) + warp * 4;
+        }
+        ISO_STAMP(tstamp, 7);
         mbar_wait(bar_acc_full + 8 * buf, (G >> 1) & 1);
         tc_fence_after();
-        if (tstamp) tstamp[0] = clock64();
+        ISO_STAMP(tstamp, 0);
+        ISO_STAMP(wst, 0);
         const uint32_t tacc = tl + buf * H;
         const bool fwd = g < L;
         const int l = fwd ? g + 1 : 2 * L - g;  // 1-based hidden layer this GEMM belongs to
         const float wsi = shdr[l - 1];
-        uint32_t rn[8];                    // next k-block's accumulator slice, loaded ahead
+        // accumulator slices of consecutive k-blocks alternate between two register sets, each loaded one k-block
+        // ahead of its use (the loops below are unrolled in pairs: no register-to-register copies)
+        uint32_t rn[8], rm[8];
         tmem_ld8_issue(tacc, rn);
-        if (kbase) kbase[15] = clock64();   // after the prefetch block
-        if (dbg && blockIdx.x == 0 && (int)G == dbg_gemm) {
-          // raw accumulator dump (unscaled), [128][256]
+        if constexpr (DBG) {
+          if (dbg && blockIdx.x == 0 && kt == 0 && (int)G == dbg_gemm) {
+            // raw accumulator dump (unscaled), [128][256]
+            tmem_ld_wait(rn);
 #pragma unroll 1
-          for (int kb = 0; kb < NKB; ++kb) {
-            uint32_t r[8];
-            tmem_ld8_issue(tacc + kb * KB, r);
-            tmem_ld_wait(r);
+            for (int kb = 0; kb < NKB; ++kb) {
+              uint32_t r[8];
+              tmem_ld8_issue(tacc + kb * KB, r);
+              tmem_ld_wait(r);
 #pragma unroll
-            for (int i = 0; i < 8; ++i) dbg[(size_t)row * H + kb * KB + cslice * 8 + i] = __uint_as_float(r[i]);
+              for (int i = 0; i < 8; ++i) dbg[(size_t)row * H + kb * KB + cslice * 8 + i] = __uint_as_float(r[i]);
+            }
+            tmem_ld8_issue(tacc, rn);
           }
         }
 
         if (fwd && l < L) {
-          // ---- E_f(l): h_l = sin(w z_l) -> A ; stash c_l = w cos(w z_l) ----
+          // ---- E_f(l): h_l = sin(w z_l) -> A ; tape_l = reduced argument + parity of w z_l ----
           const float2 sc2 = bc2(wsi * A_SCALE_INV * omega);
-          float4* st = stash + (size_t)(l - 1) * 64 * TM + row;
+          float4* st = stash + (size_t)(l - 1) * 64 * TM + row + (size_t)(cslice * 2) * TM;
           const float4* bw4 = reinterpret_cast<const float4*>(biasw + (l - 1) * H) + cslice * 2;
-          float4 bwn0 = pf0, bwn1 = pf1;   // biases one k-block ahead (k-block 0: requested during the previous stage)
-#pragma unroll 1
-          for (int kb = 0; kb < NKB; ++kb) {
-            long long* kst = kbase ? kbase + kb * 8 : nullptr;
-            if (kst) kst[0] = clock64();
-            tmem_ld_wait(rn);
-            if (kst) kst[1] = clock64();
-            const float2 v[4] = {make_float2(__uint_as_float(rn[0]), __uint_as_float(rn[1])),
-                                 make_float2(__uint_as_float(rn[2]), __uint_as_float(rn[3])),
-                                 make_float2(__uint_as_float(rn[4]), __uint_as_float(rn[5])),
-                                 make_float2(__uint_as_float(rn[6]), __uint_as_float(rn[7]))};
-            if (kb + 1 < NKB) tmem_ld8_issue(tacc + (kb + 1) * KB, rn);
-            const float2 bb[4] = {make_float2(bwn0.x, bwn0.y), make_float2(bwn0.z, bwn0.w),
-                                  make_float2(bwn1.x, bwn1.y), make_float2(bwn1.z, bwn1.w)};
-            float2 o[4], cc[4];
+          // one k-block: cur = this k-block's accumulator slice (in flight), nxt = the other register set;
+          // (b0, b1) = this k-block's biases, (nb0, nb1) receive the next k-block's (layer l + 1's first at the end)
+          auto fwd_block = [&](const int kb, uint32_t(&cur)[8], uint32_t(&nxt)[8], const float4& b0, const float4& b1,
+                               float4& nb0, float4& nb1) {
+            long long* kst = nullptr;
+            if constexpr (DBG) kst = kbase ? kbase + kb * 8 : nullptr;
+            ISO_STAMP(kst, 0);
+            tmem_ld_wait(cur);
+            ISO_STAMP(kst, 1);
+            if (kb + 1 < NKB) tmem_ld8_issue(tacc + (kb + 1) * KB, nxt);
+            const float2 bb[4] = {make_float2(b0.x, b0.y), make_float2(b0.z, b0.w), make_float2(b1.x, b1.y),
+                                  make_float2(b1.z, b1.w)};
+            float2 o[4];
+            float tw[8];
 #pragma unroll
             for (int pr = 0; pr < 4; ++pr) {
-              float2 sn, cp;
+              const float2 v = make_float2(__uint_as_float(cur[2 * pr]), __uint_as_float(cur[2 * pr + 1]));
+              float2 sn, r;
               uint32_t sx, sy;
-              sincos2(__ffma2_rn(v[pr], sc2, bb[pr]), sn, cp, sx, sy);
+              sin_red2(__ffma2_rn(v, sc2, bb[pr]), sn, r, sx, sy);
               o[pr] = __fmul2_rn(sn, bc2(A_SCALE));
-              cc[pr] = __fmul2_rn(cp, signed_scale(omega, sx, sy));
+              tw[2 * pr] = tape_word(r.x, sx);
+              tw[2 * pr + 1] = tape_word(r.y, sy);
             }
             publish(kb, o, kst);
+            if (wst && (kb == 0 || kb == NKB - 1)) wst[kb == 0 ? 1 : 2] = clock64();
             // global traffic right after the hand-off fence (which waits for everything in flight)
             if (!fwd_only) {
-              const int col4 = kb * 8 + cslice * 2;
-              if (l <= nw.spill) {
-                st_f4_policy(st + (size_t)col4 * TM, make_float4(cc[0].x, cc[0].y, cc[1].x, cc[1].y), pol_first);
-                st_f4_policy(st + (size_t)(col4 + 1) * TM, make_float4(cc[2].x, cc[2].y, cc[3].x, cc[3].y), pol_first);
-              } else {
-                st[(size_t)col4 * TM] = make_float4(cc[0].x, cc[0].y, cc[1].x, cc[1].y);
-                st[(size_t)(col4 + 1) * TM] = make_float4(cc[2].x, cc[2].y, cc[3].x, cc[3].y);
-              }
+              float4* dst = st + (size_t)(kb * 8) * TM;
+              dst[0] = make_float4(tw[0], tw[1], tw[2], tw[3]);
+              dst[TM] = make_float4(tw[4], tw[5], tw[6], tw[7]);
             }
             if (kb + 1 < NKB) {
-              bwn0 = __ldg(bw4 + (kb + 1) * 8);
-              bwn1 = __ldg(bw4 + (kb + 1) * 8 + 1);
+              nb0 = __ldg(bw4 + (kb + 1) * 8);
+              nb1 = __ldg(bw4 + (kb + 1) * 8 + 1);
             } else {   // k-block 0 of the next layer (l + 1 <= L exists: this branch is l < L)
-              pf0 = ldnc_now(bw4 + H / 4);
-              pf1 = ldnc_now(bw4 + H / 4 + 1);
+              nb0 = ldnc_now(bw4 + H / 4);
+              nb1 = ldnc_now(bw4 + H / 4 + 1);
             }
-            if (kst) kst[5] = clock64();
+            ISO_STAMP(kst, 5);
+          };
+          float4 ba0 = pf0, ba1 = pf1, bb0, bb1;
+#pragma unroll 1
+          for (int kb = 0; kb < NKB; kb += 2) {
+            fwd_block(kb, rn, rm, ba0, ba1, bb0, bb1);
+            fwd_block(kb + 1, rm, rn, bb0, bb1, ba0, ba1);
           }
+          pf0 = ba0;
+          pf1 = ba1;
+          pf2 = pf3 = make_float4(0.f, 0.f, 0.f, 0.f);   // dead here: do not carry them through the loop above
         } else if (fwd) {
           // ---- E_f(L): sdf = h_L . w_last + b_last ; A = gl_scale * w_last * c_L ----
           const float2 sc2 = bc2(wsi * A_SCALE_INV * omega);
@@ -490,14 +544,9 @@ siren_sdf_grad_kernel(const float* __restrict__ x, int n_max, const int* __restr
           const float4* bw4 = reinterpret_cast<const float4*>(biasw + (l - 1) * H) + cslice * 2;
           float2 acc2 = bc2(0.f);
           float mloc = 0.f;
-#pragma unroll 1
-          for (int kb = 0; kb < NKB; ++kb) {
-            tmem_ld_wait(rn);
-            const float2 v[4] = {make_float2(__uint_as_float(rn[0]), __uint_as_float(rn[1])),
-                                 make_float2(__uint_as_float(rn[2]), __uint_as_float(rn[3])),
-                                 make_float2(__uint_as_float(rn[4]), __uint_as_float(rn[5])),
-                                 make_float2(__uint_as_float(rn[6]), __uint_as_float(rn[7]))};
-            if (kb + 1 < NKB) tmem_ld8_issue(tacc + (kb + 1) * KB, rn);
+          auto last_block = [&](const int kb, uint32_t(&cur)[8], uint32_t(&nxt)[8]) {
+            tmem_ld_wait(cur);
+            if (kb + 1 < NKB) tmem_ld8_issue(tacc + (kb + 1) * KB, nxt);
             const float4 b0 = kb ? __ldg(bw4 + kb * 8) : pf0, b1 = kb ? __ldg(bw4 + kb * 8 + 1) : pf1;
             const float4 w0 = __ldg(w_last4 + kb * 8), w1 = __ldg(w_last4 + kb * 8 + 1);
             const float2 bb[4] = {make_float2(b0.x, b0.y), make_float2(b0.z, b0.w), make_float2(b1.x, b1.y),
@@ -507,16 +556,24 @@ siren_sdf_grad_kernel(const float* __restrict__ x, int n_max, const int* __restr
             float2 o[4];
 #pragma unroll
             for (int pr = 0; pr < 4; ++pr) {
-              float2 sn, cp;
+              const float2 v = make_float2(__uint_as_float(cur[2 * pr]), __uint_as_float(cur[2 * pr + 1]));
+              float2 sn, r;
               uint32_t sx, sy;
-              sincos2(__ffma2_rn(v[pr], sc2, bb[pr]), sn, cp, sx, sy);
+              sin_red2(__ffma2_rn(v, sc2, bb[pr]), sn, r, sx, sy);
               acc2 = __ffma2_rn(sn, ww[pr], acc2);
-              o[pr] = __fmul2_rn(__fmul2_rn(cp, signed_scale(gls, sx, sy)), ww[pr]);
-              mloc = fmaxf(mloc, fmaxf(fabsf(o[pr].x), fabsf(o[pr].y)));
+              if (!fwd_only) {
+                o[pr] = __fmul2_rn(__fmul2_rn(cos_of_reduced(r), signed_scale(gls, sx, sy)), ww[pr]);
+                mloc = fmaxf(mloc, fmaxf(fabsf(o[pr].x), fabsf(o[pr].y)));
+              }
             }
             if (!fwd_only) publish(kb, o);   // forward-only: no reverse GEMM follows, the next A is the next tile's
+          };
+#pragma unroll 1
+          for (int kb = 0; kb < NKB; kb += 2) {
+            last_block(kb, rn, rm);
+            last_block(kb + 1, rm, rn);
           }
-          if (!fwd_only && L > 1) {   // cos factors of k-blocks 0 / 1 of the first reverse stage (layer L - 1)
+          if (!fwd_only && L > 1) {   // tape words of k-blocks 0 / 1 of the first reverse stage (layer L - 1)
             const float4* stn = stash + (size_t)(L - 2) * 64 * TM + row + (size_t)(cslice * 2) * TM;
             pf0 = ldcg_now(stn); pf1 = ldcg_now(stn + TM);
             pf2 = ldcg_now(stn + (size_t)8 * TM); pf3 = ldcg_now(stn + (size_t)9 * TM);
@@ -572,7 +629,7 @@ siren_sdf_grad_kernel(const float* __restrict__ x, int n_max, const int* __restr
             append_active(still, p, nx, ny, nz);
           }
         } else if (l > 1) {
-          // ---- E_b(l): g_{l-1} = acc / scales ; gp_{l-1} = g_{l-1} * c_{l-1} -> A (row-scaled) ----
+          // ---- E_b(l): g_{l-1} = acc / scales ; gp_{l-1} = g_{l-1} * w cos(w z_{l-1}) -> A (row-scaled) ----
           const float sc = wsi * row_scale_inv;
           // Per-row scale of the next A operand (gp_{l-1}) WITHOUT a pass over the accumulator: the rows written
           // one stage ago had the measured maximum `row_max` (scaled), so max_j |g_{l-1,j}| |omega| <=
@@ -582,47 +639,49 @@ siren_sdf_grad_kernel(const float* __restrict__ x, int n_max, const int* __restr
           // the next stage re-centres on the maximum it measures itself -- the slack does not accumulate.
           const float new_scale = pow2_scale_for(row_max * row_scale_inv * shdr[HDR_GAIN + l - 1]);
           float mloc = 0.f;
-          if (kbase) { kbase[23] = clock64(); kbase[6] = (long long)__float_as_int(new_scale); }
-          const float2 scs2 = bc2(sc * new_scale);
+          const float2 scs2 = bc2(sc * new_scale * omega);   // the tape holds cos without its factor omega
           const float4* st = stash + (size_t)(l - 2) * 64 * TM + row + (size_t)(cslice * 2) * TM;
-          // cos factors: two k-blocks in flight (an L2 hit is ~1 k-block of this loop away, a miss more); those of
-          // k-blocks 0 and 1 were requested at the end of the previous stage
-          float4 c0 = pf0, c1 = pf1, d0 = pf2, d1 = pf3;
-          if (kbase) { kbase[7] = clock64(); kbase[14] = (long long)__float_as_int(c0.x + d1.w); kbase[31] = clock64(); }
-#pragma unroll 2
-          for (int kb = 0; kb < NKB; ++kb) {
-            long long* kst = kbase ? kbase + kb * 8 : nullptr;
-            if (kst) kst[0] = clock64();
-            tmem_ld_wait(rn);
-            if (kst) kst[1] = clock64();
+          // one k-block: (t0, t1) = its 8 tape words, replaced at the end by those of k-block kb + 2 (an L2 hit is
+          // ~1 k-block of this loop away, a miss more); those of k-blocks 0 and 1 were requested one stage ago
+          auto rev_block = [&](const int kb, uint32_t(&cur)[8], uint32_t(&nxt)[8], float4& t0, float4& t1) {
+            long long* kst = nullptr;
+            if constexpr (DBG) kst = kbase ? kbase + kb * 8 : nullptr;
+            ISO_STAMP(kst, 0);
+            tmem_ld_wait(cur);
+            ISO_STAMP(kst, 1);
+            if (kb + 1 < NKB) tmem_ld8_issue(tacc + (kb + 1) * KB, nxt);
             float2 o[4];
-            o[0] = __fmul2_rn(__fmul2_rn(make_float2(__uint_as_float(rn[0]), __uint_as_float(rn[1])), scs2),
-                              make_float2(c0.x, c0.y));
-            o[1] = __fmul2_rn(__fmul2_rn(make_float2(__uint_as_float(rn[2]), __uint_as_float(rn[3])), scs2),
-                              make_float2(c0.z, c0.w));
-            o[2] = __fmul2_rn(__fmul2_rn(make_float2(__uint_as_float(rn[4]), __uint_as_float(rn[5])), scs2),
-                              make_float2(c1.x, c1.y));
-            o[3] = __fmul2_rn(__fmul2_rn(make_float2(__uint_as_float(rn[6]), __uint_as_float(rn[7])), scs2),
-                              make_float2(c1.z, c1.w));
+            o[0] = __fmul2_rn(__fmul2_rn(make_float2(__uint_as_float(cur[0]), __uint_as_float(cur[1])), scs2),
+                              cos_of_tape(t0.x, t0.y));
+            o[1] = __fmul2_rn(__fmul2_rn(make_float2(__uint_as_float(cur[2]), __uint_as_float(cur[3])), scs2),
+                              cos_of_tape(t0.z, t0.w));
+            o[2] = __fmul2_rn(__fmul2_rn(make_float2(__uint_as_float(cur[4]), __uint_as_float(cur[5])), scs2),
+                              cos_of_tape(t1.x, t1.y));
+            o[3] = __fmul2_rn(__fmul2_rn(make_float2(__uint_as_float(cur[6]), __uint_as_float(cur[7])), scs2),
+                              cos_of_tape(t1.z, t1.w));
             mloc = fmaxf(fmaxf(mloc, fmaxf(fabsf(o[0].x), fabsf(o[0].y))), fmaxf(fabsf(o[1].x), fabsf(o[1].y)));
             mloc = fmaxf(fmaxf(mloc, fmaxf(fabsf(o[2].x), fabsf(o[2].y))), fmaxf(fabsf(o[3].x), fabsf(o[3].y)));
-            if (kb + 1 < NKB) tmem_ld8_issue(tacc + (kb + 1) * KB, rn);
             publish(kb, o, kst);
-            // this k-block's cos lines are dead now (the next tile rewrites them in full before reading):
+            if (wst && (kb == 0 || kb == NKB - 1)) wst[kb == 0 ? 1 : 2] = clock64();
+            // this k-block's tape lines are dead now (the next tile rewrites them in full before reading):
             // drop them from L2 instead of letting them be written back to HBM
             if ((lane & 7) == 0) {
               asm volatile("discard.global.L2 [%0], 128;" ::"l"(st + (size_t)(kb * 8) * TM) : "memory");
               asm volatile("discard.global.L2 [%0], 128;" ::"l"(st + (size_t)(kb * 8 + 1) * TM) : "memory");
             }
-            c0 = d0;
-            c1 = d1;
             if (kb + 2 < NKB) {   // right after the hand-off fence, two k-blocks ahead of its use
-              d0 = __ldcg(st + (size_t)((kb + 2) * 8) * TM);
-              d1 = __ldcg(st + (size_t)((kb + 2) * 8 + 1) * TM);
+              t0 = __ldcg(st + (size_t)((kb + 2) * 8) * TM);
+              t1 = __ldcg(st + (size_t)((kb + 2) * 8 + 1) * TM);
             }
-            if (kst) kst[5] = clock64();
+            ISO_STAMP(kst, 5);
+          };
+          float4 e0 = pf0, e1 = pf1, f0 = pf2, f1 = pf3;
+#pragma unroll 1
+          for (int kb = 0; kb < NKB; kb += 2) {
+            rev_block(kb, rn, rm, e0, e1);
+            rev_block(kb + 1, rm, rn, f0, f1);
           }
-          if (l > 2) {   // k-blocks 0 / 1 of the next reverse stage (layer l - 2's cos factors)
+          if (l > 2) {   // k-blocks 0 / 1 of the next reverse stage (layer l - 2's tape)
             const float4* stn = stash + (size_t)(l - 3) * 64 * TM + row + (size_t)(cslice * 2) * TM;
             pf0 = ldcg_now(stn); pf1 = ldcg_now(stn + TM);
             pf2 = ldcg_now(stn + (size_t)8 * TM); pf3 = ldcg_now(stn + (size_t)9 * TM);
@@ -637,27 +696,28 @@ siren_sdf_grad_kernel(const float* __restrict__ x, int n_max, const int* __restr
           // (the w0 table holds omega_0-scaled rows, so gp_0 . W_0 = sum (g_0 cos) * (omega_0 W_0))
           const float sc = wsi * row_scale_inv;
           float2 gx2 = bc2(0.f), gy2 = bc2(0.f), gz2 = bc2(0.f);
-#pragma unroll 1
-          for (int kb = 0; kb < NKB; ++kb) {
-            tmem_ld_wait(rn);
-            const float2 v[4] = {make_float2(__uint_as_float(rn[0]), __uint_as_float(rn[1])),
-                                 make_float2(__uint_as_float(rn[2]), __uint_as_float(rn[3])),
-                                 make_float2(__uint_as_float(rn[4]), __uint_as_float(rn[5])),
-                                 make_float2(__uint_as_float(rn[6]), __uint_as_float(rn[7]))};
-            if (kb + 1 < NKB) tmem_ld8_issue(tacc + (kb + 1) * KB, rn);
+          auto first_block = [&](const int kb, uint32_t(&cur)[8], uint32_t(&nxt)[8]) {
+            tmem_ld_wait(cur);
+            if (kb + 1 < NKB) tmem_ld8_issue(tacc + (kb + 1) * KB, nxt);
 #pragma unroll
             for (int pr = 0; pr < 4; ++pr) {
+              const float2 v = make_float2(__uint_as_float(cur[2 * pr]), __uint_as_float(cur[2 * pr + 1]));
               const float4 wa = __ldg(w0p + kb * 32 + pr * 2), wb = __ldg(w0p + kb * 32 + pr * 2 + 1);
               const float2 wx = make_float2(wa.x, wa.y), wy = make_float2(wa.z, wa.w), wz = make_float2(wb.x, wb.y);
               const float2 th = __ffma2_rn(wz, pz2, __ffma2_rn(wy, py2, __ffma2_rn(wx, px2, make_float2(wb.z, wb.w))));
-              float2 sn, cp;
+              float2 r;
               uint32_t sx, sy;
-              sincos2(th, sn, cp, sx, sy);
-              const float2 gp = __fmul2_rn(__fmul2_rn(v[pr], signed_scale(sc, sx, sy)), cp);
+              red2(th, r, sx, sy);   // the layer-0 cosine is recomputed, not taped: its argument costs 3 FFMA2
+              const float2 gp = __fmul2_rn(__fmul2_rn(v, signed_scale(sc, sx, sy)), cos_of_reduced(r));
               gx2 = __ffma2_rn(gp, wx, gx2);
               gy2 = __ffma2_rn(gp, wy, gy2);
               gz2 = __ffma2_rn(gp, wz, gz2);
             }
+          };
+#pragma unroll 1
+          for (int kb = 0; kb < NKB; kb += 2) {
+            first_block(kb, rn, rm);
+            first_block(kb + 1, rm, rn);
           }
           const float gx = gx2.x + gx2.y, gy = gy2.x + gy2.y, gz = gz2.x + gz2.y;
           tc_fence_before();
@@ -718,7 +778,7 @@ siren_sdf_grad_kernel(const float* __restrict__ x, int n_max, const int* __restr
             append_active(still, p, nx, ny, nz);
           }
         }
-        if (tstamp) tstamp[2] = clock64();
+        ISO_STAMP(tstamp, 2);
       }
     }
   }
@@ -728,6 +788,15 @@ siren_sdf_grad_kernel(const float* __restrict__ x, int n_max, const int* __restr
   if (warp == N_EPI_WARPS + 1) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+  }
+  // every CTA has taken its last (out-of-range) ticket before it gets here: the last one re-arms the slot
+  if (threadIdx.x == 0) {
+    __threadfence();
+    if (atomicAdd(sched + 1, 1) == (int)gridDim.x - 1) {
+      sched[0] = 0;
+      sched[1] = 0;
+      __threadfence();
+    }
   }
 }
 
@@ -773,13 +842,15 @@ int isob200_siren_pack(const float* w0, const float* b0, const float* w_hidden, 
 }
 
 static int g_siren_max_ctas = kNumSMs;   // tuning knob: persistent CTAs per launch (<= one per SM)
-static int g_siren_spill = 0;            // tuning knob: tape layers stored with the L2 evict-first policy
-int isob200_siren_set_spill_layers(int n) {
-  const int old = g_siren_spill;
-  g_siren_spill = n < 0 ? 0 : n;
+static int g_siren_stagger = 0;          // tuning knob: start delay of the CTAs on odd SMs in cycles (-1 = half a tile)
+static int g_siren_stagger_min_tiles = 3 * kNumSMs;   // ... for launches with at least this many tiles
+static unsigned g_siren_launch_seq = 0;
+int isob200_siren_set_stagger(int cycles, int min_tiles) {
+  const int old = g_siren_stagger;
+  g_siren_stagger = cycles;
+  if (min_tiles > 0) g_siren_stagger_min_tiles = min_tiles;
   return old;
 }
-
 int isob200_siren_set_max_ctas(int n) {
   const int old = g_siren_max_ctas;
   g_siren_max_ctas = n < 1 ? 1 : (n > kNumSMs ? kNumSMs : n);
@@ -803,16 +874,24 @@ static int launch_siren(const float* x, int n_max, const int* n_dev, const void*
     int dev = 0;
     ISO_CUDA(cudaGetDevice(&dev));
     if (dev < 0 || dev >= 64 || !attr_done[dev]) {
-      ISO_CUDA(cudaFuncSetAttribute(siren_sdf_grad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+      ISO_CUDA(cudaFuncSetAttribute(siren_sdf_grad_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+      ISO_CUDA(cudaFuncSetAttribute(siren_sdf_grad_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
       if (dev >= 0 && dev < 64) attr_done[dev] = true;
     }
   }
   int tiles = (n_max + TM - 1) / TM;
   int grid = tiles < g_siren_max_ctas ? tiles : g_siren_max_ctas;
   Newton nwk = nw;
-  nwk.spill = g_siren_spill;
-  siren_sdf_grad_kernel<<<grid, THREADS, SMEM_BYTES, (cudaStream_t)stream>>>(
-      x, n_max, n_dev, (const unsigned char*)blob, n_hidden, sdf, grad, (float*)scratch, dbg, dbg_gemm, nwk);
+  nwk.sched_slot = (int)(g_siren_launch_seq++ % SCHED_SLOTS);
+  // half a tile period: a tile is 2 n_hidden stages of ~10.5 k cycles plus ~20 k for the two SIMT-only ends
+  nwk.stagger_cycles = g_siren_stagger >= 0 ? g_siren_stagger : (2 * n_hidden * 10500 + 20000) / 2;
+  nwk.stagger_min_tiles = g_siren_stagger_min_tiles;
+  if (dbg)
+    siren_sdf_grad_kernel<true><<<grid, THREADS, SMEM_BYTES, (cudaStream_t)stream>>>(
+        x, n_max, n_dev, (const unsigned char*)blob, n_hidden, sdf, grad, (float*)scratch, dbg, dbg_gemm, nwk);
+  else
+    siren_sdf_grad_kernel<false><<<grid, THREADS, SMEM_BYTES, (cudaStream_t)stream>>>(
+        x, n_max, n_dev, (const unsigned char*)blob, n_hidden, sdf, grad, (float*)scratch, nullptr, -1, nwk);
   ISO_CHECK_LAUNCH("siren_sdf_grad_kernel");
   return ISOB200_OK;
 }

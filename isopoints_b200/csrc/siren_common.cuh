@@ -54,11 +54,12 @@ constexpr int SM_A_LO = A_PART;
 constexpr int SM_STAGE = 2 * A_PART;                        // 131072
 constexpr int SM_XCH = SM_STAGE + STAGES * STAGE_BYTES;     // 229376: float xch[128][4]
 constexpr int SM_BAR = SM_XCH + TM * 4 * 4;                 // 231424
-// barriers: a_ready[8], acc_full[2], w_full[3], w_empty[3]  -> 16 * 8 B
-constexpr int SM_TMEM_PTR = SM_BAR + 16 * 8;
+// barriers: a_ready[8], acc_full[2], w_full[3], w_empty[3], tile[2]  -> 18 * 8 B
+constexpr int SM_TMEM_PTR = SM_BAR + 18 * 8;
 constexpr int SM_CMP = SM_TMEM_PTR + 16;                    // int cmp[8]: warp counts + reserved base
 constexpr int SM_HDR = SM_CMP + 32;                         // float hdr[64]: per-layer scales / gains (header copy)
-constexpr int SMEM_BYTES = SM_HDR + 64 * 4;                 // 231856 <= 232448
+constexpr int SM_TILE = SM_HDR + 64 * 4;                    // int tile[2]: the scheduler's hand-off slots
+constexpr int SMEM_BYTES = SM_TILE + 16;                    // 231888 <= 232448
 
 // ---- PTX helpers -----------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -160,20 +161,19 @@ constexpr uint32_t IDESC = (1u << 4) | ((uint32_t)(H >> 3) << 17) | ((uint32_t)(
 // so every elementwise step works on column PAIRS.
 __device__ __forceinline__ float2 bc2(float a) { return make_float2(a, a); }
 
-// sin and cos of two fp32 arguments, ~1 ulp absolute (1.2e-7 / 1.5e-7 measured) for |a| < 2^21 pi:
-// j = round(a / pi) with the 1.5 * 2^23 trick, three-constant Cody-Waite reduction by pi, minimax
-// polynomials on [-pi/2, pi/2] (degree 11 odd / 12 even, least-squares fit on Chebyshev nodes).
-// Returns sn = sin(a) (sign applied through the odd polynomial's argument), cp = |.|-branch cosine
-// WITHOUT its sign, and the sign bits (bit 31) so that the caller folds them into a scale factor:
-// cos(a) = cp ^ sg.
-__device__ __forceinline__ void sincos2(float2 a, float2& sn, float2& cp, uint32_t& sgx, uint32_t& sgy) {
+// sin of two fp32 arguments, ~1 ulp absolute (1.2e-7 measured): j = round(a / pi) with the 1.5 * 2^23 trick,
+// two-constant Cody-Waite reduction by pi (3.140625 has 9 significant bits, so j * c1 is exact for |j| < 2^15;
+// the next term of pi, 5.1e-12 * j, stays below 2e-8 for |a| < 10^4 and is dropped), minimax polynomial on
+// [-pi/2, pi/2] (degree 11 odd, least-squares fit on Chebyshev nodes).  Also returns the reduced argument r
+// (a = j pi + r) and the parity of j as a sign bit (bit 31), from which the caller gets the cosine:
+// cos(a) = cos(r) ^ sg (cos_of_reduced), or stores both in one word for the reverse pass (tape_word).
+__device__ __forceinline__ void sin_red2(float2 a, float2& sn, float2& r, uint32_t& sgx, uint32_t& sgy) {
   const float2 jm = __ffma2_rn(a, bc2(0.318309886f), bc2(12582912.f));
   sgx = __float_as_uint(jm.x) << 31;
   sgy = __float_as_uint(jm.y) << 31;
   const float2 j = __fadd2_rn(jm, bc2(-12582912.f));
-  float2 r = __ffma2_rn(j, bc2(-3.140625f), a);
+  r = __ffma2_rn(j, bc2(-3.140625f), a);
   r = __ffma2_rn(j, bc2(-9.676535846665502e-4f), r);
-  r = __ffma2_rn(j, bc2(-5.126565838509123e-12f), r);
   const float2 r2 = __fmul2_rn(r, r);
   float2 t = __ffma2_rn(r2, bc2(-2.39068338458992e-08f), bc2(2.7526464236871107e-06f));
   t = __ffma2_rn(t, r2, bc2(-1.9840890308842063e-04f));
@@ -182,21 +182,32 @@ __device__ __forceinline__ void sincos2(float2 a, float2& sn, float2& cp, uint32
   t = __fmul2_rn(t, r2);
   const float2 rs = make_float2(__uint_as_float(__float_as_uint(r.x) ^ sgx), __uint_as_float(__float_as_uint(r.y) ^ sgy));
   sn = __ffma2_rn(t, rs, rs);
-#ifdef ISOB200_SIREN_POLY_COS
-  float2 u = __ffma2_rn(r2, bc2(1.9918149352093906e-09f), bc2(-2.7525521772986394e-07f));
-  u = __ffma2_rn(u, r2, bc2(2.4801065592328086e-05f));
-  u = __ffma2_rn(u, r2, bc2(-1.3888884568586946e-03f));
-  u = __ffma2_rn(u, r2, bc2(0.0416666679084301f));
-  u = __ffma2_rn(u, r2, bc2(-0.5f));
-  cp = __ffma2_rn(u, r2, bc2(1.0f));
-#else
-  // The cosine only ever multiplies back-propagated rows (the tape factor w cos(w z)); the forward value path
-  // uses the sine alone.  The epilogue is FP32-pipe bound (a packed FFMA2 holds the pipe for two cycles), so the
-  // six-term cosine polynomial moves to the special-function unit: MUFU.COS on the already reduced argument
-  // (|r| <= pi/2, where its absolute error is <= 2^-21.2), two scalar instructions per pair on an otherwise idle
-  // pipe.  Measured effect on the gradient against float64: see tests/test_gpu_siren.py.
-  cp = make_float2(__cosf(r.x), __cosf(r.y));
-#endif
+}
+// reduced argument and parity sign of a alone (no sine): for the stages that only need the cosine
+__device__ __forceinline__ void red2(float2 a, float2& r, uint32_t& sgx, uint32_t& sgy) {
+  const float2 jm = __ffma2_rn(a, bc2(0.318309886f), bc2(12582912.f));
+  sgx = __float_as_uint(jm.x) << 31;
+  sgy = __float_as_uint(jm.y) << 31;
+  const float2 j = __fadd2_rn(jm, bc2(-12582912.f));
+  r = __ffma2_rn(j, bc2(-3.140625f), a);
+  r = __ffma2_rn(j, bc2(-9.676535846665502e-4f), r);
+}
+// |cos| branch of the reduced argument (|r| <= pi/2, so the value is >= 0 up to rounding of r): MUFU.COS, absolute
+// error <= 2^-21.2 there.  The cosine only ever multiplies back-propagated rows (the tape factor w cos(w z)); the
+// forward value path uses the sine alone.  The epilogue is issue / FP32-pipe bound (a packed FFMA2 holds the pipe for
+// two cycles), so the cosine runs on the special-function unit instead of a six-term polynomial.
+__device__ __forceinline__ float2 cos_of_reduced(float2 r) { return make_float2(__cosf(r.x), __cosf(r.y)); }
+// Reverse-mode tape entry: |r| with the parity of j in the sign bit (one LOP3).  cos is even, so the reverse pass
+// takes MUFU.COS of the word as it is and xors the word's sign bit into the result: cos(a) = cos(|r|) ^ parity.
+// The cosine itself is NOT evaluated in the forward pass -- the forward epilogue paces its GEMMs, the reverse one
+// waits for them.
+__device__ __forceinline__ float tape_word(float r, uint32_t sg) {
+  return __uint_as_float((__float_as_uint(r) & 0x7fffffffu) | sg);
+}
+__device__ __forceinline__ float2 cos_of_tape(float wx, float wy) {
+  const float cx = __cosf(wx), cy = __cosf(wy);
+  return make_float2(__uint_as_float(__float_as_uint(cx) ^ (__float_as_uint(wx) & 0x80000000u)),
+                     __uint_as_float(__float_as_uint(cy) ^ (__float_as_uint(wy) & 0x80000000u)));
 }
 __device__ __forceinline__ float2 signed_scale(float sc, uint32_t sgx, uint32_t sgy) {
   return make_float2(__uint_as_float(__float_as_uint(sc) ^ sgx), __uint_as_float(__float_as_uint(sc) ^ sgy));
@@ -251,9 +262,9 @@ struct Newton {
   const float* dirs;         // (M,3) ray directions
   float* eval;               // (M) last sdf per ray
   float alpha, bound;        // step factor; radius + padding of the bounding sphere
-  // tape layers 1..spill are stored with an L2 evict-first policy: they are read last (the reverse pass
-  // walks the layers backwards), so when the live tape exceeds L2 they are the ones to send to HBM
-  int spill;
+  // tile scheduler: slot of g_tile_sched used by this launch; CTAs on odd SMs start stagger_cycles late when
+  // the launch has at least stagger_min_tiles tiles (see the producer warp)
+  int sched_slot, stagger_cycles, stagger_min_tiles;
 };
 
 // eps_denom(x, eps) of DSS/utils/mathHelper.py:14-18: (sign(x) + [x == 0]) * max(|x|, eps)

@@ -9,6 +9,43 @@ case "${1:-all}" in
     timeout 900 python -m pytest tests/test_gpu_pinned.py tests/test_gpu_dropin.py tests/test_gpu_pointops.py tests/test_gpu_offsurface.py -m gpu -q -s 2>&1 | tail -80 > gpurun_out/pytest_new.log; tail -40 gpurun_out/pytest_new.log ;;
   timeline)
     timeout 300 python scripts/siren_timeline.py > gpurun_out/siren_timeline.txt 2>&1; tail -70 gpurun_out/siren_timeline.txt ;;
+  ab)
+    # old (build/ab/libisob200_old.so) vs new library, alternating on the same box: sustained C2 step
+    for r in 1 2 3; do
+      for which in old new; do
+        if [ $which = old ]; then export ISOB200_LIB=$PWD/build/ab/libisob200_old.so; else unset ISOB200_LIB; fi
+        timeout 300 python bench.py --steps 20 --warmup 3 --no-side | python -c "import json,sys; d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print('$which', round(d['ms_per_step'],3), round(d['value']/1e6,3), round(d['config']['sdf_evaluations_per_s']/1e6,2), d['clocks']['sm_mhz'], d['kernels']['siren_project_step']['ms_per_step'])"
+      done
+    done ;;
+  siren2)
+    timeout 300 python -m pytest tests/test_gpu_siren.py tests/test_gpu_trace.py -m gpu -q -x 2>&1 | tail -3
+    ISOB200_SIREN_PAIR_HANDOFF=1 timeout 300 python -m pytest tests/test_gpu_siren.py tests/test_gpu_trace.py tests/test_gpu_pinned.py -m gpu -q -x 2>&1 | tail -3
+    timeout 300 python scripts/siren_timeline.py > gpurun_out/siren_timeline.txt 2>&1; head -24 gpurun_out/siren_timeline.txt
+    ISOB200_SIREN_PAIR_HANDOFF=1 timeout 300 python scripts/siren_timeline.py > gpurun_out/siren_timeline_pair.txt 2>&1; tail -52 gpurun_out/siren_timeline_pair.txt
+    for p in 0 1 0 1; do ISOB200_SIREN_PAIR_HANDOFF=$p timeout 300 python bench.py --steps 10 --warmup 3 --no-side | python -c "import json,sys; d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print('pair $p', d['ms_per_step'], d['value'], d['config']['sdf_evaluations_per_s'], d['clocks'])"; done ;;
+  siren)
+    timeout 600 python -m pytest tests/test_gpu_siren.py tests/test_gpu_trace.py tests/test_gpu_pinned.py tests/test_gpu_projection.py tests/test_gpu_rays.py -m gpu -q -x 2>&1 | tail -30 > gpurun_out/pytest_siren.log; tail -30 gpurun_out/pytest_siren.log
+    timeout 300 python scripts/siren_timeline.py > gpurun_out/siren_timeline.txt 2>&1; cat gpurun_out/siren_timeline.txt
+    timeout 600 ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none -k regex:siren_sdf_grad --csv --log-file gpurun_out/siren_cta_sweep_ncu.csv python scripts/siren_cta_sweep.py --once > /dev/null 2>&1
+    cut -d, -f 5,13- gpurun_out/siren_cta_sweep_ncu.csv | tail -21 ;;
+  sweep)
+    timeout 300 python scripts/siren_cta_sweep.py --stamps > gpurun_out/siren_cta_sweep.txt 2>&1
+    timeout 600 ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none -k regex:siren_sdf_grad --csv --log-file gpurun_out/siren_cta_sweep_ncu.csv python scripts/siren_cta_sweep.py --once > /dev/null 2>&1
+    cat gpurun_out/siren_cta_sweep.txt; cut -d, -f 5,13- gpurun_out/siren_cta_sweep_ncu.csv | tail -30 ;;
+  prof)
+    # r02 evidence: per-stage stamps, launch lists (C2 / C3 / C4), full captures of the dominant kernels
+    export ISO_BENCH_PREROLL=3
+    B="python bench.py --steps 1 --warmup 3 --no-side"
+    timeout 300 python scripts/siren_timeline.py > gpurun_out/siren_timeline.txt 2>&1
+    timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 3000 --csv --log-file gpurun_out/launches_c2.csv $B > gpurun_out/ncu_c2.log 2>&1
+    timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_c4.csv python bench_splat.py --steps 1 > gpurun_out/ncu_c4.log 2>&1
+    timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv --log-file gpurun_out/launches_c3.csv python bench_frnn.py --steps 1 > gpurun_out/ncu_c3.log 2>&1
+    timeout 600 ncu --set full --clock-control none --import-source on -k regex:siren_sdf_grad -s 45 -c 1 -f -o gpurun_out/prof_siren $B > gpurun_out/ncu_siren.log 2>&1
+    timeout 600 ncu --set full --clock-control none --import-source on -k regex:frnn_query -s 3 -c 1 -f -o gpurun_out/prof_frnn_query_c2 $B > gpurun_out/ncu_frnn_c2.log 2>&1
+    timeout 600 ncu --set full --clock-control none --import-source on -k regex:frnn_query -s 3 -c 1 -f -o gpurun_out/prof_frnn_query python bench_frnn.py --steps 1 > gpurun_out/ncu_frnn.log 2>&1
+    timeout 600 ncu --set full --clock-control none --import-source on -k regex:splat_raster_v2_kernel -s 3 -c 1 -f -o gpurun_out/prof_splat_raster python bench_splat.py --steps 1 > gpurun_out/ncu_raster.log 2>&1
+    timeout 600 ncu --set full --clock-control none --import-source on -k regex:splat_occ_backward_hybrid_kernel -s 3 -c 1 -f -o gpurun_out/prof_splat_occ_bwd python bench_splat.py --steps 1 > gpurun_out/ncu_occ.log 2>&1
+    ls -la gpurun_out/ | tail -30 ;;
   bench)
     timeout 900 python bench.py --steps 10 --warmup 3 > gpurun_out/bench.json 2> gpurun_out/bench.err; tail -c 6000 gpurun_out/bench.json; grep -v Warning gpurun_out/bench.err | tail -5 ;;
   refarm)
