@@ -188,11 +188,11 @@ int isob200_splat_count_pairs(const float* points, const float* ellipse, const f
  *      rasterize_points_backward.cu:227-322; mode 0), DSS._C._splat_points_occ_backward
  *      (rasterize_points.h:341-386; mode 1), DSS._C._backward_zbuf (rasterize_points.h:388-419),
  *      per-point visibility (DSS/utils/__init__.py:378-399; DSS/core/rasterizer.py:851-857) ---- */
-size_t isob200_splat_occ_backward_ws_bytes(int N, int H, int W);
+size_t isob200_splat_occ_backward_ws_bytes(int N, int H, int W, long long total_points);
 int isob200_splat_occ_backward(const float* points, const float* radii, const unsigned char* visible,
                                const int64_t* first_idx, const int64_t* num_points, const float* rs,
                                float radii_s, const float* grad_occ, int N, int H, int W,
-                               long long max_points_per_cloud, int mode, float* grad_out, int out_stride,
+                               long long total_points, int mode, float* grad_out, int out_stride,
                                void* ws, size_t ws_bytes, void* stream);
 size_t isob200_splat_search_radius_ws_bytes(int N);
 /* per-view median(visible radii) * radii_s: DSS/core/rasterizer.py:881-884 */

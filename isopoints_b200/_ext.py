@@ -72,7 +72,7 @@ _PROTOS = {
                                    _vp, _ll, _vp, _vp, _vp, _vp, _vp]),
     "isob200_splat_bin_counts": (_i, [_vp, _vp, _vp, _vp, _i, _ll, _i, _i, _vp, _vp]),
     "isob200_splat_count_pairs": (_i, [_vp, _vp, _vp, _vp, _ll, _i, _vp, _vp]),
-    "isob200_splat_occ_backward_ws_bytes": (_sz, [_i, _i, _i]),
+    "isob200_splat_occ_backward_ws_bytes": (_sz, [_i, _i, _i, _ll]),
     "isob200_splat_occ_backward": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _f, _vp, _i, _i, _i, _ll, _i, _vp, _i,
                                         _vp, _sz, _vp]),
     "isob200_splat_search_radius_ws_bytes": (_sz, [_i]),

@@ -165,7 +165,7 @@ OCC_BACKWARD_HYBRID = True
 def _occ_backward(points, radii, visible_u8, first_idx, num_points, rs, radii_s, grad_occ, mode, out, out_stride):
     N, H, W = grad_occ.shape
     lib = _ext.lib()
-    ws = _ext.workspace(lib.isob200_splat_occ_backward_ws_bytes(N, H, W), points.device) if OCC_BACKWARD_HYBRID else None
+    ws = _ext.workspace(lib.isob200_splat_occ_backward_ws_bytes(N, H, W, points.shape[0]), points.device) if OCC_BACKWARD_HYBRID else None
     _ext.check(lib.isob200_splat_occ_backward(
         _ext.ptr(points), _ext.ptr(radii), _ext.ptr(visible_u8), _ext.ptr(first_idx), _ext.ptr(num_points),
         _ext.ptr(rs), float(radii_s), _ext.ptr(grad_occ), N, H, W, points.shape[0], mode, _ext.ptr(out),

@@ -9,6 +9,9 @@ case "${1:-all}" in
     timeout 900 python -m pytest tests/test_gpu_pinned.py tests/test_gpu_dropin.py tests/test_gpu_pointops.py tests/test_gpu_offsurface.py -m gpu -q -s 2>&1 | tail -80 > gpurun_out/pytest_new.log; tail -40 gpurun_out/pytest_new.log ;;
   timeline)
     timeout 300 python scripts/siren_timeline.py > gpurun_out/siren_timeline.txt 2>&1; tail -70 gpurun_out/siren_timeline.txt ;;
+  splat)
+    timeout 600 python -m pytest tests/test_gpu_splat.py tests/test_gpu_ewa.py tests/test_gpu_offsurface.py -m gpu -q -x 2>&1 | tail -15
+    timeout 300 python bench_splat.py --steps 10 > gpurun_out/bench_splat.json 2>gpurun_out/bench_splat.err; python -c "import json; d=json.load(open('gpurun_out/bench_splat.json')); print(d['ms_fwd'], d['ms_fwd_blend_bwd'], d['value']); [print(k, v) for k, v in d['kernels'].items()]" ;;
   ab)
     # old (build/ab/libisob200_old.so) vs new library, alternating on the same box: sustained C2 step
     for r in 1 2 3; do
