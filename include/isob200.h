@@ -252,8 +252,15 @@ int isob200_wlop_step(const float* X, const float* Pc, const int64_t* idx_xp, co
 int isob200_upsample_sparsity(const float* pts, const float* normals, float edge_sensitivity,
                               const int64_t* idx, int idx_stride, int k_offset, const int64_t* lengths, int N,
                               int P, int K, float* sparsity, float* child, void* stream);
+/* farthest point sampling (torch_cluster.fps behind DSS/utils/point_processing.py:473-499; start point start[n] or
+ * 0): mind = (N,P) float scratch, single CTA per cloud.  isob200_fps_ws: same with a scratch of
+ * isob200_fps_ws_floats(N,P) floats, which lets one cloud run on all SMs (cooperative launch, slices of the cloud
+ * resident in shared memory, one grid barrier per sample); identical indices */
 int isob200_fps(const float* pts, const int64_t* lengths, const int64_t* samples, const int64_t* start, int N,
                 int P, int Mmax, float* mind, int64_t* out_idx, void* stream);
+size_t isob200_fps_ws_floats(int N, int P);
+int isob200_fps_ws(const float* pts, const int64_t* lengths, const int64_t* samples, const int64_t* start, int N,
+                   int P, int Mmax, float* ws, size_t ws_floats, int64_t* out_idx, void* stream);
 
 #ifdef __cplusplus
 }

@@ -65,6 +65,8 @@ _PROTOS = {
     "isob200_wlop_step": (_i, [_vp, _vp, _vp, _vp, _i, _i, _vp, _vp, _f, _i, _i, _i, _i, _vp, _vp]),
     "isob200_upsample_sparsity": (_i, [_vp, _vp, _f, _vp, _i, _i, _vp, _i, _i, _i, _vp, _vp, _vp]),
     "isob200_fps": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp]),
+    "isob200_fps_ws_floats": (_sz, [_i, _i]),
+    "isob200_fps_ws": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _vp, _sz, _vp, _vp]),
     "isob200_splat_ws_bytes": (_sz, [_i, _i]),
     "isob200_splat_record_bytes": (_i, []),
     "isob200_splat_bin": (_i, [_vp, _vp, _vp, _vp, _i, _ll, _ll, _i, _vp, _sz, _vp, _vp]),
@@ -93,7 +95,7 @@ _TLS = threading.local()
 # Optional per-entry-point device timing (bench.py): when PROFILE is a dict, every C-ABI call is
 # bracketed by CUDA events on the stream it is launched on; PROFILE[name] collects (start, end).
 PROFILE = None
-_NO_TIMING = ("_ws_bytes", "_blob_bytes", "_scratch_bytes", "isob200_siren_set_max_ctas", "isob200_siren_set_stagger", "isob200_last_error", "isob200_abi_version", "isob200_compiled_arch",
+_NO_TIMING = ("_ws_bytes", "_ws_floats", "_blob_bytes", "_scratch_bytes", "isob200_siren_set_max_ctas", "isob200_siren_set_stagger", "isob200_last_error", "isob200_abi_version", "isob200_compiled_arch",
               "isob200_launch_count", "isob200_splat_record_bytes")
 
 

@@ -358,6 +358,306 @@ frnn_query_exhaustive_kernel(const float* __restrict__ q_points,     // (N,P1,D)
   }
 }
 
+// ---- dense grids: one THREAD per query, collect-then-select ---------------------------------------------
+// The group-cooperative kernels above spend ~2 300 warp instructions per pair of queries at BASELINE config 3
+// (500 k uniform points, K = 16, ~8 points per cell): a third on the ring / run bookkeeping, a third on 16-wide
+// candidate steps that are mostly predicated off, a third on serial ballot + shuffle insertions -- and the two
+// groups of a warp diverge.  When the grid is dense (>= 1 point per cell) the K-th neighbour lies well inside the
+// search radius, so here each thread FIRST fixes a trial radius from the local density (the candidate block's
+// point count is two offset loads per run) such that the ball holds lambda = K + 4 sqrt(K) points on average,
+// THEN makes one pass over the cells that ball touches and appends every candidate inside it to a per-thread
+// column of shared memory (no ordering work at all: a predicated 8-byte store), and finally reads its <= 48
+// entries back K times to emit the K smallest (dist, index) keys in order.  Exactness does not rest on the
+// estimate: a thread whose ball held fewer than K (or more than the column's capacity of) candidates hands its
+// query to the warp, which runs the pruned best-first search of frnn_query_kernel on it with all 32 lanes.
+// Results are identical to the other kernels (same fp32 distance expression, same (dist, index) order).
+constexpr int COLLECT_THREADS = 128;
+constexpr int COLLECT_CAP = 48;       // entries per thread: 48 x 128 x 8 B = 48 KB of shared memory per CTA
+
+// The pruned best-first search of frnn_query_kernel for ONE query, run by a full warp (lane l ends up holding
+// the l-th best (dist, index), ascending; FLT_MAX / INT_MAX where fewer were found).
+template <int D>
+__device__ __forceinline__ void warp_pruned_search(const float (&q)[D], const float* __restrict__ prm, float r2,
+                                                   float r, const float* __restrict__ pts2,
+                                                   const int* __restrict__ off2, const int* __restrict__ sid2,
+                                                   int len2, int K, float& best_d, int& best_i) {
+  const int gl = threadIdx.x & 31;
+  const float delta = prm[D];
+  const float inv_delta = 1.0f / delta;
+  int lo[D], hi[D], res[D], cq[D];
+  float qc[D];
+  bool nonempty = true;
+#pragma unroll
+  for (int d = 0; d < D; ++d) {
+    const float rel = __fsub_rn(q[d], prm[d]);
+    res[d] = (int)prm[D + 1 + d];
+    lo[d] = max(__float2int_rd(__fmul_rn(__fsub_rn(rel, r), delta)), 0);
+    hi[d] = min(__float2int_rd(__fmul_rn(__fadd_rn(rel, r), delta)), res[d] - 1);
+    nonempty = nonempty && (lo[d] <= hi[d]);
+    qc[d] = rel * delta;
+    cq[d] = min(max(__float2int_rd(qc[d]), lo[d]), hi[d]);
+  }
+  const int grid_total = (int)prm[2 * D + 1];
+  best_d = FLT_MAX;
+  best_i = INT_MAX;
+  float bound = r2;
+  if (!nonempty) return;
+  const int R0 = max(cq[0] - lo[0], hi[0] - cq[0]);
+  const int R1 = (D == 3) ? max(cq[1] - lo[1], hi[1] - cq[1]) : 0;
+  const int R = max(R0, R1);
+  for (int ring = 0; ring <= R; ++ring) {
+    const int xstep = (D == 2) ? max(2 * ring, 1) : 1;
+    for (int ox = -ring; ox <= ring; ox += xstep) {
+      const int x = cq[0] + ox;
+      if (x < lo[0] || x > hi[0]) continue;
+      const float gx2 = axis_gap2(qc[0], x, inv_delta);
+      if (gx2 > bound) continue;
+      const int ystep = (D == 3 && (ox == -ring || ox == ring)) ? 1 : max(2 * ring, 1);
+      for (int oy = (D == 3 ? -ring : 0); oy <= (D == 3 ? ring : 0); oy += ystep) {
+        int c0;
+        float gxy2 = gx2;
+        int zlo, zhi;
+        float qcz;
+        if (D == 3) {
+          const int y = cq[1] + oy;
+          if (y < lo[1] || y > hi[1]) continue;
+          gxy2 += axis_gap2(qc[1], y, inv_delta);
+          if (gxy2 > bound) continue;
+          zlo = lo[2]; zhi = hi[2]; qcz = qc[2];
+          c0 = (x * res[1] + y) * res[2];
+        } else {
+          zlo = lo[1]; zhi = hi[1]; qcz = qc[1];
+          c0 = x * res[1];
+        }
+        const float gz = sqrtf(fmaxf(bound - gxy2, 0.0f)) * delta + 2e-3f;
+        const int za = max(zlo, __float2int_ru(qcz - 1.0f - gz));
+        const int zb = min(zhi, __float2int_rd(qcz + gz));
+        if (za > zb) continue;
+        const int start = off2[c0 + za];
+        const int end = (c0 + zb + 1 == grid_total) ? len2 : off2[c0 + zb + 1];
+        for (int base = start; base < end; base += 32) {
+          const int j = base + gl;
+          const bool valid = j < end;
+          float d = FLT_MAX;
+          if (valid) d = sqdist_ref<D>(pts2 + (size_t)j * D, q);
+          const bool cand = valid && (d <= bound);
+          unsigned m = __ballot_sync(0xffffffffu, cand);
+          if (m == 0) continue;
+          const int ci_mine = cand ? sid2[j] : INT_MAX;
+          while (m) {
+            const int src = __ffs(m) - 1;
+            m &= m - 1;
+            const float cd = __shfl_sync(0xffffffffu, d, src);
+            const int ci = __shfl_sync(0xffffffffu, ci_mine, src);
+            const bool less = (best_d < cd) || (best_d == cd && best_i < ci);
+            const int pos = __popc(__ballot_sync(0xffffffffu, less));
+            const float up_d = __shfl_up_sync(0xffffffffu, best_d, 1);
+            const int up_i = __shfl_up_sync(0xffffffffu, best_i, 1);
+            if (pos < K) {
+              if (gl > pos) { best_d = up_d; best_i = up_i; }
+              else if (gl == pos) { best_d = cd; best_i = ci; }
+            }
+          }
+          bound = fminf(r2, __shfl_sync(0xffffffffu, best_d, K - 1));
+        }
+      }
+    }
+  }
+}
+
+template <int D, typename IdxT>
+__global__ void __launch_bounds__(COLLECT_THREADS)
+frnn_query_collect_kernel(const float* __restrict__ q_points, const int* __restrict__ q_order,
+                          const int64_t* __restrict__ lengths1, const int64_t* __restrict__ lengths2,
+                          const float* __restrict__ sorted_points2, const int* __restrict__ cell_off2,
+                          const int* __restrict__ sorted_idxs2, const float* __restrict__ params,
+                          const float* __restrict__ rs, int N, int P1, int P2, int G, int K, float lambda,
+                          float* __restrict__ dists, IdxT* __restrict__ idxs) {
+  constexpr int PS = (D == 3) ? ISO_G3_SIZE : ISO_G2_SIZE;
+  extern __shared__ unsigned long long s_keys[];     // [COLLECT_CAP][COLLECT_THREADS]
+  const int tid = threadIdx.x, lane = tid & 31;
+  const long long total = (long long)N * P1;
+  const long long nslots = ((total + COLLECT_THREADS - 1) / COLLECT_THREADS) * COLLECT_THREADS;
+  for (long long item = (long long)blockIdx.x * COLLECT_THREADS + tid; item < nslots;
+       item += (long long)gridDim.x * COLLECT_THREADS) {
+    const bool in_range = item < total;
+    const int n = in_range ? (int)(item / P1) : 0;
+    const int s = in_range ? (int)(item - (long long)n * P1) : 0;
+    const int len1 = lengths1 ? (int)min((long long)lengths1[n], (long long)P1) : P1;
+    const bool live = in_range && s < len1;
+    const int len2 = lengths2 ? (int)min((long long)lengths2[n], (long long)P2) : P2;
+    const float* prm = params + (size_t)n * PS;
+    const float r = rs[n];
+    const float r2 = __fmul_rn(r, r);
+    const float* pts2 = sorted_points2 + (size_t)n * P2 * D;
+    const int* off2 = cell_off2 + (size_t)n * G;
+    const int* sid2 = sorted_idxs2 + (size_t)n * P2;
+    float q[D];
+#pragma unroll
+    for (int d = 0; d < D; ++d) q[d] = live ? q_points[((size_t)n * P1 + s) * D + d] : 0.f;
+    const int row = (live && q_order) ? q_order[(size_t)n * P1 + s] : s;
+    if (in_range && !live) {   // padded row: the reference leaves its -1 fill (grid.cu:422-423)
+      const size_t o = ((size_t)n * P1 + s) * K;
+      for (int k = 0; k < K; ++k) { dists[o + k] = -1.f; idxs[o + k] = (IdxT)-1; }
+    }
+
+    int cnt = 0;
+    bool failed = false;
+    if (live) {
+      const float delta = prm[D];
+      const float inv_delta = 1.0f / delta;
+      int lo[D], hi[D], res[D];
+      float qc[D];
+      bool nonempty = true;
+#pragma unroll
+      for (int d = 0; d < D; ++d) {
+        const float rel = __fsub_rn(q[d], prm[d]);
+        res[d] = (int)prm[D + 1 + d];
+        lo[d] = max(__float2int_rd(__fmul_rn(__fsub_rn(rel, r), delta)), 0);       // grid.cu:305-316
+        hi[d] = min(__float2int_rd(__fmul_rn(__fadd_rn(rel, r), delta)), res[d] - 1);
+        nonempty = nonempty && (lo[d] <= hi[d]);
+        qc[d] = rel * delta;
+      }
+      const int grid_total = (int)prm[2 * D + 1];
+      if (nonempty) {
+        const int zlo = lo[D - 1], zhi = hi[D - 1];
+        const int ylo = (D == 3) ? lo[1] : 0, yhi = (D == 3) ? hi[1] : 0;
+        // ---- trial radius from the block's point density ----
+        int nblock = 0;
+        for (int x = lo[0]; x <= hi[0]; ++x)
+          for (int y = ylo; y <= yhi; ++y) {
+            const int c0 = (D == 3) ? (x * res[1] + y) * res[2] : x * res[1];
+            const int a = off2[c0 + zlo];
+            const int b = (c0 + zhi + 1 == grid_total) ? len2 : off2[c0 + zhi + 1];
+            nblock += b - a;
+          }
+        float tau = r2;
+        if (nblock > K) {
+          float cells = (float)(hi[0] - lo[0] + 1) * (float)(zhi - zlo + 1);
+          if (D == 3) cells *= (float)(yhi - ylo + 1);
+          // radius (in cells) of the ball expected to hold lambda points at the block's mean density
+          const float vol = lambda * cells / (float)nblock;                  // in cell volumes
+          float rc = (D == 3) ? cbrtf(vol * 0.238732415f) : sqrtf(vol * 0.318309886f);
+          // a ball that sticks out of the grid holds fewer points: grow it by the part cut off (per axis the
+          // fraction of the diameter inside, one fixed-point step) -- the estimate only has to be roughly right
+          float inside = 1.0f;
+#pragma unroll
+          for (int d = 0; d < D; ++d) {
+            const float t = fminf(qc[d], (float)res[d] - qc[d]);             // cells to the nearer grid face
+            inside *= fminf(fmaxf(0.5f * (t / rc + 1.0f), 0.5f), 1.0f);
+          }
+          rc = (D == 3) ? rc * cbrtf(1.0f / inside) : rc * sqrtf(1.0f / inside);
+          const float re = rc * inv_delta;
+          tau = fminf(r2, re * re);
+        }
+        // ---- one pass over the cells the trial ball touches ----
+        // (a per-thread run cursor inside one flat candidate loop was tried: the cursor code then runs with ~5
+        // live lanes per instruction and costs more than the per-run trip-count divergence of these nested loops)
+        for (int x = lo[0]; x <= hi[0]; ++x) {
+          const float gx2 = axis_gap2(qc[0], x, inv_delta);
+          if (gx2 > tau) continue;
+          for (int y = ylo; y <= yhi; ++y) {
+            float gxy2 = gx2;
+            int c0;
+            if (D == 3) {
+              gxy2 += axis_gap2(qc[1], y, inv_delta);
+              if (gxy2 > tau) continue;
+              c0 = (x * res[1] + y) * res[2];
+            } else {
+              c0 = x * res[1];
+            }
+            const float gz = sqrtf(fmaxf(tau - gxy2, 0.0f)) * delta + 2e-3f;
+            const int za = max(zlo, __float2int_ru(qc[D - 1] - 1.0f - gz));
+            const int zb = min(zhi, __float2int_rd(qc[D - 1] + gz));
+            if (za > zb) continue;
+            const int start = off2[c0 + za];
+            const int end = (c0 + zb + 1 == grid_total) ? len2 : off2[c0 + zb + 1];
+            // four candidates per step: their 4 D loads are in flight together (the loop is latency bound:
+            // one query per thread leaves 16 warps per SM)
+            for (int j = start; j < end; j += 4) {
+              float dd[4];
+#pragma unroll
+              for (int u = 0; u < 4; ++u) {
+                const int jj = min(j + u, end - 1);
+                dd[u] = sqdist_ref<D>(pts2 + (size_t)jj * D, q);
+              }
+#pragma unroll
+              for (int u = 0; u < 4; ++u) {
+                if (j + u < end && dd[u] <= tau) {
+                  if (cnt < COLLECT_CAP)
+                    s_keys[cnt * COLLECT_THREADS + tid] =
+                        ((unsigned long long)__float_as_uint(dd[u]) << 32) | (unsigned)sid2[j + u];
+                  ++cnt;
+                }
+              }
+            }
+          }
+        }
+        // exact unless the ball overflowed the column, or was cut short of K by a trial radius below r
+        failed = cnt > COLLECT_CAP || (cnt < K && tau < r2);
+      }
+      if (!failed) {
+        // ---- emit the K smallest keys in ascending order (keys are unique: the index is part of them), two per
+        //      pass over the column: the smallest and second smallest key above the last one written ----
+        const size_t o = ((size_t)n * P1 + row) * K;
+        unsigned long long prev = 0;
+        bool have_prev = false;
+        for (int k = 0; k < K; k += 2) {
+          unsigned long long b1 = ~0ull, b2 = ~0ull;
+          if (k < cnt) {
+            for (int i = 0; i < cnt; ++i) {
+              const unsigned long long key = s_keys[i * COLLECT_THREADS + tid];
+              if (!have_prev || key > prev) {
+                const bool lt1 = key < b1, lt2 = key < b2;
+                b2 = lt1 ? b1 : (lt2 ? key : b2);
+                b1 = lt1 ? key : b1;
+              }
+            }
+          }
+#pragma unroll
+          for (int u = 0; u < 2; ++u) {
+            const unsigned long long best = u ? b2 : b1;
+            if (k + u >= K) break;
+            if (best != ~0ull) {
+              dists[o + k + u] = __uint_as_float((unsigned)(best >> 32));
+              idxs[o + k + u] = (IdxT)(int)(unsigned)(best & 0xffffffffu);
+              prev = best;
+              have_prev = true;
+            } else {
+              dists[o + k + u] = -1.f;
+              idxs[o + k + u] = (IdxT)-1;
+            }
+          }
+        }
+      }
+    }
+    // ---- the warp takes over the queries whose trial ball failed ----
+    unsigned fm = __ballot_sync(0xffffffffu, failed);
+    while (fm) {
+      const int src = __ffs(fm) - 1;
+      fm &= fm - 1;
+      float qq[D];
+#pragma unroll
+      for (int d = 0; d < D; ++d) qq[d] = __shfl_sync(0xffffffffu, q[d], src);
+      const int nn = __shfl_sync(0xffffffffu, n, src);
+      const int rr = __shfl_sync(0xffffffffu, row, src);
+      const int l2 = lengths2 ? (int)min((long long)lengths2[nn], (long long)P2) : P2;
+      const float r_ = rs[nn];
+      float bd;
+      int bi;
+      warp_pruned_search<D>(qq, params + (size_t)nn * PS, __fmul_rn(r_, r_), r_,
+                            sorted_points2 + (size_t)nn * P2 * D, cell_off2 + (size_t)nn * G,
+                            sorted_idxs2 + (size_t)nn * P2, l2, K, bd, bi);
+      if (lane < K) {
+        const size_t o = ((size_t)nn * P1 + rr) * K + lane;
+        const bool found = bi != INT_MAX;
+        dists[o] = found ? bd : -1.f;
+        idxs[o] = found ? (IdxT)bi : (IdxT)-1;
+      }
+    }
+  }
+}
+
 // x (N,M,U), idxs (N,L,K) -> out (N,L,K,U); 0 where idx < 0   (frnn.py:304-352)
 template <typename IdxT>
 __global__ void __launch_bounds__(256)
@@ -458,8 +758,9 @@ extern "C" {
 //   q_order  : processing slot -> original row (sorted_points1_idxs), or NULL for identity
 //   idx_is_i64: 1 -> idxs is int64 (reference API), 0 -> int32 (internal fused consumers)
 //   group_width: 0 = auto (smallest of 8/16/32 that is >= K), optionally OR-ed with a traversal mode in
-//                bits 8..9: 0 = auto (pruned best-first when the grid holds >= 1 point per cell on
-//                average, exhaustive otherwise), 1 = exhaustive, 2 = pruned.  Results are identical.
+//                bits 8..9: 0 = auto (exhaustive when the grid holds < 1 point per cell on average; else
+//                thread-per-query collect-then-select for K <= 20 and the pruned best-first group search
+//                above that), 1 = exhaustive, 2 = pruned, 3 = collect.  Results are identical.
 int isob200_frnn_find_nbrs(const float* q_points, const int* q_order, const int64_t* lengths1,
                            const int64_t* lengths2, const float* sorted_points2, const int* cell_off2,
                            const int* sorted_idxs2, const float* params, const float* rs, int N,
@@ -476,6 +777,26 @@ int isob200_frnn_find_nbrs(const float* q_points, const int* q_order, const int6
   int gw = group_width & 0xff;
   if (gw == 0) gw = (K <= 8) ? 8 : (K <= 16 ? 16 : 32);
   const bool exhaustive = mode == 1 || (mode == 0 && (long long)P2 < (long long)G);
+  // dense grid and a K whose trial ball fits a shared-memory column: thread-per-query collect-then-select
+  const bool collect = mode == 3 || (mode == 0 && !exhaustive && K <= 20);
+  if (collect) {
+    ISO_CHECK_ARG(K <= 32, "find_nbrs: collect mode needs K <= 32");
+    const float lambda = fminf((float)K + 4.0f * sqrtf((float)K), (float)(COLLECT_CAP - 8));
+    const size_t smem = (size_t)COLLECT_CAP * COLLECT_THREADS * sizeof(unsigned long long);
+    const long long items_c = (long long)N * P1;
+    long long need_c = (items_c + COLLECT_THREADS - 1) / COLLECT_THREADS;
+    const long long cap_c = (long long)kNumSMs * 4 * 32;
+    const int blocks_c = (int)(need_c < cap_c ? need_c : cap_c);
+#define QC(DD, T)                                                                                          \
+  frnn_query_collect_kernel<DD, T><<<blocks_c, COLLECT_THREADS, smem, st>>>(                               \
+      q_points, q_order, lengths1, lengths2, sorted_points2, cell_off2, sorted_idxs2, params, rs, N, P1,  \
+      P2, G, K, lambda, dists, (T*)idxs)
+    if (D == 3) { if (idx_is_i64) QC(3, int64_t); else QC(3, int); }
+    else { if (idx_is_i64) QC(2, int64_t); else QC(2, int); }
+#undef QC
+    ISO_CHECK_LAUNCH("frnn_query_collect_kernel");
+    return ISOB200_OK;
+  }
   ISO_CHECK_ARG((gw == 8 || gw == 16 || gw == 32) && gw >= K, "find_nbrs: group_width %d invalid for K=%d", gw, K);
   const long long items = (long long)N * P1;
   const int groups = 256 / gw;

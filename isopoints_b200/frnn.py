@@ -29,7 +29,8 @@ from . import _ext
 
 _GRID = namedtuple("GRID", "sorted_points2 pc2_grid_off sorted_points2_idxs grid_params")
 
-# traversal of the query kernel: 0 = auto, 1 = exhaustive block scan, 2 = pruned best-first (same results)
+# traversal of the query kernel: 0 = auto, 1 = exhaustive block scan, 2 = pruned best-first, 3 = thread-per-query
+# collect-then-select (same results)
 QUERY_MODE = 0
 
 _MAX_CELLS = 1 << 28     # 1 GiB of int32 offsets per cloud; int cell ids stay far from overflow

@@ -97,12 +97,13 @@ def farthest_sampling(point_clouds, ratio: float, random_start: bool = False):
     m = torch.ceil(num.double() * ratio).to(torch.int64)
     Mmax = int(math.ceil(P * ratio)) if P else 0
     out = torch.empty((N, Mmax), dtype=torch.int64, device=dev)
-    mind = torch.empty((N, max(P, 1)), dtype=torch.float32, device=dev)
+    lib = _ext.lib()
+    ws = torch.empty((max(int(lib.isob200_fps_ws_floats(N, P)), 1),), dtype=torch.float32, device=dev)
     start = None
     if random_start:
         start = (torch.rand((N,), device=dev) * num.float()).long()
-    _ext.check(_ext.lib().isob200_fps(_ext.ptr(pts.contiguous()), _ext.ptr(num), _ext.ptr(m), _ext.ptr(start), N, P,
-                                      Mmax, _ext.ptr(mind), _ext.ptr(out), _ext.stream(dev)))
+    _ext.check(lib.isob200_fps_ws(_ext.ptr(pts.contiguous()), _ext.ptr(num), _ext.ptr(m), _ext.ptr(start), N, P,
+                                  Mmax, _ext.ptr(ws), ws.numel(), _ext.ptr(out), _ext.stream(dev)))
     counts = m.tolist()
     sel = [out[n, : counts[n]] for n in range(N)]
     pts_list = [pts[n][sel[n]] for n in range(N)]

@@ -9,6 +9,14 @@ case "${1:-all}" in
     timeout 900 python -m pytest tests/test_gpu_pinned.py tests/test_gpu_dropin.py tests/test_gpu_pointops.py tests/test_gpu_offsurface.py -m gpu -q -s 2>&1 | tail -80 > gpurun_out/pytest_new.log; tail -40 gpurun_out/pytest_new.log ;;
   timeline)
     timeout 300 python scripts/siren_timeline.py > gpurun_out/siren_timeline.txt 2>&1; tail -70 gpurun_out/siren_timeline.txt ;;
+  pointops)
+    timeout 600 python -m pytest tests/test_gpu_pointops.py tests/test_gpu_frnn.py -m gpu -q -x 2>&1 | tail -8
+    timeout 300 python bench_frnn.py --steps 10 > gpurun_out/bench_frnn.json 2>gpurun_out/bench_frnn.err; python -c "import json; d=json.load(open('gpurun_out/bench_frnn.json')); print(d['ms_per_step'], d['value'], d['kernels_avg_ms'])"
+    timeout 600 python bench_pointops.py > gpurun_out/bench_pointops.json 2> gpurun_out/bench_pointops.err; cat gpurun_out/bench_pointops.json; tail -3 gpurun_out/bench_pointops.err ;;
+  frnn)
+    timeout 600 python -m pytest tests/test_gpu_frnn.py tests/test_gpu_pointops.py tests/test_gpu_projection.py -m gpu -q -x 2>&1 | tail -15
+    timeout 300 python bench_frnn.py --steps 10 > gpurun_out/bench_frnn.json 2>gpurun_out/bench_frnn.err; python -c "import json; d=json.load(open('gpurun_out/bench_frnn.json')); print(d['ms_per_step'], d['value'], d['kernels_avg_ms'])"
+    timeout 300 ncu --set full --clock-control none --import-source on -k regex:frnn_query -s 3 -c 1 -f -o gpurun_out/prof_frnn_query python bench_frnn.py --steps 1 > gpurun_out/ncu_frnn.log 2>&1; tail -2 gpurun_out/ncu_frnn.log ;;
   splat)
     timeout 600 python -m pytest tests/test_gpu_splat.py tests/test_gpu_ewa.py tests/test_gpu_offsurface.py -m gpu -q -x 2>&1 | tail -15
     timeout 300 python bench_splat.py --steps 10 > gpurun_out/bench_splat.json 2>gpurun_out/bench_splat.err; python -c "import json; d=json.load(open('gpurun_out/bench_splat.json')); print(d['ms_fwd'], d['ms_fwd_blend_bwd'], d['value']); [print(k, v) for k, v in d['kernels'].items()]" ;;

@@ -37,7 +37,7 @@ def test_prefix_sum_cuda_api_in_place():
     assert torch.equal(off.cpu().long(), (torch.cumsum(x.long(), 0) - x.long()).cpu())
 
 
-@pytest.fixture(params=[1, 2], ids=["exhaustive", "pruned"])
+@pytest.fixture(params=[1, 2, 3], ids=["exhaustive", "pruned", "collect"])
 def query_mode(request):
     old = frnn.QUERY_MODE
     frnn.QUERY_MODE = request.param
@@ -220,3 +220,27 @@ def test_frnn_500k_bit_exact_vs_reference_cuda(shape, query_mode):
     assert (dd[..., 1:] >= dd[..., :-1]).all() and (d <= 0.05 * 0.05).all()
     if shape == "box":
         assert 0.9 < float(full.float().mean()) <= 1.0
+
+
+@pytest.mark.parametrize("D", [3, 2])
+def test_frnn_collect_equals_pruned_on_clustered_cloud(D):
+    """The thread-per-query kernel fixes a trial radius from the MEAN density of the candidate block; on a cloud
+    whose density varies by orders of magnitude the trial ball overflows (clusters) or comes up short (voids) and
+    the warp-cooperative exact search takes over -- results must not depend on which path answered."""
+    g = torch.Generator().manual_seed(5)
+    P = 60_000
+    centers = torch.rand(40, D, generator=g)
+    clustered = centers[torch.randint(0, 40, (P // 2,), generator=g)] + 0.004 * torch.randn(P // 2, D, generator=g)
+    p = torch.cat([clustered, torch.rand(P - P // 2, D, generator=g)])[None].to(DEV)
+    lens = torch.tensor([P - 17], device=DEV)
+    old = frnn.QUERY_MODE
+    try:
+        for K in (1, 4, 9, 16, 20, 32):
+            out = {}
+            for mode in (2, 3):
+                frnn.QUERY_MODE = mode
+                d, i, _, _ = frnn.frnn_grid_points(p, p, lens, lens, K=K, r=0.08)
+                out[mode] = (d, i)
+            assert torch.equal(out[2][0], out[3][0]) and torch.equal(out[2][1], out[3][1]), K
+    finally:
+        frnn.QUERY_MODE = old

@@ -199,3 +199,31 @@ def test_knn_points_on_degenerate_clouds():
         assert (out.idx[0].cpu() == wi).float().mean() > 0.999          # equal-distance pairs may swap
     with pytest.raises(RuntimeError, match="cells"):
         frnn.frnn_grid_points(plane.to(DEV), plane.to(DEV), K=4, r=1e-7)
+
+
+def test_farthest_sampling_on_all_sms_equals_single_cta_kernel():
+    """isob200_fps_ws (cloud sliced over up to 148 CTAs, slices resident in shared memory, one grid barrier per
+    sample) picks exactly the indices of the single-CTA kernel -- two ragged clouds, 20 and 12 CTAs' worth."""
+    from isopoints_b200 import _ext
+    lib = _ext.lib()
+    g = torch.Generator().manual_seed(3)
+    N, P, M = 2, 40_000, 3000
+    pts = torch.rand(N, P, 3, generator=g).to(DEV)
+    lens = torch.tensor([P, 23_456], device=DEV)
+    m = torch.tensor([M, 1500], device=DEV)
+    start = torch.tensor([7, 0], device=DEV)
+    out = []
+    for coop in (False, True):
+        idx = torch.full((N, M), -7, dtype=torch.int64, device=DEV)
+        if coop:
+            ws = torch.empty((lib.isob200_fps_ws_floats(N, P),), dtype=torch.float32, device=DEV)
+            _ext.check(lib.isob200_fps_ws(_ext.ptr(pts), _ext.ptr(lens), _ext.ptr(m), _ext.ptr(start), N, P, M,
+                                          _ext.ptr(ws), ws.numel(), _ext.ptr(idx), _ext.stream(pts.device)))
+        else:
+            ws = torch.empty((N * P,), dtype=torch.float32, device=DEV)
+            _ext.check(lib.isob200_fps(_ext.ptr(pts), _ext.ptr(lens), _ext.ptr(m), _ext.ptr(start), N, P, M,
+                                       _ext.ptr(ws), _ext.ptr(idx), _ext.stream(pts.device)))
+        out.append(idx)
+    assert torch.equal(out[0], out[1])
+    assert int(out[1][0, 0]) == 7 and (out[1][1, 1500:] == -1).all() and (out[1][1, :1500] < 23_456).all()
+    assert out[1][0].unique().numel() == M
