@@ -70,7 +70,7 @@ def compute_isotropic_vrk_h(points_padded, num_points_per_cloud, frnn_radius, fi
     first_idx, num = _views(first_idx, num, dev)
     K = 7
     sq_dist = frnn_grid_points(pts, pts, num, num, K=K, r=frnn_radius)[0]
-    P = int(num.sum().item()) if pts.shape[0] > 1 else pts.shape[1]
+    P = int(num.sum().item())       # packed rows (a single cloud may be padded beyond its length)
     h = torch.empty(P, dtype=torch.float32, device=dev)
     _ext.check(_ext.lib().isob200_ewa_vrk_h(_ext.ptr(sq_dist), _ext.ptr(first_idx), _ext.ptr(num), num.numel(),
                                             pts.shape[1], K, P, _ext.ptr(h), _ext.stream(dev)))
@@ -227,13 +227,34 @@ class SurfaceSplatting:
             point_clouds = point_clouds.extend(w2v.shape[0])     # :241-245
         znear = getattr(cameras, "znear", kwargs.get("znear", 1.0))
         zfar = getattr(cameras, "zfar", kwargs.get("zfar", 100.0))
-        znear = float(znear.reshape(-1)[0]) if torch.is_tensor(znear) else float(znear)
-        zfar = float(zfar.reshape(-1)[0]) if torch.is_tensor(zfar) else float(zfar)
         pts = point_clouds.points_packed()
         nrm = point_clouds.normals_packed()
         first = point_clouds.cloud_to_packed_first_idx()
-        mask, kept = renderable_mask(pts, nrm, first, w2v, znear, zfar, bool(getattr(rs, "backface_culling", True)))
-        kept = kept.tolist()                                      # one read-back: the new cloud sizes
+        backface = bool(getattr(rs, "backface_culling", True))
+        zn = znear.reshape(-1).float() if torch.is_tensor(znear) else None
+        zf = zfar.reshape(-1).float() if torch.is_tensor(zfar) else None
+        per_view = ((zn is not None and zn.numel() > 1 and bool((zn != zn[0]).any())) or
+                    (zf is not None and zf.numel() > 1 and bool((zf != zf[0]).any())))
+        if not per_view:
+            znear = float(zn[0]) if zn is not None else float(znear)
+            zfar = float(zf[0]) if zf is not None else float(zfar)
+            mask, kept = renderable_mask(pts, nrm, first, w2v, znear, zfar, backface)
+            kept = kept.tolist()                                  # one read-back: the new cloud sizes
+        else:
+            # per-view clip planes (camera batches built with znear / zfar tensors): the mask kernel takes one
+            # pair per launch, so the views go through it one by one
+            nums = point_clouds.num_points_per_cloud().tolist()
+            firsts = first.tolist()
+            masks, kept = [], []
+            for v, (f0, nv) in enumerate(zip(firsts, nums)):
+                zv = float(zn[v if zn.numel() > 1 else 0]) if zn is not None else float(znear)
+                fv = float(zf[v if zf.numel() > 1 else 0]) if zf is not None else float(zfar)
+                mv, kv = renderable_mask(pts[f0:f0 + nv], None if nrm is None else nrm[f0:f0 + nv],
+                                         torch.zeros(1, dtype=torch.int64, device=pts.device), w2v[v:v + 1], zv, fv,
+                                         backface)
+                masks.append(mv)
+                kept.append(int(kv.item()))
+            mask = torch.cat(masks)
         total = sum(kept)
         if total == pts.shape[0]:
             return point_clouds, mask
@@ -242,6 +263,8 @@ class SurfaceSplatting:
                                           m8, total)
         if pts.requires_grad:                                      # keep the autograd link to the input points
             new_pts = pts[mask]
+        if nrm is not None and nrm.requires_grad:                  # ... and to the normals (boolean indexing, :250)
+            new_nrm = nrm[mask]
         feats = point_clouds.features_packed()
         parts = lambda t: None if t is None else list(torch.split(t, kept))   # noqa: E731
         new = Pointclouds(points=parts(new_pts), normals=parts(new_nrm),

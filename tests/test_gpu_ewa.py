@@ -177,6 +177,35 @@ def test_filter_renderable_compacts_in_order():
     assert same is pc and bool(mask2.all())
 
 
+def test_filter_renderable_per_view_clip_planes_and_normal_gradients():
+    """znear / zfar given as per-view tensors (camera batches in the reference carry them that way) are honoured
+    view by view, and the filtered normals keep their autograd link like the reference's boolean indexing
+    (rasterizer.py:246-253)."""
+    views = [5000, 7000]
+    pts, nrm, first, num = make_surface_points(views, seed=4)
+    w2v, proj, nmat = make_cameras(2, seed=6)
+    split = lambda x: list(torch.split(x, views))  # noqa: E731
+    zn = torch.tensor([1.0, 2.4], device=DEV)
+    want = []
+    for v in range(2):
+        pc_v = Pointclouds(points=[split(pts.to(DEV))[v]], normals=[split(nrm.to(DEV))[v]])
+        ras_v = ewa.SurfaceSplatting(cameras=_Cams(w2v[v:v + 1].to(DEV), proj[v:v + 1].to(DEV), znear=float(zn[v])),
+                                     raster_settings=ewa.PointsRasterizationSettings(backface_culling=True))
+        want.append(ras_v.filter_renderable(pc_v)[1])
+    n_dev = nrm.to(DEV).requires_grad_(True)
+    pc = Pointclouds(points=split(pts.to(DEV)), normals=split(n_dev))
+    ras = ewa.SurfaceSplatting(cameras=_Cams(w2v.to(DEV), proj.to(DEV), znear=zn),
+                               raster_settings=ewa.PointsRasterizationSettings(backface_culling=True))
+    new, mask = ras.filter_renderable(pc)
+    assert torch.equal(mask, torch.cat(want))
+    assert int(want[0].sum()) != int(ras.filter_renderable(
+        Pointclouds(points=[split(pts.to(DEV))[0]], normals=[split(nrm.to(DEV))[0]]),
+        cameras=_Cams(w2v[:1].to(DEV), proj[:1].to(DEV), znear=2.4))[1].sum())      # the planes do differ
+    assert new.num_points_per_cloud().tolist() == [int(w.sum()) for w in want]
+    new.normals_packed().sum().backward()
+    assert torch.equal(n_dev.grad, mask[:, None].expand(-1, 3).float())
+
+
 def test_surface_splatting_forward_and_gradient():
     """filter -> per-point parameters -> screen transform -> splat, and a gradient back to the world points."""
     views = [6000] * 3

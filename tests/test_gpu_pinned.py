@@ -70,7 +70,7 @@ def test_value_and_gradient_at_200k_rows_vs_float64_autograd():
         xx = xs.double().requires_grad_(True)
         s64 = m64(xx).sdf
         g64, = torch.autograd.grad(s64, xx, torch.ones_like(s64))
-        es = max(es, float((ss.double() - s64.reshape(-1)).abs().max()))
+        es = max(es, float((ss.double() - s64.detach().reshape(-1)).abs().max()))
         eg = max(eg, float((gs.double() - g64).abs().max()))
         gmax = max(gmax, float(g64.abs().max()))
     print("200k rows: sdf err %.2e abs, grad err %.2e abs = %.2e of max |grad| %.1f" % (es, eg, eg / gmax, gmax))
