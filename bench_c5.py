@@ -65,9 +65,10 @@ def splat_views(pts_world, views, n_views, S, K, occ_grads, z_grads, rgb):
     cutoff = torch.ones(1, device=dev)
     first = torch.arange(nv, device=dev, dtype=torch.int64) * P
     num = torch.full((nv,), P, device=dev, dtype=torch.int64)
-    idx, zbuf, qv, occ = splat.EllipticalRasterizer.apply(scr, ell, cutoff.expand(nv * P), radii, first, num, 0.05, S, K,
-                                                          64 if S > 512 else 32, 0, 10.0)
-    rgba = splat.blend_rgba(idx, qv, occ, None, rgb.repeat(nv, 1))
+    # raster + RGBA blend in one pass over the pixels (the renderer's path, splat.SplatRender)
+    idx, zbuf, qv, occ, rgba = splat.SplatRender.apply(scr, ell, cutoff.expand(nv * P), radii, first, num, 0.05, S, K,
+                                                       64 if S > 512 else 32, 10.0, None, rgb.repeat(nv, 1),
+                                                       splat.NORM_WEIGHT_EPS)
     og = torch.stack([occ_grads[v] for v in views])
     zg = torch.stack([z_grads[v] for v in views])
     ((occ * og).sum() + (zbuf * zg).sum()).backward()

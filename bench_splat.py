@@ -86,9 +86,11 @@ def run(args, dev, peaks, peak_src, steps=None):
                                                 tt["num_points"], 0.05, S, K, 32 if S <= 512 else 64, 0, 10.0)
 
     def fwd_bwd(tt):
+        # the renderer's path (ewa.SurfaceSplattingRenderer): raster + RGBA blend in one pass (splat.SplatRender)
         pts = tt["points"].detach().requires_grad_(True)
-        idx, zbuf, qv, occ = fwd(tt, pts)
-        img = splat.blend_rgba(idx, qv, occ, scaler, rgb)
+        idx, zbuf, qv, occ, img = splat.SplatRender.apply(
+            pts, tt["ellipse"], tt["cutoff"], tt["radii"], tt["first_idx"], tt["num_points"], 0.05, S, K,
+            32 if S <= 512 else 64, 10.0, scaler, rgb, splat.NORM_WEIGHT_EPS)
         ((occ * occ_grad).sum() + (zbuf * zbuf_grad).sum()).backward()
         return img, pts.grad
 

@@ -172,6 +172,19 @@ int isob200_splat_forward(const float* points, const float* ellipse, const float
                           float depth_merging_thres, int occ_inclusive, void* ws, size_t ws_bytes,
                           void* recs, long long capacity, int* out_idx, float* out_zbuf,
                           float* out_qvalue, float* out_occ, void* stream);
+/* isob200_splat_forward with, computed in the raster kernel's epilogue (a pixel's K entries are still in
+ * registers there): the RGBA blend of DSS/core/renderer.py:53-78 (arguments of isob200_splat_blend; feat == NULL:
+ * no blend) and / or the per-point visibility of DSS/core/rasterizer.py:851-857 (isob200_splat_visibility with
+ * mask == NULL; visible (P) uint8 zeroed by the caller, NULL: none).  Default raster variant, K <= 16.  Same bits
+ * as the separate entry points. */
+int isob200_splat_forward_fused(const float* points, const float* ellipse, const float* cutoff,
+                                const float* radii, const int64_t* first_idx, const int64_t* num_points,
+                                int N, long long P, long long max_points_per_cloud, int S, int K,
+                                float depth_merging_thres, int occ_inclusive, void* ws, size_t ws_bytes,
+                                void* recs, long long capacity, int* out_idx, float* out_zbuf,
+                                float* out_qvalue, float* out_occ, const float* scaler, const float* feat,
+                                int feat_stride, int C, float eps, float* out_img, float* out_weights,
+                                unsigned char* visible, void* stream);
 /* points_per_bin of the reference's coarse pass (rasterize_points.cu:353-412; computed there,
  * never returned) -- for the "per-tile point counts bit-exact" parity check */
 int isob200_splat_bin_counts(const float* points, const float* radii, const int64_t* first_idx,

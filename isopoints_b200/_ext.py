@@ -72,6 +72,8 @@ _PROTOS = {
     "isob200_splat_bin": (_i, [_vp, _vp, _vp, _vp, _i, _ll, _ll, _i, _vp, _sz, _vp, _vp]),
     "isob200_splat_forward": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _ll, _ll, _i, _i, _f, _i, _vp, _sz,
                                    _vp, _ll, _vp, _vp, _vp, _vp, _vp]),
+    "isob200_splat_forward_fused": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _ll, _ll, _i, _i, _f, _i, _vp, _sz,
+                                         _vp, _ll, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _f, _vp, _vp, _vp, _vp]),
     "isob200_splat_bin_counts": (_i, [_vp, _vp, _vp, _vp, _i, _ll, _i, _i, _vp, _vp]),
     "isob200_splat_count_pairs": (_i, [_vp, _vp, _vp, _vp, _ll, _i, _vp, _vp]),
     "isob200_splat_occ_backward_ws_bytes": (_sz, [_i, _i, _i, _ll]),

@@ -414,12 +414,27 @@ splat_raster_kernel(const float4* __restrict__ recs, const int* __restrict__ til
 // ---------------------------------------------------------------------------------------------
 constexpr int CHUNK2 = 256;          // records per TMA chunk in v2: one per thread (12 KB)
 
+// Optional work fused into the raster epilogue, where a pixel's K (id, Q) entries are still in registers:
+//  * RGBA blend (DSS/core/renderer.py:53-78 + pytorch3d's NormWeightedCompositor): img = [sum_k w_k f[id_k] /
+//    max(sum_k w_k, eps), occ], w_k = exp(-Q_k / 2) * scaler[id_k] -- the arithmetic of splat_blend_kernel
+//    (splat_bwd.cu) in the same order, without its second read of idx / qvalue (64 B per pixel);
+//  * per-point visibility for the backward (rasterizer.py:851-857): every id of a pixel whose first slot is taken.
+struct RasterEpi {
+  const float* scaler;   // (P) or null
+  const float* feat;     // (P, feat_stride), C <= 4 channels used; null = no blend
+  int feat_stride, C;
+  float eps;
+  float* img;            // (N,S,S,C+1)
+  float* weights;        // (N,S,S,K) or null
+  unsigned char* visible;   // (P) or null; zeroed by the caller
+};
+
 template <int K, int C>
 __global__ void __launch_bounds__(256)
 splat_raster_v2_kernel(const float4* __restrict__ recs, const int* __restrict__ tile_off,
                        const int* __restrict__ tile_cnt, int S, int T, float depth_merging_thres,
                        int occ_inclusive, int* __restrict__ out_idx, float* __restrict__ out_z,
-                       float* __restrict__ out_q, float* __restrict__ out_occ) {
+                       float* __restrict__ out_q, float* __restrict__ out_occ, const RasterEpi epi) {
   __shared__ __align__(128) float4 buf[STAGES][CHUNK2 * REC_F4];
   __shared__ __align__(8) unsigned long long bar[STAGES];
   __shared__ int pcnt[256];
@@ -598,6 +613,34 @@ splat_raster_v2_kernel(const float4* __restrict__ recs, const int* __restrict__ 
 #pragma unroll
     for (int k = 0; k < K; ++k) { pi[k] = oi[k]; pz[k] = oz[k]; pq[k] = oq[k]; }
   }
+  if (epi.visible && oi[0] >= 0) {
+#pragma unroll
+    for (int k = 0; k < K; ++k)
+      if (oi[k] >= 0) epi.visible[oi[k]] = 1;
+  }
+  if (epi.img) {
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    float sw = 0.f;
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+      float wgt = 0.f;
+      if (oi[k] >= 0) {
+        wgt = expf(-0.5f * oq[k]) * (epi.scaler ? epi.scaler[oi[k]] : 1.0f);
+        sw += wgt;
+        const float* f = epi.feat + (size_t)oi[k] * epi.feat_stride;
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+          if (c < epi.C) acc[c] += wgt * f[c];
+      }
+      if (epi.weights) epi.weights[pix * K + k] = wgt;
+    }
+    const float den = fmaxf(sw, epi.eps);
+    float* o = epi.img + pix * (epi.C + 1);
+#pragma unroll
+    for (int c = 0; c < 4; ++c)
+      if (c < epi.C) o[c] = acc[c] / den;
+    o[epi.C] = (size > 0 && (occ_inclusive ? (zmax >= 0.0f) : (zmax > 0.0f))) ? 1.0f : 0.0f;
+  }
 }
 
 // Generic K (17..150, rasterization_utils.cuh:18): same algorithm, list in local memory.
@@ -717,12 +760,12 @@ splat_pair_count_kernel(const float* __restrict__ points, const float* __restric
 template <int K>
 static void launch_raster(int variant, int tiles, cudaStream_t st, const float4* recs, const int* off,
                           const int* cnt, int S, int T, float thres, int occ_incl, int* oi, float* oz,
-                          float* oq, float* oo) {
+                          float* oq, float* oo, const RasterEpi& epi) {
   if (variant != 1) {   // v2: C slots per pixel column; K <= 8 -> 24 (72 KB), else K + 16
     constexpr int C = (K <= 8) ? 24 : K + 16;
     const int smem2 = 3 * C * 256 * (int)sizeof(float);
     cudaFuncSetAttribute(splat_raster_v2_kernel<K, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem2);
-    splat_raster_v2_kernel<K, C><<<tiles, 256, smem2, st>>>(recs, off, cnt, S, T, thres, occ_incl, oi, oz, oq, oo);
+    splat_raster_v2_kernel<K, C><<<tiles, 256, smem2, st>>>(recs, off, cnt, S, T, thres, occ_incl, oi, oz, oq, oo, epi);
     return;
   }
   const int smem = 3 * K * 256 * (int)sizeof(float);
@@ -809,13 +852,47 @@ int isob200_splat_bin(const float* points, const float* radii, const int64_t* fi
 // occ_inclusive: bit 0: 1 = naive-kernel rule q_max_z >= 0 (bin_size == 0), 0 = fine-kernel rule > 0;
 //                bits 8..9: raster variant, 0/2 = v2 (record-centric hit generation, default),
 //                1 = v1 (pixel-centric with warp-level culling).  Results are identical.
+int isob200_splat_forward_fused(const float* points, const float* ellipse, const float* cutoff,
+                                const float* radii, const int64_t* first_idx, const int64_t* num_points,
+                                int N, long long P, long long max_points_per_cloud, int S, int K,
+                                float depth_merging_thres, int occ_inclusive, void* ws, size_t ws_bytes,
+                                void* recs, long long capacity, int* out_idx, float* out_zbuf,
+                                float* out_qvalue, float* out_occ, const float* scaler, const float* feat,
+                                int feat_stride, int C, float eps, float* out_img, float* out_weights,
+                                unsigned char* visible, void* stream_);
+
 int isob200_splat_forward(const float* points, const float* ellipse, const float* cutoff,
                           const float* radii, const int64_t* first_idx, const int64_t* num_points,
                           int N, long long P, long long max_points_per_cloud, int S, int K,
                           float depth_merging_thres, int occ_inclusive, void* ws, size_t ws_bytes,
                           void* recs, long long capacity, int* out_idx, float* out_zbuf,
                           float* out_qvalue, float* out_occ, void* stream_) {
+  return isob200_splat_forward_fused(points, ellipse, cutoff, radii, first_idx, num_points, N, P,
+                                     max_points_per_cloud, S, K, depth_merging_thres, occ_inclusive, ws, ws_bytes,
+                                     recs, capacity, out_idx, out_zbuf, out_qvalue, out_occ, nullptr, nullptr, 0, 0,
+                                     0.f, nullptr, nullptr, nullptr, stream_);
+}
+
+// isob200_splat_forward with the RGBA blend (isob200_splat_blend: scaler (P) or NULL, feat (P, feat_stride) with
+// C <= 4 channels, eps; out_img (N,S,S,C+1), out_weights (N,S,S,K) or NULL) and / or the per-point visibility of
+// isob200_splat_visibility(mask = NULL) (visible (P) uint8, zeroed by the caller) computed in the raster kernel's
+// epilogue.  feat == NULL skips the blend, visible == NULL the visibility.  Needs the default raster variant and
+// K <= 16 when either is requested.  Same bits as the separate kernels.
+int isob200_splat_forward_fused(const float* points, const float* ellipse, const float* cutoff,
+                                const float* radii, const int64_t* first_idx, const int64_t* num_points,
+                                int N, long long P, long long max_points_per_cloud, int S, int K,
+                                float depth_merging_thres, int occ_inclusive, void* ws, size_t ws_bytes,
+                                void* recs, long long capacity, int* out_idx, float* out_zbuf,
+                                float* out_qvalue, float* out_occ, const float* scaler, const float* feat,
+                                int feat_stride, int C, float eps, float* out_img, float* out_weights,
+                                unsigned char* visible, void* stream_) {
   cudaStream_t st = (cudaStream_t)stream_;
+  RasterEpi epi = {scaler, feat, feat_stride, C, eps, feat ? out_img : nullptr, feat ? out_weights : nullptr, visible};
+  if (feat || visible) {
+    ISO_CHECK_ARG(K <= 16 && ((occ_inclusive >> 8) & 3) != 1,
+                  "splat_forward_fused: the fused epilogue needs the default raster variant and K <= 16");
+    ISO_CHECK_ARG(!feat || (out_img && C >= 1 && C <= 4 && feat_stride >= C), "splat_forward_fused: bad blend arguments");
+  }
   ISO_CHECK_ARG(N >= 0 && S > 0 && P >= 0, "splat_forward: bad sizes");
   ISO_CHECK_ARG(K >= 1 && K <= 150, "Must have points_per_pixel <= 150");
   if (N == 0) return ISOB200_OK;
@@ -842,7 +919,7 @@ int isob200_splat_forward(const float* points, const float* ellipse, const float
   const float4* r = (const float4*)recs;
   int* oi = out_idx; float* oz = out_zbuf; float* oq = out_qvalue; float* oo = out_occ;
   const float th = depth_merging_thres;
-#define RK(KK) case KK: launch_raster<KK>(variant, tiles, st, r, w.tile_off, w.tile_cnt, S, T, th, occ_inclusive, oi, oz, oq, oo); break;
+#define RK(KK) case KK: launch_raster<KK>(variant, tiles, st, r, w.tile_off, w.tile_cnt, S, T, th, occ_inclusive, oi, oz, oq, oo, epi); break;
   switch (K) {
     RK(1) RK(2) RK(3) RK(4) RK(5) RK(6) RK(7) RK(8) RK(9) RK(10) RK(11) RK(12) RK(13) RK(14) RK(15) RK(16)
     default:

@@ -312,14 +312,21 @@ class SurfaceSplatting:
         with torch.no_grad():
             info = self._get_per_point_info(filtered, **kwargs)
         screen = self.transform(filtered, **kwargs)
-        idx, zbuf, qvalue, occ = rasterize_elliptical_points(
+        # the renderer asks for its RGBA blend (renderer.py:53-78) in the same pass over the pixels
+        blend = None
+        if kwargs.get("blend_rgb", False) and filtered.features_packed() is not None:
+            from .splat import NORM_WEIGHT_EPS
+            blend = (info["scaler"], filtered.features_packed()[:, :3], NORM_WEIGHT_EPS)
+        out = rasterize_elliptical_points(
             screen, info["ellipse_params"], info["cutoff_threshold"], info["radii"],
             depth_merging_threshold=rs.depth_merging_threshold, image_size=rs.image_size,
             points_per_pixel=rs.points_per_pixel, bin_size=rs.bin_size, max_points_per_bin=rs.max_points_per_bin,
-            radii_backward_scaler=rs.radii_backward_scaler, clip_pts_grad=rs.clip_pts_grad)
+            radii_backward_scaler=rs.radii_backward_scaler, clip_pts_grad=rs.clip_pts_grad, blend=blend)
+        idx, zbuf, qvalue, occ = out[:4]
         frag_scaler = gather_with_neg_idx(info["scaler"], 0, idx.view(-1).long()).view_as(qvalue)   # :634-636
         fragments = PointFragments(idx=idx, zbuf=zbuf, qvalue=qvalue, scaler=frag_scaler, occupancy=occ)
-        self._last = (fragments, info["scaler"])   # per-point scaler of these fragments, for the renderer's blend
+        # per-point scaler of these fragments (and the images, when blended here) for the renderer
+        self._last = (fragments, info["scaler"], out[4] if blend is not None else None)
         if point_clouds_filter is not None:
             # visibility of the points that survived the renderable filter, scattered back to the points that
             # entered it, then padded with the first indices of the (extended) input clouds (:642-650): (B, max_P)
@@ -357,8 +364,11 @@ class SurfaceSplattingRenderer:
             return None
         fragments = kwargs.get("fragments", None)
         if fragments is None:
-            fragments, point_clouds = self.rasterizer(point_clouds, **kwargs)
+            fragments, point_clouds = self.rasterizer(point_clouds, blend_rgb=True, **kwargs)
         last = getattr(self.rasterizer, "_last", None)
+        if last is not None and last[0] is fragments and len(last) > 2 and last[2] is not None:
+            images = last[2]                      # blended in the raster kernel's epilogue
+            return (images, fragments) if kwargs.get("verbose", False) else images
         if last is not None and last[0] is fragments:
             scaler = last[1]
         else:

@@ -72,7 +72,17 @@ def _check_inputs(points, ellipse, cutoff, radii, first_idx, num_points):
         raise RuntimeError("cloud_to_packed_first_idx and num_points_per_cloud must be (N,) tensors of equal size")
 
 
-def _splat(points, ellipse, cutoff, radii, first_idx, num_points, depth_merging_thres, S, K, occ_inclusive):
+def _fusable(K):
+    """The raster kernel's fused epilogue (blend / visibility) exists for the default variant and K <= 16."""
+    return int(K) <= 16 and (RASTER_VARIANT & 3) != 1
+
+
+def _splat(points, ellipse, cutoff, radii, first_idx, num_points, depth_merging_thres, S, K, occ_inclusive,
+           blend=None, want_visible=False):
+    """idx, zbuf, qvalue, occ of DSS._C.splat_points.  ``blend`` = (scaler (P,) | None, feat (P,C), eps,
+    want_weights): also the RGBA image (N,S,S,C+1) [and the blend weights (N,S,S,K)] from the raster kernel's
+    epilogue; ``want_visible``: also the per-point visibility (P,) uint8 of rasterizer.py:851-857.  With either,
+    returns (idx, zbuf, qvalue, occ, img, weights, visible) (None where not asked for)."""
     _check_inputs(points, ellipse, cutoff, radii, first_idx, num_points)
     lib = _ext.lib()
     S, K = int(S), int(K)
@@ -87,12 +97,22 @@ def _splat(points, ellipse, cutoff, radii, first_idx, num_points, depth_merging_
     first_idx = _i64c(first_idx, dev)
     num_points = _i64c(num_points, dev)
     N = num_points.shape[0]
+    extra = blend is not None or want_visible
     idx = torch.empty((N, S, S, K), dtype=torch.int32, device=dev)
     zbuf = torch.empty((N, S, S, K), dtype=torch.float32, device=dev)
     qvalue = torch.empty((N, S, S, K), dtype=torch.float32, device=dev)
     occ = torch.empty((N, S, S), dtype=torch.float32, device=dev)
+    img = weights = vis = scaler = feat = None
+    C, eps = 0, 0.0
+    if blend is not None:
+        scaler, feat, eps, want_w = blend
+        C = feat.shape[1]
+        img = torch.empty((N, S, S, C + 1), dtype=torch.float32, device=dev)
+        weights = torch.empty((N, S, S, K), dtype=torch.float32, device=dev) if want_w else None
+    if want_visible:
+        vis = torch.zeros((P,), dtype=torch.uint8, device=dev)
     if idx.numel() == 0:
-        return idx, zbuf, qvalue, occ
+        return (idx, zbuf, qvalue, occ, img, weights, vis) if extra else (idx, zbuf, qvalue, occ)
     st = _ext.stream(dev)
     ws = _ext.workspace(lib.isob200_splat_ws_bytes(N, S), dev)
     total = torch.empty((1,), dtype=torch.int32, device=dev)
@@ -102,13 +122,21 @@ def _splat(points, ellipse, cutoff, radii, first_idx, num_points, depth_merging_
                                      N, P, maxp, S, _ext.ptr(ws), ws.numel(), _ext.ptr(total), st))
     cap = int(total.item())          # the one read-back: sizes the per-tile record buffer
     recs = torch.empty((max(cap, 1) * lib.isob200_splat_record_bytes(),), dtype=torch.uint8, device=dev)
-    _ext.check(lib.isob200_splat_forward(
+    flags = (1 if occ_inclusive else 0) | ((RASTER_VARIANT & 3) << 8)
+    if not extra:
+        _ext.check(lib.isob200_splat_forward(
+            _ext.ptr(points), _ext.ptr(ellipse), _ext.ptr(cutoff), _ext.ptr(radii), _ext.ptr(first_idx),
+            _ext.ptr(num_points), N, P, maxp, S, K, float(depth_merging_thres), flags,
+            _ext.ptr(ws), ws.numel(), _ext.ptr(recs), cap, _ext.ptr(idx), _ext.ptr(zbuf), _ext.ptr(qvalue),
+            _ext.ptr(occ), st))
+        return idx, zbuf, qvalue, occ
+    _ext.check(lib.isob200_splat_forward_fused(
         _ext.ptr(points), _ext.ptr(ellipse), _ext.ptr(cutoff), _ext.ptr(radii), _ext.ptr(first_idx),
-        _ext.ptr(num_points), N, P, maxp, S, K, float(depth_merging_thres),
-        (1 if occ_inclusive else 0) | ((RASTER_VARIANT & 3) << 8),
+        _ext.ptr(num_points), N, P, maxp, S, K, float(depth_merging_thres), flags,
         _ext.ptr(ws), ws.numel(), _ext.ptr(recs), cap, _ext.ptr(idx), _ext.ptr(zbuf), _ext.ptr(qvalue),
-        _ext.ptr(occ), st))
-    return idx, zbuf, qvalue, occ
+        _ext.ptr(occ), _ext.ptr(scaler), _ext.ptr(feat), 0 if feat is None else feat.stride(0), C, float(eps),
+        _ext.ptr(img), _ext.ptr(weights), _ext.ptr(vis), st))
+    return idx, zbuf, qvalue, occ, img, weights, vis
 
 
 def bin_counts(points, radii, first_idx, num_points, image_size, bin_size):
@@ -266,49 +294,130 @@ class EllipticalRasterizer(autograd.Function):
     def forward(ctx, pts_screen, ellipse_param, cutoff_threshold, radii, cloud_to_packed_first_idx,
                 num_points_per_cloud, depth_merging_threshold, image_size, points_per_pixel, bin_size=0,
                 max_points_per_bin=0, radii_backward_scaler=10.0):
-        idx, zbuf, qvalue_map, occ_map = _C.splat_points(
-            pts_screen, ellipse_param, cutoff_threshold, radii, cloud_to_packed_first_idx, num_points_per_cloud,
-            depth_merging_threshold, image_size, points_per_pixel, bin_size, max_points_per_bin)
+        vis = None
+        if ctx.needs_input_grad[0] and _fusable(points_per_pixel) and pts_screen.shape[0] > 0:
+            # a backward will follow: its per-point visibility (rasterizer.py:851-857) comes out of the raster
+            # kernel's epilogue instead of a second pass over idx
+            _check_bins(image_size, bin_size)
+            idx, zbuf, qvalue_map, occ_map, _, _, vis = _splat(
+                pts_screen, ellipse_param, cutoff_threshold, radii, cloud_to_packed_first_idx, num_points_per_cloud,
+                depth_merging_threshold, image_size, points_per_pixel, occ_inclusive=(bin_size == 0),
+                want_visible=True)
+        else:
+            idx, zbuf, qvalue_map, occ_map = _C.splat_points(
+                pts_screen, ellipse_param, cutoff_threshold, radii, cloud_to_packed_first_idx, num_points_per_cloud,
+                depth_merging_threshold, image_size, points_per_pixel, bin_size, max_points_per_bin)
         ctx.radii_backward_scaler = radii_backward_scaler
         ctx.depth_merging_threshold = depth_merging_threshold
-        ctx.save_for_backward(pts_screen, radii, idx, cloud_to_packed_first_idx, num_points_per_cloud)
+        ctx.has_vis = vis is not None
+        saved = (pts_screen, radii, idx, cloud_to_packed_first_idx, num_points_per_cloud)
+        ctx.save_for_backward(*(saved + ((vis,) if vis is not None else ())))
         ctx.mark_non_differentiable(idx)
         return idx, zbuf, qvalue_map, occ_map
 
     @staticmethod
     def backward(ctx, idx_grad, zbuf_grad, qvalue_grad, occ_grad):
-        pts_screen, radii, idx, first_idx, num_points = ctx.saved_tensors
-        radii_s = ctx.radii_backward_scaler
-        if radii_s == 0:
-            raise RuntimeError("radii_backward_scaler == 0 (WeightBackward) is not implemented in the reference "
-                               "either (rasterizer.py:776-777 saves 4 tensors, :809-811 unpacks 8)")
-        dev = pts_screen.device
-        P = pts_screen.shape[0]
-        pts = _f32c(pts_screen.detach(), "pts_screen")
-        radii = _f32c(radii, "radii")
-        first_idx = _i64c(first_idx, dev)
-        num_points = _i64c(num_points, dev)
-        grads = torch.zeros((P, 3), dtype=torch.float32, device=dev)
-        if occ_grad is not None and P > 0:
-            vis = visibility_mask(idx, P)                                    # rasterizer.py:851-857
-            rs = per_view_search_radius(radii, vis, first_idx, num_points, radii_s)             # :881-884
-            _occ_backward(pts, radii, vis.view(torch.uint8), first_idx, num_points, rs, radii_s,
-                          _f32c(occ_grad, "occ_grad"), 0, grads, 3)
-        if zbuf_grad is not None and P > 0:
-            N, H, W, K = idx.shape
-            _ext.check(_ext.lib().isob200_splat_zbuf_backward(
-                _ext.ptr(idx), _ext.ptr(_f32c(zbuf_grad, "zbuf_grad")), N, H, W, K,
-                grads.data_ptr() + 8, 3, _ext.stream(dev)))                  # column 2 of (P,3)
+        saved = ctx.saved_tensors
+        pts_screen, radii, idx, first_idx, num_points = saved[:5]
+        grads = _points_backward(pts_screen, radii, idx, first_idx, num_points, ctx.radii_backward_scaler,
+                                 saved[5].view(torch.bool) if ctx.has_vis else None, zbuf_grad, occ_grad)
         return (grads,) + (None,) * 11
+
+
+def _check_bins(image_size, bin_size):
+    if bin_size != 0:
+        num_bins = 1 + (int(image_size) - 1) // int(bin_size)
+        if num_bins >= kMaxPointsPerBin:   # rasterize_points.cu:462-468
+            raise RuntimeError("Got %d; that's too many!" % num_bins)
+
+
+def _points_backward(pts_screen, radii, idx, first_idx, num_points, radii_s, vis, zbuf_grad, occ_grad):
+    """EllipticalRasterizer.backward (rasterizer.py:784-973): (P,3) gradient of the screen-space points from the
+    occupancy (xy) and depth (z) gradients.  ``vis``: per-point visibility when the forward already produced it."""
+    if radii_s == 0:
+        raise RuntimeError("radii_backward_scaler == 0 (WeightBackward) is not implemented in the reference "
+                           "either (rasterizer.py:776-777 saves 4 tensors, :809-811 unpacks 8)")
+    dev = pts_screen.device
+    P = pts_screen.shape[0]
+    pts = _f32c(pts_screen.detach(), "pts_screen")
+    radii = _f32c(radii, "radii")
+    first_idx = _i64c(first_idx, dev)
+    num_points = _i64c(num_points, dev)
+    grads = torch.zeros((P, 3), dtype=torch.float32, device=dev)
+    if occ_grad is not None and P > 0:
+        if vis is None:
+            vis = visibility_mask(idx, P)                                # rasterizer.py:851-857
+        rs = per_view_search_radius(radii, vis, first_idx, num_points, radii_s)             # :881-884
+        _occ_backward(pts, radii, vis.view(torch.uint8), first_idx, num_points, rs, radii_s,
+                      _f32c(occ_grad, "occ_grad"), 0, grads, 3)
+    if zbuf_grad is not None and P > 0:
+        N, H, W, K = idx.shape
+        _ext.check(_ext.lib().isob200_splat_zbuf_backward(
+            _ext.ptr(idx), _ext.ptr(_f32c(zbuf_grad, "zbuf_grad")), N, H, W, K,
+            grads.data_ptr() + 8, 3, _ext.stream(dev)))                  # column 2 of (P,3)
+    return grads
+
+
+class SplatRender(autograd.Function):
+    """EllipticalRasterizer + the renderer's RGBA blend (renderer.py:53-78) in ONE pass over the pixels: the blend
+    runs in the raster kernel's epilogue.  Outputs (idx, zbuf, qvalue, occupancy, images); gradients: to the
+    screen-space points through occupancy (incl. the image's alpha channel, which IS the occupancy) and depth as in
+    EllipticalRasterizer.backward, to the features through the blend weights."""
+
+    @staticmethod
+    def forward(ctx, pts_screen, ellipse_param, cutoff_threshold, radii, first_idx, num_points,
+                depth_merging_threshold, image_size, points_per_pixel, bin_size, radii_backward_scaler, scaler,
+                features, eps):
+        _check_bins(image_size, bin_size)
+        feat = features if features.dtype == torch.float32 else features.float()
+        if feat.stride(-1) != 1:
+            feat = feat.contiguous()
+        sc = None if scaler is None else _f32c(scaler.reshape(-1), "scaler")
+        need_pts, need_feat = ctx.needs_input_grad[0], ctx.needs_input_grad[12]
+        idx, zbuf, qvalue, occ, img, weights, vis = _splat(
+            pts_screen, ellipse_param, cutoff_threshold, radii, first_idx, num_points, depth_merging_threshold,
+            image_size, points_per_pixel, occ_inclusive=(bin_size == 0),
+            blend=(sc, feat.detach(), eps, need_feat), want_visible=need_pts and pts_screen.shape[0] > 0)
+        ctx.meta = (radii_backward_scaler, feat.shape, eps, vis is not None, weights is not None)
+        extra = tuple(t for t in (vis, weights) if t is not None)
+        ctx.save_for_backward(pts_screen, radii, idx, first_idx, num_points, *extra)
+        ctx.mark_non_differentiable(idx)
+        return idx, zbuf, qvalue, occ, img
+
+    @staticmethod
+    def backward(ctx, idx_grad, zbuf_grad, qvalue_grad, occ_grad, img_grad):
+        radii_s, fshape, eps, has_vis, has_w = ctx.meta
+        saved = ctx.saved_tensors
+        pts_screen, radii, idx, first_idx, num_points = saved[:5]
+        vis = saved[5].view(torch.bool) if has_vis else None
+        weights = saved[5 + int(has_vis)] if has_w else None
+        C = fshape[1]
+        gpts = gfeat = None
+        if ctx.needs_input_grad[0]:
+            og = occ_grad
+            if img_grad is not None:                 # alpha = occupancy (renderer.py:76-78)
+                a = img_grad[..., C]
+                og = a if og is None else og + a
+            gpts = _points_backward(pts_screen, radii, idx, first_idx, num_points, radii_s, vis, zbuf_grad,
+                                    None if og is None else og.contiguous())
+        if ctx.needs_input_grad[12] and img_grad is not None and weights is not None:
+            N, H, W, K = idx.shape
+            gfeat = torch.zeros(fshape, dtype=torch.float32, device=idx.device)
+            _ext.check(_ext.lib().isob200_splat_blend_backward(
+                _ext.ptr(idx), _ext.ptr(weights), _ext.ptr(img_grad.contiguous()), N * H * W, K, C, float(eps),
+                _ext.ptr(gfeat), gfeat.stride(0), _ext.stream(idx.device)))
+        return (gpts,) + (None,) * 11 + (gfeat, None)
 
 
 def rasterize_elliptical_points(pcls_screen, ellipse_params, cutoff_threshold, radii,
                                 depth_merging_threshold: float = 0.05, image_size: int = 512,
                                 points_per_pixel: int = 5, bin_size: Optional[int] = None,
                                 max_points_per_bin: Optional[int] = None, radii_backward_scaler: float = 10.0,
-                                clip_pts_grad: float = -1.0):
+                                clip_pts_grad: float = -1.0, blend=None):
     """DSS/core/rasterizer.py:678-740.  ``pcls_screen`` duck-types ``points_packed()``,
-    ``cloud_to_packed_first_idx()``, ``num_points_per_cloud()``."""
+    ``cloud_to_packed_first_idx()``, ``num_points_per_cloud()``.  ``blend`` = (scaler (P,) | None, features (P,C),
+    eps): also return the renderer's RGBA images (renderer.py:53-78) as a fifth output, computed in the raster
+    kernel's epilogue (``SplatRender``) when that exists for the settings, by ``blend_rgba`` otherwise."""
     points_packed = pcls_screen.points_packed()
     cloud_to_packed_first_idx = pcls_screen.cloud_to_packed_first_idx()
     num_points_per_cloud = pcls_screen.num_points_per_cloud()
@@ -334,10 +443,17 @@ def rasterize_elliptical_points(pcls_screen, ellipse_params, cutoff_threshold, r
             norm = g.norm(dim=-1, keepdim=True)
             return torch.where(norm > m, g * (m / norm.clamp_min(1e-20)), g)
         points_packed.register_hook(_clip)
-    return EllipticalRasterizer.apply(points_packed, ellipse_params, cutoff_threshold, radii,
-                                      cloud_to_packed_first_idx, num_points_per_cloud, depth_merging_threshold,
-                                      image_size, points_per_pixel, bin_size, max_points_per_bin,
-                                      radii_backward_scaler)
+    if blend is not None and _fusable(points_per_pixel) and blend[1].shape[1] <= 4:
+        return SplatRender.apply(points_packed, ellipse_params, cutoff_threshold, radii, cloud_to_packed_first_idx,
+                                 num_points_per_cloud, depth_merging_threshold, image_size, points_per_pixel,
+                                 bin_size, radii_backward_scaler, blend[0], blend[1], blend[2])
+    out = EllipticalRasterizer.apply(points_packed, ellipse_params, cutoff_threshold, radii,
+                                     cloud_to_packed_first_idx, num_points_per_cloud, depth_merging_threshold,
+                                     image_size, points_per_pixel, bin_size, max_points_per_bin,
+                                     radii_backward_scaler)
+    if blend is not None:
+        out = out + (blend_rgba(out[0], out[2], out[3], blend[0], blend[1], blend[2]),)
+    return out
 
 
 class _Blend(autograd.Function):

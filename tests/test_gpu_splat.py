@@ -305,3 +305,46 @@ def test_blend_and_feature_gradient():
     col = (wt[..., None] * rgb2[j]).sum(-2) / wt.sum(-1, keepdim=True).clamp_min(1e-4)
     (col * w[..., :3]).sum().backward()
     np.testing.assert_allclose(rgb.grad.cpu().numpy(), rgb2.grad.cpu().numpy(), rtol=1e-4, atol=1e-6)
+
+
+@pytest.mark.parametrize("K,C", [(8, 3), (5, 4), (1, 1), (16, 2)])
+def test_fused_blend_and_visibility_equal_the_separate_kernels(K, C):
+    """SplatRender (RGBA blend + per-point visibility in the raster kernel's epilogue) against the two-step path it
+    replaces -- EllipticalRasterizer + blend_rgba, visibility_mask: same bits forward, same gradients to the screen
+    points (occupancy incl. the image's alpha channel, depth) and to the features."""
+    S = 96
+    inp = make_splat_inputs(3, [2500, 0, 1800], S, seed=31 + K, sigma_px=1.7)
+    t = _t(inp)
+    P = inp["points"].shape[0]
+    g = torch.Generator().manual_seed(K)
+    scaler = (torch.rand(P, generator=g) + 0.5).to(DEV)
+    feat0 = torch.rand(P, C, generator=g).to(DEV)
+    w_img = torch.randn(3, S, S, C + 1, generator=g).to(DEV)
+    w_occ = (torch.randn(3, S, S, generator=g) * (torch.rand(3, S, S, generator=g) < 0.2)).to(DEV)
+    w_z = torch.randn(3, S, S, K, generator=g).to(DEV)
+    res = {}
+    for fused in (False, True):
+        pts = t["points"].clone().requires_grad_(True)
+        feat = feat0.clone().requires_grad_(True)
+        if fused:
+            idx, zbuf, qv, occ, img = splat.SplatRender.apply(pts, t["ellipse"], t["cutoff"], t["radii"],
+                                                              t["first_idx"], t["num_points"], 0.05, S, K, 16, 10.0,
+                                                              scaler, feat, splat.NORM_WEIGHT_EPS)
+        else:
+            idx, zbuf, qv, occ = splat.EllipticalRasterizer.apply(pts, t["ellipse"], t["cutoff"], t["radii"],
+                                                                  t["first_idx"], t["num_points"], 0.05, S, K, 16,
+                                                                  10000, 10.0)
+            img = splat.blend_rgba(idx, qv, occ, scaler, feat)
+        ((img * w_img).sum() + (occ * w_occ).sum() + (zbuf * w_z).sum()).backward()
+        res[fused] = (idx, zbuf, qv, occ, img.detach(), pts.grad, feat.grad)
+    for a, b in zip(res[False][:5], res[True][:5]):
+        assert torch.equal(a, b)
+    # xy (occupancy) gradients are plain per-point sums in a fixed order: identical; z and feature gradients are
+    # fp32 atomics in both paths (rasterize_points.cu:835-843 does the same): equal up to summation order
+    assert torch.equal(res[True][5][:, :2], res[False][5][:, :2])
+    np.testing.assert_allclose(res[True][5][:, 2].cpu().numpy(), res[False][5][:, 2].cpu().numpy(), rtol=5e-4, atol=1e-5)
+    np.testing.assert_allclose(res[True][6].cpu().numpy(), res[False][6].cpu().numpy(), rtol=5e-4, atol=1e-5)
+    # the epilogue's visibility == the idx sweep
+    out = splat._splat(t["points"], t["ellipse"], t["cutoff"], t["radii"], t["first_idx"], t["num_points"], 0.05, S, K,
+                       False, want_visible=True)
+    assert torch.equal(out[6].bool(), splat.visibility_mask(out[0], P))
