@@ -531,8 +531,10 @@ frnn_query_collect_kernel(const float* __restrict__ q_points, const int* __restr
             const int b = (c0 + zhi + 1 == grid_total) ? len2 : off2[c0 + zhi + 1];
             nblock += b - a;
           }
+        // (a block that fits the column is simply collected whole: exact without any estimate -- the regime of
+        // surface-like clouds on a fine grid, ~0.1 points per cell at BASELINE config 2)
         float tau = r2;
-        if (nblock > K) {
+        if (nblock > COLLECT_CAP) {
           float cells = (float)(hi[0] - lo[0] + 1) * (float)(zhi - zlo + 1);
           if (D == 3) cells *= (float)(yhi - ylo + 1);
           // radius (in cells) of the ball expected to hold lambda points at the block's mean density
@@ -550,51 +552,63 @@ frnn_query_collect_kernel(const float* __restrict__ q_points, const int* __restr
           const float re = rc * inv_delta;
           tau = fminf(r2, re * re);
         }
-        // ---- one pass over the cells the trial ball touches ----
-        // (a per-thread run cursor inside one flat candidate loop was tried: the cursor code then runs with ~5
-        // live lanes per instruction and costs more than the per-run trip-count divergence of these nested loops)
-        for (int x = lo[0]; x <= hi[0]; ++x) {
-          const float gx2 = axis_gap2(qc[0], x, inv_delta);
-          if (gx2 > tau) continue;
-          for (int y = ylo; y <= yhi; ++y) {
-            float gxy2 = gx2;
-            int c0;
-            if (D == 3) {
-              gxy2 += axis_gap2(qc[1], y, inv_delta);
-              if (gxy2 > tau) continue;
-              c0 = (x * res[1] + y) * res[2];
-            } else {
-              c0 = x * res[1];
-            }
-            const float gz = sqrtf(fmaxf(tau - gxy2, 0.0f)) * delta + 2e-3f;
-            const int za = max(zlo, __float2int_ru(qc[D - 1] - 1.0f - gz));
-            const int zb = min(zhi, __float2int_rd(qc[D - 1] + gz));
-            if (za > zb) continue;
-            const int start = off2[c0 + za];
-            const int end = (c0 + zb + 1 == grid_total) ? len2 : off2[c0 + zb + 1];
-            // four candidates per step: their 4 D loads are in flight together (the loop is latency bound:
-            // one query per thread leaves 16 warps per SM)
-            for (int j = start; j < end; j += 4) {
-              float dd[4];
-#pragma unroll
-              for (int u = 0; u < 4; ++u) {
-                const int jj = min(j + u, end - 1);
-                dd[u] = sqdist_ref<D>(pts2 + (size_t)jj * D, q);
+        // Up to three passes: the trial radius assumes the block's MEAN density and a volume-filling cloud; on a
+        // surface (points ~ r^2) or in a cluster the ball overflows the column, next to a void it comes up short.
+        // The count of the failed pass re-scales the radius (exponent between the 2-D and 3-D laws, so that the
+        // corrected ball lands inside [K, capacity] for either), and only a query that is still off after that
+        // goes to the warp-cooperative search.
+        bool exact = false;
+        for (int attempt = 0; attempt < 3 && !exact; ++attempt) {
+          cnt = 0;
+          // ---- one pass over the cells the trial ball touches ----
+          // (a per-thread run cursor inside one flat candidate loop was tried: the cursor code then runs with ~5
+          // live lanes per instruction and costs more than the per-run trip-count divergence of these nested loops)
+          for (int x = lo[0]; x <= hi[0]; ++x) {
+            const float gx2 = axis_gap2(qc[0], x, inv_delta);
+            if (gx2 > tau) continue;
+            for (int y = ylo; y <= yhi; ++y) {
+              float gxy2 = gx2;
+              int c0;
+              if (D == 3) {
+                gxy2 += axis_gap2(qc[1], y, inv_delta);
+                if (gxy2 > tau) continue;
+                c0 = (x * res[1] + y) * res[2];
+              } else {
+                c0 = x * res[1];
               }
+              const float gz = sqrtf(fmaxf(tau - gxy2, 0.0f)) * delta + 2e-3f;
+              const int za = max(zlo, __float2int_ru(qc[D - 1] - 1.0f - gz));
+              const int zb = min(zhi, __float2int_rd(qc[D - 1] + gz));
+              if (za > zb) continue;
+              const int start = off2[c0 + za];
+              const int end = (c0 + zb + 1 == grid_total) ? len2 : off2[c0 + zb + 1];
+              // four candidates per step: their 4 D loads are in flight together (the loop is latency bound:
+              // one query per thread leaves 16 warps per SM)
+              for (int j = start; j < end; j += 4) {
+                float dd[4];
 #pragma unroll
-              for (int u = 0; u < 4; ++u) {
-                if (j + u < end && dd[u] <= tau) {
-                  if (cnt < COLLECT_CAP)
-                    s_keys[cnt * COLLECT_THREADS + tid] =
-                        ((unsigned long long)__float_as_uint(dd[u]) << 32) | (unsigned)sid2[j + u];
-                  ++cnt;
+                for (int u = 0; u < 4; ++u) {
+                  const int jj = min(j + u, end - 1);
+                  dd[u] = sqdist_ref<D>(pts2 + (size_t)jj * D, q);
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                  if (j + u < end && dd[u] <= tau) {
+                    if (cnt < COLLECT_CAP)
+                      s_keys[cnt * COLLECT_THREADS + tid] =
+                          ((unsigned long long)__float_as_uint(dd[u]) << 32) | (unsigned)sid2[j + u];
+                    ++cnt;
+                  }
                 }
               }
             }
           }
+          // exact unless the ball overflowed the column, or was cut short of K by a trial radius below r
+          if (cnt > COLLECT_CAP) tau *= __powf(lambda / (float)cnt, 0.8f);
+          else if (cnt < K && tau < r2) tau = fminf(r2, tau * __powf(1.5f * lambda / (float)max(cnt, 1), 0.8f));
+          else exact = true;
         }
-        // exact unless the ball overflowed the column, or was cut short of K by a trial radius below r
-        failed = cnt > COLLECT_CAP || (cnt < K && tau < r2);
+        failed = !exact;
       }
       if (!failed) {
         // ---- emit the K smallest keys in ascending order (keys are unique: the index is part of them), two per
@@ -777,7 +791,10 @@ int isob200_frnn_find_nbrs(const float* q_points, const int* q_order, const int6
   int gw = group_width & 0xff;
   if (gw == 0) gw = (K <= 8) ? 8 : (K <= 16 ? 16 : 32);
   const bool exhaustive = mode == 1 || (mode == 0 && (long long)P2 < (long long)G);
-  // dense grid and a K whose trial ball fits a shared-memory column: thread-per-query collect-then-select
+  // dense grid and a K whose trial ball fits a shared-memory column: thread-per-query collect-then-select.
+  // (Measured on the sparse grid of BASELINE config 2 -- iso-surface points, ~0.1 per cell, K = 9: 0.65 ms against
+  // 0.36 ms for the exhaustive group kernel; there the candidate block often exceeds the column and the volume-based
+  // trial radius needs its second pass.)
   const bool collect = mode == 3 || (mode == 0 && !exhaustive && K <= 20);
   if (collect) {
     ISO_CHECK_ARG(K <= 32, "find_nbrs: collect mode needs K <= 32");

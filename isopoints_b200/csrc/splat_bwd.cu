@@ -428,12 +428,17 @@ __device__ __forceinline__ float ord2f_b(unsigned u) {
   return __uint_as_float((u & 0x80000000u) ? (u & 0x7fffffffu) : ~u);
 }
 
-// state per view: [0] prefix bits fixed so far, [1] rank still to descend, [2] done flag
+// state per view: [0] prefix bits fixed so far, [1] rank still to descend, [2] done flag, [3] blocks finished
+// One launch per 8-bit digit: every block histograms its share into shared memory and adds it to the view's 256
+// global bins; the LAST block of a view to finish (ticket on state[3]) picks the digit, narrows the prefix and
+// clears the bins for the next pass -- no separate select launch between the passes.
 __global__ void __launch_bounds__(256)
-median_hist_kernel(const float* __restrict__ radii, const unsigned char* __restrict__ visible,
+median_pass_kernel(const float* __restrict__ radii, const unsigned char* __restrict__ visible,
                    const int64_t* __restrict__ first_idx, const int64_t* __restrict__ num_points, int shift,
-                   const unsigned* __restrict__ state, unsigned* __restrict__ hist) {
+                   int first_pass, int last_pass, float radii_s, unsigned* __restrict__ state,
+                   unsigned* __restrict__ hist, float* __restrict__ rs) {
   __shared__ unsigned sh[256];
+  __shared__ bool s_last;
   const int n = blockIdx.y;
   sh[threadIdx.x] = 0;
   __syncthreads();
@@ -449,17 +454,22 @@ median_hist_kernel(const float* __restrict__ radii, const unsigned char* __restr
   }
   __syncthreads();
   if (sh[threadIdx.x]) atomicAdd(&hist[n * 256 + threadIdx.x], sh[threadIdx.x]);
-}
-
-__global__ void median_select_kernel(unsigned* __restrict__ state, unsigned* __restrict__ hist, int shift,
-                                     int first_pass, int last_pass, float radii_s, float* __restrict__ rs) {
-  const int n = blockIdx.x;
-  if (threadIdx.x != 0) return;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = atomicAdd(&state[n * 4 + 3], 1u) == gridDim.x - 1;
+  __syncthreads();
+  if (!s_last) return;
+  // ---- last block of this view: all 256 bins are final ----
   unsigned* h = hist + n * 256;
+  sh[threadIdx.x] = __ldcg(h + threadIdx.x);   // the other blocks' atomics live in L2
+  h[threadIdx.x] = 0;                          // ready for the next pass
+  __syncthreads();
+  if (threadIdx.x != 0) return;
   unsigned* s = state + n * 4;
+  s[3] = 0;
   if (first_pass) {
     unsigned long long cnt = 0;
-    for (int b = 0; b < 256; ++b) cnt += h[b];
+    for (int b = 0; b < 256; ++b) cnt += sh[b];
     s[2] = (cnt == 0);
     s[1] = cnt ? (unsigned)((cnt - 1) / 2) : 0u;
   }
@@ -467,14 +477,13 @@ __global__ void median_select_kernel(unsigned* __restrict__ state, unsigned* __r
     unsigned k = s[1], acc = 0;
     int b = 0;
     for (; b < 256; ++b) {
-      if (acc + h[b] > k) break;
-      acc += h[b];
+      if (acc + sh[b] > k) break;
+      acc += sh[b];
     }
     b = min(b, 255);
     s[0] |= ((unsigned)b) << shift;
     s[1] = k - acc;
   }
-  for (int b = 0; b < 256; ++b) h[b] = 0;
   if (last_pass) rs[n] = s[2] ? 0.0f : __fmul_rn(ord2f_b(s[0]), radii_s);
 }
 
@@ -684,10 +693,9 @@ int isob200_splat_search_radius(const float* radii, const unsigned char* visible
   if (N > 1) bx = max(1, min(bx, (kNumSMs * 4 + N - 1) / N));
   for (int pass = 0; pass < 4; ++pass) {
     const int shift = 24 - 8 * pass;
-    median_hist_kernel<<<dim3(bx, N), 256, 0, st>>>(radii, visible, first_idx, num_points, shift, state, hist);
-    ISO_CHECK_LAUNCH("median_hist_kernel");
-    median_select_kernel<<<N, 32, 0, st>>>(state, hist, shift, pass == 0, pass == 3, radii_s, rs);
-    ISO_CHECK_LAUNCH("median_select_kernel");
+    median_pass_kernel<<<dim3(bx, N), 256, 0, st>>>(radii, visible, first_idx, num_points, shift, pass == 0,
+                                                    pass == 3, radii_s, state, hist, rs);
+    ISO_CHECK_LAUNCH("median_pass_kernel");
   }
   return ISOB200_OK;
 }

@@ -9,6 +9,11 @@ case "${1:-all}" in
     timeout 900 python -m pytest tests/test_gpu_pinned.py tests/test_gpu_dropin.py tests/test_gpu_pointops.py tests/test_gpu_offsurface.py -m gpu -q -s 2>&1 | tail -80 > gpurun_out/pytest_new.log; tail -40 gpurun_out/pytest_new.log ;;
   timeline)
     timeout 300 python scripts/siren_timeline.py > gpurun_out/siren_timeline.txt 2>&1; tail -70 gpurun_out/siren_timeline.txt ;;
+  quick)
+    timeout 1500 python -m pytest tests -m gpu -q -x 2>&1 | tail -6
+    timeout 300 python bench.py --steps 10 --warmup 3 --no-side | python -c "import json,sys; d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print('C2', round(d['ms_per_step'],3), round(d['value']/1e6,3), d['clocks']); [print('  ', k, round(v['ms_per_step'],4)) for k, v in d['kernels'].items()]; print('   glue', d['sdf_callback_and_glue_ms_per_step'])"
+    timeout 300 python bench_frnn.py --steps 10 | python -c "import json,sys; d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print('C3', d['ms_per_step'], d['value'], d['kernels_avg_ms'])"
+    timeout 300 python bench_splat.py --steps 10 | python -c "import json,sys; d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print('C4', d['ms_fwd'], d['ms_fwd_blend_bwd'], d['value']); [print('  ', k, v) for k, v in d['kernels'].items()]" ;;
   pointops)
     timeout 600 python -m pytest tests/test_gpu_pointops.py tests/test_gpu_frnn.py -m gpu -q -x 2>&1 | tail -8
     timeout 300 python bench_frnn.py --steps 10 > gpurun_out/bench_frnn.json 2>gpurun_out/bench_frnn.err; python -c "import json; d=json.load(open('gpurun_out/bench_frnn.json')); print(d['ms_per_step'], d['value'], d['kernels_avg_ms'])"
