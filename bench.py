@@ -421,6 +421,11 @@ def run_ours(args):
             line["splat"] = bench_splat.run(args, dev, peaks, peak_src)
             import bench_trace
             line["trace"] = bench_trace.run(dev, steps=3)
+            try:
+                import bench_pointops
+                line["pointops"] = bench_pointops.run(dev)
+            except Exception as e:      # never lose the headline line to a side record
+                line["pointops"] = {"error": "%s: %s" % (type(e).__name__, str(e)[:300])}
             if not args.no_ref_cuda:
                 line["ref_cuda"] = ref_cuda()
                 rc = line["ref_cuda"]

@@ -49,10 +49,19 @@ case "${1:-all}" in
     timeout 600 ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none -k regex:siren_sdf_grad --csv --log-file gpurun_out/siren_cta_sweep_ncu.csv python scripts/siren_cta_sweep.py --once > /dev/null 2>&1
     cat gpurun_out/siren_cta_sweep.txt; cut -d, -f 5,13- gpurun_out/siren_cta_sweep_ncu.csv | tail -30 ;;
   prof)
-    # r02 evidence: per-stage stamps, launch lists (C2 / C3 / C4), full captures of the dominant kernels
+    # r02 evidence: tests, benches, per-stage stamps, launch lists (C2 / C3 / C4), full captures of the dominant kernels
+    timeout 1500 python -m pytest tests -m gpu -q 2>&1 | tail -30 > gpurun_out/pytest_gpu.log; tail -3 gpurun_out/pytest_gpu.log
+    timeout 900 python bench.py --steps 10 --warmup 3 > gpurun_out/bench.json 2> gpurun_out/bench.err; tail -c 600 gpurun_out/bench.json; grep -v Warning gpurun_out/bench.err | tail -3
+    timeout 300 python bench.py --impl reference --steps 1 --warmup 0 > gpurun_out/bench_reference.json 2>/dev/null
+    timeout 200 python bench_splat.py --steps 10 > gpurun_out/bench_splat.json 2>/dev/null
+    timeout 200 python bench_frnn.py --steps 10 > gpurun_out/bench_frnn.json 2>/dev/null
+    timeout 200 python bench_trace.py --steps 5 > gpurun_out/bench_trace.json 2>/dev/null
+    timeout 100 python bench_rays.py --steps 20 > gpurun_out/bench_rays.json 2>/dev/null
+    timeout 300 python bench_pointops.py > gpurun_out/bench_pointops.json 2>/dev/null
+    timeout 300 python scripts/siren_timeline.py > gpurun_out/siren_timeline.txt 2>&1
+    timeout 300 python scripts/siren_cta_sweep.py > gpurun_out/siren_cta_sweep.txt 2>&1
     export ISO_BENCH_PREROLL=3
     B="python bench.py --steps 1 --warmup 3 --no-side"
-    timeout 300 python scripts/siren_timeline.py > gpurun_out/siren_timeline.txt 2>&1
     timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 3000 --csv --log-file gpurun_out/launches_c2.csv $B > gpurun_out/ncu_c2.log 2>&1
     timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_c4.csv python bench_splat.py --steps 1 > gpurun_out/ncu_c4.log 2>&1
     timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv --log-file gpurun_out/launches_c3.csv python bench_frnn.py --steps 1 > gpurun_out/ncu_c3.log 2>&1
@@ -60,8 +69,9 @@ case "${1:-all}" in
     timeout 600 ncu --set full --clock-control none --import-source on -k regex:frnn_query -s 3 -c 1 -f -o gpurun_out/prof_frnn_query_c2 $B > gpurun_out/ncu_frnn_c2.log 2>&1
     timeout 600 ncu --set full --clock-control none --import-source on -k regex:frnn_query -s 3 -c 1 -f -o gpurun_out/prof_frnn_query python bench_frnn.py --steps 1 > gpurun_out/ncu_frnn.log 2>&1
     timeout 600 ncu --set full --clock-control none --import-source on -k regex:splat_raster_v2_kernel -s 3 -c 1 -f -o gpurun_out/prof_splat_raster python bench_splat.py --steps 1 > gpurun_out/ncu_raster.log 2>&1
-    timeout 600 ncu --set full --clock-control none --import-source on -k regex:splat_occ_backward_hybrid_kernel -s 3 -c 1 -f -o gpurun_out/prof_splat_occ_bwd python bench_splat.py --steps 1 > gpurun_out/ncu_occ.log 2>&1
-    ls -la gpurun_out/ | tail -30 ;;
+    timeout 600 ncu --set full --clock-control none --import-source on -k regex:splat_occ_backward_tiled_kernel -s 3 -c 1 -f -o gpurun_out/prof_splat_occ_bwd python bench_splat.py --steps 1 > gpurun_out/ncu_occ.log 2>&1
+    timeout 600 ncu --set full --clock-control none --import-source on -k regex:fps_coop_kernel -s 1 -c 1 -f -o gpurun_out/prof_fps python bench_pointops.py > gpurun_out/ncu_fps.log 2>&1
+    ls -la gpurun_out/ | tail -40 ;;
   bench)
     timeout 900 python bench.py --steps 10 --warmup 3 > gpurun_out/bench.json 2> gpurun_out/bench.err; tail -c 6000 gpurun_out/bench.json; grep -v Warning gpurun_out/bench.err | tail -5 ;;
   refarm)

@@ -79,6 +79,7 @@ def traffic(rep):
                      ("sm__warps_active.avg.pct_of_peak_sustained_active", "occupancy_pct"),
                      ("sm__ops_path_tensor_op_utchmma_src_fp16_dst_fp32_sparsity_off.avg.pct_of_peak_sustained_elapsed",
                       "tensor_ops_pct_of_peak"),
+                     ("smsp__inst_executed.sum", "warp_inst"),
                      ("gpu__time_duration.sum", "duration")):
         try:
             extra[short] = float(d[k].replace(",", ""))
@@ -133,7 +134,8 @@ def main():
             open(os.path.join(PROF, "%s_%s.txt" % (tag, f[:-8])), "w").write(txt)
     json.dump(tr, open(tpath, "w"), indent=1, sort_keys=True)
     for f in ("bench.json", "bench_reference.json", "bench_splat.json", "bench_trace.json", "bench_n2.json",
-              "ref_cuda_timing.json"):
+              "bench_n8.json", "bench_frnn.json", "bench_pointops.json", "bench_rays.json", "ref_cuda_timing.json",
+              "siren_timeline.txt", "siren_cta_sweep.txt", "siren_ab.txt", "pytest_gpu.log"):
         p = os.path.join(OUT, f)
         if os.path.exists(p):
             text = open(p).read()
