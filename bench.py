@@ -105,6 +105,10 @@ class ClockSampler:
             self._h = pynvml.nvmlDeviceGetHandleByIndex(idx)
             self._nv = pynvml
             self._max = float(pynvml.nvmlDeviceGetMaxClockInfo(self._h, pynvml.NVML_CLOCK_SM))
+            try:
+                self._plimit = pynvml.nvmlDeviceGetEnforcedPowerLimit(self._h) / 1000.0
+            except Exception:
+                self._plimit = None
         except Exception:
             self._h = None
 
@@ -167,6 +171,8 @@ class ClockSampler:
         return {"sm_mhz": float(np.median(self.sm)), "sm_max_mhz": float(max(self.mx)),
                 "reasons": sorted(self.reasons), "samples": len(self.sm),
                 "power_w": float(np.median(self.pw)) if self.pw else None,
+                "power_w_max": float(max(self.pw)) if self.pw else None,
+                "power_limit_w": getattr(self, "_plimit", None),
                 "source": "nvml" if self._h is not None else "nvidia-smi"}
 
 
@@ -371,7 +377,13 @@ def run_ours(args):
                 "rows_per_launch": siren_stats["rows"] / max(siren_stats["calls"], 1),
                 "tensor_pipe_frac": 3 * achieved / peak_tf,
                 "note": "fp32 accuracy from 3 fp16 MMAs per product: frac <= 1/3 by construction; "
-                        "tensor_pipe_frac counts the issued MMA work", "ncu": _ncu("prof_siren")}
+                        "tensor_pipe_frac counts the issued MMA work",
+                "limiter": "board power: sw_power_cap holds the SM clock below its maximum for the whole timed region "
+                           "(see clocks); a kernel build with 8.6 % fewer cycles per tile gives the same step time at a "
+                           "2 % lower clock (A/B on one box, profiles/r02a_siren_ab.txt) -- the ceiling is energy per "
+                           "evaluation (3 x 672 fp16 MMAs per 128 rows), and cuBLAS bf16 itself sustains 62 % of nominal "
+                           "under the same cap (MEASURED_PEAKS.json)",
+                "ncu": _ncu("prof_siren")}
 
     line = {
         "metric": "iso-points/sec (project+resample)", "value": C2_POINTS * world / (ms * 1e-3), "unit": "points/s",

@@ -21,6 +21,19 @@ def _ncu(capture):
 def _ncu_traffic(capture):
     """dram__bytes_read.sum + dram__bytes_write.sum per launch from that capture, or None."""
     return _ncu(capture).get("dram_bytes_per_launch")
+
+
+def _issue_ceiling(capture, launch_ms, sm_mhz=1965.0):
+    """For a kernel that ncu shows to be instruction-issue bound, the ceiling is the issue rate: 148 SMs x 4
+    schedulers x 1 warp instruction per cycle.  warp instructions per launch come from the committed `ncu --set full`
+    capture (profiles/ncu_traffic.json), the launch time is measured live."""
+    n = _ncu(capture).get("warp_inst")
+    if not n or not launch_ms:
+        return None
+    peak = 148 * 4 * sm_mhz * 1e6 / 1e9
+    ach = n / (launch_ms * 1e-3) / 1e9
+    return {"warp_inst_per_launch": n, "achieved_ginst_s": ach, "peak_ginst_s": peak, "frac": ach / peak,
+            "peak_is": "148 SMs x 4 schedulers x %.0f MHz (max SM clock)" % sm_mhz}
 P, K, R = 500_000, 16, 0.05
 
 
@@ -67,10 +80,12 @@ def run(args, dev, peaks, peak_src, steps=None):
     roof = None
     if q:
         ach = alg / (q * 1e-3) / 1e9
-        roof = {"kernel": "frnn_query_kernel<3,16,int64>", "bound": "hbm", "achieved": ach, "peak": peaks["hbm_gbs"],
+        roof = {"kernel": "frnn_query_collect_kernel<3,int64>", "bound": "hbm", "achieved": ach, "peak": peaks["hbm_gbs"],
                 "unit": "GB/s", "frac": ach / peaks["hbm_gbs"], "traffic": _ncu_traffic("prof_frnn_query"), "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": alg, "avg_launch_ms": q,
-                "limiter": "instruction issue, not HBM (candidates are served by L1/L2)", "ncu": _ncu("prof_frnn_query")}
+                "limiter": "instruction issue / L1 latency at 16 warps per SM, not HBM (candidates are served by L1/L2: "
+                           "~200 candidate tests + a K-pass selection per query)",
+                "issue": _issue_ceiling("prof_frnn_query", q), "ncu": _ncu("prof_frnn_query")}
     return {"metric": "FRNN queries/sec", "unit": "queries/s",
             "config": {"workload": "C3: %d uniform points in the unit box, self query, K=%d, r=%g, radius_cell_ratio=2"
                                    % (P, K, R), "l2": "flushed between steps"},

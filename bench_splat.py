@@ -24,6 +24,19 @@ def _ncu_traffic(capture):
     """dram__bytes_read.sum + dram__bytes_write.sum per launch from that capture, or None."""
     return _ncu(capture).get("dram_bytes_per_launch")
 
+
+def _issue_ceiling(capture, launch_ms, sm_mhz=1965.0):
+    """For a kernel that ncu shows to be instruction-issue bound, the ceiling is the issue rate: 148 SMs x 4
+    schedulers x 1 warp instruction per cycle.  warp instructions per launch come from the committed `ncu --set full`
+    capture (profiles/ncu_traffic.json), the launch time is measured live."""
+    n = _ncu(capture).get("warp_inst")
+    if not n or not launch_ms:
+        return None
+    peak = 148 * 4 * sm_mhz * 1e6 / 1e9
+    ach = n / (launch_ms * 1e-3) / 1e9
+    return {"warp_inst_per_launch": n, "achieved_ginst_s": ach, "peak_ginst_s": peak, "frac": ach / peak,
+            "peak_is": "148 SMs x 4 schedulers x %.0f MHz (max SM clock)" % sm_mhz}
+
 V, PV, S, K = 8, 300_000, 512, 8
 
 
@@ -141,7 +154,7 @@ def run(args, dev, peaks, peak_src, steps=None):
     # dominant kernel: the raster kernel inside splat_forward; algorithmic bytes per launch
     # (SURVEY 8d): 36 B per point in + (12K + 4) B per pixel out
     alg = 36 * V * PV + (12 * K + 4) * V * S * S
-    f = kern.get("splat_forward")
+    f = (kern.get("splat_forward_fused") or kern.get("splat_forward"))
     roof = None
     if f:
         ach = alg / (f["avg_ms"] * 1e-3) / 1e9
@@ -149,6 +162,8 @@ def run(args, dev, peaks, peak_src, steps=None):
                 "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": ach / peaks["hbm_gbs"], "traffic": _ncu_traffic("prof_splat_raster"),
                 "peak_source": peak_src, "algorithmic_bytes_per_launch": alg, "avg_launch_ms": f["avg_ms"],
                 "limiter": "instruction issue / shared-memory atomics, DRAM traffic = algorithmic bytes",
+                # the raster kernel alone (the timed entry point also runs the tile fill): its ncu duration
+                "issue": _issue_ceiling("prof_splat_raster", _ncu("prof_splat_raster").get("duration_us", 0) / 1e3),
                 "ncu": _ncu("prof_splat_raster")}
     ewa_rec = run_ewa(dev, peaks, peak_src, steps, flush)
     return {"ewa_point_params": ewa_rec, "metric": "pixel-splats/sec", "unit": "pixel-splats/s",

@@ -85,6 +85,11 @@ def traffic(rep):
             extra[short] = float(d[k].replace(",", ""))
         except Exception:
             pass
+    try:    # the launch duration in one unit (ncu picks ns / us / ms per report)
+        tm = {"ns": 1e-3, "us": 1.0, "usecond": 1.0, "ms": 1e3, "msecond": 1e3, "s": 1e6, "second": 1e6}
+        extra["duration_us"] = float(d["gpu__time_duration.sum"].replace(",", "")) * tm.get(u["gpu__time_duration.sum"], 1.0)
+    except Exception:
+        pass
     return name, tot, extra
 
 
