@@ -109,6 +109,8 @@ def _version_key(spec):
 
 def _pack(spec):
     lib = _ext.lib()
+    if "ISOB200_SIREN_STAGGER" in os.environ:       # tuning knob of csrc/siren.cu: cycles (-1 = half a tile, 0 = off)
+        lib.isob200_siren_set_stagger(int(os.environ["ISOB200_SIREN_STAGGER"]), 0)
     dev = spec.first.weight.device
     L = len(spec.hidden)
     with torch.no_grad():

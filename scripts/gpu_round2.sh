@@ -25,6 +25,13 @@ case "${1:-all}" in
   splat)
     timeout 600 python -m pytest tests/test_gpu_splat.py tests/test_gpu_ewa.py tests/test_gpu_offsurface.py -m gpu -q -x 2>&1 | tail -15
     timeout 300 python bench_splat.py --steps 10 > gpurun_out/bench_splat.json 2>gpurun_out/bench_splat.err; python -c "import json; d=json.load(open('gpurun_out/bench_splat.json')); print(d['ms_fwd'], d['ms_fwd_blend_bwd'], d['value']); [print(k, v) for k, v in d['kernels'].items()]" ;;
+  stagger)
+    # sustained C2 step with the phase stagger of the SIREN kernel off / on, alternating on one box
+    for r in 1 2 3; do
+      for st in 0 -1; do
+        ISOB200_SIREN_STAGGER=$st timeout 300 python bench.py --steps 20 --warmup 3 --no-side | python -c "import json,sys; d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print('stagger $st', round(d['ms_per_step'],3), round(d['value']/1e6,3), round(d['config']['sdf_evaluations_per_s']/1e6,2), d['clocks']['sm_mhz'], d['clocks']['power_w'], d['kernels']['siren_project_step']['ms_per_step'])"
+      done
+    done ;;
   ab)
     # old (build/ab/libisob200_old.so) vs new library, alternating on the same box: sustained C2 step
     for r in 1 2 3; do

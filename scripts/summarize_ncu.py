@@ -142,6 +142,9 @@ def main():
               "bench_n8.json", "bench_frnn.json", "bench_pointops.json", "bench_rays.json", "ref_cuda_timing.json",
               "siren_timeline.txt", "siren_cta_sweep.txt", "siren_ab.txt", "pytest_gpu.log"):
         p = os.path.join(OUT, f)
+        if os.path.exists(p) and not f.endswith(".json"):      # plain-text evidence: verbatim
+            open(os.path.join(PROF, "%s_%s" % (tag, f.replace(".log", ".txt"))), "w").write(open(p).read())
+            continue
         if os.path.exists(p):
             text = open(p).read()
             try:                                   # a pretty-printed file is one JSON document: keep it whole
