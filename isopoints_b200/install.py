@@ -111,3 +111,13 @@ def uninstall():
                 sys.modules.pop(name, None)
             else:
                 sys.modules[name] = old
+
+
+class _CallableModule(types.ModuleType):
+    """``isopoints_b200.install()`` is the spelling the documentation uses: calling the module runs ``install``."""
+
+    def __call__(self, *args, **kwargs):
+        return install(*args, **kwargs)
+
+
+sys.modules[__name__].__class__ = _CallableModule

@@ -21,7 +21,7 @@ def test_install_registers_the_reference_import_names_and_uninstall_restores():
         for name in ("splat_points", "_splat_points_naive", "_backward_zbuf", "_splat_points_occ_backward",
                      "_splat_points_occ_fast_cuda_backward"):          # DSS/csrc/ext.cpp:5-18
             assert getattr(c, name) == getattr(splat._C, name)
-        install.install()                             # idempotent
+        install()                                     # idempotent; the module itself is callable
     finally:
         install.uninstall()
     for k, v in before.items():
