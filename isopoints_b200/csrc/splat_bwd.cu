@@ -341,7 +341,7 @@ splat_occ_backward_tiled_kernel(const float* __restrict__ points, const float* _
                                 const int* __restrict__ poff, const int* __restrict__ plist, int H, int W, int TX,
                                 int TY, float* __restrict__ grad_out, int out_stride) {
   __shared__ float4 srec[OCC_CHUNK];
-  __shared__ int s_cnt[64], s_off[64], s_pre[65];
+  __shared__ int s_cnt[64], s_off[64], s_pre[65], s_take;
   const int n = blockIdx.y, tr = blockIdx.x;
   const int t = n * TX * TY + tr;
   const int np = pcnt[t];
@@ -383,11 +383,11 @@ splat_occ_backward_tiled_kernel(const float* __restrict__ points, const float* _
         s_pre[k] = acc;
         acc += s_cnt[k];
       }
-      s_pre[k] = acc;
-      s_pre[64] = k;    // tiles taken in this pass (>= 1: a tile never exceeds the chunk)
+      s_pre[k] = acc;   // k <= 64: total records of the tiles taken
+      s_take = k;       // tiles taken in this pass (>= 1: a tile never exceeds the chunk)
     }
     __syncthreads();
-    const int ntake = s_pre[64];
+    const int ntake = s_take;
     const int nrec = s_pre[ntake];
     for (int k = 0; k < ntake; ++k) {
       const float4* src = recs + s_off[k];

@@ -348,3 +348,41 @@ def test_fused_blend_and_visibility_equal_the_separate_kernels(K, C):
     out = splat._splat(t["points"], t["ellipse"], t["cutoff"], t["radii"], t["first_idx"], t["num_points"], 0.05, S, K,
                        False, want_visible=True)
     assert torch.equal(out[6].bool(), splat.visibility_mask(out[0], P))
+
+
+@pytest.mark.parametrize("scaler,density", [(24.0, 1.0), (9.0, 0.15), (60.0, 0.02)])
+def test_backward_tiled_sweep_many_passes_equals_window(scaler, density):
+    """Search radii of several tiles: the tile-owner kernel stages its neighbourhood in more than one pass (a pass
+    holds 2 304 records or 64 tiles) and accumulates across passes; it must still equal the plain window sweep."""
+    S, V = 160, 2
+    inp = make_splat_inputs(V, [2500, 1800], S, seed=29, sigma_px=1.6)
+    t = _t(inp)
+    g = torch.Generator().manual_seed(int(scaler))
+    occ_grad = (torch.randn(V, S, S, generator=g) * (torch.rand(V, S, S, generator=g) < density)).to(DEV)
+    res = []
+    for hybrid in (True, False):
+        splat.OCC_BACKWARD_HYBRID = hybrid
+        pts = t["points"].clone().requires_grad_(True)
+        out = splat.EllipticalRasterizer.apply(pts, t["ellipse"], t["cutoff"], t["radii"], t["first_idx"],
+                                               t["num_points"], 0.05, S, 6, 16, 0, scaler)
+        (out[3] * occ_grad).sum().backward()
+        res.append(pts.grad.clone())
+    splat.OCC_BACKWARD_HYBRID = True
+    scale = res[1].abs().amax(0).clamp_min(1e-20)
+    np.testing.assert_allclose((res[0] / scale).cpu().numpy(), (res[1] / scale).cpu().numpy(), rtol=2e-4, atol=2e-5)
+    assert res[1][:, :2].abs().sum() > 0
+
+
+def test_blend_request_with_more_than_16_points_per_pixel_uses_the_separate_kernels():
+    """The fused epilogue exists for K <= 16; above that rasterize_elliptical_points(blend=...) composes the same
+    image with blend_rgba."""
+    S, K = 48, 20
+    inp = make_splat_inputs(1, 1200, S, seed=4, sigma_px=2.2, behind_frac=0.0)
+    t = _t(inp)
+    P = inp["points"].shape[0]
+    rgb = torch.rand(P, 3, device=DEV)
+    pcl = Pointclouds([t["points"]])
+    out = splat.rasterize_elliptical_points(pcl, t["ellipse"], t["cutoff"][:1], t["radii"], 0.05, S, K, bin_size=None,
+                                            blend=(None, rgb, splat.NORM_WEIGHT_EPS))
+    assert len(out) == 5 and out[4].shape == (1, S, S, 4)
+    assert torch.equal(out[4], splat.blend_rgba(out[0], out[2], out[3], None, rgb))
