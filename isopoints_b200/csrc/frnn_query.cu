@@ -523,6 +523,10 @@ frnn_query_collect_kernel(const float* __restrict__ q_points, const int* __restr
         const int zlo = lo[D - 1], zhi = hi[D - 1];
         const int ylo = (D == 3) ? lo[1] : 0, yhi = (D == 3) ? hi[1] : 0;
         // ---- trial radius from the block's point density ----
+        // (A three-scale estimate -- own cell / 3^D cells / block, log-log interpolation of the box that holds
+        // 1.9 lambda points -- was measured too: it helps clumped clouds (C2's iso-points: 0.58 -> 0.40 ms) but its
+        // single-cell count is noisy on uniform data (C3: 0.56 -> 0.76 ms), and on C2 the pruned group kernel
+        // stays ahead of both.)
         int nblock = 0;
         for (int x = lo[0]; x <= hi[0]; ++x)
           for (int y = ylo; y <= yhi; ++y) {
@@ -531,8 +535,7 @@ frnn_query_collect_kernel(const float* __restrict__ q_points, const int* __restr
             const int b = (c0 + zhi + 1 == grid_total) ? len2 : off2[c0 + zhi + 1];
             nblock += b - a;
           }
-        // (a block that fits the column is simply collected whole: exact without any estimate -- the regime of
-        // surface-like clouds on a fine grid, ~0.1 points per cell at BASELINE config 2)
+        // (a block that fits the column is simply collected whole: exact without any estimate)
         float tau = r2;
         if (nblock > COLLECT_CAP) {
           float cells = (float)(hi[0] - lo[0] + 1) * (float)(zhi - zlo + 1);
@@ -554,12 +557,13 @@ frnn_query_collect_kernel(const float* __restrict__ q_points, const int* __restr
         }
         // Up to three passes: the trial radius assumes the block's MEAN density and a volume-filling cloud; on a
         // surface (points ~ r^2) or in a cluster the ball overflows the column, next to a void it comes up short.
-        // The count of the failed pass re-scales the radius (exponent between the 2-D and 3-D laws, so that the
-        // corrected ball lands inside [K, capacity] for either), and only a query that is still off after that
-        // goes to the warp-cooperative search.
+        // A failed pass re-scales the radius from the counts it saw, and only a query that is still off after
+        // the third goes to the warp-cooperative search.
         bool exact = false;
         for (int attempt = 0; attempt < 3 && !exact; ++attempt) {
           cnt = 0;
+          int cntq = 0;                        // candidates inside a quarter of the trial tau (half the radius)
+          const float tauq = 0.25f * tau;
           // ---- one pass over the cells the trial ball touches ----
           // (a per-thread run cursor inside one flat candidate loop was tried: the cursor code then runs with ~5
           // live lanes per instruction and costs more than the per-run trip-count divergence of these nested loops)
@@ -598,15 +602,25 @@ frnn_query_collect_kernel(const float* __restrict__ q_points, const int* __restr
                       s_keys[cnt * COLLECT_THREADS + tid] =
                           ((unsigned long long)__float_as_uint(dd[u]) << 32) | (unsigned)sid2[j + u];
                     ++cnt;
+                    cntq += dd[u] <= tauq;
                   }
                 }
               }
             }
           }
-          // exact unless the ball overflowed the column, or was cut short of K by a trial radius below r
-          if (cnt > COLLECT_CAP) tau *= __powf(lambda / (float)cnt, 0.8f);
-          else if (cnt < K && tau < r2) tau = fminf(r2, tau * __powf(1.5f * lambda / (float)max(cnt, 1), 0.8f));
-          else exact = true;
+          // exact unless the ball overflowed the column, or was cut short of K by a trial radius below r.
+          // The failed pass measured the count at two radii (tau and tau / 4): count ~ tau^e locally, with e =
+          // 1.5 in a volume, 1 on a surface and far below that inside a clump of near-coincident points (iso-points
+          // of a random-init SIREN: e ~ 0.4) -- the next tau is read off that power law.
+          if (cnt > COLLECT_CAP || (cnt < K && tau < r2)) {
+            float e = 0.5f * __log2f((float)max(cnt, 1) / fmaxf((float)cntq, 0.5f));
+            e = fminf(fmaxf(e, 0.2f), 1.5f);
+            const float target = cnt > COLLECT_CAP ? lambda : 1.5f * lambda;
+            const float scale = exp2f(__log2f(target / (float)max(cnt, 1)) / e);
+            tau = fminf(r2, tau * fminf(fmaxf(scale, 1e-4f), 64.0f));
+          } else {
+            exact = true;
+          }
         }
         failed = !exact;
       }
