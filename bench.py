@@ -56,6 +56,20 @@ def _ncu_traffic(capture):
     """dram__bytes_read.sum + dram__bytes_write.sum per launch from that capture, or None."""
     return _ncu(capture).get("dram_bytes_per_launch")
 
+
+
+def _issue_ceiling(capture, launch_ms, sm_mhz=1965.0):
+    """Ceiling of an instruction-issue-bound kernel: 148 SMs x 4 schedulers x 1 warp instruction per cycle; warp
+    instructions per launch from the committed `ncu --set full` capture, launch time measured live."""
+    n = _ncu(capture).get("warp_inst")
+    if not n or not launch_ms:
+        return None
+    peak = 148 * 4 * sm_mhz * 1e6 / 1e9
+    ach = n / (launch_ms * 1e-3) / 1e9
+    return {"warp_inst_per_launch": n, "achieved_ginst_s": ach, "peak_ginst_s": peak, "frac": ach / peak,
+            "peak_is": "148 SMs x 4 schedulers x %.0f MHz (max SM clock)" % sm_mhz}
+
+
 C2_POINTS = 200_000
 C2_WORKLOAD = ("C2: 200000 pts/GPU, SURVEY-pinned SIREN 8x256 SDF (reference Siren(n_layers=7) under "
                "torch.manual_seed(0)), project(10 it)+resample(knn_k=8, 1 it)+reproject(3 it)")
@@ -360,6 +374,7 @@ def run_ours(args):
                      "traffic": _ncu_traffic("prof_frnn_query_c2"), "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": alg, "avg_launch_ms": q["avg_ms"],
                      "limiter": "instruction issue, not HBM (candidates are served by L1/L2)",
+                     "issue": _issue_ceiling("prof_frnn_query_c2", q["avg_ms"]),
                      "ncu": _ncu("prof_frnn_query_c2")}
         roof = frnn_roof
     if sd:
