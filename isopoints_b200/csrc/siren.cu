@@ -43,6 +43,7 @@
 //
 // Only H = 256 is built (BASELINE C2's "8-layer x 256 SIREN"); other widths keep the autograd path.
 #include "siren_common.cuh"
+#include <atomic>
 
 namespace isob200 {
 namespace siren {
@@ -844,7 +845,7 @@ int isob200_siren_pack(const float* w0, const float* b0, const float* w_hidden, 
 static int g_siren_max_ctas = kNumSMs;   // tuning knob: persistent CTAs per launch (<= one per SM)
 static int g_siren_stagger = 0;          // tuning knob: start delay of the CTAs on odd SMs in cycles (-1 = half a tile)
 static int g_siren_stagger_min_tiles = 3 * kNumSMs;   // ... for launches with at least this many tiles
-static unsigned g_siren_launch_seq = 0;
+static std::atomic<unsigned> g_siren_launch_seq{0};   // ctypes releases the GIL: host threads may launch concurrently
 int isob200_siren_set_stagger(int cycles, int min_tiles) {
   const int old = g_siren_stagger;
   g_siren_stagger = cycles;
@@ -882,7 +883,7 @@ static int launch_siren(const float* x, int n_max, const int* n_dev, const void*
   int tiles = (n_max + TM - 1) / TM;
   int grid = tiles < g_siren_max_ctas ? tiles : g_siren_max_ctas;
   Newton nwk = nw;
-  nwk.sched_slot = (int)(g_siren_launch_seq++ % SCHED_SLOTS);
+  nwk.sched_slot = (int)(g_siren_launch_seq.fetch_add(1, std::memory_order_relaxed) % SCHED_SLOTS);
   // half a tile period: a tile is 2 n_hidden stages of ~10.5 k cycles plus ~20 k for the two SIMT-only ends
   nwk.stagger_cycles = g_siren_stagger >= 0 ? g_siren_stagger : (2 * n_hidden * 10500 + 20000) / 2;
   nwk.stagger_min_tiles = g_siren_stagger_min_tiles;
