@@ -392,7 +392,9 @@ def run_ours(args):
                 "rows_per_launch": siren_stats["rows"] / max(siren_stats["calls"], 1),
                 "tensor_pipe_frac": 3 * achieved / peak_tf,
                 "note": "fp32 accuracy from 3 fp16 MMAs per product: frac <= 1/3 by construction; "
-                        "tensor_pipe_frac counts the issued MMA work",
+                        "tensor_pipe_frac counts the issued MMA work; both this kernel and the cuBLAS reference of "
+                        "`peak` run at the board's power limit, so tensor_pipe_frac is also the fraction of the energy "
+                        "roofline (MAC/s per watt relative to a pure GEMM)",
                 "limiter": "board power: sw_power_cap holds the SM clock below its maximum for the whole timed region "
                            "(see clocks); a kernel build with 8.6 % fewer cycles per tile gives the same step time at a "
                            "2 % lower clock (A/B on one box, profiles/r02a_siren_ab.txt) -- the ceiling is energy per "
