@@ -90,6 +90,7 @@ def run_ray_tracing(dev, steps, flush, cams=4, pixels=50_000):
         ms = 0.0
         l0 = lib.isob200_launch_count()
         rows0 = siren.STATS["rows"]
+        siren.MASKED_ROWS = []          # device counters of the march's masked evaluations (no host read-back there)
         for k in range(steps):
             flush.fill_(k & 0xff)
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -99,9 +100,11 @@ def run_ray_tracing(dev, steps, flush, cams=4, pixels=50_000):
             torch.cuda.synchronize()
             ms += a.elapsed_time(b)
         ms /= steps
+        masked_rows = int(torch.stack(siren.MASKED_ROWS).sum().item()) if siren.MASKED_ROWS else 0
+        siren.MASKED_ROWS = None
         rec[name] = {"ms_per_step": ms, "rays_per_s": cams * pixels / (ms * 1e-3), "hit_frac": float(mask.float().mean()),
                      "gpu_launches_per_step": (lib.isob200_launch_count() - l0) / steps,
-                     "sdf_evaluations_per_step": (siren.STATS["rows"] - rows0) / steps}
+                     "sdf_evaluations_per_step": (siren.STATS["rows"] - rows0 + masked_rows) / steps}
     rec["speedup"] = rec["torch_no_grad"]["ms_per_step"] / rec["fused_forward_only"]["ms_per_step"]
     return rec
 

@@ -16,7 +16,9 @@ Where the time goes is the SDF: ~2 x (sphere_tracing_iters + 1) evaluations per 
 unfinished ray plus ``n_secant_steps``.  ``sdf`` is a callable as in the reference; pass
 ``isopoints_b200.siren.sdf_fn(decoder)`` to evaluate the reference's Siren decoder with the forward-only fused
 tcgen05 kernel (``isob200_siren_sdf``: value only, half the tensor work of value + gradient).  The per-ray
-bookkeeping between evaluations is masked PyTorch on flat per-ray tensors, like the reference's.
+bookkeeping between evaluations is masked PyTorch on flat per-ray tensors, like the reference's; with the fused
+decoder the masked evaluations of the march run off device-side row counts (``sdf_fn.masked``), so the marching loop
+is enqueued without a single read-back.
 """
 import torch
 from torch import nn
@@ -135,6 +137,10 @@ class RayTracing(nn.Module):
         t_min, t_max = t_s.clone(), t_e.clone()
         nxt_s = _masked_eval(sdf, p_s, un_s)
         nxt_e = _masked_eval(sdf, p_e, un_e)
+        # With the fused decoder the masked evaluations read their row counts from device memory, so the loop is
+        # enqueued without a read-back: the two ``.any()`` exits below are skipped -- an iteration over an empty
+        # active set changes nothing (every update is masked), it only costs empty launches.
+        nosync = hit.is_cuda and getattr(sdf, "masked", None) is not None and getattr(sdf, "fused", lambda: False)()
         iters = 0
         while True:
             cur_s = torch.where(un_s, nxt_s, zero)
@@ -143,7 +149,7 @@ class RayTracing(nn.Module):
             cur_e = torch.where(cur_e <= self.sdf_threshold, zero, cur_e)
             un_s = un_s & (cur_s > self.sdf_threshold)
             un_e = un_e & (cur_e > self.sdf_threshold)
-            if (not bool((un_s | un_e).any())) or iters == self.sphere_tracing_iters:
+            if iters == self.sphere_tracing_iters or (not nosync and not bool((un_s | un_e).any())):
                 break
             iters += 1
             t_s = t_s + cur_s
@@ -154,7 +160,7 @@ class RayTracing(nn.Module):
             # step back where the march went through the surface (:997-1023)
             bad_s, bad_e = nxt_s < 0, nxt_e < 0
             k = 0
-            while bool((bad_s | bad_e).any()) and k < self.line_step_iters:
+            while k < self.line_step_iters and (nosync or bool((bad_s | bad_e).any())):
                 back = (1 - self.line_search_step) / (2 ** k)
                 t_s = torch.where(bad_s, t_s - back * cur_s, t_s)
                 p_s = torch.where(bad_s[:, None], rays.at(t_s), p_s)
@@ -264,6 +270,11 @@ def _eval_chunked(sdf, points, chunk):
 
 def _masked_eval(sdf, points, mask):
     """zeros(R) with sdf(points[mask]) at the masked rows (the reference's ``x[mask] = sdf(p[mask])``)."""
+    fast = getattr(sdf, "masked", None)
+    if fast is not None and points.is_cuda:
+        out = fast(points, mask)
+        if out is not None:
+            return out
     out = torch.zeros(points.shape[0], dtype=torch.float32, device=points.device)
     idx = torch.nonzero(mask).reshape(-1)
     if idx.numel():

@@ -29,6 +29,9 @@ STATS = {"calls": 0, "rows": 0, "flops": 0}
 # when a list: the sync-free projection loop appends (first-iteration rows, device tensor of the live
 # row counts entering iterations 1..) so that bench.py can count the rows actually evaluated
 RECORD = None
+# when a list: ``sdf_fn.masked`` appends the device counters of the rows it evaluated (bench_trace.py sums them up
+# after the timed region)
+MASKED_ROWS = None
 
 
 def resolve_record():
@@ -226,10 +229,55 @@ class sdf_fn:
 
     def __init__(self, model, **forward_kwargs):
         self.model, self.forward_kwargs = model, forward_kwargs
+        self._tags, self._rows = {}, None
 
     def fused(self):
         """True when ``model`` is evaluated by the fused kernel (memory per row: 4 bytes out, no activations)."""
         return match(self.model, self.forward_kwargs) is not None
+
+    def masked(self, points, mask):
+        """``zeros(R)`` with the sdf at the rows of ``points`` (R,3) where ``mask`` -- the reference's
+        ``out[mask] = sdf(points[mask])`` -- WITHOUT a host synchronisation: the masked rows are compacted on the
+        device (``isob200_compact_valid``, which also carries their row numbers), the fused kernel evaluates the
+        live count it finds in device memory, and the values are scattered back (rows past the count land in a
+        spare slot).  None when the decoder is not fusable or the tensors are not on a GPU."""
+        if not (points.is_cuda and self.fused()):
+            return None
+        lib = _ext.lib()
+        dev = points.device
+        pts = points.reshape(-1, 3)
+        if pts.dtype != torch.float32:
+            return None
+        pts = pts.contiguous()
+        R = pts.shape[0]
+        out = torch.zeros((R + 1,), dtype=torch.float32, device=dev)
+        if R == 0:
+            return out[:0]
+        spec = match(self.model, self.forward_kwargs)
+        blob, scratch, L = packed(self.model, spec)
+        key = (R, dev)
+        tag = self._tags.get(key)
+        if tag is None:     # row numbers as the bit pattern of a float column: they ride through the compaction
+            tag = torch.zeros((R, 3), dtype=torch.float32, device=dev)
+            tag[:, 0] = torch.arange(R, dtype=torch.int32, device=dev).view(torch.float32)
+            self._tags = {key: tag}
+            self._rows = torch.arange(R, dtype=torch.int32, device=dev)
+        cp = torch.empty((R, 3), dtype=torch.float32, device=dev)
+        ct = torch.empty((R, 3), dtype=torch.float32, device=dev)
+        cnt = torch.empty((1,), dtype=torch.int32, device=dev)
+        ws = _ext.workspace(lib.isob200_project_step_ws_bytes(R), dev)
+        st = _ext.stream(dev)
+        _ext.check(lib.isob200_compact_valid(_ext.ptr(pts), _ext.ptr(tag), _ext.ptr(mask.reshape(-1).contiguous().view(torch.uint8)),
+                                             R, _ext.ptr(cp), _ext.ptr(ct), _ext.ptr(cnt), _ext.ptr(ws), ws.numel(), st))
+        val = torch.empty((R,), dtype=torch.float32, device=dev)
+        STATS["calls"] += 1
+        _ext.check(lib.isob200_siren_sdf(_ext.ptr(cp), R, _ext.ptr(cnt), _ext.ptr(blob), L, _ext.ptr(val),
+                                         _ext.ptr(scratch), scratch.numel(), st))
+        if MASKED_ROWS is not None:
+            MASKED_ROWS.append(cnt)
+        idx = torch.where(self._rows < cnt, ct[:, 0].contiguous().view(torch.int32), torch.full_like(self._rows, R))
+        out.scatter_(0, idx.long(), val)
+        return out[:R]
 
     def __call__(self, x):
         v = sdf(self.model, x, self.forward_kwargs) if x.is_cuda else None
