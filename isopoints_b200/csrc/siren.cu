@@ -7,7 +7,7 @@
 // reverse-mode input gradient for 128-point tiles:
 //
 //   forward   z_0 = x W_0^T + b_0 (K = 3, SIMT)            h_0 = sin(w0 z_0)
-//             z_l = h_{l-1} W_l^T + b_l  (tcgen05 GEMM)    h_l = sin(w z_l),  c_l = w cos(w z_l)
+//             z_l = h_{l-1} W_l^T + b_l  (tcgen05 GEMM)    h_l = sin(w z_l),  c_l = w cos(w z_l) (taken in the backward pass)
 //             sdf = h_L . w_last + b_last
 //   backward  gp_L = w_last * c_L ;  g_{l-1} = gp_l W_l (tcgen05 GEMM) ;  gp_{l-1} = g_{l-1} * c_{l-1}
 //             grad = gp_0 W_0
@@ -32,14 +32,19 @@
 //     (W for the forward pass, W^T for the backward pass) and streamed L2 -> smem with 1-D TMA
 //     bulk copies (cp.async.bulk + mbarrier complete_tx) through a 3-stage ring by a producer
 //     warp;
-//   * w cos(w z_l) for the backward pass goes to a per-CTA scratch slab in global memory
-//     (float4 per thread, 512 B contiguous per warp); it is written and read back by the same
-//     thread within ~100 us, i.e. mostly L2 traffic.
+//   * the reverse-mode tape is NOT the cosine: the forward epilogue (which paces its GEMM) stores the
+//     reduced argument of each sine with the parity of the reduction in its sign bit, and the reverse
+//     epilogue (which waits for its GEMM) takes MUFU.COS of that word.  The tape lives in a per-CTA
+//     scratch slab in global memory (float4 per thread, 512 B contiguous per warp): written and read
+//     back by the same thread within ~100 us, prefetched into L2 one stage ahead, discarded from L2
+//     after its last use;
+//   * tiles are handed out dynamically (one atomic per tile on a self-resetting device table).
 //   Warp roles: warps 0-15 epilogue (TMEM lane quarter = warp % 4; within every 32-column k-block
 //   the warp owns the 8-column slice warp / 4, i.e. exactly one 16-byte K-chunk of its row, so the
 //   k-blocks of the next GEMM's A operand complete one after the other and the tensor core trails
-//   the epilogue by a single k-block), warp 16 weight producer, warp 17 TMEM allocator +
-//   single-thread MMA issuer.
+//   the epilogue by a single k-block), warp 16 tile scheduler + weight producer, warp 17 TMEM
+//   allocator + single-thread MMA issuer.
+//   What bounds it in a sustained run is the board's power limit, not cycles.
 //
 // Only H = 256 is built (BASELINE C2's "8-layer x 256 SIREN"); other widths keep the autograd path.
 #include "siren_common.cuh"
