@@ -4,7 +4,10 @@
 // per query, K-entry MinK in local memory, fixed <<<256,256>>> grid), frnn.py:304-352
 // (frnn_gather as an expand+gather+mask chain) and backward/backward.cu:8-147.
 //
-// Query kernel design (B200): a GROUP of GW lanes (GW = 8/16/32 >= K) cooperates on one query.
+// Three query kernels with identical results.  Dense grids (>= 1 point per cell) and K <= 20: one THREAD per
+// query, collect-then-select (frnn_query_collect_kernel below: trial radius from the local density, candidates
+// appended to a per-thread shared-memory column, K smallest emitted; warp-cooperative exact fallback).  Otherwise
+// the group kernels: a GROUP of GW lanes (GW = 8/16/32 >= K) cooperates on one query.
 //  * the candidate cells of a query form (2c+1)^(D-1) runs that are CONTIGUOUS in the sorted
 //    point array (z is the fastest cell index), so the group streams each run with coalesced
 //    loads, GW candidates per step -- no per-thread divergent pointer chasing;

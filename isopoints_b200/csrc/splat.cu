@@ -21,7 +21,10 @@
 //      one-lane-per-record box test against its pixel block, ballots the survivors, and only
 //      those are evaluated per pixel (exact reference predicate) and inserted into a K-entry
 //      (z, id, Q) list held in REGISTERS, sorted by (z, id).  Outputs idx/zbuf/qvalue/occ are
-//      written once, vectorised, -1 padding included (no fill pass).
+//      written once, vectorised, -1 padding included (no fill pass).  (The default raster kernel is v2 below:
+//      record-centric hit generation into per-pixel shared-memory lists, then one thread per pixel; its
+//      epilogue optionally computes the renderer's RGBA blend and the per-point visibility of the backward
+//      while the pixel's K entries are still in registers -- isob200_splat_forward_fused.)
 // Result = reference on tie-free depth: the K covering points with the smallest z, ascending,
 // cut at z - z0 > depth_merging_thres (:203-206); equal z is ordered by smaller point id (the
 // reference keeps whichever its atomics inserted first).

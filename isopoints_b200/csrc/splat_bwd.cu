@@ -18,6 +18,10 @@
 // warp-shuffle reduction and ONE plain store per coordinate: no grid build, no atomics,
 // run-to-run deterministic.  The predicate per (pixel, point) pair is the reference's, in its
 // fp32 form (dist2 = fma(dx, dx, dy*dy) <= r^2, ...), so the set of contributing pairs is equal.
+// The fast path (mode 0) goes one step further (splat_occ_backward_tiled_kernel): points are binned by the
+// 16x16 tile of their centre, one CTA per tile stages the neighbourhood's non-zero gradient pixels in shared
+// memory once and every THREAD owns a point -- 0.77 -> 0.28 ms at BASELINE config 4; the warp-per-point
+// kernels remain for the slow-path semantics (mode 1) and as the plain reference sweep (no workspace).
 // NOT reproduced: the reference closes the last 2-D grid cell of views n >= 1 with a local count
 // while its offsets are packed-global (rasterize_points_backward.cu:124-126), silently dropping
 // that cell's points; here every in-radius pair contributes.
