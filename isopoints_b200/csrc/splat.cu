@@ -138,6 +138,41 @@ splat_tile_fill_kernel(const float* __restrict__ points, const float* __restrict
   }
 }
 
+// ---- privatised form of the count kernel ------------------------------------------------------------------------
+// The plain count kernel issues one global atomic per (tile, point) pair: 3.4 M atomics on 8 192 counters at BASELINE
+// config 4, ~415 per address, and the L2 atomic unit serialises per address.  Here a CTA takes a contiguous chunk of
+// >= 8 192 points of ONE view, bins it into a shared-memory histogram of that view's tiles and adds the non-zero
+// bins to the global counters: 0.075 -> 0.05 ms.  (The same idea for the fill kernel -- reserve a CTA's range of
+// every tile's slice with one atomic, hand the slots out from shared memory in a second pass -- was measured and
+// dropped: two passes on 300 CTAs write the 163 MB of records slower than one pass on 1 184, 0.12 -> 0.20 ms.)
+constexpr int PRIV_MAX_TILES = 4096;      // tiles per view the shared-memory histogram holds (16 KB)
+constexpr int PRIV_CHUNK = 8192;          // points per CTA
+
+__global__ void __launch_bounds__(256)
+splat_tile_count_priv_kernel(const float* __restrict__ points, const float* __restrict__ radii,
+                             const int64_t* __restrict__ first_idx, const int64_t* __restrict__ num_points,
+                             int S, int T, int* __restrict__ tile_cnt) {
+  extern __shared__ int s_hist[];          // [T*T]
+  const int n = blockIdx.y, nt = T * T;
+  const long long first = first_idx[n], num = num_points[n];
+  const long long chunk = (num + gridDim.x - 1) / gridDim.x;
+  const long long b = (long long)blockIdx.x * chunk, e = min(num, b + chunk);
+  if (b >= e) return;
+  for (int i = threadIdx.x; i < nt; i += blockDim.x) s_hist[i] = 0;
+  __syncthreads();
+  const float fS = (float)S;
+  for (long long i = b + threadIdx.x; i < e; i += blockDim.x) {
+    TileRect t;
+    if (!point_tile_rect(points, radii, first + i, S, fS, t)) continue;
+    for (int ty = t.ty0; ty <= t.ty1; ++ty)
+      for (int tx = t.tx0; tx <= t.tx1; ++tx) atomicAdd(&s_hist[ty * T + tx], 1);
+  }
+  __syncthreads();
+  int* cnt = tile_cnt + (size_t)n * nt;
+  for (int i = threadIdx.x; i < nt; i += blockDim.x)
+    if (s_hist[i]) atomicAdd(&cnt[i], s_hist[i]);
+}
+
 // ---- TMA / mbarrier helpers (cp.async.bulk: SASS UBLKCP) ----
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
@@ -831,11 +866,20 @@ int isob200_splat_bin(const float* points, const float* radii, const int64_t* fi
   ISO_CUDA(cudaMemsetAsync(w.tile_cnt, 0, (char*)w.tile_off - (char*)w.tile_cnt, st));
   if (N > 0 && P > 0 && max_points_per_cloud > 0) {
     ISO_CHECK_ARG(points && radii && first_idx && num_points, "splat_bin: null pointer");
-    int bx = grid_for(max_points_per_cloud, 256, 8);
-    if (N > 1) bx = max(1, min(bx, (kNumSMs * 8 + N - 1) / N));
-    splat_tile_count_kernel<<<dim3(bx, N), 256, 0, st>>>(points, radii, first_idx, num_points, S, T,
-                                                        w.tile_cnt);
-    ISO_CHECK_LAUNCH("splat_tile_count_kernel");
+    if (T * T <= PRIV_MAX_TILES && P / N >= PRIV_CHUNK) {
+      // chunks sized for the AVERAGE view (max_points_per_cloud is only an upper bound, usually P itself): a
+      // larger view gets proportionally larger chunks, the grid is the same for every view
+      const int pbx = (int)min((long long)div_up(P / N, PRIV_CHUNK), (long long)kNumSMs * 4);
+      splat_tile_count_priv_kernel<<<dim3(pbx, N), 256, (size_t)T * T * sizeof(int), st>>>(
+          points, radii, first_idx, num_points, S, T, w.tile_cnt);
+      ISO_CHECK_LAUNCH("splat_tile_count_priv_kernel");
+    } else {
+      int bx = grid_for(max_points_per_cloud, 256, 8);
+      if (N > 1) bx = max(1, min(bx, (kNumSMs * 8 + N - 1) / N));
+      splat_tile_count_kernel<<<dim3(bx, N), 256, 0, st>>>(points, radii, first_idx, num_points, S, T,
+                                                          w.tile_cnt);
+      ISO_CHECK_LAUNCH("splat_tile_count_kernel");
+    }
   }
   if (nt > 0) {
     int rc = exclusive_scan_i32(w.tile_cnt, w.tile_off, (int)nt, 1, (long long)nt, (long long)nt, w.scan_ws,
