@@ -266,6 +266,14 @@ siren_sdf_grad_kernel(const float* __restrict__ x, int n_max, const int* __restr
             uint32_t s = it % STAGES;
             uint32_t ph = (it / STAGES) & 1;
             mbar_wait(bar_w_empty + 8 * s, ph ^ 1);
+            if constexpr (DBG) {
+              // dbg_gemm == -3 (energy experiment, wrong results): the weight stream is skipped after the first
+              // pass over the ring -- what the 4.7 TB/s of L2 -> shared-memory traffic costs under the power cap
+              if (dbg_gemm == -3 && it >= STAGES) {
+                mbar_arrive(bar_w_full + 8 * s);
+                continue;
+              }
+            }
             mbar_expect_tx(bar_w_full + 8 * s, STAGE_BYTES);
             tma_bulk_g2s(sbase + SM_STAGE + s * STAGE_BYTES, img + (size_t)i * STAGE_BYTES, STAGE_BYTES,
                          bar_w_full + 8 * s);
@@ -329,9 +337,13 @@ siren_sdf_grad_kernel(const float* __restrict__ x, int n_max, const int* __restr
               uint64_t dal = make_desc(a_lo + k16 * 2 * A_LBO, A_LBO);
               uint64_t dbh = make_desc(b_hi + k16 * 2 * B_LBO, B_LBO);
               uint64_t dbl = make_desc(b_lo + k16 * 2 * B_LBO, B_LBO);
-              tc_mma_f16(d_tmem, dal, dbh, IDESC, (i | k16) ? 1u : 0u);
-              tc_mma_f16(d_tmem, dah, dbl, IDESC, 1u);
-              tc_mma_f16(d_tmem, dah, dbh, IDESC, 1u);
+              bool one_product = false;   // dbg_gemm == -6 (energy experiment, wrong results): hi*hi only
+              if constexpr (DBG) one_product = dbg_gemm == -6;
+              if (!one_product) {
+                tc_mma_f16(d_tmem, dal, dbh, IDESC, (i | k16) ? 1u : 0u);
+                tc_mma_f16(d_tmem, dah, dbl, IDESC, 1u);
+              }
+              tc_mma_f16(d_tmem, dah, dbh, IDESC, (one_product && !(i | k16)) ? 0u : 1u);
             }
             tc_commit(bar_w_empty + 8 * s);  // stage reusable once these MMAs have read it
           }
@@ -512,7 +524,15 @@ siren_sdf_grad_kernel(const float* __restrict__ x, int n_max, const int* __restr
               const float2 v = make_float2(__uint_as_float(cur[2 * pr]), __uint_as_float(cur[2 * pr + 1]));
               float2 sn, r;
               uint32_t sx, sy;
-              sin_red2(__ffma2_rn(v, sc2, bb[pr]), sn, r, sx, sy);
+              bool sfu_sine = false;   // dbg_gemm == -7 (energy experiment): the sine on the special-function unit
+              if constexpr (DBG) sfu_sine = dbg_gemm == -7;
+              if (sfu_sine) {
+                red2(__ffma2_rn(v, sc2, bb[pr]), r, sx, sy);
+                sn = make_float2(__uint_as_float(__float_as_uint(__sinf(r.x)) ^ sx),
+                                 __uint_as_float(__float_as_uint(__sinf(r.y)) ^ sy));
+              } else {
+                sin_red2(__ffma2_rn(v, sc2, bb[pr]), sn, r, sx, sy);
+              }
               o[pr] = __fmul2_rn(sn, bc2(A_SCALE));
               tw[2 * pr] = tape_word(r.x, sx);
               tw[2 * pr + 1] = tape_word(r.y, sy);
@@ -520,7 +540,9 @@ siren_sdf_grad_kernel(const float* __restrict__ x, int n_max, const int* __restr
             publish(kb, o, kst);
             if (wst && (kb == 0 || kb == NKB - 1)) wst[kb == 0 ? 1 : 2] = clock64();
             // global traffic right after the hand-off fence (which waits for everything in flight)
-            if (!fwd_only) {
+            bool tape_on = !fwd_only;
+            if constexpr (DBG) tape_on = tape_on && dbg_gemm != -5;   // -5: energy experiment without tape traffic
+            if (tape_on) {
               float4* dst = st + (size_t)(kb * 8) * TM;
               dst[0] = make_float4(tw[0], tw[1], tw[2], tw[3]);
               dst[TM] = make_float4(tw[4], tw[5], tw[6], tw[7]);
@@ -675,7 +697,9 @@ siren_sdf_grad_kernel(const float* __restrict__ x, int n_max, const int* __restr
               asm volatile("discard.global.L2 [%0], 128;" ::"l"(st + (size_t)(kb * 8) * TM) : "memory");
               asm volatile("discard.global.L2 [%0], 128;" ::"l"(st + (size_t)(kb * 8 + 1) * TM) : "memory");
             }
-            if (kb + 2 < NKB) {   // right after the hand-off fence, two k-blocks ahead of its use
+            bool tape_on = true;
+            if constexpr (DBG) tape_on = dbg_gemm != -5;
+            if (kb + 2 < NKB && tape_on) {   // right after the hand-off fence, two k-blocks ahead of its use
               t0 = __ldcg(st + (size_t)((kb + 2) * 8) * TM);
               t1 = __ldcg(st + (size_t)((kb + 2) * 8 + 1) * TM);
             }
