@@ -38,7 +38,8 @@ case "${1:-all}" in
       done
     done ;;
   ab)
-    # old (build/ab/libisob200_old.so) vs new library, alternating on the same box: sustained C2 step
+    # old (build/ab/libisob200_old.so: `git worktree` of an earlier commit, python -m isopoints_b200.build there, copy the
+    # .so) vs new library, alternating on the same box: sustained C2 step
     for r in 1 2 3; do
       for which in old new; do
         if [ $which = old ]; then export ISOB200_LIB=$PWD/build/ab/libisob200_old.so; else unset ISOB200_LIB; fi
