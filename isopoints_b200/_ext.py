@@ -90,6 +90,7 @@ _PROTOS = {
     "isob200_splat_blend_backward": (_i, [_vp, _vp, _vp, _ll, _i, _i, _f, _vp, _i, _vp]),
 }
 
+ABI_VERSION = 2      # include/isob200.h as of round 2; a stale .so fails the load instead of misbehaving
 _LIB = None
 _RAW = None
 _TLS = threading.local()
@@ -157,6 +158,9 @@ def lib():
             fn.restype = res
             fn.argtypes = args
             setattr(w, name, _wrap(name, fn))
+        if not os.environ.get("ISOB200_LIB") and h.isob200_abi_version() != ABI_VERSION:
+            raise ImportError("isopoints_b200: %s has ABI version %d, the Python side expects %d -- rebuild with "
+                              "`python -m isopoints_b200.build --force`" % (LIB_PATH, h.isob200_abi_version(), ABI_VERSION))
         _RAW = h
         _LIB = w
     return _LIB

@@ -20,7 +20,7 @@ void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 extern "C" {
 long long isob200_launch_count(void) { return isob200::g_launches.load(); }
 const char* isob200_last_error(void) { return isob200::g_err; }
-int isob200_abi_version(void) { return 1; }
+int isob200_abi_version(void) { return 2; }   // 2: round 2 (fused splat epilogue, fps_ws, occ-backward workspace signature)
 int isob200_compiled_arch(void) {
 #ifdef ISOB200_ARCH
   return ISOB200_ARCH;
