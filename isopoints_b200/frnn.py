@@ -32,6 +32,9 @@ _GRID = namedtuple("GRID", "sorted_points2 pc2_grid_off sorted_points2_idxs grid
 # traversal of the query kernel: 0 = auto, 1 = exhaustive block scan, 2 = pruned best-first, 3 = thread-per-query
 # collect-then-select (same results)
 QUERY_MODE = 0
+# hint for the auto mode (bit 10 of the C entry's group_width): the radius spans many point spacings, so the K-th
+# neighbour lies far inside it -- set by callers that choose r that way (UniformProjection._create_tree)
+FAR_RADIUS_HINT = False
 
 _MAX_CELLS = 1 << 28     # 1 GiB of int32 offsets per cloud; int cell ids stay far from overflow
 _PARAMS_SIZE = {2: 6, 3: 8}
@@ -94,7 +97,7 @@ def find_nbrs(points1, lengths1, lengths2, grid, K, r, q_points=None, q_order=No
         _ext.ptr(qp), _ext.ptr(q_order), _ext.ptr(lengths1), _ext.ptr(lengths2),
         _ext.ptr(sorted_points2), _ext.ptr(off), _ext.ptr(sorted_idxs2), _ext.ptr(params), _ext.ptr(r),
         N, P1, P2, D, G, K, _ext.ptr(dists), _ext.ptr(idxs), 1 if idx_dtype == torch.int64 else 0,
-        (QUERY_MODE & 3) << 8, _ext.stream(dev)))
+        ((QUERY_MODE & 3) << 8) | ((1 << 10) if FAR_RADIUS_HINT else 0), _ext.stream(dev)))
     return idxs, dists
 
 

@@ -117,9 +117,14 @@ class UniformProjection(LevelSetProjection):
             mn, mx = torch.aminmax(points_padded, dim=1)
             diag = (mx - mn).norm(dim=-1)
         search_radius = torch.sqrt(diag / num_points_per_cloud.float()) * self.knn_k
-        dists, idxs, _, grid = frnn.frnn_grid_points(
-            points_padded, points_padded, num_points_per_cloud, num_points_per_cloud,
-            K=self.knn_k + 1, r=search_radius, grid=None, return_nn=False)
+        # r = knn_k estimated point spacings: ~knn_k^2 neighbours inside it on a surface, the K-th one far inside
+        hint, frnn.FAR_RADIUS_HINT = frnn.FAR_RADIUS_HINT, True
+        try:
+            dists, idxs, _, grid = frnn.frnn_grid_points(
+                points_padded, points_padded, num_points_per_cloud, num_points_per_cloud,
+                K=self.knn_k + 1, r=search_radius, grid=None, return_nn=False)
+        finally:
+            frnn.FAR_RADIUS_HINT = hint
         self._knn_gather = frnn.frnn_gather
         self._knn_full_idx = idxs
         self._knn_idx = idxs[..., 1:]
