@@ -71,7 +71,7 @@ def splat_views(pts_world, views, n_views, S, K, occ_grads, z_grads, rgb):
                                                        splat.NORM_WEIGHT_EPS)
     og = torch.stack([occ_grads[v] for v in views])
     zg = torch.stack([z_grads[v] for v in views])
-    ((occ * og).sum() + (zbuf * zg).sum()).backward()
+    torch.autograd.backward([occ, zbuf], [og, zg])   # the incoming image-space gradients, no synthetic loss kernels
     return rgba, p.grad
 
 

@@ -66,13 +66,31 @@ bbox_kernel(const float* __restrict__ points, const int64_t* __restrict__ length
       mx[d] = fmaxf(mx[d], __shfl_xor_sync(0xffffffffu, mx[d], o));
     }
   }
-  if ((threadIdx.x & 31) == 0 && len > 0) {
+  // one pair of atomics per block and component (a warp-level hand-off made the 2*D words a serial hot spot:
+  // 20 us at 120 k points)
+  __shared__ float s_mn[8][D], s_mx[8][D];
+  const int w = threadIdx.x >> 5;
+  if ((threadIdx.x & 31) == 0) {
 #pragma unroll
-    for (int d = 0; d < D; ++d) {
-      atomicMin(&bbox[n * 8 + d], f2ord(mn[d]));
-      atomicMax(&bbox[n * 8 + 4 + d], f2ord(mx[d]));
-    }
+    for (int d = 0; d < D; ++d) { s_mn[w][d] = mn[d]; s_mx[w][d] = mx[d]; }
   }
+  __syncthreads();
+  if (threadIdx.x < D && len > 0) {
+    float a = s_mn[0][threadIdx.x], b = s_mx[0][threadIdx.x];
+#pragma unroll
+    for (int k = 1; k < 8; ++k) { a = fminf(a, s_mn[k][threadIdx.x]); b = fmaxf(b, s_mx[k][threadIdx.x]); }
+    atomicMin(&bbox[n * 8 + threadIdx.x], f2ord(a));
+    atomicMax(&bbox[n * 8 + 4 + threadIdx.x], f2ord(b));
+  }
+}
+
+// bbox words -> floats: out[n] = (min[0..D), max[0..D)); zeros for an empty cloud
+__global__ void bbox_decode_kernel(const unsigned* __restrict__ bbox, int N, int D, float* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N * 2 * D) return;
+  const int n = i / (2 * D), j = i % (2 * D);
+  const bool empty = bbox[n * 8] == 0xffffffffu && bbox[n * 8 + 4] == 0u;
+  out[i] = empty ? 0.f : ord2f(bbox[n * 8 + (j < D ? j : 4 + j - D)]);
 }
 
 // One thread per cloud; restates frnn.py:55-71 with the arithmetic torch performs for it on a
@@ -89,10 +107,12 @@ __global__ void grid_params_kernel(const unsigned* __restrict__ bbox, const floa
   constexpr int MAXRES = (D == 3) ? ISO_G3_MAX_RES : ISO_G2_MAX_RES;
   float gmin[D], gsize[D];
   float min_size = FLT_MAX;
+  // a cloud without live rows left the box at its initial words: a one-cell grid at the origin instead of NaNs
+  const bool empty = bbox[n * 8] == 0xffffffffu && bbox[n * 8 + 4] == 0u;
 #pragma unroll
   for (int d = 0; d < D; ++d) {
-    gmin[d] = ord2f(bbox[n * 8 + d]);
-    float gmax = ord2f(bbox[n * 8 + 4 + d]);
+    gmin[d] = empty ? 0.f : ord2f(bbox[n * 8 + d]);
+    float gmax = empty ? 0.f : ord2f(bbox[n * 8 + 4 + d]);
     gsize[d] = __fsub_rn(gmax, gmin[d]);
     min_size = fminf(min_size, gsize[d]);
   }
@@ -431,6 +451,17 @@ static int frnn_build_impl(const float* points, const int64_t* lengths, const fl
   return ISOB200_OK;
 }
 
+static int launch_bbox(const float* points, const int64_t* lengths, int N, int P, int D, unsigned* bbox,
+                       cudaStream_t stream) {
+  int bx = grid_for((long long)P * D, 256, 4);
+  bx = min(bx, 2 * kNumSMs);
+  if (N > 1) bx = max(1, bx / N);
+  if (D == 3) bbox_kernel<3><<<dim3(bx, N), 256, 0, stream>>>(points, lengths, P, bbox);
+  else bbox_kernel<2><<<dim3(bx, N), 256, 0, stream>>>(points, lengths, P, bbox);
+  ISO_CHECK_LAUNCH("bbox_kernel");
+  return ISOB200_OK;
+}
+
 }  // namespace isob200
 
 using namespace isob200;
@@ -457,17 +488,40 @@ int isob200_frnn_grid_params(const float* points, const int64_t* lengths, const 
   ISO_CHECK_LAUNCH("bbox_init_kernel");
   if (g_max) ISO_CUDA(cudaMemsetAsync(g_max, 0, sizeof(int), stream));
   if (P > 0) {
-    int bx = grid_for((long long)P * D, 256, 4);
-    if (N > 1) bx = max(1, bx / N);
-    if (D == 3) bbox_kernel<3><<<dim3(bx, N), 256, 0, stream>>>(points, lengths, P, bbox);
-    else bbox_kernel<2><<<dim3(bx, N), 256, 0, stream>>>(points, lengths, P, bbox);
-    ISO_CHECK_LAUNCH("bbox_kernel");
+    const int rc = launch_bbox(points, lengths, N, P, D, bbox, stream);
+    if (rc != ISOB200_OK) return rc;
   }
   if (D == 3)
     grid_params_kernel<3><<<div_up(N, 64), 64, 0, stream>>>(bbox, rs, N, radius_cell_ratio, params, g_max);
   else
     grid_params_kernel<2><<<div_up(N, 64), 64, 0, stream>>>(bbox, rs, N, radius_cell_ratio, params, g_max);
   ISO_CHECK_LAUNCH("grid_params_kernel");
+  return ISOB200_OK;
+}
+
+// Axis-aligned bounding box of the live rows of each cloud: out (N, 2, D) = min, max (zeros for an empty cloud);
+// lengths (N) int64 on the device, may be null (= P).  What `points.min(0) / .max(0)` of levelset_sampling.py:254
+// gives on the filtered cloud, without the host knowing the survivor count.  ws: at least 32*N bytes.
+int isob200_points_bbox(const float* points, const int64_t* lengths, int N, int P, int D, float* out, void* ws,
+                        size_t ws_bytes, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  ISO_CHECK_ARG(D == 2 || D == 3, "points_bbox: only D=2/3 supported (got %d)", D);
+  ISO_CHECK_ARG(N >= 0 && P >= 0, "points_bbox: negative size");
+  if (N == 0) return ISOB200_OK;
+  ISO_CHECK_ARG(points && out && ws, "points_bbox: null pointer");
+  if (ws_bytes < (size_t)N * 32) {
+    set_error("points_bbox: workspace too small");
+    return ISOB200_ERR_WORKSPACE;
+  }
+  unsigned* bbox = (unsigned*)ws;
+  bbox_init_kernel<<<div_up(N * 8, 256), 256, 0, stream>>>(bbox, N);
+  ISO_CHECK_LAUNCH("bbox_init_kernel");
+  if (P > 0) {
+    const int rc = launch_bbox(points, lengths, N, P, D, bbox, stream);
+    if (rc != ISOB200_OK) return rc;
+  }
+  bbox_decode_kernel<<<div_up(N * 2 * D, 128), 128, 0, stream>>>(bbox, N, D, out);
+  ISO_CHECK_LAUNCH("bbox_decode_kernel");
   return ISOB200_OK;
 }
 

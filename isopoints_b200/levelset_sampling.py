@@ -18,6 +18,7 @@ levelset_sampling.py:142-170).  There is no CPU / PyTorch fallback for the kerne
 """
 from collections import namedtuple
 import math
+import os
 from typing import Callable, Optional, Tuple, Union
 
 import torch
@@ -30,6 +31,10 @@ from . import siren
 from .structures import (convert_pointclouds_to_tensor, is_pointclouds, packed_to_padded,
                          padded_to_packed_idx, reduce_mask_padded,
                          num_points_2_cloud_to_packed_first_idx)
+
+# one cloud + fused SIREN: enqueue filter + resample without reading the survivor count back first
+# (UniformProjection._filter_resample_run_ahead); off = the read-back right after the projection
+RUN_AHEAD = os.environ.get("ISOB200_RUN_AHEAD", "1") != "0"
 
 ProjectionResult = namedtuple('ProjectionResult', ('points', 'normals', 'mask'))
 _KNN = namedtuple("KNN", "dists idx knn")  # pytorch3d.ops.knn._KNN
@@ -167,13 +172,15 @@ class UniformProjection(LevelSetProjection):
     # ------------------------------------------------------------------------------------
     def _project_points(self, model: Callable, points: torch.Tensor, num_points: torch.Tensor,
                         proj_max_iters: int = None, proj_tolerance: float = None, num_points_list=None,
-                        **forward_kwargs) -> ProjectionResult:
+                        _live=None, **forward_kwargs) -> ProjectionResult:
         """Newton projection of the live rows of ``points`` (B,P,3) (levelset_sampling.py:290-351).
 
         Returns padded points (B,Pmax,3), the last SDF gradient as normals (B,Pmax,3) and the
         converged mask (B,Pmax) bool.  Non-converged points keep their last position.
         ``num_points_list``: the host copy of ``num_points`` when the caller already has it
-        (saves one read-back).
+        (saves one read-back).  ``_live`` (internal; one cloud, the fused SIREN path): an int32 device scalar --
+        only the first ``_live`` rows are projected, the rest come back unconverged; the host never learns
+        the count here.
         """
         proj_max_iters = proj_max_iters or self.proj_max_iters
         proj_tolerance = proj_tolerance or self.proj_tolerance
@@ -184,6 +191,9 @@ class UniformProjection(LevelSetProjection):
         points = points.contiguous()
         if points.dtype != torch.float32:
             raise RuntimeError("expected scalar type Float")
+        if _live is not None:
+            assert B == 1 and _live.dtype == torch.int32
+            num_points_list = [P]
         num_list = [int(x) for x in (num_points_list if num_points_list is not None else num_points.tolist())]
         full = all(n == P for n in num_list)
         if full:
@@ -197,6 +207,8 @@ class UniformProjection(LevelSetProjection):
 
         analytic = getattr(model, "isob200_analytic_sdf", None)
         fused = siren.match(model, forward_kwargs) if M > 0 else None
+        if _live is not None and (fused is None or analytic is not None):
+            raise RuntimeError("a device-side row count needs the fused SIREN path")
         if analytic is not None and not forward_kwargs and M > 0:
             kind, radius = analytic
             if kind != "sphere":
@@ -222,15 +234,16 @@ class UniformProjection(LevelSetProjection):
                 last = (it == proj_max_iters)
                 cur = points_packed if it == 0 else nxt[it & 1]
                 _ext.check(lib.isob200_siren_project_step(
-                    _ext.ptr(cur), M, None if it == 0 else _ext.ptr(cnt[it:]), _ext.ptr(blob), n_hidden,
+                    _ext.ptr(cur), M, _ext.ptr(_live) if it == 0 else _ext.ptr(cnt[it:]), _ext.ptr(blob), n_hidden,
                     _ext.ptr(scratch), scratch.numel(), _ext.ptr(points_packed), _ext.ptr(normals_packed),
                     _ext.ptr(nc_u8), None if it == 0 else _ext.ptr(act[it & 1]), float(proj_tolerance), 0.1,
                     0 if last else 1, _ext.ptr(act[(it + 1) & 1]),
                     None if last else _ext.ptr(nxt[(it + 1) & 1]), _ext.ptr(cnt[it + 1:]), st))
             siren.STATS["calls"] += proj_max_iters + 1
-            siren.STATS["rows"] += M
+            if _live is None:
+                siren.STATS["rows"] += M
             if siren.RECORD is not None:   # bench.py: live row counts, resolved after the timed region
-                siren.RECORD.append((M, cnt))
+                siren.RECORD.append((M if _live is None else _live, cnt))
             valid_packed = ~not_converged
         else:
             if M > 0:
@@ -281,7 +294,7 @@ class UniformProjection(LevelSetProjection):
 
     # ------------------------------------------------------------------------------------
     def resample(self, model, points_init, normals_init, num_points, sample_iters=None,
-                 num_points_list=None, **forward_kwargs) -> ProjectionResult:
+                 num_points_list=None, _live=None, **forward_kwargs) -> ProjectionResult:
         """Repulse along neighbours' tangent planes then re-project, ``sample_iters`` times
         (levelset_sampling.py:239-288)."""
         sample_iters = sample_iters or self.sample_iters
@@ -292,15 +305,27 @@ class UniformProjection(LevelSetProjection):
         if sample_iters == 0:
             return ProjectionResult(points_init, normals_init,
                                     points_init.new_full(points_init.shape[:-1], True, dtype=torch.bool))
-        if points_init.nelement() < 2 * (self.knn_k + 1):
+        if _live is None and points_init.nelement() < 2 * (self.knn_k + 1):
             return ProjectionResult(points_init, normals_init,
                                     points_init.new_full(points_init.shape[:-1], True, dtype=torch.bool))
         _ext.require_cuda(points_init)
         lib = _ext.lib()
         dev = points_init.device
         flat = points_init.reshape(-1, 3)
-        mn, mx = torch.aminmax(flat, dim=0)
-        diag = (mx - mn).norm()  # stays on the device (:254)
+        if _live is None:
+            mn, mx = torch.aminmax(flat, dim=0)
+            diag = (mx - mn).norm()  # stays on the device (:254)
+        else:
+            # one cloud whose first `_live` rows count (device scalar; `num_points` is its int64 copy): same
+            # bounding box from a kernel that reads the count on the device; an empty cloud gets diag = 1 so
+            # that the speculative grid stays finite (the caller drops the result when it learns the count)
+            box = torch.empty((1, 2, 3), dtype=torch.float32, device=dev)
+            ws = _ext.workspace(64, dev)
+            _ext.check(lib.isob200_points_bbox(_ext.ptr(points_init.contiguous()), _ext.ptr(num_points), 1,
+                                               int(points_init.shape[1]), 3, _ext.ptr(box), _ext.ptr(ws), ws.numel(),
+                                               _ext.stream(dev)))
+            diag = (box[0, 1] - box[0, 0]).norm()
+            diag = torch.where(_live[0] > 0, diag, torch.ones_like(diag))
         inv_sigma_spatial = (num_points.float() / diag).contiguous()  # (B,)
 
         points = points_init.contiguous()
@@ -325,7 +350,8 @@ class UniformProjection(LevelSetProjection):
             # sample_iter (`points = points + move`); the projection result is only returned.
             points = moved
             projection_result = self._project_points(model, points, num_points, proj_max_iters=3,
-                                                     num_points_list=num_points_list, **forward_kwargs)
+                                                     num_points_list=num_points_list, _live=_live,
+                                                     **forward_kwargs)
         return projection_result
 
     # ------------------------------------------------------------------------------------
@@ -380,6 +406,52 @@ class UniformProjection(LevelSetProjection):
         points, num_points = upsample(points, n_points, num_points=num_points, neighborhood_size=31)
         return points, num_points
 
+    def _run_ahead_ok(self, model, mask, points, forward_kwargs) -> bool:
+        """Whether filter + resample can be enqueued without the host knowing the survivor count: one cloud, the
+        fused SIREN decoder, and none of the steps overridden (the point-sharded subclass decides collectively)."""
+        cls, base = type(self), UniformProjection
+        return (RUN_AHEAD and mask.shape[0] == 1 and mask.shape[1] > 0 and points.is_cuda
+                and points.dtype == torch.float32
+                and all(getattr(cls, f) is getattr(base, f)
+                        for f in ("_nothing_converged", "_create_tree", "resample", "_project_points"))
+                and getattr(model, "isob200_analytic_sdf", None) is None
+                and siren.match(model, forward_kwargs) is not None)
+
+    def _filter_resample_run_ahead(self, model, result: ProjectionResult, sample_iters, **forward_kwargs):
+        """``_filter_projection_result`` + ``resample`` (:401-409) with the survivor count left on the device: the
+        compaction keeps its M-row buffers, every later kernel takes the count from device memory (FRNN lengths,
+        the bounding box, the Newton kernels' row count), and the one read-back happens after the whole step is
+        enqueued -- the host runs ahead of the GPU instead of waiting for the projection to drain.  Returns None
+        when nothing converged (:396-399)."""
+        points, normals, mask = result
+        lib = _ext.lib()
+        dev = points.device
+        M = int(mask.shape[1])
+        pts, nrm = points.reshape(-1, 3).contiguous(), normals.reshape(-1, 3).contiguous()
+        valid = mask.reshape(-1).contiguous().view(torch.uint8)
+        out_p, out_n = torch.zeros_like(pts), torch.zeros_like(nrm)   # rows past the count: finite
+        count = torch.zeros((1,), dtype=torch.int32, device=dev)
+        ws = _ext.workspace(lib.isob200_project_step_ws_bytes(M), dev)
+        _ext.check(lib.isob200_compact_valid(_ext.ptr(pts), _ext.ptr(nrm), _ext.ptr(valid), M, _ext.ptr(out_p),
+                                             _ext.ptr(out_n), _ext.ptr(count), _ext.ptr(ws), ws.numel(),
+                                             _ext.stream(dev)))
+        tree = {k: self.__dict__.get(k) for k in ("_knn_idx", "_knn_dists", "_knn_full_idx", "_knn_src",
+                                                  "_knn_nn_cache")}
+        res = self.resample(model, out_p[None], out_n[None], count.long(), sample_iters=sample_iters, _live=count,
+                            **forward_kwargs)
+        n = int(count.item())
+        if n == 0 or sample_iters == 0 or 3 * n < 2 * (self.knn_k + 1):
+            self.__dict__.update(tree)   # the read-back path builds no tree in these cases
+            if n == 0:
+                return None
+            # resample's own early returns (:242-245)
+            return ProjectionResult(out_p[:n][None], out_n[:n][None], mask.new_ones((1, n)))
+        if self._knn_idx is not None and self._knn_idx.shape[1] == M:
+            self._knn_full_idx = self._knn_full_idx[:, :n]
+            self._knn_idx, self._knn_dists = self._knn_idx[:, :n], self._knn_dists[:, :n]
+            self._knn_src, self._knn_nn_cache = self._knn_src[:, :n], None
+        return ProjectionResult(res.points[:, :n], res.normals[:, :n], res.mask[:, :n])
+
     def _nothing_converged(self, counts) -> bool:
         """The early exit of :396-399 (``not valid_projection.any()``) from the survivor counts already on the
         host.  A hook: the point-sharded subclass has to take this decision collectively."""
@@ -414,14 +486,22 @@ class UniformProjection(LevelSetProjection):
                     return {'levelset_points': points_projected, 'mask': valid_projection}
             else:
                 unfiltered = (points_projected, valid_projection)
-                (points_projected, normals_projected, valid_projection), counts, num_points = \
-                    _filter_projection_result_counted(
-                        ProjectionResult(points_projected, normals_projected, valid_projection))
-                if self._nothing_converged(counts):   # (:396-399)
-                    return {'levelset_points': unfiltered[0], 'mask': unfiltered[1]}
-                points_projected, normals_projected, valid_projection = self.resample(
-                    model, points_projected, normals_projected, num_points, sample_iters=sample_iters,
-                    num_points_list=counts, **forward_kwargs)
+                if self._run_ahead_ok(model, valid_projection, points_projected, forward_kwargs):
+                    res = self._filter_resample_run_ahead(
+                        model, ProjectionResult(points_projected, normals_projected, valid_projection),
+                        sample_iters, **forward_kwargs)
+                    if res is None:   # (:396-399)
+                        return {'levelset_points': unfiltered[0], 'mask': unfiltered[1]}
+                    points_projected, normals_projected, valid_projection = res
+                else:
+                    (points_projected, normals_projected, valid_projection), counts, num_points = \
+                        _filter_projection_result_counted(
+                            ProjectionResult(points_projected, normals_projected, valid_projection))
+                    if self._nothing_converged(counts):   # (:396-399)
+                        return {'levelset_points': unfiltered[0], 'mask': unfiltered[1]}
+                    points_projected, normals_projected, valid_projection = self.resample(
+                        model, points_projected, normals_projected, num_points, sample_iters=sample_iters,
+                        num_points_list=counts, **forward_kwargs)
                 num_points = valid_projection.sum(dim=-1)
 
             if not skip_upsampling and ref_pcl is not None:

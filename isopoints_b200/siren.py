@@ -39,8 +39,8 @@ def resolve_record():
     global RECORD
     if RECORD:
         for m, cnt in RECORD:
-            # iteration 0 evaluated all m rows (already counted: it runs without a device count)
-            STATS["rows"] += sum(int(c) for c in cnt.tolist()[1:-1])
+            # iteration 0 evaluated all m rows (already counted when it ran without a device count)
+            STATS["rows"] += sum(int(c) for c in cnt.tolist()[1:-1]) + (int(m.item()) if torch.is_tensor(m) else 0)
         RECORD = []
 
 

@@ -167,3 +167,45 @@ def test_c2_fused_vs_opaque_per_point_at_200k():
           % (oa["mask"].shape[1], ob["mask"].shape[1], na_, nb_))
     assert abs(oa["mask"].shape[1] - ob["mask"].shape[1]) <= 0.01 * ob["mask"].shape[1]
     assert abs(na_ - nb_) <= 0.01 * nb_
+
+
+def _project(proj, model, x, run_ahead, **kw):
+    from isopoints_b200 import levelset_sampling as ls
+    old, ls.RUN_AHEAD = ls.RUN_AHEAD, run_ahead
+    try:
+        return proj.project_points(x, model, skip_upsampling=True, **kw)
+    finally:
+        ls.RUN_AHEAD = old
+
+
+@pytest.mark.parametrize("n,sample_iters", [(200_000, 1), (30_000, 2), (7, 1)])
+def test_run_ahead_filter_resample_equals_the_read_back_path_bit_for_bit(n, sample_iters):
+    """The survivor count left on the device (filter + resample enqueued at the projection's capacity, one read-back
+    at the end) against the count read right after the projection: same kernels on the same live rows, so every
+    output -- points, normals, mask, and the cached K-NN table -- has to be identical."""
+    model = pinned_siren(0).to(DEV)
+    x = _c2_cloud(n).to(DEV)
+    pa = UniformProjection(proj_max_iters=10, proj_tolerance=5e-5, knn_k=8, sample_iters=sample_iters)
+    pb = UniformProjection(proj_max_iters=10, proj_tolerance=5e-5, knn_k=8, sample_iters=sample_iters)
+    a = _project(pa, model, x, True)
+    b = _project(pb, model, x, False)
+    assert a.keys() == b.keys()
+    for k in a:
+        assert a[k].shape == b[k].shape and torch.equal(a[k], b[k]), k
+    if pa._knn_idx is not None or pb._knn_idx is not None:
+        assert torch.equal(pa._knn_idx, pb._knn_idx) and torch.equal(pa._knn_dists, pb._knn_dists)
+        assert torch.equal(pa._knn_nn, pb._knn_nn)
+    print("n = %d: %d survivors, identical" % (n, a["levelset_points"].shape[1]))
+
+
+def test_run_ahead_when_nothing_converges_returns_the_unfiltered_projection():
+    """:396-399 -- no survivor: the speculative resample runs over an empty cloud (finite grid, no exception) and the
+    unfiltered projection comes back without 'levelset_normals', as on the read-back path."""
+    model = pinned_siren(0).to(DEV)
+    x = _c2_cloud(5_000).to(DEV)
+    kw = dict(proj_max_iters=1, proj_tolerance=1e-12, knn_k=8, sample_iters=1)
+    a = _project(UniformProjection(**kw), model, x, True)
+    b = _project(UniformProjection(**kw), model, x, False)
+    assert set(a.keys()) == set(b.keys()) == {"levelset_points", "mask"}
+    assert not bool(a["mask"].any())
+    assert torch.equal(a["levelset_points"], b["levelset_points"]) and torch.equal(a["mask"], b["mask"])
