@@ -40,6 +40,11 @@ int isob200_exclusive_scan_i32(const int* in, int* out, int n, int rows, long lo
 int isob200_frnn_grid_params(const float* points, const int64_t* lengths, const float* rs, int N,
                              int P, int D, double radius_cell_ratio, float* params, int* g_max,
                              void* ws, size_t ws_bytes, void* stream);
+/* the same for a caller that sizes its (N, g_cap) cell table before reading g_max back: a cloud that needs more
+ * cells gets a one-cell grid no query reaches (everything stays in bounds); g_max still reports the true size */
+int isob200_frnn_grid_params_capped(const float* points, const int64_t* lengths, const float* rs, int N,
+                                    int P, int D, double radius_cell_ratio, int g_cap, float* params, int* g_max,
+                                    void* ws, size_t ws_bytes, void* stream);
 /* min / max over the live rows of each cloud, out (N,2,D), lengths on the device: the bounding box of
  * DSS/models/levelset_sampling.py:254 (`points.view(-1,3).max(0) - min(0)`) without a host-side survivor count */
 int isob200_points_bbox(const float* points, const int64_t* lengths, int N, int P, int D, float* out, void* ws,

@@ -30,6 +30,7 @@ _PROTOS = {
     "isob200_exclusive_scan_ws_bytes": (_sz, [_i, _i]),
     "isob200_exclusive_scan_i32": (_i, [_vp, _vp, _i, _i, _ll, _ll, _vp, _sz, _vp]),
     "isob200_frnn_grid_params": (_i, [_vp, _vp, _vp, _i, _i, _i, _d, _vp, _vp, _vp, _sz, _vp]),
+    "isob200_frnn_grid_params_capped": (_i, [_vp, _vp, _vp, _i, _i, _i, _d, _i, _vp, _vp, _vp, _sz, _vp]),
     "isob200_points_bbox": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _sz, _vp]),
     "isob200_frnn_insert_points": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     "isob200_frnn_counting_sort": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),

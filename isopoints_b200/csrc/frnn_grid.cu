@@ -99,7 +99,7 @@ __global__ void bbox_decode_kernel(const unsigned* __restrict__ bbox, int N, int
 // to the fp32 params tensor, comparisons against the scalar in fp32.
 template <int D>
 __global__ void grid_params_kernel(const unsigned* __restrict__ bbox, const float* __restrict__ rs,
-                                   int N, double radius_cell_ratio, float* __restrict__ params,
+                                   int N, double radius_cell_ratio, int g_cap, float* __restrict__ params,
                                    int* __restrict__ g_max) {
   const int n = blockIdx.x * blockDim.x + threadIdx.x;
   if (n >= N) return;
@@ -141,7 +141,17 @@ __global__ void grid_params_kernel(const unsigned* __restrict__ bbox, const floa
   // `total` is a float product of up to three resolutions: with a collapsed axis (min extent 0) the reference's
   // cell-size floor (:62-63) does not engage and a tiny radius asks for more cells than an int holds.  Report
   // INT_MAX instead of an overflowed cast: the host wrapper raises (the reference would fail in its allocation).
-  if (g_max) atomicMax(g_max, (total < 1073741824.f) ? (int)total : 0x7fffffff);
+  const int tot = (total < 1073741824.f) ? (int)total : 0x7fffffff;
+  if (g_max) atomicMax(g_max, tot);
+  if (tot > g_cap) {
+    // the caller sized its cell table for g_cap cells before knowing the grid (isob200_frnn_grid_params_capped) and
+    // this cloud needs more: hand out a one-cell grid placed where no query box reaches it, so that the build and
+    // the queries stay inside the table and finish at once; g_max tells the caller to discard them and redo
+#pragma unroll
+    for (int d = 0; d < D; ++d) { p[d] = FLT_MAX; p[D + 1 + d] = 1.f; }
+    p[D] = 1.f;
+    p[2 * D + 1] = 1.f;
+  }
 }
 
 // ----------------------------------------------------------------------------------------
@@ -471,10 +481,26 @@ extern "C" {
 // params: (N, 8) for D=3 / (N, 6) for D=2, fp32, reference slot layout (grid.h:5-24).
 // g_max (device int, may be null): receives max_n grid_total (the reference's G, frnn.py:70-71).
 // ws: at least 32*N + 4 bytes.
+int isob200_frnn_grid_params_capped(const float* points, const int64_t* lengths, const float* rs, int N,
+                                    int P, int D, double radius_cell_ratio, int g_cap, float* params, int* g_max,
+                                    void* ws, size_t ws_bytes, void* stream_);
+
 int isob200_frnn_grid_params(const float* points, const int64_t* lengths, const float* rs, int N,
                              int P, int D, double radius_cell_ratio, float* params, int* g_max,
                              void* ws, size_t ws_bytes, void* stream_) {
+  return isob200_frnn_grid_params_capped(points, lengths, rs, N, P, D, radius_cell_ratio, 0x7fffffff, params, g_max,
+                                         ws, ws_bytes, stream_);
+}
+
+// The same with a cell budget: for a caller that allocates its (N, g_cap) cell table BEFORE reading g_max back (no
+// host round trip between the parameters and the build).  A cloud whose grid needs more than g_cap cells gets a
+// one-cell grid that no query reaches (build and queries stay in bounds, find nothing); g_max still receives the
+// true size, so the caller learns afterwards that the results must be discarded and redone with the real G.
+int isob200_frnn_grid_params_capped(const float* points, const int64_t* lengths, const float* rs, int N,
+                                    int P, int D, double radius_cell_ratio, int g_cap, float* params, int* g_max,
+                                    void* ws, size_t ws_bytes, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
+  ISO_CHECK_ARG(g_cap >= 1, "frnn_grid_params: the cell budget must be positive");
   ISO_CHECK_ARG(D == 2 || D == 3, "frnn_grid_params: only D=2/3 supported (got %d)", D);
   ISO_CHECK_ARG(N >= 0 && P >= 0, "frnn_grid_params: negative size");
   if (N == 0) return ISOB200_OK;
@@ -492,9 +518,9 @@ int isob200_frnn_grid_params(const float* points, const int64_t* lengths, const 
     if (rc != ISOB200_OK) return rc;
   }
   if (D == 3)
-    grid_params_kernel<3><<<div_up(N, 64), 64, 0, stream>>>(bbox, rs, N, radius_cell_ratio, params, g_max);
+    grid_params_kernel<3><<<div_up(N, 64), 64, 0, stream>>>(bbox, rs, N, radius_cell_ratio, g_cap, params, g_max);
   else
-    grid_params_kernel<2><<<div_up(N, 64), 64, 0, stream>>>(bbox, rs, N, radius_cell_ratio, params, g_max);
+    grid_params_kernel<2><<<div_up(N, 64), 64, 0, stream>>>(bbox, rs, N, radius_cell_ratio, g_cap, params, g_max);
   ISO_CHECK_LAUNCH("grid_params_kernel");
   return ISOB200_OK;
 }

@@ -810,12 +810,13 @@ int isob200_frnn_find_nbrs(const float* q_points, const int* q_order, const int6
   // bit 10: the caller knows that the radius spans many point spacings (the K-th neighbour lies far inside r):
   // on a sparse grid the pruned traversal then beats the exhaustive one (C2's resample tree: 0.29 vs 0.35 ms)
   const bool far_radius = (group_width >> 10) & 1;
-  const bool exhaustive = mode == 1 || (mode == 0 && (long long)P2 < (long long)G && !far_radius);
+  const bool sparse = (long long)P2 < (long long)G;
+  const bool exhaustive = mode == 1 || (mode == 0 && sparse && !far_radius);
   // dense grid and a K whose trial ball fits a shared-memory column: thread-per-query collect-then-select.
   // (Measured on the sparse grid of BASELINE config 2 -- iso-surface points, ~0.1 per cell, K = 9: 0.65 ms against
   // 0.36 ms for the exhaustive group kernel; there the candidate block often exceeds the column and the volume-based
   // trial radius needs its second pass.)
-  const bool collect = mode == 3 || (mode == 0 && !exhaustive && K <= 20);
+  const bool collect = mode == 3 || (mode == 0 && !sparse && K <= 20);
   if (collect) {
     ISO_CHECK_ARG(K <= 32, "find_nbrs: collect mode needs K <= 32");
     const float lambda = fminf((float)K + 4.0f * sqrtf((float)K), (float)(COLLECT_CAP - 8));

@@ -147,30 +147,87 @@ splat_tile_fill_kernel(const float* __restrict__ points, const float* __restrict
 // dropped: two passes on 300 CTAs write the 163 MB of records slower than one pass on 1 184, 0.12 -> 0.20 ms.)
 constexpr int PRIV_MAX_TILES = 4096;      // tiles per view the shared-memory histogram holds (16 KB)
 constexpr int PRIV_CHUNK = 8192;          // points per CTA
+constexpr int FUSED_SCAN_MAX_TILES = 1 << 17;   // tiles (all views) the count kernel's last CTA scans itself
 
 __global__ void __launch_bounds__(256)
 splat_tile_count_priv_kernel(const float* __restrict__ points, const float* __restrict__ radii,
                              const int64_t* __restrict__ first_idx, const int64_t* __restrict__ num_points,
-                             int S, int T, int* __restrict__ tile_cnt) {
+                             int S, int T, int* __restrict__ tile_cnt, int* __restrict__ ticket,
+                             int* __restrict__ tile_off, int* __restrict__ total, int* __restrict__ total_out) {
   extern __shared__ int s_hist[];          // [T*T]
   const int n = blockIdx.y, nt = T * T;
   const long long first = first_idx[n], num = num_points[n];
   const long long chunk = (num + gridDim.x - 1) / gridDim.x;
   const long long b = (long long)blockIdx.x * chunk, e = min(num, b + chunk);
-  if (b >= e) return;
-  for (int i = threadIdx.x; i < nt; i += blockDim.x) s_hist[i] = 0;
-  __syncthreads();
-  const float fS = (float)S;
-  for (long long i = b + threadIdx.x; i < e; i += blockDim.x) {
-    TileRect t;
-    if (!point_tile_rect(points, radii, first + i, S, fS, t)) continue;
-    for (int ty = t.ty0; ty <= t.ty1; ++ty)
-      for (int tx = t.tx0; tx <= t.tx1; ++tx) atomicAdd(&s_hist[ty * T + tx], 1);
+  if (b < e) {
+    for (int i = threadIdx.x; i < nt; i += blockDim.x) s_hist[i] = 0;
+    __syncthreads();
+    const float fS = (float)S;
+    for (long long i = b + threadIdx.x; i < e; i += blockDim.x) {
+      TileRect t;
+      if (!point_tile_rect(points, radii, first + i, S, fS, t)) continue;
+      for (int ty = t.ty0; ty <= t.ty1; ++ty)
+        for (int tx = t.tx0; tx <= t.tx1; ++tx) atomicAdd(&s_hist[ty * T + tx], 1);
+    }
+    __syncthreads();
+    int* cnt = tile_cnt + (size_t)n * nt;
+    for (int i = threadIdx.x; i < nt; i += blockDim.x)
+      if (s_hist[i]) atomicAdd(&cnt[i], s_hist[i]);
   }
+  if (!ticket) return;
+  // ---- the last CTA to finish turns the counts of all views into offsets and the record total: no scan
+  //      launches, no separate total kernel, no device-to-device copy behind this kernel ----
+  __shared__ int s_part[256];
+  __shared__ bool s_last;
+  __threadfence();
   __syncthreads();
-  int* cnt = tile_cnt + (size_t)n * nt;
-  for (int i = threadIdx.x; i < nt; i += blockDim.x)
-    if (s_hist[i]) atomicAdd(&cnt[i], s_hist[i]);
+  if (threadIdx.x == 0) s_last = atomicAdd(ticket, 1) == (int)(gridDim.x * gridDim.y) - 1;
+  __syncthreads();
+  if (!s_last) return;
+  const int all = nt * (int)gridDim.y;
+  const int per = (((all + 255) / 256) + 3) & ~3;            // a thread's segment: whole int4s (tile_cnt is aligned)
+  const int lo = min(threadIdx.x * per, all), hi = min(lo + per, all);
+  int sum = 0;
+  {
+    int i = lo;
+#pragma unroll 4
+    for (; i + 4 <= hi; i += 4) {                            // the other CTAs' atomics live in L2: ld.cg
+      const int4 v = __ldcg(reinterpret_cast<const int4*>(tile_cnt + i));
+      sum += v.x + v.y + v.z + v.w;
+    }
+    for (; i < hi; ++i) sum += __ldcg(tile_cnt + i);
+  }
+  // block-wide exclusive scan of the 256 segment sums: shuffle scan per warp, then over the 8 warp totals
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  int inc = sum;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int t = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc += t;
+  }
+  if (lane == 31) s_part[warp] = inc;
+  __syncthreads();
+  int base = 0, grand = 0;
+#pragma unroll
+  for (int w = 0; w < 8; ++w) {
+    const int t = s_part[w];
+    if (w < warp) base += t;
+    grand += t;
+  }
+  if (threadIdx.x == 0) { total[0] = grand; total_out[0] = grand; }
+  int acc = base + inc - sum;
+  {
+    int i = lo;
+#pragma unroll 4
+    for (; i + 4 <= hi; i += 4) {
+      const int4 v = __ldcg(reinterpret_cast<const int4*>(tile_cnt + i));
+      int4 o;
+      o.x = acc; o.y = acc + v.x; o.z = o.y + v.y; o.w = o.z + v.z;
+      acc = o.w + v.w;
+      *reinterpret_cast<int4*>(tile_off + i) = o;
+    }
+    for (; i < hi; ++i) { tile_off[i] = acc; acc += __ldcg(tile_cnt + i); }
+  }
 }
 
 // ---- TMA / mbarrier helpers (cp.async.bulk: SASS UBLKCP) ----
@@ -816,6 +873,7 @@ struct SplatWs {
   int* tile_cnt;
   int* tile_off;
   int* tile_cur;
+  int* ticket;
   int* total;
   void* scan_ws;
   size_t scan_bytes;
@@ -830,6 +888,7 @@ static SplatWs carve_splat_ws(void* ws, int N, int S) {
   auto take = [&](size_t b) { void* p = ws ? (char*)ws + off : nullptr; off += align_up(b); return p; };
   w.tile_cnt = (int*)take(nt * 4);
   w.tile_cur = (int*)take(nt * 4);     // adjacent to tile_cnt: one memset clears both
+  w.ticket = (int*)take(4);            // ... and the finish ticket of the count kernel
   w.tile_off = (int*)take(nt * 4);
   w.total = (int*)take(4);
   w.scan_bytes = scan_ws_bytes((int)nt, 1);
@@ -870,9 +929,12 @@ int isob200_splat_bin(const float* points, const float* radii, const int64_t* fi
       // chunks sized for the AVERAGE view (max_points_per_cloud is only an upper bound, usually P itself): a
       // larger view gets proportionally larger chunks, the grid is the same for every view
       const int pbx = (int)min((long long)div_up(P / N, PRIV_CHUNK), (long long)kNumSMs * 4);
+      const bool tail = nt <= (size_t)FUSED_SCAN_MAX_TILES;
       splat_tile_count_priv_kernel<<<dim3(pbx, N), 256, (size_t)T * T * sizeof(int), st>>>(
-          points, radii, first_idx, num_points, S, T, w.tile_cnt);
+          points, radii, first_idx, num_points, S, T, w.tile_cnt, tail ? w.ticket : nullptr, w.tile_off, w.total,
+          total_out);
       ISO_CHECK_LAUNCH("splat_tile_count_priv_kernel");
+      if (tail) return ISOB200_OK;
     } else {
       int bx = grid_for(max_points_per_cloud, 256, 8);
       if (N > 1) bx = max(1, min(bx, (kNumSMs * 8 + N - 1) / N));

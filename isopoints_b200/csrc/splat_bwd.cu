@@ -449,13 +449,39 @@ median_pass_kernel(const float* __restrict__ radii, const unsigned char* __restr
   const long long first = first_idx[n], num = num_points[n];
   const unsigned prefix = state[n * 4 + 0];
   const unsigned himask = (shift >= 24) ? 0u : (0xffffffffu << (shift + 8));
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < 2 * num;
-       i += (long long)gridDim.x * blockDim.x) {
-    const long long p = first + (i >> 1);
-    if (visible && !visible[p]) continue;
-    const unsigned u = f2ord_b(radii[2 * first + i]);
-    if (((u ^ prefix) & himask) == 0) atomicAdd(&sh[(u >> shift) & 255u], 1u);
+  // a thread's consecutive samples mostly share the digit in the high passes (same exponent): count runs in a
+  // register and touch the shared bin once per run instead of once per sample.  Four points (one float2 of radii +
+  // one visibility byte each) are loaded before any is used: with one dependent load per iteration the pass ran
+  // at the memory latency (~25 us for 21 MB), not the bandwidth.
+  unsigned cur = 0, run = 0;
+  const float2* r2 = reinterpret_cast<const float2*>(radii) + first;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x; i0 < num; i0 += 4 * stride) {
+    float2 rv[4];
+    bool ok[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const long long i = i0 + u * stride;
+      ok[u] = i < num;
+      rv[u] = ok[u] ? __ldg(r2 + i) : make_float2(0.f, 0.f);
+      if (ok[u] && visible) ok[u] = visible[first + i] != 0;
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      if (!ok[u]) continue;
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        const unsigned w = f2ord_b(c ? rv[u].y : rv[u].x);
+        if (((w ^ prefix) & himask) != 0) continue;
+        const unsigned dig = (w >> shift) & 255u;
+        if (dig == cur) { ++run; continue; }
+        if (run) atomicAdd(&sh[cur], run);
+        cur = dig;
+        run = 1;
+      }
+    }
   }
+  if (run) atomicAdd(&sh[cur], run);
   __syncthreads();
   if (sh[threadIdx.x]) atomicAdd(&hist[n * 256 + threadIdx.x], sh[threadIdx.x]);
   __threadfence();
@@ -468,27 +494,50 @@ median_pass_kernel(const float* __restrict__ radii, const unsigned char* __restr
   sh[threadIdx.x] = __ldcg(h + threadIdx.x);   // the other blocks' atomics live in L2
   h[threadIdx.x] = 0;                          // ready for the next pass
   __syncthreads();
-  if (threadIdx.x != 0) return;
+  if (threadIdx.x >= 32) return;
+  // warp 0 picks the digit: lane l owns bins [8l, 8l + 8); a shuffle scan over the lane totals finds the lane that
+  // holds rank k, that lane walks its eight bins (a single thread walking all 256 was ~8 us per pass on the
+  // critical path of a 4-pass chain)
   unsigned* s = state + n * 4;
-  s[3] = 0;
+  const int lane = threadIdx.x;
+  unsigned v[8], tot = 0;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { v[j] = sh[lane * 8 + j]; tot += v[j]; }
+  unsigned inc = tot;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const unsigned t = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc += t;
+  }
+  const unsigned all = __shfl_sync(0xffffffffu, inc, 31);
+  unsigned done = s[2], k = s[1];
+  const unsigned pre = s[0];
+  __syncwarp();
   if (first_pass) {
-    unsigned long long cnt = 0;
-    for (int b = 0; b < 256; ++b) cnt += sh[b];
-    s[2] = (cnt == 0);
-    s[1] = cnt ? (unsigned)((cnt - 1) / 2) : 0u;
+    done = (all == 0);
+    k = all ? (all - 1) / 2 : 0u;
   }
-  if (!s[2]) {
-    unsigned k = s[1], acc = 0;
-    int b = 0;
-    for (; b < 256; ++b) {
-      if (acc + sh[b] > k) break;
-      acc += sh[b];
+  const unsigned exc = inc - tot;
+  const bool mine = !done && (k < all ? (k >= exc && k < inc) : lane == 31);
+  if (mine) {
+    unsigned acc = exc;
+    int j = 0;
+    for (; j < 7; ++j) {
+      if (acc + v[j] > k) break;
+      acc += v[j];
     }
-    b = min(b, 255);
-    s[0] |= ((unsigned)b) << shift;
+    s[0] = pre | (((unsigned)(lane * 8 + j)) << shift);
     s[1] = k - acc;
+    if (last_pass) rs[n] = __fmul_rn(ord2f_b(s[0]), radii_s);
   }
-  if (last_pass) rs[n] = s[2] ? 0.0f : __fmul_rn(ord2f_b(s[0]), radii_s);
+  if (lane == 0) {
+    s[3] = 0;
+    if (first_pass) {
+      s[2] = done;
+      if (done) s[1] = 0;
+    }
+    if (last_pass && done) rs[n] = 0.0f;
+  }
 }
 
 // z_grad[idx] += grad_zbuf; zero gradients skipped, stop at the first -1 (rasterize_points.cu:835-843)
@@ -693,8 +742,8 @@ int isob200_splat_search_radius(const float* radii, const unsigned char* visible
   unsigned* hist = (unsigned*)ws;
   unsigned* state = hist + (size_t)N * 256;
   ISO_CUDA(cudaMemsetAsync(ws, 0, (size_t)N * (256 + 4) * sizeof(unsigned), st));
-  int bx = grid_for(2 * max(max_points_per_cloud, 1ll), 256, 4);
-  if (N > 1) bx = max(1, min(bx, (kNumSMs * 4 + N - 1) / N));
+  int bx = grid_for(div_up(max(max_points_per_cloud, 1ll), 4), 256, 8);   // four points per thread and trip
+  if (N > 1) bx = max(1, min(bx, (kNumSMs * 8 + N - 1) / N));
   for (int pass = 0; pass < 4; ++pass) {
     const int shift = 24 - 8 * pass;
     median_pass_kernel<<<dim3(bx, N), 256, 0, st>>>(radii, visible, first_idx, num_points, shift, pass == 0,

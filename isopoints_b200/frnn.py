@@ -36,6 +36,13 @@ QUERY_MODE = 0
 # neighbour lies far inside it -- set by callers that choose r that way (UniformProjection._create_tree)
 FAR_RADIUS_HINT = False
 
+# When a list (set by a caller that defers its own read-backs, UniformProjection._filter_resample_run_ahead):
+# build_grid sizes the cell table for SPECULATIVE_CELLS cells instead of reading the grid size back, and appends
+# (device int32 with the true size, the capacity used); the caller compares them after its own synchronisation and
+# redoes the search when a grid did not fit (the kernels stay in bounds meanwhile: isob200_frnn_grid_params_capped)
+DEFERRED_GRID_CHECKS = None
+SPECULATIVE_CELLS = 2 * 129 ** 3   # twice the largest grid of a cube-shaped box (128 cells along the shortest axis)
+
 _MAX_CELLS = 1 << 28     # 1 GiB of int32 offsets per cloud; int cell ids stay far from overflow
 _PARAMS_SIZE = {2: 6, 3: 8}
 _TOTAL_IDX = {2: 5, 3: 7}
@@ -52,6 +59,13 @@ def _grid_params(points2, lengths2, r, radius_cell_ratio):
     params = torch.zeros((N, _PARAMS_SIZE[D]), dtype=torch.float32, device=points2.device)
     gmax = torch.zeros((1,), dtype=torch.int32, device=points2.device)
     ws = _ext.workspace(32 * max(N, 1) + 4, points2.device)
+    if DEFERRED_GRID_CHECKS is not None:
+        cap = max(1, min(SPECULATIVE_CELLS, _MAX_CELLS // max(N, 1)))
+        _ext.check(lib.isob200_frnn_grid_params_capped(
+            _ext.ptr(points2), _ext.ptr(lengths2), _ext.ptr(r), N, P2, D, float(radius_cell_ratio), cap,
+            _ext.ptr(params), _ext.ptr(gmax), _ext.ptr(ws), ws.numel(), _ext.stream(points2.device)))
+        DEFERRED_GRID_CHECKS.append((gmax, cap))
+        return params, cap
     _ext.check(lib.isob200_frnn_grid_params(
         _ext.ptr(points2), _ext.ptr(lengths2), _ext.ptr(r), N, P2, D, float(radius_cell_ratio),
         _ext.ptr(params), _ext.ptr(gmax), _ext.ptr(ws), ws.numel(), _ext.stream(points2.device)))

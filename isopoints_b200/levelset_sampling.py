@@ -437,8 +437,13 @@ class UniformProjection(LevelSetProjection):
                                              _ext.stream(dev)))
         tree = {k: self.__dict__.get(k) for k in ("_knn_idx", "_knn_dists", "_knn_full_idx", "_knn_src",
                                                   "_knn_nn_cache")}
-        res = self.resample(model, out_p[None], out_n[None], count.long(), sample_iters=sample_iters, _live=count,
-                            **forward_kwargs)
+        outer, checks = frnn.DEFERRED_GRID_CHECKS, []
+        frnn.DEFERRED_GRID_CHECKS = checks   # no grid-size read-back either: cell tables sized ahead, checked below
+        try:
+            res = self.resample(model, out_p[None], out_n[None], count.long(), sample_iters=sample_iters,
+                                _live=count, **forward_kwargs)
+        finally:
+            frnn.DEFERRED_GRID_CHECKS = outer
         n = int(count.item())
         if n == 0 or sample_iters == 0 or 3 * n < 2 * (self.knn_k + 1):
             self.__dict__.update(tree)   # the read-back path builds no tree in these cases
@@ -446,6 +451,12 @@ class UniformProjection(LevelSetProjection):
                 return None
             # resample's own early returns (:242-245)
             return ProjectionResult(out_p[:n][None], out_n[:n][None], mask.new_ones((1, n)))
+        if any(int(g.item()) > cap for g, cap in checks):
+            # a grid needed more cells than the table sized ahead of time (a strongly anisotropic box): its search
+            # found nothing; redo on the compacted survivors with the sizes read back
+            self.__dict__.update(tree)
+            return self.resample(model, out_p[:n][None], out_n[:n][None], count.long(), sample_iters=sample_iters,
+                                 num_points_list=[n], **forward_kwargs)
         if self._knn_idx is not None and self._knn_idx.shape[1] == M:
             self._knn_full_idx = self._knn_full_idx[:, :n]
             self._knn_idx, self._knn_dists = self._knn_idx[:, :n], self._knn_dists[:, :n]

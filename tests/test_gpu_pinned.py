@@ -209,3 +209,44 @@ def test_run_ahead_when_nothing_converges_returns_the_unfiltered_projection():
     assert set(a.keys()) == set(b.keys()) == {"levelset_points", "mask"}
     assert not bool(a["mask"].any())
     assert torch.equal(a["levelset_points"], b["levelset_points"]) and torch.equal(a["mask"], b["mask"])
+
+
+def test_run_ahead_redoes_the_search_when_the_cell_table_sized_ahead_is_too_small():
+    """The run-ahead path sizes the FRNN cell table before it knows the grid; with a budget far below what this cloud
+    needs the capped parameters hand out a grid no query reaches (nothing out of bounds), the deferred check sees it,
+    and the step is redone with the sizes read back: same result as the read-back path."""
+    from isopoints_b200 import frnn
+    model = pinned_siren(0).to(DEV)
+    x = _c2_cloud(30_000).to(DEV)
+    kw = dict(proj_max_iters=10, proj_tolerance=5e-5, knn_k=8, sample_iters=1)
+    old, frnn.SPECULATIVE_CELLS = frnn.SPECULATIVE_CELLS, 1000
+    try:
+        a = _project(UniformProjection(**kw), model, x, True)
+    finally:
+        frnn.SPECULATIVE_CELLS = old
+    b = _project(UniformProjection(**kw), model, x, False)
+    for k in b:
+        assert torch.equal(a[k], b[k]), k
+    assert frnn.DEFERRED_GRID_CHECKS is None
+
+
+def test_capped_grid_parameters_keep_an_oversized_grid_in_bounds():
+    """isob200_frnn_grid_params_capped with a budget below the grid size: g_max reports the true size, the parameters
+    describe a single cell, and build + query over a (N, cap) table find nothing (and touch nothing outside it)."""
+    from isopoints_b200 import frnn
+    g = torch.Generator().manual_seed(3)
+    pts = torch.rand(2, 5000, 3, generator=g).to(DEV)
+    lens = torch.tensor([5000, 4000], device=DEV)
+    r = torch.full((2,), 0.05, device=DEV)
+    frnn.DEFERRED_GRID_CHECKS, old_cells = [], frnn.SPECULATIVE_CELLS
+    frnn.SPECULATIVE_CELLS = 64
+    try:
+        dists, idxs, _, grid = frnn.frnn_grid_points(pts, pts, lens, lens, K=8, r=r)
+        (gmax, cap), = frnn.DEFERRED_GRID_CHECKS
+    finally:
+        frnn.DEFERRED_GRID_CHECKS, frnn.SPECULATIVE_CELLS = None, old_cells
+    torch.cuda.synchronize()
+    assert cap == 64 and int(gmax) > 64 and grid.pc2_grid_off.shape == (2, 64)
+    assert bool((grid.grid_params[:, 7] == 1).all()) and bool((idxs == -1).all())
+    ref_d, ref_i, _, ref_grid = frnn.frnn_grid_points(pts, pts, lens, lens, K=8, r=r)
+    assert int(gmax) == ref_grid.pc2_grid_off.shape[1] and bool((ref_i[0, :, 0] >= 0).all())
