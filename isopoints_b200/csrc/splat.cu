@@ -66,6 +66,18 @@ struct TileRect { int tx0, tx1, ty0, ty1; };
 
 // Tiles are indexed in OUTPUT image coordinates (col = S-1-xi, row = S-1-yi, the flip of
 // rasterize_points.cu:160-161 / :577-578) so that the raster kernel's stores are coalesced.
+__device__ __forceinline__ bool tile_rect_of(float px, float py, float pz, float rx, float ry, int S, float fS,
+                                             TileRect& t) {
+  if (!(pz >= 0.0f)) return false;                       // behind the camera (:87-88)
+  int xl, xh, yl, yh;
+  pixel_range(px, rx, S, fS, xl, xh);
+  pixel_range(py, ry, S, fS, yl, yh);
+  if (xl > xh || yl > yh) return false;
+  t.tx0 = (S - 1 - xh) / TILE; t.tx1 = (S - 1 - xl) / TILE;
+  t.ty0 = (S - 1 - yh) / TILE; t.ty1 = (S - 1 - yl) / TILE;
+  return true;
+}
+
 __device__ __forceinline__ bool point_tile_rect(const float* __restrict__ points,
                                                 const float* __restrict__ radii, long long p, int S,
                                                 float fS, TileRect& t) {
@@ -163,11 +175,24 @@ splat_tile_count_priv_kernel(const float* __restrict__ points, const float* __re
     for (int i = threadIdx.x; i < nt; i += blockDim.x) s_hist[i] = 0;
     __syncthreads();
     const float fS = (float)S;
-    for (long long i = b + threadIdx.x; i < e; i += blockDim.x) {
-      TileRect t;
-      if (!point_tile_rect(points, radii, first + i, S, fS, t)) continue;
-      for (int ty = t.ty0; ty <= t.ty1; ++ty)
-        for (int tx = t.tx0; tx <= t.tx1; ++tx) atomicAdd(&s_hist[ty * T + tx], 1);
+    // four points' coordinates and radii are loaded before any is used (few CTAs, one dependent load chain per
+    // thread otherwise: the kernel ran at the memory latency)
+    for (long long i0 = b + threadIdx.x; i0 < e; i0 += 4 * blockDim.x) {
+      float px[4], py[4], pz[4], rx[4], ry[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const long long i = i0 + (long long)u * blockDim.x;
+        const long long p = first + (i < e ? i : i0);
+        px[u] = points[3 * p]; py[u] = points[3 * p + 1]; pz[u] = i < e ? points[3 * p + 2] : -1.0f;
+        rx[u] = radii[2 * p]; ry[u] = radii[2 * p + 1];
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        TileRect t;
+        if (!tile_rect_of(px[u], py[u], pz[u], rx[u], ry[u], S, fS, t)) continue;
+        for (int ty = t.ty0; ty <= t.ty1; ++ty)
+          for (int tx = t.tx0; tx <= t.tx1; ++tx) atomicAdd(&s_hist[ty * T + tx], 1);
+      }
     }
     __syncthreads();
     int* cnt = tile_cnt + (size_t)n * nt;
