@@ -549,14 +549,14 @@ struct RasterEpi {
   unsigned char* visible;   // (P) or null; zeroed by the caller
 };
 
-template <int K, int C>
+template <int K, int C, int STG>
 __global__ void __launch_bounds__(256)
 splat_raster_v2_kernel(const float4* __restrict__ recs, const int* __restrict__ tile_off,
                        const int* __restrict__ tile_cnt, int S, int T, float depth_merging_thres,
                        int occ_inclusive, int* __restrict__ out_idx, float* __restrict__ out_z,
                        float* __restrict__ out_q, float* __restrict__ out_occ, const RasterEpi epi) {
-  __shared__ __align__(128) float4 buf[STAGES][CHUNK2 * REC_F4];
-  __shared__ __align__(8) unsigned long long bar[STAGES];
+  __shared__ __align__(128) float4 buf[STG][CHUNK2 * REC_F4];
+  __shared__ __align__(8) unsigned long long bar[STG];
   __shared__ int pcnt[256];
   __shared__ float ndcx[TILE], ndcy[TILE];
   extern __shared__ __align__(16) float list_smem[];   // [3][C][256]: z | id | q columns per pixel
@@ -580,29 +580,29 @@ splat_raster_v2_kernel(const float4* __restrict__ recs, const int* __restrict__ 
   if (tid < TILE) ndcx[tid] = pix_to_ndc(S - 1 - (tx * TILE + tid), fS);
   else if (tid < 2 * TILE) ndcy[tid - TILE] = pix_to_ndc(S - 1 - (ty * TILE + tid - TILE), fS);
   if (tid == 0) {
-    mbar_init(&bar[0], 1);
-    mbar_init(&bar[1], 1);
+#pragma unroll
+    for (int g = 0; g < STG; ++g) mbar_init(&bar[g], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
 
-  int gc = 0;   // chunks streamed so far over both passes: stage = gc & 1, parity = (gc >> 1) & 1
+  int gc = 0;   // chunks streamed so far over both passes: stage = gc % STG, parity = (gc / STG) & 1
   auto issue = [&](int c, int g) {
     const int cnt = min(CHUNK2, nrec - c * CHUNK2);
     const unsigned bytes = (unsigned)cnt * REC_F4 * 16u;
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    mbar_expect_tx(&bar[g & 1], bytes);
-    tma_bulk_g2s(&buf[g & 1][0], recs + (base + (long long)c * CHUNK2) * REC_F4, bytes, &bar[g & 1]);
+    mbar_expect_tx(&bar[g % STG], bytes);
+    tma_bulk_g2s(&buf[g % STG][0], recs + (base + (long long)c * CHUNK2) * REC_F4, bytes, &bar[g % STG]);
   };
 
   // ---- phase 1: hit generation, one thread per record ----
   if (tid == 0)
-    for (int c = 0; c < STAGES && c < nchunks; ++c) issue(c, gc + c);
+    for (int c = 0; c < STG && c < nchunks; ++c) issue(c, gc + c);
   for (int c = 0; c < nchunks; ++c, ++gc) {
-    mbar_wait(&bar[gc & 1], (unsigned)((gc >> 1) & 1));
+    mbar_wait(&bar[gc % STG], (unsigned)((gc / STG) & 1));
     const int cnt = min(CHUNK2, nrec - c * CHUNK2);
     if (tid < cnt) {
-      const float4* rb = buf[gc & 1] + tid * REC_F4;
+      const float4* rb = buf[gc % STG] + tid * REC_F4;
       const float4 a0 = rb[0], a1 = rb[1], a2 = rb[2];
       int xl, xh, yl, yh;
       pixel_range(a0.x, a1.w, S, fS, xl, xh);
@@ -627,7 +627,7 @@ splat_raster_v2_kernel(const float4* __restrict__ recs, const int* __restrict__ 
       }
     }
     __syncthreads();
-    if (tid == 0 && c + STAGES < nchunks) issue(c + STAGES, gc + STAGES);
+    if (tid == 0 && c + STG < nchunks) issue(c + STG, gc + STG);
   }
 
   // ---- phase 2: per-pixel selection ----
@@ -646,12 +646,12 @@ splat_raster_v2_kernel(const float4* __restrict__ recs, const int* __restrict__ 
     const float xf = ndcx[tid & 15], yf = ndcy[tid >> 4];
     const unsigned need = __ballot_sync(0xffffffffu, overflow);
     if (tid == 0)
-      for (int c = 0; c < STAGES && c < nchunks; ++c) issue(c, gc + c);
+      for (int c = 0; c < STG && c < nchunks; ++c) issue(c, gc + c);
     for (int c = 0; c < nchunks; ++c, ++gc) {
-      mbar_wait(&bar[gc & 1], (unsigned)((gc >> 1) & 1));
+      mbar_wait(&bar[gc % STG], (unsigned)((gc / STG) & 1));
       const int cnt = min(CHUNK2, nrec - c * CHUNK2);
       if (need) {
-        const float4* rb = buf[gc & 1];
+        const float4* rb = buf[gc % STG];
         for (int s = 0; s < cnt; ++s) {
           const float4 a0 = rb[s * REC_F4 + 0], a1 = rb[s * REC_F4 + 1], a2 = rb[s * REC_F4 + 2];
           const float dx = __fsub_rn(xf, a0.x), dy = __fsub_rn(yf, a0.y);
@@ -663,7 +663,7 @@ splat_raster_v2_kernel(const float4* __restrict__ recs, const int* __restrict__ 
         }
       }
       __syncthreads();
-      if (tid == 0 && c + STAGES < nchunks) issue(c + STAGES, gc + STAGES);
+      if (tid == 0 && c + STG < nchunks) issue(c + STG, gc + STG);
     }
     if (overflow) SL.drain(L);
   }
@@ -881,11 +881,22 @@ template <int K>
 static void launch_raster(int variant, int tiles, cudaStream_t st, const float4* recs, const int* off,
                           const int* cnt, int S, int T, float thres, int occ_incl, int* oi, float* oz,
                           float* oq, float* oo, const RasterEpi& epi) {
-  if (variant != 1) {   // v2: C slots per pixel column; K <= 8 -> 24 (72 KB), else K + 16
+  if (variant != 1) {
+    // v2.  K <= 8: 20 slots per pixel column (60 KB) + ONE 12 KB staging buffer = 73 KB per CTA, three CTAs per SM --
+    // the other CTAs of the SM cover the record copy that a second buffer would overlap (measured against 24 slots
+    // + two buffers = 97 KB, two CTAs per SM: 0.486 -> 0.468 ms for the fused forward of BASELINE config 4; that
+    // form stays selectable as variant 2).  Larger K: K + 16 slots, two buffers.
+    if (K <= 8 && variant != 2) {
+      constexpr int C = 20;
+      const int smem2 = 3 * C * 256 * (int)sizeof(float);
+      cudaFuncSetAttribute(splat_raster_v2_kernel<K, C, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem2);
+      splat_raster_v2_kernel<K, C, 1><<<tiles, 256, smem2, st>>>(recs, off, cnt, S, T, thres, occ_incl, oi, oz, oq, oo, epi);
+      return;
+    }
     constexpr int C = (K <= 8) ? 24 : K + 16;
     const int smem2 = 3 * C * 256 * (int)sizeof(float);
-    cudaFuncSetAttribute(splat_raster_v2_kernel<K, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem2);
-    splat_raster_v2_kernel<K, C><<<tiles, 256, smem2, st>>>(recs, off, cnt, S, T, thres, occ_incl, oi, oz, oq, oo, epi);
+    cudaFuncSetAttribute(splat_raster_v2_kernel<K, C, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem2);
+    splat_raster_v2_kernel<K, C, STAGES><<<tiles, 256, smem2, st>>>(recs, off, cnt, S, T, thres, occ_incl, oi, oz, oq, oo, epi);
     return;
   }
   const int smem = 3 * K * 256 * (int)sizeof(float);
@@ -984,7 +995,8 @@ int isob200_splat_bin(const float* points, const float* radii, const int64_t* fi
 // `capacity` records of isob200_splat_record_bytes() each (capacity >= the total read back).
 // Outputs are fully written: idx int32 (N,S,S,K), zbuf/qvalue f32 (N,S,S,K), occ f32 (N,S,S).
 // occ_inclusive: bit 0: 1 = naive-kernel rule q_max_z >= 0 (bin_size == 0), 0 = fine-kernel rule > 0;
-//                bits 8..9: raster variant, 0/2 = v2 (record-centric hit generation, default),
+//                bits 8..9: raster variant, 0 = v2 (record-centric hit generation, default), 2 = v2 with the
+//                round-2a shared-memory budget (24 slots, two staging buffers),
 //                1 = v1 (pixel-centric with warp-level culling).  Results are identical.
 int isob200_splat_forward_fused(const float* points, const float* ellipse, const float* cutoff,
                                 const float* radii, const int64_t* first_idx, const int64_t* num_points,

@@ -20,6 +20,7 @@ the fine kernel's z > 0, rasterize_points.cu:196 vs :581) and the reference's ``
 argument check.  The (N,B,B,M) ``bin_points`` matrix is not materialised.
 There is no CPU / PyTorch fallback: CPU tensors raise.
 """
+import os
 from typing import NamedTuple, Optional
 
 import torch
@@ -27,9 +28,9 @@ from torch import autograd
 
 from . import _ext
 
-# raster kernel variant: 0/2 = v2 (record-centric hit generation, default), 1 = v1 (pixel-centric with
+# raster kernel variant: 0 = v2 (record-centric hit generation, default), 2 = v2 with two CTAs per SM, 1 = v1 (pixel-centric with
 # warp-level culling).  Identical results; v1 is kept as the fallback algorithm inside v2 and for A/B timing.
-RASTER_VARIANT = 0
+RASTER_VARIANT = int(os.environ.get("ISOB200_RASTER_VARIANT", "0"))
 
 kMaxPointsPerBin = 22
 kMaxPointsPerPixel = 150

@@ -23,7 +23,7 @@ def _fwd(t, S, K, thres=0.05, bin_size=16):
                                  t["num_points"], thres, S, K, bin_size, 10000)
 
 
-@pytest.fixture(params=[1, 2], ids=["raster_v1", "raster_v2"])
+@pytest.fixture(params=[1, 2, 0], ids=["raster_v1", "raster_v2_two_ctas", "raster_v2_default"])
 def raster_variant(request):
     old = splat.RASTER_VARIANT
     splat.RASTER_VARIANT = request.param
