@@ -14,6 +14,12 @@ case "${1:-all}" in
     timeout 900 compute-sanitizer --tool memcheck --error-exitcode 7 python -m pytest tests/test_gpu_frnn.py tests/test_gpu_splat.py tests/test_gpu_pointops.py tests/test_gpu_siren.py -m gpu -q -x -k "small_bit_exact or clustered or fused_blend or tiled_sweep or backward_matches_oracle or all_sms or layer_counts or fused_newton or device_side" > gpurun_out/sanitizer_memcheck.log 2>&1; echo "memcheck rc=$?"; tail -4 gpurun_out/sanitizer_memcheck.log
     timeout 900 compute-sanitizer --tool racecheck --error-exitcode 7 python -m pytest tests/test_gpu_frnn.py tests/test_gpu_splat.py tests/test_gpu_siren.py -m gpu -q -x -k "clustered or fused_blend or tiled_sweep or layer_counts" > gpurun_out/sanitizer_racecheck.log 2>&1; echo "racecheck rc=$?"; tail -4 gpurun_out/sanitizer_racecheck.log
     timeout 600 compute-sanitizer --tool synccheck --error-exitcode 7 python -m pytest tests/test_gpu_siren.py tests/test_gpu_pointops.py -m gpu -q -x -k "layer_counts or all_sms" > gpurun_out/sanitizer_synccheck.log 2>&1; echo "synccheck rc=$?"; tail -4 gpurun_out/sanitizer_synccheck.log ;;
+  sanitize2)
+    # the kernels touched at the end of the round: capped grid parameters + bounding box, median passes, the tile
+    # count kernel's scan tail, the three-CTA raster budget, the run-ahead projection step
+    timeout 1200 compute-sanitizer --tool memcheck --error-exitcode 7 python -m pytest tests/test_gpu_frnn.py tests/test_gpu_splat.py tests/test_gpu_pinned.py -m gpu -q -x -k "small_bit_exact or capped_grid or cell_table or nothing_converges or 30000 or fused_blend or edge_cases or dense_overdraw or backward_matches_oracle or tiled_sweep or (c4_scale and raster_v2_default)" > gpurun_out/sanitizer2_memcheck.log 2>&1; echo "memcheck rc=$?"; tail -4 gpurun_out/sanitizer2_memcheck.log
+    timeout 900 compute-sanitizer --tool racecheck --error-exitcode 7 python -m pytest tests/test_gpu_splat.py tests/test_gpu_frnn.py -m gpu -q -x -k "fused_blend or dense_overdraw or edge_cases or capped_grid" > gpurun_out/sanitizer2_racecheck.log 2>&1; echo "racecheck rc=$?"; tail -4 gpurun_out/sanitizer2_racecheck.log
+    timeout 300 python scripts/step_gaps.py > gpurun_out/step_gaps.txt 2>&1; tail -32 gpurun_out/step_gaps.txt ;;
   quick)
     timeout 1500 python -m pytest tests -m gpu -q -x 2>&1 | tail -6
     timeout 300 python bench.py --steps 10 --warmup 3 --no-side | python -c "import json,sys; d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print('C2', round(d['ms_per_step'],3), round(d['value']/1e6,3), d['clocks']); [print('  ', k, round(v['ms_per_step'],4)) for k, v in d['kernels'].items()]; print('   glue', d['sdf_callback_and_glue_ms_per_step'])"
