@@ -104,6 +104,28 @@ class ShardedUniformProjection(UniformProjection):
         dist.all_reduce(total, op=dist.ReduceOp.SUM, group=self.group)
         return int(total.item()) == 0
 
+    def _search_own_rows(self, pts_loc, g_pts, begin, len1, len2, radius):
+        """K + 1 nearest gathered points of every own point (FRNN, the tree of levelset_sampling.py:110-140).  The
+        gathered cloud holds this rank's shard as rows [begin, begin + nloc), so the cell order of the own queries
+        falls out of the grid build: they are walked in that order (what a self-query gets from
+        ``frnn_grid_points``; in shard order neighbouring queries touch unrelated cells: 0.73 ms instead of
+        0.3 ms for 120 k of 970 k points).  Same results; no read-back."""
+        nloc, dev = pts_loc.shape[0], pts_loc.device
+        radius = radius.to(torch.float32).contiguous()
+        grid = frnn.build_grid(g_pts[None], len2, radius)
+        s = grid.sorted_points2_idxs[0]
+        own = (s >= begin) & (s < begin + nloc)
+        slot = torch.where(own, torch.cumsum(own, 0) - 1, nloc)            # the others share a spare slot
+        order = torch.empty((nloc + 1,), dtype=torch.int32, device=dev).scatter_(0, slot, s - begin)[:nloc]
+        q_pts = pts_loc[order.long()]
+        hint, frnn.FAR_RADIUS_HINT = frnn.FAR_RADIUS_HINT, True     # r = knn_k point spacings, as in _create_tree
+        try:
+            idx, _ = frnn.find_nbrs(pts_loc[None], len1, len2, grid, self.knn_k + 1, radius,
+                                    q_points=q_pts[None].contiguous(), q_order=order[None].contiguous())
+        finally:
+            frnn.FAR_RADIUS_HINT = hint
+        return idx
+
     def resample(self, model, points_init, normals_init, num_points, sample_iters=None,
                  num_points_list=None, **forward_kwargs) -> ProjectionResult:
         sample_iters = sample_iters or self.sample_iters
@@ -145,8 +167,8 @@ class ShardedUniformProjection(UniformProjection):
                 len2 = torch.tensor([ntot], dtype=torch.int64, device=dev)
                 len1 = torch.tensor([nloc], dtype=torch.int64, device=dev)
                 if nloc:      # (an empty shard has nothing to search for, but stays in the exchange above)
-                    _, idx, _, _ = frnn.frnn_grid_points(pts_loc[None], g_pts[None], len1, len2, K=self.knn_k + 1,
-                                                         r=radius, return_nn=False)
+                    idx = self._search_own_rows(pts_loc, g_pts, sum(counts[:dist.get_rank(self.group)]), len1, len2,
+                                                radius)
             moved = torch.empty_like(pts_loc)
             if nloc:
                 _ext.check(lib.isob200_resample_step(
