@@ -436,7 +436,7 @@ def run_ours(args):
             import bench_c5
             del flush
             torch.cuda.empty_cache()
-            line["c5"] = bench_c5.run(rank, world, dev, steps=2, check=True)
+            line["c5"] = bench_c5.run(rank, world, dev, steps=5, check=True)   # 2 steps were noisy (allocator growth)
         except Exception as e:      # never lose the headline line to the side record
             line["c5"] = {"error": "%s: %s" % (type(e).__name__, str(e)[:300])}
     if rank == 0:

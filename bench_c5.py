@@ -75,7 +75,7 @@ def splat_views(pts_world, views, n_views, S, K, occ_grads, z_grads, rgb):
     return rgba, p.grad
 
 
-def run(rank, world, dev, points=2_000_000, views=16, size=1024, sdf="siren", steps=2, check=False):
+def run(rank, world, dev, points=2_000_000, views=16, size=1024, sdf="siren", steps=5, check=False):
     """One record (python dict; identical on every rank).  `world` > 1 needs an initialised process group."""
     import torch.distributed as dist
     from isopoints_b200.dist import (ShardedUniformProjection, all_gather_varlen, all_reduce_point_grads,
@@ -155,7 +155,7 @@ def main():
     ap.add_argument("--points", type=int, default=2_000_000)
     ap.add_argument("--views", type=int, default=16)
     ap.add_argument("--size", type=int, default=1024)
-    ap.add_argument("--steps", type=int, default=2)
+    ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--sdf", default="siren", choices=["siren", "opaque", "sphere"])
     ap.add_argument("--check", action="store_true")
     args = ap.parse_args()
