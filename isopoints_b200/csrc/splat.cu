@@ -153,13 +153,13 @@ splat_tile_fill_kernel(const float* __restrict__ points, const float* __restrict
 // ---- privatised form of the count kernel ------------------------------------------------------------------------
 // The plain count kernel issues one global atomic per (tile, point) pair: 3.4 M atomics on 8 192 counters at BASELINE
 // config 4, ~415 per address, and the L2 atomic unit serialises per address.  Here a CTA takes a contiguous chunk of
-// >= 8 192 points of ONE view, bins it into a shared-memory histogram of that view's tiles and adds the non-zero
-// bins to the global counters: 0.075 -> 0.05 ms.  (The same idea for the fill kernel -- reserve a CTA's range of
+// >= 4 096 points of ONE view, bins it into a shared-memory histogram of that view's tiles and adds the non-zero
+// bins to the global counters: 0.075 -> 0.05 ms (chunks of 8 192 left half the SMs without a CTA: 0.059 ms for
+// the whole binning entry against 0.048; 2 048 is the same as 4 096).  (The same idea for the fill kernel -- reserve a CTA's range of
 // every tile's slice with one atomic, hand the slots out from shared memory in a second pass -- was measured and
 // dropped: two passes on 300 CTAs write the 163 MB of records slower than one pass on 1 184, 0.12 -> 0.20 ms.)
 constexpr int PRIV_MAX_TILES = 4096;      // tiles per view the shared-memory histogram holds (16 KB)
-constexpr int PRIV_CHUNK = 8192;          // points per CTA
-constexpr int FUSED_SCAN_MAX_TILES = 1 << 17;   // tiles (all views) the count kernel's last CTA scans itself
+constexpr int PRIV_CHUNK = 4096;          // points per CTA
 
 __global__ void __launch_bounds__(256)
 splat_tile_count_priv_kernel(const float* __restrict__ points, const float* __restrict__ radii,
@@ -199,60 +199,11 @@ splat_tile_count_priv_kernel(const float* __restrict__ points, const float* __re
     for (int i = threadIdx.x; i < nt; i += blockDim.x)
       if (s_hist[i]) atomicAdd(&cnt[i], s_hist[i]);
   }
-  if (!ticket) return;
-  // ---- the last CTA to finish turns the counts of all views into offsets and the record total: no scan
-  //      launches, no separate total kernel, no device-to-device copy behind this kernel ----
-  __shared__ int s_part[256];
-  __shared__ bool s_last;
-  __threadfence();
-  __syncthreads();
-  if (threadIdx.x == 0) s_last = atomicAdd(ticket, 1) == (int)(gridDim.x * gridDim.y) - 1;
-  __syncthreads();
-  if (!s_last) return;
-  const int all = nt * (int)gridDim.y;
-  const int per = (((all + 255) / 256) + 3) & ~3;            // a thread's segment: whole int4s (tile_cnt is aligned)
-  const int lo = min(threadIdx.x * per, all), hi = min(lo + per, all);
-  int sum = 0;
-  {
-    int i = lo;
-#pragma unroll 4
-    for (; i + 4 <= hi; i += 4) {                            // the other CTAs' atomics live in L2: ld.cg
-      const int4 v = __ldcg(reinterpret_cast<const int4*>(tile_cnt + i));
-      sum += v.x + v.y + v.z + v.w;
-    }
-    for (; i < hi; ++i) sum += __ldcg(tile_cnt + i);
-  }
-  // block-wide exclusive scan of the 256 segment sums: shuffle scan per warp, then over the 8 warp totals
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  int inc = sum;
-#pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    const int t = __shfl_up_sync(0xffffffffu, inc, o);
-    if (lane >= o) inc += t;
-  }
-  if (lane == 31) s_part[warp] = inc;
-  __syncthreads();
-  int base = 0, grand = 0;
-#pragma unroll
-  for (int w = 0; w < 8; ++w) {
-    const int t = s_part[w];
-    if (w < warp) base += t;
-    grand += t;
-  }
-  if (threadIdx.x == 0) { total[0] = grand; total_out[0] = grand; }
-  int acc = base + inc - sum;
-  {
-    int i = lo;
-#pragma unroll 4
-    for (; i + 4 <= hi; i += 4) {
-      const int4 v = __ldcg(reinterpret_cast<const int4*>(tile_cnt + i));
-      int4 o;
-      o.x = acc; o.y = acc + v.x; o.z = o.y + v.y; o.w = o.z + v.z;
-      acc = o.w + v.w;
-      *reinterpret_cast<int4*>(tile_off + i) = o;
-    }
-    for (; i < hi; ++i) { tile_off[i] = acc; acc += __ldcg(tile_cnt + i); }
-  }
+  // the last CTA to finish turns the counts of all views into offsets and the record total: no scan launches, no
+  // separate total kernel, no device-to-device copy behind this kernel
+  if (ticket)
+    last_cta_exclusive_scan(ticket, (int)(gridDim.x * gridDim.y), tile_cnt, tile_off, nt * (int)gridDim.y, total,
+                            total_out);
 }
 
 // ---- TMA / mbarrier helpers (cp.async.bulk: SASS UBLKCP) ----
@@ -965,7 +916,7 @@ int isob200_splat_bin(const float* points, const float* radii, const int64_t* fi
       // chunks sized for the AVERAGE view (max_points_per_cloud is only an upper bound, usually P itself): a
       // larger view gets proportionally larger chunks, the grid is the same for every view
       const int pbx = (int)min((long long)div_up(P / N, PRIV_CHUNK), (long long)kNumSMs * 4);
-      const bool tail = nt <= (size_t)FUSED_SCAN_MAX_TILES;
+      const bool tail = nt <= (size_t)LAST_CTA_SCAN_MAX;
       splat_tile_count_priv_kernel<<<dim3(pbx, N), 256, (size_t)T * T * sizeof(int), st>>>(
           points, radii, first_idx, num_points, S, T, w.tile_cnt, tail ? w.ticket : nullptr, w.tile_off, w.total,
           total_out);

@@ -148,7 +148,8 @@ splat_occ_backward_kernel(const float* __restrict__ points, const float* __restr
 constexpr int GT = 16;   // tile side of the gradient-pixel lists
 
 __global__ void __launch_bounds__(256)
-gradpix_count_kernel(const float* __restrict__ grad_occ, int H, int W, int TX, int TY, int* __restrict__ tile_cnt) {
+gradpix_count_kernel(const float* __restrict__ grad_occ, int H, int W, int TX, int TY, int* __restrict__ tile_cnt,
+                     int* __restrict__ ticket, int* __restrict__ tile_off) {
   const int t = blockIdx.x;                       // n*TY*TX + ty*TX + tx
   const int n = t / (TX * TY), tr = t - n * TX * TY;
   const int ty = tr / TX, tx = tr - ty * TX;
@@ -156,6 +157,7 @@ gradpix_count_kernel(const float* __restrict__ grad_occ, int H, int W, int TX, i
   const bool nz = col < W && row < H && grad_occ[((size_t)n * H + row) * W + col] != 0.0f;
   const int c = __syncthreads_count(nz);
   if (threadIdx.x == 0) tile_cnt[t] = c;
+  if (ticket) last_cta_exclusive_scan(ticket, (int)gridDim.x, tile_cnt, tile_off, (int)gridDim.x, nullptr, nullptr);
 }
 
 __global__ void __launch_bounds__(256)
@@ -335,6 +337,57 @@ occ_point_bin_kernel(const float* __restrict__ points, const unsigned char* __re
     if (FILL) plist[poff[t] + atomicAdd(pcnt + t, 1)] = (int)i;
     else atomicAdd(pcnt + t, 1);
   }
+}
+
+// Count form of the kernel above with the privatisation of splat_tile_count_priv_kernel (splat.cu): a CTA takes a
+// contiguous chunk of one view's points, counts into a shared-memory histogram of that view's tiles, adds the non-zero
+// bins to the global counters, and the last CTA turns the counts into offsets (no scan launches).
+constexpr int OCC_PRIV_MAX_TILES = 4096;
+constexpr int OCC_PRIV_CHUNK = 4096;
+
+__global__ void __launch_bounds__(256)
+occ_point_count_priv_kernel(const float* __restrict__ points, const unsigned char* __restrict__ visible,
+                            const int64_t* __restrict__ first_idx, const int64_t* __restrict__ num_points, int H, int W,
+                            int TX, int TY, int* __restrict__ pcnt, int* __restrict__ ticket, int* __restrict__ poff,
+                            float* __restrict__ grad_out, int out_stride) {
+  extern __shared__ int s_hist[];   // [TX*TY]
+  const int n = blockIdx.y, nt = TX * TY;
+  const long long first = first_idx[n], num = num_points[n];
+  const long long chunk = (num + gridDim.x - 1) / gridDim.x;
+  const long long b = (long long)blockIdx.x * chunk, e = min(num, b + chunk);
+  if (b < e) {
+    for (int i = threadIdx.x; i < nt; i += blockDim.x) s_hist[i] = 0;
+    __syncthreads();
+    for (long long i0 = b + threadIdx.x; i0 < e; i0 += 4 * blockDim.x) {
+      float px[4], py[4], pz[4];
+      bool vis[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {                 // four points' loads in flight
+        const long long i = i0 + (long long)u * blockDim.x;
+        const long long p = first + (i < e ? i : i0);
+        px[u] = points[3 * p]; py[u] = points[3 * p + 1]; pz[u] = points[3 * p + 2];
+        vis[u] = visible == nullptr || visible[p];
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const long long i = i0 + (long long)u * blockDim.x;
+        if (i >= e) break;
+        const long long p = first + i;
+        if (!(vis[u] && !(pz[u] < 0.f || fabsf(py[u]) > 1.0f || fabsf(px[u]) > 1.0f))) {   // occ_point_live
+          grad_out[(size_t)p * out_stride + 0] = 0.f;
+          grad_out[(size_t)p * out_stride + 1] = 0.f;
+          continue;
+        }
+        const int col = W - 1 - ndc_to_cell(px[u], W), row = H - 1 - ndc_to_cell(py[u], H);
+        atomicAdd(&s_hist[(row / GT) * TX + col / GT], 1);
+      }
+    }
+    __syncthreads();
+    int* cnt = pcnt + (size_t)n * nt;
+    for (int i = threadIdx.x; i < nt; i += blockDim.x)
+      if (s_hist[i]) atomicAdd(&cnt[i], s_hist[i]);
+  }
+  last_cta_exclusive_scan(ticket, (int)(gridDim.x * gridDim.y), pcnt, poff, nt * (int)gridDim.y, nullptr, nullptr);
 }
 
 __global__ void __launch_bounds__(256)
@@ -683,10 +736,17 @@ int isob200_splat_occ_backward(const float* points, const float* radii, const un
     void* sws = base; const size_t sws_bytes = align_up(scan_ws_bytes(nt, 1)); base += sws_bytes;
     float4* recs = (float4*)base; base += align_up((size_t)N * H * W * sizeof(float4));
     int* plist = (int*)base;
-    gradpix_count_kernel<<<nt, 256, 0, st>>>(grad_occ, H, W, TX, TY, tcnt);
+    // small tables: the counting kernels' last CTAs do the scans (two tickets at the head of the scan scratch)
+    const bool tail_scan = nt <= LAST_CTA_SCAN_MAX;
+    int* tickets = (int*)sws;
+    int rc = ISOB200_OK;
+    if (tail_scan) ISO_CUDA(cudaMemsetAsync(tickets, 0, 2 * sizeof(int), st));
+    gradpix_count_kernel<<<nt, 256, 0, st>>>(grad_occ, H, W, TX, TY, tcnt, tail_scan ? tickets : nullptr, toff);
     ISO_CHECK_LAUNCH("gradpix_count_kernel");
-    int rc = exclusive_scan_i32(tcnt, toff, nt, 1, nt, nt, sws, sws_bytes, st);
-    if (rc) return rc;
+    if (!tail_scan) {
+      rc = exclusive_scan_i32(tcnt, toff, nt, 1, nt, nt, sws, sws_bytes, st);
+      if (rc) return rc;
+    }
     gradpix_fill_kernel<<<nt, 256, 0, st>>>(grad_occ, H, W, TX, TY, toff, recs);
     ISO_CHECK_LAUNCH("gradpix_fill_kernel");
     if (mode == 0) {
@@ -694,11 +754,18 @@ int isob200_splat_occ_backward(const float* points, const float* radii, const un
       int pbx = grid_for(max(max_points_per_cloud, 1ll), 256, 8);
       if (N > 1) pbx = max(1, min(pbx, (kNumSMs * 8 + N - 1) / N));
       ISO_CUDA(cudaMemsetAsync(pcnt, 0, (size_t)nt * 4, st));
-      occ_point_bin_kernel<false><<<dim3(pbx, N), 256, 0, st>>>(points, visible, first_idx, num_points, H, W, TX, TY,
-                                                               pcnt, nullptr, nullptr, grad_out, out_stride);
-      ISO_CHECK_LAUNCH("occ_point_bin_kernel<count>");
-      rc = exclusive_scan_i32(pcnt, poff, nt, 1, nt, nt, sws, sws_bytes, st);
-      if (rc) return rc;
+      if (tail_scan && TX * TY <= OCC_PRIV_MAX_TILES && max_points_per_cloud / N >= OCC_PRIV_CHUNK) {
+        const int cbx = (int)min((long long)div_up(max_points_per_cloud / N, OCC_PRIV_CHUNK), (long long)kNumSMs * 4);
+        occ_point_count_priv_kernel<<<dim3(cbx, N), 256, (size_t)TX * TY * sizeof(int), st>>>(
+            points, visible, first_idx, num_points, H, W, TX, TY, pcnt, tickets + 1, poff, grad_out, out_stride);
+        ISO_CHECK_LAUNCH("occ_point_count_priv_kernel");
+      } else {
+        occ_point_bin_kernel<false><<<dim3(pbx, N), 256, 0, st>>>(points, visible, first_idx, num_points, H, W, TX,
+                                                                 TY, pcnt, nullptr, nullptr, grad_out, out_stride);
+        ISO_CHECK_LAUNCH("occ_point_bin_kernel<count>");
+        rc = exclusive_scan_i32(pcnt, poff, nt, 1, nt, nt, sws, sws_bytes, st);
+        if (rc) return rc;
+      }
       ISO_CUDA(cudaMemsetAsync(pcnt, 0, (size_t)nt * 4, st));
       occ_point_bin_kernel<true><<<dim3(pbx, N), 256, 0, st>>>(points, visible, first_idx, num_points, H, W, TX, TY,
                                                               pcnt, poff, plist, grad_out, out_stride);
