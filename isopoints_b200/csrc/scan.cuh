@@ -7,11 +7,14 @@ int exclusive_scan_i32(const int* in, int* out, int n, int rows, long long in_st
                        long long out_stride, void* ws, size_t ws_bytes, cudaStream_t stream);
 
 // ---- scan in the tail of the kernel that produced the counts ---------------------------------------------------
-// For count tables of up to LAST_CTA_SCAN_MAX entries the three scan launches cost more than the scan: every CTA
+// For count tables of up to LAST_CTA_SCAN_MAX entries the three scan launches cost more than the scan (one CTA walks
+// the table with 16-byte loads: ~4 us at 16 k entries; at 60 k entries -- the digit tables of the FRNN radix build --
+// it was measured slower than the three launches, 0.10 -> 0.19 ms per build, and is not used there): every CTA
 // (256 threads) of the producing kernel calls this once its own counts are in global memory; the CTA that draws the
 // last ticket turns cnt[0, n) into exclusive offsets off[0, n) and writes the grand total to total_a / total_b
-// (either may be null).  `ticket` is a zeroed int; cnt / off are 16-byte aligned; `off` may not alias `cnt`.
-constexpr int LAST_CTA_SCAN_MAX = 1 << 17;
+// (either may be null).  `ticket` is a zeroed int; cnt / off are 16-byte aligned; `off` may be `cnt` (in place:
+// a thread re-reads only its own segment before overwriting it).
+constexpr int LAST_CTA_SCAN_MAX = 1 << 14;
 
 #ifdef __CUDACC__
 __device__ __forceinline__ void last_cta_exclusive_scan(int* ticket, int n_ctas, const int* cnt, int* off, int n,
