@@ -47,21 +47,30 @@ def run(args, dev, peaks, peak_src, steps=None):
     lens = torch.tensor([P], device=dev)
     r = torch.tensor([R], device=dev)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-    for _ in range(3):
-        frnn.frnn_grid_points(p, p, lens, lens, K=K, r=r)
-    torch.cuda.synchronize()
+    def timed(n):
+        out = []
+        for k in range(n):
+            flush.fill_(k & 0xff)
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            res = frnn.frnn_grid_points(p, p, lens, lens, K=K, r=r)
+            b.record()
+            torch.cuda.synchronize()
+            out.append(a.elapsed_time(b))
+            keep.append(res)          # the previous call's outputs stay alive while the next ones are allocated,
+            del keep[:-1]             # as in a caller that rebinds `dists, idxs = ...` (two sets of blocks)
+        return out
+
+    keep = []
+    timed(5)                          # warm-up with the timed loop's allocation pattern (a first cudaMalloc costs ms)
+    each = timed(steps)
+    ms = sum(each) / steps
+    _ext.PROFILE = {}                 # per-entry CUDA events: a separate pass, so that they do not sit in `ms`
+    timed(2)
     _ext.PROFILE = {}
-    ms = 0.0
-    for k in range(steps):
-        flush.fill_(k & 0xff)
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record()
-        d, i, _, _ = frnn.frnn_grid_points(p, p, lens, lens, K=K, r=r)
-        b.record()
-        torch.cuda.synchronize()
-        ms += a.elapsed_time(b)
-    ms /= steps
+    timed(steps)
     prof, _ext.PROFILE = _ext.PROFILE, None
+    d, i = keep[-1][0], keep[-1][1]
     kern = {n.replace("isob200_", ""): sum(x.elapsed_time(y) for x, y in v) / len(v) for n, v in prof.items()}
     import time
     dh = torch.empty((1, P, K), dtype=torch.float32).pin_memory()
@@ -92,7 +101,7 @@ def run(args, dev, peaks, peak_src, steps=None):
             "value": P / (ms * 1e-3), "ms_per_step": ms, "avg_neighbours_found": float((i >= 0).float().sum(-1).mean()),
             "e2e": {"value": P / (e2e_ms * 1e-3), "unit": "queries/s", "ms_per_step": e2e_ms,
                     "h2d_bytes_per_step": host.numel() * 4, "d2h_bytes_per_step": dh.numel() * 4 + ih.numel() * 8},
-            "roofline": roof, "kernels_avg_ms": kern}
+            "roofline": roof, "kernels_avg_ms": kern, "ms_each_step": each}
 
 
 if __name__ == "__main__":
