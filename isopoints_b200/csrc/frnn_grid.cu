@@ -50,13 +50,22 @@ bbox_kernel(const float* __restrict__ points, const int64_t* __restrict__ length
   for (int d = 0; d < D; ++d) { mn[d] = FLT_MAX; mx[d] = -FLT_MAX; }
   // flat coalesced sweep over the D*len floats of this cloud; component = flat index mod D
   const long long total = (long long)len * D;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
-       i += (long long)gridDim.x * blockDim.x) {
-    float v = src[i];
-    int d = (int)(i % D);
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x; i0 < total; i0 += 4 * stride) {
+    float v[4];
 #pragma unroll
-    for (int e = 0; e < D; ++e)
-      if (e == d) { mn[e] = fminf(mn[e], v); mx[e] = fmaxf(mx[e], v); }
+    for (int u = 0; u < 4; ++u) {          // four loads in flight per thread
+      const long long i = i0 + u * stride;
+      v[u] = i < total ? src[i] : src[i0];
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const long long i = i0 + u * stride;
+      const int d = (int)((i < total ? i : i0) % D);
+#pragma unroll
+      for (int e = 0; e < D; ++e)
+        if (e == d) { mn[e] = fminf(mn[e], v[u]); mx[e] = fmaxf(mx[e], v[u]); }
+    }
   }
 #pragma unroll
   for (int d = 0; d < D; ++d) {
@@ -464,7 +473,7 @@ static int frnn_build_impl(const float* points, const int64_t* lengths, const fl
 static int launch_bbox(const float* points, const int64_t* lengths, int N, int P, int D, unsigned* bbox,
                        cudaStream_t stream) {
   int bx = grid_for((long long)P * D, 256, 4);
-  bx = min(bx, 2 * kNumSMs);
+  bx = min(bx, 4 * kNumSMs);
   if (N > 1) bx = max(1, bx / N);
   if (D == 3) bbox_kernel<3><<<dim3(bx, N), 256, 0, stream>>>(points, lengths, P, bbox);
   else bbox_kernel<2><<<dim3(bx, N), 256, 0, stream>>>(points, lengths, P, bbox);
